@@ -1,0 +1,9 @@
+"""Public names of the package (re-exported by the import shim)."""
+from .errors import (ConfigError, DimensionMismatch, IndexError_, IndexNotBuilt,  # noqa: F401
+                     InvalidVectorDimension, NotImplementedError_, QuantizationError,
+                     VectorDbError)
+from .index import NO_ID, GpuIndex  # noqa: F401
+
+__all__ = ["GpuIndex", "NO_ID", "VectorDbError", "IndexNotBuilt", "DimensionMismatch",
+           "InvalidVectorDimension", "QuantizationError", "IndexError_", "ConfigError",
+           "NotImplementedError_"]

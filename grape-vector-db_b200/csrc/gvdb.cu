@@ -1,0 +1,743 @@
+// gvdb.cu — C ABI (include/gvdb.h) over the sm_100a kernels in gvdb_kernels.cuh.
+//
+// One gvdb_index = one shard in one GPU's HBM:
+//   rows   f32  [cap][dim]                       the originals (stage-2 operand)
+//   codes  uint4[(cap/32)][nchunk][32]           1-bit codes, blocked (see gvdb_kernels.cuh)
+//   norms  f32  [cap]                            sequential-fold L2 norms
+//   live   u32  [cap/32]                         tombstone bitmap
+// Search is a fixed kernel sequence per query tile (no host round trips in between):
+//   ingest_kernel<QUERY> -> { scan_kernel -> select_kernel } per row segment
+//   -> rescore_kernel -> topk_kernel
+// Row segments grow geometrically: the first segment emits every row, select_kernel turns
+// what was emitted into the exact R-th smallest distance so far, and later segments only
+// emit rows that beat it — the expected emission per segment stays <= cap/4.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "gvdb.h"
+#include "gvdb_flat.cuh"
+#include "gvdb_kernels.cuh"
+
+namespace {
+
+using namespace gvdb;
+
+thread_local std::string g_err;
+
+struct Err {
+    gvdb_status st;
+    std::string msg;
+};
+[[noreturn]] void fail(gvdb_status st, const std::string& msg) { throw Err{st, msg}; }
+
+#define CU(x)                                                                              \
+    do {                                                                                   \
+        cudaError_t e__ = (x);                                                             \
+        if (e__ != cudaSuccess)                                                            \
+            fail(GVDB_ERR_INDEX, std::string(#x) + ": " + cudaGetErrorString(e__));        \
+    } while (0)
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+    void ensure(size_t need) {
+        if (need <= bytes) return;
+        if (p) CU(cudaFree(p));
+        p = nullptr; bytes = 0;
+        CU(cudaMalloc(&p, need));
+        bytes = need;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
+    template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct Workspace {
+    cudaStream_t stream = nullptr;   // used by the host-pointer entry points
+    cudaEvent_t idle = nullptr;      // recorded after the last kernel that touched the buffers
+    bool used = false;
+    DevBuf qpack, qnorm, cnt, flag, buf, rec_ham, rec_ids, rec_score;
+    DevBuf q_in, ids_out, sc_out, codes_tmp, misc;
+    uint32_t* h_flag = nullptr;      // pinned
+    ~Workspace() {
+        for (DevBuf* b : {&qpack, &qnorm, &cnt, &flag, &buf, &rec_ham, &rec_ids, &rec_score, &q_in,
+                          &ids_out, &sc_out, &codes_tmp, &misc}) b->release();
+        if (h_flag) cudaFreeHost(h_flag);
+        if (idle) cudaEventDestroy(idle);
+        if (stream) cudaStreamDestroy(stream);
+    }
+};
+
+const int kSupportedChunks[] = {1, 2, 3, 4, 6, 8, 12, 16, 24, 32};
+
+}  // namespace
+
+struct gvdb_index {
+    gvdb_config cfg{};
+    int dim = 0, nchunk = 0, qs = 0, nbytes = 0;
+    uint64_t n_rows = 0, n_live = 0, cap_rows = 0;
+    float* rows = nullptr;
+    uint4* codes = nullptr;
+    float* norms = nullptr;
+    uint32_t* live = nullptr;
+    int sm_count = 148;
+    std::mutex pool_mu;
+    std::vector<std::unique_ptr<Workspace>> pool;
+    uint32_t query_tile = 1024;
+    int scan_ctas_per_sm = 16;
+};
+
+namespace {
+
+struct DeviceGuard {
+    int prev = 0;
+    explicit DeviceGuard(int dev) {
+        cudaGetDevice(&prev);
+        CU(cudaSetDevice(dev));
+    }
+    ~DeviceGuard() { cudaSetDevice(prev); }
+};
+
+struct WsLease {
+    gvdb_index* h;
+    Workspace* ws;
+    cudaStream_t stream;   // the stream this lease runs on
+    WsLease(gvdb_index* h_, cudaStream_t user_stream, bool use_user) : h(h_), ws(nullptr) {
+        {
+            std::lock_guard<std::mutex> lk(h->pool_mu);
+            if (!h->pool.empty()) {
+                ws = h->pool.back().release();
+                h->pool.pop_back();
+            }
+        }
+        if (!ws) {
+            ws = new Workspace();
+            CU(cudaStreamCreateWithFlags(&ws->stream, cudaStreamNonBlocking));
+            CU(cudaEventCreateWithFlags(&ws->idle, cudaEventDisableTiming));
+            CU(cudaMallocHost(&ws->h_flag, 64));
+        }
+        stream = use_user ? user_stream : ws->stream;
+        if (ws->used) CU(cudaStreamWaitEvent(stream, ws->idle, 0));
+    }
+    ~WsLease() {
+        cudaEventRecord(ws->idle, stream);
+        ws->used = true;
+        std::lock_guard<std::mutex> lk(h->pool_mu);
+        h->pool.emplace_back(ws);
+    }
+};
+
+size_t tiles_for(uint64_t rows) { return (size_t)((rows + 31) / 32); }
+
+void grow(gvdb_index* h, uint64_t need_rows) {
+    if (need_rows <= h->cap_rows) return;
+    uint64_t new_cap = std::max<uint64_t>(need_rows, h->cap_rows + h->cap_rows / 2);
+    new_cap = std::max<uint64_t>(new_cap, 1024);
+    new_cap = (new_cap + 31) / 32 * 32;
+    float* rows = nullptr; uint4* codes = nullptr; float* norms = nullptr; uint32_t* live = nullptr;
+    size_t code_bytes = tiles_for(new_cap) * h->nchunk * 32 * sizeof(uint4);
+    CU(cudaMalloc(&rows, new_cap * (size_t)h->dim * sizeof(float)));
+    CU(cudaMalloc(&codes, code_bytes));
+    CU(cudaMalloc(&norms, new_cap * sizeof(float)));
+    CU(cudaMalloc(&live, tiles_for(new_cap) * sizeof(uint32_t)));
+    CU(cudaMemset(codes, 0, code_bytes));
+    CU(cudaMemset(norms, 0, new_cap * sizeof(float)));
+    CU(cudaMemset(live, 0, tiles_for(new_cap) * sizeof(uint32_t)));
+    if (h->n_rows) {
+        CU(cudaMemcpy(rows, h->rows, h->n_rows * (size_t)h->dim * sizeof(float), cudaMemcpyDeviceToDevice));
+        CU(cudaMemcpy(codes, h->codes, tiles_for(h->n_rows) * h->nchunk * 32 * sizeof(uint4), cudaMemcpyDeviceToDevice));
+        CU(cudaMemcpy(norms, h->norms, h->n_rows * sizeof(float), cudaMemcpyDeviceToDevice));
+        CU(cudaMemcpy(live, h->live, tiles_for(h->n_rows) * sizeof(uint32_t), cudaMemcpyDeviceToDevice));
+    }
+    CU(cudaDeviceSynchronize());
+    if (h->rows) cudaFree(h->rows);
+    if (h->codes) cudaFree(h->codes);
+    if (h->norms) cudaFree(h->norms);
+    if (h->live) cudaFree(h->live);
+    h->rows = rows; h->codes = codes; h->norms = norms; h->live = live; h->cap_rows = new_cap;
+}
+
+// ---- kernel dispatch on NCHUNK ----------------------------------------------------------
+template <int NCHUNK, int MODE>
+void launch_scan_t(cudaStream_t st, dim3 grid, size_t smem, const uint4* codes, const uint32_t* live,
+                   uint32_t tile_lo, uint32_t tile_hi, const uint32_t* qpack, int nq, int qgroup,
+                   uint32_t* cnt, uint64_t* buf, uint32_t cap, uint32_t* overflow, uint32_t* dist_out,
+                   uint64_t dist_stride, uint64_t n_rows) {
+    static bool attr_set = false;   // benign race: idempotent
+    if (!attr_set) {
+        CU(cudaFuncSetAttribute(scan_kernel<NCHUNK, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        attr_set = true;
+    }
+    scan_kernel<NCHUNK, MODE><<<grid, SCAN_THREADS, smem, st>>>(
+        codes, live, tile_lo, tile_hi, qpack, nq, qgroup, cnt, buf, cap, overflow, dist_out,
+        dist_stride, n_rows);
+    CU(cudaGetLastError());
+}
+
+template <int MODE>
+void launch_scan(int nchunk, cudaStream_t st, dim3 grid, size_t smem, const uint4* codes,
+                 const uint32_t* live, uint32_t tile_lo, uint32_t tile_hi, const uint32_t* qpack,
+                 int nq, int qgroup, uint32_t* cnt, uint64_t* buf, uint32_t cap, uint32_t* overflow,
+                 uint32_t* dist_out, uint64_t dist_stride, uint64_t n_rows) {
+#define GVDB_CASE(N)                                                                          \
+    case N:                                                                                   \
+        launch_scan_t<N, MODE>(st, grid, smem, codes, live, tile_lo, tile_hi, qpack, nq, qgroup, \
+                               cnt, buf, cap, overflow, dist_out, dist_stride, n_rows);       \
+        break;
+    switch (nchunk) {
+        GVDB_CASE(1) GVDB_CASE(2) GVDB_CASE(3) GVDB_CASE(4) GVDB_CASE(6) GVDB_CASE(8)
+        GVDB_CASE(12) GVDB_CASE(16) GVDB_CASE(24) GVDB_CASE(32)
+        default: fail(GVDB_ERR_INDEX, "unsupported code width");
+    }
+#undef GVDB_CASE
+}
+
+constexpr int kQGroup = 128;   // queries staged per CTA
+
+dim3 scan_grid(const gvdb_index* h, uint32_t ntiles, uint32_t nq) {
+    const uint32_t warps = SCAN_THREADS / 32;
+    uint32_t y = (nq + kQGroup - 1) / kQGroup;
+    uint32_t x_full = (ntiles + warps - 1) / warps;
+    uint32_t x = x_full;
+    if (y > 2) x = std::min<uint32_t>(x_full, std::max<uint32_t>(1, (uint32_t)(h->sm_count * h->scan_ctas_per_sm) / y));
+    x = std::max<uint32_t>(x, 1);
+    return dim3(x, y, 1);
+}
+
+uint32_t pick_cap(uint32_t R) { return R <= 1024 ? 8192u : 16384u; }
+constexpr uint32_t kMaxR = SORT_N / 2;
+
+// Stage 1 + stage 2 for queries [0,nq) (device pointers): fills rec_* [nq][R].
+void search_core(gvdb_index* h, Workspace* ws, cudaStream_t st, const float* queries_dev,
+                 uint32_t nq, uint32_t R, uint32_t* rec_ham, uint64_t* rec_ids, float* rec_score) {
+    if (h->n_rows == 0) fail(GVDB_ERR_INDEX_NOT_BUILT, "index not built: search before any add");
+    if (R == 0) fail(GVDB_ERR_INVALID_ARGUMENT, "rescore_count must be >= 1");
+    if (R > kMaxR)
+        fail(GVDB_ERR_NOT_IMPLEMENTED, "rescore_count > 2048 is not implemented on the GPU path yet");
+    const uint32_t cap = pick_cap(R);
+    const uint32_t ntiles = (uint32_t)tiles_for(h->n_rows);
+    const uint32_t QT = h->query_tile;
+    const uint32_t qt_max = std::min(QT, nq);
+    ws->qpack.ensure((size_t)qt_max * h->qs * 4);
+    ws->qnorm.ensure((size_t)qt_max * 4);
+    ws->cnt.ensure((size_t)qt_max * 4);
+    ws->flag.ensure(256);
+    ws->buf.ensure((size_t)qt_max * cap * 8);
+    CU(cudaMemsetAsync(ws->flag.p, 0, 256, st));
+    // geometric segments; growth keeps expected emission R*(g-1) <= cap/4
+    const uint32_t seg0_tiles = 4096 / 32;
+    const uint32_t g = std::max<uint32_t>(2, cap / (4 * R));
+    for (uint32_t qt0 = 0; qt0 < nq; qt0 += QT) {
+        const uint32_t nqt = std::min(QT, nq - qt0);
+        ingest_kernel<true><<<(nqt + STAGE_ROWS - 1) / STAGE_ROWS, STAGE_ROWS, 0, st>>>(
+            queries_dev + (size_t)qt0 * h->dim, nqt, h->dim, h->cfg.threshold, h->nchunk, 0, nullptr,
+            ws->qnorm.as<float>(), nullptr, ws->qpack.as<uint32_t>(), h->qs);
+        CU(cudaGetLastError());
+        CU(cudaMemsetAsync(ws->cnt.p, 0, (size_t)nqt * 4, st));
+        uint32_t lo = 0;
+        while (lo < ntiles) {
+            uint64_t hi64 = lo == 0 ? seg0_tiles : (uint64_t)lo * g;
+            uint32_t hi = (uint32_t)std::min<uint64_t>(hi64, ntiles);
+            dim3 grid = scan_grid(h, hi - lo, nqt);
+            launch_scan<0>(h->nchunk, st, grid, (size_t)kQGroup * h->qs * 4, h->codes, h->live, lo, hi,
+                           ws->qpack.as<uint32_t>(), (int)nqt, kQGroup, ws->cnt.as<uint32_t>(),
+                           ws->buf.as<uint64_t>(), cap, ws->flag.as<uint32_t>(), nullptr, 0, h->n_rows);
+            select_kernel<<<nqt, SORT_THREADS, SORT_N * 8, st>>>(
+                ws->buf.as<uint64_t>(), cap, ws->cnt.as<uint32_t>(), R, ws->qpack.as<uint32_t>(),
+                h->qs, h->nchunk * 4);
+            CU(cudaGetLastError());
+            lo = hi;
+        }
+        const uint64_t pairs = (uint64_t)nqt * R;
+        rescore_kernel<<<(unsigned)((pairs + STAGE_ROWS - 1) / STAGE_ROWS), STAGE_ROWS, 0, st>>>(
+            h->rows, h->norms, h->cfg.row_base, h->dim, queries_dev + (size_t)qt0 * h->dim,
+            ws->qnorm.as<float>(), ws->buf.as<uint64_t>(), cap, ws->cnt.as<uint32_t>(), R, nqt,
+            rec_ham + (size_t)qt0 * R, rec_ids + (size_t)qt0 * R, rec_score + (size_t)qt0 * R);
+        CU(cudaGetLastError());
+    }
+}
+
+void check_overflow(Workspace* ws, cudaStream_t st) {
+    CU(cudaMemcpyAsync(ws->h_flag, ws->flag.p, 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    if (ws->h_flag[0])
+        fail(GVDB_ERR_INDEX,
+             "candidate buffer overflow in the Hamming scan (heavily duplicated corpus?); "
+             "the exact fallback is not implemented yet");
+}
+
+void launch_topk(cudaStream_t st, const uint64_t* rec_ids, const float* rec_score, uint32_t nq,
+                 uint32_t R, uint32_t k, uint64_t* ids_out, float* scores_out) {
+    uint32_t n_eff = 64;
+    while (n_eff < R) n_eff <<= 1;
+    uint32_t threads = std::min<uint32_t>(1024, std::max<uint32_t>(32, n_eff / 2));
+    topk_kernel<<<nq, threads, n_eff * 8, st>>>(rec_ids, rec_score, R, n_eff, k, ids_out, scores_out);
+    CU(cudaGetLastError());
+}
+
+void search_device(gvdb_index* h, Workspace* ws, cudaStream_t st, const float* q_dev, uint32_t nq,
+                   uint32_t k, uint32_t R, uint64_t* ids_out, float* scores_out, uint64_t* cand_ids,
+                   uint32_t* cand_ham) {
+    if (k > R) fail(GVDB_ERR_INVALID_ARGUMENT, "k must be <= rescore_count");
+    ws->rec_ham.ensure((size_t)nq * R * 4);
+    ws->rec_ids.ensure((size_t)nq * R * 8);
+    ws->rec_score.ensure((size_t)nq * R * 4);
+    search_core(h, ws, st, q_dev, nq, R, ws->rec_ham.as<uint32_t>(), ws->rec_ids.as<uint64_t>(),
+                ws->rec_score.as<float>());
+    launch_topk(st, ws->rec_ids.as<uint64_t>(), ws->rec_score.as<float>(), nq, R, k, ids_out, scores_out);
+    if (cand_ids) CU(cudaMemcpyAsync(cand_ids, ws->rec_ids.p, (size_t)nq * R * 8, cudaMemcpyDeviceToDevice, st));
+    if (cand_ham) CU(cudaMemcpyAsync(cand_ham, ws->rec_ham.p, (size_t)nq * R * 4, cudaMemcpyDeviceToDevice, st));
+    check_overflow(ws, st);
+}
+
+// Exact flat search: same segment/select machinery with key = image(1 - cos) << 32 | row.
+void flat_device(gvdb_index* h, Workspace* ws, cudaStream_t st, const float* q_dev, uint32_t nq,
+                 uint32_t k, uint64_t* ids_out, float* dist_out) {
+    if (h->n_rows == 0) fail(GVDB_ERR_INDEX_NOT_BUILT, "index not built: search before any add");
+    if (k == 0) fail(GVDB_ERR_INVALID_ARGUMENT, "k must be >= 1");
+    if (k > kMaxR) fail(GVDB_ERR_NOT_IMPLEMENTED, "flat search with k > 2048 is not implemented yet");
+    const uint32_t cap = pick_cap(k);
+    const uint32_t QT = h->query_tile;
+    const uint32_t qt_max = std::min(QT, nq);
+    ws->qpack.ensure((size_t)qt_max * h->qs * 4);
+    ws->qnorm.ensure((size_t)qt_max * 4);
+    ws->cnt.ensure((size_t)qt_max * 4);
+    ws->flag.ensure(256);
+    ws->buf.ensure((size_t)qt_max * cap * 8);
+    ws->misc.ensure((size_t)qt_max * 4);   // per-query key thresholds
+    CU(cudaMemsetAsync(ws->flag.p, 0, 256, st));
+    const uint64_t seg0 = 4096;
+    const uint64_t g = std::max<uint32_t>(2, cap / (4 * k));
+    for (uint32_t qt0 = 0; qt0 < nq; qt0 += QT) {
+        const uint32_t nqt = std::min(QT, nq - qt0);
+        const float* qd = q_dev + (size_t)qt0 * h->dim;
+        ingest_kernel<true><<<(nqt + STAGE_ROWS - 1) / STAGE_ROWS, STAGE_ROWS, 0, st>>>(
+            qd, nqt, h->dim, h->cfg.threshold, h->nchunk, 0, nullptr, ws->qnorm.as<float>(), nullptr,
+            ws->qpack.as<uint32_t>(), h->qs);
+        CU(cudaGetLastError());
+        CU(cudaMemsetAsync(ws->cnt.p, 0, (size_t)nqt * 4, st));
+        CU(cudaMemsetAsync(ws->misc.p, 0xff, (size_t)nqt * 4, st));   // TAU_ALL
+        uint64_t lo = 0;
+        while (lo < h->n_rows) {
+            uint64_t hi = std::min<uint64_t>(lo == 0 ? seg0 : lo * g, h->n_rows);
+            dim3 grid((unsigned)((hi - lo + FLAT_TM - 1) / FLAT_TM), (nqt + FLAT_TN - 1) / FLAT_TN, 1);
+            flat_scan_kernel<<<grid, FLAT_THREADS, 0, st>>>(
+                h->rows, h->norms, h->live, lo, hi, h->dim, qd, ws->qnorm.as<float>(), nqt,
+                ws->misc.as<uint32_t>(), ws->cnt.as<uint32_t>(), ws->buf.as<uint64_t>(), cap,
+                ws->flag.as<uint32_t>());
+            CU(cudaGetLastError());
+            select_kernel<<<nqt, SORT_THREADS, SORT_N * 8, st>>>(
+                ws->buf.as<uint64_t>(), cap, ws->cnt.as<uint32_t>(), k, ws->misc.as<uint32_t>(), 1, 0);
+            CU(cudaGetLastError());
+            lo = hi;
+        }
+        flat_emit_kernel<<<(nqt * k + 255) / 256, 256, 0, st>>>(
+            ws->buf.as<uint64_t>(), cap, ws->cnt.as<uint32_t>(), nqt, k, h->cfg.row_base,
+            ids_out + (size_t)qt0 * k, dist_out + (size_t)qt0 * k);
+        CU(cudaGetLastError());
+    }
+    check_overflow(ws, st);
+}
+
+void add_device_impl(gvdb_index* h, cudaStream_t st, const float* rows_dev, uint64_t n,
+                     bool copy_rows, uint64_t* first_out) {
+    if (first_out) *first_out = h->n_rows;
+    if (n == 0) return;
+    if (h->n_rows + n > 0xfffffff0ull) fail(GVDB_ERR_INDEX, "a shard holds at most 2^32-16 rows");
+    grow(h, h->n_rows + n);
+    float* dst = h->rows + h->n_rows * (size_t)h->dim;
+    if (copy_rows)
+        CU(cudaMemcpyAsync(dst, rows_dev, n * (size_t)h->dim * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    ingest_kernel<false><<<(unsigned)((n + STAGE_ROWS - 1) / STAGE_ROWS), STAGE_ROWS, 0, st>>>(
+        dst, n, h->dim, h->cfg.threshold, h->nchunk, h->n_rows, h->codes, h->norms, h->live, nullptr, 0);
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(st));
+    h->n_rows += n;
+    h->n_live += n;
+}
+
+template <class F>
+gvdb_status guarded(F&& f) {
+    try {
+        f();
+        return GVDB_OK;
+    } catch (const Err& e) {
+        g_err = e.msg;
+        return e.st;
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return GVDB_ERR_INDEX;
+    } catch (...) {
+        g_err = "unknown error";
+        return GVDB_ERR_INDEX;
+    }
+}
+
+void need(const void* p, const char* what) {
+    if (!p) fail(GVDB_ERR_INVALID_ARGUMENT, std::string(what) + " is NULL");
+}
+
+}  // namespace
+
+// =========================================================================================
+extern "C" {
+
+uint32_t gvdb_abi_version(void) { return GVDB_ABI_VERSION; }
+const char* gvdb_last_error(void) { return g_err.c_str(); }
+
+gvdb_status gvdb_create(const gvdb_config* cfg, gvdb_index** out) {
+    return guarded([&] {
+        need(cfg, "cfg"); need(out, "out");
+        *out = nullptr;
+        if (cfg->struct_size != sizeof(gvdb_config))
+            fail(GVDB_ERR_INVALID_ARGUMENT, "gvdb_config.struct_size mismatch");
+        if (cfg->dim == 0) fail(GVDB_ERR_INVALID_VECTOR_DIMENSION, "dimension must be > 0");
+        if (cfg->dim > 4096) fail(GVDB_ERR_INVALID_ARGUMENT, "dimension > 4096 is not supported");
+        int ndev = 0;
+        cudaError_t e = cudaGetDeviceCount(&ndev);
+        if (e != cudaSuccess || ndev == 0)
+            fail(GVDB_ERR_INDEX, std::string("no usable CUDA device (there is no CPU fallback): ") +
+                                     cudaGetErrorString(e));
+        if (cfg->device < 0 || cfg->device >= ndev) fail(GVDB_ERR_INVALID_ARGUMENT, "bad device ordinal");
+        DeviceGuard dg(cfg->device);
+        cudaDeviceProp prop;
+        CU(cudaGetDeviceProperties(&prop, cfg->device));
+        if (prop.major < 10)
+            fail(GVDB_ERR_INDEX, "this library is built for sm_100a (B200) only");
+        std::unique_ptr<gvdb_index> h(new gvdb_index());
+        h->cfg = *cfg;
+        h->dim = (int)cfg->dim;
+        h->nbytes = (h->dim + 7) / 8;
+        int want = (h->dim + 127) / 128;
+        for (int c : kSupportedChunks) if (c >= want) { h->nchunk = c; break; }
+        h->qs = h->nchunk * 4 + 4;
+        h->sm_count = prop.multiProcessorCount;
+        if (const char* s = getenv("GVDB_QUERY_TILE")) h->query_tile = std::max(1, atoi(s));
+        if (const char* s = getenv("GVDB_SCAN_CTAS_PER_SM")) h->scan_ctas_per_sm = std::max(1, atoi(s));
+        if (cfg->capacity_rows) grow(h.get(), cfg->capacity_rows);
+        *out = h.release();
+    });
+}
+
+void gvdb_destroy(gvdb_index* h) {
+    if (!h) return;
+    int prev = 0;
+    cudaGetDevice(&prev);
+    cudaSetDevice(h->cfg.device);
+    cudaDeviceSynchronize();
+    h->pool.clear();
+    if (h->rows) cudaFree(h->rows);
+    if (h->codes) cudaFree(h->codes);
+    if (h->norms) cudaFree(h->norms);
+    if (h->live) cudaFree(h->live);
+    delete h;
+    cudaSetDevice(prev);
+}
+
+gvdb_status gvdb_reserve(gvdb_index* h, uint64_t capacity_rows) {
+    return guarded([&] {
+        need(h, "index");
+        DeviceGuard dg(h->cfg.device);
+        grow(h, capacity_rows);
+    });
+}
+
+gvdb_status gvdb_add(gvdb_index* h, const float* rows, uint64_t n, uint64_t* first_row_out) {
+    return guarded([&] {
+        need(h, "index");
+        if (n) need(rows, "rows");
+        DeviceGuard dg(h->cfg.device);
+        if (first_row_out) *first_row_out = h->n_rows;
+        if (n == 0) return;
+        grow(h, h->n_rows + n);
+        WsLease lease(h, nullptr, false);
+        // rows go straight into their final place in HBM; ingest reads them from there
+        CU(cudaMemcpyAsync(h->rows + h->n_rows * (size_t)h->dim, rows, n * (size_t)h->dim * sizeof(float),
+                           cudaMemcpyHostToDevice, lease.stream));
+        add_device_impl(h, lease.stream, nullptr, n, false, nullptr);
+    });
+}
+
+gvdb_status gvdb_add_device(gvdb_index* h, void* stream, const float* rows_dev, uint64_t n,
+                            uint64_t* first_row_out) {
+    return guarded([&] {
+        need(h, "index");
+        if (n) need(rows_dev, "rows_dev");
+        DeviceGuard dg(h->cfg.device);
+        add_device_impl(h, (cudaStream_t)stream, rows_dev, n, true, first_row_out);
+    });
+}
+
+gvdb_status gvdb_remove(gvdb_index* h, uint64_t local_row, int32_t* was_live_out) {
+    return guarded([&] {
+        need(h, "index");
+        DeviceGuard dg(h->cfg.device);
+        int32_t was = 0;
+        if (local_row < h->n_rows) {
+            uint32_t word = 0;
+            CU(cudaMemcpy(&word, h->live + (local_row >> 5), 4, cudaMemcpyDeviceToHost));
+            if (word & (1u << (local_row & 31))) {
+                was = 1;
+                word &= ~(1u << (local_row & 31));
+                CU(cudaMemcpy(h->live + (local_row >> 5), &word, 4, cudaMemcpyHostToDevice));
+                h->n_live -= 1;
+            }
+        }
+        if (was_live_out) *was_live_out = was;
+    });
+}
+
+gvdb_status gvdb_clear(gvdb_index* h) {
+    return guarded([&] {
+        need(h, "index");
+        DeviceGuard dg(h->cfg.device);
+        CU(cudaDeviceSynchronize());
+        if (h->cap_rows) {
+            CU(cudaMemset(h->codes, 0, tiles_for(h->cap_rows) * h->nchunk * 32 * sizeof(uint4)));
+            CU(cudaMemset(h->live, 0, tiles_for(h->cap_rows) * sizeof(uint32_t)));
+        }
+        h->n_rows = 0;
+        h->n_live = 0;
+    });
+}
+
+uint64_t gvdb_len(const gvdb_index* h) { return h ? h->n_live : 0; }
+
+gvdb_status gvdb_get_stats(const gvdb_index* h, gvdb_stats* out) {
+    return guarded([&] {
+        need(h, "index"); need(out, "out");
+        out->vector_count = h->n_live;
+        out->rows = h->n_rows;
+        out->dimension = (uint64_t)h->dim;
+        out->memory_usage = h->n_rows * (uint64_t)h->dim * 4;
+        out->code_bytes_per_row = (uint64_t)h->nchunk * 16;
+        out->hbm_bytes = h->cap_rows * ((uint64_t)h->dim * 4 + 4) +
+                         tiles_for(h->cap_rows) * ((uint64_t)h->nchunk * 512 + 4);
+    });
+}
+
+uint64_t gvdb_rescore_count(uint64_t n, float ratio) {
+    // (candidates.len() as f32 * rescore_ratio) as usize, then .min(len)  — quantization.rs:178-179
+    float p = (float)n * ratio;
+    uint64_t r;
+    if (!(p > 0.0f)) r = 0;
+    else if (p >= 18446744073709551616.0f) r = UINT64_MAX;
+    else r = (uint64_t)p;
+    return r < n ? r : n;
+}
+
+gvdb_status gvdb_quantize(gvdb_index* h, const float* x, uint64_t n, uint8_t* codes_out) {
+    return guarded([&] {
+        need(h, "index");
+        if (n == 0) return;
+        need(x, "x"); need(codes_out, "codes_out");
+        DeviceGuard dg(h->cfg.device);
+        WsLease lease(h, nullptr, false);
+        Workspace* ws = lease.ws;
+        cudaStream_t st = lease.stream;
+        const uint64_t chunk = 65536;
+        ws->q_in.ensure(chunk * (size_t)h->dim * 4);
+        ws->codes_tmp.ensure(tiles_for(chunk) * h->nchunk * 512 + chunk * 4 + tiles_for(chunk) * 4 +
+                             chunk * (size_t)h->nbytes);
+        uint8_t* base = ws->codes_tmp.as<uint8_t>();
+        uint4* codes = reinterpret_cast<uint4*>(base);
+        float* norms = reinterpret_cast<float*>(base + tiles_for(chunk) * h->nchunk * 512);
+        uint32_t* live = reinterpret_cast<uint32_t*>(norms + chunk);
+        uint8_t* flat = reinterpret_cast<uint8_t*>(live + tiles_for(chunk));
+        for (uint64_t i0 = 0; i0 < n; i0 += chunk) {
+            uint64_t m = std::min(chunk, n - i0);
+            CU(cudaMemcpyAsync(ws->q_in.p, x + i0 * h->dim, m * (size_t)h->dim * 4, cudaMemcpyHostToDevice, st));
+            CU(cudaMemsetAsync(live, 0, tiles_for(chunk) * 4, st));
+            ingest_kernel<false><<<(unsigned)((m + STAGE_ROWS - 1) / STAGE_ROWS), STAGE_ROWS, 0, st>>>(
+                ws->q_in.as<float>(), m, h->dim, h->cfg.threshold, h->nchunk, 0, codes, norms, live, nullptr, 0);
+            unblock_codes_kernel<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(codes, h->nchunk, 0, m, h->nbytes, flat);
+            CU(cudaGetLastError());
+            CU(cudaMemcpyAsync(codes_out + i0 * h->nbytes, flat, m * (size_t)h->nbytes, cudaMemcpyDeviceToHost, st));
+            CU(cudaStreamSynchronize(st));
+        }
+    });
+}
+
+gvdb_status gvdb_get_codes(gvdb_index* h, uint64_t first, uint64_t n, uint8_t* codes_out) {
+    return guarded([&] {
+        need(h, "index");
+        if (n == 0) return;
+        need(codes_out, "codes_out");
+        if (first + n > h->n_rows) fail(GVDB_ERR_INVALID_ARGUMENT, "row range out of bounds");
+        DeviceGuard dg(h->cfg.device);
+        WsLease lease(h, nullptr, false);
+        Workspace* ws = lease.ws;
+        cudaStream_t st = lease.stream;
+        const uint64_t chunk = 1 << 20;
+        ws->codes_tmp.ensure(std::min(chunk, n) * (size_t)h->nbytes);
+        for (uint64_t i0 = 0; i0 < n; i0 += chunk) {
+            uint64_t m = std::min(chunk, n - i0);
+            unblock_codes_kernel<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(
+                h->codes, h->nchunk, first + i0, m, h->nbytes, ws->codes_tmp.as<uint8_t>());
+            CU(cudaGetLastError());
+            CU(cudaMemcpyAsync(codes_out + i0 * h->nbytes, ws->codes_tmp.p, m * (size_t)h->nbytes, cudaMemcpyDeviceToHost, st));
+            CU(cudaStreamSynchronize(st));
+        }
+    });
+}
+
+gvdb_status gvdb_hamming(gvdb_index* h, const uint8_t* q_codes, uint32_t nq, uint32_t* dist_out) {
+    return guarded([&] {
+        need(h, "index");
+        if (nq == 0 || h->n_rows == 0) return;
+        need(q_codes, "q_codes"); need(dist_out, "dist_out");
+        DeviceGuard dg(h->cfg.device);
+        WsLease lease(h, nullptr, false);
+        Workspace* ws = lease.ws;
+        cudaStream_t st = lease.stream;
+        const uint64_t N = h->n_rows;
+        uint32_t qchunk = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(nq, (256ull << 20) / (N * 4)));
+        qchunk = std::min<uint32_t>(qchunk, 1024);
+        ws->q_in.ensure((size_t)qchunk * h->nbytes);
+        ws->qpack.ensure((size_t)qchunk * h->qs * 4);
+        ws->misc.ensure((size_t)qchunk * N * 4);
+        const uint32_t ntiles = (uint32_t)tiles_for(N);
+        for (uint32_t q0 = 0; q0 < nq; q0 += qchunk) {
+            uint32_t m = std::min(qchunk, nq - q0);
+            CU(cudaMemcpyAsync(ws->q_in.p, q_codes + (size_t)q0 * h->nbytes, (size_t)m * h->nbytes, cudaMemcpyHostToDevice, st));
+            pack_query_codes_kernel<<<m, 64, 0, st>>>(ws->q_in.as<uint8_t>(), m, h->nbytes, h->nchunk, ws->qpack.as<uint32_t>(), h->qs);
+            CU(cudaGetLastError());
+            dim3 grid = scan_grid(h, ntiles, m);
+            launch_scan<1>(h->nchunk, st, grid, (size_t)kQGroup * h->qs * 4, h->codes, h->live, 0, ntiles,
+                           ws->qpack.as<uint32_t>(), (int)m, kQGroup, nullptr, nullptr, 0, nullptr,
+                           ws->misc.as<uint32_t>(), N, N);
+            CU(cudaMemcpyAsync(dist_out + (size_t)q0 * N, ws->misc.p, (size_t)m * N * 4, cudaMemcpyDeviceToHost, st));
+            CU(cudaStreamSynchronize(st));
+        }
+    });
+}
+
+gvdb_status gvdb_search_batch_device(gvdb_index* h, void* stream, const float* queries_dev, uint32_t nq,
+                                     uint32_t k, uint32_t rescore_count, uint64_t* ids_out_dev,
+                                     float* scores_out_dev, uint64_t* cand_ids_out_dev,
+                                     uint32_t* cand_ham_out_dev) {
+    return guarded([&] {
+        need(h, "index");
+        if (nq == 0) return;
+        need(queries_dev, "queries"); need(ids_out_dev, "ids_out"); need(scores_out_dev, "scores_out");
+        DeviceGuard dg(h->cfg.device);
+        WsLease lease(h, (cudaStream_t)stream, true);
+        search_device(h, lease.ws, lease.stream, queries_dev, nq, k, rescore_count, ids_out_dev,
+                      scores_out_dev, cand_ids_out_dev, cand_ham_out_dev);
+    });
+}
+
+gvdb_status gvdb_search_batch(gvdb_index* h, const float* queries, uint32_t nq, uint32_t k,
+                              uint32_t rescore_count, uint64_t* ids_out, float* scores_out,
+                              uint64_t* cand_ids_out, uint32_t* cand_ham_out) {
+    return guarded([&] {
+        need(h, "index");
+        if (nq == 0) return;
+        need(queries, "queries"); need(ids_out, "ids_out"); need(scores_out, "scores_out");
+        DeviceGuard dg(h->cfg.device);
+        WsLease lease(h, nullptr, false);
+        Workspace* ws = lease.ws;
+        cudaStream_t st = lease.stream;
+        const uint32_t R = rescore_count;
+        ws->q_in.ensure((size_t)nq * h->dim * 4);
+        ws->ids_out.ensure((size_t)nq * std::max(k, 1u) * 8);
+        ws->sc_out.ensure((size_t)nq * std::max(k, 1u) * 4);
+        CU(cudaMemcpyAsync(ws->q_in.p, queries, (size_t)nq * h->dim * 4, cudaMemcpyHostToDevice, st));
+        search_device(h, ws, st, ws->q_in.as<float>(), nq, k, R, ws->ids_out.as<uint64_t>(),
+                      ws->sc_out.as<float>(), nullptr, nullptr);
+        CU(cudaMemcpyAsync(ids_out, ws->ids_out.p, (size_t)nq * k * 8, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(scores_out, ws->sc_out.p, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, st));
+        if (cand_ids_out) CU(cudaMemcpyAsync(cand_ids_out, ws->rec_ids.p, (size_t)nq * R * 8, cudaMemcpyDeviceToHost, st));
+        if (cand_ham_out) CU(cudaMemcpyAsync(cand_ham_out, ws->rec_ham.p, (size_t)nq * R * 4, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+    });
+}
+
+gvdb_status gvdb_flat_search_batch_device(gvdb_index* h, void* stream, const float* queries_dev,
+                                          uint32_t nq, uint32_t k, uint64_t* ids_out_dev,
+                                          float* dist_out_dev) {
+    return guarded([&] {
+        need(h, "index");
+        if (nq == 0) return;
+        need(queries_dev, "queries"); need(ids_out_dev, "ids_out"); need(dist_out_dev, "dist_out");
+        DeviceGuard dg(h->cfg.device);
+        WsLease lease(h, (cudaStream_t)stream, true);
+        flat_device(h, lease.ws, lease.stream, queries_dev, nq, k, ids_out_dev, dist_out_dev);
+    });
+}
+
+gvdb_status gvdb_flat_search_batch(gvdb_index* h, const float* queries, uint32_t nq, uint32_t k,
+                                   uint64_t* ids_out, float* dist_out) {
+    return guarded([&] {
+        need(h, "index");
+        if (nq == 0) return;
+        need(queries, "queries"); need(ids_out, "ids_out"); need(dist_out, "dist_out");
+        DeviceGuard dg(h->cfg.device);
+        WsLease lease(h, nullptr, false);
+        Workspace* ws = lease.ws;
+        cudaStream_t st = lease.stream;
+        ws->q_in.ensure((size_t)nq * h->dim * 4);
+        ws->ids_out.ensure((size_t)nq * std::max(k, 1u) * 8);
+        ws->sc_out.ensure((size_t)nq * std::max(k, 1u) * 4);
+        CU(cudaMemcpyAsync(ws->q_in.p, queries, (size_t)nq * h->dim * 4, cudaMemcpyHostToDevice, st));
+        flat_device(h, ws, st, ws->q_in.as<float>(), nq, k, ws->ids_out.as<uint64_t>(), ws->sc_out.as<float>());
+        CU(cudaMemcpyAsync(ids_out, ws->ids_out.p, (size_t)nq * k * 8, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(dist_out, ws->sc_out.p, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+    });
+}
+
+gvdb_status gvdb_search_shard_device(gvdb_index* h, void* stream, const float* queries_dev, uint32_t nq,
+                                     uint32_t rescore_count, uint32_t* rec_ham_dev,
+                                     uint64_t* rec_ids_dev, float* rec_score_dev) {
+    return guarded([&] {
+        need(h, "index");
+        if (nq == 0) return;
+        need(queries_dev, "queries"); need(rec_ham_dev, "rec_ham"); need(rec_ids_dev, "rec_ids");
+        need(rec_score_dev, "rec_score");
+        DeviceGuard dg(h->cfg.device);
+        WsLease lease(h, (cudaStream_t)stream, true);
+        search_core(h, lease.ws, lease.stream, queries_dev, nq, rescore_count, rec_ham_dev, rec_ids_dev,
+                    rec_score_dev);
+        check_overflow(lease.ws, lease.stream);
+    });
+}
+
+gvdb_status gvdb_merge_shards_device(gvdb_index* h, void* stream, uint32_t n_shards,
+                                     const uint32_t* rec_ham_dev, const uint64_t* rec_ids_dev,
+                                     const float* rec_score_dev, uint32_t nq, uint32_t rescore_count,
+                                     uint32_t k, uint64_t* ids_out_dev, float* scores_out_dev) {
+    return guarded([&] {
+        need(h, "index");
+        if (nq == 0) return;
+        need(rec_ham_dev, "rec_ham"); need(rec_ids_dev, "rec_ids"); need(rec_score_dev, "rec_score");
+        need(ids_out_dev, "ids_out"); need(scores_out_dev, "scores_out");
+        const uint32_t R = rescore_count;
+        if (R == 0 || R > kMaxR) fail(GVDB_ERR_INVALID_ARGUMENT, "rescore_count must be in [1, 2048]");
+        if (k > R) fail(GVDB_ERR_INVALID_ARGUMENT, "k must be <= rescore_count");
+        if (n_shards == 0) fail(GVDB_ERR_INVALID_ARGUMENT, "n_shards must be >= 1");
+        DeviceGuard dg(h->cfg.device);
+        WsLease lease(h, (cudaStream_t)stream, true);
+        Workspace* ws = lease.ws;
+        cudaStream_t st = lease.stream;
+        ws->rec_ham.ensure((size_t)nq * R * 4);
+        ws->rec_ids.ensure((size_t)nq * R * 8);
+        ws->rec_score.ensure((size_t)nq * R * 4);
+        merge_select_kernel<<<nq, SORT_THREADS, SORT_N * 8, st>>>(
+            n_shards, rec_ham_dev, rec_ids_dev, rec_score_dev, nq, R, ws->rec_ids.as<uint64_t>(),
+            ws->rec_score.as<float>(), ws->rec_ham.as<uint32_t>());
+        CU(cudaGetLastError());
+        launch_topk(st, ws->rec_ids.as<uint64_t>(), ws->rec_score.as<float>(), nq, R, k, ids_out_dev, scores_out_dev);
+        CU(cudaStreamSynchronize(st));
+    });
+}
+
+}  // extern "C"

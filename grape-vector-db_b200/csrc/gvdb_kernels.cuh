@@ -1,0 +1,484 @@
+// gvdb_kernels.cuh — sm_100a kernels of the quantized-search path.
+//
+//   ingest_kernel     f32 rows -> 1-bit codes (blocked layout) + sequential L2 norms
+//                     [BinaryQuantizer::quantize, /root/reference/src/quantization.rs:97-101]
+//   scan_kernel       1-bit Hamming scan, XOR + popc, 128-bit coalesced loads, query codes
+//                     staged in shared memory by TMA bulk copy, fused threshold filter
+//                     [hamming_distance/similarity + the stage-1 loop, quantization.rs:130-148,165-172]
+//   select_kernel     exact top-R by the unique key (hamming << 32 | row): block bitonic sort
+//                     [the stable sort + slice of quantization.rs:175-179]
+//   rescore_kernel    exact-order f32 cosine of the kept candidates (bit-identical folds)
+//                     [cosine_similarity_manual, quantization.rs:206-216]
+//   topk_kernel       order by (cosine desc, hamming asc, row asc), emit k
+//                     [the stable sort of quantization.rs:190]
+//   merge_select_kernel  cross-shard stage-1 cut over gathered records
+//                     [replaces concat+sort+truncate, src/distributed/shard.rs:776-783]
+//
+// HBM layout of the codes ("blocked"): rows are grouped in tiles of 32; a row's code is
+// NCHUNK 16-byte chunks; chunk c of row r of tile t lives at uint4 index
+// (t*NCHUNK + c)*32 + r.  A warp that owns a tile therefore reads every chunk as one fully
+// coalesced 512-byte request (LDG.128 per lane), and a tile is NCHUNK*512 contiguous bytes.
+// Inside a chunk the bytes are the reference's BinaryVector::to_bytes() bytes
+// (bit j -> byte j/8, bit 7-(j%8)); Hamming distance is invariant to that choice.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace gvdb {
+
+constexpr uint32_t TAU_ALL = 0xffffffffu;   // "emit every live row"
+constexpr int SCAN_THREADS = 256;           // 8 warps = 8 tiles of 32 rows in flight per CTA
+constexpr int SORT_N = 4096;                // block bitonic capacity (u64 keys, 32 KB smem)
+constexpr int SORT_THREADS = 1024;
+constexpr int STAGE_ROWS = 128;             // rows per CTA in the transposing kernels
+
+// ---------------------------------------------------------------------------------------
+// small PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ uint4 ldg_stream(const uint4* p) {   // read-once data: skip L1
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+// TMA 1-D bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP).
+__device__ __forceinline__ void tma_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes,
+                                             uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+        :: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+// Orderable image of an f32: ascending u32 order == ascending float order; -0.0 and +0.0
+// share one image (Rust's partial_cmp calls them Equal, so they must tie).
+__device__ __forceinline__ uint32_t f32_asc_key(float f) {
+    if (f == 0.0f) f = 0.0f;   // canonicalise -0.0
+    uint32_t u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+// ---------------------------------------------------------------------------------------
+// Block-wide bitonic sort of n (power of two, <= SORT_N) u64 keys in shared memory,
+// ascending.  Keys are unique by construction, so the result is deterministic.
+__device__ __forceinline__ void bitonic_sort_smem(uint64_t* s, uint32_t n) {
+    for (uint32_t k = 2; k <= n; k <<= 1) {
+        for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+            for (uint32_t t = threadIdx.x; t < (n >> 1); t += blockDim.x) {
+                uint32_t i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                uint32_t l = i | j;
+                bool up = (i & k) == 0;
+                uint64_t a = s[i], b = s[l];
+                if ((a > b) == up) { s[i] = b; s[l] = a; }
+            }
+            __syncthreads();
+        }
+    }
+}
+__device__ __forceinline__ uint32_t next_pow2(uint32_t v) {
+    return v <= 1 ? 1u : 1u << (32 - __clz(v - 1));
+}
+
+// ---------------------------------------------------------------------------------------
+// ingest_kernel: one thread per row, 32-column slabs transposed through shared memory so
+// global reads are full 128-byte lines and each thread still walks ITS row left to right
+// (the norm is a sequential f32 fold: sum = sum + x*x, mul and add rounded separately).
+// QUERY=false: writes blocked codes + norms + live bits for corpus rows.
+// QUERY=true : writes qpack[i*qs .. ] = code words, then [tau=TAU_ALL, 0, 0, 0], and qnorm.
+template <bool QUERY>
+__global__ void __launch_bounds__(STAGE_ROWS)
+ingest_kernel(const float* __restrict__ x, uint64_t n, int dim, float thr, int nchunk,
+              uint64_t first_row, uint4* __restrict__ codes, float* __restrict__ norms,
+              uint32_t* __restrict__ live, uint32_t* __restrict__ qpack, int qs) {
+    __shared__ float tile[STAGE_ROWS][33];
+    const int tid = threadIdx.x;
+    const uint64_t i0 = (uint64_t)blockIdx.x * STAGE_ROWS;
+    const uint64_t i = i0 + tid;
+    const bool valid = i < n;
+    const bool vec4 = (dim & 3) == 0;
+    float ss = 0.0f;
+    const uint64_t g = first_row + i;
+    for (int c = 0; c < nchunk; ++c) {
+        uint32_t w[4] = {0u, 0u, 0u, 0u};
+        for (int sub = 0; sub < 4; ++sub) {
+            const int j0 = (c * 4 + sub) * 32;
+            if (j0 < dim) {   // block-uniform
+                __syncthreads();
+                if (vec4) {
+                    for (int idx = tid; idx < STAGE_ROWS * 8; idx += STAGE_ROWS) {
+                        int r = idx >> 3, seg = idx & 7;
+                        int j = j0 + seg * 4;
+                        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (i0 + r < n && j < dim)
+                            v = *reinterpret_cast<const float4*>(x + (i0 + r) * (uint64_t)dim + j);
+                        tile[r][seg * 4 + 0] = v.x; tile[r][seg * 4 + 1] = v.y;
+                        tile[r][seg * 4 + 2] = v.z; tile[r][seg * 4 + 3] = v.w;
+                    }
+                } else {
+                    for (int idx = tid; idx < STAGE_ROWS * 32; idx += STAGE_ROWS) {
+                        int r = idx >> 5, e = idx & 31;
+                        int j = j0 + e;
+                        tile[r][e] = (i0 + r < n && j < dim) ? x[(i0 + r) * (uint64_t)dim + j] : 0.f;
+                    }
+                }
+                __syncthreads();
+                const int lim = min(32, dim - j0);
+                uint32_t word = 0;
+                for (int e = 0; e < lim; ++e) {
+                    float v = tile[tid][e];
+                    ss = __fadd_rn(ss, __fmul_rn(v, v));
+                    // Msb0 inside each byte, bytes in memory order (little-endian word)
+                    word |= (uint32_t)(v > thr) << ((e & ~7) | (7 - (e & 7)));
+                }
+                w[sub] = word;
+            }
+        }
+        if (valid) {
+            uint4 pk = make_uint4(w[0], w[1], w[2], w[3]);
+            if (QUERY) *reinterpret_cast<uint4*>(qpack + i * (uint64_t)qs + c * 4) = pk;
+            else codes[((g >> 5) * (uint64_t)nchunk + c) * 32 + (g & 31)] = pk;
+        }
+    }
+    if (valid) {
+        norms[QUERY ? i : g] = __fsqrt_rn(ss);
+        if (QUERY) *reinterpret_cast<uint4*>(qpack + i * (uint64_t)qs + nchunk * 4) =
+                       make_uint4(TAU_ALL, 0u, 0u, 0u);
+        else atomicOr(&live[g >> 5], 1u << (g & 31));
+    }
+}
+
+// Query codes supplied by the caller (reference byte layout, nbytes per query) -> qpack.
+__global__ void pack_query_codes_kernel(const uint8_t* __restrict__ qcodes, uint32_t nq,
+                                        int nbytes, int nchunk, uint32_t* __restrict__ qpack,
+                                        int qs) {
+    uint32_t q = blockIdx.x;
+    if (q >= nq) return;
+    for (int w = threadIdx.x; w < qs; w += blockDim.x) {
+        uint32_t v = 0;
+        if (w < nchunk * 4) {
+            for (int b = 0; b < 4; ++b) {
+                int byte = w * 4 + b;
+                if (byte < nbytes) v |= (uint32_t)qcodes[(uint64_t)q * nbytes + byte] << (8 * b);
+            }
+        } else if (w == nchunk * 4) v = TAU_ALL;
+        qpack[(uint64_t)q * qs + w] = v;
+    }
+}
+
+// blocked codes -> reference byte layout (for gvdb_get_codes / parity)
+__global__ void unblock_codes_kernel(const uint4* __restrict__ codes, int nchunk, uint64_t first,
+                                     uint64_t n, int nbytes, uint8_t* __restrict__ out) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint64_t g = first + i;
+    for (int c = 0; c < nchunk; ++c) {
+        uint4 v = codes[((g >> 5) * (uint64_t)nchunk + c) * 32 + (g & 31)];
+        uint32_t w[4] = {v.x, v.y, v.z, v.w};
+        for (int b = 0; b < 16; ++b) {
+            int byte = c * 16 + b;
+            if (byte < nbytes) out[i * (uint64_t)nbytes + byte] = (uint8_t)(w[b >> 2] >> (8 * (b & 3)));
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// scan_kernel — THE hot loop.  One warp owns a tile of 32 rows: each lane keeps its row's
+// code in NCHUNK uint4 registers (one coalesced 512 B request per chunk) and walks the query
+// group staged in shared memory (one TMA bulk copy per CTA; every lane reads the same
+// address, i.e. a broadcast LDS.128).  Per (row, query): NCHUNK*4 XOR + popc.
+// MODE 0 (search): rows that beat the query's current threshold are appended to the query's
+//                  candidate buffer as key = hamming << 32 | row; distances never touch HBM.
+// MODE 1 (parity): every distance is written out (gvdb_hamming).
+// Algorithmic bytes per launch: (tile_hi - tile_lo) * 32 * NCHUNK * 16 (codes streamed once
+// per query group) — see DESIGN.md §5.
+template <int NCHUNK, int MODE>
+__global__ void __launch_bounds__(SCAN_THREADS)
+scan_kernel(const uint4* __restrict__ codes, const uint32_t* __restrict__ live, uint32_t tile_lo,
+            uint32_t tile_hi, const uint32_t* __restrict__ qpack, int nq, int qgroup,
+            uint32_t* __restrict__ cnt, uint64_t* __restrict__ buf, uint32_t cap,
+            uint32_t* __restrict__ overflow, uint32_t* __restrict__ dist_out,
+            uint64_t dist_stride, uint64_t n_rows) {
+    constexpr int QS = NCHUNK * 4 + 4;   // words per staged query: code, then [tau,0,0,0]
+    extern __shared__ __align__(128) uint32_t sq[];
+    __shared__ __align__(8) uint64_t mbar;
+
+    const int q0 = blockIdx.y * qgroup;
+    const int nql = min(qgroup, nq - q0);
+    const uint32_t bar = smem_u32(&mbar);
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const uint32_t bytes = (uint32_t)nql * QS * 4u;
+        mbar_expect_tx(bar, bytes);
+        tma_bulk_g2s(smem_u32(sq), qpack + (size_t)q0 * QS, bytes, bar);
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr int WARPS = SCAN_THREADS / 32;
+    bool staged = false;
+
+    for (uint32_t tile = tile_lo + blockIdx.x * WARPS + warp; tile < tile_hi;
+         tile += gridDim.x * WARPS) {
+        uint4 r[NCHUNK];
+        const uint4* base = codes + ((size_t)tile * NCHUNK) * 32 + lane;
+#pragma unroll
+        for (int c = 0; c < NCHUNK; ++c) r[c] = ldg_stream(base + c * 32);
+        const bool alive = (live[tile] >> lane) & 1u;
+        const uint32_t row = tile * 32u + lane;
+        if (!staged) {                       // row loads are in flight while the TMA lands
+            while (!mbar_try_wait(bar, 0)) {}
+            staged = true;
+        }
+#pragma unroll 2
+        for (int q = 0; q < nql; ++q) {
+            const uint4* qp = reinterpret_cast<const uint4*>(sq + q * QS);
+            uint32_t d = 0;
+#pragma unroll
+            for (int c = 0; c < NCHUNK; ++c) {
+                const uint4 v = qp[c];
+                d += __popc(r[c].x ^ v.x) + __popc(r[c].y ^ v.y) + __popc(r[c].z ^ v.z) +
+                     __popc(r[c].w ^ v.w);
+            }
+            if (MODE == 0) {
+                const uint32_t tau = sq[q * QS + NCHUNK * 4];
+                // strict '<': tau is the R-th smallest distance over EARLIER rows, so a later
+                // row that ties it has a larger row number and cannot enter the top R.
+                if (alive && d < tau) {
+                    const uint32_t pos = atomicAdd(&cnt[q0 + q], 1u);
+                    if (pos < cap) buf[(size_t)(q0 + q) * cap + pos] = ((uint64_t)d << 32) | row;
+                    else *overflow = 1u;
+                }
+            } else {
+                if (row < n_rows) dist_out[(size_t)(q0 + q) * dist_stride + row] = d;
+            }
+        }
+    }
+    if (!staged) { while (!mbar_try_wait(bar, 0)) {} }   // never exit with a copy in flight
+}
+
+// ---------------------------------------------------------------------------------------
+// select_kernel: one CTA per query.  Streams the query's candidate keys through a
+// SORT_N-wide block bitonic sort, keeping the R smallest; writes them back sorted, sets
+// cnt = kept and the query's next threshold (R-th smallest distance, or TAU_ALL while
+// fewer than R live rows have been seen).  R <= SORT_N/2.
+__global__ void __launch_bounds__(SORT_THREADS)
+select_kernel(uint64_t* __restrict__ buf, uint32_t cap, uint32_t* __restrict__ cnt, uint32_t R,
+              uint32_t* __restrict__ qpack, int qs, int tau_word) {
+    extern __shared__ __align__(16) uint64_t skeys[];
+    const uint32_t q = blockIdx.x;
+    uint64_t* mine = buf + (size_t)q * cap;
+    const uint32_t n_in = min(cnt[q], cap);
+    uint32_t have = 0, consumed = 0;
+    while (consumed < n_in) {
+        const uint32_t take = min((uint32_t)SORT_N - have, n_in - consumed);
+        const uint32_t total = have + take;
+        const uint32_t n_eff = max(64u, next_pow2(total));
+        for (uint32_t i = threadIdx.x; i < n_eff - have; i += blockDim.x)
+            skeys[have + i] = i < take ? mine[consumed + i] : UINT64_MAX;
+        __syncthreads();
+        bitonic_sort_smem(skeys, n_eff);
+        have = min(R, total);
+        consumed += take;
+    }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < have; i += blockDim.x) mine[i] = skeys[i];
+    if (threadIdx.x == 0) {
+        cnt[q] = have;
+        qpack[(size_t)q * qs + tau_word] = (have >= R && R > 0) ? (uint32_t)(skeys[R - 1] >> 32) : TAU_ALL;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// rescore_kernel: one thread per (query, candidate).  32-column slabs of the candidate's row
+// and of its query are transposed through shared memory; each thread then folds its own
+// pair strictly left to right:  dot = dot + q[j]*c[j]  (separate roundings, never FMA),
+// which is bit-identical to the reference's iterator sum.  ||q|| and ||c|| are the same
+// sequential folds, computed once (prep / ingest) instead of once per pair.
+// Outputs the shard record (hamming, global row, cosine) in stage-1 order.
+__global__ void __launch_bounds__(STAGE_ROWS)
+rescore_kernel(const float* __restrict__ rows, const float* __restrict__ norms, uint64_t row_base,
+               int dim, const float* __restrict__ queries, const float* __restrict__ qnorm,
+               const uint64_t* __restrict__ buf, uint32_t cap, const uint32_t* __restrict__ cnt,
+               uint32_t R, uint32_t nq, uint32_t* __restrict__ out_ham,
+               uint64_t* __restrict__ out_ids, float* __restrict__ out_score) {
+    __shared__ float tc[STAGE_ROWS][33];
+    __shared__ float tq[STAGE_ROWS][33];
+    __shared__ uint32_t s_row[STAGE_ROWS];
+    __shared__ uint32_t s_q[STAGE_ROWS];
+    const int tid = threadIdx.x;
+    const uint64_t p = (uint64_t)blockIdx.x * STAGE_ROWS + tid;
+    const uint32_t q = (uint32_t)(p / R), r = (uint32_t)(p % R);
+    const bool slot = q < nq;
+    const bool valid = slot && r < cnt[q];
+    uint64_t key = valid ? buf[(size_t)q * cap + r] : UINT64_MAX;
+    s_row[tid] = valid ? (uint32_t)key : 0xffffffffu;
+    s_q[tid] = valid ? q : 0xffffffffu;
+    const bool vec4 = (dim & 3) == 0;
+    float dot = 0.0f;
+    for (int j0 = 0; j0 < dim; j0 += 32) {
+        __syncthreads();
+        if (vec4) {
+            for (int idx = tid; idx < STAGE_ROWS * 8; idx += STAGE_ROWS) {
+                int rr = idx >> 3, seg = idx & 7;
+                int j = j0 + seg * 4;
+                uint32_t crow = s_row[rr], cq = s_q[rr];
+                float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+                if (crow != 0xffffffffu && j < dim) {
+                    a = *reinterpret_cast<const float4*>(rows + (uint64_t)crow * dim + j);
+                    b = *reinterpret_cast<const float4*>(queries + (uint64_t)cq * dim + j);
+                }
+                tc[rr][seg * 4 + 0] = a.x; tc[rr][seg * 4 + 1] = a.y;
+                tc[rr][seg * 4 + 2] = a.z; tc[rr][seg * 4 + 3] = a.w;
+                tq[rr][seg * 4 + 0] = b.x; tq[rr][seg * 4 + 1] = b.y;
+                tq[rr][seg * 4 + 2] = b.z; tq[rr][seg * 4 + 3] = b.w;
+            }
+        } else {
+            for (int idx = tid; idx < STAGE_ROWS * 32; idx += STAGE_ROWS) {
+                int rr = idx >> 5, e = idx & 31;
+                int j = j0 + e;
+                uint32_t crow = s_row[rr], cq = s_q[rr];
+                bool ok = crow != 0xffffffffu && j < dim;
+                tc[rr][e] = ok ? rows[(uint64_t)crow * dim + j] : 0.f;
+                tq[rr][e] = ok ? queries[(uint64_t)cq * dim + j] : 0.f;
+            }
+        }
+        __syncthreads();
+        const int lim = min(32, dim - j0);
+        for (int e = 0; e < lim; ++e) dot = __fadd_rn(dot, __fmul_rn(tq[tid][e], tc[tid][e]));
+    }
+    if (slot) {
+        float cosv = -INFINITY;
+        if (valid) {
+            const float na = qnorm[q], nb = norms[(uint32_t)key];
+            cosv = (na == 0.0f || nb == 0.0f) ? 0.0f : __fdiv_rn(dot, __fmul_rn(na, nb));
+        }
+        out_ham[p] = valid ? (uint32_t)(key >> 32) : 0xffffffffu;
+        out_ids[p] = valid ? row_base + (uint32_t)key : UINT64_MAX;
+        out_score[p] = cosv;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// topk_kernel: one CTA per query over its R records (already in (hamming, row) order).
+// Sort key = (descending image of the cosine) << 32 | position, so equal cosines keep
+// stage-1 order — exactly what the reference's second stable sort does.
+__global__ void topk_kernel(const uint64_t* __restrict__ rec_ids, const float* __restrict__ rec_score,
+                            uint32_t R, uint32_t n_eff, uint32_t k, uint64_t* __restrict__ ids_out,
+                            float* __restrict__ scores_out) {
+    extern __shared__ __align__(16) uint64_t skeys[];
+    const uint32_t q = blockIdx.x;
+    const uint64_t* ids = rec_ids + (size_t)q * R;
+    const float* sc = rec_score + (size_t)q * R;
+    for (uint32_t i = threadIdx.x; i < n_eff; i += blockDim.x) {
+        uint64_t key = UINT64_MAX;
+        if (i < R && ids[i] != UINT64_MAX) key = ((uint64_t)(~f32_asc_key(sc[i])) << 32) | i;
+        skeys[i] = key;
+    }
+    __syncthreads();
+    bitonic_sort_smem(skeys, n_eff);
+    for (uint32_t t = threadIdx.x; t < k; t += blockDim.x) {
+        uint64_t key = t < n_eff ? skeys[t] : UINT64_MAX;
+        if (key == UINT64_MAX) {
+            ids_out[(size_t)q * k + t] = UINT64_MAX;
+            scores_out[(size_t)q * k + t] = -INFINITY;
+        } else {
+            uint32_t pos = (uint32_t)key;
+            ids_out[(size_t)q * k + t] = ids[pos];
+            scores_out[(size_t)q * k + t] = sc[pos];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// merge_select_kernel: one CTA per query over the gathered [shard][query][R] records.
+// Keeps the global top R by (hamming, global row) — the stage-1 cut the single-index search
+// would have made — and writes them, in that order, as one merged record list per query.
+// Key = hamming << 40 | global row (rows < 2^40) ; payload (source slot) rides in a
+// parallel shared array addressed through the low bits, recovered by a second lookup.
+__global__ void __launch_bounds__(SORT_THREADS)
+merge_select_kernel(uint32_t n_shards, const uint32_t* __restrict__ rec_ham,
+                    const uint64_t* __restrict__ rec_ids, const float* __restrict__ rec_score,
+                    uint32_t nq, uint32_t R, uint64_t* __restrict__ out_ids,
+                    float* __restrict__ out_score, uint32_t* __restrict__ out_ham) {
+    // Sort keys carry (hamming, global row); the score is looked up again afterwards by
+    // binary-searching the source shard's (sorted) list — no payload array needed because
+    // (hamming, row) is unique across shards.
+    extern __shared__ __align__(16) uint64_t skeys[];
+    const uint32_t q = blockIdx.x;
+    const uint32_t total_in = n_shards * R;
+    uint32_t have = 0, consumed = 0;
+    while (consumed < total_in) {
+        const uint32_t take = min((uint32_t)SORT_N - have, total_in - consumed);
+        const uint32_t total = have + take;
+        const uint32_t n_eff = max(64u, next_pow2(total));
+        for (uint32_t i = threadIdx.x; i < n_eff - have; i += blockDim.x) {
+            uint64_t key = UINT64_MAX;
+            if (i < take) {
+                uint32_t src = consumed + i;
+                uint32_t s = src / R, r = src % R;
+                size_t at = ((size_t)s * nq + q) * R + r;
+                uint64_t id = rec_ids[at];
+                if (id != UINT64_MAX) key = ((uint64_t)rec_ham[at] << 40) | id;
+            }
+            skeys[have + i] = key;
+        }
+        __syncthreads();
+        bitonic_sort_smem(skeys, n_eff);
+        have = min(R, total);
+        consumed += take;
+    }
+    __syncthreads();
+    for (uint32_t t = threadIdx.x; t < R; t += blockDim.x) {
+        uint64_t key = t < have ? skeys[t] : UINT64_MAX;
+        uint64_t id = UINT64_MAX;
+        uint32_t hm = 0xffffffffu;
+        float sc = -INFINITY;
+        if (key != UINT64_MAX) {
+            id = key & ((1ull << 40) - 1);
+            hm = (uint32_t)(key >> 40);
+            // find the record: scan the shards' lists (each sorted by the same key)
+            for (uint32_t s = 0; s < n_shards; ++s) {
+                const size_t base = ((size_t)s * nq + q) * R;
+                uint32_t lo = 0, hi = R;
+                while (lo < hi) {
+                    uint32_t mid = (lo + hi) >> 1;
+                    uint64_t mid_id = rec_ids[base + mid];
+                    uint64_t mk = mid_id == UINT64_MAX ? UINT64_MAX
+                                                       : (((uint64_t)rec_ham[base + mid] << 40) | mid_id);
+                    if (mk < key) lo = mid + 1; else hi = mid;
+                }
+                if (lo < R && rec_ids[base + lo] == id && rec_ham[base + lo] == hm) {
+                    sc = rec_score[base + lo];
+                    break;
+                }
+            }
+        }
+        out_ids[(size_t)q * R + t] = id;
+        out_ham[(size_t)q * R + t] = hm;
+        out_score[(size_t)q * R + t] = sc;
+    }
+}
+
+}  // namespace gvdb

@@ -1,0 +1,233 @@
+"""GpuIndex: one shard of the corpus in one B200's HBM, driven through the C ABI.
+
+Thin, typed wrapper over include/gvdb.h.  Host-array entry points take numpy arrays;
+`*_device` entry points take torch CUDA tensors and run on torch's current stream
+(torch is plumbing here: device memory, streams, torch.distributed).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _ffi
+from .errors import raise_for_status
+
+NO_ID = np.uint64(_ffi.GVDB_NO_ID)
+
+
+def _np(a, dtype):
+    return np.ascontiguousarray(a, dtype=dtype)
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class GpuIndex:
+    """Rows [row_base, row_base + len) of the corpus: 1-bit codes + f32 originals in HBM."""
+
+    def __init__(self, dim: int, threshold: float = 0.0, rescore_ratio: float = 0.1,
+                 device: int = 0, capacity_rows: int = 0, row_base: int = 0):
+        self._lib = _ffi.lib()
+        cfg = _ffi.GvdbConfig()
+        cfg.struct_size = C.sizeof(_ffi.GvdbConfig)
+        cfg.dim = dim
+        cfg.threshold = threshold
+        cfg.rescore_ratio = rescore_ratio
+        cfg.device = device
+        cfg.flags = 0
+        cfg.capacity_rows = capacity_rows
+        cfg.row_base = row_base
+        h = C.c_void_p()
+        raise_for_status(self._lib.gvdb_create(C.byref(cfg), C.byref(h)), self._lib)
+        self._h = h
+        self.dim = dim
+        self.threshold = threshold
+        self.rescore_ratio = rescore_ratio
+        self.device = device
+        self.row_base = row_base
+        self.nbytes = (dim + 7) // 8
+
+    # -- lifecycle ---------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.gvdb_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def _ok(self, st):
+        raise_for_status(st, self._lib)
+
+    # -- ingest ------------------------------------------------------------------------
+    def add(self, rows) -> int:
+        rows = _np(rows, np.float32)
+        if rows.ndim != 2 or rows.shape[1] != self.dim:
+            from .errors import DimensionMismatch
+            raise DimensionMismatch(self.dim, rows.shape[-1] if rows.ndim else 0)
+        first = C.c_uint64()
+        self._ok(self._lib.gvdb_add(self._h, _ptr(rows), rows.shape[0], C.byref(first)))
+        return int(first.value)
+
+    def add_device(self, rows_t) -> int:
+        import torch
+        assert rows_t.is_cuda and rows_t.dtype == torch.float32 and rows_t.is_contiguous()
+        assert rows_t.dim() == 2 and rows_t.shape[1] == self.dim
+        first = C.c_uint64()
+        st = torch.cuda.current_stream(rows_t.device).cuda_stream
+        self._ok(self._lib.gvdb_add_device(self._h, C.c_void_p(st), C.c_void_p(rows_t.data_ptr()),
+                                           rows_t.shape[0], C.byref(first)))
+        return int(first.value)
+
+    def reserve(self, capacity_rows: int):
+        self._ok(self._lib.gvdb_reserve(self._h, capacity_rows))
+
+    def remove(self, local_row: int) -> bool:
+        was = C.c_int32()
+        self._ok(self._lib.gvdb_remove(self._h, local_row, C.byref(was)))
+        return bool(was.value)
+
+    def clear(self):
+        self._ok(self._lib.gvdb_clear(self._h))
+
+    def __len__(self):
+        return int(self._lib.gvdb_len(self._h))
+
+    def stats(self) -> dict:
+        s = _ffi.GvdbStats()
+        self._ok(self._lib.gvdb_get_stats(self._h, C.byref(s)))
+        return {f: int(getattr(s, f)) for f, _ in s._fields_}
+
+    @property
+    def rows(self) -> int:
+        return self.stats()["rows"]
+
+    # -- quantizer pieces --------------------------------------------------------------
+    def quantize(self, x) -> np.ndarray:
+        x = _np(x, np.float32)
+        single = x.ndim == 1
+        x2 = x.reshape(1, -1) if single else x
+        if x2.shape[1] != self.dim:
+            from .errors import DimensionMismatch
+            raise DimensionMismatch(self.dim, x2.shape[1])
+        out = np.zeros((x2.shape[0], self.nbytes), dtype=np.uint8)
+        self._ok(self._lib.gvdb_quantize(self._h, _ptr(x2), x2.shape[0], _ptr(out)))
+        return out[0] if single else out
+
+    def get_codes(self, first: int = 0, n: int | None = None) -> np.ndarray:
+        n = self.rows - first if n is None else n
+        out = np.zeros((n, self.nbytes), dtype=np.uint8)
+        self._ok(self._lib.gvdb_get_codes(self._h, first, n, _ptr(out)))
+        return out
+
+    def hamming(self, q_codes) -> np.ndarray:
+        q = _np(q_codes, np.uint8)
+        q2 = q.reshape(1, -1) if q.ndim == 1 else q
+        assert q2.shape[1] == self.nbytes
+        out = np.zeros((q2.shape[0], self.rows), dtype=np.uint32)
+        self._ok(self._lib.gvdb_hamming(self._h, _ptr(q2), q2.shape[0], _ptr(out)))
+        return out
+
+    def rescore_count(self, n: int | None = None, ratio: float | None = None) -> int:
+        n = len(self) if n is None else n
+        ratio = self.rescore_ratio if ratio is None else ratio
+        return int(self._lib.gvdb_rescore_count(n, ratio))
+
+    # -- two-stage search ----------------------------------------------------------------
+    def search_batch(self, queries, k: int, rescore_count: int, want_candidates: bool = False):
+        q = _np(queries, np.float32)
+        if q.ndim != 2 or q.shape[1] != self.dim:
+            from .errors import DimensionMismatch
+            raise DimensionMismatch(self.dim, q.shape[-1] if q.ndim else 0)
+        nq = q.shape[0]
+        ids = np.full((nq, k), NO_ID, dtype=np.uint64)
+        sc = np.full((nq, k), -np.inf, dtype=np.float32)
+        ci = ch = None
+        if want_candidates:
+            ci = np.full((nq, rescore_count), NO_ID, dtype=np.uint64)
+            ch = np.full((nq, rescore_count), 0xFFFFFFFF, dtype=np.uint32)
+        self._ok(self._lib.gvdb_search_batch(self._h, _ptr(q), nq, k, rescore_count, _ptr(ids),
+                                             _ptr(sc), _ptr(ci), _ptr(ch)))
+        return (ids, sc, ci, ch) if want_candidates else (ids, sc)
+
+    def search_batch_device(self, queries_t, k: int, rescore_count: int, ids_out=None,
+                            scores_out=None):
+        import torch
+        assert queries_t.is_cuda and queries_t.dtype == torch.float32 and queries_t.is_contiguous()
+        nq = queries_t.shape[0]
+        dev = queries_t.device
+        if ids_out is None:
+            ids_out = torch.empty((nq, k), dtype=torch.int64, device=dev)
+        if scores_out is None:
+            scores_out = torch.empty((nq, k), dtype=torch.float32, device=dev)
+        st = torch.cuda.current_stream(dev).cuda_stream
+        self._ok(self._lib.gvdb_search_batch_device(
+            self._h, C.c_void_p(st), C.c_void_p(queries_t.data_ptr()), nq, k, rescore_count,
+            C.c_void_p(ids_out.data_ptr()), C.c_void_p(scores_out.data_ptr()), None, None))
+        return ids_out, scores_out
+
+    # -- exact flat search ----------------------------------------------------------------
+    def flat_search_batch(self, queries, k: int):
+        q = _np(queries, np.float32)
+        if q.ndim != 2 or q.shape[1] != self.dim:
+            from .errors import DimensionMismatch
+            raise DimensionMismatch(self.dim, q.shape[-1] if q.ndim else 0)
+        nq = q.shape[0]
+        ids = np.full((nq, k), NO_ID, dtype=np.uint64)
+        ds = np.full((nq, k), np.inf, dtype=np.float32)
+        self._ok(self._lib.gvdb_flat_search_batch(self._h, _ptr(q), nq, k, _ptr(ids), _ptr(ds)))
+        return ids, ds
+
+    def flat_search_batch_device(self, queries_t, k: int):
+        import torch
+        assert queries_t.is_cuda and queries_t.dtype == torch.float32 and queries_t.is_contiguous()
+        nq = queries_t.shape[0]
+        dev = queries_t.device
+        ids = torch.empty((nq, k), dtype=torch.int64, device=dev)
+        ds = torch.empty((nq, k), dtype=torch.float32, device=dev)
+        st = torch.cuda.current_stream(dev).cuda_stream
+        self._ok(self._lib.gvdb_flat_search_batch_device(
+            self._h, C.c_void_p(st), C.c_void_p(queries_t.data_ptr()), nq, k,
+            C.c_void_p(ids.data_ptr()), C.c_void_p(ds.data_ptr())))
+        return ids, ds
+
+    # -- sharded search: the two halves around the exchange ---------------------------------
+    def search_shard_device(self, queries_t, rescore_count: int):
+        """Local records (ham u32->int32 bits, ids int64 bits of u64, score f32), each [nq, R]."""
+        import torch
+        nq = queries_t.shape[0]
+        dev = queries_t.device
+        ham = torch.empty((nq, rescore_count), dtype=torch.int32, device=dev)
+        ids = torch.empty((nq, rescore_count), dtype=torch.int64, device=dev)
+        sc = torch.empty((nq, rescore_count), dtype=torch.float32, device=dev)
+        st = torch.cuda.current_stream(dev).cuda_stream
+        self._ok(self._lib.gvdb_search_shard_device(
+            self._h, C.c_void_p(st), C.c_void_p(queries_t.data_ptr()), nq, rescore_count,
+            C.c_void_p(ham.data_ptr()), C.c_void_p(ids.data_ptr()), C.c_void_p(sc.data_ptr())))
+        return ham, ids, sc
+
+    def merge_shards_device(self, ham_all, ids_all, sc_all, k: int):
+        """Gathered [n_shards, nq, R] records -> (ids [nq,k] int64, scores [nq,k] f32)."""
+        import torch
+        n_shards, nq, R = ham_all.shape
+        assert ham_all.is_cuda and ham_all.is_contiguous() and ids_all.is_contiguous()
+        dev = ham_all.device
+        ids = torch.empty((nq, k), dtype=torch.int64, device=dev)
+        sc = torch.empty((nq, k), dtype=torch.float32, device=dev)
+        st = torch.cuda.current_stream(dev).cuda_stream
+        self._ok(self._lib.gvdb_merge_shards_device(
+            self._h, C.c_void_p(st), n_shards, C.c_void_p(ham_all.data_ptr()),
+            C.c_void_p(ids_all.data_ptr()), C.c_void_p(sc_all.data_ptr()), nq, R, k,
+            C.c_void_p(ids.data_ptr()), C.c_void_p(sc.data_ptr())))
+        return ids, sc

@@ -1,0 +1,175 @@
+/* gvdb.h — C ABI of the B200-native quantized-search engine for grape-vector-db.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no C++ or
+ * torch types.  One gvdb_index is ONE SHARD on ONE GPU: a contiguous range of corpus
+ * rows held in HBM as (a) 1-bit codes, (b) the original f32 rows, (c) per-row L2
+ * norms and (d) a live bitmap.  The reference interfaces each entry point replaces
+ * are cited as /root/reference file:line.  Ids are dense row numbers; the String ids
+ * of `trait VectorIndex` (src/index.rs:35-62) stay on the host side of the FFI
+ * (id_to_index / index_to_id maps, src/index.rs:333-334) — see INTEGRATION.md.
+ *
+ * Threading: search entry points are re-entrant (the reference calls
+ * VectorIndex::search under a tokio READ guard from many worker threads,
+ * src/lib.rs:469-477).  Mutating entry points (add/remove/clear/reserve) require
+ * exclusivity, exactly what the reference's write guard gives (src/lib.rs:351-352).
+ *
+ * Errors: every call returns a gvdb_status; nothing aborts or throws across the
+ * boundary.  gvdb_last_error() returns the calling thread's last message.
+ * There is NO CPU fallback: without a usable CUDA device gvdb_create fails.
+ */
+#ifndef GVDB_H
+#define GVDB_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GVDB_ABI_VERSION 1u
+
+#if defined(__GNUC__)
+#define GVDB_API __attribute__((visibility("default")))
+#else
+#define GVDB_API
+#endif
+
+/* Status codes map 1:1 onto the VectorDbError variants this path emits
+ * (src/types.rs:859-920). */
+typedef enum gvdb_status {
+    GVDB_OK = 0,
+    GVDB_ERR_INDEX_NOT_BUILT = 1,          /* VectorDbError::IndexNotBuilt  (src/index.rs:213,621-623) */
+    GVDB_ERR_DIMENSION_MISMATCH = 2,       /* ::DimensionMismatch{expected,actual} (src/index.rs:590-594) */
+    GVDB_ERR_INVALID_VECTOR_DIMENSION = 3, /* ::InvalidVectorDimension (src/quantization.rs:131-133,335) */
+    GVDB_ERR_QUANTIZATION = 4,             /* ::QuantizationError(String) (src/quantization.rs:158-162) */
+    GVDB_ERR_INDEX = 5,                    /* ::IndexError(String): CUDA / allocation / internal failures */
+    GVDB_ERR_INVALID_ARGUMENT = 6,         /* ::ConfigError(String) */
+    GVDB_ERR_NOT_IMPLEMENTED = 7           /* ::NotImplemented(String) */
+} gvdb_status;
+
+#define GVDB_NO_ID UINT64_MAX /* unfilled id slot; its score is -inf (distance +inf) */
+
+typedef struct gvdb_index gvdb_index; /* opaque: one shard on one GPU */
+
+/* BinaryQuantizationConfig (src/quantization.rs:11-31) + placement.  Zero-initialise,
+ * set struct_size = sizeof(gvdb_config), then fill. */
+typedef struct gvdb_config {
+    uint32_t struct_size;
+    uint32_t dim;            /* vector dimension (> 0) */
+    float threshold;         /* BinaryQuantizationConfig::threshold  (default 0.0) */
+    float rescore_ratio;     /* BinaryQuantizationConfig::rescore_ratio (default 0.1) */
+    int32_t device;          /* CUDA device ordinal */
+    uint32_t flags;          /* reserved, 0 */
+    uint64_t capacity_rows;  /* rows to reserve in HBM up front (0 = grow on demand) */
+    uint64_t row_base;       /* global row number of this shard's local row 0 */
+} gvdb_config;
+
+/* IndexStats (src/index.rs:82-88) plus the HBM footprint. */
+typedef struct gvdb_stats {
+    uint64_t vector_count;   /* live rows == VectorIndex::len() */
+    uint64_t rows;           /* rows ever added (live + tombstoned) */
+    uint64_t dimension;
+    uint64_t memory_usage;   /* rows * dim * 4, the reference's figure (src/index.rs:676-679) */
+    uint64_t hbm_bytes;      /* bytes actually reserved on the device */
+    uint64_t code_bytes_per_row;
+} gvdb_stats;
+
+/* ---- lifecycle ------------------------------------------------------------------ */
+GVDB_API uint32_t gvdb_abi_version(void);
+GVDB_API const char* gvdb_last_error(void);
+/* replaces FaissVectorIndex::new / HnswVectorIndex::new at the wiring point src/lib.rs:256-261 */
+GVDB_API gvdb_status gvdb_create(const gvdb_config* cfg, gvdb_index** out);
+GVDB_API void gvdb_destroy(gvdb_index* h);
+
+/* ---- ingest (exclusive) ----------------------------------------------------------- */
+/* VectorIndex::add_vectors (src/index.rs:612-617; caller src/lib.rs:350-353).  `rows` is
+ * n x dim row-major f32 in HOST memory; rows are copied to HBM, quantised
+ * (BinaryQuantizer::quantize_batch, src/quantization.rs:125-127) and normed on the GPU.
+ * *first_row_out = local row number of rows[0]. */
+GVDB_API gvdb_status gvdb_add(gvdb_index* h, const float* rows, uint64_t n, uint64_t* first_row_out);
+/* Same with `rows` already in DEVICE memory of h's GPU; work is enqueued on `stream`
+ * (a cudaStream_t, NULL = default stream) and completed before return. */
+GVDB_API gvdb_status gvdb_add_device(gvdb_index* h, void* stream, const float* rows_dev, uint64_t n,
+                            uint64_t* first_row_out);
+GVDB_API gvdb_status gvdb_reserve(gvdb_index* h, uint64_t capacity_rows);
+/* VectorIndex::remove_vector (src/index.rs:642-650): tombstone; *was_live_out = Ok(bool). */
+GVDB_API gvdb_status gvdb_remove(gvdb_index* h, uint64_t local_row, int32_t* was_live_out);
+/* VectorIndex::clear (src/index.rs:664-670) */
+GVDB_API gvdb_status gvdb_clear(gvdb_index* h);
+/* VectorIndex::len / get_stats (src/index.rs:652-658,672-681) */
+GVDB_API uint64_t gvdb_len(const gvdb_index* h);
+GVDB_API gvdb_status gvdb_get_stats(const gvdb_index* h, gvdb_stats* out);
+
+/* ---- quantizer pieces (parity / BinaryVector interop) ----------------------------- */
+/* BinaryQuantizer::quantize_batch (src/quantization.rs:86-127) on the GPU: n x dim f32
+ * (host) -> n x ceil(dim/8) bytes (host) in BinaryVector::to_bytes() layout
+ * (bit j -> byte j/8, bit 7-(j%8); src/quantization.rs:37,54-56). */
+GVDB_API gvdb_status gvdb_quantize(gvdb_index* h, const float* x, uint64_t n, uint8_t* codes_out);
+/* Stored codes of local rows [first, first+n) in the same byte layout. */
+GVDB_API gvdb_status gvdb_get_codes(gvdb_index* h, uint64_t first, uint64_t n, uint8_t* codes_out);
+/* BinaryQuantizer::hamming_distance (src/quantization.rs:130-141) of each query code
+ * against every stored row: q_codes nq x ceil(dim/8) bytes (host) -> dist_out nq x rows
+ * u32 (host).  Tombstoned rows are included (this is the raw scan). */
+GVDB_API gvdb_status gvdb_hamming(gvdb_index* h, const uint8_t* q_codes, uint32_t nq, uint32_t* dist_out);
+/* rescore_count of src/quantization.rs:178-179: min(n, (usize)((f32)n * ratio)). */
+GVDB_API uint64_t gvdb_rescore_count(uint64_t n, float ratio);
+
+/* ---- two-stage search (re-entrant) -------------------------------------------------- */
+/* BinaryQuantizer::multi_stage_search (src/quantization.rs:151-193) for a batch, wired as
+ * docs/architecture.md:355-372 describes: quantise the query, 1-bit Hamming scan over all
+ * live rows, keep the top `rescore_count` by (hamming asc, row asc) [= the stable sort of
+ * :175], exact f32 cosine of those [:181-187, :206-216], order by (cosine desc, hamming
+ * asc, row asc) [= the stable sort of :190] and return the first k (k <= rescore_count;
+ * the reference returns all rescore_count, i.e. k == rescore_count).
+ *   queries        nq x dim f32
+ *   ids_out        nq x k   u64 GLOBAL row numbers (row_base + local), GVDB_NO_ID if unfilled
+ *   scores_out     nq x k   f32 cosine similarity, -inf if unfilled
+ *   cand_ids_out   optional nq x rescore_count u64: the stage-1 candidate list in order
+ *   cand_ham_out   optional nq x rescore_count u32: their Hamming distances (UINT32_MAX unfilled)
+ * Host-pointer form: copies inside, results ready on return. */
+GVDB_API gvdb_status gvdb_search_batch(gvdb_index* h, const float* queries, uint32_t nq, uint32_t k,
+                              uint32_t rescore_count, uint64_t* ids_out, float* scores_out,
+                              uint64_t* cand_ids_out, uint32_t* cand_ham_out);
+/* Device-pointer form: every pointer is DEVICE memory on h's GPU; kernels are enqueued on
+ * `stream`; the call returns after the stream has been checked for candidate-buffer
+ * overflow (one 4-byte read-back), so results are complete on return. */
+GVDB_API gvdb_status gvdb_search_batch_device(gvdb_index* h, void* stream, const float* queries_dev,
+                                     uint32_t nq, uint32_t k, uint32_t rescore_count,
+                                     uint64_t* ids_out_dev, float* scores_out_dev,
+                                     uint64_t* cand_ids_out_dev, uint32_t* cand_ham_out_dev);
+
+/* ---- exact flat search (re-entrant) ------------------------------------------------- */
+/* FaissVectorIndex::search (src/index.rs:620-640) + cosine_distance (:686-700) for a batch:
+ * distance = 1 - cos (+inf on a zero norm) over all live rows, ascending, ties by row.
+ *   ids_out nq x k (GVDB_NO_ID unfilled), dist_out nq x k (+inf unfilled). */
+GVDB_API gvdb_status gvdb_flat_search_batch(gvdb_index* h, const float* queries, uint32_t nq, uint32_t k,
+                                   uint64_t* ids_out, float* dist_out);
+GVDB_API gvdb_status gvdb_flat_search_batch_device(gvdb_index* h, void* stream, const float* queries_dev,
+                                          uint32_t nq, uint32_t k, uint64_t* ids_out_dev,
+                                          float* dist_out_dev);
+
+/* ---- row-sharded search: the two halves around the exchange step -------------------- */
+/* Replaces the scatter side of ShardManager::search_vectors (src/distributed/shard.rs:760-775).
+ * Local stage 1 + stage 2 of this shard: writes, per query, this shard's top `rescore_count`
+ * records in (hamming asc, global row asc) order:
+ *   rec_ham nq x R u32 (UINT32_MAX unfilled), rec_ids nq x R u64 global (GVDB_NO_ID),
+ *   rec_score nq x R f32 cosine (-inf).  All DEVICE pointers. */
+GVDB_API gvdb_status gvdb_search_shard_device(gvdb_index* h, void* stream, const float* queries_dev,
+                                     uint32_t nq, uint32_t rescore_count, uint32_t* rec_ham_dev,
+                                     uint64_t* rec_ids_dev, float* rec_score_dev);
+/* Replaces the gather side (concat + sort + truncate, src/distributed/shard.rs:776-783) with the
+ * rule that reproduces the single-index result: over the n_shards x R gathered records of
+ * each query keep the global top R by (hamming, global row), then order by (cosine desc,
+ * hamming asc, row asc) and emit k.  Record arrays are laid out [shard][query][R] — exactly
+ * what an all-gather of the gvdb_search_shard_device outputs produces. */
+GVDB_API gvdb_status gvdb_merge_shards_device(gvdb_index* h, void* stream, uint32_t n_shards,
+                                     const uint32_t* rec_ham_dev, const uint64_t* rec_ids_dev,
+                                     const float* rec_score_dev, uint32_t nq,
+                                     uint32_t rescore_count, uint32_t k, uint64_t* ids_out_dev,
+                                     float* scores_out_dev);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GVDB_H */

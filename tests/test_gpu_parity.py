@@ -1,0 +1,251 @@
+"""GPU parity: the CUDA path, called through the C ABI, against the CPU oracle on identical
+seeded inputs.  Integer stages (codes, Hamming distances, candidate lists, top-k ids) must be
+bit-exact; rescored cosines are compared bit-for-bit as well (the kernels reproduce the
+reference's sequential f32 folds), which is stricter than the 1e-3 relative the north star asks."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from oracle import oracle  # noqa: E402
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.fixture(scope="module")
+def gv(built):
+    import grape_vector_db_b200 as g
+    return g
+
+
+def _bits(a):
+    return np.ascontiguousarray(a, dtype=np.float32).view(np.uint32)
+
+
+def _check_two_stage(gv, rows, queries, R, k, threshold=0.0):
+    with gv.GpuIndex(rows.shape[1], threshold=threshold) as idx:
+        idx.add(rows)
+        ids, sc, ci, ch = idx.search_batch(queries, k, R, want_candidates=True)
+    codes = oracle.quantize_batch(rows, threshold)
+    for qi in range(queries.shape[0]):
+        oi, os_, oci, och = oracle.multi_stage_search(queries[qi], rows, R, threshold, codes=codes,
+                                                      want_candidates=True)
+        r = len(oi)
+        assert np.array_equal(ci[qi, :r], oci), f"stage-1 candidate ids differ (query {qi})"
+        assert np.array_equal(ch[qi, :r], och), f"stage-1 Hamming distances differ (query {qi})"
+        assert np.all(ci[qi, r:] == gv.NO_ID)
+        kk = min(k, r)
+        assert np.array_equal(ids[qi, :kk], oi[:kk]), f"top-k ids differ (query {qi})"
+        assert np.array_equal(_bits(sc[qi, :kk]), _bits(os_[:kk])), f"scores differ (query {qi})"
+        assert np.all(ids[qi, kk:] == gv.NO_ID) and np.all(np.isneginf(sc[qi, kk:]))
+
+
+def test_quantize_kats(gv):
+    with gv.GpuIndex(5) as idx:
+        assert idx.quantize([0.5, -0.3, 0.8, -0.1, 0.2]).tolist() == [0xA8]
+    with gv.GpuIndex(4) as idx:
+        a = idx.quantize([1.0, -1.0, 1.0, -1.0])
+        b = idx.quantize([1.0, 1.0, -1.0, -1.0])
+        assert a.tolist() == [0xA0] and b.tolist() == [0xC0]
+        idx.add(np.array([[1.0, 1.0, -1.0, -1.0]], dtype=np.float32))
+        assert idx.hamming(a).tolist() == [[2]]
+    with gv.GpuIndex(8) as idx:
+        x = np.array([0.0, -0.0, np.nan, 1e-45, -1e-45, np.inf, -np.inf, 0.5], dtype=np.float32)
+        assert idx.quantize(x).tolist() == [0b00010101]
+    with gv.GpuIndex(13) as idx:
+        assert idx.quantize(np.ones(13, dtype=np.float32)).tolist() == [0xFF, 0xF8]
+
+
+@pytest.mark.parametrize("dim", [5, 64, 100, 128, 384, 768, 1000, 1536, 3072])
+def test_codes_and_hamming_bit_exact(gv, dim):
+    from grape_vector_db_b200 import synth
+    n, nq = 1234, 7
+    rows = synth.iid_rows(0, n, dim)
+    rows[5] = 0.0
+    rows[6, ::2] = np.nan
+    qs = synth.iid_queries(0, nq, dim)
+    for thr in (0.0, 37.0):
+        with gv.GpuIndex(dim, threshold=thr) as idx:
+            idx.add(rows[:1000])
+            idx.add(rows[1000:])           # second add starts mid-tile (1000 % 32 != 0)
+            want = oracle.quantize_batch(rows, thr)
+            assert np.array_equal(idx.get_codes(), want)
+            assert np.array_equal(idx.quantize(rows), want)
+            qc = oracle.quantize_batch(qs, thr)
+            got = idx.hamming(qc)
+            for qi in range(nq):
+                assert np.array_equal(got[qi], oracle.hamming_all(qc[qi], want))
+
+
+def test_c1_binary_quantization_demo_config(gv):
+    """BASELINE config 1: 10k x 768, ratio 0.1 -> R = 1000, k = 10 (and the full R list)."""
+    from grape_vector_db_b200 import synth
+    rows = synth.lowrank_rows(0, 10_000, 768)
+    qs = synth.lowrank_queries(0, 100, 768)
+    R = oracle.rescore_count(10_000, 0.1)
+    assert R == 1000
+    _check_two_stage(gv, rows, qs[:24], R, 10)
+    _check_two_stage(gv, rows, qs[24:32], R, R)          # reference returns all R
+
+
+def test_iid_dataset_and_ties(gv):
+    from grape_vector_db_b200 import synth
+    rows = synth.iid_rows(0, 6000, 768)
+    qs = synth.iid_queries(0, 16, 768)
+    _check_two_stage(gv, rows, qs, 40, 10)
+    # tiny alphabet: massive Hamming AND cosine ties -> exercises both tie-break rules
+    rng = np.random.default_rng(3)
+    rows = rng.integers(-1, 2, size=(5000, 24)).astype(np.float32)
+    qs = rng.integers(-1, 2, size=(9, 24)).astype(np.float32)
+    _check_two_stage(gv, rows, qs, 64, 64)
+    _check_two_stage(gv, rows, qs, 300, 17)
+
+
+def test_segmented_scan_larger_corpus(gv):
+    """Enough rows for several geometric scan segments (4096 -> 209k -> ...)."""
+    from grape_vector_db_b200 import synth
+    rows = synth.lowrank_rows(0, 300_000, 128)
+    qs = synth.lowrank_queries(0, 12, 128)
+    _check_two_stage(gv, rows, qs, 40, 10)
+    _check_two_stage(gv, rows, qs[:4], 1000, 10)
+
+
+def test_ragged_and_degenerate_shapes(gv):
+    from grape_vector_db_b200 import synth
+    rows = synth.lowrank_rows(0, 50, 96)
+    qs = synth.lowrank_queries(0, 3, 96)
+    _check_two_stage(gv, rows, qs, 40, 10)
+    _check_two_stage(gv, rows, qs, 64, 64)               # R > N: everything comes back
+    _check_two_stage(gv, rows[:1], qs, 1, 1)
+    z = rows.copy()
+    z[3] = 0.0                                           # zero-norm candidate -> cosine 0.0
+    qz = qs.copy()
+    qz[1] = 0.0                                          # zero query
+    _check_two_stage(gv, z, qz, 50, 50)
+
+
+def test_errors(gv):
+    with gv.GpuIndex(16) as idx:
+        with pytest.raises(gv.IndexNotBuilt):
+            idx.search_batch(np.zeros((1, 16), np.float32), 1, 1)
+        with pytest.raises(gv.DimensionMismatch):
+            idx.add(np.zeros((2, 15), np.float32))
+        idx.add(np.ones((4, 16), np.float32))
+        with pytest.raises(gv.ConfigError):
+            idx.search_batch(np.zeros((1, 16), np.float32), 5, 2)    # k > R
+        with pytest.raises(gv.DimensionMismatch):
+            idx.search_batch(np.zeros((1, 8), np.float32), 1, 1)
+
+
+def test_tombstones_and_clear(gv):
+    from grape_vector_db_b200 import synth
+    rows = synth.lowrank_rows(0, 3000, 64)
+    qs = synth.lowrank_queries(0, 5, 64)
+    dead = [0, 17, 31, 32, 999, 2999]
+    with gv.GpuIndex(64) as idx:
+        idx.add(rows)
+        for d in dead:
+            assert idx.remove(d) is True
+        assert idx.remove(17) is False and idx.remove(10**6) is False
+        assert len(idx) == 3000 - len(dead) and idx.rows == 3000
+        ids, sc = idx.search_batch(qs, 10, 40)
+        fids, fd = idx.flat_search_batch(qs, 10)
+        live = np.ones(3000, dtype=bool)
+        live[dead] = False
+        kept = np.flatnonzero(live)
+        oi, os_ = oracle.multi_stage_search_batch(qs, rows[live], 40, 10)
+        assert np.array_equal(ids, kept[oi.astype(np.int64)].astype(np.uint64))
+        assert np.array_equal(_bits(sc), _bits(os_))
+        ofi, ofd = oracle.flat_search_batch(qs, rows, 10, live=live.astype(np.uint8))
+        assert np.array_equal(fids, ofi) and np.array_equal(_bits(fd), _bits(ofd))
+        idx.clear()
+        assert len(idx) == 0
+        with pytest.raises(gv.IndexNotBuilt):
+            idx.search_batch(qs, 1, 1)
+        idx.add(rows[:100])
+        ids, _ = idx.search_batch(qs, 5, 10)
+        oi, _ = oracle.multi_stage_search_batch(qs, rows[:100], 10, 5)
+        assert np.array_equal(ids, oi)
+
+
+@pytest.mark.parametrize("dim", [24, 100, 768])
+def test_flat_search_bit_exact(gv, dim):
+    from grape_vector_db_b200 import synth
+    rows = synth.iid_rows(0, 9000, dim)
+    rows[11] = 0.0
+    qs = synth.iid_queries(0, 70, dim)
+    qs[2] = 0.0
+    with gv.GpuIndex(dim) as idx:
+        idx.add(rows)
+        ids, ds = idx.flat_search_batch(qs, 10)
+        ids2, ds2 = idx.flat_search_batch(qs[:3], 300)
+    oi, od = oracle.flat_search_batch(qs, rows, 10, nthreads=8)
+    assert np.array_equal(ids, oi) and np.array_equal(_bits(ds), _bits(od))
+    oi, od = oracle.flat_search_batch(qs[:3], rows, 300, nthreads=3)
+    assert np.array_equal(ids2, oi) and np.array_equal(_bits(ds2), _bits(od))
+
+
+def test_golden_fixture(gv):
+    from grape_vector_db_b200 import synth
+    g = json.load(open(os.path.join(GOLDEN, "kat_small.json")))
+    for case in g["cases"]:
+        gen = synth.lowrank_rows if case["dataset"] == "lowrank" else synth.iid_rows
+        genq = synth.lowrank_queries if case["dataset"] == "lowrank" else synth.iid_queries
+        rows, qs = gen(0, case["n"], case["dim"]), genq(0, case["nq"], case["dim"])
+        with gv.GpuIndex(case["dim"]) as idx:
+            idx.add(rows)
+            assert [int(x) for x in idx.get_codes(0, 4).ravel()[:32]] == case["codes_head"]
+            ids, sc = idx.search_batch(qs, case["k"], case["R"])
+        assert ids.tolist() == case["ids"]
+        assert _bits(sc).tolist() == case["score_bits"]
+
+
+def test_device_api_and_row_base(gv):
+    import torch
+    from grape_vector_db_b200 import synth
+    dev = torch.device("cuda:0")
+    rows_t = synth.lowrank_rows_torch(0, 40_000, 768, dev)
+    qs_t = synth.lowrank_queries_torch(0, 33, 768, dev)
+    rows, qs = rows_t.cpu().numpy(), qs_t.cpu().numpy()
+    assert np.array_equal(rows, synth.lowrank_rows(0, 40_000, 768))   # generator: GPU == host
+    with gv.GpuIndex(768, row_base=1_000_000) as idx:
+        idx.add_device(rows_t[:25_000])
+        idx.add_device(rows_t[25_000:])
+        ids, sc = idx.search_batch_device(qs_t, 10, 40)
+        torch.cuda.synchronize()
+        oi, os_ = oracle.multi_stage_search_batch(qs, rows, 40, 10, nthreads=8)
+        assert np.array_equal(ids.cpu().numpy().astype(np.uint64), oi + np.uint64(1_000_000))
+        assert np.array_equal(_bits(sc.cpu().numpy()), _bits(os_))
+
+
+def test_logical_shards_merge_equals_single_index(gv):
+    """S logical shards on ONE GPU + the merge kernel == the single-index result."""
+    import torch
+    from grape_vector_db_b200 import synth
+    dev = torch.device("cuda:0")
+    n, dim, nq, R, k = 30_000, 256, 20, 40, 10
+    rows = synth.lowrank_rows(0, n, dim)
+    qs = synth.lowrank_queries(0, nq, dim)
+    qs_t = torch.from_numpy(qs).to(dev)
+    oi, os_ = oracle.multi_stage_search_batch(qs, rows, R, k, nthreads=8)
+    for S in (1, 3, 8):
+        bounds = [(s * ((n + S - 1) // S), min(n, (s + 1) * ((n + S - 1) // S))) for s in range(S)]
+        shards = []
+        recs = []
+        for lo, hi in bounds:
+            ix = gv.GpuIndex(dim, row_base=lo)
+            ix.add(rows[lo:hi])
+            shards.append(ix)
+            recs.append(ix.search_shard_device(qs_t, R))
+        ham = torch.stack([r[0] for r in recs]).contiguous()
+        ids = torch.stack([r[1] for r in recs]).contiguous()
+        sc = torch.stack([r[2] for r in recs]).contiguous()
+        mi, ms = shards[0].merge_shards_device(ham, ids, sc, k)
+        torch.cuda.synchronize()
+        assert np.array_equal(mi.cpu().numpy().astype(np.uint64), oi), f"S={S}"
+        assert np.array_equal(_bits(ms.cpu().numpy()), _bits(os_)), f"S={S}"
+        for ix in shards:
+            ix.close()
