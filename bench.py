@@ -1,0 +1,370 @@
+#!/usr/bin/env python
+"""bench.py — QPS of the quantized two-stage search (BASELINE.json configs[1]):
+1M x 768 f32 corpus, 1-bit Hamming scan -> top R = k*oversample candidates -> exact f32
+cosine rescoring -> top-10, batches of 1024 queries, on N B200s (corpus row-sharded,
+one all-gather + merge per batch when N > 1).
+
+  python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+  python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU algorithm
+                                                            # (oracle port) on the host cores
+
+A "step" is one pass of the hot path over one batch of 1024 synthetic queries.
+  value     whole-job QPS, queries already resident in HBM, CUDA events, max over ranks
+  e2e       same metric through the C ABI with HOST buffers (pinned): H2D of the queries and
+            D2H of the results inside the timed region
+  roofline  the dominant kernel (scan_kernel) inside the timed steps, from per-launch CUDA
+            events recorded by the library on the launching stream
+  roofline_stream  the same kernel at its HBM-bound operating point (2 queries per corpus
+            pass over a larger-than-L2 corpus) — the "scan GB/s vs HBM peak" half of the metric
+  cpu_baseline  the oracle port of the reference algorithm timed on the host cores (N=1, rank 0)
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "QPS at recall@10>=0.95 (1M x 768, batch 1024, top-10, 1-bit scan + f32 rerank)"
+UNIT = "queries/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--rows", type=int, default=1_000_000)
+    ap.add_argument("--dim", type=int, default=768)
+    ap.add_argument("--batch", type=int, default=1024)
+    ap.add_argument("--k", type=int, default=10)
+    ap.add_argument("--oversample", type=int, default=4)
+    ap.add_argument("--stream-rows", type=int, default=8_000_000,
+                    help="rows of the larger-than-L2 corpus used for roofline_stream (0 = skip)")
+    ap.add_argument("--cpu-sample", type=int, default=128, help="queries timed on the CPU baseline")
+    ap.add_argument("--recall-queries", type=int, default=64)
+    ap.add_argument("--no-cpu", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("hbm_gbs", 6650.0), "measured (MEASURED_PEAKS.json)", d.get("sm_max_mhz", 1965.0)
+    return 6650.0, "fallback (B200_PROFILING.md)", 1965.0
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-i", str(self.gpu), "-lms", "100"], stdout=self.f,
+                                      stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self) -> dict:
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        for line in self.f.read().strip().splitlines():
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1])); mx.append(float(c[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.f.name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# =============================================================================================
+def run_reference(args, rank, world):
+    """The reference's own CPU algorithm for the path (oracle port: the Rust crate cannot be
+    built here), all host threads, on a bounded sample of the same workload per step."""
+    if rank != 0:
+        return
+    from grape_vector_db_b200 import synth
+    from oracle import oracle
+    n, dim, k, R = args.rows, args.dim, args.k, args.k * args.oversample
+    threads = oracle.hardware_threads()
+    sample = max(threads, min(args.cpu_sample, args.batch))
+    rows = np.concatenate([synth.lowrank_rows(i, min(100_000, n - i), dim) for i in range(0, n, 100_000)])
+    codes = oracle.quantize_batch(rows)
+    qs = synth.lowrank_queries(0, sample * (args.steps + args.warmup), dim)
+    for w in range(args.warmup):
+        oracle.multi_stage_search_batch(qs[w * sample:(w + 1) * sample], rows, R, k, codes=codes, nthreads=threads)
+    t0 = time.perf_counter()
+    for s in range(args.steps):
+        b = (args.warmup + s) * sample
+        oracle.multi_stage_search_batch(qs[b:b + sample], rows, R, k, codes=codes, nthreads=threads)
+    dt = time.perf_counter() - t0
+    qps = sample * args.steps / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": qps, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u32 popcount + f32",
+        "data": "synthetic", "gpu_launches": 0,
+        "config": workload_config(args, 1) | {"sample": f"{sample} queries per step (bounded sample of the {args.batch}-query batch)"},
+        "cpu_baseline": {"value": qps, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"{sample} queries/step x {args.steps} steps, full {n}x{dim} corpus, faithful full stable sort"},
+        "e2e": {"value": qps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, world):
+    return {"workload": f"configs[1]: {args.rows}x{args.dim} binary-quantized scan + fp32 cosine rerank, "
+                        f"batch {args.batch}, top-{args.k}, oversample {args.oversample}x (R={args.k * args.oversample})",
+            "rows": args.rows, "dim": args.dim, "batch": args.batch, "k": args.k,
+            "rescore_count": args.k * args.oversample, "dataset": "lowrank L=16 integer-exact, seed 42",
+            "parallelism": f"row-shard x{world}" if world > 1 else "single shard",
+            "l2": "256 MB L2 flush between timed steps"}
+
+
+def build_index(gv, synth, torch, dev, lo, hi, dim, chunk=131072):
+    idx = gv.GpuIndex(dim, device=dev.index, capacity_rows=hi - lo, row_base=lo)
+    for i in range(lo, hi, chunk):
+        m = min(chunk, hi - i)
+        idx.add_device(synth.lowrank_rows_torch(i, m, dim, dev))
+    return idx
+
+
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    import grape_vector_db_b200 as gv
+    from grape_vector_db_b200 import dist as gdist
+    from grape_vector_db_b200 import synth
+
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    n, dim, k, R, B = args.rows, args.dim, args.k, args.k * args.oversample, args.batch
+    K, W = args.steps, args.warmup
+    hbm_peak, peak_src, sm_max = peaks()
+
+    lo, hi = gdist.shard_bounds(n, world, rank)
+    index = build_index(gv, synth, torch, dev, lo, hi, dim)
+    searcher = gdist.ShardedSearcher(index)
+    NB = 4
+    q_dev = [synth.lowrank_queries_torch(b * B, B, dim, dev) for b in range(NB)]
+    q_pin = [torch.empty((B, dim), dtype=torch.float32).pin_memory() for _ in range(NB)]
+    for a, b in zip(q_pin, q_dev):
+        a.copy_(b)
+    ids_out = torch.empty((B, k), dtype=torch.int64, device=dev)
+    sc_out = torch.empty((B, k), dtype=torch.float32, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    def maxr(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- device-resident timing ---------------------------------------------------------
+    for w in range(W):
+        searcher.search_batch_device(q_dev[w % NB], k, R, ids_out, sc_out)
+    torch.cuda.synchronize()
+    index.profile_read(reset=True)
+    index.profile_enable(True)
+    clocks = ClockSampler(local_rank)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    barrier(); torch.cuda.synchronize()
+    clocks.start()
+    wall0 = time.perf_counter()
+    for s in range(K):
+        flush.zero_()                                  # evict the codes from L2 (not timed)
+        ev[s][0].record()
+        searcher.search_batch_device(q_dev[s % NB], k, R, ids_out, sc_out)
+        ev[s][1].record()
+    torch.cuda.synchronize(); barrier()
+    wall = time.perf_counter() - wall0
+    clk = clocks.stop()
+    prof = index.profile_read(reset=True)
+    index.profile_enable(False)
+    dev_ms = sum(a.elapsed_time(b) for a, b in ev)
+    dev_ms = maxr(dev_ms)
+    value = B * K / (dev_ms * 1e-3)
+    last_ids = ids_out.cpu().numpy().astype(np.uint64)
+    last_sc = sc_out.cpu().numpy()
+    last_batch = (K - 1) % NB
+
+    # ---- end-to-end through the host-pointer C ABI ------------------------------------------
+    def e2e_step(b):
+        if world == 1:
+            return index.search_batch(q_pin[b].numpy(), k, R)          # gvdb_search_batch: H2D + D2H inside
+        qd = q_pin[b].to(dev, non_blocking=True)
+        i_, s_ = searcher.search_batch_device(qd, k, R, ids_out, sc_out)
+        return i_.cpu(), s_.cpu()
+    for w in range(max(1, W)):
+        e2e_step(w % NB)
+    barrier(); torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for s in range(K):
+        e2e_step(s % NB)
+    torch.cuda.synchronize(); barrier()
+    e2e_s = maxr(time.perf_counter() - t0)
+    e2e = {"value": B * K / e2e_s, "unit": UNIT, "h2d_bytes_per_step": B * dim * 4,
+           "d2h_bytes_per_step": B * k * 12, "ms_per_step": 1e3 * e2e_s / K,
+           "api": "gvdb_search_batch (host pointers, pinned)" if world == 1 else
+                  "pinned H2D + gvdb_search_shard_device + NCCL all-gather + gvdb_merge_shards_device + D2H"}
+
+    # ---- roofline of the dominant kernel inside the timed steps ---------------------------------
+    scan_ms_per_launch = prof["scan_ms"] / max(1, prof["scan_launches"])
+    step_kernel_ms = sum(prof[x] for x in ("scan_ms", "select_ms", "rescore_ms", "topk_ms", "prep_ms", "merge_ms"))
+    achieved = prof["scan_bytes"] / (prof["scan_ms"] * 1e-3) / 1e9 if prof["scan_ms"] > 0 else 0.0
+    sm_mhz = clk.get("sm_mhz") or sm_max
+    popc_rate = prof["scan_pairs"] * index.stats()["code_bytes_per_row"] / 4.0 / (prof["scan_ms"] * 1e-3) if prof["scan_ms"] > 0 else 0.0
+    roofline = {
+        "kernel": "scan_kernel<NCHUNK=%d,MODE=0>" % (index.stats()["code_bytes_per_row"] // 16),
+        "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+        "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+        "launches": int(prof["scan_launches"]), "ms_per_launch": scan_ms_per_launch,
+        "share_of_step_kernel_time": prof["scan_ms"] / step_kernel_ms if step_kernel_ms else None,
+        "algorithmic_bytes_per_step": prof["scan_bytes"] / K,
+        "note": ("at batch 1024 one corpus pass serves 128 queries, so this kernel is bound by the "
+                 "integer popc pipe, not HBM; popc issue rate below. The HBM-bound operating point "
+                 "(2 queries per pass) is roofline_stream."),
+        "popc_per_s": popc_rate,
+        "popc_pipe_frac_at_16_per_clk_per_sm": popc_rate / (148 * 16 * sm_mhz * 1e6),
+        "stage_ms_per_step": {x: prof[x] / K for x in ("prep_ms", "scan_ms", "select_ms", "rescore_ms", "topk_ms", "merge_ms")},
+    }
+
+    # ---- parity + recall + CPU baseline (rank 0, N=1) --------------------------------------------
+    extra = {}
+    cpu_baseline = None
+    if world == 1:
+        # recall@10 against the exact f32 flat search (GPU, bit-exact FaissVectorIndex semantics)
+        nr = min(args.recall_queries, B)
+        fid, _ = index.flat_search_batch_device(q_dev[last_batch][:nr].contiguous(), k)
+        fid = fid.cpu().numpy().astype(np.uint64)
+        extra["recall_at_10"] = float(np.mean([len(set(last_ids[i]) & set(fid[i])) / k for i in range(nr)]))
+        extra["recall_queries"] = nr
+        if not args.no_cpu:
+            from oracle import oracle
+            threads = oracle.hardware_threads()
+            rows = np.concatenate([synth.lowrank_rows_torch(i, min(131072, n - i), dim, dev).cpu().numpy()
+                                   for i in range(0, n, 131072)])
+            codes = oracle.quantize_batch(rows)
+            ns = min(args.cpu_sample, B)
+            qs = q_pin[last_batch].numpy()[:ns]
+            t0 = time.perf_counter()
+            oi, os_ = oracle.multi_stage_search_batch(qs, rows, R, k, codes=codes, nthreads=threads)
+            dt = time.perf_counter() - t0
+            extra["parity"] = {
+                "checked_queries": ns,
+                "topk_ids_bit_exact": bool(np.array_equal(oi, last_ids[:ns])),
+                "scores_bit_exact": bool(np.array_equal(os_.view(np.uint32), last_sc[:ns].view(np.uint32))),
+            }
+            cpu_baseline = {"value": ns / dt, "unit": UNIT, "cores": threads, "kind": "port",
+                            "sample": f"{ns} queries of the timed batch on the full {n}x{dim} corpus, "
+                                      "oracle port of multi_stage_search (full stable sort), one query per thread"}
+            t0 = time.perf_counter()
+            oracle.multi_stage_search_batch(qs, rows, R, k, codes=codes, nthreads=threads, select=True)
+            extra["cpu_baseline_select_variant_qps"] = ns / (time.perf_counter() - t0)
+            del rows, codes
+
+    # ---- the same kernel at its HBM-bound operating point -------------------------------------------
+    roofline_stream = None
+    if world == 1 and args.stream_rows > 0:
+        del index, searcher
+        torch.cuda.empty_cache()
+        big = build_index(gv, synth, torch, dev, 0, args.stream_rows, dim)
+        code_bytes = args.stream_rows * big.stats()["code_bytes_per_row"]
+        out = {}
+        for T in (1, 2, 4):
+            qd = q_dev[0][:T].contiguous()
+            for _ in range(3):
+                big.search_batch_device(qd, k, R)
+            big.profile_read(reset=True); big.profile_enable(True)
+            reps = 20
+            for _ in range(reps):
+                big.search_batch_device(qd, k, R)
+            p = big.profile_read(reset=True); big.profile_enable(False)
+            gbps = p["scan_bytes"] / (p["scan_ms"] * 1e-3) / 1e9
+            out[f"T{T}"] = {"achieved": gbps, "frac": gbps / hbm_peak, "scan_ms_per_pass": p["scan_ms"] / reps,
+                            "launches_per_pass": p["scan_launches"] / reps}
+        best = max(out.values(), key=lambda d: d["achieved"])
+        roofline_stream = {"kernel": roofline["kernel"], "bound": "hbm", "achieved": best["achieved"],
+                           "peak": hbm_peak, "unit": "GB/s", "frac": best["frac"], "traffic": None,
+                           "peak_source": peak_src, "rows": args.stream_rows, "code_bytes": code_bytes,
+                           "l2": "codes (%.0f MB) exceed the 126 MB L2" % (code_bytes / 1e6),
+                           "by_queries_per_pass": out}
+        big.close()
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "u32 xor+popc (scan), f32 (rescoring)", "data": "synthetic",
+            "config": workload_config(args, world), "clocks": clk,
+            "e2e": e2e, "gpu_launches": int(prof["launches"]),
+            "roofline": roofline, "roofline_stream": roofline_stream, "cpu_baseline": cpu_baseline,
+            "wall_s_timed_region": wall,
+        }
+        line.update(extra)
+        print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    try:
+        run_ours(args, rank, world, local_rank)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -33,6 +33,13 @@ class GvdbStats(C.Structure):
                 ("code_bytes_per_row", C.c_uint64)]
 
 
+class GvdbProfile(C.Structure):
+    _fields_ = [("launches", C.c_uint64), ("scan_launches", C.c_uint64), ("scan_ms", C.c_double),
+                ("scan_bytes", C.c_double), ("scan_pairs", C.c_double), ("select_ms", C.c_double),
+                ("rescore_ms", C.c_double), ("topk_ms", C.c_double), ("prep_ms", C.c_double),
+                ("flat_ms", C.c_double), ("merge_ms", C.c_double)]
+
+
 # every symbol include/gvdb.h declares: name -> (restype, argtypes)
 _vp, _u32, _u64, _i32 = C.c_void_p, C.c_uint32, C.c_uint64, C.c_int32
 SYMBOLS = {
@@ -55,8 +62,11 @@ SYMBOLS = {
     "gvdb_search_batch_device": (_i32, [_vp, _vp, _vp, _u32, _u32, _u32, _vp, _vp, _vp, _vp]),
     "gvdb_flat_search_batch": (_i32, [_vp, _vp, _u32, _u32, _vp, _vp]),
     "gvdb_flat_search_batch_device": (_i32, [_vp, _vp, _vp, _u32, _u32, _vp, _vp]),
-    "gvdb_search_shard_device": (_i32, [_vp, _vp, _vp, _u32, _u32, _vp, _vp, _vp]),
-    "gvdb_merge_shards_device": (_i32, [_vp, _vp, _u32, _vp, _vp, _vp, _u32, _u32, _u32, _vp, _vp]),
+    "gvdb_shard_record_bytes": (_u64, [_u32, _u32]),
+    "gvdb_search_shard_device": (_i32, [_vp, _vp, _vp, _u32, _u32, _vp]),
+    "gvdb_merge_shards_device": (_i32, [_vp, _vp, _u32, _vp, _u32, _u32, _u32, _vp, _vp]),
+    "gvdb_profile_enable": (_i32, [_vp, _i32]),
+    "gvdb_profile_read": (_i32, [_vp, _vp, _i32]),
 }
 
 _lib = None

@@ -14,6 +14,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -60,7 +61,25 @@ struct DevBuf {
     template <class T> T* as() const { return reinterpret_cast<T*>(p); }
 };
 
+enum Kind { K_SCAN = 0, K_SELECT, K_RESCORE, K_TOPK, K_PREP, K_FLAT, K_MERGE, K_COUNT };
+struct ProfRec {
+    int kind;
+    cudaEvent_t e0, e1;
+    double bytes, pairs;
+};
+
 struct Workspace {
+    std::vector<cudaEvent_t> ev_pool;   // timing events, reused across calls
+    size_t ev_used = 0;
+    std::vector<ProfRec> recs;
+    cudaEvent_t next_event() {
+        if (ev_used == ev_pool.size()) {
+            cudaEvent_t e;
+            cudaEventCreate(&e);
+            ev_pool.push_back(e);
+        }
+        return ev_pool[ev_used++];
+    }
     cudaStream_t stream = nullptr;   // used by the host-pointer entry points
     cudaEvent_t idle = nullptr;      // recorded after the last kernel that touched the buffers
     bool used = false;
@@ -71,6 +90,7 @@ struct Workspace {
         for (DevBuf* b : {&qpack, &qnorm, &cnt, &flag, &buf, &rec_ham, &rec_ids, &rec_score, &q_in,
                           &ids_out, &sc_out, &codes_tmp, &misc}) b->release();
         if (h_flag) cudaFreeHost(h_flag);
+        for (cudaEvent_t e : ev_pool) cudaEventDestroy(e);
         if (idle) cudaEventDestroy(idle);
         if (stream) cudaStreamDestroy(stream);
     }
@@ -93,6 +113,10 @@ struct gvdb_index {
     std::vector<std::unique_ptr<Workspace>> pool;
     uint32_t query_tile = 1024;
     int scan_ctas_per_sm = 16;
+    std::atomic<int> profile_on{0};
+    std::atomic<uint64_t> launches{0};
+    std::mutex prof_mu;
+    gvdb_profile prof{};
 };
 
 namespace {
@@ -105,6 +129,47 @@ struct DeviceGuard {
     }
     ~DeviceGuard() { cudaSetDevice(prev); }
 };
+
+// Brackets one kernel launch with events (only when profiling is on) and counts it.
+struct Timed {
+    Workspace* ws; cudaStream_t st; bool on; ProfRec rec;
+    Timed(gvdb_index* h, Workspace* ws_, cudaStream_t st_, int kind, double bytes = 0, double pairs = 0)
+        : ws(ws_), st(st_), on(h->profile_on.load(std::memory_order_relaxed) != 0) {
+        h->launches.fetch_add(1, std::memory_order_relaxed);
+        if (on) {
+            rec = ProfRec{kind, ws->next_event(), ws->next_event(), bytes, pairs};
+            cudaEventRecord(rec.e0, st);
+        }
+    }
+    ~Timed() {
+        if (on) {
+            cudaEventRecord(rec.e1, st);
+            ws->recs.push_back(rec);
+        }
+    }
+};
+
+// Call after the stream has been synchronised.
+void flush_profile(gvdb_index* h, Workspace* ws) {
+    if (ws->recs.empty()) { ws->ev_used = 0; return; }
+    std::lock_guard<std::mutex> lk(h->prof_mu);
+    for (const ProfRec& r : ws->recs) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, r.e0, r.e1) != cudaSuccess) continue;
+        switch (r.kind) {
+            case K_SCAN: h->prof.scan_ms += ms; h->prof.scan_launches += 1;
+                         h->prof.scan_bytes += r.bytes; h->prof.scan_pairs += r.pairs; break;
+            case K_SELECT: h->prof.select_ms += ms; break;
+            case K_RESCORE: h->prof.rescore_ms += ms; break;
+            case K_TOPK: h->prof.topk_ms += ms; break;
+            case K_PREP: h->prof.prep_ms += ms; break;
+            case K_FLAT: h->prof.flat_ms += ms; break;
+            case K_MERGE: h->prof.merge_ms += ms; break;
+        }
+    }
+    ws->recs.clear();
+    ws->ev_used = 0;
+}
 
 struct WsLease {
     gvdb_index* h;
@@ -237,9 +302,12 @@ void search_core(gvdb_index* h, Workspace* ws, cudaStream_t st, const float* que
     const uint32_t g = std::max<uint32_t>(2, cap / (4 * R));
     for (uint32_t qt0 = 0; qt0 < nq; qt0 += QT) {
         const uint32_t nqt = std::min(QT, nq - qt0);
-        ingest_kernel<true><<<(nqt + STAGE_ROWS - 1) / STAGE_ROWS, STAGE_ROWS, 0, st>>>(
-            queries_dev + (size_t)qt0 * h->dim, nqt, h->dim, h->cfg.threshold, h->nchunk, 0, nullptr,
-            ws->qnorm.as<float>(), nullptr, ws->qpack.as<uint32_t>(), h->qs);
+        {
+            Timed t(h, ws, st, K_PREP);
+            ingest_kernel<true><<<(nqt + STAGE_ROWS - 1) / STAGE_ROWS, STAGE_ROWS, 0, st>>>(
+                queries_dev + (size_t)qt0 * h->dim, nqt, h->dim, h->cfg.threshold, h->nchunk, 0, nullptr,
+                ws->qnorm.as<float>(), nullptr, ws->qpack.as<uint32_t>(), h->qs);
+        }
         CU(cudaGetLastError());
         CU(cudaMemsetAsync(ws->cnt.p, 0, (size_t)nqt * 4, st));
         uint32_t lo = 0;
@@ -247,39 +315,53 @@ void search_core(gvdb_index* h, Workspace* ws, cudaStream_t st, const float* que
             uint64_t hi64 = lo == 0 ? seg0_tiles : (uint64_t)lo * g;
             uint32_t hi = (uint32_t)std::min<uint64_t>(hi64, ntiles);
             dim3 grid = scan_grid(h, hi - lo, nqt);
-            launch_scan<0>(h->nchunk, st, grid, (size_t)kQGroup * h->qs * 4, h->codes, h->live, lo, hi,
-                           ws->qpack.as<uint32_t>(), (int)nqt, kQGroup, ws->cnt.as<uint32_t>(),
-                           ws->buf.as<uint64_t>(), cap, ws->flag.as<uint32_t>(), nullptr, 0, h->n_rows);
-            select_kernel<<<nqt, SORT_THREADS, SORT_N * 8, st>>>(
-                ws->buf.as<uint64_t>(), cap, ws->cnt.as<uint32_t>(), R, ws->qpack.as<uint32_t>(),
-                h->qs, h->nchunk * 4);
+            {
+                const double seg_rows = (double)(hi - lo) * 32.0;
+                Timed t(h, ws, st, K_SCAN, seg_rows * h->nchunk * 16.0 * grid.y, seg_rows * nqt);
+                launch_scan<0>(h->nchunk, st, grid, (size_t)kQGroup * h->qs * 4, h->codes, h->live, lo, hi,
+                               ws->qpack.as<uint32_t>(), (int)nqt, kQGroup, ws->cnt.as<uint32_t>(),
+                               ws->buf.as<uint64_t>(), cap, ws->flag.as<uint32_t>(), nullptr, 0, h->n_rows);
+            }
+            {
+                Timed t(h, ws, st, K_SELECT);
+                select_kernel<<<nqt, SORT_THREADS, SORT_N * 8, st>>>(
+                    ws->buf.as<uint64_t>(), cap, ws->cnt.as<uint32_t>(), R, ws->qpack.as<uint32_t>(),
+                    h->qs, h->nchunk * 4);
+            }
             CU(cudaGetLastError());
             lo = hi;
         }
         const uint64_t pairs = (uint64_t)nqt * R;
-        rescore_kernel<<<(unsigned)((pairs + STAGE_ROWS - 1) / STAGE_ROWS), STAGE_ROWS, 0, st>>>(
-            h->rows, h->norms, h->cfg.row_base, h->dim, queries_dev + (size_t)qt0 * h->dim,
-            ws->qnorm.as<float>(), ws->buf.as<uint64_t>(), cap, ws->cnt.as<uint32_t>(), R, nqt,
-            rec_ham + (size_t)qt0 * R, rec_ids + (size_t)qt0 * R, rec_score + (size_t)qt0 * R);
+        {
+            Timed t(h, ws, st, K_RESCORE);
+            rescore_kernel<<<(unsigned)((pairs + STAGE_ROWS - 1) / STAGE_ROWS), STAGE_ROWS, 0, st>>>(
+                h->rows, h->norms, h->cfg.row_base, h->dim, queries_dev + (size_t)qt0 * h->dim,
+                ws->qnorm.as<float>(), ws->buf.as<uint64_t>(), cap, ws->cnt.as<uint32_t>(), R, nqt,
+                rec_ham + (size_t)qt0 * R, rec_ids + (size_t)qt0 * R, rec_score + (size_t)qt0 * R);
+        }
         CU(cudaGetLastError());
     }
 }
 
-void check_overflow(Workspace* ws, cudaStream_t st) {
+void check_overflow(gvdb_index* h, Workspace* ws, cudaStream_t st) {
     CU(cudaMemcpyAsync(ws->h_flag, ws->flag.p, 4, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
+    flush_profile(h, ws);
     if (ws->h_flag[0])
         fail(GVDB_ERR_INDEX,
              "candidate buffer overflow in the Hamming scan (heavily duplicated corpus?); "
              "the exact fallback is not implemented yet");
 }
 
-void launch_topk(cudaStream_t st, const uint64_t* rec_ids, const float* rec_score, uint32_t nq,
+void launch_topk(gvdb_index* h, Workspace* ws, cudaStream_t st, const uint64_t* rec_ids, const float* rec_score, uint32_t nq,
                  uint32_t R, uint32_t k, uint64_t* ids_out, float* scores_out) {
     uint32_t n_eff = 64;
     while (n_eff < R) n_eff <<= 1;
     uint32_t threads = std::min<uint32_t>(1024, std::max<uint32_t>(32, n_eff / 2));
-    topk_kernel<<<nq, threads, n_eff * 8, st>>>(rec_ids, rec_score, R, n_eff, k, ids_out, scores_out);
+    {
+        Timed t(h, ws, st, K_TOPK);
+        topk_kernel<<<nq, threads, n_eff * 8, st>>>(rec_ids, rec_score, R, n_eff, k, ids_out, scores_out);
+    }
     CU(cudaGetLastError());
 }
 
@@ -292,10 +374,10 @@ void search_device(gvdb_index* h, Workspace* ws, cudaStream_t st, const float* q
     ws->rec_score.ensure((size_t)nq * R * 4);
     search_core(h, ws, st, q_dev, nq, R, ws->rec_ham.as<uint32_t>(), ws->rec_ids.as<uint64_t>(),
                 ws->rec_score.as<float>());
-    launch_topk(st, ws->rec_ids.as<uint64_t>(), ws->rec_score.as<float>(), nq, R, k, ids_out, scores_out);
+    launch_topk(h, ws, st, ws->rec_ids.as<uint64_t>(), ws->rec_score.as<float>(), nq, R, k, ids_out, scores_out);
     if (cand_ids) CU(cudaMemcpyAsync(cand_ids, ws->rec_ids.p, (size_t)nq * R * 8, cudaMemcpyDeviceToDevice, st));
     if (cand_ham) CU(cudaMemcpyAsync(cand_ham, ws->rec_ham.p, (size_t)nq * R * 4, cudaMemcpyDeviceToDevice, st));
-    check_overflow(ws, st);
+    check_overflow(h, ws, st);
 }
 
 // Exact flat search: same segment/select machinery with key = image(1 - cos) << 32 | row.
@@ -319,9 +401,12 @@ void flat_device(gvdb_index* h, Workspace* ws, cudaStream_t st, const float* q_d
     for (uint32_t qt0 = 0; qt0 < nq; qt0 += QT) {
         const uint32_t nqt = std::min(QT, nq - qt0);
         const float* qd = q_dev + (size_t)qt0 * h->dim;
-        ingest_kernel<true><<<(nqt + STAGE_ROWS - 1) / STAGE_ROWS, STAGE_ROWS, 0, st>>>(
-            qd, nqt, h->dim, h->cfg.threshold, h->nchunk, 0, nullptr, ws->qnorm.as<float>(), nullptr,
-            ws->qpack.as<uint32_t>(), h->qs);
+        {
+            Timed t(h, ws, st, K_PREP);
+            ingest_kernel<true><<<(nqt + STAGE_ROWS - 1) / STAGE_ROWS, STAGE_ROWS, 0, st>>>(
+                qd, nqt, h->dim, h->cfg.threshold, h->nchunk, 0, nullptr, ws->qnorm.as<float>(), nullptr,
+                ws->qpack.as<uint32_t>(), h->qs);
+        }
         CU(cudaGetLastError());
         CU(cudaMemsetAsync(ws->cnt.p, 0, (size_t)nqt * 4, st));
         CU(cudaMemsetAsync(ws->misc.p, 0xff, (size_t)nqt * 4, st));   // TAU_ALL
@@ -329,22 +414,29 @@ void flat_device(gvdb_index* h, Workspace* ws, cudaStream_t st, const float* q_d
         while (lo < h->n_rows) {
             uint64_t hi = std::min<uint64_t>(lo == 0 ? seg0 : lo * g, h->n_rows);
             dim3 grid((unsigned)((hi - lo + FLAT_TM - 1) / FLAT_TM), (nqt + FLAT_TN - 1) / FLAT_TN, 1);
-            flat_scan_kernel<<<grid, FLAT_THREADS, 0, st>>>(
-                h->rows, h->norms, h->live, lo, hi, h->dim, qd, ws->qnorm.as<float>(), nqt,
-                ws->misc.as<uint32_t>(), ws->cnt.as<uint32_t>(), ws->buf.as<uint64_t>(), cap,
-                ws->flag.as<uint32_t>());
+            {
+                Timed t(h, ws, st, K_FLAT);
+                flat_scan_kernel<<<grid, FLAT_THREADS, 0, st>>>(
+                    h->rows, h->norms, h->live, lo, hi, h->dim, qd, ws->qnorm.as<float>(), nqt,
+                    ws->misc.as<uint32_t>(), ws->cnt.as<uint32_t>(), ws->buf.as<uint64_t>(), cap,
+                    ws->flag.as<uint32_t>());
+            }
             CU(cudaGetLastError());
-            select_kernel<<<nqt, SORT_THREADS, SORT_N * 8, st>>>(
-                ws->buf.as<uint64_t>(), cap, ws->cnt.as<uint32_t>(), k, ws->misc.as<uint32_t>(), 1, 0);
+            {
+                Timed t(h, ws, st, K_SELECT);
+                select_kernel<<<nqt, SORT_THREADS, SORT_N * 8, st>>>(
+                    ws->buf.as<uint64_t>(), cap, ws->cnt.as<uint32_t>(), k, ws->misc.as<uint32_t>(), 1, 0);
+            }
             CU(cudaGetLastError());
             lo = hi;
         }
+        h->launches.fetch_add(1, std::memory_order_relaxed);
         flat_emit_kernel<<<(nqt * k + 255) / 256, 256, 0, st>>>(
             ws->buf.as<uint64_t>(), cap, ws->cnt.as<uint32_t>(), nqt, k, h->cfg.row_base,
             ids_out + (size_t)qt0 * k, dist_out + (size_t)qt0 * k);
         CU(cudaGetLastError());
     }
-    check_overflow(ws, st);
+    check_overflow(h, ws, st);
 }
 
 void add_device_impl(gvdb_index* h, cudaStream_t st, const float* rows_dev, uint64_t n,
@@ -695,31 +787,34 @@ gvdb_status gvdb_flat_search_batch(gvdb_index* h, const float* queries, uint32_t
     });
 }
 
+uint64_t gvdb_shard_record_bytes(uint32_t nq, uint32_t rescore_count) {
+    return (uint64_t)nq * rescore_count * 16ull;
+}
+
 gvdb_status gvdb_search_shard_device(gvdb_index* h, void* stream, const float* queries_dev, uint32_t nq,
-                                     uint32_t rescore_count, uint32_t* rec_ham_dev,
-                                     uint64_t* rec_ids_dev, float* rec_score_dev) {
+                                     uint32_t rescore_count, void* records_dev) {
     return guarded([&] {
         need(h, "index");
         if (nq == 0) return;
-        need(queries_dev, "queries"); need(rec_ham_dev, "rec_ham"); need(rec_ids_dev, "rec_ids");
-        need(rec_score_dev, "rec_score");
+        need(queries_dev, "queries"); need(records_dev, "records");
         DeviceGuard dg(h->cfg.device);
         WsLease lease(h, (cudaStream_t)stream, true);
-        search_core(h, lease.ws, lease.stream, queries_dev, nq, rescore_count, rec_ham_dev, rec_ids_dev,
-                    rec_score_dev);
-        check_overflow(lease.ws, lease.stream);
+        const uint64_t nr = (uint64_t)nq * rescore_count;
+        uint8_t* base = static_cast<uint8_t*>(records_dev);
+        search_core(h, lease.ws, lease.stream, queries_dev, nq, rescore_count,
+                    reinterpret_cast<uint32_t*>(base + nr * 8), reinterpret_cast<uint64_t*>(base),
+                    reinterpret_cast<float*>(base + nr * 12));
+        check_overflow(h, lease.ws, lease.stream);
     });
 }
 
 gvdb_status gvdb_merge_shards_device(gvdb_index* h, void* stream, uint32_t n_shards,
-                                     const uint32_t* rec_ham_dev, const uint64_t* rec_ids_dev,
-                                     const float* rec_score_dev, uint32_t nq, uint32_t rescore_count,
+                                     const void* records_dev, uint32_t nq, uint32_t rescore_count,
                                      uint32_t k, uint64_t* ids_out_dev, float* scores_out_dev) {
     return guarded([&] {
         need(h, "index");
         if (nq == 0) return;
-        need(rec_ham_dev, "rec_ham"); need(rec_ids_dev, "rec_ids"); need(rec_score_dev, "rec_score");
-        need(ids_out_dev, "ids_out"); need(scores_out_dev, "scores_out");
+        need(records_dev, "records"); need(ids_out_dev, "ids_out"); need(scores_out_dev, "scores_out");
         const uint32_t R = rescore_count;
         if (R == 0 || R > kMaxR) fail(GVDB_ERR_INVALID_ARGUMENT, "rescore_count must be in [1, 2048]");
         if (k > R) fail(GVDB_ERR_INVALID_ARGUMENT, "k must be <= rescore_count");
@@ -731,12 +826,37 @@ gvdb_status gvdb_merge_shards_device(gvdb_index* h, void* stream, uint32_t n_sha
         ws->rec_ham.ensure((size_t)nq * R * 4);
         ws->rec_ids.ensure((size_t)nq * R * 8);
         ws->rec_score.ensure((size_t)nq * R * 4);
-        merge_select_kernel<<<nq, SORT_THREADS, SORT_N * 8, st>>>(
-            n_shards, rec_ham_dev, rec_ids_dev, rec_score_dev, nq, R, ws->rec_ids.as<uint64_t>(),
-            ws->rec_score.as<float>(), ws->rec_ham.as<uint32_t>());
+        ShardRecords rec{static_cast<const uint8_t*>(records_dev), gvdb_shard_record_bytes(nq, R), nq, R};
+        {
+            Timed t(h, ws, st, K_MERGE);
+            merge_select_kernel<<<nq, SORT_THREADS, SORT_N * 8, st>>>(
+                n_shards, rec, ws->rec_ids.as<uint64_t>(), ws->rec_score.as<float>(),
+                ws->rec_ham.as<uint32_t>());
+        }
         CU(cudaGetLastError());
-        launch_topk(st, ws->rec_ids.as<uint64_t>(), ws->rec_score.as<float>(), nq, R, k, ids_out_dev, scores_out_dev);
+        launch_topk(h, ws, st, ws->rec_ids.as<uint64_t>(), ws->rec_score.as<float>(), nq, R, k, ids_out_dev, scores_out_dev);
         CU(cudaStreamSynchronize(st));
+        flush_profile(h, ws);
+    });
+}
+
+gvdb_status gvdb_profile_enable(gvdb_index* h, int32_t on) {
+    return guarded([&] {
+        need(h, "index");
+        h->profile_on.store(on ? 1 : 0);
+    });
+}
+
+gvdb_status gvdb_profile_read(gvdb_index* h, gvdb_profile* out, int32_t reset) {
+    return guarded([&] {
+        need(h, "index"); need(out, "out");
+        std::lock_guard<std::mutex> lk(h->prof_mu);
+        h->prof.launches = h->launches.load();
+        *out = h->prof;
+        if (reset) {
+            h->prof = gvdb_profile{};
+            h->launches.store(0);
+        }
     });
 }
 

@@ -412,21 +412,34 @@ __global__ void topk_kernel(const uint64_t* __restrict__ rec_ids, const float* _
 }
 
 // ---------------------------------------------------------------------------------------
-// merge_select_kernel: one CTA per query over the gathered [shard][query][R] records.
+// merge_select_kernel: one CTA per query over the gathered shard records
+// (n_shards packed buffers back to back, each [ids u64 | ham u32 | score f32] x nq x R).
 // Keeps the global top R by (hamming, global row) — the stage-1 cut the single-index search
 // would have made — and writes them, in that order, as one merged record list per query.
-// Key = hamming << 40 | global row (rows < 2^40) ; payload (source slot) rides in a
-// parallel shared array addressed through the low bits, recovered by a second lookup.
+// Sort key = hamming << 40 | global row (rows < 2^40).  (hamming, row) is unique across
+// shards and every shard's list is sorted by it, so the score of a kept key is recovered by
+// a binary search in the shard lists instead of carrying a payload through the sort.
+struct ShardRecords {
+    const uint8_t* base;
+    uint64_t shard_bytes;
+    uint32_t nq, R;
+    __device__ __forceinline__ const uint64_t* ids(uint32_t s) const {
+        return reinterpret_cast<const uint64_t*>(base + s * shard_bytes);
+    }
+    __device__ __forceinline__ const uint32_t* ham(uint32_t s) const {
+        return reinterpret_cast<const uint32_t*>(base + s * shard_bytes + (uint64_t)nq * R * 8);
+    }
+    __device__ __forceinline__ const float* score(uint32_t s) const {
+        return reinterpret_cast<const float*>(base + s * shard_bytes + (uint64_t)nq * R * 12);
+    }
+};
+
 __global__ void __launch_bounds__(SORT_THREADS)
-merge_select_kernel(uint32_t n_shards, const uint32_t* __restrict__ rec_ham,
-                    const uint64_t* __restrict__ rec_ids, const float* __restrict__ rec_score,
-                    uint32_t nq, uint32_t R, uint64_t* __restrict__ out_ids,
+merge_select_kernel(uint32_t n_shards, ShardRecords rec, uint64_t* __restrict__ out_ids,
                     float* __restrict__ out_score, uint32_t* __restrict__ out_ham) {
-    // Sort keys carry (hamming, global row); the score is looked up again afterwards by
-    // binary-searching the source shard's (sorted) list — no payload array needed because
-    // (hamming, row) is unique across shards.
     extern __shared__ __align__(16) uint64_t skeys[];
     const uint32_t q = blockIdx.x;
+    const uint32_t R = rec.R;
     const uint32_t total_in = n_shards * R;
     uint32_t have = 0, consumed = 0;
     while (consumed < total_in) {
@@ -436,11 +449,11 @@ merge_select_kernel(uint32_t n_shards, const uint32_t* __restrict__ rec_ham,
         for (uint32_t i = threadIdx.x; i < n_eff - have; i += blockDim.x) {
             uint64_t key = UINT64_MAX;
             if (i < take) {
-                uint32_t src = consumed + i;
-                uint32_t s = src / R, r = src % R;
-                size_t at = ((size_t)s * nq + q) * R + r;
-                uint64_t id = rec_ids[at];
-                if (id != UINT64_MAX) key = ((uint64_t)rec_ham[at] << 40) | id;
+                const uint32_t src = consumed + i;
+                const uint32_t s = src / R, r = src % R;
+                const size_t at = (size_t)q * R + r;
+                const uint64_t id = rec.ids(s)[at];
+                if (id != UINT64_MAX) key = ((uint64_t)rec.ham(s)[at] << 40) | id;
             }
             skeys[have + i] = key;
         }
@@ -451,26 +464,26 @@ merge_select_kernel(uint32_t n_shards, const uint32_t* __restrict__ rec_ham,
     }
     __syncthreads();
     for (uint32_t t = threadIdx.x; t < R; t += blockDim.x) {
-        uint64_t key = t < have ? skeys[t] : UINT64_MAX;
+        const uint64_t key = t < have ? skeys[t] : UINT64_MAX;
         uint64_t id = UINT64_MAX;
         uint32_t hm = 0xffffffffu;
         float sc = -INFINITY;
         if (key != UINT64_MAX) {
             id = key & ((1ull << 40) - 1);
             hm = (uint32_t)(key >> 40);
-            // find the record: scan the shards' lists (each sorted by the same key)
             for (uint32_t s = 0; s < n_shards; ++s) {
-                const size_t base = ((size_t)s * nq + q) * R;
+                const uint64_t* ids = rec.ids(s) + (size_t)q * R;
+                const uint32_t* ham = rec.ham(s) + (size_t)q * R;
                 uint32_t lo = 0, hi = R;
                 while (lo < hi) {
-                    uint32_t mid = (lo + hi) >> 1;
-                    uint64_t mid_id = rec_ids[base + mid];
-                    uint64_t mk = mid_id == UINT64_MAX ? UINT64_MAX
-                                                       : (((uint64_t)rec_ham[base + mid] << 40) | mid_id);
+                    const uint32_t mid = (lo + hi) >> 1;
+                    const uint64_t mid_id = ids[mid];
+                    const uint64_t mk = mid_id == UINT64_MAX ? UINT64_MAX
+                                                             : (((uint64_t)ham[mid] << 40) | mid_id);
                     if (mk < key) lo = mid + 1; else hi = mid;
                 }
-                if (lo < R && rec_ids[base + lo] == id && rec_ham[base + lo] == hm) {
-                    sc = rec_score[base + lo];
+                if (lo < R && ids[lo] == id && ham[lo] == hm) {
+                    sc = rec.score(s)[(size_t)q * R + lo];
                     break;
                 }
             }

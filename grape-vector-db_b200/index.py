@@ -203,31 +203,46 @@ class GpuIndex:
         return ids, ds
 
     # -- sharded search: the two halves around the exchange ---------------------------------
-    def search_shard_device(self, queries_t, rescore_count: int):
-        """Local records (ham u32->int32 bits, ids int64 bits of u64, score f32), each [nq, R]."""
+    def shard_record_bytes(self, nq: int, rescore_count: int) -> int:
+        return int(self._lib.gvdb_shard_record_bytes(nq, rescore_count))
+
+    def search_shard_device(self, queries_t, rescore_count: int, records_out=None):
+        """This shard's packed records (uint8 tensor, [ids u64 | ham u32 | score f32] x nq x R)."""
         import torch
         nq = queries_t.shape[0]
         dev = queries_t.device
-        ham = torch.empty((nq, rescore_count), dtype=torch.int32, device=dev)
-        ids = torch.empty((nq, rescore_count), dtype=torch.int64, device=dev)
-        sc = torch.empty((nq, rescore_count), dtype=torch.float32, device=dev)
+        nbytes = self.shard_record_bytes(nq, rescore_count)
+        if records_out is None:
+            records_out = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        assert records_out.numel() == nbytes and records_out.is_contiguous()
         st = torch.cuda.current_stream(dev).cuda_stream
         self._ok(self._lib.gvdb_search_shard_device(
             self._h, C.c_void_p(st), C.c_void_p(queries_t.data_ptr()), nq, rescore_count,
-            C.c_void_p(ham.data_ptr()), C.c_void_p(ids.data_ptr()), C.c_void_p(sc.data_ptr())))
-        return ham, ids, sc
+            C.c_void_p(records_out.data_ptr())))
+        return records_out
 
-    def merge_shards_device(self, ham_all, ids_all, sc_all, k: int):
-        """Gathered [n_shards, nq, R] records -> (ids [nq,k] int64, scores [nq,k] f32)."""
+    def merge_shards_device(self, records_all, n_shards: int, nq: int, rescore_count: int, k: int,
+                            ids_out=None, scores_out=None):
+        """n_shards packed record buffers back to back -> (ids [nq,k] int64, scores [nq,k] f32)."""
         import torch
-        n_shards, nq, R = ham_all.shape
-        assert ham_all.is_cuda and ham_all.is_contiguous() and ids_all.is_contiguous()
-        dev = ham_all.device
-        ids = torch.empty((nq, k), dtype=torch.int64, device=dev)
-        sc = torch.empty((nq, k), dtype=torch.float32, device=dev)
+        assert records_all.is_cuda and records_all.is_contiguous()
+        assert records_all.numel() == n_shards * self.shard_record_bytes(nq, rescore_count)
+        dev = records_all.device
+        if ids_out is None:
+            ids_out = torch.empty((nq, k), dtype=torch.int64, device=dev)
+        if scores_out is None:
+            scores_out = torch.empty((nq, k), dtype=torch.float32, device=dev)
         st = torch.cuda.current_stream(dev).cuda_stream
         self._ok(self._lib.gvdb_merge_shards_device(
-            self._h, C.c_void_p(st), n_shards, C.c_void_p(ham_all.data_ptr()),
-            C.c_void_p(ids_all.data_ptr()), C.c_void_p(sc_all.data_ptr()), nq, R, k,
-            C.c_void_p(ids.data_ptr()), C.c_void_p(sc.data_ptr())))
-        return ids, sc
+            self._h, C.c_void_p(st), n_shards, C.c_void_p(records_all.data_ptr()), nq,
+            rescore_count, k, C.c_void_p(ids_out.data_ptr()), C.c_void_p(scores_out.data_ptr())))
+        return ids_out, scores_out
+
+    # -- measurement hooks --------------------------------------------------------------------
+    def profile_enable(self, on: bool = True):
+        self._ok(self._lib.gvdb_profile_enable(self._h, 1 if on else 0))
+
+    def profile_read(self, reset: bool = True) -> dict:
+        p = _ffi.GvdbProfile()
+        self._ok(self._lib.gvdb_profile_read(self._h, C.byref(p), 1 if reset else 0))
+        return {f: getattr(p, f) for f, _ in p._fields_}

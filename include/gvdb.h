@@ -150,24 +150,39 @@ GVDB_API gvdb_status gvdb_flat_search_batch_device(gvdb_index* h, void* stream, 
                                           float* dist_out_dev);
 
 /* ---- row-sharded search: the two halves around the exchange step -------------------- */
-/* Replaces the scatter side of ShardManager::search_vectors (src/distributed/shard.rs:760-775).
- * Local stage 1 + stage 2 of this shard: writes, per query, this shard's top `rescore_count`
- * records in (hamming asc, global row asc) order:
- *   rec_ham nq x R u32 (UINT32_MAX unfilled), rec_ids nq x R u64 global (GVDB_NO_ID),
- *   rec_score nq x R f32 cosine (-inf).  All DEVICE pointers. */
+/* A shard's answer for nq queries is ONE packed record buffer (so the exchange is one
+ * all-gather):  [ ids u64 nq x R | ham u32 nq x R | score f32 nq x R ],  16 * nq * R bytes.
+ * Per query the R records are in (hamming asc, global row asc) order; unfilled slots are
+ * (GVDB_NO_ID, UINT32_MAX, -inf). */
+GVDB_API uint64_t gvdb_shard_record_bytes(uint32_t nq, uint32_t rescore_count);
+/* Replaces the scatter side of ShardManager::search_vectors (src/distributed/shard.rs:760-775):
+ * local stage 1 + stage 2 of this shard -> records_dev (DEVICE, gvdb_shard_record_bytes). */
 GVDB_API gvdb_status gvdb_search_shard_device(gvdb_index* h, void* stream, const float* queries_dev,
-                                     uint32_t nq, uint32_t rescore_count, uint32_t* rec_ham_dev,
-                                     uint64_t* rec_ids_dev, float* rec_score_dev);
+                                              uint32_t nq, uint32_t rescore_count, void* records_dev);
 /* Replaces the gather side (concat + sort + truncate, src/distributed/shard.rs:776-783) with the
  * rule that reproduces the single-index result: over the n_shards x R gathered records of
  * each query keep the global top R by (hamming, global row), then order by (cosine desc,
- * hamming asc, row asc) and emit k.  Record arrays are laid out [shard][query][R] — exactly
- * what an all-gather of the gvdb_search_shard_device outputs produces. */
+ * hamming asc, row asc) and emit k.  `records_dev` is n_shards packed buffers back to back,
+ * in rank order — exactly what an all-gather of the gvdb_search_shard_device outputs yields. */
 GVDB_API gvdb_status gvdb_merge_shards_device(gvdb_index* h, void* stream, uint32_t n_shards,
-                                     const uint32_t* rec_ham_dev, const uint64_t* rec_ids_dev,
-                                     const float* rec_score_dev, uint32_t nq,
-                                     uint32_t rescore_count, uint32_t k, uint64_t* ids_out_dev,
-                                     float* scores_out_dev);
+                                              const void* records_dev, uint32_t nq,
+                                              uint32_t rescore_count, uint32_t k,
+                                              uint64_t* ids_out_dev, float* scores_out_dev);
+
+/* ---- measurement hooks ---------------------------------------------------------------- */
+/* When enabled, every kernel the library launches is bracketed by CUDA events on the stream
+ * it is launched on; times are accumulated at the call's final synchronisation. */
+typedef struct gvdb_profile {
+    uint64_t launches;        /* all kernels launched by this index */
+    uint64_t scan_launches;   /* scan_kernel launches */
+    double scan_ms;           /* summed scan_kernel device time */
+    double scan_bytes;        /* algorithmic code bytes streamed by those launches:
+                                 rows_in_segment * code_bytes_per_row * query_groups */
+    double scan_pairs;        /* (row, query) pairs evaluated */
+    double select_ms, rescore_ms, topk_ms, prep_ms, flat_ms, merge_ms;
+} gvdb_profile;
+GVDB_API gvdb_status gvdb_profile_enable(gvdb_index* h, int32_t on);
+GVDB_API gvdb_status gvdb_profile_read(gvdb_index* h, gvdb_profile* out, int32_t reset);
 
 #ifdef __cplusplus
 }

@@ -240,10 +240,8 @@ def test_logical_shards_merge_equals_single_index(gv):
             ix.add(rows[lo:hi])
             shards.append(ix)
             recs.append(ix.search_shard_device(qs_t, R))
-        ham = torch.stack([r[0] for r in recs]).contiguous()
-        ids = torch.stack([r[1] for r in recs]).contiguous()
-        sc = torch.stack([r[2] for r in recs]).contiguous()
-        mi, ms = shards[0].merge_shards_device(ham, ids, sc, k)
+        allrec = torch.cat(recs).contiguous()
+        mi, ms = shards[0].merge_shards_device(allrec, S, nq, R, k)
         torch.cuda.synchronize()
         assert np.array_equal(mi.cpu().numpy().astype(np.uint64), oi), f"S={S}"
         assert np.array_equal(_bits(ms.cpu().numpy()), _bits(os_)), f"S={S}"
