@@ -113,6 +113,7 @@ struct gvdb_index {
     std::vector<std::unique_ptr<Workspace>> pool;
     uint32_t query_tile = 1024;
     int scan_ctas_per_sm = 16;
+    int scan_variant = -1;   // GVDB_SCAN_NCSA: adder-count override for tuning (768-d only)
     std::atomic<int> profile_on{0};
     std::atomic<uint64_t> launches{0};
     std::mutex prof_mu;
@@ -230,39 +231,52 @@ void grow(gvdb_index* h, uint64_t need_rows) {
     h->rows = rows; h->codes = codes; h->norms = norms; h->live = live; h->cap_rows = new_cap;
 }
 
-// ---- kernel dispatch on NCHUNK ----------------------------------------------------------
-template <int NCHUNK, int MODE>
+// ---- kernel dispatch on NCHUNK (and, for tuning, on the carry-save adder count) ------------
+template <int NCHUNK, int MODE, int NCSA>
 void launch_scan_t(cudaStream_t st, dim3 grid, size_t smem, const uint4* codes, const uint32_t* live,
                    uint32_t tile_lo, uint32_t tile_hi, const uint32_t* qpack, int nq, int qgroup,
                    uint32_t* cnt, uint64_t* buf, uint32_t cap, uint32_t* overflow, uint32_t* dist_out,
                    uint64_t dist_stride, uint64_t n_rows) {
     static bool attr_set = false;   // benign race: idempotent
     if (!attr_set) {
-        CU(cudaFuncSetAttribute(scan_kernel<NCHUNK, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        CU(cudaFuncSetAttribute(scan_kernel<NCHUNK, MODE, NCSA>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
         attr_set = true;
     }
-    scan_kernel<NCHUNK, MODE><<<grid, SCAN_THREADS, smem, st>>>(
+    scan_kernel<NCHUNK, MODE, NCSA><<<grid, SCAN_THREADS, smem, st>>>(
         codes, live, tile_lo, tile_hi, qpack, nq, qgroup, cnt, buf, cap, overflow, dist_out,
         dist_stride, n_rows);
     CU(cudaGetLastError());
 }
 
+// default adder count: ~0.44 adders per word balances the XU (popc) and ALU (LOP3) pipes
+constexpr int default_ncsa(int nchunk) { return nchunk * 2; }   // W/2, tuned on B200 (profiles/r01_ncsa_tuning.txt)
+
 template <int MODE>
-void launch_scan(int nchunk, cudaStream_t st, dim3 grid, size_t smem, const uint4* codes,
+void launch_scan(int nchunk, int variant, cudaStream_t st, dim3 grid, size_t smem, const uint4* codes,
                  const uint32_t* live, uint32_t tile_lo, uint32_t tile_hi, const uint32_t* qpack,
                  int nq, int qgroup, uint32_t* cnt, uint64_t* buf, uint32_t cap, uint32_t* overflow,
                  uint32_t* dist_out, uint64_t dist_stride, uint64_t n_rows) {
-#define GVDB_CASE(N)                                                                          \
-    case N:                                                                                   \
-        launch_scan_t<N, MODE>(st, grid, smem, codes, live, tile_lo, tile_hi, qpack, nq, qgroup, \
-                               cnt, buf, cap, overflow, dist_out, dist_stride, n_rows);       \
-        break;
+#define GVDB_ARGS st, grid, smem, codes, live, tile_lo, tile_hi, qpack, nq, qgroup, cnt, buf, cap, overflow, dist_out, dist_stride, n_rows
+#define GVDB_CASE(N) case N: launch_scan_t<N, MODE, default_ncsa(N)>(GVDB_ARGS); break;
+    if (nchunk == 6 && MODE == 0 && variant >= 0) {   // tuning variants for the 768-d kernel
+        switch (variant) {
+            case 0: launch_scan_t<6, MODE, 0>(GVDB_ARGS); return;
+            case 8: launch_scan_t<6, MODE, 8>(GVDB_ARGS); return;
+            case 9: launch_scan_t<6, MODE, 9>(GVDB_ARGS); return;
+            case 10: launch_scan_t<6, MODE, 10>(GVDB_ARGS); return;
+            case 12: launch_scan_t<6, MODE, 12>(GVDB_ARGS); return;
+            case 13: launch_scan_t<6, MODE, 13>(GVDB_ARGS); return;
+            case 14: launch_scan_t<6, MODE, 14>(GVDB_ARGS); return;
+            default: break;
+        }
+    }
     switch (nchunk) {
         GVDB_CASE(1) GVDB_CASE(2) GVDB_CASE(3) GVDB_CASE(4) GVDB_CASE(6) GVDB_CASE(8)
         GVDB_CASE(12) GVDB_CASE(16) GVDB_CASE(24) GVDB_CASE(32)
         default: fail(GVDB_ERR_INDEX, "unsupported code width");
     }
 #undef GVDB_CASE
+#undef GVDB_ARGS
 }
 
 constexpr int kQGroup = 128;   // queries staged per CTA
@@ -318,7 +332,7 @@ void search_core(gvdb_index* h, Workspace* ws, cudaStream_t st, const float* que
             {
                 const double seg_rows = (double)(hi - lo) * 32.0;
                 Timed t(h, ws, st, K_SCAN, seg_rows * h->nchunk * 16.0 * grid.y, seg_rows * nqt);
-                launch_scan<0>(h->nchunk, st, grid, (size_t)kQGroup * h->qs * 4, h->codes, h->live, lo, hi,
+                launch_scan<0>(h->nchunk, h->scan_variant, st, grid, (size_t)kQGroup * h->qs * 4, h->codes, h->live, lo, hi,
                                ws->qpack.as<uint32_t>(), (int)nqt, kQGroup, ws->cnt.as<uint32_t>(),
                                ws->buf.as<uint64_t>(), cap, ws->flag.as<uint32_t>(), nullptr, 0, h->n_rows);
             }
@@ -513,6 +527,7 @@ gvdb_status gvdb_create(const gvdb_config* cfg, gvdb_index** out) {
         h->qs = h->nchunk * 4 + 4;
         h->sm_count = prop.multiProcessorCount;
         if (const char* s = getenv("GVDB_QUERY_TILE")) h->query_tile = std::max(1, atoi(s));
+        if (const char* s = getenv("GVDB_SCAN_NCSA")) h->scan_variant = atoi(s);
         if (const char* s = getenv("GVDB_SCAN_CTAS_PER_SM")) h->scan_ctas_per_sm = std::max(1, atoi(s));
         if (cfg->capacity_rows) grow(h.get(), cfg->capacity_rows);
         *out = h.release();
@@ -703,7 +718,7 @@ gvdb_status gvdb_hamming(gvdb_index* h, const uint8_t* q_codes, uint32_t nq, uin
             pack_query_codes_kernel<<<m, 64, 0, st>>>(ws->q_in.as<uint8_t>(), m, h->nbytes, h->nchunk, ws->qpack.as<uint32_t>(), h->qs);
             CU(cudaGetLastError());
             dim3 grid = scan_grid(h, ntiles, m);
-            launch_scan<1>(h->nchunk, st, grid, (size_t)kQGroup * h->qs * 4, h->codes, h->live, 0, ntiles,
+            launch_scan<1>(h->nchunk, -1, st, grid, (size_t)kQGroup * h->qs * 4, h->codes, h->live, 0, ntiles,
                            ws->qpack.as<uint32_t>(), (int)m, kQGroup, nullptr, nullptr, 0, nullptr,
                            ws->misc.as<uint32_t>(), N, N);
             CU(cudaMemcpyAsync(dist_out + (size_t)q0 * N, ws->misc.p, (size_t)m * N * 4, cudaMemcpyDeviceToHost, st));

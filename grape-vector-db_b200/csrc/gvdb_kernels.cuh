@@ -202,6 +202,73 @@ __global__ void unblock_codes_kernel(const uint4* __restrict__ codes, int nchunk
 }
 
 // ---------------------------------------------------------------------------------------
+// Hamming distance of W xor-ed words with NCSA carry-save adders in front of the popcounts.
+// B200 issues 16 popc/clk/SM (XU pipe) but 64 LOP3/clk/SM (ALU pipe); the plain loop is
+// XU-bound.  A full adder (sum = a^b^c, carry = maj(a,b,c): two LOP3) turns three words of
+// weight w into one of weight w and one of weight 2w, i.e. removes one popc for two LOP3.
+// NCSA adders are spent greedily on the lowest weight class that still has three words;
+// the result is exact: d = P1 + 2*P2 + 4*P4 with Pw the popcount sum of weight class w.
+__device__ __forceinline__ uint32_t lop3_xor3(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t r;
+    asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+    return r;
+}
+__device__ __forceinline__ uint32_t lop3_maj(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t r;
+    asm("lop3.b32 %0, %1, %2, %3, 0xE8;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+    return r;
+}
+
+template <int W, int NCSA>
+__device__ __forceinline__ uint32_t hamming_csa(const uint32_t (&x)[W]) {
+    // stage A: adders over consecutive triples of the inputs (weight 1 -> 1 + 2)
+    constexpr int nA = (NCSA < W / 3) ? NCSA : W / 3;
+    constexpr int n1 = nA + (W - 3 * nA);           // weight-1 words after stage A
+    uint32_t w1[n1 > 0 ? n1 : 1];
+    uint32_t w2a[nA > 0 ? nA : 1];
+#pragma unroll
+    for (int i = 0; i < nA; ++i) {
+        w1[i] = lop3_xor3(x[3 * i], x[3 * i + 1], x[3 * i + 2]);
+        w2a[i] = lop3_maj(x[3 * i], x[3 * i + 1], x[3 * i + 2]);
+    }
+#pragma unroll
+    for (int i = 3 * nA; i < W; ++i) w1[nA + i - 3 * nA] = x[i];
+    // stage B: adders over triples of the weight-1 words
+    constexpr int remB = NCSA - nA;
+    constexpr int nB = (remB < n1 / 3) ? remB : n1 / 3;
+    constexpr int n1b = nB + (n1 - 3 * nB);
+    uint32_t v1[n1b > 0 ? n1b : 1];
+    uint32_t w2b[nB > 0 ? nB : 1];
+#pragma unroll
+    for (int i = 0; i < nB; ++i) {
+        v1[i] = lop3_xor3(w1[3 * i], w1[3 * i + 1], w1[3 * i + 2]);
+        w2b[i] = lop3_maj(w1[3 * i], w1[3 * i + 1], w1[3 * i + 2]);
+    }
+#pragma unroll
+    for (int i = 3 * nB; i < n1; ++i) v1[nB + i - 3 * nB] = w1[i];
+    // stage C: adders over triples of the weight-2 words (2 -> 2 + 4)
+    constexpr int n2 = nA + nB;
+    uint32_t w2[n2 > 0 ? n2 : 1];
+#pragma unroll
+    for (int i = 0; i < nA; ++i) w2[i] = w2a[i];
+#pragma unroll
+    for (int i = 0; i < nB; ++i) w2[nA + i] = w2b[i];
+    constexpr int remC = NCSA - nA - nB;
+    constexpr int nC = (remC < n2 / 3) ? remC : n2 / 3;
+    uint32_t p1 = 0, p2 = 0, p4 = 0;
+#pragma unroll
+    for (int i = 0; i < n1b; ++i) p1 += __popc(v1[i]);
+#pragma unroll
+    for (int i = 0; i < nC; ++i) {
+        p2 += __popc(lop3_xor3(w2[3 * i], w2[3 * i + 1], w2[3 * i + 2]));
+        p4 += __popc(lop3_maj(w2[3 * i], w2[3 * i + 1], w2[3 * i + 2]));
+    }
+#pragma unroll
+    for (int i = 3 * nC; i < n2; ++i) p2 += __popc(w2[i]);
+    return p1 + 2u * p2 + 4u * p4;
+}
+
+// ---------------------------------------------------------------------------------------
 // scan_kernel — THE hot loop.  One warp owns a tile of 32 rows: each lane keeps its row's
 // code in NCHUNK uint4 registers (one coalesced 512 B request per chunk) and walks the query
 // group staged in shared memory (one TMA bulk copy per CTA; every lane reads the same
@@ -211,7 +278,7 @@ __global__ void unblock_codes_kernel(const uint4* __restrict__ codes, int nchunk
 // MODE 1 (parity): every distance is written out (gvdb_hamming).
 // Algorithmic bytes per launch: (tile_hi - tile_lo) * 32 * NCHUNK * 16 (codes streamed once
 // per query group) — see DESIGN.md §5.
-template <int NCHUNK, int MODE>
+template <int NCHUNK, int MODE, int NCSA>
 __global__ void __launch_bounds__(SCAN_THREADS)
 scan_kernel(const uint4* __restrict__ codes, const uint32_t* __restrict__ live, uint32_t tile_lo,
             uint32_t tile_hi, const uint32_t* __restrict__ qpack, int nq, int qgroup,
@@ -254,13 +321,14 @@ scan_kernel(const uint4* __restrict__ codes, const uint32_t* __restrict__ live, 
 #pragma unroll 2
         for (int q = 0; q < nql; ++q) {
             const uint4* qp = reinterpret_cast<const uint4*>(sq + q * QS);
-            uint32_t d = 0;
+            uint32_t x[NCHUNK * 4];
 #pragma unroll
             for (int c = 0; c < NCHUNK; ++c) {
                 const uint4 v = qp[c];
-                d += __popc(r[c].x ^ v.x) + __popc(r[c].y ^ v.y) + __popc(r[c].z ^ v.z) +
-                     __popc(r[c].w ^ v.w);
+                x[4 * c + 0] = r[c].x ^ v.x; x[4 * c + 1] = r[c].y ^ v.y;
+                x[4 * c + 2] = r[c].z ^ v.z; x[4 * c + 3] = r[c].w ^ v.w;
             }
+            const uint32_t d = hamming_csa<NCHUNK * 4, NCSA>(x);
             if (MODE == 0) {
                 const uint32_t tau = sq[q * QS + NCHUNK * 4];
                 // strict '<': tau is the R-th smallest distance over EARLIER rows, so a later

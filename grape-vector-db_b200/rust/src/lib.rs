@@ -1,0 +1,196 @@
+//! gvdb-sys: Rust binding of the C ABI in include/gvdb.h, plus `GpuVectorIndex`, an
+//! `impl VectorIndex` (reference src/index.rs:35-62) that can be dropped in at the wiring point
+//! src/lib.rs:256-261 in place of `HnswVectorIndex::new()` / `FaissVectorIndex::new(..)`.
+//!
+//! Not compiled in this repository (the image has no Rust toolchain); the C++ mirror in
+//! ../host/gvdb_host.hpp has the same structure and IS tested on a B200.
+#![allow(non_camel_case_types)]
+use std::collections::HashMap;
+use std::ffi::{c_char, c_void, CStr};
+
+#[repr(C)]
+pub struct gvdb_index { _private: [u8; 0] }
+
+#[repr(C)]
+#[derive(Default, Clone, Copy)]
+pub struct gvdb_config {
+    pub struct_size: u32,
+    pub dim: u32,
+    pub threshold: f32,
+    pub rescore_ratio: f32,
+    pub device: i32,
+    pub flags: u32,
+    pub capacity_rows: u64,
+    pub row_base: u64,
+}
+
+#[repr(C)]
+#[derive(Default, Clone, Copy)]
+pub struct gvdb_stats {
+    pub vector_count: u64,
+    pub rows: u64,
+    pub dimension: u64,
+    pub memory_usage: u64,
+    pub hbm_bytes: u64,
+    pub code_bytes_per_row: u64,
+}
+
+pub const GVDB_NO_ID: u64 = u64::MAX;
+
+extern "C" {
+    pub fn gvdb_abi_version() -> u32;
+    pub fn gvdb_last_error() -> *const c_char;
+    pub fn gvdb_create(cfg: *const gvdb_config, out: *mut *mut gvdb_index) -> i32;
+    pub fn gvdb_destroy(h: *mut gvdb_index);
+    pub fn gvdb_add(h: *mut gvdb_index, rows: *const f32, n: u64, first_row_out: *mut u64) -> i32;
+    pub fn gvdb_add_device(h: *mut gvdb_index, stream: *mut c_void, rows_dev: *const f32, n: u64, first_row_out: *mut u64) -> i32;
+    pub fn gvdb_reserve(h: *mut gvdb_index, capacity_rows: u64) -> i32;
+    pub fn gvdb_remove(h: *mut gvdb_index, local_row: u64, was_live_out: *mut i32) -> i32;
+    pub fn gvdb_clear(h: *mut gvdb_index) -> i32;
+    pub fn gvdb_len(h: *const gvdb_index) -> u64;
+    pub fn gvdb_get_stats(h: *const gvdb_index, out: *mut gvdb_stats) -> i32;
+    pub fn gvdb_quantize(h: *mut gvdb_index, x: *const f32, n: u64, codes_out: *mut u8) -> i32;
+    pub fn gvdb_get_codes(h: *mut gvdb_index, first: u64, n: u64, codes_out: *mut u8) -> i32;
+    pub fn gvdb_hamming(h: *mut gvdb_index, q_codes: *const u8, nq: u32, dist_out: *mut u32) -> i32;
+    pub fn gvdb_rescore_count(n: u64, ratio: f32) -> u64;
+    pub fn gvdb_search_batch(h: *mut gvdb_index, queries: *const f32, nq: u32, k: u32, rescore_count: u32,
+                             ids_out: *mut u64, scores_out: *mut f32, cand_ids_out: *mut u64, cand_ham_out: *mut u32) -> i32;
+    pub fn gvdb_flat_search_batch(h: *mut gvdb_index, queries: *const f32, nq: u32, k: u32,
+                                  ids_out: *mut u64, dist_out: *mut f32) -> i32;
+    pub fn gvdb_shard_record_bytes(nq: u32, rescore_count: u32) -> u64;
+    pub fn gvdb_search_shard_device(h: *mut gvdb_index, stream: *mut c_void, queries_dev: *const f32, nq: u32,
+                                    rescore_count: u32, records_dev: *mut c_void) -> i32;
+    pub fn gvdb_merge_shards_device(h: *mut gvdb_index, stream: *mut c_void, n_shards: u32, records_dev: *const c_void,
+                                    nq: u32, rescore_count: u32, k: u32, ids_out_dev: *mut u64, scores_out_dev: *mut f32) -> i32;
+}
+
+/// Owned handle; `Send + Sync` because the C ABI's search entry points are re-entrant and the
+/// mutating ones are only reachable through `&mut self` (the reference's write guard).
+pub struct GpuIndex { h: *mut gvdb_index, dim: usize }
+unsafe impl Send for GpuIndex {}
+unsafe impl Sync for GpuIndex {}
+
+impl Drop for GpuIndex {
+    fn drop(&mut self) { unsafe { gvdb_destroy(self.h) } }
+}
+
+fn last_error() -> String {
+    unsafe { CStr::from_ptr(gvdb_last_error()).to_string_lossy().into_owned() }
+}
+
+#[cfg(feature = "vector-index")]
+mod trait_impl {
+    use super::*;
+    use grape_vector_db::index::{IndexStats, VectorIndex};
+    use grape_vector_db::types::VectorDbError;
+
+    fn map_err(st: i32) -> VectorDbError {
+        match st {
+            1 => VectorDbError::IndexNotBuilt,
+            2 => VectorDbError::IndexError(last_error()), // DimensionMismatch is raised on the Rust side with both numbers
+            3 => VectorDbError::InvalidVectorDimension,
+            4 => VectorDbError::QuantizationError(last_error()),
+            6 => VectorDbError::ConfigError(last_error()),
+            7 => VectorDbError::NotImplemented(last_error()),
+            _ => VectorDbError::IndexError(last_error()),
+        }
+    }
+
+    /// The GPU index behind `Arc<RwLock<dyn VectorIndex>>` (src/lib.rs:238).
+    pub struct GpuVectorIndex {
+        inner: Option<GpuIndex>,
+        id_to_index: HashMap<String, u64>,   // same two maps as FaissVectorIndex (src/index.rs:333-334)
+        index_to_id: HashMap<u64, String>,
+        exact: bool,
+        oversample: u32,
+        threshold: f32,
+        device: i32,
+    }
+
+    impl GpuVectorIndex {
+        pub fn new(exact: bool, oversample: u32, device: i32) -> Self {
+            Self { inner: None, id_to_index: HashMap::new(), index_to_id: HashMap::new(), exact, oversample, threshold: 0.0, device }
+        }
+    }
+
+    impl VectorIndex for GpuVectorIndex {
+        fn add_vector(&mut self, id: String, vector: Vec<f32>) -> Result<(), VectorDbError> {
+            self.add_vectors(vec![(id, vector)])
+        }
+        fn add_vectors(&mut self, vectors: Vec<(String, Vec<f32>)>) -> Result<(), VectorDbError> {
+            if vectors.is_empty() { return Ok(()); }
+            if self.inner.is_none() {
+                let dim = vectors[0].1.len();
+                let cfg = gvdb_config { struct_size: std::mem::size_of::<gvdb_config>() as u32, dim: dim as u32,
+                                        threshold: self.threshold, rescore_ratio: 0.1, device: self.device, ..Default::default() };
+                let mut h = std::ptr::null_mut();
+                let st = unsafe { gvdb_create(&cfg, &mut h) };
+                if st != 0 { return Err(map_err(st)); }
+                self.inner = Some(GpuIndex { h, dim });
+            }
+            let ix = self.inner.as_ref().unwrap();
+            let mut flat = Vec::with_capacity(vectors.len() * ix.dim);
+            for (_, v) in &vectors {
+                if v.len() != ix.dim {   // src/index.rs:590-594
+                    return Err(VectorDbError::DimensionMismatch { expected: ix.dim, actual: v.len() });
+                }
+                flat.extend_from_slice(v);
+            }
+            let mut first = 0u64;
+            let st = unsafe { gvdb_add(ix.h, flat.as_ptr(), vectors.len() as u64, &mut first) };
+            if st != 0 { return Err(map_err(st)); }
+            for (i, (id, _)) in vectors.into_iter().enumerate() {
+                if let Some(old) = self.id_to_index.insert(id.clone(), first + i as u64) {
+                    let mut was = 0i32;
+                    unsafe { gvdb_remove(ix.h, old, &mut was) };
+                    self.index_to_id.remove(&old);
+                }
+                self.index_to_id.insert(first + i as u64, id);
+            }
+            Ok(())
+        }
+        fn search(&self, query: &[f32], k: usize) -> Result<Vec<(String, f32)>, VectorDbError> {
+            let ix = self.inner.as_ref().ok_or(VectorDbError::IndexNotBuilt)?;   // src/index.rs:621-623
+            if query.len() != ix.dim {
+                return Err(VectorDbError::DimensionMismatch { expected: ix.dim, actual: query.len() });
+            }
+            if k == 0 { return Ok(Vec::new()); }
+            let mut ids = vec![GVDB_NO_ID; k];
+            let mut val = vec![0f32; k];
+            let st = unsafe {
+                if self.exact {
+                    gvdb_flat_search_batch(ix.h, query.as_ptr(), 1, k as u32, ids.as_mut_ptr(), val.as_mut_ptr())
+                } else {
+                    gvdb_search_batch(ix.h, query.as_ptr(), 1, k as u32, (k as u32) * self.oversample,
+                                      ids.as_mut_ptr(), val.as_mut_ptr(), std::ptr::null_mut(), std::ptr::null_mut())
+                }
+            };
+            if st != 0 { return Err(map_err(st)); }
+            // score convention of the exact reference path: distance = 1 - cos, ascending (src/index.rs:630-637)
+            Ok(ids.iter().zip(val.iter()).take_while(|(i, _)| **i != GVDB_NO_ID)
+                  .map(|(i, v)| (self.index_to_id[i].clone(), if self.exact { *v } else { 1.0 - *v })).collect())
+        }
+        fn remove_vector(&mut self, id: &str) -> Result<bool, VectorDbError> {          // src/index.rs:642-650
+            if let Some(row) = self.id_to_index.remove(id) {
+                self.index_to_id.remove(&row);
+                let mut was = 0i32;
+                let st = unsafe { gvdb_remove(self.inner.as_ref().unwrap().h, row, &mut was) };
+                if st != 0 { return Err(map_err(st)); }
+                Ok(true)
+            } else { Ok(false) }
+        }
+        fn len(&self) -> usize { self.id_to_index.len() }
+        fn is_empty(&self) -> bool { self.id_to_index.is_empty() }
+        fn optimize(&mut self) -> Result<(), VectorDbError> { Ok(()) }
+        fn clear(&mut self) { self.inner = None; self.id_to_index.clear(); self.index_to_id.clear(); }
+        fn get_stats(&self) -> IndexStats {
+            let mut s = gvdb_stats::default();
+            if let Some(ix) = &self.inner { unsafe { gvdb_get_stats(ix.h, &mut s) }; }
+            IndexStats { vector_count: self.len(), dimension: s.dimension as usize,
+                         index_type: if self.exact { "GpuFlat".into() } else { "GpuBinaryTwoStage".into() },
+                         memory_usage: s.memory_usage as usize }
+        }
+    }
+}
+#[cfg(feature = "vector-index")]
+pub use trait_impl::GpuVectorIndex;

@@ -1,0 +1,101 @@
+"""The N>1 host logic on CPU: two gloo ranks run the product's sharding arithmetic, packed-record
+layout and the one-collective exchange (grape_vector_db_b200.dist); per-shard searches and the
+merge are done by the CPU oracle here (test infrastructure) because the product's shard search and
+merge are CUDA kernels.  The merged answer must equal the single-index oracle answer."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, n, dim, nq, R, k, out_dir):
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+    from grape_vector_db_b200 import dist as gdist
+    from grape_vector_db_b200 import synth
+    from oracle import oracle
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    lo, hi = gdist.shard_bounds(n, world, rank)
+    rows = synth.lowrank_rows(lo, hi - lo, dim)          # each rank regenerates ITS rows only
+    qs = synth.lowrank_queries(0, nq, dim)
+    ids = np.full((nq, R), np.iinfo(np.uint64).max, dtype=np.uint64)
+    ham = np.full((nq, R), 0xFFFFFFFF, dtype=np.uint32)
+    sc = np.full((nq, R), -np.inf, dtype=np.float32)
+    for qi in range(nq):
+        i, s, ci, ch = oracle.multi_stage_search(qs[qi], rows, R, want_candidates=True)
+        by = {int(c): t for t, c in enumerate(ci)}
+        r = len(ci)
+        ids[qi, :r] = ci + np.uint64(lo)
+        ham[qi, :r] = ch
+        for ii, ss in zip(i, s):
+            sc[qi, by[int(ii)]] = ss
+    local = torch.from_numpy(gdist.pack_records(ids, ham, sc))
+    assert local.numel() == gdist.record_bytes(nq, R)
+    allrec = gdist.all_gather_records(local).numpy()
+    if rank == 0:
+        per = gdist.record_bytes(nq, R)
+        parts = [gdist.unpack_records(allrec[s * per:(s + 1) * per], nq, R) for s in range(world)]
+        got_i = np.zeros((nq, k), np.uint64)
+        got_s = np.zeros((nq, k), np.float32)
+        for qi in range(nq):
+            gi, gs = oracle.shard_merge(np.concatenate([p[1][qi] for p in parts]),
+                                        np.concatenate([p[0][qi] for p in parts]),
+                                        np.concatenate([p[2][qi] for p in parts]), R, k)
+            got_i[qi, :len(gi)] = gi
+            got_s[qi, :len(gs)] = gs
+        np.save(os.path.join(out_dir, "ids.npy"), got_i)
+        np.save(os.path.join(out_dir, "sc.npy"), got_s)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_shard_bounds_cover_and_partition():
+    from grape_vector_db_b200 import dist as gdist
+    for n in (0, 1, 7, 1000, 1_000_000, 100_000_001):
+        for g in (1, 2, 3, 4, 8):
+            b = [gdist.shard_bounds(n, g, s) for s in range(g)]
+            assert b[0][0] == 0 and b[-1][1] == n
+            assert all(b[i][1] == b[i + 1][0] for i in range(g - 1))
+            assert all(lo <= hi for lo, hi in b)
+
+
+def test_pack_unpack_roundtrip():
+    from grape_vector_db_b200 import dist as gdist
+    rng = np.random.default_rng(0)
+    ids = rng.integers(0, 2**40, size=(5, 7)).astype(np.uint64)
+    ham = rng.integers(0, 768, size=(5, 7)).astype(np.uint32)
+    sc = rng.standard_normal((5, 7)).astype(np.float32)
+    buf = gdist.pack_records(ids, ham, sc)
+    assert buf.size == gdist.record_bytes(5, 7)
+    a, b, c = gdist.unpack_records(buf, 5, 7)
+    assert np.array_equal(a, ids) and np.array_equal(b, ham) and np.array_equal(c, sc)
+
+
+@pytest.mark.timeout(300)
+def test_two_rank_gloo_exchange_and_merge(tmp_path):
+    import torch.multiprocessing as mp
+    from grape_vector_db_b200 import synth
+    from oracle import oracle
+    n, dim, nq, R, k, world = 5000, 128, 6, 40, 10, 2
+    port = _free_port()
+    mp.spawn(_worker, args=(world, port, n, dim, nq, R, k, str(tmp_path)), nprocs=world, join=True)
+    rows = synth.lowrank_rows(0, n, dim)
+    qs = synth.lowrank_queries(0, nq, dim)
+    want_i, want_s = oracle.multi_stage_search_batch(qs, rows, R, k)
+    got_i = np.load(tmp_path / "ids.npy")
+    got_s = np.load(tmp_path / "sc.npy")
+    assert np.array_equal(got_i, want_i)
+    assert np.array_equal(got_s.view(np.uint32), want_s.view(np.uint32))
