@@ -1,0 +1,397 @@
+// gvdb_tc.cuh — the batched Hamming scan on the 5th-gen tensor cores (tcgen05 + TMEM), sm_100a.
+//
+// Used when a corpus pass serves a large query tile (>= 64 queries), where the scan really is a
+// dense contraction: rows x queries x dim.  The CUDA-core kernel (scan_kernel) is then bound by
+// the integer pipes (16 popc + 64 LOP3 per clk per SM); tcgen05.mma.kind::i8 does 8192 MAC/clk/SM.
+//
+// Exactness.  Row codes are expanded on chip to A in {0,1} (int8), query codes are expanded once
+// per batch to B in {+1,-1} (int8, +1 where the query bit is 1).  Over the code bits,
+//     S = sum_k A_k * B_k = n11 - n10         (int32 accumulation, exact)
+//     hamming = n10 + n01 = popc(q) - S       (popc(q) = n11 + n01)
+// so hamming < tau  <=>  S + (tau - popc(q)) > 0.  Pad bits are 0 in A and contribute nothing.
+// The per-query bias v = tau - popc(q) is added ON the tensor core by one extra K=32 MMA per
+// accumulator block (A = 32 ones per row, B = 32 int8 digits summing to v), so the epilogue is
+// a pure sign test on registers: the tensor core's operand traffic saturates shared memory,
+// and a per-element threshold load from shared memory would starve (measured: 3x slower).
+// The K order of the expansion is a fixed permutation of the code bits applied to rows and
+// queries alike (Hamming distance is invariant to it); it is chosen so that one row word
+// expands with SHF + LOP3 only:  out[8*w + i] = (code_word[w] >> i) & 0x01010101.
+//
+// Data flow per CTA (persistent over groups of 128 rows = 4 code tiles):
+//   warps 0-3  "row owners": lane = row.  Load the row's code (coalesced, blocked layout),
+//              expand it and write it into TMEM as the A operand (tcgen05.st, K/4 columns);
+//              later read the int32 accumulators back (tcgen05.ld), compare with the per-query
+//              threshold and append survivors (key = hamming << 32 | row) — same contract as
+//              scan_kernel MODE 0.  MODE 1 writes every distance (parity tests).
+//   warp 4     TMA producer: bulk-copies 16 KB blocks of pre-expanded queries (already in the
+//              UMMA K-major no-swizzle core-matrix order) into a 4-stage shared-memory ring.
+//   warp 5     MMA issuer: one elected lane issues tcgen05.mma (M=128, N=128, K=32), A from
+//              TMEM, B from shared memory, D in TMEM (2 x 128 columns, double buffered).
+//   mbarriers  full/empty per stage, a_ready, acc_full/acc_empty per accumulator buffer;
+//              tcgen05.commit signals MMA completion.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "gvdb_kernels.cuh"
+
+namespace gvdb {
+
+constexpr int TC_ROWS = 128;        // rows per CTA group (UMMA M)
+constexpr int TC_NQ = 128;          // queries per accumulator block (UMMA N)
+constexpr int TC_KSTAGE = 128;      // K bytes per shared-memory stage (4 MMAs of K=32)
+constexpr int TC_STAGES = 4;
+constexpr int TC_STAGE_BYTES = TC_NQ * TC_KSTAGE;   // 16 KB
+constexpr int TC_THREADS = 192;     // 4 row-owner warps + producer warp + MMA warp
+constexpr uint32_t TC_TMEM_COLS = 512;
+constexpr int TC_BIAS_BYTES = TC_NQ * 32;           // 4 KB: one K=32 slice of per-query bias digits
+__host__ __device__ constexpr size_t tc_qblock_bytes(int nchunk) {
+    return (size_t)(nchunk * 128 / TC_KSTAGE) * TC_STAGE_BYTES + TC_BIAS_BYTES;
+}
+
+// ---- PTX wrappers ------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) {}
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_alloc(uint32_t smem_dst, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_dst), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tc_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem desc], int8 x int8 -> int32
+__device__ __forceinline__ void tc_mma_i8_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc,
+                                             uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, {%5, %5, %5, %5}, p;\n\t}"
+        :: "r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(0u) : "memory");
+}
+// 32 lanes x 8 columns per call (each thread: its own lane, 8 consecutive 32-bit columns)
+__device__ __forceinline__ void tc_st8(uint32_t taddr, const uint32_t (&v)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 :: "r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+                 : "memory");
+}
+__device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr) : "memory");
+}
+
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+        "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr) : "memory");
+}
+
+// UMMA shared-memory descriptor, K-major, no swizzle: 8x16 B core matrices (128 B contiguous);
+// LBO = byte stride between core matrices along K, SBO = along N.  (cute::UMMA::SmemDescriptor)
+__device__ __forceinline__ uint64_t tc_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) |
+           ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46);
+}
+// UMMA instruction descriptor (cute::UMMA::InstrDescriptor): D=S32, A=B=INT8, K-major both.
+__host__ __device__ constexpr uint32_t tc_idesc_i8(int M, int N) {
+    return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// ---- query pre-expansion ---------------------------------------------------------------------------
+// qpack (code words + tau, as produced by ingest_kernel<QUERY>) -> qexp, int8 +-1 in the exact byte
+// order the TMA stages need:  block (qb, ks) of 16 KB at qb*tc_qblock_bytes + ks*16384 (the last
+// 4 KB of a query block hold the bias digits, written by tc_bias_kernel), inside a 16 KB block
+//   offset(n, kk) = (n/8)*1024 + (kk/16)*128 + (n%8)*16 + (kk%16),  n = query in block, kk = K byte in stage
+// K byte k of a query  <->  code bit (w*32 + 8*b + i) with  k = (8*w + i)*4 + b   (see header).
+// Queries beyond nq (padding up to a multiple of 128) are all zero.  Also writes popc(q).
+__global__ void tc_expand_queries_kernel(const uint32_t* __restrict__ qpack, int qs, int nchunk, uint32_t nq,
+                                         uint32_t nq_pad, int8_t* __restrict__ qexp,
+                                         uint32_t* __restrict__ qpop) {
+    const uint32_t q = blockIdx.x;                 // one CTA per (padded) query
+    if (q >= nq_pad) return;
+    const int K = nchunk * 128;
+    const uint32_t qb = q / TC_NQ, n = q % TC_NQ;
+    uint32_t pop = 0;
+    for (int k4 = threadIdx.x; k4 < K / 4; k4 += blockDim.x) {   // one 32-bit output word (4 K bytes)
+        const int w = k4 >> 3, i = k4 & 7;
+        uint32_t out = 0;
+        if (q < nq) {
+            const uint32_t word = qpack[(size_t)q * qs + w];
+            const uint32_t bits = (word >> i) & 0x01010101u;            // byte b = code bit 8b+i
+            // 1 -> +1 (0x01), 0 -> -1 (0xFF)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) out |= (((bits >> (8 * b)) & 1u) ? 0x01u : 0xFFu) << (8 * b);
+            if (i == 0) pop += __popc(word);
+        }
+        const int k = k4 * 4;
+        const int ks = k / TC_KSTAGE, kk = k % TC_KSTAGE;
+        const size_t off = (size_t)qb * tc_qblock_bytes(nchunk) + (size_t)ks * TC_STAGE_BYTES + (n / 8) * 1024 + (kk / 16) * 128 + (n % 8) * 16 + (kk % 16);
+        *reinterpret_cast<uint32_t*>(qexp + off) = out;
+    }
+    // block reduce popcount (blockDim <= 256)
+    __shared__ uint32_t red[8];
+    for (int o = 16; o > 0; o >>= 1) pop += __shfl_xor_sync(0xffffffffu, pop, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = pop;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t s = 0;
+        for (int i = 0; i < (int)(blockDim.x + 31) / 32; ++i) s += red[i];
+        qpop[q] = q < nq ? s : 0u;
+    }
+}
+
+// Per-query bias digits for the current thresholds: v = tau - popc(q) (v = K+1 when tau is
+// TAU_ALL: everything passes; v = -(K+1) for padding queries: nothing passes), written as 32 int8
+// digits in [-127,127] summing to v, in the K-major core-matrix order of a 128 x 32 B block:
+//   offset(n, kk) = (n/8)*256 + (kk/16)*128 + (n%8)*16 + (kk%16).   zero_bias: v = 0 (MODE 1).
+__global__ void tc_bias_kernel(const uint32_t* __restrict__ qpack, int qs, int nchunk,
+                               const uint32_t* __restrict__ qpop, uint32_t nq, uint32_t nq_pad,
+                               int8_t* __restrict__ qexp, int32_t* __restrict__ qbias, int zero_bias) {
+    const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nq_pad) return;
+    const int K = nchunk * 128;
+    int v = -(K + 1);
+    if (q < nq) {
+        const uint32_t tau = qpack[(size_t)q * qs + nchunk * 4];
+        v = tau == TAU_ALL ? K + 1 : (int)tau - (int)qpop[q];
+        if (v > K + 1) v = K + 1;
+        if (v < -(K + 1)) v = -(K + 1);
+    }
+    if (zero_bias) v = 0;
+    qbias[q] = v;
+    const uint32_t qb = q / TC_NQ, n = q % TC_NQ;
+    int8_t* blk = qexp + (size_t)qb * tc_qblock_bytes(nchunk) + (size_t)(K / TC_KSTAGE) * TC_STAGE_BYTES;
+    int rest = v;
+    for (int kk = 0; kk < 32; ++kk) {
+        int d = rest > 127 ? 127 : (rest < -127 ? -127 : rest);
+        rest -= d;
+        blk[(n / 8) * 256 + (kk / 16) * 128 + (n % 8) * 16 + (kk % 16)] = (int8_t)d;
+    }
+}
+
+// ---- the scan ------------------------------------------------------------------------------------------
+// MODE 0: append survivors (search).  MODE 1: write all distances (dist_out[q*stride + row]).
+template <int NCHUNK, int MODE>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+tc_scan_kernel(const uint4* __restrict__ codes, const uint32_t* __restrict__ live, uint32_t tile_lo,
+               uint32_t tile_hi, const int8_t* __restrict__ qexp, const uint32_t* __restrict__ qpop,
+               const int32_t* __restrict__ qbias, uint32_t nq, uint32_t nq_pad,
+               uint32_t* __restrict__ cnt, uint64_t* __restrict__ buf, uint32_t cap,
+               uint32_t* __restrict__ overflow, uint32_t* __restrict__ dist_out, uint64_t dist_stride,
+               uint64_t n_rows, int dbg = 0) {
+    constexpr int K = NCHUNK * 128;
+    constexpr int KS = K / TC_KSTAGE;          // stages per accumulator block
+    constexpr int A_COLS = K / 4;              // TMEM columns of the A operand (+8: the ones slice)
+    constexpr uint32_t IDESC = tc_idesc_i8(TC_ROWS, TC_NQ);
+    static_assert(A_COLS + 8 + 2 * TC_NQ <= 512, "TMEM budget");
+
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t* stage_base = smem;                                           // TC_STAGES * 16 KB
+    int32_t* s_bias = reinterpret_cast<int32_t*>(smem + TC_STAGES * TC_STAGE_BYTES);  // nq_pad biases (slow path only)
+    uint32_t* s_pop = reinterpret_cast<uint32_t*>(s_bias + nq_pad);                   // nq_pad popcounts
+    __shared__ __align__(8) uint64_t bars[TC_STAGES * 2 + 1 + 4];
+    __shared__ uint32_t s_tmem_base;
+    const uint32_t bar0 = smem_u32(bars);
+    auto full_bar = [&](int s) { return bar0 + 8u * s; };
+    auto empty_bar = [&](int s) { return bar0 + 8u * (TC_STAGES + s); };
+    const uint32_t a_ready = bar0 + 8u * (2 * TC_STAGES);
+    auto acc_full = [&](int b) { return bar0 + 8u * (2 * TC_STAGES + 1 + b); };
+    auto acc_empty = [&](int b) { return bar0 + 8u * (2 * TC_STAGES + 3 + b); };
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t nqb = nq_pad / TC_NQ;
+    const uint32_t ngroups = (tile_hi - tile_lo + 3) / 4;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < TC_STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        mbar_init(a_ready, 4);
+        for (int b = 0; b < 2; ++b) { mbar_init(acc_full(b), 1); mbar_init(acc_empty(b), 4); }
+        fence_mbar_init();
+    }
+    if (warp == 5) tc_alloc(smem_u32(&s_tmem_base), TC_TMEM_COLS);
+    for (uint32_t q = threadIdx.x; q < nq_pad; q += TC_THREADS) {
+        s_bias[q] = qbias[q];
+        s_pop[q] = q < nq ? qpop[q] : 0u;
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = s_tmem_base;
+    const uint32_t tmem_a = tmem;                 // columns [0, A_COLS): codes; [A_COLS, A_COLS+8): ones
+    const uint32_t tmem_d = tmem + A_COLS + 8;    // two accumulator buffers of TC_NQ columns
+
+    if (warp < 4) {
+        // ===================== row owners: expand A, then epilogue =====================
+        uint32_t acc_phase[2] = {0, 0};
+        uint32_t it = 0;
+        const uint32_t lane_taddr = (uint32_t)(warp * 32) << 16;
+        {
+            uint32_t ones[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) ones[i] = 0x01010101u;
+            tc_st8(tmem_a + lane_taddr + A_COLS, ones);     // A slice of the bias MMA
+        }
+        for (uint32_t g = blockIdx.x; g < ngroups; g += gridDim.x) {
+            const uint32_t tile = tile_lo + g * 4 + warp;
+            const bool in_range = tile < tile_hi;
+            const uint32_t row = tile * 32u + lane;
+            const bool alive = in_range && ((live[in_range ? tile : tile_lo] >> lane) & 1u);
+            uint4 r[NCHUNK];
+#pragma unroll
+            for (int c = 0; c < NCHUNK; ++c)
+                r[c] = in_range ? ldg_stream(codes + ((size_t)tile * NCHUNK + c) * 32 + lane) : make_uint4(0, 0, 0, 0);
+            // The previous group's last accumulator has been consumed by this warp's epilogue, and
+            // every MMA that read A completed before that acc_full fired: A may be overwritten.
+#pragma unroll
+            for (int c = 0; c < NCHUNK; ++c) {
+                const uint32_t w4[4] = {r[c].x, r[c].y, r[c].z, r[c].w};
+#pragma unroll
+                for (int wi = 0; wi < 4; ++wi) {
+                    uint32_t v[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) v[i] = (w4[wi] >> i) & 0x01010101u;
+                    tc_st8(tmem_a + lane_taddr + (uint32_t)((c * 4 + wi) * 8), v);
+                }
+            }
+            tc_wait_st();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(a_ready);
+
+            for (uint32_t qb = 0; qb < nqb; ++qb, ++it) {
+                const uint32_t b = it & 1u;
+                mbar_wait(acc_full(b), acc_phase[b]);
+                acc_phase[b] ^= 1u;
+                tc_fence_after();
+#pragma unroll 1
+                for (int half = 0; half < ((dbg & 1) ? 0 : 2); ++half) {
+                    uint32_t v0[32], v1[32];
+                    const uint32_t col0 = tmem_d + lane_taddr + b * TC_NQ + half * 64;
+                    tc_ld32(col0, v0);
+                    tc_ld32(col0 + 32, v1);
+                    tc_wait_ld();
+                    if (MODE == 0) {
+                        // D = S + bias: a survivor has D > 0.  Survivors are rare: one max-reduce
+                        // over the 64 registers decides whether to look at individual elements.
+                        int32_t mx = (int32_t)v0[0];
+#pragma unroll
+                        for (int j = 1; j < 32; ++j) mx = max(mx, (int32_t)v0[j]);
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) mx = max(mx, (int32_t)v1[j]);
+                        if (mx > 0 && alive) {
+#pragma unroll
+                            for (int j = 0; j < 64; ++j) {
+                                const int32_t dv = (int32_t)(j < 32 ? v0[j & 31] : v1[j & 31]);
+                                if (dv > 0) {
+                                    const uint32_t q = qb * TC_NQ + half * 64 + j;
+                                    // hamming = popc(q) - S = popc(q) + bias - D
+                                    const uint32_t d = (uint32_t)((int32_t)s_pop[q] + s_bias[q] - dv);
+                                    const uint32_t pos = atomicAdd(&cnt[q], 1u);
+                                    if (pos < cap) buf[(size_t)q * cap + pos] = ((uint64_t)d << 32) | row;
+                                    else *overflow = 1u;
+                                }
+                            }
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 64; ++j) {
+                            const uint32_t q = qb * TC_NQ + half * 64 + j;
+                            const int32_t dv = (int32_t)(j < 32 ? v0[j & 31] : v1[j & 31]);
+                            if (q < nq && in_range && row < n_rows)
+                                dist_out[(size_t)q * dist_stride + row] = (uint32_t)((int32_t)s_pop[q] + s_bias[q] - dv);
+                        }
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(acc_empty(b));
+            }
+        }
+    } else if (warp == 4) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0;
+            for (uint32_t g = blockIdx.x; g < ngroups; g += gridDim.x) {
+                for (uint32_t qb = 0; qb < nqb; ++qb) {
+                    const int8_t* qblk = qexp + (size_t)qb * tc_qblock_bytes(NCHUNK);
+                    for (int ks = 0; ks <= KS; ++ks) {            // KS code stages + the bias slice
+                        const uint32_t bytes = ks < KS ? TC_STAGE_BYTES : TC_BIAS_BYTES;
+                        mbar_wait(empty_bar(stage), phase ^ 1u);
+                        mbar_expect_tx(full_bar(stage), bytes);
+                        tma_bulk_g2s(smem_u32(stage_base + stage * TC_STAGE_BYTES),
+                                     qblk + (size_t)ks * TC_STAGE_BYTES, bytes, full_bar(stage));
+                        if (++stage == TC_STAGES) { stage = 0; phase ^= 1u; }
+                    }
+                }
+            }
+        }
+    } else {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0;
+            uint32_t a_phase = 0;
+            uint32_t acc_phase[2] = {0, 0};
+            uint32_t it = 0;
+            for (uint32_t g = blockIdx.x; g < ngroups; g += gridDim.x) {
+                mbar_wait(a_ready, a_phase);
+                a_phase ^= 1u;
+                tc_fence_after();
+                for (uint32_t qb = 0; qb < nqb; ++qb, ++it) {
+                    const uint32_t b = it & 1u;
+                    mbar_wait(acc_empty(b), acc_phase[b] ^ 1u);      // first use of each buffer passes
+                    acc_phase[b] ^= 1u;
+                    tc_fence_after();
+                    for (int ks = 0; ks < KS; ++ks) {
+                        mbar_wait(full_bar(stage), phase);
+                        tc_fence_after();
+                        const uint32_t sb = smem_u32(stage_base + stage * TC_STAGE_BYTES);
+#pragma unroll
+                        for (int j = 0; j < TC_KSTAGE / 32; ++j) {
+                            const uint64_t bdesc = tc_smem_desc(sb + j * 256, 128, 1024);
+                            tc_mma_i8_ts(tmem_d + b * TC_NQ, tmem_a + (uint32_t)((ks * (TC_KSTAGE / 32) + j) * 8),
+                                         bdesc, IDESC, (ks | j) != 0 ? 1u : 0u);
+                        }
+                        tc_commit(empty_bar(stage));                 // stage free when these MMAs retire
+                        if (++stage == TC_STAGES) { stage = 0; phase ^= 1u; }
+                    }
+                    {   // bias: D += ones(128 x 32) * digits(128 queries x 32)
+                        mbar_wait(full_bar(stage), phase);
+                        tc_fence_after();
+                        const uint32_t sb = smem_u32(stage_base + stage * TC_STAGE_BYTES);
+                        tc_mma_i8_ts(tmem_d + b * TC_NQ, tmem_a + A_COLS, tc_smem_desc(sb, 128, 256), IDESC, 1u);
+                        tc_commit(empty_bar(stage));
+                        if (++stage == TC_STAGES) { stage = 0; phase ^= 1u; }
+                    }
+                    tc_commit(acc_full(b));
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 5) {
+        __syncwarp();
+        tc_dealloc(tmem, TC_TMEM_COLS);
+    }
+}
+
+}  // namespace gvdb

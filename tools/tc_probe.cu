@@ -1,0 +1,149 @@
+// tc_probe.cu — standalone check + timing of the tcgen05 Hamming scan (gvdb_tc.cuh) against a
+// plain popc kernel.  Build: nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo
+//   -I grape-vector-db_b200/csrc -o gpurun_out/tc_probe tools/tc_probe.cu     Run on a B200.
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+#include <algorithm>
+#include "gvdb_tc.cuh"
+using namespace gvdb;
+#define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e), __FILE__, __LINE__); exit(2); } } while (0)
+
+template <int NCHUNK>
+__global__ void ref_kernel(const uint4* codes, uint32_t ntiles, const uint32_t* qpack, int qs, uint32_t nq, uint32_t* dist, uint64_t stride, uint64_t n_rows) {
+    uint32_t tile = blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32, lane = threadIdx.x & 31;
+    if (tile >= ntiles) return;
+    uint32_t row = tile * 32 + lane;
+    uint4 r[NCHUNK];
+    for (int c = 0; c < NCHUNK; ++c) r[c] = codes[((size_t)tile * NCHUNK + c) * 32 + lane];
+    for (uint32_t q = 0; q < nq; ++q) {
+        uint32_t d = 0;
+        for (int c = 0; c < NCHUNK; ++c) {
+            const uint32_t* w = qpack + (size_t)q * qs + c * 4;
+            d += __popc(r[c].x ^ w[0]) + __popc(r[c].y ^ w[1]) + __popc(r[c].z ^ w[2]) + __popc(r[c].w ^ w[3]);
+        }
+        if (row < n_rows) dist[(size_t)q * stride + row] = d;
+    }
+}
+
+static uint64_t rng_state = 88172645463325252ull;
+static uint32_t rnd() { rng_state ^= rng_state << 13; rng_state ^= rng_state >> 7; rng_state ^= rng_state << 17; return (uint32_t)(rng_state >> 16); }
+
+int main(int argc, char** argv) {
+    constexpr int NCHUNK = 6;
+    const int qs = NCHUNK * 4 + 4;
+    uint64_t n_rows = argc > 1 ? atoll(argv[1]) : 148 * 128 * 2 + 77;
+    uint32_t nq = argc > 2 ? atoi(argv[2]) : 300;
+    int timing = argc > 3 ? atoi(argv[3]) : 0;
+    uint32_t ntiles = (uint32_t)((n_rows + 31) / 32);
+    uint32_t nq_pad = (nq + TC_NQ - 1) / TC_NQ * TC_NQ;
+    size_t code_words = (size_t)ntiles * NCHUNK * 32 * 4;
+    std::vector<uint32_t> h_codes(code_words), h_qpack((size_t)nq * qs), h_live(ntiles, 0xffffffffu);
+    for (auto& w : h_codes) w = rnd();
+    if (n_rows % 32) h_live[ntiles - 1] = (1u << (n_rows % 32)) - 1u;   // rows past the end are not live
+    for (uint32_t q = 0; q < nq; ++q) {
+        for (int w = 0; w < NCHUNK * 4; ++w) h_qpack[(size_t)q * qs + w] = rnd();
+        h_qpack[(size_t)q * qs + NCHUNK * 4] = TAU_ALL;
+        for (int w = 1; w < 4; ++w) h_qpack[(size_t)q * qs + NCHUNK * 4 + w] = 0;
+    }
+    uint4* d_codes; uint32_t *d_qpack, *d_live, *d_ref, *d_tc, *d_qpop, *d_cnt, *d_flag; int8_t* d_qexp; int32_t* d_qbias; uint64_t* d_buf;
+    CK(cudaMalloc(&d_codes, code_words * 4)); CK(cudaMalloc(&d_qpack, h_qpack.size() * 4)); CK(cudaMalloc(&d_live, ntiles * 4));
+    const bool check = !timing;
+    size_t dist_bytes = check ? (size_t)nq * n_rows * 4 : 4;
+    CK(cudaMalloc(&d_ref, dist_bytes)); CK(cudaMalloc(&d_tc, dist_bytes));
+    CK(cudaMalloc(&d_qexp, (size_t)(nq_pad / TC_NQ) * tc_qblock_bytes(NCHUNK))); CK(cudaMalloc(&d_qbias, nq_pad * 4)); CK(cudaMalloc(&d_qpop, nq_pad * 4));
+    const uint32_t cap = 8192;
+    CK(cudaMalloc(&d_cnt, nq_pad * 4)); CK(cudaMalloc(&d_flag, 4)); CK(cudaMalloc(&d_buf, (size_t)nq_pad * cap * 8));
+    CK(cudaMemcpy(d_codes, h_codes.data(), code_words * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d_qpack, h_qpack.data(), h_qpack.size() * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d_live, h_live.data(), ntiles * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemset(d_tc, 0xff, dist_bytes)); CK(cudaMemset(d_cnt, 0, nq_pad * 4)); CK(cudaMemset(d_flag, 0, 4));
+
+    tc_expand_queries_kernel<<<nq_pad, 64>>>(d_qpack, qs, NCHUNK, nq, nq_pad, d_qexp, d_qpop);
+    CK(cudaGetLastError());
+    int sms = 0; CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0));
+    uint32_t ngroups = (ntiles + 3) / 4;
+    uint32_t grid = ngroups < (uint32_t)sms ? ngroups : sms;
+    size_t smem = TC_STAGES * TC_STAGE_BYTES + (size_t)nq_pad * 8;
+    if (check) {
+        CK(cudaFuncSetAttribute(tc_scan_kernel<NCHUNK, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        tc_bias_kernel<<<(nq_pad + 127) / 128, 128>>>(d_qpack, qs, NCHUNK, d_qpop, nq, nq_pad, d_qexp, d_qbias, 1);
+        ref_kernel<NCHUNK><<<(ntiles + 7) / 8, 256>>>(d_codes, ntiles, d_qpack, qs, nq, d_ref, n_rows, n_rows);
+        CK(cudaGetLastError());
+        tc_scan_kernel<NCHUNK, 1><<<grid, TC_THREADS, smem>>>(d_codes, d_live, 0, ntiles, d_qexp, d_qpop, d_qbias, nq, nq_pad,
+                                                             d_cnt, d_buf, cap, d_flag, d_tc, n_rows, n_rows);
+        CK(cudaGetLastError());
+        CK(cudaDeviceSynchronize());
+        std::vector<uint32_t> a((size_t)nq * n_rows), b((size_t)nq * n_rows);
+        CK(cudaMemcpy(a.data(), d_ref, dist_bytes, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(b.data(), d_tc, dist_bytes, cudaMemcpyDeviceToHost));
+        size_t bad = 0, first = (size_t)-1;
+        for (size_t i = 0; i < a.size(); ++i) if (a[i] != b[i]) { if (!bad) first = i; ++bad; }
+        printf("check: rows=%llu nq=%u mismatches=%zu of %zu\n", (unsigned long long)n_rows, nq, bad, a.size());
+        if (bad) {
+            printf("first mismatch at q=%zu row=%zu ref=%u tc=%u\n", first / n_rows, first % n_rows, a[first], b[first]);
+            for (int i = 0; i < 8; ++i) printf("  [%d] ref=%u tc=%u\n", i, a[i], b[i]);
+            return 1;
+        }
+        // ---- search mode (MODE 0): survivors of a finite threshold must be exactly {ham < tau} ----
+        const uint32_t tau = 352;
+        for (uint32_t q = 0; q < nq; ++q) h_qpack[(size_t)q * qs + NCHUNK * 4] = (q % 7 == 3) ? TAU_ALL : tau + (q % 5);
+        CK(cudaMemcpy(d_qpack, h_qpack.data(), h_qpack.size() * 4, cudaMemcpyHostToDevice));
+        tc_bias_kernel<<<(nq_pad + 127) / 128, 128>>>(d_qpack, qs, NCHUNK, d_qpop, nq, nq_pad, d_qexp, d_qbias, 0);
+        CK(cudaFuncSetAttribute(tc_scan_kernel<NCHUNK, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const uint32_t bigcap = 65536;
+        uint64_t* d_buf2; CK(cudaMalloc(&d_buf2, (size_t)nq_pad * bigcap * 8));
+        CK(cudaMemset(d_cnt, 0, nq_pad * 4));
+        tc_scan_kernel<NCHUNK, 0><<<grid, TC_THREADS, smem>>>(d_codes, d_live, 0, ntiles, d_qexp, d_qpop, d_qbias, nq, nq_pad,
+                                                             d_cnt, d_buf2, bigcap, d_flag, nullptr, 0, n_rows);
+        CK(cudaGetLastError());
+        CK(cudaDeviceSynchronize());
+        std::vector<uint32_t> h_cnt(nq_pad);
+        CK(cudaMemcpy(h_cnt.data(), d_cnt, nq_pad * 4, cudaMemcpyDeviceToHost));
+        std::vector<uint64_t> h_buf((size_t)nq_pad * bigcap);
+        CK(cudaMemcpy(h_buf.data(), d_buf2, h_buf.size() * 8, cudaMemcpyDeviceToHost));
+        size_t badq = 0, total = 0;
+        for (uint32_t q = 0; q < nq_pad; ++q) {
+            std::vector<uint64_t> want;
+            if (q < nq) {
+                uint32_t t = h_qpack[(size_t)q * qs + NCHUNK * 4];
+                for (uint64_t r = 0; r < n_rows; ++r) { uint32_t d = a[(size_t)q * n_rows + r]; if (t == TAU_ALL || d < t) want.push_back(((uint64_t)d << 32) | r); }
+            }
+            std::vector<uint64_t> got(h_buf.begin() + (size_t)q * bigcap, h_buf.begin() + (size_t)q * bigcap + std::min<uint32_t>(h_cnt[q], bigcap));
+            std::sort(got.begin(), got.end()); std::sort(want.begin(), want.end());
+            total += want.size();
+            if (q < nq && h_qpack[(size_t)q * qs + NCHUNK * 4] == TAU_ALL && n_rows > bigcap) continue;   // overflow by construction
+            if (got != want) { if (!badq) printf("search-mode mismatch q=%u got=%zu want=%zu\n", q, got.size(), want.size()); ++badq; }
+        }
+        printf("search-mode check: %zu survivors, bad queries=%zu\n", total, badq);
+        if (badq) return 1;
+    } else {
+        // timing in search mode with a threshold that lets nothing through (tau = 0)
+        for (uint32_t q = 0; q < nq; ++q) h_qpack[(size_t)q * qs + NCHUNK * 4] = 200;   // ham < 200 never happens on random codes
+        CK(cudaMemcpy(d_qpack, h_qpack.data(), h_qpack.size() * 4, cudaMemcpyHostToDevice));
+        tc_bias_kernel<<<(nq_pad + 127) / 128, 128>>>(d_qpack, qs, NCHUNK, d_qpop, nq, nq_pad, d_qexp, d_qbias, 0);
+        CK(cudaFuncSetAttribute(tc_scan_kernel<NCHUNK, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+        for (int rep = 0; rep < 3; ++rep)
+            tc_scan_kernel<NCHUNK, 0><<<grid, TC_THREADS, smem>>>(d_codes, d_live, 0, ntiles, d_qexp, d_qpop, d_qbias, nq, nq_pad,
+                                                                 d_cnt, d_buf, cap, d_flag, nullptr, 0, n_rows);
+        CK(cudaDeviceSynchronize());
+        const int reps = 10;
+        for (int dbg : {0, 1}) {
+        cudaEventRecord(e0);
+        for (int rep = 0; rep < reps; ++rep)
+            tc_scan_kernel<NCHUNK, 0><<<grid, TC_THREADS, smem>>>(d_codes, d_live, 0, ntiles, d_qexp, d_qpop, d_qbias, nq, nq_pad,
+                                                                 d_cnt, d_buf, cap, d_flag, nullptr, 0, n_rows, dbg);
+        cudaEventRecord(e1);
+        CK(cudaDeviceSynchronize());
+        float ms = 0; cudaEventElapsedTime(&ms, e0, e1); ms /= reps;
+        double macs = (double)n_rows * nq_pad * NCHUNK * 128;
+        printf("timing dbg=%d (1=no-epilogue 2=no-tma 8=ldtm-only): rows=%llu nq=%u  %.3f ms/launch  %.1f TMAC/s (int8)  = %.1f%% of 148 SMs x 8192 MAC/clk @1.965GHz\n",
+               dbg, (unsigned long long)n_rows, nq, ms, macs / ms / 1e9, 100.0 * macs / (ms * 1e-3) / (148.0 * 8192 * 1.965e9));
+        }
+        uint32_t flag = 0, c0 = 0; CK(cudaMemcpy(&flag, d_flag, 4, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(&c0, d_cnt, 4, cudaMemcpyDeviceToHost));
+        printf("overflow=%u cnt[0]=%u\n", flag, c0);
+    }
+    printf("OK\n");
+    return 0;
+}
