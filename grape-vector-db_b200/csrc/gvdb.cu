@@ -27,6 +27,7 @@
 #include "gvdb.h"
 #include "gvdb_flat.cuh"
 #include "gvdb_kernels.cuh"
+#include "gvdb_tc.cuh"
 
 namespace {
 
@@ -85,10 +86,12 @@ struct Workspace {
     bool used = false;
     DevBuf qpack, qnorm, cnt, flag, buf, rec_ham, rec_ids, rec_score;
     DevBuf q_in, ids_out, sc_out, codes_tmp, misc;
+    DevBuf qexp, qpop, qbias;        // tcgen05 path: pre-expanded queries, popcounts, biases
+    DevBuf tc_recs, list_counts;     // tcgen05 path: warp-private survivor records
     uint32_t* h_flag = nullptr;      // pinned
     ~Workspace() {
         for (DevBuf* b : {&qpack, &qnorm, &cnt, &flag, &buf, &rec_ham, &rec_ids, &rec_score, &q_in,
-                          &ids_out, &sc_out, &codes_tmp, &misc}) b->release();
+                          &ids_out, &sc_out, &codes_tmp, &misc, &qexp, &qpop, &qbias, &tc_recs, &list_counts}) b->release();
         if (h_flag) cudaFreeHost(h_flag);
         for (cudaEvent_t e : ev_pool) cudaEventDestroy(e);
         if (idle) cudaEventDestroy(idle);
@@ -113,7 +116,8 @@ struct gvdb_index {
     std::vector<std::unique_ptr<Workspace>> pool;
     uint32_t query_tile = 1024;
     int scan_ctas_per_sm = 16;
-    int scan_variant = -1;   // GVDB_SCAN_NCSA: adder-count override for tuning (768-d only)
+    int scan_variant = -1;     // GVDB_SCAN_NCSA: adder-count override for tuning (768-d only)
+    uint32_t tc_min_q = 64;    // GVDB_TC_MIN_Q: query-tile size from which the tcgen05 scan is used
     std::atomic<int> profile_on{0};
     std::atomic<uint64_t> launches{0};
     std::mutex prof_mu;
@@ -279,6 +283,76 @@ void launch_scan(int nchunk, int variant, cudaStream_t st, dim3 grid, size_t sme
 #undef GVDB_ARGS
 }
 
+// ---- tcgen05 scan dispatch (dims up to 768: A operand + 2 accumulators fit the 512 TMEM columns) ---
+bool tc_supported(int nchunk) { return nchunk == 1 || nchunk == 2 || nchunk == 3 || nchunk == 4 || nchunk == 6; }
+
+// MODE 0: survivors -> warp-private record lists -> tc_scatter_kernel -> per-query buffers.
+// MODE 1: every distance to dist_out (parity).
+template <int MODE>
+void launch_tc_scan(gvdb_index* h, Workspace* ws, cudaStream_t st, uint32_t tile_lo, uint32_t tile_hi,
+                    uint32_t nq, uint32_t nq_pad, uint32_t* cnt, uint64_t* buf, uint32_t cap,
+                    uint32_t* overflow, uint32_t* dist_out, uint64_t dist_stride) {
+    const uint32_t ngroups = (tile_hi - tile_lo + 3) / 4;
+    const uint32_t grid = std::min<uint32_t>(ngroups, (uint32_t)h->sm_count);
+    const uint32_t nlists = grid * 4;
+    const size_t smem = (size_t)TC_STAGES * TC_STAGE_BYTES + (size_t)nq_pad * 8;
+    uint32_t rec_cap = 0;
+    if (MODE == 0) {
+        // expected survivors per launch <= nq * cap / 4 (segment sizing); 4x head-room per list
+        uint64_t want = 4ull * ((uint64_t)nq * cap / 4) / nlists;
+        rec_cap = 4096;
+        while (rec_cap < want && rec_cap < 65536) rec_cap <<= 1;
+        ws->tc_recs.ensure((size_t)nlists * rec_cap * sizeof(uint2));
+        ws->list_counts.ensure((size_t)h->sm_count * 4 * 4);
+    }
+    const int8_t* qexp = ws->qexp.as<int8_t>();
+    const uint32_t* qpop = ws->qpop.as<uint32_t>();
+    const int32_t* qbias = ws->qbias.as<int32_t>();
+    uint2* recs = ws->tc_recs.as<uint2>();
+    uint32_t* lc = ws->list_counts.as<uint32_t>();
+#define GVDB_TC_CASE(N)                                                                              \
+    case N: {                                                                                        \
+        static bool attr = false;                                                                    \
+        if (!attr) {                                                                                 \
+            CU(cudaFuncSetAttribute(tc_scan_kernel<N, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)); \
+            attr = true;                                                                             \
+        }                                                                                            \
+        tc_scan_kernel<N, MODE><<<grid, TC_THREADS, smem, st>>>(h->codes, h->live, tile_lo, tile_hi, qexp, qpop, qbias, \
+                                                               nq, nq_pad, recs, rec_cap, lc, overflow, dist_out,       \
+                                                               dist_stride, h->n_rows, 0);                              \
+        break;                                                                                       \
+    }
+    switch (h->nchunk) {
+        GVDB_TC_CASE(1) GVDB_TC_CASE(2) GVDB_TC_CASE(3) GVDB_TC_CASE(4) GVDB_TC_CASE(6)
+        default: fail(GVDB_ERR_INDEX, "tcgen05 scan: unsupported code width");
+    }
+#undef GVDB_TC_CASE
+    CU(cudaGetLastError());
+    if (MODE == 0) {
+        h->launches.fetch_add(1, std::memory_order_relaxed);
+        tc_scatter_kernel<<<dim3((rec_cap + 255) / 256, nlists), 256, 0, st>>>(
+            recs, rec_cap, lc, h->codes, h->nchunk, ws->qpack.as<uint32_t>(), h->qs, cnt, buf, cap, overflow);
+        CU(cudaGetLastError());
+    }
+}
+
+void tc_prepare_queries(gvdb_index* h, Workspace* ws, cudaStream_t st, uint32_t nq, uint32_t nq_pad) {
+    ws->qexp.ensure((size_t)(nq_pad / TC_NQ) * tc_qblock_bytes(h->nchunk));
+    ws->qpop.ensure((size_t)nq_pad * 4);
+    ws->qbias.ensure((size_t)nq_pad * 4);
+    h->launches.fetch_add(1, std::memory_order_relaxed);
+    tc_expand_queries_kernel<<<nq_pad, 64, 0, st>>>(ws->qpack.as<uint32_t>(), h->qs, h->nchunk, nq, nq_pad,
+                                                    ws->qexp.as<int8_t>(), ws->qpop.as<uint32_t>());
+    CU(cudaGetLastError());
+}
+
+void tc_update_bias(gvdb_index* h, Workspace* ws, cudaStream_t st, uint32_t nq, uint32_t nq_pad, int zero_bias) {
+    h->launches.fetch_add(1, std::memory_order_relaxed);
+    tc_bias_kernel<<<(nq_pad + 127) / 128, 128, 0, st>>>(ws->qpack.as<uint32_t>(), h->qs, h->nchunk, ws->qpop.as<uint32_t>(),
+                                                         nq, nq_pad, ws->qexp.as<int8_t>(), ws->qbias.as<int32_t>(), zero_bias);
+    CU(cudaGetLastError());
+}
+
 constexpr int kQGroup = 128;   // queries staged per CTA
 
 dim3 scan_grid(const gvdb_index* h, uint32_t ntiles, uint32_t nq) {
@@ -324,13 +398,23 @@ void search_core(gvdb_index* h, Workspace* ws, cudaStream_t st, const float* que
         }
         CU(cudaGetLastError());
         CU(cudaMemsetAsync(ws->cnt.p, 0, (size_t)nqt * 4, st));
+        // Large query tiles: the scan is a dense contraction -> tcgen05 (gvdb_tc.cuh).  The first
+        // segment (tau = "emit all", 4096 rows) always runs on the popc kernel.
+        const bool use_tc = nqt >= h->tc_min_q && tc_supported(h->nchunk) && ntiles > seg0_tiles;
+        const uint32_t nq_pad = (nqt + TC_NQ - 1) / TC_NQ * TC_NQ;
+        if (use_tc) tc_prepare_queries(h, ws, st, nqt, nq_pad);
         uint32_t lo = 0;
         while (lo < ntiles) {
             uint64_t hi64 = lo == 0 ? seg0_tiles : (uint64_t)lo * g;
             uint32_t hi = (uint32_t)std::min<uint64_t>(hi64, ntiles);
-            dim3 grid = scan_grid(h, hi - lo, nqt);
-            {
-                const double seg_rows = (double)(hi - lo) * 32.0;
+            const double seg_rows = (double)(hi - lo) * 32.0;
+            if (use_tc && lo > 0) {
+                tc_update_bias(h, ws, st, nqt, nq_pad, 0);
+                Timed t(h, ws, st, K_SCAN, seg_rows * h->nchunk * 16.0, seg_rows * nqt);
+                launch_tc_scan<0>(h, ws, st, lo, hi, nqt, nq_pad, ws->cnt.as<uint32_t>(), ws->buf.as<uint64_t>(), cap,
+                                  ws->flag.as<uint32_t>(), nullptr, 0);
+            } else {
+                dim3 grid = scan_grid(h, hi - lo, nqt);
                 Timed t(h, ws, st, K_SCAN, seg_rows * h->nchunk * 16.0 * grid.y, seg_rows * nqt);
                 launch_scan<0>(h->nchunk, h->scan_variant, st, grid, (size_t)kQGroup * h->qs * 4, h->codes, h->live, lo, hi,
                                ws->qpack.as<uint32_t>(), (int)nqt, kQGroup, ws->cnt.as<uint32_t>(),
@@ -528,6 +612,7 @@ gvdb_status gvdb_create(const gvdb_config* cfg, gvdb_index** out) {
         h->sm_count = prop.multiProcessorCount;
         if (const char* s = getenv("GVDB_QUERY_TILE")) h->query_tile = std::max(1, atoi(s));
         if (const char* s = getenv("GVDB_SCAN_NCSA")) h->scan_variant = atoi(s);
+        if (const char* s = getenv("GVDB_TC_MIN_Q")) h->tc_min_q = (uint32_t)std::max(1, atoi(s));
         if (const char* s = getenv("GVDB_SCAN_CTAS_PER_SM")) h->scan_ctas_per_sm = std::max(1, atoi(s));
         if (cfg->capacity_rows) grow(h.get(), cfg->capacity_rows);
         *out = h.release();
@@ -717,10 +802,17 @@ gvdb_status gvdb_hamming(gvdb_index* h, const uint8_t* q_codes, uint32_t nq, uin
             CU(cudaMemcpyAsync(ws->q_in.p, q_codes + (size_t)q0 * h->nbytes, (size_t)m * h->nbytes, cudaMemcpyHostToDevice, st));
             pack_query_codes_kernel<<<m, 64, 0, st>>>(ws->q_in.as<uint8_t>(), m, h->nbytes, h->nchunk, ws->qpack.as<uint32_t>(), h->qs);
             CU(cudaGetLastError());
-            dim3 grid = scan_grid(h, ntiles, m);
-            launch_scan<1>(h->nchunk, -1, st, grid, (size_t)kQGroup * h->qs * 4, h->codes, h->live, 0, ntiles,
-                           ws->qpack.as<uint32_t>(), (int)m, kQGroup, nullptr, nullptr, 0, nullptr,
-                           ws->misc.as<uint32_t>(), N, N);
+            if (m >= h->tc_min_q && tc_supported(h->nchunk)) {     // same kernel the batched search uses
+                const uint32_t m_pad = (m + TC_NQ - 1) / TC_NQ * TC_NQ;
+                tc_prepare_queries(h, ws, st, m, m_pad);
+                tc_update_bias(h, ws, st, m, m_pad, 1);
+                launch_tc_scan<1>(h, ws, st, 0, ntiles, m, m_pad, nullptr, nullptr, 0, nullptr, ws->misc.as<uint32_t>(), N);
+            } else {
+                dim3 grid = scan_grid(h, ntiles, m);
+                launch_scan<1>(h->nchunk, -1, st, grid, (size_t)kQGroup * h->qs * 4, h->codes, h->live, 0, ntiles,
+                               ws->qpack.as<uint32_t>(), (int)m, kQGroup, nullptr, nullptr, 0, nullptr,
+                               ws->misc.as<uint32_t>(), N, N);
+            }
             CU(cudaMemcpyAsync(dist_out + (size_t)q0 * N, ws->misc.p, (size_t)m * N * 4, cudaMemcpyDeviceToHost, st));
             CU(cudaStreamSynchronize(st));
         }

@@ -9,6 +9,8 @@
 //     S = sum_k A_k * B_k = n11 - n10         (int32 accumulation, exact)
 //     hamming = n10 + n01 = popc(q) - S       (popc(q) = n11 + n01)
 // so hamming < tau  <=>  S + (tau - popc(q)) > 0.  Pad bits are 0 in A and contribute nothing.
+// The kernel stores B NEGATED (-1 where the query bit is 1) and a negated bias, so the
+// accumulator is D = -(S + tau - popc(q)) and a survivor is simply D < 0: its sign bit.
 // The per-query bias v = tau - popc(q) is added ON the tensor core by one extra K=32 MMA per
 // accumulator block (A = 32 ones per row, B = 32 int8 digits summing to v), so the epilogue is
 // a pure sign test on registers: the tensor core's operand traffic saturates shared memory,
@@ -137,9 +139,9 @@ __global__ void tc_expand_queries_kernel(const uint32_t* __restrict__ qpack, int
         if (q < nq) {
             const uint32_t word = qpack[(size_t)q * qs + w];
             const uint32_t bits = (word >> i) & 0x01010101u;            // byte b = code bit 8b+i
-            // 1 -> +1 (0x01), 0 -> -1 (0xFF)
+            // negated B: query bit 1 -> -1 (0xFF), 0 -> +1 (0x01)
 #pragma unroll
-            for (int b = 0; b < 4; ++b) out |= (((bits >> (8 * b)) & 1u) ? 0x01u : 0xFFu) << (8 * b);
+            for (int b = 0; b < 4; ++b) out |= (((bits >> (8 * b)) & 1u) ? 0xFFu : 0x01u) << (8 * b);
             if (i == 0) pop += __popc(word);
         }
         const int k = k4 * 4;
@@ -184,7 +186,7 @@ __global__ void tc_bias_kernel(const uint32_t* __restrict__ qpack, int qs, int n
     for (int kk = 0; kk < 32; ++kk) {
         int d = rest > 127 ? 127 : (rest < -127 ? -127 : rest);
         rest -= d;
-        blk[(n / 8) * 256 + (kk / 16) * 128 + (n % 8) * 16 + (kk % 16)] = (int8_t)d;
+        blk[(n / 8) * 256 + (kk / 16) * 128 + (n % 8) * 16 + (kk % 16)] = (int8_t)(-d);   // negated, like B
     }
 }
 
@@ -195,7 +197,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_scan_kernel(const uint4* __restrict__ codes, const uint32_t* __restrict__ live, uint32_t tile_lo,
                uint32_t tile_hi, const int8_t* __restrict__ qexp, const uint32_t* __restrict__ qpop,
                const int32_t* __restrict__ qbias, uint32_t nq, uint32_t nq_pad,
-               uint32_t* __restrict__ cnt, uint64_t* __restrict__ buf, uint32_t cap,
+               uint2* __restrict__ recs, uint32_t rec_cap, uint32_t* __restrict__ cta_counts,
                uint32_t* __restrict__ overflow, uint32_t* __restrict__ dist_out, uint64_t dist_stride,
                uint64_t n_rows, int dbg = 0) {
     constexpr int K = NCHUNK * 128;
@@ -244,6 +246,13 @@ tc_scan_kernel(const uint4* __restrict__ codes, const uint32_t* __restrict__ liv
         uint32_t acc_phase[2] = {0, 0};
         uint32_t it = 0;
         const uint32_t lane_taddr = (uint32_t)(warp * 32) << 16;
+        // Survivor records of this warp: a private list, slots handed out with ballot + popc from a
+        // register counter.  No shared memory and no atomics in the epilogue: while MMAs run, the
+        // tensor core's operand traffic owns the shared-memory pipe and the L2 round trip of a
+        // global atomic would sit on the accumulator hand-off (both measured: 3x slower scans).
+        uint2* my_list = recs + (size_t)(blockIdx.x * 4 + warp) * rec_cap;
+        uint32_t my_count = 0;
+        const uint32_t lane_lt = (1u << lane) - 1u;
         {
             uint32_t ones[8];
 #pragma unroll
@@ -290,34 +299,39 @@ tc_scan_kernel(const uint4* __restrict__ codes, const uint32_t* __restrict__ liv
                     tc_ld32(col0 + 32, v1);
                     tc_wait_ld();
                     if (MODE == 0) {
-                        // D = S + bias: a survivor has D > 0.  Survivors are rare: one max-reduce
-                        // over the 64 registers decides whether to look at individual elements.
-                        int32_t mx = (int32_t)v0[0];
+                        // D = -(S + bias): a survivor has D < 0.  Collect the 64 sign bits with one
+                        // funnel shift per element (four independent chains); survivors are rare.
+                        uint32_t ma = 0, mb = 0, mc = 0, md = 0;
 #pragma unroll
-                        for (int j = 1; j < 32; ++j) mx = max(mx, (int32_t)v0[j]);
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) mx = max(mx, (int32_t)v1[j]);
-                        if (mx > 0 && alive) {
-#pragma unroll
-                            for (int j = 0; j < 64; ++j) {
-                                const int32_t dv = (int32_t)(j < 32 ? v0[j & 31] : v1[j & 31]);
-                                if (dv > 0) {
-                                    const uint32_t q = qb * TC_NQ + half * 64 + j;
-                                    // hamming = popc(q) - S = popc(q) + bias - D
-                                    const uint32_t d = (uint32_t)((int32_t)s_pop[q] + s_bias[q] - dv);
-                                    const uint32_t pos = atomicAdd(&cnt[q], 1u);
-                                    if (pos < cap) buf[(size_t)q * cap + pos] = ((uint64_t)d << 32) | row;
-                                    else *overflow = 1u;
-                                }
+                        for (int j = 0; j < 16; ++j) {
+                            ma = __funnelshift_l(v0[j], ma, 1);
+                            mb = __funnelshift_l(v0[16 + j], mb, 1);
+                            mc = __funnelshift_l(v1[j], mc, 1);
+                            md = __funnelshift_l(v1[16 + j], md, 1);
+                        }
+                        // element e of this half-block sits at bit 63 - e
+                        uint64_t mask = ((uint64_t)((ma << 16) | mb) << 32) | (uint64_t)((mc << 16) | md);
+                        if (!alive) mask = 0;
+                        const uint32_t qbase = qb * TC_NQ + half * 64;
+                        while (__any_sync(0xffffffffu, mask != 0)) {
+                            const bool has = mask != 0;
+                            const uint32_t m = __ballot_sync(0xffffffffu, has);
+                            if (has) {
+                                const int e = __clzll((long long)mask);
+                                mask &= ~(0x8000000000000000ull >> e);
+                                const uint32_t slot = my_count + __popc(m & lane_lt);
+                                if (slot < rec_cap) my_list[slot] = make_uint2(row, qbase + e);
                             }
+                            my_count += __popc(m);
                         }
                     } else {
 #pragma unroll
                         for (int j = 0; j < 64; ++j) {
                             const uint32_t q = qb * TC_NQ + half * 64 + j;
                             const int32_t dv = (int32_t)(j < 32 ? v0[j & 31] : v1[j & 31]);
+                            // D = -(S + bias)  ->  hamming = popc(q) - S = popc(q) + bias + D
                             if (q < nq && in_range && row < n_rows)
-                                dist_out[(size_t)q * dist_stride + row] = (uint32_t)((int32_t)s_pop[q] + s_bias[q] - dv);
+                                dist_out[(size_t)q * dist_stride + row] = (uint32_t)((int32_t)s_pop[q] + s_bias[q] + dv);
                         }
                     }
                 }
@@ -325,6 +339,10 @@ tc_scan_kernel(const uint4* __restrict__ codes, const uint32_t* __restrict__ liv
                 __syncwarp();
                 if (lane == 0) mbar_arrive(acc_empty(b));
             }
+        }
+        if (MODE == 0 && lane == 0) {
+            cta_counts[blockIdx.x * 4 + warp] = min(my_count, rec_cap);
+            if (my_count > rec_cap) *overflow = 1u;
         }
     } else if (warp == 4) {
         // ===================== TMA producer =====================
@@ -392,6 +410,31 @@ tc_scan_kernel(const uint4* __restrict__ codes, const uint32_t* __restrict__ liv
         __syncwarp();
         tc_dealloc(tmem, TC_TMEM_COLS);
     }
+}
+
+// Warp-private survivor records (row, query) -> per-query candidate buffers, same contract as
+// scan_kernel: key = hamming << 32 | row.  The distance is recomputed from the codes (xor + popc
+// over nchunk*4 words, served from L2) — cheaper than carrying it through the epilogue.
+// grid = (ceil(rec_cap / 256), number of lists = 4 x scan CTAs); full occupancy hides the atomics.
+__global__ void tc_scatter_kernel(const uint2* __restrict__ recs, uint32_t rec_cap,
+                                  const uint32_t* __restrict__ list_counts, const uint4* __restrict__ codes,
+                                  int nchunk, const uint32_t* __restrict__ qpack, int qs,
+                                  uint32_t* __restrict__ cnt, uint64_t* __restrict__ buf, uint32_t cap,
+                                  uint32_t* __restrict__ overflow) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= list_counts[blockIdx.y]) return;
+    const uint2 r = recs[(size_t)blockIdx.y * rec_cap + i];
+    const uint32_t row = r.x, q = r.y;
+    const uint4* rc = codes + ((size_t)(row >> 5) * nchunk) * 32 + (row & 31);
+    const uint4* qc = reinterpret_cast<const uint4*>(qpack + (size_t)q * qs);
+    uint32_t d = 0;
+    for (int c = 0; c < nchunk; ++c) {
+        const uint4 a = rc[c * 32], b = qc[c];
+        d += __popc(a.x ^ b.x) + __popc(a.y ^ b.y) + __popc(a.z ^ b.z) + __popc(a.w ^ b.w);
+    }
+    const uint32_t pos = atomicAdd(&cnt[q], 1u);
+    if (pos < cap) buf[(size_t)q * cap + pos] = ((uint64_t)d << 32) | row;
+    else *overflow = 1u;
 }
 
 }  // namespace gvdb

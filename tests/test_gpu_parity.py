@@ -247,3 +247,57 @@ def test_logical_shards_merge_equals_single_index(gv):
         assert np.array_equal(_bits(ms.cpu().numpy()), _bits(os_)), f"S={S}"
         for ix in shards:
             ix.close()
+
+
+@pytest.mark.parametrize("dim", [64, 384, 500, 768])
+def test_tensor_core_scan_distances_bit_exact(gv, dim):
+    """>= 64 queries route the scan to the tcgen05 kernel (gvdb_tc.cuh): all distances exact."""
+    from grape_vector_db_b200 import synth
+    n, nq = 20_011, 150
+    rows = synth.iid_rows(0, n, dim)
+    qs = synth.iid_queries(0, nq, dim)
+    with gv.GpuIndex(dim) as idx:
+        idx.add(rows)
+        codes = oracle.quantize_batch(rows)
+        qc = oracle.quantize_batch(qs)
+        got = idx.hamming(qc)
+        for qi in range(0, nq, 7):
+            assert np.array_equal(got[qi], oracle.hamming_all(qc[qi], codes)), f"query {qi}"
+
+
+def test_tensor_core_search_path(gv, monkeypatch):
+    """Batched search (>= 64 queries, several row segments) through the tcgen05 scan: stage-1
+    candidates, ids and scores bit-exact; and identical to the CUDA-core path (GVDB_TC_MIN_Q)."""
+    from grape_vector_db_b200 import synth
+    rows = synth.lowrank_rows(0, 120_000, 768)
+    qs = synth.lowrank_queries(0, 200, 768)
+    _check_two_stage(gv, rows, qs[:96], 40, 10)
+    rows2 = synth.iid_rows(0, 70_000, 256)
+    qs2 = synth.iid_queries(0, 130, 256)
+    _check_two_stage(gv, rows2, qs2[:70], 300, 20)
+    # heavy ties + tombstones on the tensor-core path
+    rng = np.random.default_rng(5)
+    rows3 = rng.integers(-1, 2, size=(30_000, 48)).astype(np.float32)
+    qs3 = rng.integers(-1, 2, size=(80, 48)).astype(np.float32)
+    with gv.GpuIndex(48) as idx:
+        idx.add(rows3)
+        dead = list(range(0, 30_000, 97))
+        for d in dead:
+            idx.remove(d)
+        ids, sc = idx.search_batch(qs3, 16, 64)
+    live = np.ones(30_000, dtype=bool)
+    live[dead] = False
+    kept = np.flatnonzero(live)
+    oi, os_ = oracle.multi_stage_search_batch(qs3, rows3[live], 64, 16, nthreads=8)
+    assert np.array_equal(ids, kept[oi.astype(np.int64)].astype(np.uint64))
+    assert np.array_equal(_bits(sc), _bits(os_))
+    # same answers with the tensor-core path disabled
+    monkeypatch.setenv("GVDB_TC_MIN_Q", "1000000")
+    with gv.GpuIndex(768) as idx:
+        idx.add(rows)
+        a = idx.search_batch(qs, 10, 40)
+    monkeypatch.delenv("GVDB_TC_MIN_Q")
+    with gv.GpuIndex(768) as idx:
+        idx.add(rows)
+        b = idx.search_batch(qs, 10, 40)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(_bits(a[1]), _bits(b[1]))

@@ -46,13 +46,14 @@ int main(int argc, char** argv) {
         h_qpack[(size_t)q * qs + NCHUNK * 4] = TAU_ALL;
         for (int w = 1; w < 4; ++w) h_qpack[(size_t)q * qs + NCHUNK * 4 + w] = 0;
     }
-    uint4* d_codes; uint32_t *d_qpack, *d_live, *d_ref, *d_tc, *d_qpop, *d_cnt, *d_flag; int8_t* d_qexp; int32_t* d_qbias; uint64_t* d_buf;
+    uint4* d_codes; uint32_t *d_qpack, *d_live, *d_ref, *d_tc, *d_qpop, *d_cnt, *d_flag; int8_t* d_qexp; int32_t* d_qbias; uint2* d_recs; uint32_t* d_ctacnt; uint64_t* d_buf;
     CK(cudaMalloc(&d_codes, code_words * 4)); CK(cudaMalloc(&d_qpack, h_qpack.size() * 4)); CK(cudaMalloc(&d_live, ntiles * 4));
     const bool check = !timing;
     size_t dist_bytes = check ? (size_t)nq * n_rows * 4 : 4;
     CK(cudaMalloc(&d_ref, dist_bytes)); CK(cudaMalloc(&d_tc, dist_bytes));
     CK(cudaMalloc(&d_qexp, (size_t)(nq_pad / TC_NQ) * tc_qblock_bytes(NCHUNK))); CK(cudaMalloc(&d_qbias, nq_pad * 4)); CK(cudaMalloc(&d_qpop, nq_pad * 4));
-    const uint32_t cap = 8192;
+    const uint32_t cap = 8192; const uint32_t rec_cap = 1u << 17;
+    CK(cudaMalloc(&d_recs, (size_t)148 * 4 * rec_cap * 8)); CK(cudaMalloc(&d_ctacnt, 148 * 4 * 4)); CK(cudaMemset(d_ctacnt, 0, 148 * 4 * 4));
     CK(cudaMalloc(&d_cnt, nq_pad * 4)); CK(cudaMalloc(&d_flag, 4)); CK(cudaMalloc(&d_buf, (size_t)nq_pad * cap * 8));
     CK(cudaMemcpy(d_codes, h_codes.data(), code_words * 4, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(d_qpack, h_qpack.data(), h_qpack.size() * 4, cudaMemcpyHostToDevice));
@@ -71,7 +72,7 @@ int main(int argc, char** argv) {
         ref_kernel<NCHUNK><<<(ntiles + 7) / 8, 256>>>(d_codes, ntiles, d_qpack, qs, nq, d_ref, n_rows, n_rows);
         CK(cudaGetLastError());
         tc_scan_kernel<NCHUNK, 1><<<grid, TC_THREADS, smem>>>(d_codes, d_live, 0, ntiles, d_qexp, d_qpop, d_qbias, nq, nq_pad,
-                                                             d_cnt, d_buf, cap, d_flag, d_tc, n_rows, n_rows);
+                                                             d_recs, rec_cap, d_ctacnt, d_flag, d_tc, n_rows, n_rows);
         CK(cudaGetLastError());
         CK(cudaDeviceSynchronize());
         std::vector<uint32_t> a((size_t)nq * n_rows), b((size_t)nq * n_rows);
@@ -95,7 +96,8 @@ int main(int argc, char** argv) {
         uint64_t* d_buf2; CK(cudaMalloc(&d_buf2, (size_t)nq_pad * bigcap * 8));
         CK(cudaMemset(d_cnt, 0, nq_pad * 4));
         tc_scan_kernel<NCHUNK, 0><<<grid, TC_THREADS, smem>>>(d_codes, d_live, 0, ntiles, d_qexp, d_qpop, d_qbias, nq, nq_pad,
-                                                             d_cnt, d_buf2, bigcap, d_flag, nullptr, 0, n_rows);
+                                                             d_recs, rec_cap, d_ctacnt, d_flag, nullptr, 0, n_rows);
+        tc_scatter_kernel<<<dim3((rec_cap + 255) / 256, grid * 4), 256>>>(d_recs, rec_cap, d_ctacnt, d_codes, NCHUNK, d_qpack, qs, d_cnt, d_buf2, bigcap, d_flag);
         CK(cudaGetLastError());
         CK(cudaDeviceSynchronize());
         std::vector<uint32_t> h_cnt(nq_pad);
@@ -119,21 +121,25 @@ int main(int argc, char** argv) {
         if (badq) return 1;
     } else {
         // timing in search mode with a threshold that lets nothing through (tau = 0)
-        for (uint32_t q = 0; q < nq; ++q) h_qpack[(size_t)q * qs + NCHUNK * 4] = 200;   // ham < 200 never happens on random codes
+        const uint32_t tau_t = argc > 4 ? atoi(argv[4]) : 200;   // 200: no survivors; 352: ~1%; 335: ~2e-4
+        for (uint32_t q = 0; q < nq; ++q) h_qpack[(size_t)q * qs + NCHUNK * 4] = tau_t;
         CK(cudaMemcpy(d_qpack, h_qpack.data(), h_qpack.size() * 4, cudaMemcpyHostToDevice));
         tc_bias_kernel<<<(nq_pad + 127) / 128, 128>>>(d_qpack, qs, NCHUNK, d_qpop, nq, nq_pad, d_qexp, d_qbias, 0);
         CK(cudaFuncSetAttribute(tc_scan_kernel<NCHUNK, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
         for (int rep = 0; rep < 3; ++rep)
             tc_scan_kernel<NCHUNK, 0><<<grid, TC_THREADS, smem>>>(d_codes, d_live, 0, ntiles, d_qexp, d_qpop, d_qbias, nq, nq_pad,
-                                                                 d_cnt, d_buf, cap, d_flag, nullptr, 0, n_rows);
+                                                                 d_recs, rec_cap, d_ctacnt, d_flag, nullptr, 0, n_rows);
         CK(cudaDeviceSynchronize());
         const int reps = 10;
         for (int dbg : {0, 1}) {
         cudaEventRecord(e0);
-        for (int rep = 0; rep < reps; ++rep)
+        for (int rep = 0; rep < reps; ++rep) {
+            cudaMemsetAsync(d_cnt, 0, nq_pad * 4);
             tc_scan_kernel<NCHUNK, 0><<<grid, TC_THREADS, smem>>>(d_codes, d_live, 0, ntiles, d_qexp, d_qpop, d_qbias, nq, nq_pad,
-                                                                 d_cnt, d_buf, cap, d_flag, nullptr, 0, n_rows, dbg);
+                                                                 d_recs, rec_cap, d_ctacnt, d_flag, nullptr, 0, n_rows, dbg);
+            if (!(dbg & 1)) tc_scatter_kernel<<<dim3((16384 + 255) / 256, grid * 4), 256>>>(d_recs, rec_cap, d_ctacnt, d_codes, NCHUNK, d_qpack, qs, d_cnt, d_buf, cap, d_flag);
+        }
         cudaEventRecord(e1);
         CK(cudaDeviceSynchronize());
         float ms = 0; cudaEventElapsedTime(&ms, e0, e1); ms /= reps;
