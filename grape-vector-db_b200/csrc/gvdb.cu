@@ -288,14 +288,35 @@ bool tc_supported(int nchunk) { return nchunk == 1 || nchunk == 2 || nchunk == 3
 
 // MODE 0: survivors -> warp-private record lists -> tc_scatter_kernel -> per-query buffers.
 // MODE 1: every distance to dist_out (parity).
+// Work split of one tcgen05 scan launch: items = query slices x row slices, one CTA per SM looping
+// over items.  Pick the row-slice count that fills whole waves of SMs.
+struct TcSplit { uint32_t qslices, rslices, grid; };
+TcSplit tc_split(const gvdb_index* h, uint32_t ngroups, uint32_t nq_pad) {
+    const uint32_t sms = (uint32_t)h->sm_count;
+    const uint32_t qsl = (nq_pad / TC_NQ + TC_QBLOCKS - 1) / TC_QBLOCKS;
+    const uint32_t rmax = std::max<uint32_t>(1, std::min<uint32_t>(ngroups, std::max<uint32_t>(1, 8 * sms / qsl)));
+    uint32_t best = 1;
+    double best_eff = 0.0;
+    for (uint32_t r = 1; r <= rmax; ++r) {
+        const uint64_t items = (uint64_t)qsl * r;
+        const uint64_t waves = (items + sms - 1) / sms;
+        const double eff = (double)items / (double)(waves * sms);
+        if (eff > best_eff + 1e-9) { best_eff = eff; best = r; }
+    }
+    return TcSplit{qsl, best, (uint32_t)std::min<uint64_t>((uint64_t)qsl * best, sms)};
+}
+
+// MODE 0: survivors -> warp-private record lists -> tc_scatter_kernel -> per-query buffers.
+// MODE 1: every distance to dist_out (parity).
 template <int MODE>
 void launch_tc_scan(gvdb_index* h, Workspace* ws, cudaStream_t st, uint32_t tile_lo, uint32_t tile_hi,
                     uint32_t nq, uint32_t nq_pad, uint32_t* cnt, uint64_t* buf, uint32_t cap,
                     uint32_t* overflow, uint32_t* dist_out, uint64_t dist_stride) {
     const uint32_t ngroups = (tile_hi - tile_lo + 3) / 4;
-    const uint32_t grid = std::min<uint32_t>(ngroups, (uint32_t)h->sm_count);
+    const TcSplit sp = tc_split(h, ngroups, nq_pad);
+    const uint32_t grid = sp.grid;
     const uint32_t nlists = grid * 4;
-    const size_t smem = (size_t)TC_STAGES * TC_STAGE_BYTES + (size_t)nq_pad * 8;
+    const size_t smem = (size_t)TC_QBLOCKS * tc_qblock_bytes(h->nchunk);
     uint32_t rec_cap = 0;
     if (MODE == 0) {
         // expected survivors per launch <= nq * cap / 4 (segment sizing); 4x head-room per list
@@ -314,12 +335,13 @@ void launch_tc_scan(gvdb_index* h, Workspace* ws, cudaStream_t st, uint32_t tile
     case N: {                                                                                        \
         static bool attr = false;                                                                    \
         if (!attr) {                                                                                 \
-            CU(cudaFuncSetAttribute(tc_scan_kernel<N, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)); \
+            CU(cudaFuncSetAttribute(tc_scan_kernel<N, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                    (int)(TC_QBLOCKS * tc_qblock_bytes(N))));                        \
             attr = true;                                                                             \
         }                                                                                            \
         tc_scan_kernel<N, MODE><<<grid, TC_THREADS, smem, st>>>(h->codes, h->live, tile_lo, tile_hi, qexp, qpop, qbias, \
-                                                               nq, nq_pad, recs, rec_cap, lc, overflow, dist_out,       \
-                                                               dist_stride, h->n_rows, 0);                              \
+                                                               nq, nq_pad, sp.qslices, sp.rslices, recs, rec_cap, lc,  \
+                                                               overflow, dist_out, dist_stride, h->n_rows, 0);          \
         break;                                                                                       \
     }
     switch (h->nchunk) {

@@ -2,35 +2,42 @@
 //
 // Used when a corpus pass serves a large query tile (>= 64 queries), where the scan really is a
 // dense contraction: rows x queries x dim.  The CUDA-core kernel (scan_kernel) is then bound by
-// the integer pipes (16 popc + 64 LOP3 per clk per SM); tcgen05.mma.kind::i8 does 8192 MAC/clk/SM.
+// the integer pipes (16 popc + 64 LOP3 per clk per SM); tcgen05.mma.kind::i8 does 8192 MAC/clk/SM
+// (measured with tools/mma_floor.cu: 64 clk per M128 x N128 x K32 MMA, A in TMEM or shared memory,
+// any shared-memory layout, identical for kind::f8f6f4).
 //
-// Exactness.  Row codes are expanded on chip to A in {0,1} (int8), query codes are expanded once
-// per batch to B in {+1,-1} (int8, +1 where the query bit is 1).  Over the code bits,
-//     S = sum_k A_k * B_k = n11 - n10         (int32 accumulation, exact)
-//     hamming = n10 + n01 = popc(q) - S       (popc(q) = n11 + n01)
+// Exactness.  Row codes are expanded on chip to A in {0,-128} (int8), query codes are expanded
+// once per batch to B in {+1,-1} (int8, +1 where the query bit is 1).  Over the code bits,
+//     S = n11 - n10,   sum_k A_k * B_k = -128 * S        (int32 accumulation, exact)
+//     hamming = n10 + n01 = popc(q) - S                  (popc(q) = n11 + n01)
 // so hamming < tau  <=>  S + (tau - popc(q)) > 0.  Pad bits are 0 in A and contribute nothing.
-// The kernel stores B NEGATED (-1 where the query bit is 1) and a negated bias, so the
-// accumulator is D = -(S + tau - popc(q)) and a survivor is simply D < 0: its sign bit.
 // The per-query bias v = tau - popc(q) is added ON the tensor core by one extra K=32 MMA per
-// accumulator block (A = 32 ones per row, B = 32 int8 digits summing to v), so the epilogue is
-// a pure sign test on registers: the tensor core's operand traffic saturates shared memory,
-// and a per-element threshold load from shared memory would starve (measured: 3x slower).
-// The K order of the expansion is a fixed permutation of the code bits applied to rows and
-// queries alike (Hamming distance is invariant to it); it is chosen so that one row word
-// expands with SHF + LOP3 only:  out[8*w + i] = (code_word[w] >> i) & 0x01010101.
+// accumulator block (A = 32 x -128 per row, B = 32 int8 digits summing to v), so the accumulator
+// is D = -128 * (S + v), a survivor is simply D < 0, and the epilogue is a pure sign test on
+// registers (a per-element threshold load from shared memory measured 3x slower).
+// -128 rather than 1 because it is the byte's top bit: one row word expands with a LEFT shift
+// (which the compiler may issue on the FMA pipe as IMAD.SHL) plus one LOP3 per output word,
+//     out[8*w + i] = (code_word[w] << (7 - i)) & 0x80808080,
+// so the expansion is spread over two issue pipes.  The K order this implies is a fixed
+// permutation of the code bits applied to rows and queries alike (Hamming distance is invariant).
 //
-// Data flow per CTA (persistent over groups of 128 rows = 4 code tiles):
-//   warps 0-3  "row owners": lane = row.  Load the row's code (coalesced, blocked layout),
-//              expand it and write it into TMEM as the A operand (tcgen05.st, K/4 columns);
-//              later read the int32 accumulators back (tcgen05.ld), compare with the per-query
-//              threshold and append survivors (key = hamming << 32 | row) — same contract as
-//              scan_kernel MODE 0.  MODE 1 writes every distance (parity tests).
-//   warp 4     TMA producer: bulk-copies 16 KB blocks of pre-expanded queries (already in the
-//              UMMA K-major no-swizzle core-matrix order) into a 4-stage shared-memory ring.
-//   warp 5     MMA issuer: one elected lane issues tcgen05.mma (M=128, N=128, K=32), A from
-//              TMEM, B from shared memory, D in TMEM (2 x 128 columns, double buffered).
-//   mbarriers  full/empty per stage, a_ready, acc_full/acc_empty per accumulator buffer;
-//              tcgen05.commit signals MMA completion.
+// Work decomposition.  item = (query slice, row slice).  A query slice is up to TC_QBLOCKS blocks
+// of 128 queries whose expanded codes (+ bias digits) stay RESIDENT in shared memory (200 KB at
+// 768 bits) for the whole item; the item's rows stream through TMEM as the A operand, 128 at a
+// time.  (Streaming the queries through a shared-memory ring instead needs 64 B/clk/SM from L2,
+// more than the L2 delivers to 148 SMs at once: that version measured 47 % of the MMA floor.)
+//
+// Warp roles per CTA (one CTA per SM, persistent over items):
+//   warps 0-3  expanders: lane = row.  Load the row's code (coalesced, blocked layout, next group
+//              prefetched), expand it and write it into TMEM as the A operand (tcgen05.st), in
+//              two K halves with their own ready/free barriers so that rewriting A for the next
+//              128 rows overlaps the MMAs still reading the other half.
+//   warps 4-7  epilogue: read the int32 accumulators back (tcgen05.ld), sign-test them and append
+//              survivors to warp-private record lists (MODE 0), or write every distance (MODE 1).
+//   warp 8     one thread: TMA bulk loads of the query slice, then tcgen05.mma issue
+//              (M=128, N=128, K=32; A from TMEM, B from shared memory, D in TMEM, 2 buffers).
+//   mbarriers  b_full/b_free, a_ready/a_free per K half, acc_full/acc_empty per accumulator
+//              buffer; tcgen05.commit signals MMA completion.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -39,16 +46,16 @@
 
 namespace gvdb {
 
-constexpr int TC_ROWS = 128;        // rows per CTA group (UMMA M)
+constexpr int TC_ROWS = 128;        // rows per group (UMMA M)
 constexpr int TC_NQ = 128;          // queries per accumulator block (UMMA N)
-constexpr int TC_KSTAGE = 128;      // K bytes per shared-memory stage (4 MMAs of K=32)
-constexpr int TC_STAGES = 4;
+constexpr int TC_KSTAGE = 128;      // K bytes per 16 KB query sub-block = one 16-byte code chunk
 constexpr int TC_STAGE_BYTES = TC_NQ * TC_KSTAGE;   // 16 KB
-constexpr int TC_THREADS = 192;     // 4 row-owner warps + producer warp + MMA warp
+constexpr int TC_QBLOCKS = 2;       // resident query blocks per item = TMEM accumulator buffers
+constexpr int TC_THREADS = 288;     // 4 expander warps + 4 epilogue warps + loader/MMA-issuer warp
 constexpr uint32_t TC_TMEM_COLS = 512;
 constexpr int TC_BIAS_BYTES = TC_NQ * 32;           // 4 KB: one K=32 slice of per-query bias digits
 __host__ __device__ constexpr size_t tc_qblock_bytes(int nchunk) {
-    return (size_t)(nchunk * 128 / TC_KSTAGE) * TC_STAGE_BYTES + TC_BIAS_BYTES;
+    return (size_t)nchunk * TC_STAGE_BYTES + TC_BIAS_BYTES;
 }
 
 // ---- PTX wrappers ------------------------------------------------------------------------------
@@ -57,6 +64,14 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     while (!mbar_try_wait(bar, parity)) {}
+}
+// One lane of a converged warp; the compiler keeps the surrounding control flow warp-uniform, so
+// descriptors and TMEM addresses stay in uniform registers (an `if (lane == 0)` around the MMA
+// loop costs a register-to-uniform waterfall per MMA: ~72 clk per issue, above the 64 clk floor).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+    return pred != 0;
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -76,8 +91,8 @@ __device__ __forceinline__ void tc_mma_i8_ts(uint32_t d_tmem, uint32_t a_tmem, u
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, {%5, %5, %5, %5}, p;\n\t}"
-        :: "r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(0u) : "memory");
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, p;\n\t}"
+        :: "r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
 }
 // 32 lanes x 8 columns per call (each thread: its own lane, 8 consecutive 32-bit columns)
 __device__ __forceinline__ void tc_st8(uint32_t taddr, const uint32_t (&v)[8]) {
@@ -87,14 +102,6 @@ __device__ __forceinline__ void tc_st8(uint32_t taddr, const uint32_t (&v)[8]) {
 }
 __device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&v)[16]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-        : "r"(taddr) : "memory");
-}
-
 __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -117,12 +124,13 @@ __device__ __forceinline__ uint64_t tc_smem_desc(uint32_t smem_addr, uint32_t lb
 __host__ __device__ constexpr uint32_t tc_idesc_i8(int M, int N) {
     return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
+constexpr uint32_t TC_A_BIT4 = 0x80808080u;   // A = -128 where the code bit is set
 
 // ---- query pre-expansion ---------------------------------------------------------------------------
 // qpack (code words + tau, as produced by ingest_kernel<QUERY>) -> qexp, int8 +-1 in the exact byte
-// order the TMA stages need:  block (qb, ks) of 16 KB at qb*tc_qblock_bytes + ks*16384 (the last
-// 4 KB of a query block hold the bias digits, written by tc_bias_kernel), inside a 16 KB block
-//   offset(n, kk) = (n/8)*1024 + (kk/16)*128 + (n%8)*16 + (kk%16),  n = query in block, kk = K byte in stage
+// order the resident blocks need:  sub-block (qb, ks) of 16 KB at qb*tc_qblock_bytes + ks*16384 (the
+// last 4 KB of a query block hold the bias digits, written by tc_bias_kernel), inside a sub-block
+//   offset(n, kk) = (n/8)*1024 + (kk/16)*128 + (n%8)*16 + (kk%16),  n = query in block, kk = K byte
 // K byte k of a query  <->  code bit (w*32 + 8*b + i) with  k = (8*w + i)*4 + b   (see header).
 // Queries beyond nq (padding up to a multiple of 128) are all zero.  Also writes popc(q).
 __global__ void tc_expand_queries_kernel(const uint32_t* __restrict__ qpack, int qs, int nchunk, uint32_t nq,
@@ -139,9 +147,8 @@ __global__ void tc_expand_queries_kernel(const uint32_t* __restrict__ qpack, int
         if (q < nq) {
             const uint32_t word = qpack[(size_t)q * qs + w];
             const uint32_t bits = (word >> i) & 0x01010101u;            // byte b = code bit 8b+i
-            // negated B: query bit 1 -> -1 (0xFF), 0 -> +1 (0x01)
 #pragma unroll
-            for (int b = 0; b < 4; ++b) out |= (((bits >> (8 * b)) & 1u) ? 0xFFu : 0x01u) << (8 * b);
+            for (int b = 0; b < 4; ++b) out |= (((bits >> (8 * b)) & 1u) ? 0x01u : 0xFFu) << (8 * b);
             if (i == 0) pop += __popc(word);
         }
         const int k = k4 * 4;
@@ -181,232 +188,313 @@ __global__ void tc_bias_kernel(const uint32_t* __restrict__ qpack, int qs, int n
     if (zero_bias) v = 0;
     qbias[q] = v;
     const uint32_t qb = q / TC_NQ, n = q % TC_NQ;
-    int8_t* blk = qexp + (size_t)qb * tc_qblock_bytes(nchunk) + (size_t)(K / TC_KSTAGE) * TC_STAGE_BYTES;
+    int8_t* blk = qexp + (size_t)qb * tc_qblock_bytes(nchunk) + (size_t)nchunk * TC_STAGE_BYTES;
     int rest = v;
     for (int kk = 0; kk < 32; ++kk) {
         int d = rest > 127 ? 127 : (rest < -127 ? -127 : rest);
         rest -= d;
-        blk[(n / 8) * 256 + (kk / 16) * 128 + (n % 8) * 16 + (kk % 16)] = (int8_t)(-d);   // negated, like B
+        blk[(n / 8) * 256 + (kk / 16) * 128 + (n % 8) * 16 + (kk % 16)] = (int8_t)d;
     }
 }
 
 // ---- the scan ------------------------------------------------------------------------------------------
 // MODE 0: append survivors (search).  MODE 1: write all distances (dist_out[q*stride + row]).
+// prof (optional, tools/tc_probe): cycle accounting of CTA 0.
 template <int NCHUNK, int MODE>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_scan_kernel(const uint4* __restrict__ codes, const uint32_t* __restrict__ live, uint32_t tile_lo,
                uint32_t tile_hi, const int8_t* __restrict__ qexp, const uint32_t* __restrict__ qpop,
-               const int32_t* __restrict__ qbias, uint32_t nq, uint32_t nq_pad,
-               uint2* __restrict__ recs, uint32_t rec_cap, uint32_t* __restrict__ cta_counts,
-               uint32_t* __restrict__ overflow, uint32_t* __restrict__ dist_out, uint64_t dist_stride,
-               uint64_t n_rows, int dbg = 0) {
+               const int32_t* __restrict__ qbias, uint32_t nq, uint32_t nq_pad, uint32_t n_qslices,
+               uint32_t n_rslices, uint2* __restrict__ recs, uint32_t rec_cap,
+               uint32_t* __restrict__ list_counts, uint32_t* __restrict__ overflow,
+               uint32_t* __restrict__ dist_out, uint64_t dist_stride, uint64_t n_rows, int dbg = 0,
+               unsigned long long* __restrict__ prof = nullptr) {
     constexpr int K = NCHUNK * 128;
-    constexpr int KS = K / TC_KSTAGE;          // stages per accumulator block
-    constexpr int A_COLS = K / 4;              // TMEM columns of the A operand (+8: the ones slice)
+    constexpr int A_COLS = K / 4;              // TMEM columns of the A operand (+8: the bias slice)
+    constexpr int LO = (NCHUNK + 1) / 2;       // chunks in the low half of A (own ready/free barriers)
     constexpr uint32_t IDESC = tc_idesc_i8(TC_ROWS, TC_NQ);
+    constexpr uint32_t QBLOCK_BYTES = (uint32_t)tc_qblock_bytes(NCHUNK);
     static_assert(A_COLS + 8 + 2 * TC_NQ <= 512, "TMEM budget");
 
-    extern __shared__ __align__(1024) uint8_t smem[];
-    uint8_t* stage_base = smem;                                           // TC_STAGES * 16 KB
-    int32_t* s_bias = reinterpret_cast<int32_t*>(smem + TC_STAGES * TC_STAGE_BYTES);  // nq_pad biases (slow path only)
-    uint32_t* s_pop = reinterpret_cast<uint32_t*>(s_bias + nq_pad);                   // nq_pad popcounts
-    __shared__ __align__(8) uint64_t bars[TC_STAGES * 2 + 1 + 4];
+    extern __shared__ __align__(1024) uint8_t smem[];      // TC_QBLOCKS resident query blocks
+    __shared__ int32_t s_bias[TC_QBLOCKS * TC_NQ];           // MODE 1 only
+    __shared__ uint32_t s_pop[TC_QBLOCKS * TC_NQ];
+    __shared__ __align__(8) uint64_t bars[10];
     __shared__ uint32_t s_tmem_base;
     const uint32_t bar0 = smem_u32(bars);
-    auto full_bar = [&](int s) { return bar0 + 8u * s; };
-    auto empty_bar = [&](int s) { return bar0 + 8u * (TC_STAGES + s); };
-    const uint32_t a_ready = bar0 + 8u * (2 * TC_STAGES);
-    auto acc_full = [&](int b) { return bar0 + 8u * (2 * TC_STAGES + 1 + b); };
-    auto acc_empty = [&](int b) { return bar0 + 8u * (2 * TC_STAGES + 3 + b); };
+    const uint32_t b_full = bar0, b_free = bar0 + 8;
+    auto a_ready = [&](int h) { return bar0 + 8u * (2 + h); };
+    auto a_free = [&](int h) { return bar0 + 8u * (4 + h); };
+    auto acc_full = [&](int b) { return bar0 + 8u * (6 + b); };
+    auto acc_empty = [&](int b) { return bar0 + 8u * (8 + b); };
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t nqb = nq_pad / TC_NQ;
     const uint32_t ngroups = (tile_hi - tile_lo + 3) / 4;
+    const uint32_t n_items = n_qslices * n_rslices;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < TC_STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-        mbar_init(a_ready, 4);
+        mbar_init(b_full, 1); mbar_init(b_free, 1);
+        for (int h = 0; h < 2; ++h) { mbar_init(a_ready(h), 4); mbar_init(a_free(h), 1); }
         for (int b = 0; b < 2; ++b) { mbar_init(acc_full(b), 1); mbar_init(acc_empty(b), 4); }
         fence_mbar_init();
     }
-    if (warp == 5) tc_alloc(smem_u32(&s_tmem_base), TC_TMEM_COLS);
-    for (uint32_t q = threadIdx.x; q < nq_pad; q += TC_THREADS) {
-        s_bias[q] = qbias[q];
-        s_pop[q] = q < nq ? qpop[q] : 0u;
-    }
+    if (warp == 8) tc_alloc(smem_u32(&s_tmem_base), TC_TMEM_COLS);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = s_tmem_base;
-    const uint32_t tmem_a = tmem;                 // columns [0, A_COLS): codes; [A_COLS, A_COLS+8): ones
+    const uint32_t tmem_a = tmem;                 // columns [0, A_COLS): codes; [A_COLS, A_COLS+8): bias slice
     const uint32_t tmem_d = tmem + A_COLS + 8;    // two accumulator buffers of TC_NQ columns
+    const uint32_t lane_taddr = (uint32_t)((warp & 3) * 32) << 16;
+
+    unsigned long long pw[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#define TC_PROF_T0() const long long t0__ = prof ? clock64() : 0
+#define TC_PROF_ADD(i) do { if (prof) pw[i] += (unsigned long long)(clock64() - t0__); } while (0)
+
+    // item -> (query blocks, row groups)
+    auto item_range = [&](uint32_t item, uint32_t& qb0, uint32_t& nb, uint32_t& g_lo, uint32_t& g_hi) {
+        const uint32_t qsl = item / n_rslices, rsl = item % n_rslices;
+        qb0 = qsl * TC_QBLOCKS;
+        nb = min((uint32_t)TC_QBLOCKS, nqb - qb0);
+        g_lo = (uint32_t)((uint64_t)ngroups * rsl / n_rslices);
+        g_hi = (uint32_t)((uint64_t)ngroups * (rsl + 1) / n_rslices);
+    };
 
     if (warp < 4) {
-        // ===================== row owners: expand A, then epilogue =====================
-        uint32_t acc_phase[2] = {0, 0};
-        uint32_t it = 0;
-        const uint32_t lane_taddr = (uint32_t)(warp * 32) << 16;
-        // Survivor records of this warp: a private list, slots handed out with ballot + popc from a
-        // register counter.  No shared memory and no atomics in the epilogue: while MMAs run, the
-        // tensor core's operand traffic owns the shared-memory pipe and the L2 round trip of a
-        // global atomic would sit on the accumulator hand-off (both measured: 3x slower scans).
-        uint2* my_list = recs + (size_t)(blockIdx.x * 4 + warp) * rec_cap;
-        uint32_t my_count = 0;
-        const uint32_t lane_lt = (1u << lane) - 1u;
+        // ===================== expanders: codes -> A operand in TMEM =====================
+        uint32_t free_phase[2] = {1, 1};          // first wait on a fresh barrier passes
         {
             uint32_t ones[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) ones[i] = 0x01010101u;
+            for (int i = 0; i < 8; ++i) ones[i] = TC_A_BIT4;
             tc_st8(tmem_a + lane_taddr + A_COLS, ones);     // A slice of the bias MMA
         }
-        for (uint32_t g = blockIdx.x; g < ngroups; g += gridDim.x) {
+        auto load_codes = [&](uint32_t g, uint4 (&r)[NCHUNK]) {
             const uint32_t tile = tile_lo + g * 4 + warp;
             const bool in_range = tile < tile_hi;
-            const uint32_t row = tile * 32u + lane;
-            const bool alive = in_range && ((live[in_range ? tile : tile_lo] >> lane) & 1u);
-            uint4 r[NCHUNK];
 #pragma unroll
             for (int c = 0; c < NCHUNK; ++c)
                 r[c] = in_range ? ldg_stream(codes + ((size_t)tile * NCHUNK + c) * 32 + lane) : make_uint4(0, 0, 0, 0);
-            // The previous group's last accumulator has been consumed by this warp's epilogue, and
-            // every MMA that read A completed before that acc_full fired: A may be overwritten.
+        };
+        auto expand = [&](const uint4 (&r)[NCHUNK], int c_lo, int c_hi, int h) {
+            { TC_PROF_T0(); mbar_wait(a_free(h), free_phase[h]); TC_PROF_ADD(h); }   // MMAs that read this half have retired
+            free_phase[h] ^= 1u;
+            tc_fence_after();
+            TC_PROF_T0();
 #pragma unroll
             for (int c = 0; c < NCHUNK; ++c) {
+                if (c < c_lo || c >= c_hi) continue;
                 const uint32_t w4[4] = {r[c].x, r[c].y, r[c].z, r[c].w};
 #pragma unroll
                 for (int wi = 0; wi < 4; ++wi) {
                     uint32_t v[8];
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) v[i] = (w4[wi] >> i) & 0x01010101u;
+                    for (int i = 0; i < 8; ++i) v[i] = (w4[wi] << (7 - i)) & TC_A_BIT4;
                     tc_st8(tmem_a + lane_taddr + (uint32_t)((c * 4 + wi) * 8), v);
                 }
             }
             tc_wait_st();
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(a_ready);
-
-            for (uint32_t qb = 0; qb < nqb; ++qb, ++it) {
-                const uint32_t b = it & 1u;
-                mbar_wait(acc_full(b), acc_phase[b]);
-                acc_phase[b] ^= 1u;
-                tc_fence_after();
+            if (lane == 0) mbar_arrive(a_ready(h));
+            TC_PROF_ADD(2 + h);
+        };
+        for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x) {
+            uint32_t qb0, nb, g_lo, g_hi;
+            item_range(item, qb0, nb, g_lo, g_hi);
+            uint4 r[NCHUNK];
+            if (g_lo < g_hi) load_codes(g_lo, r);
+            for (uint32_t g = g_lo; g < g_hi; ++g) {
+                uint4 rn[NCHUNK];
+                if (g + 1 < g_hi) load_codes(g + 1, rn);       // in flight while this group expands
+                expand(r, 0, LO, 0);
+                expand(r, LO, NCHUNK, 1);
+#pragma unroll
+                for (int c = 0; c < NCHUNK; ++c) r[c] = rn[c];
+            }
+        }
+        if (prof && blockIdx.x == 0 && threadIdx.x == 0)
+            for (int i = 0; i < 4; ++i) prof[i] = pw[i];
+    } else if (warp < 8) {
+        // ===================== epilogue: accumulators -> survivors / distances =====================
+        const int ew = warp - 4;
+        uint32_t full_phase[2] = {0, 0};
+        uint32_t it = 0;                          // running accumulator-block counter (buffer = it & 1)
+        // Survivor records of this warp: a private list, slots handed out with ballot + popc from a
+        // register counter.  No shared memory and no atomics in the epilogue.
+        uint2* my_list = recs + (size_t)(blockIdx.x * 4 + ew) * rec_cap;
+        uint32_t my_count = 0;
+        const uint32_t lane_lt = (1u << lane) - 1u;
+        for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x) {
+            uint32_t qb0, nb, g_lo, g_hi;
+            item_range(item, qb0, nb, g_lo, g_hi);
+            if (MODE == 1) {
+                asm volatile("bar.sync 1, 128;" ::: "memory");      // previous item's readers are done
+                for (uint32_t i = threadIdx.x - 128; i < nb * TC_NQ; i += 128) {
+                    const uint32_t q = qb0 * TC_NQ + i;
+                    s_bias[i] = qbias[q];
+                    s_pop[i] = q < nq ? qpop[q] : 0u;
+                }
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+            }
+            for (uint32_t g = g_lo; g < g_hi; ++g) {
+                const uint32_t tile = tile_lo + g * 4 + ew;
+                const bool in_range = tile < tile_hi;
+                const uint32_t row = tile * 32u + lane;
+                const bool alive = in_range && ((live[in_range ? tile : tile_lo] >> lane) & 1u);
+                for (uint32_t blk = 0; blk < nb; ++blk, ++it) {
+                    const uint32_t b = it & 1u;
+                    const uint32_t qbase = (qb0 + blk) * TC_NQ, qloc = blk * TC_NQ;
+                    { TC_PROF_T0(); mbar_wait(acc_full(b), full_phase[b]); TC_PROF_ADD(0); }
+                    full_phase[b] ^= 1u;
+                    tc_fence_after();
+                    TC_PROF_T0();
 #pragma unroll 1
-                for (int half = 0; half < ((dbg & 1) ? 0 : 2); ++half) {
-                    uint32_t v0[32], v1[32];
-                    const uint32_t col0 = tmem_d + lane_taddr + b * TC_NQ + half * 64;
-                    tc_ld32(col0, v0);
-                    tc_ld32(col0 + 32, v1);
-                    tc_wait_ld();
-                    if (MODE == 0) {
-                        // D = -(S + bias): a survivor has D < 0.  Collect the 64 sign bits with one
-                        // funnel shift per element (four independent chains); survivors are rare.
-                        uint32_t ma = 0, mb = 0, mc = 0, md = 0;
+                    for (int half = 0; half < ((dbg & 1) ? 0 : 2); ++half) {
+                        uint32_t v0[32], v1[32];
+                        const uint32_t col0 = tmem_d + lane_taddr + b * TC_NQ + half * 64;
+                        tc_ld32(col0, v0);
+                        tc_ld32(col0 + 32, v1);
+                        tc_wait_ld();
+                        if (MODE == 0) {
+                            // D = -128 (S + bias): a survivor has D < 0.  Collect the 64 sign bits with
+                            // one funnel shift per element (four independent chains); survivors are rare.
+                            uint32_t ma = 0, mb = 0, mc = 0, md = 0;
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            ma = __funnelshift_l(v0[j], ma, 1);
-                            mb = __funnelshift_l(v0[16 + j], mb, 1);
-                            mc = __funnelshift_l(v1[j], mc, 1);
-                            md = __funnelshift_l(v1[16 + j], md, 1);
-                        }
-                        // element e of this half-block sits at bit 63 - e
-                        uint64_t mask = ((uint64_t)((ma << 16) | mb) << 32) | (uint64_t)((mc << 16) | md);
-                        if (!alive) mask = 0;
-                        const uint32_t qbase = qb * TC_NQ + half * 64;
-                        while (__any_sync(0xffffffffu, mask != 0)) {
-                            const bool has = mask != 0;
-                            const uint32_t m = __ballot_sync(0xffffffffu, has);
-                            if (has) {
-                                const int e = __clzll((long long)mask);
-                                mask &= ~(0x8000000000000000ull >> e);
-                                const uint32_t slot = my_count + __popc(m & lane_lt);
-                                if (slot < rec_cap) my_list[slot] = make_uint2(row, qbase + e);
+                            for (int j = 0; j < 16; ++j) {
+                                ma = __funnelshift_l(v0[j], ma, 1);
+                                mb = __funnelshift_l(v0[16 + j], mb, 1);
+                                mc = __funnelshift_l(v1[j], mc, 1);
+                                md = __funnelshift_l(v1[16 + j], md, 1);
                             }
-                            my_count += __popc(m);
-                        }
-                    } else {
+                            // element e of this half-block sits at bit 63 - e
+                            uint64_t mask = ((uint64_t)((ma << 16) | mb) << 32) | (uint64_t)((mc << 16) | md);
+                            if (!alive) mask = 0;
+                            const uint32_t q0 = qbase + half * 64;
+                            while (__any_sync(0xffffffffu, mask != 0)) {
+                                const bool has = mask != 0;
+                                const uint32_t m = __ballot_sync(0xffffffffu, has);
+                                if (has) {
+                                    const int e = __clzll((long long)mask);
+                                    mask &= ~(0x8000000000000000ull >> e);
+                                    const uint32_t slot = my_count + __popc(m & lane_lt);
+                                    if (slot < rec_cap) my_list[slot] = make_uint2(row, q0 + e);
+                                }
+                                my_count += __popc(m);
+                            }
+                        } else {
 #pragma unroll
-                        for (int j = 0; j < 64; ++j) {
-                            const uint32_t q = qb * TC_NQ + half * 64 + j;
-                            const int32_t dv = (int32_t)(j < 32 ? v0[j & 31] : v1[j & 31]);
-                            // D = -(S + bias)  ->  hamming = popc(q) - S = popc(q) + bias + D
-                            if (q < nq && in_range && row < n_rows)
-                                dist_out[(size_t)q * dist_stride + row] = (uint32_t)((int32_t)s_pop[q] + s_bias[q] + dv);
+                            for (int j = 0; j < 64; ++j) {
+                                const uint32_t q = qbase + half * 64 + j;
+                                const uint32_t ql = qloc + half * 64 + j;
+                                const int32_t dv = (int32_t)(j < 32 ? v0[j & 31] : v1[j & 31]) >> 7;   // -(S + bias)
+                                // hamming = popc(q) - S = popc(q) + bias + D/128
+                                if (q < nq && in_range && row < n_rows)
+                                    dist_out[(size_t)q * dist_stride + row] = (uint32_t)((int32_t)s_pop[ql] + s_bias[ql] + dv);
+                            }
                         }
                     }
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(acc_empty(b));
+                    TC_PROF_ADD(1);
                 }
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(acc_empty(b));
             }
         }
         if (MODE == 0 && lane == 0) {
-            cta_counts[blockIdx.x * 4 + warp] = min(my_count, rec_cap);
+            list_counts[blockIdx.x * 4 + ew] = min(my_count, rec_cap);
             if (my_count > rec_cap) *overflow = 1u;
         }
-    } else if (warp == 4) {
-        // ===================== TMA producer =====================
-        if (lane == 0) {
-            uint32_t stage = 0, phase = 0;
-            for (uint32_t g = blockIdx.x; g < ngroups; g += gridDim.x) {
-                for (uint32_t qb = 0; qb < nqb; ++qb) {
-                    const int8_t* qblk = qexp + (size_t)qb * tc_qblock_bytes(NCHUNK);
-                    for (int ks = 0; ks <= KS; ++ks) {            // KS code stages + the bias slice
-                        const uint32_t bytes = ks < KS ? TC_STAGE_BYTES : TC_BIAS_BYTES;
-                        mbar_wait(empty_bar(stage), phase ^ 1u);
-                        mbar_expect_tx(full_bar(stage), bytes);
-                        tma_bulk_g2s(smem_u32(stage_base + stage * TC_STAGE_BYTES),
-                                     qblk + (size_t)ks * TC_STAGE_BYTES, bytes, full_bar(stage));
-                        if (++stage == TC_STAGES) { stage = 0; phase ^= 1u; }
-                    }
-                }
-            }
-        }
+        if (prof && blockIdx.x == 0 && threadIdx.x == 128)
+            for (int i = 0; i < 2; ++i) prof[4 + i] = pw[i];
     } else {
-        // ===================== MMA issuer =====================
-        if (lane == 0) {
-            uint32_t stage = 0, phase = 0;
-            uint32_t a_phase = 0;
-            uint32_t acc_phase[2] = {0, 0};
-            uint32_t it = 0;
-            for (uint32_t g = blockIdx.x; g < ngroups; g += gridDim.x) {
-                mbar_wait(a_ready, a_phase);
-                a_phase ^= 1u;
-                tc_fence_after();
-                for (uint32_t qb = 0; qb < nqb; ++qb, ++it) {
-                    const uint32_t b = it & 1u;
-                    mbar_wait(acc_empty(b), acc_phase[b] ^ 1u);      // first use of each buffer passes
-                    acc_phase[b] ^= 1u;
-                    tc_fence_after();
-                    for (int ks = 0; ks < KS; ++ks) {
-                        mbar_wait(full_bar(stage), phase);
-                        tc_fence_after();
-                        const uint32_t sb = smem_u32(stage_base + stage * TC_STAGE_BYTES);
-#pragma unroll
-                        for (int j = 0; j < TC_KSTAGE / 32; ++j) {
-                            const uint64_t bdesc = tc_smem_desc(sb + j * 256, 128, 1024);
-                            tc_mma_i8_ts(tmem_d + b * TC_NQ, tmem_a + (uint32_t)((ks * (TC_KSTAGE / 32) + j) * 8),
-                                         bdesc, IDESC, (ks | j) != 0 ? 1u : 0u);
-                        }
-                        tc_commit(empty_bar(stage));                 // stage free when these MMAs retire
-                        if (++stage == TC_STAGES) { stage = 0; phase ^= 1u; }
-                    }
-                    {   // bias: D += ones(128 x 32) * digits(128 queries x 32)
-                        mbar_wait(full_bar(stage), phase);
-                        tc_fence_after();
-                        const uint32_t sb = smem_u32(stage_base + stage * TC_STAGE_BYTES);
-                        tc_mma_i8_ts(tmem_d + b * TC_NQ, tmem_a + A_COLS, tc_smem_desc(sb, 128, 256), IDESC, 1u);
-                        tc_commit(empty_bar(stage));
-                        if (++stage == TC_STAGES) { stage = 0; phase ^= 1u; }
-                    }
-                    tc_commit(acc_full(b));
+        // ===================== query loader (TMA) + MMA issuer: warp 8, one elected lane issues =====================
+        uint32_t bfull_phase = 0, bfree_phase = 0;
+        uint32_t ready_phase[2] = {0, 0};
+        uint32_t empty_phase[2] = {1, 1};         // first use of each accumulator buffer passes
+        uint32_t it = 0;
+        bool first_item = true;
+        const long long t_begin = prof ? clock64() : 0;
+        unsigned long long ns_begin = 0;
+        if (prof) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns_begin));
+        for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x) {
+            uint32_t qb0, nb, g_lo, g_hi;
+            item_range(item, qb0, nb, g_lo, g_hi);
+            if (g_lo >= g_hi) continue;
+            if (!first_item) {                    // the previous item's MMAs still read the resident blocks
+                mbar_wait(b_free, bfree_phase);
+                bfree_phase ^= 1u;
+            }
+            first_item = false;
+            if (elect_one()) {
+                mbar_expect_tx(b_full, nb * QBLOCK_BYTES);
+                for (uint32_t blk = 0; blk < nb; ++blk) {
+                    const int8_t* src = qexp + (size_t)(qb0 + blk) * QBLOCK_BYTES;
+                    const uint32_t dst = smem_u32(smem + blk * QBLOCK_BYTES);
+                    for (uint32_t off = 0; off < QBLOCK_BYTES; off += TC_STAGE_BYTES)
+                        tma_bulk_g2s(dst + off, src + off, min((uint32_t)TC_STAGE_BYTES, QBLOCK_BYTES - off), b_full);
                 }
             }
+            __syncwarp();
+            { TC_PROF_T0(); mbar_wait(b_full, bfull_phase); TC_PROF_ADD(3); }
+            bfull_phase ^= 1u;
+            for (uint32_t g = g_lo; g < g_hi; ++g) {
+                for (uint32_t blk = 0; blk < nb; ++blk, ++it) {
+                    const uint32_t b = it & 1u;
+                    const bool last_blk = blk + 1 == nb;
+                    { TC_PROF_T0(); mbar_wait(acc_empty(b), empty_phase[b]); TC_PROF_ADD(0); }
+                    empty_phase[b] ^= 1u;
+                    tc_fence_after();
+                    const uint64_t bdesc0 = tc_smem_desc(smem_u32(smem + blk * QBLOCK_BYTES), 128, 1024);
+                    const uint32_t d_addr = tmem_d + b * TC_NQ;
+#pragma unroll
+                    for (int ks = 0; ks < NCHUNK; ++ks) {
+                        if (blk == 0 && (ks == 0 || ks == LO)) {
+                            const int h = ks == 0 ? 0 : 1;
+                            { TC_PROF_T0(); mbar_wait(a_ready(h), ready_phase[h]); TC_PROF_ADD(1 + h); }
+                            ready_phase[h] ^= 1u;
+                            tc_fence_after();
+                        }
+                        if (elect_one()) {
+#pragma unroll
+                            for (int j = 0; j < TC_KSTAGE / 32; ++j)      // the address field counts 16-byte units
+                                tc_mma_i8_ts(d_addr, tmem_a + (uint32_t)((ks * (TC_KSTAGE / 32) + j) * 8),
+                                             bdesc0 + (uint64_t)((ks * TC_STAGE_BYTES + j * 256) >> 4), IDESC, (ks | j) != 0 ? 1u : 0u);
+                            if (last_blk && ks == LO - 1) tc_commit(a_free(0));   // low half of A may be rewritten
+                        }
+                        __syncwarp();
+                    }
+                    if (NCHUNK == 1 && blk == 0) {      // high half is empty: keep its barriers in step
+                        mbar_wait(a_ready(1), ready_phase[1]);
+                        ready_phase[1] ^= 1u;
+                    }
+                    if (elect_one()) {
+                        // bias: D += (-128)(128 x 32) * digits(128 queries x 32)
+                        tc_mma_i8_ts(d_addr, tmem_a + A_COLS,
+                                     tc_smem_desc(smem_u32(smem + blk * QBLOCK_BYTES + NCHUNK * TC_STAGE_BYTES), 128, 256), IDESC, 1u);
+                        if (last_blk) tc_commit(a_free(1));
+                        tc_commit(acc_full(b));
+                    }
+                    __syncwarp();
+                }
+            }
+            if (elect_one()) tc_commit(b_free);
+            __syncwarp();
+        }
+        if (prof && blockIdx.x == 0 && lane == 0) {
+            unsigned long long ns;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
+            pw[6] = (unsigned long long)(clock64() - t_begin);
+            pw[7] = ns - ns_begin;
+            for (int i = 0; i < 8; ++i) prof[8 + i] = pw[i];
         }
     }
+#undef TC_PROF_T0
+#undef TC_PROF_ADD
     tc_fence_before();
     __syncthreads();
-    if (warp == 5) {
+    if (warp == 8) {
         __syncwarp();
         tc_dealloc(tmem, TC_TMEM_COLS);
     }

@@ -64,14 +64,19 @@ int main(int argc, char** argv) {
     CK(cudaGetLastError());
     int sms = 0; CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0));
     uint32_t ngroups = (ntiles + 3) / 4;
-    uint32_t grid = ngroups < (uint32_t)sms ? ngroups : sms;
-    size_t smem = TC_STAGES * TC_STAGE_BYTES + (size_t)nq_pad * 8;
+    const uint32_t n_qsl = (nq_pad / TC_NQ + TC_QBLOCKS - 1) / TC_QBLOCKS;
+    uint32_t n_rsl = argc > 5 ? atoi(argv[5]) : 0;
+    if (!n_rsl) { n_rsl = sms / n_qsl; if (!n_rsl) n_rsl = 1; }
+    if (n_rsl > ngroups) n_rsl = ngroups;
+    uint32_t grid = n_qsl * n_rsl < (uint32_t)sms ? n_qsl * n_rsl : sms;
+    size_t smem = TC_QBLOCKS * tc_qblock_bytes(NCHUNK);
+    printf("split: %u query slices x %u row slices, grid %u\n", n_qsl, n_rsl, grid);
     if (check) {
         CK(cudaFuncSetAttribute(tc_scan_kernel<NCHUNK, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         tc_bias_kernel<<<(nq_pad + 127) / 128, 128>>>(d_qpack, qs, NCHUNK, d_qpop, nq, nq_pad, d_qexp, d_qbias, 1);
         ref_kernel<NCHUNK><<<(ntiles + 7) / 8, 256>>>(d_codes, ntiles, d_qpack, qs, nq, d_ref, n_rows, n_rows);
         CK(cudaGetLastError());
-        tc_scan_kernel<NCHUNK, 1><<<grid, TC_THREADS, smem>>>(d_codes, d_live, 0, ntiles, d_qexp, d_qpop, d_qbias, nq, nq_pad,
+        tc_scan_kernel<NCHUNK, 1><<<grid, TC_THREADS, smem>>>(d_codes, d_live, 0, ntiles, d_qexp, d_qpop, d_qbias, nq, nq_pad, n_qsl, n_rsl,
                                                              d_recs, rec_cap, d_ctacnt, d_flag, d_tc, n_rows, n_rows);
         CK(cudaGetLastError());
         CK(cudaDeviceSynchronize());
@@ -95,7 +100,7 @@ int main(int argc, char** argv) {
         const uint32_t bigcap = 65536;
         uint64_t* d_buf2; CK(cudaMalloc(&d_buf2, (size_t)nq_pad * bigcap * 8));
         CK(cudaMemset(d_cnt, 0, nq_pad * 4));
-        tc_scan_kernel<NCHUNK, 0><<<grid, TC_THREADS, smem>>>(d_codes, d_live, 0, ntiles, d_qexp, d_qpop, d_qbias, nq, nq_pad,
+        tc_scan_kernel<NCHUNK, 0><<<grid, TC_THREADS, smem>>>(d_codes, d_live, 0, ntiles, d_qexp, d_qpop, d_qbias, nq, nq_pad, n_qsl, n_rsl,
                                                              d_recs, rec_cap, d_ctacnt, d_flag, nullptr, 0, n_rows);
         tc_scatter_kernel<<<dim3((rec_cap + 255) / 256, grid * 4), 256>>>(d_recs, rec_cap, d_ctacnt, d_codes, NCHUNK, d_qpack, qs, d_cnt, d_buf2, bigcap, d_flag);
         CK(cudaGetLastError());
@@ -128,22 +133,28 @@ int main(int argc, char** argv) {
         CK(cudaFuncSetAttribute(tc_scan_kernel<NCHUNK, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
         for (int rep = 0; rep < 3; ++rep)
-            tc_scan_kernel<NCHUNK, 0><<<grid, TC_THREADS, smem>>>(d_codes, d_live, 0, ntiles, d_qexp, d_qpop, d_qbias, nq, nq_pad,
+            tc_scan_kernel<NCHUNK, 0><<<grid, TC_THREADS, smem>>>(d_codes, d_live, 0, ntiles, d_qexp, d_qpop, d_qbias, nq, nq_pad, n_qsl, n_rsl,
                                                                  d_recs, rec_cap, d_ctacnt, d_flag, nullptr, 0, n_rows);
         CK(cudaDeviceSynchronize());
         const int reps = 10;
+        unsigned long long* d_prof; CK(cudaMalloc(&d_prof, 16 * 8)); CK(cudaMemset(d_prof, 0, 16 * 8));
         for (int dbg : {0, 1}) {
         cudaEventRecord(e0);
         for (int rep = 0; rep < reps; ++rep) {
             cudaMemsetAsync(d_cnt, 0, nq_pad * 4);
-            tc_scan_kernel<NCHUNK, 0><<<grid, TC_THREADS, smem>>>(d_codes, d_live, 0, ntiles, d_qexp, d_qpop, d_qbias, nq, nq_pad,
-                                                                 d_recs, rec_cap, d_ctacnt, d_flag, nullptr, 0, n_rows, dbg);
+            tc_scan_kernel<NCHUNK, 0><<<grid, TC_THREADS, smem>>>(d_codes, d_live, 0, ntiles, d_qexp, d_qpop, d_qbias, nq, nq_pad, n_qsl, n_rsl,
+                                                                 d_recs, rec_cap, d_ctacnt, d_flag, nullptr, 0, n_rows, dbg, d_prof);
             if (!(dbg & 1)) tc_scatter_kernel<<<dim3((16384 + 255) / 256, grid * 4), 256>>>(d_recs, rec_cap, d_ctacnt, d_codes, NCHUNK, d_qpack, qs, d_cnt, d_buf, cap, d_flag);
         }
         cudaEventRecord(e1);
         CK(cudaDeviceSynchronize());
         float ms = 0; cudaEventElapsedTime(&ms, e0, e1); ms /= reps;
         double macs = (double)n_rows * nq_pad * NCHUNK * 128;
+        unsigned long long hp[16]; CK(cudaMemcpy(hp, d_prof, 16 * 8, cudaMemcpyDeviceToHost));
+        const double grp = (double)((ntiles + 3) / 4) / n_rsl * ((n_qsl * n_rsl + grid - 1) / grid);
+        printf("  per group (clk): expander: wait a_free lo %.0f hi %.0f  expand lo %.0f hi %.0f | epilogue: wait acc_full %.0f  work %.0f | mma: wait acc_empty %.0f  a_ready lo %.0f hi %.0f  b_full(total) %llu | total %.0f clk/group, SM clock %.0f MHz\n",
+               hp[0] / grp, hp[1] / grp, hp[2] / grp, hp[3] / grp, hp[4] / grp, hp[5] / grp, hp[8] / grp, hp[9] / grp, hp[10] / grp, hp[11],
+               hp[14] / grp, hp[15] ? 1e3 * (double)hp[14] / (double)hp[15] : 0.0);
         printf("timing dbg=%d (1=no-epilogue 2=no-tma 8=ldtm-only): rows=%llu nq=%u  %.3f ms/launch  %.1f TMAC/s (int8)  = %.1f%% of 148 SMs x 8192 MAC/clk @1.965GHz\n",
                dbg, (unsigned long long)n_rows, nq, ms, macs / ms / 1e9, 100.0 * macs / (ms * 1e-3) / (148.0 * 8192 * 1.965e9));
         }
