@@ -37,7 +37,9 @@ class GvdbProfile(C.Structure):
     _fields_ = [("launches", C.c_uint64), ("scan_launches", C.c_uint64), ("scan_ms", C.c_double),
                 ("scan_bytes", C.c_double), ("scan_pairs", C.c_double), ("select_ms", C.c_double),
                 ("rescore_ms", C.c_double), ("topk_ms", C.c_double), ("prep_ms", C.c_double),
-                ("flat_ms", C.c_double), ("merge_ms", C.c_double)]
+                ("flat_ms", C.c_double), ("merge_ms", C.c_double), ("tc_launches", C.c_uint64),
+                ("tc_ms", C.c_double), ("tc_macs", C.c_double), ("tc_bytes", C.c_double),
+                ("scatter_ms", C.c_double)]
 
 
 # every symbol include/gvdb.h declares: name -> (restype, argtypes)
@@ -84,7 +86,7 @@ def lib() -> C.CDLL:
             fn = getattr(L, name)  # AttributeError if the library does not export it
             fn.restype = res
             fn.argtypes = args
-        if L.gvdb_abi_version() != 1:
+        if L.gvdb_abi_version() != 2:
             raise RuntimeError("libgvdb.so ABI version mismatch")
         _lib = L
     return _lib

@@ -62,7 +62,7 @@ struct DevBuf {
     template <class T> T* as() const { return reinterpret_cast<T*>(p); }
 };
 
-enum Kind { K_SCAN = 0, K_SELECT, K_RESCORE, K_TOPK, K_PREP, K_FLAT, K_MERGE, K_COUNT };
+enum Kind { K_SCAN = 0, K_SELECT, K_RESCORE, K_TOPK, K_PREP, K_FLAT, K_MERGE, K_TCSCAN, K_SCATTER, K_COUNT };
 struct ProfRec {
     int kind;
     cudaEvent_t e0, e1;
@@ -118,6 +118,8 @@ struct gvdb_index {
     int scan_ctas_per_sm = 16;
     int scan_variant = -1;     // GVDB_SCAN_NCSA: adder-count override for tuning (768-d only)
     uint32_t tc_min_q = 64;    // GVDB_TC_MIN_Q: query-tile size from which the tcgen05 scan is used
+    uint32_t seg0_rows = 4096; // GVDB_SEG0_ROWS: rows of the first ("emit everything") segment
+    uint32_t seg_growth = 16;  // GVDB_SEG_GROWTH: cap on the geometric segment growth (0 = cap/(4R) only)
     std::atomic<int> profile_on{0};
     std::atomic<uint64_t> launches{0};
     std::mutex prof_mu;
@@ -170,6 +172,9 @@ void flush_profile(gvdb_index* h, Workspace* ws) {
             case K_PREP: h->prof.prep_ms += ms; break;
             case K_FLAT: h->prof.flat_ms += ms; break;
             case K_MERGE: h->prof.merge_ms += ms; break;
+            case K_TCSCAN: h->prof.tc_ms += ms; h->prof.tc_launches += 1;
+                           h->prof.tc_bytes += r.bytes; h->prof.tc_macs += r.pairs; break;
+            case K_SCATTER: h->prof.scatter_ms += ms; break;
         }
     }
     ws->recs.clear();
@@ -236,17 +241,17 @@ void grow(gvdb_index* h, uint64_t need_rows) {
 }
 
 // ---- kernel dispatch on NCHUNK (and, for tuning, on the carry-save adder count) ------------
-template <int NCHUNK, int MODE, int NCSA>
+template <int NCHUNK, int MODE, int NCSA, bool AGG>
 void launch_scan_t(cudaStream_t st, dim3 grid, size_t smem, const uint4* codes, const uint32_t* live,
                    uint32_t tile_lo, uint32_t tile_hi, const uint32_t* qpack, int nq, int qgroup,
                    uint32_t* cnt, uint64_t* buf, uint32_t cap, uint32_t* overflow, uint32_t* dist_out,
                    uint64_t dist_stride, uint64_t n_rows) {
     static bool attr_set = false;   // benign race: idempotent
     if (!attr_set) {
-        CU(cudaFuncSetAttribute(scan_kernel<NCHUNK, MODE, NCSA>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        CU(cudaFuncSetAttribute(scan_kernel<NCHUNK, MODE, NCSA, AGG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
         attr_set = true;
     }
-    scan_kernel<NCHUNK, MODE, NCSA><<<grid, SCAN_THREADS, smem, st>>>(
+    scan_kernel<NCHUNK, MODE, NCSA, AGG><<<grid, SCAN_THREADS, smem, st>>>(
         codes, live, tile_lo, tile_hi, qpack, nq, qgroup, cnt, buf, cap, overflow, dist_out,
         dist_stride, n_rows);
     CU(cudaGetLastError());
@@ -261,16 +266,19 @@ void launch_scan(int nchunk, int variant, cudaStream_t st, dim3 grid, size_t sme
                  int nq, int qgroup, uint32_t* cnt, uint64_t* buf, uint32_t cap, uint32_t* overflow,
                  uint32_t* dist_out, uint64_t dist_stride, uint64_t n_rows) {
 #define GVDB_ARGS st, grid, smem, codes, live, tile_lo, tile_hi, qpack, nq, qgroup, cnt, buf, cap, overflow, dist_out, dist_stride, n_rows
-#define GVDB_CASE(N) case N: launch_scan_t<N, MODE, default_ncsa(N)>(GVDB_ARGS); break;
+#define GVDB_CASE(N) case N: if (agg) launch_scan_t<N, MODE, default_ncsa(N), MODE == 0>(GVDB_ARGS); \
+                             else launch_scan_t<N, MODE, default_ncsa(N), false>(GVDB_ARGS); break;
+    // many queries per pass: survivors of one tile are appended with one atomic per (tile, query)
+    const bool agg = MODE == 0 && nq >= 8;
     if (nchunk == 6 && MODE == 0 && variant >= 0) {   // tuning variants for the 768-d kernel
         switch (variant) {
-            case 0: launch_scan_t<6, MODE, 0>(GVDB_ARGS); return;
-            case 8: launch_scan_t<6, MODE, 8>(GVDB_ARGS); return;
-            case 9: launch_scan_t<6, MODE, 9>(GVDB_ARGS); return;
-            case 10: launch_scan_t<6, MODE, 10>(GVDB_ARGS); return;
-            case 12: launch_scan_t<6, MODE, 12>(GVDB_ARGS); return;
-            case 13: launch_scan_t<6, MODE, 13>(GVDB_ARGS); return;
-            case 14: launch_scan_t<6, MODE, 14>(GVDB_ARGS); return;
+            case 0: launch_scan_t<6, MODE, 0, false>(GVDB_ARGS); return;
+            case 8: launch_scan_t<6, MODE, 8, false>(GVDB_ARGS); return;
+            case 9: launch_scan_t<6, MODE, 9, false>(GVDB_ARGS); return;
+            case 10: launch_scan_t<6, MODE, 10, false>(GVDB_ARGS); return;
+            case 12: launch_scan_t<6, MODE, 12, false>(GVDB_ARGS); return;
+            case 13: launch_scan_t<6, MODE, 13, false>(GVDB_ARGS); return;
+            case 14: launch_scan_t<6, MODE, 14, false>(GVDB_ARGS); return;
             default: break;
         }
     }
@@ -331,6 +339,10 @@ void launch_tc_scan(gvdb_index* h, Workspace* ws, cudaStream_t st, uint32_t tile
     const int32_t* qbias = ws->qbias.as<int32_t>();
     uint2* recs = ws->tc_recs.as<uint2>();
     uint32_t* lc = ws->list_counts.as<uint32_t>();
+    const double seg_rows = (double)(tile_hi - tile_lo) * 32.0;
+    {
+    Timed t(h, ws, st, K_TCSCAN, seg_rows * h->nchunk * 16.0 * sp.qslices,
+            seg_rows * (double)nq_pad * (h->nchunk * 128.0 + 32.0));
 #define GVDB_TC_CASE(N)                                                                              \
     case N: {                                                                                        \
         static bool attr = false;                                                                    \
@@ -349,10 +361,11 @@ void launch_tc_scan(gvdb_index* h, Workspace* ws, cudaStream_t st, uint32_t tile
         default: fail(GVDB_ERR_INDEX, "tcgen05 scan: unsupported code width");
     }
 #undef GVDB_TC_CASE
+    }
     CU(cudaGetLastError());
     if (MODE == 0) {
-        h->launches.fetch_add(1, std::memory_order_relaxed);
-        tc_scatter_kernel<<<dim3((rec_cap + 255) / 256, nlists), 256, 0, st>>>(
+        Timed t(h, ws, st, K_SCATTER);
+        tc_scatter_kernel<<<dim3(TC_SCATTER_X, nlists), 256, 0, st>>>(
             recs, rec_cap, lc, h->codes, h->nchunk, ws->qpack.as<uint32_t>(), h->qs, cnt, buf, cap, overflow);
         CU(cudaGetLastError());
     }
@@ -387,6 +400,11 @@ dim3 scan_grid(const gvdb_index* h, uint32_t ntiles, uint32_t nq) {
     return dim3(x, y, 1);
 }
 
+uint32_t next_pow2_host(uint32_t v) {
+    uint32_t p = 1;
+    while (p < v) p <<= 1;
+    return p;
+}
 uint32_t pick_cap(uint32_t R) { return R <= 1024 ? 8192u : 16384u; }
 constexpr uint32_t kMaxR = SORT_N / 2;
 
@@ -408,8 +426,21 @@ void search_core(gvdb_index* h, Workspace* ws, cudaStream_t st, const float* que
     ws->buf.ensure((size_t)qt_max * cap * 8);
     CU(cudaMemsetAsync(ws->flag.p, 0, 256, st));
     // geometric segments; growth keeps expected emission R*(g-1) <= cap/4
-    const uint32_t seg0_tiles = 4096 / 32;
-    const uint32_t g = std::max<uint32_t>(2, cap / (4 * R));
+    const uint32_t seg0_tiles = h->seg0_rows / 32;
+    uint32_t g = std::max<uint32_t>(2, cap / (4 * R));
+    // the cap trades survivors per segment (epilogue + select work) for launches: only worth it
+    // where the tensor-core scan runs; few-query passes are HBM-bound and want few launches
+    if (h->seg_growth >= 2 && std::min(QT, nq) >= h->tc_min_q && tc_supported(h->nchunk)) g = std::min(g, h->seg_growth);
+    const uint32_t r_pow2 = std::max<uint32_t>(32, next_pow2_host(R));
+    const uint32_t nbins = (uint32_t)h->nchunk * 128 + 1;
+    const size_t selh_smem = (size_t)r_pow2 * 8 + (size_t)SORT_N * 8 + (size_t)nbins * 4;
+    {
+        static bool attr = false;   // benign race: idempotent
+        if (!attr) {
+            CU(cudaFuncSetAttribute(select_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
+            attr = true;
+        }
+    }
     for (uint32_t qt0 = 0; qt0 < nq; qt0 += QT) {
         const uint32_t nqt = std::min(QT, nq - qt0);
         {
@@ -432,7 +463,6 @@ void search_core(gvdb_index* h, Workspace* ws, cudaStream_t st, const float* que
             const double seg_rows = (double)(hi - lo) * 32.0;
             if (use_tc && lo > 0) {
                 tc_update_bias(h, ws, st, nqt, nq_pad, 0);
-                Timed t(h, ws, st, K_SCAN, seg_rows * h->nchunk * 16.0, seg_rows * nqt);
                 launch_tc_scan<0>(h, ws, st, lo, hi, nqt, nq_pad, ws->cnt.as<uint32_t>(), ws->buf.as<uint64_t>(), cap,
                                   ws->flag.as<uint32_t>(), nullptr, 0);
             } else {
@@ -444,9 +474,9 @@ void search_core(gvdb_index* h, Workspace* ws, cudaStream_t st, const float* que
             }
             {
                 Timed t(h, ws, st, K_SELECT);
-                select_kernel<<<nqt, SORT_THREADS, SORT_N * 8, st>>>(
-                    ws->buf.as<uint64_t>(), cap, ws->cnt.as<uint32_t>(), R, ws->qpack.as<uint32_t>(),
-                    h->qs, h->nchunk * 4);
+                select_hist_kernel<<<nqt, SELH_THREADS, selh_smem, st>>>(
+                    ws->buf.as<uint64_t>(), cap, ws->cnt.as<uint32_t>(), R, r_pow2, nbins,
+                    ws->qpack.as<uint32_t>(), h->qs, h->nchunk * 4);
             }
             CU(cudaGetLastError());
             lo = hi;
@@ -635,6 +665,8 @@ gvdb_status gvdb_create(const gvdb_config* cfg, gvdb_index** out) {
         if (const char* s = getenv("GVDB_QUERY_TILE")) h->query_tile = std::max(1, atoi(s));
         if (const char* s = getenv("GVDB_SCAN_NCSA")) h->scan_variant = atoi(s);
         if (const char* s = getenv("GVDB_TC_MIN_Q")) h->tc_min_q = (uint32_t)std::max(1, atoi(s));
+        if (const char* s = getenv("GVDB_SEG0_ROWS")) h->seg0_rows = (uint32_t)std::max(32, atoi(s)) / 32 * 32;
+        if (const char* s = getenv("GVDB_SEG_GROWTH")) h->seg_growth = (uint32_t)std::max(0, atoi(s));
         if (const char* s = getenv("GVDB_SCAN_CTAS_PER_SM")) h->scan_ctas_per_sm = std::max(1, atoi(s));
         if (cfg->capacity_rows) grow(h.get(), cfg->capacity_rows);
         *out = h.release();

@@ -278,7 +278,7 @@ __device__ __forceinline__ uint32_t hamming_csa(const uint32_t (&x)[W]) {
 // MODE 1 (parity): every distance is written out (gvdb_hamming).
 // Algorithmic bytes per launch: (tile_hi - tile_lo) * 32 * NCHUNK * 16 (codes streamed once
 // per query group) — see DESIGN.md §5.
-template <int NCHUNK, int MODE, int NCSA>
+template <int NCHUNK, int MODE, int NCSA, bool AGG>
 __global__ void __launch_bounds__(SCAN_THREADS)
 scan_kernel(const uint4* __restrict__ codes, const uint32_t* __restrict__ live, uint32_t tile_lo,
             uint32_t tile_hi, const uint32_t* __restrict__ qpack, int nq, int qgroup,
@@ -333,7 +333,22 @@ scan_kernel(const uint4* __restrict__ codes, const uint32_t* __restrict__ live, 
                 const uint32_t tau = sq[q * QS + NCHUNK * 4];
                 // strict '<': tau is the R-th smallest distance over EARLIER rows, so a later
                 // row that ties it has a larger row number and cannot enter the top R.
-                if (alive && d < tau) {
+                const bool hit = alive && d < tau;
+                if (AGG) {
+                    // warp-aggregated append: one atomic per (tile, query) instead of one per row
+                    const uint32_t m = __ballot_sync(0xffffffffu, hit);
+                    if (m) {
+                        uint32_t base = 0;
+                        const int leader = __ffs(m) - 1;
+                        if (lane == leader) base = atomicAdd(&cnt[q0 + q], (uint32_t)__popc(m));
+                        base = __shfl_sync(0xffffffffu, base, leader);
+                        if (hit) {
+                            const uint32_t pos = base + __popc(m & ((1u << lane) - 1u));
+                            if (pos < cap) buf[(size_t)(q0 + q) * cap + pos] = ((uint64_t)d << 32) | row;
+                            else *overflow = 1u;
+                        }
+                    }
+                } else if (hit) {
                     const uint32_t pos = atomicAdd(&cnt[q0 + q], 1u);
                     if (pos < cap) buf[(size_t)(q0 + q) * cap + pos] = ((uint64_t)d << 32) | row;
                     else *overflow = 1u;
@@ -375,6 +390,128 @@ select_kernel(uint64_t* __restrict__ buf, uint32_t cap, uint32_t* __restrict__ c
     if (threadIdx.x == 0) {
         cnt[q] = have;
         qpack[(size_t)q * qs + tau_word] = (have >= R && R > 0) ? (uint32_t)(skeys[R - 1] >> 32) : TAU_ALL;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// select_hist_kernel: the same contract as select_kernel for keys whose high word is a Hamming
+// distance (a small integer < nbins): exact top-R by (hamming, row) without sorting the input.
+//   1. histogram of the distances in shared memory, prefix scan -> threshold bin b* (the bin that
+//      holds the R-th smallest key) and how many keys of that bin are still needed;
+//   2. keys below b* are kept outright; the keys IN b* compete on their row number: a small tie
+//      set is sorted in shared memory, a large one goes through a 4 x 8-bit radix select on the row;
+//   3. the R kept keys are sorted (bitonic over next_pow2(R)) and written back.
+// Dynamic shared memory: r_pow2 u64 (kept) + SORT_N u64 (ties) + nbins u32 (histogram).
+constexpr int SELH_THREADS = 256;
+
+__global__ void __launch_bounds__(SELH_THREADS)
+select_hist_kernel(uint64_t* __restrict__ buf, uint32_t cap, uint32_t* __restrict__ cnt, uint32_t R,
+                   uint32_t r_pow2, uint32_t nbins, uint32_t* __restrict__ qpack, int qs, int tau_word) {
+    extern __shared__ __align__(16) uint64_t sel[];
+    uint64_t* tie = sel + r_pow2;
+    uint32_t* hist = reinterpret_cast<uint32_t*>(tie + SORT_N);
+    __shared__ uint32_t s_bstar, s_below, s_nsel, s_ntie, s_prefix, s_need;
+    const uint32_t q = blockIdx.x;
+    uint64_t* mine = buf + (size_t)q * cap;
+    const uint32_t n = min(cnt[q], cap);
+    const uint32_t tid = threadIdx.x;
+
+    if (n <= R) {                                   // everything is kept: just order it
+        for (uint32_t i = tid; i < r_pow2; i += SELH_THREADS) sel[i] = i < n ? mine[i] : UINT64_MAX;
+        __syncthreads();
+        bitonic_sort_smem(sel, r_pow2);
+        for (uint32_t i = tid; i < n; i += SELH_THREADS) mine[i] = sel[i];
+        if (tid == 0) {
+            cnt[q] = n;
+            qpack[(size_t)q * qs + tau_word] = (n >= R && R > 0) ? (uint32_t)(sel[R - 1] >> 32) : TAU_ALL;
+        }
+        return;
+    }
+    for (uint32_t i = tid; i < nbins; i += SELH_THREADS) hist[i] = 0;
+    if (tid == 0) { s_nsel = 0; s_ntie = 0; }
+    __syncthreads();
+    for (uint32_t i = tid; i < n; i += SELH_THREADS)
+        atomicAdd(&hist[min((uint32_t)(mine[i] >> 32), nbins - 1)], 1u);
+    __syncthreads();
+    if (tid < 32) {                                 // warp 0: which bin holds the R-th smallest key?
+        const uint32_t per = (nbins + 31) / 32;
+        const uint32_t b0 = tid * per, b1 = min(nbins, b0 + per);
+        uint32_t sum = 0;
+        for (uint32_t b = b0; b < b1; ++b) sum += hist[b];
+        uint32_t incl = sum;
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+            if ((int)tid >= o) incl += t;
+        }
+        uint32_t run = incl - sum;                  // keys in bins before b0
+        if (run < R && incl >= R) {                 // exactly one lane
+            for (uint32_t b = b0; b < b1; ++b) {
+                const uint32_t h = hist[b];
+                if (run + h >= R) { s_bstar = b; s_below = run; s_need = R - run; break; }
+                run += h;
+            }
+        }
+    }
+    __syncthreads();
+    const uint32_t bstar = s_bstar, below = s_below, need = s_need;
+    const uint32_t ntie_all = hist[bstar];
+    const bool small_ties = ntie_all <= (uint32_t)SORT_N;
+    for (uint32_t i = tid; i < n; i += SELH_THREADS) {
+        const uint64_t key = mine[i];
+        const uint32_t h = min((uint32_t)(key >> 32), nbins - 1);
+        if (h < bstar) sel[atomicAdd(&s_nsel, 1u)] = key;
+        else if (h == bstar && small_ties) tie[atomicAdd(&s_ntie, 1u)] = key;
+    }
+    __syncthreads();
+    if (small_ties) {
+        if (ntie_all > need) {                      // order the ties by row, keep the first `need`
+            const uint32_t n_eff = max(32u, next_pow2(ntie_all));
+            for (uint32_t i = ntie_all + tid; i < n_eff; i += SELH_THREADS) tie[i] = UINT64_MAX;
+            __syncthreads();
+            bitonic_sort_smem(tie, n_eff);
+        }
+    } else {
+        // radix select on the row number among the keys of bin b*: find the need-th smallest row
+        uint32_t prefix = 0, want = need;           // rows matching `prefix` in the bits decided so far
+        uint32_t* h256 = reinterpret_cast<uint32_t*>(tie);
+        for (int shift = 24; shift >= 0; shift -= 8) {
+            for (uint32_t i = tid; i < 256; i += SELH_THREADS) h256[i] = 0;
+            __syncthreads();
+            const uint32_t hi_mask = shift == 24 ? 0u : ~((1u << (shift + 8)) - 1u);
+            for (uint32_t i = tid; i < n; i += SELH_THREADS) {
+                const uint64_t key = mine[i];
+                const uint32_t row = (uint32_t)key;
+                if (min((uint32_t)(key >> 32), nbins - 1) == bstar && (row & hi_mask) == prefix)
+                    atomicAdd(&h256[(row >> shift) & 255u], 1u);
+            }
+            __syncthreads();
+            if (tid == 0) {
+                uint32_t run = 0, d = 0;
+                for (; d < 256; ++d) { if (run + h256[d] >= want) break; run += h256[d]; }
+                s_prefix = prefix | (d << shift);
+                s_need = want - run;
+            }
+            __syncthreads();
+            prefix = s_prefix; want = s_need;
+            __syncthreads();
+        }
+        // rows are unique, so exactly `need` keys of the bin have row <= prefix
+        for (uint32_t i = tid; i < n; i += SELH_THREADS) {
+            const uint64_t key = mine[i];
+            if (min((uint32_t)(key >> 32), nbins - 1) == bstar && (uint32_t)key <= prefix)
+                sel[below + atomicAdd(&s_ntie, 1u)] = key;
+        }
+        __syncthreads();
+    }
+    if (small_ties)
+        for (uint32_t i = tid; i < need; i += SELH_THREADS) sel[below + i] = tie[i];
+    for (uint32_t i = R + tid; i < r_pow2; i += SELH_THREADS) sel[i] = UINT64_MAX;
+    __syncthreads();
+    bitonic_sort_smem(sel, r_pow2);
+    for (uint32_t i = tid; i < R; i += SELH_THREADS) mine[i] = sel[i];
+    if (tid == 0) {
+        cnt[q] = R;
+        qpack[(size_t)q * qs + tau_word] = (uint32_t)(sel[R - 1] >> 32);
     }
 }
 

@@ -503,26 +503,28 @@ tc_scan_kernel(const uint4* __restrict__ codes, const uint32_t* __restrict__ liv
 // Warp-private survivor records (row, query) -> per-query candidate buffers, same contract as
 // scan_kernel: key = hamming << 32 | row.  The distance is recomputed from the codes (xor + popc
 // over nchunk*4 words, served from L2) — cheaper than carrying it through the epilogue.
-// grid = (ceil(rec_cap / 256), number of lists = 4 x scan CTAs); full occupancy hides the atomics.
+// grid = (TC_SCATTER_X, number of lists = 4 x scan CTAs), each CTA strides over its list.
+constexpr int TC_SCATTER_X = 4;
 __global__ void tc_scatter_kernel(const uint2* __restrict__ recs, uint32_t rec_cap,
                                   const uint32_t* __restrict__ list_counts, const uint4* __restrict__ codes,
                                   int nchunk, const uint32_t* __restrict__ qpack, int qs,
                                   uint32_t* __restrict__ cnt, uint64_t* __restrict__ buf, uint32_t cap,
                                   uint32_t* __restrict__ overflow) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= list_counts[blockIdx.y]) return;
-    const uint2 r = recs[(size_t)blockIdx.y * rec_cap + i];
-    const uint32_t row = r.x, q = r.y;
-    const uint4* rc = codes + ((size_t)(row >> 5) * nchunk) * 32 + (row & 31);
-    const uint4* qc = reinterpret_cast<const uint4*>(qpack + (size_t)q * qs);
-    uint32_t d = 0;
-    for (int c = 0; c < nchunk; ++c) {
-        const uint4 a = rc[c * 32], b = qc[c];
-        d += __popc(a.x ^ b.x) + __popc(a.y ^ b.y) + __popc(a.z ^ b.z) + __popc(a.w ^ b.w);
+    const uint32_t n_list = list_counts[blockIdx.y];
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_list; i += gridDim.x * blockDim.x) {
+        const uint2 r = recs[(size_t)blockIdx.y * rec_cap + i];
+        const uint32_t row = r.x, q = r.y;
+        const uint4* rc = codes + ((size_t)(row >> 5) * nchunk) * 32 + (row & 31);
+        const uint4* qc = reinterpret_cast<const uint4*>(qpack + (size_t)q * qs);
+        uint32_t d = 0;
+        for (int c = 0; c < nchunk; ++c) {
+            const uint4 a = rc[c * 32], b = qc[c];
+            d += __popc(a.x ^ b.x) + __popc(a.y ^ b.y) + __popc(a.z ^ b.z) + __popc(a.w ^ b.w);
+        }
+        const uint32_t pos = atomicAdd(&cnt[q], 1u);
+        if (pos < cap) buf[(size_t)q * cap + pos] = ((uint64_t)d << 32) | row;
+        else *overflow = 1u;
     }
-    const uint32_t pos = atomicAdd(&cnt[q], 1u);
-    if (pos < cap) buf[(size_t)q * cap + pos] = ((uint64_t)d << 32) | row;
-    else *overflow = 1u;
 }
 
 }  // namespace gvdb

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define GVDB_ABI_VERSION 1u
+#define GVDB_ABI_VERSION 2u
 
 #if defined(__GNUC__)
 #define GVDB_API __attribute__((visibility("default")))
@@ -180,6 +180,12 @@ typedef struct gvdb_profile {
                                  rows_in_segment * code_bytes_per_row * query_groups */
     double scan_pairs;        /* (row, query) pairs evaluated */
     double select_ms, rescore_ms, topk_ms, prep_ms, flat_ms, merge_ms;
+    uint64_t tc_launches;     /* tc_scan_kernel (tcgen05) launches */
+    double tc_ms;             /* summed tc_scan_kernel device time */
+    double tc_macs;           /* int8 multiply-accumulates those launches performed:
+                                 rows_in_segment * padded queries * code bits (+ the bias slice) */
+    double tc_bytes;          /* code bytes those launches read: rows * code_bytes_per_row * query slices */
+    double scatter_ms;        /* tc_scatter_kernel (survivor records -> candidate buffers) */
 } gvdb_profile;
 GVDB_API gvdb_status gvdb_profile_enable(gvdb_index* h, int32_t on);
 GVDB_API gvdb_status gvdb_profile_read(gvdb_index* h, gvdb_profile* out, int32_t reset);

@@ -102,7 +102,7 @@ int main(int argc, char** argv) {
         CK(cudaMemset(d_cnt, 0, nq_pad * 4));
         tc_scan_kernel<NCHUNK, 0><<<grid, TC_THREADS, smem>>>(d_codes, d_live, 0, ntiles, d_qexp, d_qpop, d_qbias, nq, nq_pad, n_qsl, n_rsl,
                                                              d_recs, rec_cap, d_ctacnt, d_flag, nullptr, 0, n_rows);
-        tc_scatter_kernel<<<dim3((rec_cap + 255) / 256, grid * 4), 256>>>(d_recs, rec_cap, d_ctacnt, d_codes, NCHUNK, d_qpack, qs, d_cnt, d_buf2, bigcap, d_flag);
+        tc_scatter_kernel<<<dim3(TC_SCATTER_X, grid * 4), 256>>>(d_recs, rec_cap, d_ctacnt, d_codes, NCHUNK, d_qpack, qs, d_cnt, d_buf2, bigcap, d_flag);
         CK(cudaGetLastError());
         CK(cudaDeviceSynchronize());
         std::vector<uint32_t> h_cnt(nq_pad);
@@ -144,7 +144,7 @@ int main(int argc, char** argv) {
             cudaMemsetAsync(d_cnt, 0, nq_pad * 4);
             tc_scan_kernel<NCHUNK, 0><<<grid, TC_THREADS, smem>>>(d_codes, d_live, 0, ntiles, d_qexp, d_qpop, d_qbias, nq, nq_pad, n_qsl, n_rsl,
                                                                  d_recs, rec_cap, d_ctacnt, d_flag, nullptr, 0, n_rows, dbg, d_prof);
-            if (!(dbg & 1)) tc_scatter_kernel<<<dim3((16384 + 255) / 256, grid * 4), 256>>>(d_recs, rec_cap, d_ctacnt, d_codes, NCHUNK, d_qpack, qs, d_cnt, d_buf, cap, d_flag);
+            if (!(dbg & 1)) tc_scatter_kernel<<<dim3(TC_SCATTER_X, grid * 4), 256>>>(d_recs, rec_cap, d_ctacnt, d_codes, NCHUNK, d_qpack, qs, d_cnt, d_buf, cap, d_flag);
         }
         cudaEventRecord(e1);
         CK(cudaDeviceSynchronize());
