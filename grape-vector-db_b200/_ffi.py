@@ -66,6 +66,7 @@ SYMBOLS = {
     "gvdb_flat_search_batch_device": (_i32, [_vp, _vp, _vp, _u32, _u32, _vp, _vp]),
     "gvdb_shard_record_bytes": (_u64, [_u32, _u32]),
     "gvdb_search_shard_device": (_i32, [_vp, _vp, _vp, _u32, _u32, _vp]),
+    "gvdb_search_shard_sliced_device": (_i32, [_vp, _vp, _vp, _u32, _u32, _u32, _vp]),
     "gvdb_merge_shards_device": (_i32, [_vp, _vp, _u32, _vp, _u32, _u32, _u32, _vp, _vp]),
     "gvdb_profile_enable": (_i32, [_vp, _i32]),
     "gvdb_profile_read": (_i32, [_vp, _vp, _i32]),

@@ -388,11 +388,22 @@ void tc_update_bias(gvdb_index* h, Workspace* ws, cudaStream_t st, uint32_t nq, 
     CU(cudaGetLastError());
 }
 
-constexpr int kQGroup = 128;   // queries staged per CTA
+constexpr int kQGroup = 128;   // queries staged per CTA (at most)
 
-dim3 scan_grid(const gvdb_index* h, uint32_t ntiles, uint32_t nq) {
+// Queries staged per CTA for a scan over `ntiles` tiles: the full group when the row range alone
+// fills the GPU; for short ranges (the first segment) smaller groups, so that the launch still
+// spreads over every SM (the per-CTA work is a serial walk over its query group).
+int pick_qgroup(const gvdb_index* h, uint32_t ntiles, uint32_t nq) {
     const uint32_t warps = SCAN_THREADS / 32;
-    uint32_t y = (nq + kQGroup - 1) / kQGroup;
+    const uint32_t x_full = (ntiles + warps - 1) / warps;
+    int g = kQGroup;
+    while (g > 8 && (uint64_t)x_full * ((nq + g - 1) / g) < 4ull * h->sm_count) g >>= 1;
+    return g;
+}
+
+dim3 scan_grid(const gvdb_index* h, uint32_t ntiles, uint32_t nq, int qgroup = kQGroup) {
+    const uint32_t warps = SCAN_THREADS / 32;
+    uint32_t y = (nq + qgroup - 1) / qgroup;
     uint32_t x_full = (ntiles + warps - 1) / warps;
     uint32_t x = x_full;
     if (y > 2) x = std::min<uint32_t>(x_full, std::max<uint32_t>(1, (uint32_t)(h->sm_count * h->scan_ctas_per_sm) / y));
@@ -410,7 +421,8 @@ constexpr uint32_t kMaxR = SORT_N / 2;
 
 // Stage 1 + stage 2 for queries [0,nq) (device pointers): fills rec_* [nq][R].
 void search_core(gvdb_index* h, Workspace* ws, cudaStream_t st, const float* queries_dev,
-                 uint32_t nq, uint32_t R, uint32_t* rec_ham, uint64_t* rec_ids, float* rec_score) {
+                 uint32_t nq, uint32_t R, uint32_t* rec_ham, uint64_t* rec_ids, float* rec_score,
+                 bool reset_overflow_flag = true) {
     if (h->n_rows == 0) fail(GVDB_ERR_INDEX_NOT_BUILT, "index not built: search before any add");
     if (R == 0) fail(GVDB_ERR_INVALID_ARGUMENT, "rescore_count must be >= 1");
     if (R > kMaxR)
@@ -421,10 +433,10 @@ void search_core(gvdb_index* h, Workspace* ws, cudaStream_t st, const float* que
     const uint32_t qt_max = std::min(QT, nq);
     ws->qpack.ensure((size_t)qt_max * h->qs * 4);
     ws->qnorm.ensure((size_t)qt_max * 4);
-    ws->cnt.ensure((size_t)qt_max * 4);
+    ws->cnt.ensure((size_t)qt_max * 4 * CNT_STRIDE);
     ws->flag.ensure(256);
     ws->buf.ensure((size_t)qt_max * cap * 8);
-    CU(cudaMemsetAsync(ws->flag.p, 0, 256, st));
+    if (reset_overflow_flag) CU(cudaMemsetAsync(ws->flag.p, 0, 256, st));
     // geometric segments; growth keeps expected emission R*(g-1) <= cap/4
     const uint32_t seg0_tiles = h->seg0_rows / 32;
     uint32_t g = std::max<uint32_t>(2, cap / (4 * R));
@@ -445,12 +457,17 @@ void search_core(gvdb_index* h, Workspace* ws, cudaStream_t st, const float* que
         const uint32_t nqt = std::min(QT, nq - qt0);
         {
             Timed t(h, ws, st, K_PREP);
-            ingest_kernel<true><<<(nqt + STAGE_ROWS - 1) / STAGE_ROWS, STAGE_ROWS, 0, st>>>(
-                queries_dev + (size_t)qt0 * h->dim, nqt, h->dim, h->cfg.threshold, h->nchunk, 0, nullptr,
-                ws->qnorm.as<float>(), nullptr, ws->qpack.as<uint32_t>(), h->qs);
+            if ((h->dim & 3) == 0)
+                query_prep_direct_kernel<<<(nqt + 31) / 32, 32, 0, st>>>(
+                    queries_dev + (size_t)qt0 * h->dim, nqt, h->dim, h->cfg.threshold, h->nchunk,
+                    ws->qnorm.as<float>(), ws->qpack.as<uint32_t>(), h->qs);
+            else
+                ingest_kernel<true><<<(nqt + STAGE_ROWS - 1) / STAGE_ROWS, STAGE_ROWS, 0, st>>>(
+                    queries_dev + (size_t)qt0 * h->dim, nqt, h->dim, h->cfg.threshold, h->nchunk, 0, nullptr,
+                    ws->qnorm.as<float>(), nullptr, ws->qpack.as<uint32_t>(), h->qs);
         }
         CU(cudaGetLastError());
-        CU(cudaMemsetAsync(ws->cnt.p, 0, (size_t)nqt * 4, st));
+        CU(cudaMemsetAsync(ws->cnt.p, 0, (size_t)nqt * 4 * CNT_STRIDE, st));
         // Large query tiles: the scan is a dense contraction -> tcgen05 (gvdb_tc.cuh).  The first
         // segment (tau = "emit all", 4096 rows) always runs on the popc kernel.
         const bool use_tc = nqt >= h->tc_min_q && tc_supported(h->nchunk) && ntiles > seg0_tiles;
@@ -466,10 +483,11 @@ void search_core(gvdb_index* h, Workspace* ws, cudaStream_t st, const float* que
                 launch_tc_scan<0>(h, ws, st, lo, hi, nqt, nq_pad, ws->cnt.as<uint32_t>(), ws->buf.as<uint64_t>(), cap,
                                   ws->flag.as<uint32_t>(), nullptr, 0);
             } else {
-                dim3 grid = scan_grid(h, hi - lo, nqt);
+                const int qg = pick_qgroup(h, hi - lo, nqt);
+                dim3 grid = scan_grid(h, hi - lo, nqt, qg);
                 Timed t(h, ws, st, K_SCAN, seg_rows * h->nchunk * 16.0 * grid.y, seg_rows * nqt);
-                launch_scan<0>(h->nchunk, h->scan_variant, st, grid, (size_t)kQGroup * h->qs * 4, h->codes, h->live, lo, hi,
-                               ws->qpack.as<uint32_t>(), (int)nqt, kQGroup, ws->cnt.as<uint32_t>(),
+                launch_scan<0>(h->nchunk, h->scan_variant, st, grid, (size_t)qg * h->qs * 4, h->codes, h->live, lo, hi,
+                               ws->qpack.as<uint32_t>(), (int)nqt, qg, ws->cnt.as<uint32_t>(),
                                ws->buf.as<uint64_t>(), cap, ws->flag.as<uint32_t>(), nullptr, 0, h->n_rows);
             }
             {
@@ -484,10 +502,16 @@ void search_core(gvdb_index* h, Workspace* ws, cudaStream_t st, const float* que
         const uint64_t pairs = (uint64_t)nqt * R;
         {
             Timed t(h, ws, st, K_RESCORE);
-            rescore_kernel<<<(unsigned)((pairs + STAGE_ROWS - 1) / STAGE_ROWS), STAGE_ROWS, 0, st>>>(
-                h->rows, h->norms, h->cfg.row_base, h->dim, queries_dev + (size_t)qt0 * h->dim,
-                ws->qnorm.as<float>(), ws->buf.as<uint64_t>(), cap, ws->cnt.as<uint32_t>(), R, nqt,
-                rec_ham + (size_t)qt0 * R, rec_ids + (size_t)qt0 * R, rec_score + (size_t)qt0 * R);
+            if ((h->dim & 3) == 0)
+                rescore_direct_kernel<<<(unsigned)((pairs + 127) / 128), 128, 0, st>>>(
+                    h->rows, h->norms, h->cfg.row_base, h->dim, queries_dev + (size_t)qt0 * h->dim,
+                    ws->qnorm.as<float>(), ws->buf.as<uint64_t>(), cap, ws->cnt.as<uint32_t>(), R, nqt,
+                    rec_ham + (size_t)qt0 * R, rec_ids + (size_t)qt0 * R, rec_score + (size_t)qt0 * R);
+            else
+                rescore_kernel<<<(unsigned)((pairs + STAGE_ROWS - 1) / STAGE_ROWS), STAGE_ROWS, 0, st>>>(
+                    h->rows, h->norms, h->cfg.row_base, h->dim, queries_dev + (size_t)qt0 * h->dim,
+                    ws->qnorm.as<float>(), ws->buf.as<uint64_t>(), cap, ws->cnt.as<uint32_t>(), R, nqt,
+                    rec_ham + (size_t)qt0 * R, rec_ids + (size_t)qt0 * R, rec_score + (size_t)qt0 * R);
         }
         CU(cudaGetLastError());
     }
@@ -541,7 +565,7 @@ void flat_device(gvdb_index* h, Workspace* ws, cudaStream_t st, const float* q_d
     const uint32_t qt_max = std::min(QT, nq);
     ws->qpack.ensure((size_t)qt_max * h->qs * 4);
     ws->qnorm.ensure((size_t)qt_max * 4);
-    ws->cnt.ensure((size_t)qt_max * 4);
+    ws->cnt.ensure((size_t)qt_max * 4 * CNT_STRIDE);
     ws->flag.ensure(256);
     ws->buf.ensure((size_t)qt_max * cap * 8);
     ws->misc.ensure((size_t)qt_max * 4);   // per-query key thresholds
@@ -558,7 +582,7 @@ void flat_device(gvdb_index* h, Workspace* ws, cudaStream_t st, const float* q_d
                 ws->qpack.as<uint32_t>(), h->qs);
         }
         CU(cudaGetLastError());
-        CU(cudaMemsetAsync(ws->cnt.p, 0, (size_t)nqt * 4, st));
+        CU(cudaMemsetAsync(ws->cnt.p, 0, (size_t)nqt * 4 * CNT_STRIDE, st));
         CU(cudaMemsetAsync(ws->misc.p, 0xff, (size_t)nqt * 4, st));   // TAU_ALL
         uint64_t lo = 0;
         while (lo < h->n_rows) {
@@ -965,6 +989,28 @@ gvdb_status gvdb_search_shard_device(gvdb_index* h, void* stream, const float* q
         search_core(h, lease.ws, lease.stream, queries_dev, nq, rescore_count,
                     reinterpret_cast<uint32_t*>(base + nr * 8), reinterpret_cast<uint64_t*>(base),
                     reinterpret_cast<float*>(base + nr * 12));
+        check_overflow(h, lease.ws, lease.stream);
+    });
+}
+
+gvdb_status gvdb_search_shard_sliced_device(gvdb_index* h, void* stream, const float* queries_dev, uint32_t nq,
+                                            uint32_t rescore_count, uint32_t n_slices, void* records_dev) {
+    return guarded([&] {
+        need(h, "index");
+        if (nq == 0) return;
+        need(queries_dev, "queries"); need(records_dev, "records");
+        if (n_slices == 0 || nq % n_slices != 0)
+            fail(GVDB_ERR_INVALID_ARGUMENT, "nq must be a positive multiple of n_slices");
+        DeviceGuard dg(h->cfg.device);
+        WsLease lease(h, (cudaStream_t)stream, true);
+        const uint32_t per = nq / n_slices;
+        const uint64_t nr = (uint64_t)per * rescore_count;
+        for (uint32_t s = 0; s < n_slices; ++s) {
+            uint8_t* base = static_cast<uint8_t*>(records_dev) + (uint64_t)s * nr * 16;
+            search_core(h, lease.ws, lease.stream, queries_dev + (size_t)s * per * h->dim, per, rescore_count,
+                        reinterpret_cast<uint32_t*>(base + nr * 8), reinterpret_cast<uint64_t*>(base),
+                        reinterpret_cast<float*>(base + nr * 12), s == 0);
+        }
         check_overflow(h, lease.ws, lease.stream);
     });
 }

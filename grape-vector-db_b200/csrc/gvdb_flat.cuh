@@ -102,7 +102,7 @@ flat_scan_kernel(const float* __restrict__ rows, const float* __restrict__ norms
                           : __fsub_rn(1.0f, __fdiv_rn(acc[i][j], __fmul_rn(qn[j], rn)));
             const uint32_t img = f32_asc_key(d);
             if (img < tq[j]) {
-                const uint32_t pos = atomicAdd(&cnt[q], 1u);
+                const uint32_t pos = atomicAdd(&cnt[(size_t)q * CNT_STRIDE], 1u);
                 if (pos < cap) buf[(size_t)q * cap + pos] = ((uint64_t)img << 32) | (uint32_t)row;
                 else *overflow = 1u;
             }
@@ -118,7 +118,7 @@ __global__ void flat_emit_kernel(const uint64_t* __restrict__ buf, uint32_t cap,
     uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= nq * k) return;
     uint32_t q = idx / k, t = idx % k;
-    if (t < cnt[q]) {
+    if (t < cnt[(size_t)q * CNT_STRIDE]) {
         uint64_t key = buf[(size_t)q * cap + t];
         uint32_t u = (uint32_t)(key >> 32);
         uint32_t bits = (u & 0x80000000u) ? (u ^ 0x80000000u) : ~u;

@@ -27,6 +27,9 @@
 namespace gvdb {
 
 constexpr uint32_t TAU_ALL = 0xffffffffu;   // "emit every live row"
+// Per-query candidate counters live one per 128-byte line (cnt[q * CNT_STRIDE]): appends are L2
+// atomics, which serialise per line; packed counters put 1024 hot addresses on 32 lines.
+constexpr int CNT_STRIDE = 32;
 constexpr int SCAN_THREADS = 256;           // 8 warps = 8 tiles of 32 rows in flight per CTA
 constexpr int SORT_N = 4096;                // block bitonic capacity (u64 keys, 32 KB smem)
 constexpr int SORT_THREADS = 1024;
@@ -340,7 +343,7 @@ scan_kernel(const uint4* __restrict__ codes, const uint32_t* __restrict__ live, 
                     if (m) {
                         uint32_t base = 0;
                         const int leader = __ffs(m) - 1;
-                        if (lane == leader) base = atomicAdd(&cnt[q0 + q], (uint32_t)__popc(m));
+                        if (lane == leader) base = atomicAdd(&cnt[(size_t)(q0 + q) * CNT_STRIDE], (uint32_t)__popc(m));
                         base = __shfl_sync(0xffffffffu, base, leader);
                         if (hit) {
                             const uint32_t pos = base + __popc(m & ((1u << lane) - 1u));
@@ -349,7 +352,7 @@ scan_kernel(const uint4* __restrict__ codes, const uint32_t* __restrict__ live, 
                         }
                     }
                 } else if (hit) {
-                    const uint32_t pos = atomicAdd(&cnt[q0 + q], 1u);
+                    const uint32_t pos = atomicAdd(&cnt[(size_t)(q0 + q) * CNT_STRIDE], 1u);
                     if (pos < cap) buf[(size_t)(q0 + q) * cap + pos] = ((uint64_t)d << 32) | row;
                     else *overflow = 1u;
                 }
@@ -372,7 +375,7 @@ select_kernel(uint64_t* __restrict__ buf, uint32_t cap, uint32_t* __restrict__ c
     extern __shared__ __align__(16) uint64_t skeys[];
     const uint32_t q = blockIdx.x;
     uint64_t* mine = buf + (size_t)q * cap;
-    const uint32_t n_in = min(cnt[q], cap);
+    const uint32_t n_in = min(cnt[(size_t)q * CNT_STRIDE], cap);
     uint32_t have = 0, consumed = 0;
     while (consumed < n_in) {
         const uint32_t take = min((uint32_t)SORT_N - have, n_in - consumed);
@@ -388,7 +391,7 @@ select_kernel(uint64_t* __restrict__ buf, uint32_t cap, uint32_t* __restrict__ c
     __syncthreads();
     for (uint32_t i = threadIdx.x; i < have; i += blockDim.x) mine[i] = skeys[i];
     if (threadIdx.x == 0) {
-        cnt[q] = have;
+        cnt[(size_t)q * CNT_STRIDE] = have;
         qpack[(size_t)q * qs + tau_word] = (have >= R && R > 0) ? (uint32_t)(skeys[R - 1] >> 32) : TAU_ALL;
     }
 }
@@ -413,7 +416,7 @@ select_hist_kernel(uint64_t* __restrict__ buf, uint32_t cap, uint32_t* __restric
     __shared__ uint32_t s_bstar, s_below, s_nsel, s_ntie, s_prefix, s_need;
     const uint32_t q = blockIdx.x;
     uint64_t* mine = buf + (size_t)q * cap;
-    const uint32_t n = min(cnt[q], cap);
+    const uint32_t n = min(cnt[(size_t)q * CNT_STRIDE], cap);
     const uint32_t tid = threadIdx.x;
 
     if (n <= R) {                                   // everything is kept: just order it
@@ -422,7 +425,7 @@ select_hist_kernel(uint64_t* __restrict__ buf, uint32_t cap, uint32_t* __restric
         bitonic_sort_smem(sel, r_pow2);
         for (uint32_t i = tid; i < n; i += SELH_THREADS) mine[i] = sel[i];
         if (tid == 0) {
-            cnt[q] = n;
+            cnt[(size_t)q * CNT_STRIDE] = n;
             qpack[(size_t)q * qs + tau_word] = (n >= R && R > 0) ? (uint32_t)(sel[R - 1] >> 32) : TAU_ALL;
         }
         return;
@@ -510,7 +513,7 @@ select_hist_kernel(uint64_t* __restrict__ buf, uint32_t cap, uint32_t* __restric
     bitonic_sort_smem(sel, r_pow2);
     for (uint32_t i = tid; i < R; i += SELH_THREADS) mine[i] = sel[i];
     if (tid == 0) {
-        cnt[q] = R;
+        cnt[(size_t)q * CNT_STRIDE] = R;
         qpack[(size_t)q * qs + tau_word] = (uint32_t)(sel[R - 1] >> 32);
     }
 }
@@ -536,7 +539,7 @@ rescore_kernel(const float* __restrict__ rows, const float* __restrict__ norms, 
     const uint64_t p = (uint64_t)blockIdx.x * STAGE_ROWS + tid;
     const uint32_t q = (uint32_t)(p / R), r = (uint32_t)(p % R);
     const bool slot = q < nq;
-    const bool valid = slot && r < cnt[q];
+    const bool valid = slot && r < cnt[(size_t)q * CNT_STRIDE];
     uint64_t key = valid ? buf[(size_t)q * cap + r] : UINT64_MAX;
     s_row[tid] = valid ? (uint32_t)key : 0xffffffffu;
     s_q[tid] = valid ? q : 0xffffffffu;
@@ -583,6 +586,101 @@ rescore_kernel(const float* __restrict__ rows, const float* __restrict__ norms, 
         out_ids[p] = valid ? row_base + (uint32_t)key : UINT64_MAX;
         out_score[p] = cosv;
     }
+}
+
+// ---------------------------------------------------------------------------------------
+// Direct variants for dim % 4 == 0 (every BASELINE config): no shared-memory transposition.
+// Each thread streams ITS row with 128-bit loads, DEPTH loads in flight (the loads are
+// independent; only the f32 adds form the sequential chain the reference's fold dictates),
+// so the kernels run at memory-system speed instead of one global-latency per 32-column slab.
+constexpr int DIRECT_DEPTH = 8;      // float4 loads in flight per operand per thread
+
+__device__ __forceinline__ float4 ldg_f4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+
+// queries -> qpack (code words, then [tau = TAU_ALL, 0, 0, 0]) + sequential-fold norms.
+// Same outputs as ingest_kernel<true>; one thread per query, 32 queries per CTA.
+__global__ void __launch_bounds__(32)
+query_prep_direct_kernel(const float* __restrict__ x, uint32_t n, int dim, float thr, int nchunk,
+                         float* __restrict__ norms, uint32_t* __restrict__ qpack, int qs) {
+    const uint32_t i = blockIdx.x * 32u + threadIdx.x;
+    if (i >= n) return;
+    const float* row = x + (size_t)i * dim;
+    const int nv = dim >> 2;                       // float4 per row
+    float ss = 0.0f;
+    uint32_t word = 0;
+    uint32_t* out = qpack + (size_t)i * qs;
+    for (int v0 = 0; v0 < nv; v0 += DIRECT_DEPTH) {
+        float4 buf[DIRECT_DEPTH];
+#pragma unroll
+        for (int u = 0; u < DIRECT_DEPTH; ++u)
+            buf[u] = v0 + u < nv ? ldg_f4(row + 4 * (v0 + u)) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int u = 0; u < DIRECT_DEPTH; ++u) {
+            if (v0 + u < nv) {
+                const float e4[4] = {buf[u].x, buf[u].y, buf[u].z, buf[u].w};
+                const int j0 = 4 * (v0 + u);
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    const float v = e4[t];
+                    ss = __fadd_rn(ss, __fmul_rn(v, v));
+                    const int e = (j0 + t) & 31;
+                    // Msb0 inside each byte, bytes in memory order (little-endian word)
+                    word |= (uint32_t)(v > thr) << ((e & ~7) | (7 - (e & 7)));
+                }
+                if (((j0 + 4) & 31) == 0) { out[j0 >> 5] = word; word = 0; }
+            }
+        }
+    }
+    const int full_words = dim >> 5;
+    if (dim & 31) out[full_words] = word;          // trailing partial word (pad bits 0)
+    for (int w = (dim + 31) >> 5; w < nchunk * 4; ++w) out[w] = 0u;
+    out[nchunk * 4] = TAU_ALL; out[nchunk * 4 + 1] = 0u; out[nchunk * 4 + 2] = 0u; out[nchunk * 4 + 3] = 0u;
+    norms[i] = __fsqrt_rn(ss);
+}
+
+// Same contract as rescore_kernel; one thread per (query, candidate) pair.
+__global__ void __launch_bounds__(128)
+rescore_direct_kernel(const float* __restrict__ rows, const float* __restrict__ norms, uint64_t row_base,
+                      int dim, const float* __restrict__ queries, const float* __restrict__ qnorm,
+                      const uint64_t* __restrict__ buf, uint32_t cap, const uint32_t* __restrict__ cnt,
+                      uint32_t R, uint32_t nq, uint32_t* __restrict__ out_ham,
+                      uint64_t* __restrict__ out_ids, float* __restrict__ out_score) {
+    const uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t q = (uint32_t)(p / R), r = (uint32_t)(p % R);
+    if (q >= nq) return;
+    const bool valid = r < cnt[(size_t)q * CNT_STRIDE];
+    float cosv = -INFINITY;
+    uint64_t key = UINT64_MAX;
+    if (valid) {
+        key = buf[(size_t)q * cap + r];
+        const float* crow = rows + (size_t)(uint32_t)key * dim;
+        const float* qrow = queries + (size_t)q * dim;
+        const int nv = dim >> 2;
+        float dot = 0.0f;
+        for (int v0 = 0; v0 < nv; v0 += DIRECT_DEPTH) {
+            float4 a[DIRECT_DEPTH], b[DIRECT_DEPTH];
+#pragma unroll
+            for (int u = 0; u < DIRECT_DEPTH; ++u) {
+                const bool in = v0 + u < nv;
+                a[u] = in ? ldg_f4(qrow + 4 * (v0 + u)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                b[u] = in ? ldg_f4(crow + 4 * (v0 + u)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int u = 0; u < DIRECT_DEPTH; ++u) {
+                if (v0 + u < nv) {
+                    dot = __fadd_rn(dot, __fmul_rn(a[u].x, b[u].x));
+                    dot = __fadd_rn(dot, __fmul_rn(a[u].y, b[u].y));
+                    dot = __fadd_rn(dot, __fmul_rn(a[u].z, b[u].z));
+                    dot = __fadd_rn(dot, __fmul_rn(a[u].w, b[u].w));
+                }
+            }
+        }
+        const float na = qnorm[q], nb = norms[(uint32_t)key];
+        cosv = (na == 0.0f || nb == 0.0f) ? 0.0f : __fdiv_rn(dot, __fmul_rn(na, nb));
+    }
+    out_ham[p] = valid ? (uint32_t)(key >> 32) : 0xffffffffu;
+    out_ids[p] = valid ? row_base + (uint32_t)key : UINT64_MAX;
+    out_score[p] = cosv;
 }
 
 // ---------------------------------------------------------------------------------------

@@ -521,7 +521,7 @@ __global__ void tc_scatter_kernel(const uint2* __restrict__ recs, uint32_t rec_c
             const uint4 a = rc[c * 32], b = qc[c];
             d += __popc(a.x ^ b.x) + __popc(a.y ^ b.y) + __popc(a.z ^ b.z) + __popc(a.w ^ b.w);
         }
-        const uint32_t pos = atomicAdd(&cnt[q], 1u);
+        const uint32_t pos = atomicAdd(&cnt[(size_t)q * CNT_STRIDE], 1u);
         if (pos < cap) buf[(size_t)q * cap + pos] = ((uint64_t)d << 32) | row;
         else *overflow = 1u;
     }

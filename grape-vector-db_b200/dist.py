@@ -3,9 +3,10 @@
 
 Partitioning: rank g owns the contiguous global rows
 [g*ceil(N/G), min(N, (g+1)*ceil(N/G))), both codes and f32 originals; queries are replicated.
-Each rank answers with one packed record buffer (its local top-R per query, already
-rescored); ONE all-gather moves the buffers; every rank then runs the merge kernel, which
-re-applies the stage-1 cut globally and orders by (cosine desc, hamming asc, row asc) —
+Each rank answers with packed record buffers (its local top-R per query, already rescored),
+one per query slice; ONE all-to-all moves them so that rank r holds every shard's records for
+query slice r; rank r runs the merge kernel on its slice, which re-applies the stage-1 cut
+globally and orders by (cosine desc, hamming asc, row asc) —
 the rule that makes the sharded answer equal to the single-index answer, where the
 reference's own scatter/gather is concat + sort + truncate
 (/root/reference/src/distributed/shard.rs:760-786).
@@ -62,8 +63,39 @@ def all_gather_records(local, group=None):
     return out
 
 
+def all_to_all_records(send, group=None):
+    """The query-sliced exchange: `send` is `world` equal chunks, chunk s = this shard's packed
+    records for query slice s; the result is `world` chunks, chunk r = rank r's records for MY
+    slice — exactly the layout gvdb_merge_shards_device consumes.  NCCL: one all_to_all_single
+    over NVLink; gloo (CPU tests): the same data movement with an all-gather + slice."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    assert send.numel() % world == 0
+    per = send.numel() // world
+    if send.is_cuda:
+        recv = torch.empty_like(send)
+        dist.all_to_all_single(recv, send, group=group)
+        return recv
+    everything = all_gather_records(send, group)          # [world][world][per]
+    return torch.cat([everything[r * send.numel() + rank * per: r * send.numel() + (rank + 1) * per]
+                      for r in range(world)])
+
+
+def slice_bounds(nq: int, world: int, rank: int) -> tuple[int, int]:
+    """Query slice of `rank` when nq is a multiple of world."""
+    per = nq // world
+    return rank * per, (rank + 1) * per
+
+
 class ShardedSearcher:
-    """Drives one rank's GpuIndex shard and the exchange + merge."""
+    """Drives one rank's GpuIndex shard and the exchange + merge.
+
+    Every rank holds the same (replicated) query batch.  Each rank scans ITS rows for all the
+    queries and writes its local top-R records grouped by query slice; one all-to-all gives
+    rank r every shard's records for query slice r; rank r merges those (global stage-1 cut +
+    final order) and a last small all-gather makes the top-k lists complete on every rank."""
 
     def __init__(self, index, group=None):
         import torch.distributed as dist
@@ -72,8 +104,7 @@ class ShardedSearcher:
         self.distributed = dist.is_available() and dist.is_initialized()
         self.world = dist.get_world_size(group) if self.distributed else 1
         self.rank = dist.get_rank(group) if self.distributed else 0
-        self._local = None
-        self._all = None
+        self._send = None
 
     def search_batch_device(self, queries_t, k: int, rescore_count: int, ids_out=None,
                             scores_out=None):
@@ -82,11 +113,24 @@ class ShardedSearcher:
         if self.world == 1:
             return self.index.search_batch_device(queries_t, k, rescore_count, ids_out, scores_out)
         nq = queries_t.shape[0]
-        nbytes = self.index.shard_record_bytes(nq, rescore_count)
-        if self._local is None or self._local.numel() != nbytes:
-            self._local = torch.empty(nbytes, dtype=torch.uint8, device=queries_t.device)
-            self._all = torch.empty(nbytes * self.world, dtype=torch.uint8, device=queries_t.device)
-        self.index.search_shard_device(queries_t, rescore_count, records_out=self._local)
-        dist.all_gather_into_tensor(self._all, self._local, group=self.group)
-        return self.index.merge_shards_device(self._all, self.world, nq, rescore_count, k,
-                                              ids_out, scores_out)
+        W = self.world
+        pad = (-nq) % W
+        if pad:   # equal slices: repeat the last query, drop its answers below
+            queries_t = torch.cat([queries_t, queries_t[-1:].expand(pad, -1)]).contiguous()
+        nqp = nq + pad
+        per = nqp // W
+        nbytes = W * self.index.shard_record_bytes(per, rescore_count)
+        if self._send is None or self._send.numel() != nbytes:
+            self._send = torch.empty(nbytes, dtype=torch.uint8, device=queries_t.device)
+        self.index.search_shard_sliced_device(queries_t, rescore_count, W, records_out=self._send)
+        recv = all_to_all_records(self._send, self.group)
+        my_ids, my_sc = self.index.merge_shards_device(recv, W, per, rescore_count, k)
+        all_ids = torch.empty((nqp, k), dtype=torch.int64, device=queries_t.device)
+        all_sc = torch.empty((nqp, k), dtype=torch.float32, device=queries_t.device)
+        dist.all_gather_into_tensor(all_ids, my_ids, group=self.group)
+        dist.all_gather_into_tensor(all_sc, my_sc, group=self.group)
+        if ids_out is not None:
+            ids_out.copy_(all_ids[:nq])
+            scores_out.copy_(all_sc[:nq])
+            return ids_out, scores_out
+        return all_ids[:nq], all_sc[:nq]

@@ -221,6 +221,23 @@ class GpuIndex:
             C.c_void_p(records_out.data_ptr())))
         return records_out
 
+    def search_shard_sliced_device(self, queries_t, rescore_count: int, n_slices: int, records_out=None):
+        """n_slices packed record buffers back to back, buffer s for queries
+        [s*nq/n_slices, (s+1)*nq/n_slices) — the send buffer of a query-sliced all-to-all."""
+        import torch
+        nq = queries_t.shape[0]
+        assert nq % n_slices == 0
+        dev = queries_t.device
+        nbytes = n_slices * self.shard_record_bytes(nq // n_slices, rescore_count)
+        if records_out is None:
+            records_out = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        assert records_out.numel() == nbytes and records_out.is_contiguous()
+        st = torch.cuda.current_stream(dev).cuda_stream
+        self._ok(self._lib.gvdb_search_shard_sliced_device(
+            self._h, C.c_void_p(st), C.c_void_p(queries_t.data_ptr()), nq, rescore_count, n_slices,
+            C.c_void_p(records_out.data_ptr())))
+        return records_out
+
     def merge_shards_device(self, records_all, n_shards: int, nq: int, rescore_count: int, k: int,
                             ids_out=None, scores_out=None):
         """n_shards packed record buffers back to back -> (ids [nq,k] int64, scores [nq,k] f32)."""

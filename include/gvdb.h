@@ -159,6 +159,14 @@ GVDB_API uint64_t gvdb_shard_record_bytes(uint32_t nq, uint32_t rescore_count);
  * local stage 1 + stage 2 of this shard -> records_dev (DEVICE, gvdb_shard_record_bytes). */
 GVDB_API gvdb_status gvdb_search_shard_device(gvdb_index* h, void* stream, const float* queries_dev,
                                               uint32_t nq, uint32_t rescore_count, void* records_dev);
+/* Same, with the answer laid out for a query-sliced exchange: queries are cut into n_slices equal
+ * consecutive slices (nq % n_slices == 0) and records_dev receives n_slices packed buffers back
+ * to back, buffer s = gvdb_shard_record_bytes(nq / n_slices, R) bytes for slice s.  With one
+ * slice per rank an all-to-all hands every rank all shards' records for ITS slice of the
+ * queries, so the merge (and the rest of the per-query work) is divided across ranks too. */
+GVDB_API gvdb_status gvdb_search_shard_sliced_device(gvdb_index* h, void* stream, const float* queries_dev,
+                                                     uint32_t nq, uint32_t rescore_count, uint32_t n_slices,
+                                                     void* records_dev);
 /* Replaces the gather side (concat + sort + truncate, src/distributed/shard.rs:776-783) with the
  * rule that reproduces the single-index result: over the n_shards x R gathered records of
  * each query keep the global top R by (hamming, global row), then order by (cosine desc,

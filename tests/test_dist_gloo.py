@@ -45,6 +45,26 @@ def _worker(rank, world, port, n, dim, nq, R, k, out_dir):
     local = torch.from_numpy(gdist.pack_records(ids, ham, sc))
     assert local.numel() == gdist.record_bytes(nq, R)
     allrec = gdist.all_gather_records(local).numpy()
+    # the query-sliced exchange the product uses (one slice per rank): every rank merges ITS slice
+    per_q = nq // world
+    send = torch.from_numpy(np.concatenate([
+        gdist.pack_records(ids[s * per_q:(s + 1) * per_q], ham[s * per_q:(s + 1) * per_q],
+                           sc[s * per_q:(s + 1) * per_q]) for s in range(world)]))
+    recv = gdist.all_to_all_records(send).numpy()
+    per_b = gdist.record_bytes(per_q, R)
+    mine = [gdist.unpack_records(recv[s * per_b:(s + 1) * per_b], per_q, R) for s in range(world)]
+    sl_i = np.zeros((per_q, k), np.uint64)
+    sl_s = np.zeros((per_q, k), np.float32)
+    for qi in range(per_q):
+        gi, gs = oracle.shard_merge(np.concatenate([p[1][qi] for p in mine]),
+                                    np.concatenate([p[0][qi] for p in mine]),
+                                    np.concatenate([p[2][qi] for p in mine]), R, k)
+        sl_i[qi, :len(gi)] = gi
+        sl_s[qi, :len(gs)] = gs
+    lo_q, hi_q = gdist.slice_bounds(nq, world, rank)
+    assert hi_q - lo_q == per_q
+    np.save(os.path.join(out_dir, f"slice_ids_{rank}.npy"), sl_i)
+    np.save(os.path.join(out_dir, f"slice_sc_{rank}.npy"), sl_s)
     if rank == 0:
         per = gdist.record_bytes(nq, R)
         parts = [gdist.unpack_records(allrec[s * per:(s + 1) * per], nq, R) for s in range(world)]
@@ -99,3 +119,8 @@ def test_two_rank_gloo_exchange_and_merge(tmp_path):
     got_s = np.load(tmp_path / "sc.npy")
     assert np.array_equal(got_i, want_i)
     assert np.array_equal(got_s.view(np.uint32), want_s.view(np.uint32))
+    # query-sliced all-to-all: rank r's merged slice == rows [r*nq/world, ...) of the answer
+    sl_i = np.concatenate([np.load(tmp_path / f"slice_ids_{r}.npy") for r in range(world)])
+    sl_s = np.concatenate([np.load(tmp_path / f"slice_sc_{r}.npy") for r in range(world)])
+    assert np.array_equal(sl_i, want_i)
+    assert np.array_equal(sl_s.view(np.uint32), want_s.view(np.uint32))

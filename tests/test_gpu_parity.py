@@ -249,6 +249,41 @@ def test_logical_shards_merge_equals_single_index(gv):
             ix.close()
 
 
+def test_query_sliced_exchange_equals_single_index(gv):
+    """The N>1 data path emulated on ONE GPU: S logical shards each write their records grouped
+    by query slice (gvdb_search_shard_sliced_device); "rank" r then merges every shard's
+    records for slice r.  Concatenated slices == the single-index result, bit for bit."""
+    import torch
+    from grape_vector_db_b200 import synth
+    dev = torch.device("cuda:0")
+    n, dim, nq, R, k = 40_000, 768, 96, 40, 10
+    rows = synth.lowrank_rows(0, n, dim)
+    qs = synth.lowrank_queries(0, nq, dim)
+    qs_t = torch.from_numpy(qs).to(dev)
+    oi, os_ = oracle.multi_stage_search_batch(qs, rows, R, k, nthreads=8)
+    for S in (2, 4):
+        per_rows = (n + S - 1) // S
+        shards, sends = [], []
+        for s in range(S):
+            lo, hi = s * per_rows, min(n, (s + 1) * per_rows)
+            ix = gv.GpuIndex(dim, row_base=lo)
+            ix.add(rows[lo:hi])
+            shards.append(ix)
+            sends.append(ix.search_shard_sliced_device(qs_t, R, S))
+        per_q = nq // S
+        per_b = shards[0].shard_record_bytes(per_q, R)
+        got_i, got_s = [], []
+        for r in range(S):     # what rank r receives from the all-to-all
+            recv = torch.cat([sends[src][r * per_b:(r + 1) * per_b] for src in range(S)]).contiguous()
+            mi, ms = shards[r].merge_shards_device(recv, S, per_q, R, k)
+            got_i.append(mi.cpu().numpy().astype(np.uint64))
+            got_s.append(ms.cpu().numpy())
+        assert np.array_equal(np.concatenate(got_i), oi), f"S={S}"
+        assert np.array_equal(_bits(np.concatenate(got_s)), _bits(os_)), f"S={S}"
+        for ix in shards:
+            ix.close()
+
+
 @pytest.mark.parametrize("dim", [64, 384, 500, 768])
 def test_tensor_core_scan_distances_bit_exact(gv, dim):
     """>= 64 queries route the scan to the tcgen05 kernel (gvdb_tc.cuh): all distances exact."""

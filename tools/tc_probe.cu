@@ -54,11 +54,11 @@ int main(int argc, char** argv) {
     CK(cudaMalloc(&d_qexp, (size_t)(nq_pad / TC_NQ) * tc_qblock_bytes(NCHUNK))); CK(cudaMalloc(&d_qbias, nq_pad * 4)); CK(cudaMalloc(&d_qpop, nq_pad * 4));
     const uint32_t cap = 8192; const uint32_t rec_cap = 1u << 17;
     CK(cudaMalloc(&d_recs, (size_t)148 * 4 * rec_cap * 8)); CK(cudaMalloc(&d_ctacnt, 148 * 4 * 4)); CK(cudaMemset(d_ctacnt, 0, 148 * 4 * 4));
-    CK(cudaMalloc(&d_cnt, nq_pad * 4)); CK(cudaMalloc(&d_flag, 4)); CK(cudaMalloc(&d_buf, (size_t)nq_pad * cap * 8));
+    CK(cudaMalloc(&d_cnt, nq_pad * 4 * CNT_STRIDE)); CK(cudaMalloc(&d_flag, 4)); CK(cudaMalloc(&d_buf, (size_t)nq_pad * cap * 8));
     CK(cudaMemcpy(d_codes, h_codes.data(), code_words * 4, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(d_qpack, h_qpack.data(), h_qpack.size() * 4, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(d_live, h_live.data(), ntiles * 4, cudaMemcpyHostToDevice));
-    CK(cudaMemset(d_tc, 0xff, dist_bytes)); CK(cudaMemset(d_cnt, 0, nq_pad * 4)); CK(cudaMemset(d_flag, 0, 4));
+    CK(cudaMemset(d_tc, 0xff, dist_bytes)); CK(cudaMemset(d_cnt, 0, nq_pad * 4 * CNT_STRIDE)); CK(cudaMemset(d_flag, 0, 4));
 
     tc_expand_queries_kernel<<<nq_pad, 64>>>(d_qpack, qs, NCHUNK, nq, nq_pad, d_qexp, d_qpop);
     CK(cudaGetLastError());
@@ -99,14 +99,15 @@ int main(int argc, char** argv) {
         CK(cudaFuncSetAttribute(tc_scan_kernel<NCHUNK, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         const uint32_t bigcap = 65536;
         uint64_t* d_buf2; CK(cudaMalloc(&d_buf2, (size_t)nq_pad * bigcap * 8));
-        CK(cudaMemset(d_cnt, 0, nq_pad * 4));
+        CK(cudaMemset(d_cnt, 0, nq_pad * 4 * CNT_STRIDE));
         tc_scan_kernel<NCHUNK, 0><<<grid, TC_THREADS, smem>>>(d_codes, d_live, 0, ntiles, d_qexp, d_qpop, d_qbias, nq, nq_pad, n_qsl, n_rsl,
                                                              d_recs, rec_cap, d_ctacnt, d_flag, nullptr, 0, n_rows);
         tc_scatter_kernel<<<dim3(TC_SCATTER_X, grid * 4), 256>>>(d_recs, rec_cap, d_ctacnt, d_codes, NCHUNK, d_qpack, qs, d_cnt, d_buf2, bigcap, d_flag);
         CK(cudaGetLastError());
         CK(cudaDeviceSynchronize());
-        std::vector<uint32_t> h_cnt(nq_pad);
-        CK(cudaMemcpy(h_cnt.data(), d_cnt, nq_pad * 4, cudaMemcpyDeviceToHost));
+        std::vector<uint32_t> h_cnt_s((size_t)nq_pad * CNT_STRIDE), h_cnt(nq_pad);
+        CK(cudaMemcpy(h_cnt_s.data(), d_cnt, (size_t)nq_pad * 4 * CNT_STRIDE, cudaMemcpyDeviceToHost));
+        for (uint32_t q = 0; q < nq_pad; ++q) h_cnt[q] = h_cnt_s[(size_t)q * CNT_STRIDE];
         std::vector<uint64_t> h_buf((size_t)nq_pad * bigcap);
         CK(cudaMemcpy(h_buf.data(), d_buf2, h_buf.size() * 8, cudaMemcpyDeviceToHost));
         size_t badq = 0, total = 0;
@@ -141,7 +142,7 @@ int main(int argc, char** argv) {
         for (int dbg : {0, 1}) {
         cudaEventRecord(e0);
         for (int rep = 0; rep < reps; ++rep) {
-            cudaMemsetAsync(d_cnt, 0, nq_pad * 4);
+            cudaMemsetAsync(d_cnt, 0, nq_pad * 4 * CNT_STRIDE);
             tc_scan_kernel<NCHUNK, 0><<<grid, TC_THREADS, smem>>>(d_codes, d_live, 0, ntiles, d_qexp, d_qpop, d_qbias, nq, nq_pad, n_qsl, n_rsl,
                                                                  d_recs, rec_cap, d_ctacnt, d_flag, nullptr, 0, n_rows, dbg, d_prof);
             if (!(dbg & 1)) tc_scatter_kernel<<<dim3(TC_SCATTER_X, grid * 4), 256>>>(d_recs, rec_cap, d_ctacnt, d_codes, NCHUNK, d_qpack, qs, d_cnt, d_buf, cap, d_flag);
