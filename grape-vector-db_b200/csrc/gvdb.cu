@@ -502,11 +502,23 @@ void search_core(gvdb_index* h, Workspace* ws, cudaStream_t st, const float* que
         const uint64_t pairs = (uint64_t)nqt * R;
         {
             Timed t(h, ws, st, K_RESCORE);
-            if ((h->dim & 3) == 0)
-                rescore_direct_kernel<<<(unsigned)((pairs + 127) / 128), 128, 0, st>>>(
-                    h->rows, h->norms, h->cfg.row_base, h->dim, queries_dev + (size_t)qt0 * h->dim,
+            if ((h->dim & 3) == 0) {
+                const int cols = std::min(h->dim, RS_SLAB);
+                const int stride = ((cols >> 2) & 1) ? cols : cols + 4;      // stride/4 odd: conflict-free LDS.128
+                // 32 consecutive pairs touch at most 31/R + 2 consecutive queries
+                const int q_slots = (int)std::min<uint32_t>(32, 31 / R + 2);
+                const size_t smem = (size_t)(32 + q_slots) * stride * sizeof(float);
+                static bool attr = false;   // benign race: idempotent
+                if (!attr) {
+                    CU(cudaFuncSetAttribute(rescore_slab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            64 * (RS_SLAB + 4) * (int)sizeof(float)));
+                    attr = true;
+                }
+                rescore_slab_kernel<<<(unsigned)((pairs + 31) / 32), 32, smem, st>>>(
+                    h->rows, h->norms, h->cfg.row_base, h->dim, stride, q_slots, queries_dev + (size_t)qt0 * h->dim,
                     ws->qnorm.as<float>(), ws->buf.as<uint64_t>(), cap, ws->cnt.as<uint32_t>(), R, nqt,
                     rec_ham + (size_t)qt0 * R, rec_ids + (size_t)qt0 * R, rec_score + (size_t)qt0 * R);
+            }
             else
                 rescore_kernel<<<(unsigned)((pairs + STAGE_ROWS - 1) / STAGE_ROWS), STAGE_ROWS, 0, st>>>(
                     h->rows, h->norms, h->cfg.row_base, h->dim, queries_dev + (size_t)qt0 * h->dim,

@@ -638,49 +638,82 @@ query_prep_direct_kernel(const float* __restrict__ x, uint32_t n, int dim, float
     norms[i] = __fsqrt_rn(ss);
 }
 
-// Same contract as rescore_kernel; one thread per (query, candidate) pair.
-__global__ void __launch_bounds__(128)
-rescore_direct_kernel(const float* __restrict__ rows, const float* __restrict__ norms, uint64_t row_base,
-                      int dim, const float* __restrict__ queries, const float* __restrict__ qnorm,
-                      const uint64_t* __restrict__ buf, uint32_t cap, const uint32_t* __restrict__ cnt,
-                      uint32_t R, uint32_t nq, uint32_t* __restrict__ out_ham,
-                      uint64_t* __restrict__ out_ids, float* __restrict__ out_score) {
-    const uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+// ---------------------------------------------------------------------------------------
+// rescore_slab_kernel (dim % 4 == 0): one WARP per 32 (query, candidate) pairs.  The warp copies
+// its 32 candidate rows into shared memory with cp.async, every row as contiguous 512-byte
+// requests (a gather of whole 3 KB rows runs at HBM speed; per-lane 16-byte reads of 32
+// different rows do not), then lane l folds pair l strictly left to right from shared memory.
+// Rows sit `stride` floats apart with stride/4 odd, so the per-lane LDS.128 are conflict-free.
+// Slabs of up to RS_SLAB columns bound the shared memory for large dims.
+constexpr int RS_SLAB = 768;
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
+
+__global__ void __launch_bounds__(32)
+rescore_slab_kernel(const float* __restrict__ rows, const float* __restrict__ norms, uint64_t row_base,
+                    int dim, int stride, int q_slots, const float* __restrict__ queries,
+                    const float* __restrict__ qnorm, const uint64_t* __restrict__ buf, uint32_t cap,
+                    const uint32_t* __restrict__ cnt, uint32_t R, uint32_t nq, uint32_t* __restrict__ out_ham,
+                    uint64_t* __restrict__ out_ids, float* __restrict__ out_score) {
+    extern __shared__ __align__(16) float srow[];            // 32 candidate rows, then q_slots query rows
+    float* sq = srow + (size_t)32 * stride;
+    const int lane = threadIdx.x;
+    const uint64_t p0 = (uint64_t)blockIdx.x * 32u;
+    const uint64_t p = p0 + lane;
     const uint32_t q = (uint32_t)(p / R), r = (uint32_t)(p % R);
-    if (q >= nq) return;
-    const bool valid = r < cnt[(size_t)q * CNT_STRIDE];
-    float cosv = -INFINITY;
-    uint64_t key = UINT64_MAX;
-    if (valid) {
-        key = buf[(size_t)q * cap + r];
-        const float* crow = rows + (size_t)(uint32_t)key * dim;
-        const float* qrow = queries + (size_t)q * dim;
-        const int nv = dim >> 2;
-        float dot = 0.0f;
-        for (int v0 = 0; v0 < nv; v0 += DIRECT_DEPTH) {
-            float4 a[DIRECT_DEPTH], b[DIRECT_DEPTH];
-#pragma unroll
-            for (int u = 0; u < DIRECT_DEPTH; ++u) {
-                const bool in = v0 + u < nv;
-                a[u] = in ? ldg_f4(qrow + 4 * (v0 + u)) : make_float4(0.f, 0.f, 0.f, 0.f);
-                b[u] = in ? ldg_f4(crow + 4 * (v0 + u)) : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-#pragma unroll
-            for (int u = 0; u < DIRECT_DEPTH; ++u) {
-                if (v0 + u < nv) {
-                    dot = __fadd_rn(dot, __fmul_rn(a[u].x, b[u].x));
-                    dot = __fadd_rn(dot, __fmul_rn(a[u].y, b[u].y));
-                    dot = __fadd_rn(dot, __fmul_rn(a[u].z, b[u].z));
-                    dot = __fadd_rn(dot, __fmul_rn(a[u].w, b[u].w));
-                }
+    const uint32_t q_first = (uint32_t)(p0 / R);             // the warp's pairs cover queries q_first ...
+    const bool slot = q < nq;
+    const bool valid = slot && r < cnt[(size_t)q * CNT_STRIDE];
+    const uint64_t key = valid ? buf[(size_t)q * cap + r] : UINT64_MAX;
+    const uint32_t my_row = (uint32_t)key;
+    float dot = 0.0f;
+    for (int c0 = 0; c0 < dim; c0 += RS_SLAB) {
+        const int cols = min(RS_SLAB, dim - c0);
+        const int nv = cols >> 2;                            // float4 per row in this slab
+        if (c0) __syncwarp();
+        for (int rr = 0; rr < 32; ++rr) {                    // row rr of the warp, 512 B per request
+            const uint32_t grow = __shfl_sync(0xffffffffu, my_row, rr);
+            if (grow == 0xffffffffu) continue;               // warp-uniform
+            const float* src = rows + (size_t)grow * dim + c0;
+            const uint32_t dst = smem_u32(srow + (size_t)rr * stride);
+            for (int v = lane; v < nv; v += 32) cp_async16(dst + 16u * v, src + 4 * v);
+        }
+        for (int qq = 0; qq < q_slots; ++qq) {               // the (few) distinct queries of these pairs
+            if (q_first + qq >= nq) break;
+            const float* src = queries + (size_t)(q_first + qq) * dim + c0;
+            const uint32_t dst = smem_u32(sq + (size_t)qq * stride);
+            for (int v = lane; v < nv; v += 32) cp_async16(dst + 16u * v, src + 4 * v);
+        }
+        cp_async_wait_all();
+        __syncwarp();
+        if (valid) {
+            const float4* mine = reinterpret_cast<const float4*>(srow + (size_t)lane * stride);
+            const float4* myq = reinterpret_cast<const float4*>(sq + (size_t)(q - q_first) * stride);
+#pragma unroll 4
+            for (int v = 0; v < nv; ++v) {
+                const float4 a = myq[v], b = mine[v];
+                dot = __fadd_rn(dot, __fmul_rn(a.x, b.x));
+                dot = __fadd_rn(dot, __fmul_rn(a.y, b.y));
+                dot = __fadd_rn(dot, __fmul_rn(a.z, b.z));
+                dot = __fadd_rn(dot, __fmul_rn(a.w, b.w));
             }
         }
-        const float na = qnorm[q], nb = norms[(uint32_t)key];
-        cosv = (na == 0.0f || nb == 0.0f) ? 0.0f : __fdiv_rn(dot, __fmul_rn(na, nb));
     }
-    out_ham[p] = valid ? (uint32_t)(key >> 32) : 0xffffffffu;
-    out_ids[p] = valid ? row_base + (uint32_t)key : UINT64_MAX;
-    out_score[p] = cosv;
+    if (slot) {
+        float cosv = -INFINITY;
+        if (valid) {
+            const float na = qnorm[q], nb = norms[my_row];
+            cosv = (na == 0.0f || nb == 0.0f) ? 0.0f : __fdiv_rn(dot, __fmul_rn(na, nb));
+        }
+        out_ham[p] = valid ? (uint32_t)(key >> 32) : 0xffffffffu;
+        out_ids[p] = valid ? row_base + my_row : UINT64_MAX;
+        out_score[p] = cosv;
+    }
 }
 
 // ---------------------------------------------------------------------------------------
