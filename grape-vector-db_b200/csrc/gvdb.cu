@@ -291,8 +291,8 @@ void launch_scan(int nchunk, int variant, cudaStream_t st, dim3 grid, size_t sme
 #undef GVDB_ARGS
 }
 
-// ---- tcgen05 scan dispatch (dims up to 768: A operand + 2 accumulators fit the 512 TMEM columns) ---
-bool tc_supported(int nchunk) { return nchunk == 1 || nchunk == 2 || nchunk == 3 || nchunk == 4 || nchunk == 6; }
+// ---- tcgen05 scan dispatch (codes up to 1536 bits: the resident query block must fit shared memory) ---
+bool tc_supported(int nchunk) { return tc_supported_chunks(nchunk); }
 
 // MODE 0: survivors -> warp-private record lists -> tc_scatter_kernel -> per-query buffers.
 // MODE 1: every distance to dist_out (parity).
@@ -301,7 +301,8 @@ bool tc_supported(int nchunk) { return nchunk == 1 || nchunk == 2 || nchunk == 3
 struct TcSplit { uint32_t qslices, rslices, grid; };
 TcSplit tc_split(const gvdb_index* h, uint32_t ngroups, uint32_t nq_pad) {
     const uint32_t sms = (uint32_t)h->sm_count;
-    const uint32_t qsl = (nq_pad / TC_NQ + TC_QBLOCKS - 1) / TC_QBLOCKS;
+    const uint32_t qb = (uint32_t)tc_qblocks(h->nchunk);
+    const uint32_t qsl = (nq_pad / TC_NQ + qb - 1) / qb;
     const uint32_t rmax = std::max<uint32_t>(1, std::min<uint32_t>(ngroups, std::max<uint32_t>(1, 8 * sms / qsl)));
     uint32_t best = 1;
     double best_eff = 0.0;
@@ -324,7 +325,7 @@ void launch_tc_scan(gvdb_index* h, Workspace* ws, cudaStream_t st, uint32_t tile
     const TcSplit sp = tc_split(h, ngroups, nq_pad);
     const uint32_t grid = sp.grid;
     const uint32_t nlists = grid * 4;
-    const size_t smem = (size_t)TC_QBLOCKS * tc_qblock_bytes(h->nchunk);
+    const size_t smem = (size_t)tc_qblocks(h->nchunk) * tc_qblock_bytes(h->nchunk);
     uint32_t rec_cap = 0;
     if (MODE == 0) {
         // expected survivors per launch <= nq * cap / 4 (segment sizing); 4x head-room per list
@@ -348,7 +349,7 @@ void launch_tc_scan(gvdb_index* h, Workspace* ws, cudaStream_t st, uint32_t tile
         static bool attr = false;                                                                    \
         if (!attr) {                                                                                 \
             CU(cudaFuncSetAttribute(tc_scan_kernel<N, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                    (int)(TC_QBLOCKS * tc_qblock_bytes(N))));                        \
+                                    (int)(tc_qblocks(N) * tc_qblock_bytes(N))));                        \
             attr = true;                                                                             \
         }                                                                                            \
         tc_scan_kernel<N, MODE><<<grid, TC_THREADS, smem, st>>>(h->codes, h->live, tile_lo, tile_hi, qexp, qpop, qbias, \
@@ -357,7 +358,7 @@ void launch_tc_scan(gvdb_index* h, Workspace* ws, cudaStream_t st, uint32_t tile
         break;                                                                                       \
     }
     switch (h->nchunk) {
-        GVDB_TC_CASE(1) GVDB_TC_CASE(2) GVDB_TC_CASE(3) GVDB_TC_CASE(4) GVDB_TC_CASE(6)
+        GVDB_TC_CASE(1) GVDB_TC_CASE(2) GVDB_TC_CASE(3) GVDB_TC_CASE(4) GVDB_TC_CASE(6) GVDB_TC_CASE(8) GVDB_TC_CASE(12)
         default: fail(GVDB_ERR_INDEX, "tcgen05 scan: unsupported code width");
     }
 #undef GVDB_TC_CASE

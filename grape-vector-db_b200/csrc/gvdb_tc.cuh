@@ -21,20 +21,21 @@
 // so the expansion is spread over two issue pipes.  The K order this implies is a fixed
 // permutation of the code bits applied to rows and queries alike (Hamming distance is invariant).
 //
-// Work decomposition.  item = (query slice, row slice).  A query slice is up to TC_QBLOCKS blocks
+// Work decomposition.  item = (query slice, row slice).  A query slice is up to tc_qblocks() blocks
 // of 128 queries whose expanded codes (+ bias digits) stay RESIDENT in shared memory (200 KB at
-// 768 bits) for the whole item; the item's rows stream through TMEM as the A operand, 128 at a
-// time.  (Streaming the queries through a shared-memory ring instead needs 64 B/clk/SM from L2,
+// 768 bits: two blocks; 196 KB at 1536 bits: one block) for the whole item; the item's rows stream
+// through TMEM as the A operand, 128 at a time.  (Streaming the queries through a shared-memory ring instead needs 64 B/clk/SM from L2,
 // more than the L2 delivers to 148 SMs at once: that version measured 47 % of the MMA floor.)
 //
 // Warp roles per CTA (one CTA per SM, persistent over items):
 //   warps 0-3  expanders: lane = row.  Load the row's code (coalesced, blocked layout, next group
-//              prefetched), expand it and write it into TMEM as the A operand (tcgen05.st), in
-//              two K halves with their own ready/free barriers so that rewriting A for the next
-//              128 rows overlaps the MMAs still reading the other half.
+//              prefetched), expand it and write it into TMEM as the A operand (tcgen05.st).  A is a
+//              ring of two slots with their own ready/free barriers; a group goes through it in 2
+//              phases (4 for 1024/1536-bit codes), so rewriting one slot overlaps the MMAs that
+//              still read the other.
 //   warps 4-7  epilogue: read the int32 accumulators back (tcgen05.ld), sign-test them and append
 //              survivors to warp-private record lists (MODE 0), or write every distance (MODE 1).
-//   warp 8     one thread: TMA bulk loads of the query slice, then tcgen05.mma issue
+//   warp 8     warp-uniform control flow, one elected lane: TMA bulk loads of the query slice, then tcgen05.mma issue
 //              (M=128, N=128, K=32; A from TMEM, B from shared memory, D in TMEM, 2 buffers).
 //   mbarriers  b_full/b_free, a_ready/a_free per K half, acc_full/acc_empty per accumulator
 //              buffer; tcgen05.commit signals MMA completion.
@@ -50,7 +51,15 @@ constexpr int TC_ROWS = 128;        // rows per group (UMMA M)
 constexpr int TC_NQ = 128;          // queries per accumulator block (UMMA N)
 constexpr int TC_KSTAGE = 128;      // K bytes per 16 KB query sub-block = one 16-byte code chunk
 constexpr int TC_STAGE_BYTES = TC_NQ * TC_KSTAGE;   // 16 KB
-constexpr int TC_QBLOCKS = 2;       // resident query blocks per item = TMEM accumulator buffers
+// Resident query blocks per item (each has its own TMEM accumulator buffer): two while they fit
+// the 227 KB of shared memory (K <= 768 bits), one for 1024- and 1536-bit codes.
+__host__ __device__ constexpr int tc_qblocks(int nchunk) { return nchunk <= 6 ? 2 : 1; }
+// The A operand lives in a ring of two TMEM slots of tc_slot_chunks() code chunks (32 columns
+// each); a row group is expanded and consumed in phases, phase ph using slot ph & 1.
+__host__ __device__ constexpr int tc_slot_chunks(int nchunk) { return nchunk <= 6 ? (nchunk + 1) / 2 : nchunk / 4; }
+__host__ __device__ constexpr bool tc_supported_chunks(int nchunk) {
+    return nchunk == 1 || nchunk == 2 || nchunk == 3 || nchunk == 4 || nchunk == 6 || nchunk == 8 || nchunk == 12;
+}
 constexpr int TC_THREADS = 288;     // 4 expander warps + 4 epilogue warps + loader/MMA-issuer warp
 constexpr uint32_t TC_TMEM_COLS = 512;
 constexpr int TC_BIAS_BYTES = TC_NQ * 32;           // 4 KB: one K=32 slice of per-query bias digits
@@ -209,16 +218,18 @@ tc_scan_kernel(const uint4* __restrict__ codes, const uint32_t* __restrict__ liv
                uint32_t* __restrict__ list_counts, uint32_t* __restrict__ overflow,
                uint32_t* __restrict__ dist_out, uint64_t dist_stride, uint64_t n_rows, int dbg = 0,
                unsigned long long* __restrict__ prof = nullptr) {
-    constexpr int K = NCHUNK * 128;
-    constexpr int A_COLS = K / 4;              // TMEM columns of the A operand (+8: the bias slice)
-    constexpr int LO = (NCHUNK + 1) / 2;       // chunks in the low half of A (own ready/free barriers)
+    constexpr int QB = tc_qblocks(NCHUNK);     // resident query blocks
+    constexpr int SC = tc_slot_chunks(NCHUNK); // chunks per A slot
+    constexpr int PH = (NCHUNK + SC - 1) / SC; // phases per row group
+    constexpr int A_COLS = 2 * SC * 32;        // TMEM columns of the A ring (+8: the bias slice)
     constexpr uint32_t IDESC = tc_idesc_i8(TC_ROWS, TC_NQ);
     constexpr uint32_t QBLOCK_BYTES = (uint32_t)tc_qblock_bytes(NCHUNK);
     static_assert(A_COLS + 8 + 2 * TC_NQ <= 512, "TMEM budget");
+    static_assert(QB * tc_qblock_bytes(NCHUNK) <= 220 * 1024, "shared memory budget");
 
-    extern __shared__ __align__(1024) uint8_t smem[];      // TC_QBLOCKS resident query blocks
-    __shared__ int32_t s_bias[TC_QBLOCKS * TC_NQ];           // MODE 1 only
-    __shared__ uint32_t s_pop[TC_QBLOCKS * TC_NQ];
+    extern __shared__ __align__(1024) uint8_t smem[];      // QB resident query blocks
+    __shared__ int32_t s_bias[QB * TC_NQ];                   // MODE 1 only
+    __shared__ uint32_t s_pop[QB * TC_NQ];
     __shared__ __align__(8) uint64_t bars[10];
     __shared__ uint32_t s_tmem_base;
     const uint32_t bar0 = smem_u32(bars);
@@ -255,8 +266,8 @@ tc_scan_kernel(const uint4* __restrict__ codes, const uint32_t* __restrict__ liv
     // item -> (query blocks, row groups)
     auto item_range = [&](uint32_t item, uint32_t& qb0, uint32_t& nb, uint32_t& g_lo, uint32_t& g_hi) {
         const uint32_t qsl = item / n_rslices, rsl = item % n_rslices;
-        qb0 = qsl * TC_QBLOCKS;
-        nb = min((uint32_t)TC_QBLOCKS, nqb - qb0);
+        qb0 = qsl * QB;
+        nb = min((uint32_t)QB, nqb - qb0);
         g_lo = (uint32_t)((uint64_t)ngroups * rsl / n_rslices);
         g_hi = (uint32_t)((uint64_t)ngroups * (rsl + 1) / n_rslices);
     };
@@ -277,7 +288,7 @@ tc_scan_kernel(const uint4* __restrict__ codes, const uint32_t* __restrict__ liv
             for (int c = 0; c < NCHUNK; ++c)
                 r[c] = in_range ? ldg_stream(codes + ((size_t)tile * NCHUNK + c) * 32 + lane) : make_uint4(0, 0, 0, 0);
         };
-        auto expand = [&](const uint4 (&r)[NCHUNK], int c_lo, int c_hi, int h) {
+        auto expand = [&](const uint4 (&r)[NCHUNK], int c_lo, int c_hi, int h) {   // chunks [c_lo, c_hi) -> slot h
             { TC_PROF_T0(); mbar_wait(a_free(h), free_phase[h]); TC_PROF_ADD(h); }   // MMAs that read this half have retired
             free_phase[h] ^= 1u;
             tc_fence_after();
@@ -291,7 +302,7 @@ tc_scan_kernel(const uint4* __restrict__ codes, const uint32_t* __restrict__ liv
                     uint32_t v[8];
 #pragma unroll
                     for (int i = 0; i < 8; ++i) v[i] = (w4[wi] << (7 - i)) & TC_A_BIT4;
-                    tc_st8(tmem_a + lane_taddr + (uint32_t)((c * 4 + wi) * 8), v);
+                    tc_st8(tmem_a + lane_taddr + (uint32_t)(h * SC * 32 + ((c - c_lo) * 4 + wi) * 8), v);
                 }
             }
             tc_wait_st();
@@ -308,8 +319,9 @@ tc_scan_kernel(const uint4* __restrict__ codes, const uint32_t* __restrict__ liv
             for (uint32_t g = g_lo; g < g_hi; ++g) {
                 uint4 rn[NCHUNK];
                 if (g + 1 < g_hi) load_codes(g + 1, rn);       // in flight while this group expands
-                expand(r, 0, LO, 0);
-                expand(r, LO, NCHUNK, 1);
+#pragma unroll
+                for (int ph = 0; ph < PH; ++ph)
+                    expand(r, ph * SC, (ph + 1) * SC < NCHUNK ? (ph + 1) * SC : NCHUNK, ph & 1);
 #pragma unroll
                 for (int c = 0; c < NCHUNK; ++c) r[c] = rn[c];
             }
@@ -450,8 +462,8 @@ tc_scan_kernel(const uint4* __restrict__ codes, const uint32_t* __restrict__ liv
                     const uint32_t d_addr = tmem_d + b * TC_NQ;
 #pragma unroll
                     for (int ks = 0; ks < NCHUNK; ++ks) {
-                        if (blk == 0 && (ks == 0 || ks == LO)) {
-                            const int h = ks == 0 ? 0 : 1;
+                        const int ph = ks / SC, h = ph & 1, kc = ks % SC;   // phase, slot, chunk in slot
+                        if (blk == 0 && kc == 0) {
                             { TC_PROF_T0(); mbar_wait(a_ready(h), ready_phase[h]); TC_PROF_ADD(1 + h); }
                             ready_phase[h] ^= 1u;
                             tc_fence_after();
@@ -459,21 +471,18 @@ tc_scan_kernel(const uint4* __restrict__ codes, const uint32_t* __restrict__ liv
                         if (elect_one()) {
 #pragma unroll
                             for (int j = 0; j < TC_KSTAGE / 32; ++j)      // the address field counts 16-byte units
-                                tc_mma_i8_ts(d_addr, tmem_a + (uint32_t)((ks * (TC_KSTAGE / 32) + j) * 8),
+                                tc_mma_i8_ts(d_addr, tmem_a + (uint32_t)(h * SC * 32 + (kc * (TC_KSTAGE / 32) + j) * 8),
                                              bdesc0 + (uint64_t)((ks * TC_STAGE_BYTES + j * 256) >> 4), IDESC, (ks | j) != 0 ? 1u : 0u);
-                            if (last_blk && ks == LO - 1) tc_commit(a_free(0));   // low half of A may be rewritten
+                            // this slot of A may be rewritten once the MMAs issued so far retire
+                            if (last_blk && kc == SC - 1 && ks != NCHUNK - 1) tc_commit(a_free(h));
                         }
                         __syncwarp();
-                    }
-                    if (NCHUNK == 1 && blk == 0) {      // high half is empty: keep its barriers in step
-                        mbar_wait(a_ready(1), ready_phase[1]);
-                        ready_phase[1] ^= 1u;
                     }
                     if (elect_one()) {
                         // bias: D += (-128)(128 x 32) * digits(128 queries x 32)
                         tc_mma_i8_ts(d_addr, tmem_a + A_COLS,
                                      tc_smem_desc(smem_u32(smem + blk * QBLOCK_BYTES + NCHUNK * TC_STAGE_BYTES), 128, 256), IDESC, 1u);
-                        if (last_blk) tc_commit(a_free(1));
+                        if (last_blk) tc_commit(a_free(((NCHUNK - 1) / SC) & 1));   // the last phase's slot
                         tc_commit(acc_full(b));
                     }
                     __syncwarp();

@@ -284,7 +284,7 @@ def test_query_sliced_exchange_equals_single_index(gv):
             ix.close()
 
 
-@pytest.mark.parametrize("dim", [64, 384, 500, 768])
+@pytest.mark.parametrize("dim", [64, 384, 500, 768, 1024, 1536])
 def test_tensor_core_scan_distances_bit_exact(gv, dim):
     """>= 64 queries route the scan to the tcgen05 kernel (gvdb_tc.cuh): all distances exact."""
     from grape_vector_db_b200 import synth
@@ -310,6 +310,10 @@ def test_tensor_core_search_path(gv, monkeypatch):
     rows2 = synth.iid_rows(0, 70_000, 256)
     qs2 = synth.iid_queries(0, 130, 256)
     _check_two_stage(gv, rows2, qs2[:70], 300, 20)
+    # 1536-bit codes (text-embedding-3-small width): one resident query block, four A phases
+    rows4 = synth.lowrank_rows(0, 50_000, 1536)
+    qs4 = synth.lowrank_queries(0, 140, 1536)
+    _check_two_stage(gv, rows4, qs4, 40, 10)
     # heavy ties + tombstones on the tensor-core path
     rng = np.random.default_rng(5)
     rows3 = rng.integers(-1, 2, size=(30_000, 48)).astype(np.float32)

@@ -30,7 +30,11 @@ static uint64_t rng_state = 88172645463325252ull;
 static uint32_t rnd() { rng_state ^= rng_state << 13; rng_state ^= rng_state >> 7; rng_state ^= rng_state << 17; return (uint32_t)(rng_state >> 16); }
 
 int main(int argc, char** argv) {
-    constexpr int NCHUNK = 6;
+#ifndef PROBE_NCHUNK
+#define PROBE_NCHUNK 6
+#endif
+    constexpr int NCHUNK = PROBE_NCHUNK;
+    constexpr int TC_QBLOCKS = tc_qblocks(NCHUNK);
     const int qs = NCHUNK * 4 + 4;
     uint64_t n_rows = argc > 1 ? atoll(argv[1]) : 148 * 128 * 2 + 77;
     uint32_t nq = argc > 2 ? atoi(argv[2]) : 300;
