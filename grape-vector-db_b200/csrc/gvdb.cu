@@ -28,6 +28,7 @@
 #include "gvdb_flat.cuh"
 #include "gvdb_kernels.cuh"
 #include "gvdb_tc.cuh"
+#include "gvdb_bigr.cuh"
 
 namespace {
 
@@ -88,10 +89,12 @@ struct Workspace {
     DevBuf q_in, ids_out, sc_out, codes_tmp, misc;
     DevBuf qexp, qpop, qbias;        // tcgen05 path: pre-expanded queries, popcounts, biases
     DevBuf tc_recs, list_counts;     // tcgen05 path: warp-private survivor records
+    DevBuf big_keys, big_keys2, big_aux, big_k32, big_v32, big_tmp;   // large-R path (gvdb_bigr.cuh)
     uint32_t* h_flag = nullptr;      // pinned
     ~Workspace() {
         for (DevBuf* b : {&qpack, &qnorm, &cnt, &flag, &buf, &rec_ham, &rec_ids, &rec_score, &q_in,
-                          &ids_out, &sc_out, &codes_tmp, &misc, &qexp, &qpop, &qbias, &tc_recs, &list_counts}) b->release();
+                          &ids_out, &sc_out, &codes_tmp, &misc, &qexp, &qpop, &qbias, &tc_recs, &list_counts,
+                          &big_keys, &big_keys2, &big_aux, &big_k32, &big_v32, &big_tmp}) b->release();
         if (h_flag) cudaFreeHost(h_flag);
         for (cudaEvent_t e : ev_pool) cudaEventDestroy(e);
         if (idle) cudaEventDestroy(idle);
@@ -427,7 +430,7 @@ void search_core(gvdb_index* h, Workspace* ws, cudaStream_t st, const float* que
     if (h->n_rows == 0) fail(GVDB_ERR_INDEX_NOT_BUILT, "index not built: search before any add");
     if (R == 0) fail(GVDB_ERR_INVALID_ARGUMENT, "rescore_count must be >= 1");
     if (R > kMaxR)
-        fail(GVDB_ERR_NOT_IMPLEMENTED, "rescore_count > 2048 is not implemented on the GPU path yet");
+        fail(GVDB_ERR_NOT_IMPLEMENTED, "rescore_count > 2048 is not implemented for the sharded entry points");
     const uint32_t cap = pick_cap(R);
     const uint32_t ntiles = (uint32_t)tiles_for(h->n_rows);
     const uint32_t QT = h->query_tile;
@@ -552,10 +555,106 @@ void launch_topk(gvdb_index* h, Workspace* ws, cudaStream_t st, const uint64_t* 
     CU(cudaGetLastError());
 }
 
+// Large rescore counts (R > 2048): the cut by counting of gvdb_bigr.cuh, one query at a time
+// (distances are produced for chunks of queries).  Same outputs and ordering as search_device.
+void search_big_r(gvdb_index* h, Workspace* ws, cudaStream_t st, const float* q_dev, uint32_t nq, uint32_t k,
+                  uint32_t R, uint64_t* ids_out, float* scores_out, uint64_t* cand_ids, uint32_t* cand_ham) {
+    if (h->n_rows == 0) fail(GVDB_ERR_INDEX_NOT_BUILT, "index not built: search before any add");
+    if ((h->dim & 3) != 0) fail(GVDB_ERR_NOT_IMPLEMENTED, "rescore_count > 2048 needs dim % 4 == 0");
+    const uint64_t N = h->n_rows;
+    const uint32_t ntiles = (uint32_t)tiles_for(N);
+    const uint32_t nbins = (uint32_t)h->nchunk * 128 + 1;
+    int key_bits = 32;
+    while ((1u << (key_bits - 32)) < nbins) ++key_bits;
+    const uint32_t QC = std::min<uint32_t>(nq, 16);
+    ws->qpack.ensure((size_t)QC * h->qs * 4);
+    ws->qnorm.ensure((size_t)QC * 4);
+    ws->misc.ensure((size_t)QC * N * 4);
+    ws->big_keys.ensure(N * 8);
+    ws->big_keys2.ensure(N * 8);
+    ws->big_aux.ensure((size_t)nbins * 4 + 64);
+    ws->big_k32.ensure((size_t)R * 8);
+    ws->big_v32.ensure((size_t)R * 8);
+    ws->rec_ham.ensure((size_t)R * 4);
+    ws->rec_ids.ensure((size_t)R * 8);
+    ws->rec_score.ensure((size_t)R * 4);
+    uint32_t* hist = ws->big_aux.as<uint32_t>();
+    BigRCut* cut = reinterpret_cast<BigRCut*>(ws->big_aux.as<uint8_t>() + (size_t)nbins * 4 + (16 - (nbins * 4) % 16) % 16);
+    uint32_t* k32 = ws->big_k32.as<uint32_t>();
+    uint32_t* k32o = k32 + R;
+    uint32_t* v32 = ws->big_v32.as<uint32_t>();
+    uint32_t* v32o = v32 + R;
+    size_t tmp_a = 0, tmp_b = 0;
+    CU(cub::DeviceRadixSort::SortKeys(nullptr, tmp_a, ws->big_keys.as<uint64_t>(), ws->big_keys2.as<uint64_t>(),
+                                      (int64_t)N, 0, key_bits, st));
+    CU(cub::DeviceRadixSort::SortPairs(nullptr, tmp_b, k32, k32o, v32, v32o, (int64_t)R, 0, 32, st));
+    ws->big_tmp.ensure(std::max(tmp_a, tmp_b) + 256);
+    static bool attr = false;   // benign race: idempotent
+    if (!attr) {
+        CU(cudaFuncSetAttribute(rescore_slab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                64 * (RS_SLAB + 4) * (int)sizeof(float)));
+        attr = true;
+    }
+    const int cols = std::min(h->dim, RS_SLAB);
+    const int stride = ((cols >> 2) & 1) ? cols : cols + 4;
+    const int hist_grid = (int)std::min<uint64_t>((N + 255) / 256, (uint64_t)h->sm_count * 8);
+    for (uint32_t q0 = 0; q0 < nq; q0 += QC) {
+        const uint32_t m = std::min(QC, nq - q0);
+        query_prep_direct_kernel<<<(m + 31) / 32, 32, 0, st>>>(q_dev + (size_t)q0 * h->dim, m, h->dim, h->cfg.threshold,
+                                                              h->nchunk, ws->qnorm.as<float>(), ws->qpack.as<uint32_t>(), h->qs);
+        CU(cudaGetLastError());
+        {
+            const int qg = pick_qgroup(h, ntiles, m);
+            dim3 grid = scan_grid(h, ntiles, m, qg);
+            launch_scan<1>(h->nchunk, -1, st, grid, (size_t)qg * h->qs * 4, h->codes, h->live, 0, ntiles,
+                           ws->qpack.as<uint32_t>(), (int)m, qg, nullptr, nullptr, 0, nullptr, ws->misc.as<uint32_t>(), N, N);
+        }
+        h->launches.fetch_add(2, std::memory_order_relaxed);
+        for (uint32_t qi = 0; qi < m; ++qi) {
+            const uint32_t* dist = ws->misc.as<uint32_t>() + (size_t)qi * N;
+            const uint32_t gq = q0 + qi;
+            CU(cudaMemsetAsync(ws->big_aux.p, 0, ws->big_aux.bytes, st));
+            dist_hist_kernel<<<hist_grid, 256, nbins * 4, st>>>(dist, h->live, N, nbins, hist);
+            cut_kernel<<<1, 32, 0, st>>>(hist, nbins, R, cut);
+            CU(cudaGetLastError());
+            BigRCut hc;
+            CU(cudaMemcpyAsync(&hc, cut, sizeof(hc), cudaMemcpyDeviceToHost, st));
+            CU(cudaStreamSynchronize(st));
+            if (hc.r_eff > 0) {
+                cut_compact_kernel<<<hist_grid, 256, 0, st>>>(dist, h->live, N, cut, ws->big_keys.as<uint64_t>());
+                size_t tb = ws->big_tmp.bytes;
+                CU(cub::DeviceRadixSort::SortKeys(ws->big_tmp.p, tb, ws->big_keys.as<uint64_t>(), ws->big_keys2.as<uint64_t>(),
+                                                  (int64_t)hc.m, 0, key_bits, st));
+            }
+            // candidates = the first r_eff sorted keys; rescoring writes the query's R records
+            const int q_slots = 2;
+            rescore_slab_kernel<<<(R + 31) / 32, 32, (size_t)(32 + q_slots) * stride * sizeof(float), st>>>(
+                h->rows, h->norms, h->cfg.row_base, h->dim, stride, q_slots, q_dev + (size_t)gq * h->dim,
+                ws->qnorm.as<float>() + qi, ws->big_keys2.as<uint64_t>(), 0, &cut->r_eff, R, 1,
+                ws->rec_ham.as<uint32_t>(), ws->rec_ids.as<uint64_t>(), ws->rec_score.as<float>());
+            cos_key_kernel<<<(R + 255) / 256, 256, 0, st>>>(ws->rec_score.as<float>(), R, k32, v32);
+            size_t tb = ws->big_tmp.bytes;
+            CU(cub::DeviceRadixSort::SortPairs(ws->big_tmp.p, tb, k32, k32o, v32, v32o, (int64_t)R, 0, 32, st));
+            bigr_emit_kernel<<<(k + 255) / 256, 256, 0, st>>>(v32o, cut, ws->rec_ids.as<uint64_t>(), ws->rec_score.as<float>(), k,
+                                                            ids_out + (size_t)gq * k, scores_out + (size_t)gq * k);
+            CU(cudaGetLastError());
+            if (cand_ids) CU(cudaMemcpyAsync(cand_ids + (size_t)gq * R, ws->rec_ids.p, (size_t)R * 8, cudaMemcpyDeviceToDevice, st));
+            if (cand_ham) CU(cudaMemcpyAsync(cand_ham + (size_t)gq * R, ws->rec_ham.p, (size_t)R * 4, cudaMemcpyDeviceToDevice, st));
+            h->launches.fetch_add(7, std::memory_order_relaxed);
+        }
+    }
+    CU(cudaStreamSynchronize(st));
+    flush_profile(h, ws);
+}
+
 void search_device(gvdb_index* h, Workspace* ws, cudaStream_t st, const float* q_dev, uint32_t nq,
                    uint32_t k, uint32_t R, uint64_t* ids_out, float* scores_out, uint64_t* cand_ids,
                    uint32_t* cand_ham) {
     if (k > R) fail(GVDB_ERR_INVALID_ARGUMENT, "k must be <= rescore_count");
+    if (R > kMaxR) {
+        search_big_r(h, ws, st, q_dev, nq, k, R, ids_out, scores_out, cand_ids, cand_ham);
+        return;
+    }
     ws->rec_ham.ensure((size_t)nq * R * 4);
     ws->rec_ids.ensure((size_t)nq * R * 8);
     ws->rec_score.ensure((size_t)nq * R * 4);
@@ -941,12 +1040,20 @@ gvdb_status gvdb_search_batch(gvdb_index* h, const float* queries, uint32_t nq, 
         ws->ids_out.ensure((size_t)nq * std::max(k, 1u) * 8);
         ws->sc_out.ensure((size_t)nq * std::max(k, 1u) * 4);
         CU(cudaMemcpyAsync(ws->q_in.p, queries, (size_t)nq * h->dim * 4, cudaMemcpyHostToDevice, st));
+        // the large-R path keeps one query's records at a time: give it full candidate buffers
+        uint64_t* cand_ids_dev = nullptr;
+        uint32_t* cand_ham_dev = nullptr;
+        if (R > kMaxR && (cand_ids_out || cand_ham_out)) {
+            ws->codes_tmp.ensure((size_t)nq * R * 12);
+            cand_ids_dev = ws->codes_tmp.as<uint64_t>();
+            cand_ham_dev = reinterpret_cast<uint32_t*>(ws->codes_tmp.as<uint8_t>() + (size_t)nq * R * 8);
+        }
         search_device(h, ws, st, ws->q_in.as<float>(), nq, k, R, ws->ids_out.as<uint64_t>(),
-                      ws->sc_out.as<float>(), nullptr, nullptr);
+                      ws->sc_out.as<float>(), cand_ids_dev, cand_ham_dev);
         CU(cudaMemcpyAsync(ids_out, ws->ids_out.p, (size_t)nq * k * 8, cudaMemcpyDeviceToHost, st));
         CU(cudaMemcpyAsync(scores_out, ws->sc_out.p, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, st));
-        if (cand_ids_out) CU(cudaMemcpyAsync(cand_ids_out, ws->rec_ids.p, (size_t)nq * R * 8, cudaMemcpyDeviceToHost, st));
-        if (cand_ham_out) CU(cudaMemcpyAsync(cand_ham_out, ws->rec_ham.p, (size_t)nq * R * 4, cudaMemcpyDeviceToHost, st));
+        if (cand_ids_out) CU(cudaMemcpyAsync(cand_ids_out, cand_ids_dev ? (void*)cand_ids_dev : ws->rec_ids.p, (size_t)nq * R * 8, cudaMemcpyDeviceToHost, st));
+        if (cand_ham_out) CU(cudaMemcpyAsync(cand_ham_out, cand_ham_dev ? (void*)cand_ham_dev : ws->rec_ham.p, (size_t)nq * R * 4, cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
     });
 }

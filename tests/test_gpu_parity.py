@@ -104,6 +104,45 @@ def test_iid_dataset_and_ties(gv):
     _check_two_stage(gv, rows, qs, 300, 17)
 
 
+def test_ratio_mode_large_rescore_count(gv):
+    """The reference's default rescore_ratio = 0.1 on corpora where R > 2048 (quantization.rs:178-179):
+    the cut-by-counting path.  Stage-1 list, ids and scores bit-exact; k = R (the reference returns
+    all R pairs), ties at the threshold bin, tombstones, R >= live rows."""
+    from grape_vector_db_b200 import synth
+    rows = synth.lowrank_rows(0, 60_000, 256)
+    qs = synth.lowrank_queries(0, 5, 256)
+    with gv.GpuIndex(256) as idx:
+        R = idx.rescore_count(60_000, 0.1)
+    assert R == 6000
+    _check_two_stage(gv, rows, qs[:3], R, 10)
+    _check_two_stage(gv, rows, qs[3:5], R, R)
+    # heavy ties: 24-bit codes of a 3-letter alphabet, R cuts through a huge tie group
+    rng = np.random.default_rng(11)
+    rows2 = rng.integers(-1, 2, size=(40_000, 24)).astype(np.float32)
+    qs2 = rng.integers(-1, 2, size=(3, 24)).astype(np.float32)
+    _check_two_stage(gv, rows2, qs2, 4000, 50)
+    # R larger than the corpus, and tombstones
+    rows3 = synth.iid_rows(0, 3000, 128)
+    qs3 = synth.iid_queries(0, 2, 128)
+    _check_two_stage(gv, rows3, qs3, 5000, 5000)
+    with gv.GpuIndex(128) as idx:
+        idx.add(rows3)
+        dead = list(range(1, 3000, 3))
+        for d in dead:
+            idx.remove(d)
+        ids, sc = idx.search_batch(qs3, 2500, 2500)
+    live = np.ones(3000, dtype=bool)
+    live[dead] = False
+    kept = np.flatnonzero(live)
+    for qi in range(2):
+        oi, os_ = oracle.multi_stage_search(qs3[qi], rows3[live], 2500)
+        n = len(oi)
+        assert n == 2000
+        assert np.array_equal(ids[qi, :n], kept[oi.astype(np.int64)].astype(np.uint64))
+        assert np.array_equal(_bits(sc[qi, :n]), _bits(os_))
+        assert np.all(ids[qi, n:] == gv.NO_ID)
+
+
 def test_segmented_scan_larger_corpus(gv):
     """Enough rows for several geometric scan segments (4096 -> 209k -> ...)."""
     from grape_vector_db_b200 import synth
