@@ -287,6 +287,7 @@ def run_ours(args, rank, world, local_rank):
                      "during the run; the HBM-bound operating point of the scan (1-2 queries per pass, "
                      "CUDA-core kernel) is roofline_stream."),
             "stage_ms_per_step": {x: prof[x] / K for x in stage_keys},
+            "optimistic_reruns": int(prof["optimistic_reruns"]),
         }
     else:
         achieved = prof["scan_bytes"] / (prof["scan_ms"] * 1e-3) / 1e9 if prof["scan_ms"] > 0 else 0.0

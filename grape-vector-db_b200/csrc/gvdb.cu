@@ -122,9 +122,11 @@ struct gvdb_index {
     int scan_variant = -1;     // GVDB_SCAN_NCSA: adder-count override for tuning (768-d only)
     uint32_t tc_min_q = 64;    // GVDB_TC_MIN_Q: query-tile size from which the tcgen05 scan is used
     uint32_t seg0_rows = 4096; // GVDB_SEG0_ROWS: rows of the first ("emit everything") segment
+    uint32_t opt_m = 5;        // GVDB_OPT_M: order statistic of the optimistic single-pass threshold (0 = off)
     uint32_t seg_growth = 16;  // GVDB_SEG_GROWTH: cap on the geometric segment growth (0 = cap/(4R) only)
     std::atomic<int> profile_on{0};
     std::atomic<uint64_t> launches{0};
+    std::atomic<uint64_t> optimistic_reruns{0};
     std::mutex prof_mu;
     gvdb_profile prof{};
 };
@@ -426,7 +428,7 @@ constexpr uint32_t kMaxR = SORT_N / 2;
 // Stage 1 + stage 2 for queries [0,nq) (device pointers): fills rec_* [nq][R].
 void search_core(gvdb_index* h, Workspace* ws, cudaStream_t st, const float* queries_dev,
                  uint32_t nq, uint32_t R, uint32_t* rec_ham, uint64_t* rec_ids, float* rec_score,
-                 bool reset_overflow_flag = true) {
+                 bool reset_overflow_flag = true, bool allow_optimistic = true, bool* used_optimistic = nullptr) {
     if (h->n_rows == 0) fail(GVDB_ERR_INDEX_NOT_BUILT, "index not built: search before any add");
     if (R == 0) fail(GVDB_ERR_INVALID_ARGUMENT, "rescore_count must be >= 1");
     if (R > kMaxR)
@@ -476,10 +478,17 @@ void search_core(gvdb_index* h, Workspace* ws, cudaStream_t st, const float* que
         // segment (tau = "emit all", 4096 rows) always runs on the popc kernel.
         const bool use_tc = nqt >= h->tc_min_q && tc_supported(h->nchunk) && ntiles > seg0_tiles;
         const uint32_t nq_pad = (nqt + TC_NQ - 1) / TC_NQ * TC_NQ;
+        // Optimistic single pass: one tensor-core launch over everything after the first segment,
+        // thresholded at the m-th smallest distance of the first segment (expected survivors per
+        // query m * rows_left / rows_seen <= cap / 4); verified on the device, rerun if refuted.
+        const uint32_t opt_m = (allow_optimistic && use_tc && h->opt_m > 0 && h->opt_m <= R &&
+                                (uint64_t)h->opt_m * (ntiles - seg0_tiles) <= (uint64_t)(cap / 4) * seg0_tiles)
+                                   ? h->opt_m : 0u;
+        if (opt_m && used_optimistic) *used_optimistic = true;
         if (use_tc) tc_prepare_queries(h, ws, st, nqt, nq_pad);
         uint32_t lo = 0;
         while (lo < ntiles) {
-            uint64_t hi64 = lo == 0 ? seg0_tiles : (uint64_t)lo * g;
+            uint64_t hi64 = lo == 0 ? seg0_tiles : (opt_m ? (uint64_t)ntiles : (uint64_t)lo * g);
             uint32_t hi = (uint32_t)std::min<uint64_t>(hi64, ntiles);
             const double seg_rows = (double)(hi - lo) * 32.0;
             if (use_tc && lo > 0) {
@@ -498,7 +507,8 @@ void search_core(gvdb_index* h, Workspace* ws, cudaStream_t st, const float* que
                 Timed t(h, ws, st, K_SELECT);
                 select_hist_kernel<<<nqt, SELH_THREADS, selh_smem, st>>>(
                     ws->buf.as<uint64_t>(), cap, ws->cnt.as<uint32_t>(), R, r_pow2, nbins,
-                    ws->qpack.as<uint32_t>(), h->qs, h->nchunk * 4);
+                    ws->qpack.as<uint32_t>(), h->qs, h->nchunk * 4, lo == 0 ? opt_m : 0u,
+                    (opt_m && lo > 0) ? 1 : 0, ws->flag.as<uint32_t>());
             }
             CU(cudaGetLastError());
             lo = hi;
@@ -533,14 +543,21 @@ void search_core(gvdb_index* h, Workspace* ws, cudaStream_t st, const float* que
     }
 }
 
-void check_overflow(gvdb_index* h, Workspace* ws, cudaStream_t st) {
-    CU(cudaMemcpyAsync(ws->h_flag, ws->flag.p, 4, cudaMemcpyDeviceToHost, st));
+// Final synchronisation of a search call.  Returns true when the call must be run again without
+// the optimistic threshold (the device refuted the guess, or a candidate buffer overflowed under it).
+bool check_overflow(gvdb_index* h, Workspace* ws, cudaStream_t st, bool was_optimistic = false) {
+    CU(cudaMemcpyAsync(ws->h_flag, ws->flag.p, 8, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     flush_profile(h, ws);
+    if (was_optimistic && (ws->h_flag[0] || ws->h_flag[1])) {
+        h->optimistic_reruns.fetch_add(1, std::memory_order_relaxed);
+        return true;
+    }
     if (ws->h_flag[0])
         fail(GVDB_ERR_INDEX,
              "candidate buffer overflow in the Hamming scan (heavily duplicated corpus?); "
              "the exact fallback is not implemented yet");
+    return false;
 }
 
 void launch_topk(gvdb_index* h, Workspace* ws, cudaStream_t st, const uint64_t* rec_ids, const float* rec_score, uint32_t nq,
@@ -658,12 +675,15 @@ void search_device(gvdb_index* h, Workspace* ws, cudaStream_t st, const float* q
     ws->rec_ham.ensure((size_t)nq * R * 4);
     ws->rec_ids.ensure((size_t)nq * R * 8);
     ws->rec_score.ensure((size_t)nq * R * 4);
-    search_core(h, ws, st, q_dev, nq, R, ws->rec_ham.as<uint32_t>(), ws->rec_ids.as<uint64_t>(),
-                ws->rec_score.as<float>());
-    launch_topk(h, ws, st, ws->rec_ids.as<uint64_t>(), ws->rec_score.as<float>(), nq, R, k, ids_out, scores_out);
-    if (cand_ids) CU(cudaMemcpyAsync(cand_ids, ws->rec_ids.p, (size_t)nq * R * 8, cudaMemcpyDeviceToDevice, st));
-    if (cand_ham) CU(cudaMemcpyAsync(cand_ham, ws->rec_ham.p, (size_t)nq * R * 4, cudaMemcpyDeviceToDevice, st));
-    check_overflow(h, ws, st);
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        bool optimistic = false;
+        search_core(h, ws, st, q_dev, nq, R, ws->rec_ham.as<uint32_t>(), ws->rec_ids.as<uint64_t>(),
+                    ws->rec_score.as<float>(), true, attempt == 0, &optimistic);
+        launch_topk(h, ws, st, ws->rec_ids.as<uint64_t>(), ws->rec_score.as<float>(), nq, R, k, ids_out, scores_out);
+        if (cand_ids) CU(cudaMemcpyAsync(cand_ids, ws->rec_ids.p, (size_t)nq * R * 8, cudaMemcpyDeviceToDevice, st));
+        if (cand_ham) CU(cudaMemcpyAsync(cand_ham, ws->rec_ham.p, (size_t)nq * R * 4, cudaMemcpyDeviceToDevice, st));
+        if (!check_overflow(h, ws, st, optimistic)) break;
+    }
 }
 
 // Exact flat search: same segment/select machinery with key = image(1 - cos) << 32 | row.
@@ -802,6 +822,7 @@ gvdb_status gvdb_create(const gvdb_config* cfg, gvdb_index** out) {
         if (const char* s = getenv("GVDB_SCAN_NCSA")) h->scan_variant = atoi(s);
         if (const char* s = getenv("GVDB_TC_MIN_Q")) h->tc_min_q = (uint32_t)std::max(1, atoi(s));
         if (const char* s = getenv("GVDB_SEG0_ROWS")) h->seg0_rows = (uint32_t)std::max(32, atoi(s)) / 32 * 32;
+        if (const char* s = getenv("GVDB_OPT_M")) h->opt_m = (uint32_t)std::max(0, atoi(s));
         if (const char* s = getenv("GVDB_SEG_GROWTH")) h->seg_growth = (uint32_t)std::max(0, atoi(s));
         if (const char* s = getenv("GVDB_SCAN_CTAS_PER_SM")) h->scan_ctas_per_sm = std::max(1, atoi(s));
         if (cfg->capacity_rows) grow(h.get(), cfg->capacity_rows);
@@ -1106,10 +1127,13 @@ gvdb_status gvdb_search_shard_device(gvdb_index* h, void* stream, const float* q
         WsLease lease(h, (cudaStream_t)stream, true);
         const uint64_t nr = (uint64_t)nq * rescore_count;
         uint8_t* base = static_cast<uint8_t*>(records_dev);
-        search_core(h, lease.ws, lease.stream, queries_dev, nq, rescore_count,
-                    reinterpret_cast<uint32_t*>(base + nr * 8), reinterpret_cast<uint64_t*>(base),
-                    reinterpret_cast<float*>(base + nr * 12));
-        check_overflow(h, lease.ws, lease.stream);
+        for (int attempt = 0; attempt < 2; ++attempt) {
+            bool optimistic = false;
+            search_core(h, lease.ws, lease.stream, queries_dev, nq, rescore_count,
+                        reinterpret_cast<uint32_t*>(base + nr * 8), reinterpret_cast<uint64_t*>(base),
+                        reinterpret_cast<float*>(base + nr * 12), true, attempt == 0, &optimistic);
+            if (!check_overflow(h, lease.ws, lease.stream, optimistic)) break;
+        }
     });
 }
 
@@ -1125,13 +1149,16 @@ gvdb_status gvdb_search_shard_sliced_device(gvdb_index* h, void* stream, const f
         WsLease lease(h, (cudaStream_t)stream, true);
         const uint32_t per = nq / n_slices;
         const uint64_t nr = (uint64_t)per * rescore_count;
-        for (uint32_t s = 0; s < n_slices; ++s) {
-            uint8_t* base = static_cast<uint8_t*>(records_dev) + (uint64_t)s * nr * 16;
-            search_core(h, lease.ws, lease.stream, queries_dev + (size_t)s * per * h->dim, per, rescore_count,
-                        reinterpret_cast<uint32_t*>(base + nr * 8), reinterpret_cast<uint64_t*>(base),
-                        reinterpret_cast<float*>(base + nr * 12), s == 0);
+        for (int attempt = 0; attempt < 2; ++attempt) {
+            bool optimistic = false;
+            for (uint32_t s = 0; s < n_slices; ++s) {
+                uint8_t* base = static_cast<uint8_t*>(records_dev) + (uint64_t)s * nr * 16;
+                search_core(h, lease.ws, lease.stream, queries_dev + (size_t)s * per * h->dim, per, rescore_count,
+                            reinterpret_cast<uint32_t*>(base + nr * 8), reinterpret_cast<uint64_t*>(base),
+                            reinterpret_cast<float*>(base + nr * 12), s == 0, attempt == 0, &optimistic);
+            }
+            if (!check_overflow(h, lease.ws, lease.stream, optimistic)) break;
         }
-        check_overflow(h, lease.ws, lease.stream);
     });
 }
 
@@ -1179,10 +1206,12 @@ gvdb_status gvdb_profile_read(gvdb_index* h, gvdb_profile* out, int32_t reset) {
         need(h, "index"); need(out, "out");
         std::lock_guard<std::mutex> lk(h->prof_mu);
         h->prof.launches = h->launches.load();
+        h->prof.optimistic_reruns = h->optimistic_reruns.load();
         *out = h->prof;
         if (reset) {
             h->prof = gvdb_profile{};
             h->launches.store(0);
+            h->optimistic_reruns.store(0);
         }
     });
 }

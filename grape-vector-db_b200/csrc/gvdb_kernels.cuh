@@ -407,9 +407,36 @@ select_kernel(uint64_t* __restrict__ buf, uint32_t cap, uint32_t* __restrict__ c
 // Dynamic shared memory: r_pow2 u64 (kept) + SORT_N u64 (ties) + nbins u32 (histogram).
 constexpr int SELH_THREADS = 256;
 
+// Threshold for the next scan segment after a select that kept `have` sorted keys.
+//   tau[0]  = the R-th smallest distance so far (TAU_ALL while fewer than R rows were seen): only
+//             rows strictly below it can still enter the top R.
+//   opt_m   > 0 (optimistic single pass): tau[0] = min(tau[0], d_(m) + 1) with d_(m) the m-th
+//             smallest distance of the rows seen so far, remembered in tau[1].  If the rows seen so
+//             far are a fair sample, about m * (rows left / rows seen) rows lie below it.  The
+//             guess is checked, not trusted:
+//   verify  after the pass: the top R is exact iff at least R candidates lie strictly below tau[1]
+//             (then every row of the true top R was emitted); otherwise flags[1] asks for a rerun.
+__device__ __forceinline__ void select_set_tau(const uint64_t* sel, uint32_t have, uint32_t R, uint32_t* tau,
+                                               uint32_t opt_m, int verify, uint32_t* flags) {
+    const uint32_t tau_r = (have >= R && R > 0) ? (uint32_t)(sel[R - 1] >> 32) : TAU_ALL;
+    if (verify) {
+        if (!(have >= R && tau_r < tau[1])) flags[1] = 1u;
+        tau[0] = tau_r;
+        return;
+    }
+    uint32_t t = tau_r;
+    if (opt_m > 0 && have >= opt_m) {
+        const uint32_t tau_opt = (uint32_t)(sel[opt_m - 1] >> 32) + 1u;
+        tau[1] = tau_opt;
+        t = min(t, tau_opt);
+    }
+    tau[0] = t;
+}
+
 __global__ void __launch_bounds__(SELH_THREADS)
 select_hist_kernel(uint64_t* __restrict__ buf, uint32_t cap, uint32_t* __restrict__ cnt, uint32_t R,
-                   uint32_t r_pow2, uint32_t nbins, uint32_t* __restrict__ qpack, int qs, int tau_word) {
+                   uint32_t r_pow2, uint32_t nbins, uint32_t* __restrict__ qpack, int qs, int tau_word,
+                   uint32_t opt_m, int verify, uint32_t* __restrict__ flags) {
     extern __shared__ __align__(16) uint64_t sel[];
     uint64_t* tie = sel + r_pow2;
     uint32_t* hist = reinterpret_cast<uint32_t*>(tie + SORT_N);
@@ -426,7 +453,7 @@ select_hist_kernel(uint64_t* __restrict__ buf, uint32_t cap, uint32_t* __restric
         for (uint32_t i = tid; i < n; i += SELH_THREADS) mine[i] = sel[i];
         if (tid == 0) {
             cnt[(size_t)q * CNT_STRIDE] = n;
-            qpack[(size_t)q * qs + tau_word] = (n >= R && R > 0) ? (uint32_t)(sel[R - 1] >> 32) : TAU_ALL;
+            select_set_tau(sel, n, R, qpack + (size_t)q * qs + tau_word, opt_m, verify, flags);
         }
         return;
     }
@@ -514,7 +541,7 @@ select_hist_kernel(uint64_t* __restrict__ buf, uint32_t cap, uint32_t* __restric
     for (uint32_t i = tid; i < R; i += SELH_THREADS) mine[i] = sel[i];
     if (tid == 0) {
         cnt[(size_t)q * CNT_STRIDE] = R;
-        qpack[(size_t)q * qs + tau_word] = (uint32_t)(sel[R - 1] >> 32);
+        select_set_tau(sel, R, R, qpack + (size_t)q * qs + tau_word, opt_m, verify, flags);
     }
 }
 
