@@ -60,6 +60,8 @@ extern "C" {
     pub fn gvdb_shard_record_bytes(nq: u32, rescore_count: u32) -> u64;
     pub fn gvdb_search_shard_device(h: *mut gvdb_index, stream: *mut c_void, queries_dev: *const f32, nq: u32,
                                     rescore_count: u32, records_dev: *mut c_void) -> i32;
+    pub fn gvdb_search_shard_sliced_device(h: *mut gvdb_index, stream: *mut c_void, queries_dev: *const f32, nq: u32,
+                                           rescore_count: u32, n_slices: u32, records_dev: *mut c_void) -> i32;
     pub fn gvdb_merge_shards_device(h: *mut gvdb_index, stream: *mut c_void, n_shards: u32, records_dev: *const c_void,
                                     nq: u32, rescore_count: u32, k: u32, ids_out_dev: *mut u64, scores_out_dev: *mut f32) -> i32;
 }
