@@ -56,6 +56,8 @@ SYMBOLS = {
     "gvdb_clear": (_i32, [_vp]),
     "gvdb_len": (_u64, [_vp]),
     "gvdb_get_stats": (_i32, [_vp, C.POINTER(GvdbStats)]),
+    "gvdb_save": (_i32, [_vp, C.c_char_p]),
+    "gvdb_load": (_i32, [C.c_char_p, _i32, C.POINTER(_vp)]),
     "gvdb_quantize": (_i32, [_vp, _vp, _u64, _vp]),
     "gvdb_get_codes": (_i32, [_vp, _u64, _u64, _vp]),
     "gvdb_hamming": (_i32, [_vp, _vp, _u32, _vp]),

@@ -927,6 +927,135 @@ gvdb_status gvdb_get_stats(const gvdb_index* h, gvdb_stats* out) {
     });
 }
 
+// ---- persistence ------------------------------------------------------------------------------------
+namespace {
+struct FileHeader {
+    char magic[8];
+    uint32_t version, dim;
+    float threshold, rescore_ratio;
+    uint64_t rows, live_rows, row_base;
+    uint32_t code_bytes, pad0;
+    uint8_t pad[8];
+};
+static_assert(sizeof(FileHeader) == 64, "header is 64 bytes");
+uint64_t pad64(uint64_t n) { return (n + 63) / 64 * 64; }
+
+struct File {
+    FILE* f = nullptr;
+    File(const char* path, const char* mode) : f(fopen(path, mode)) {}
+    ~File() { if (f) fclose(f); }
+};
+
+// device <-> file through a pinned staging buffer
+void dev_to_file(FILE* f, const void* dev, uint64_t bytes, uint64_t padded, void* stage, size_t stage_bytes) {
+    for (uint64_t off = 0; off < bytes; off += stage_bytes) {
+        const size_t m = (size_t)std::min<uint64_t>(stage_bytes, bytes - off);
+        CU(cudaMemcpy(stage, static_cast<const uint8_t*>(dev) + off, m, cudaMemcpyDeviceToHost));
+        if (fwrite(stage, 1, m, f) != m) fail(GVDB_ERR_INDEX, "gvdb_save: short write");
+    }
+    static const uint8_t zeros[64] = {0};
+    if (padded > bytes && fwrite(zeros, 1, (size_t)(padded - bytes), f) != padded - bytes)
+        fail(GVDB_ERR_INDEX, "gvdb_save: short write");
+}
+void file_to_dev(FILE* f, void* dev, uint64_t bytes, uint64_t padded, void* stage, size_t stage_bytes) {
+    for (uint64_t off = 0; off < bytes; off += stage_bytes) {
+        const size_t m = (size_t)std::min<uint64_t>(stage_bytes, bytes - off);
+        if (fread(stage, 1, m, f) != m) fail(GVDB_ERR_INDEX, "gvdb_load: truncated file");
+        CU(cudaMemcpy(static_cast<uint8_t*>(dev) + off, stage, m, cudaMemcpyHostToDevice));
+    }
+    if (padded > bytes && fseek(f, (long)(padded - bytes), SEEK_CUR) != 0) fail(GVDB_ERR_INDEX, "gvdb_load: truncated file");
+}
+}  // namespace
+
+gvdb_status gvdb_save(gvdb_index* h, const char* path) {
+    return guarded([&] {
+        need(h, "index"); need(path, "path");
+        DeviceGuard dg(h->cfg.device);
+        CU(cudaDeviceSynchronize());
+        File file(path, "wb");
+        if (!file.f) fail(GVDB_ERR_INDEX, std::string("gvdb_save: cannot open ") + path);
+        FileHeader hd{};
+        memcpy(hd.magic, "GVDBIDX1", 8);
+        hd.version = 1; hd.dim = (uint32_t)h->dim;
+        hd.threshold = h->cfg.threshold; hd.rescore_ratio = h->cfg.rescore_ratio;
+        hd.rows = h->n_rows; hd.live_rows = h->n_live; hd.row_base = h->cfg.row_base;
+        hd.code_bytes = (uint32_t)h->nbytes;
+        if (fwrite(&hd, sizeof(hd), 1, file.f) != 1) fail(GVDB_ERR_INDEX, "gvdb_save: short write");
+        const size_t stage_bytes = 32u << 20;
+        void* stage = nullptr;
+        CU(cudaMallocHost(&stage, stage_bytes));
+        struct Free { void* p; ~Free() { cudaFreeHost(p); } } guard{stage};
+        const uint64_t N = h->n_rows;
+        {   // codes: blocked -> reference byte layout, in chunks
+            const uint64_t chunk = stage_bytes / (uint64_t)h->nbytes;
+            DevBuf tmp; tmp.ensure(std::max<uint64_t>(1, std::min(chunk, N)) * h->nbytes);
+            uint64_t written = 0;
+            for (uint64_t i0 = 0; i0 < N; i0 += chunk) {
+                const uint64_t m = std::min(chunk, N - i0);
+                unblock_codes_kernel<<<(unsigned)((m + 255) / 256), 256>>>(h->codes, h->nchunk, i0, m, h->nbytes, tmp.as<uint8_t>());
+                CU(cudaGetLastError());
+                dev_to_file(file.f, tmp.p, m * h->nbytes, m * h->nbytes, stage, stage_bytes);
+                written += m * h->nbytes;
+            }
+            tmp.release();
+            static const uint8_t zeros[64] = {0};
+            const uint64_t padn = pad64(written) - written;
+            if (padn && fwrite(zeros, 1, (size_t)padn, file.f) != padn) fail(GVDB_ERR_INDEX, "gvdb_save: short write");
+        }
+        dev_to_file(file.f, h->norms, N * 4, pad64(N * 4), stage, stage_bytes);
+        dev_to_file(file.f, h->live, tiles_for(N) * 4, pad64(tiles_for(N) * 4), stage, stage_bytes);
+        dev_to_file(file.f, h->rows, N * (uint64_t)h->dim * 4, N * (uint64_t)h->dim * 4, stage, stage_bytes);
+        if (fflush(file.f) != 0) fail(GVDB_ERR_INDEX, "gvdb_save: flush failed");
+    });
+}
+
+gvdb_status gvdb_load(const char* path, int32_t device, gvdb_index** out) {
+    return guarded([&] {
+        need(path, "path"); need(out, "out");
+        *out = nullptr;
+        File file(path, "rb");
+        if (!file.f) fail(GVDB_ERR_INDEX, std::string("gvdb_load: cannot open ") + path);
+        FileHeader hd{};
+        if (fread(&hd, sizeof(hd), 1, file.f) != 1 || memcmp(hd.magic, "GVDBIDX1", 8) != 0 || hd.version != 1)
+            fail(GVDB_ERR_INDEX, "gvdb_load: not a gvdb index file");
+        if (hd.code_bytes != (hd.dim + 7) / 8) fail(GVDB_ERR_INDEX, "gvdb_load: inconsistent header");
+        gvdb_config cfg{};
+        cfg.struct_size = sizeof(cfg); cfg.dim = hd.dim; cfg.threshold = hd.threshold;
+        cfg.rescore_ratio = hd.rescore_ratio; cfg.device = device; cfg.capacity_rows = hd.rows; cfg.row_base = hd.row_base;
+        gvdb_index* h = nullptr;
+        if (gvdb_create(&cfg, &h) != GVDB_OK) fail(GVDB_ERR_INDEX, std::string("gvdb_load: ") + g_err);
+        std::unique_ptr<gvdb_index, void (*)(gvdb_index*)> owner(h, gvdb_destroy);
+        DeviceGuard dg(device);
+        const uint64_t N = hd.rows;
+        const size_t stage_bytes = 32u << 20;
+        void* stage = nullptr;
+        CU(cudaMallocHost(&stage, stage_bytes));
+        struct Free { void* p; ~Free() { cudaFreeHost(p); } } guard{stage};
+        if (N) {
+            const uint64_t chunk = stage_bytes / (uint64_t)h->nbytes;
+            DevBuf tmp; tmp.ensure(std::min(chunk, N) * h->nbytes);
+            uint64_t readn = 0;
+            for (uint64_t i0 = 0; i0 < N; i0 += chunk) {
+                const uint64_t m = std::min(chunk, N - i0);
+                file_to_dev(file.f, tmp.p, m * h->nbytes, m * h->nbytes, stage, stage_bytes);
+                block_codes_kernel<<<(unsigned)((m + 255) / 256), 256>>>(tmp.as<uint8_t>(), h->nchunk, i0, m, h->nbytes, h->codes);
+                CU(cudaGetLastError());
+                CU(cudaDeviceSynchronize());
+                readn += m * h->nbytes;
+            }
+            tmp.release();
+            if (pad64(readn) > readn && fseek(file.f, (long)(pad64(readn) - readn), SEEK_CUR) != 0)
+                fail(GVDB_ERR_INDEX, "gvdb_load: truncated file");
+            file_to_dev(file.f, h->norms, N * 4, pad64(N * 4), stage, stage_bytes);
+            file_to_dev(file.f, h->live, tiles_for(N) * 4, pad64(tiles_for(N) * 4), stage, stage_bytes);
+            file_to_dev(file.f, h->rows, N * (uint64_t)h->dim * 4, N * (uint64_t)h->dim * 4, stage, stage_bytes);
+        }
+        h->n_rows = N;
+        h->n_live = hd.live_rows;
+        *out = owner.release();
+    });
+}
+
 uint64_t gvdb_rescore_count(uint64_t n, float ratio) {
     // (candidates.len() as f32 * rescore_ratio) as usize, then .min(len)  — quantization.rs:178-179
     float p = (float)n * ratio;

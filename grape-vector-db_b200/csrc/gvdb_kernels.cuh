@@ -204,6 +204,22 @@ __global__ void unblock_codes_kernel(const uint4* __restrict__ codes, int nchunk
     }
 }
 
+// reference byte layout (nbytes per row, rows [first, first+n)) -> blocked codes (gvdb_load)
+__global__ void block_codes_kernel(const uint8_t* __restrict__ in, int nchunk, uint64_t first, uint64_t n,
+                                   int nbytes, uint4* __restrict__ codes) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint64_t g = first + i;
+    for (int c = 0; c < nchunk; ++c) {
+        uint32_t w[4] = {0u, 0u, 0u, 0u};
+        for (int b = 0; b < 16; ++b) {
+            int byte = c * 16 + b;
+            if (byte < nbytes) w[b >> 2] |= (uint32_t)in[i * (uint64_t)nbytes + byte] << (8 * (b & 3));
+        }
+        codes[((g >> 5) * (uint64_t)nchunk + c) * 32 + (g & 31)] = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+}
+
 // ---------------------------------------------------------------------------------------
 // Hamming distance of W xor-ed words with NCSA carry-save adders in front of the popcounts.
 // B200 issues 16 popc/clk/SM (XU pipe) but 64 LOP3/clk/SM (ALU pipe); the plain loop is

@@ -49,6 +49,30 @@ class GpuIndex:
         self.row_base = row_base
         self.nbytes = (dim + 7) // 8
 
+    # -- persistence ---------------------------------------------------------------------
+    def save(self, path: str):
+        """Write the shard (codes, norms, tombstones, f32 rows) to one flat file (gvdb_save)."""
+        self._ok(self._lib.gvdb_save(self._h, str(path).encode()))
+
+    @classmethod
+    def load(cls, path: str, device: int = 0) -> "GpuIndex":
+        """Restore a shard written by save() without re-quantising (gvdb_load)."""
+        lib = _ffi.lib()
+        h = C.c_void_p()
+        raise_for_status(lib.gvdb_load(str(path).encode(), device, C.byref(h)), lib)
+        self = cls.__new__(cls)
+        self._lib = lib
+        self._h = h
+        s = _ffi.GvdbStats()
+        raise_for_status(lib.gvdb_get_stats(h, C.byref(s)), lib)
+        self.dim = int(s.dimension)
+        self.device = device
+        self.nbytes = (self.dim + 7) // 8
+        self.threshold = None      # stored in the file; not needed on the Python side
+        self.rescore_ratio = 0.1
+        self.row_base = None
+        return self
+
     # -- lifecycle ---------------------------------------------------------------------
     def close(self):
         if getattr(self, "_h", None):

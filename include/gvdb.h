@@ -101,6 +101,22 @@ GVDB_API gvdb_status gvdb_clear(gvdb_index* h);
 GVDB_API uint64_t gvdb_len(const gvdb_index* h);
 GVDB_API gvdb_status gvdb_get_stats(const gvdb_index* h, gvdb_stats* out);
 
+/* ---- persistence ------------------------------------------------ */
+/* One flat little-endian file per shard, readable with mmap:
+ *   [  0, 64)  header: "GVDBIDX1", u32 version = 1, u32 dim, f32 threshold, f32 rescore_ratio,
+ *              u64 rows, u64 live rows, u64 row_base, u32 code bytes per row = ceil(dim/8), zero pad
+ *   codes      rows x ceil(dim/8) bytes, BinaryVector::to_bytes() layout (src/quantization.rs:54-56),
+ *              padded to a multiple of 64 bytes
+ *   norms      rows x f32 (sequential-fold L2 norms), padded to 64
+ *   live       ceil(rows/32) x u32 bitmap (bit r of word t = row 32t + r; 0 = tombstone), padded to 64
+ *   rows       rows x dim f32, row-major
+ * The reference reserves a `quantized` sled tree but never writes it and re-inserts vectors one
+ * at a time on restart (src/advanced_storage.rs:52-62,105-112; src/query.rs:282-409); loading
+ * this file restores the shard without re-quantising. */
+GVDB_API gvdb_status gvdb_save(gvdb_index* h, const char* path);
+/* Creates a new index on `device` from a file written by gvdb_save. */
+GVDB_API gvdb_status gvdb_load(const char* path, int32_t device, gvdb_index** out);
+
 /* ---- quantizer pieces (parity / BinaryVector interop) ----------------------------- */
 /* BinaryQuantizer::quantize_batch (src/quantization.rs:86-127) on the GPU: n x dim f32
  * (host) -> n x ceil(dim/8) bytes (host) in BinaryVector::to_bytes() layout
