@@ -54,6 +54,12 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=128, help="queries timed on the CPU baseline")
     ap.add_argument("--recall-queries", type=int, default=64)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--layout", default="peer-rows", choices=["peer-rows", "replicated-codes", "row-sharded"],
+                    help="N > 1.  'peer-rows' / 'replicated-codes': every GPU holds all 1-bit codes and 1/N of the "
+                         "f32 rows and searches its own query batch; candidate rows are read from their owner's HBM "
+                         "over NVLink inside the rescoring kernel (peer-rows, CUDA IPC) or scored by the owner and "
+                         "exchanged with NCCL collectives (replicated-codes).  'row-sharded': codes and rows sharded "
+                         "by row, queries replicated, per-shard top-R merged after one all-to-all")
     return ap.parse_args()
 
 
@@ -154,15 +160,23 @@ def workload_config(args, world):
                         f"batch {args.batch} per GPU, top-{args.k}, oversample {args.oversample}x (R={args.k * args.oversample})",
             "rows": args.rows, "dim": args.dim, "batch": args.batch, "global_batch": B, "k": args.k,
             "rescore_count": args.k * args.oversample, "dataset": "lowrank L=16 integer-exact, seed 42",
-            "parallelism": (f"corpus row-sharded x{world} ({args.rows // world} rows per GPU), global batch {B} "
-                            f"replicated; per-GPU scan work (rows/GPU x queries) is fixed as N grows; one NCCL "
-                            f"all-to-all of the per-shard top-R records, query-sliced merge, all-gather of the top-k")
-                           if world > 1 else "single shard",
+            "parallelism": "single shard" if world == 1 else (
+                (f"1-bit codes replicated ({args.rows * args.dim // 8 >> 20} MiB per GPU), f32 rows row-sharded x{world} "
+                 f"({args.rows // world} rows per GPU); every GPU searches its own batch of {args.batch} queries "
+                 f"(global batch {B}); the rescoring kernel reads candidate rows from their owner's HBM over "
+                 f"NVLink (CUDA IPC peer mapping), no collective in the data path") if args.layout == "peer-rows" else
+                (f"1-bit codes replicated ({args.rows * args.dim // 8 >> 20} MiB per GPU), f32 rows row-sharded x{world} "
+                 f"({args.rows // world} rows per GPU); every GPU searches its own batch of {args.batch} queries "
+                 f"(global batch {B}): NCCL all-gather of queries and candidate keys, owner-computes rescoring, "
+                 f"all-to-all of the scores") if args.layout == "replicated-codes" else
+                (f"corpus row-sharded x{world} ({args.rows // world} rows per GPU), global batch {B} "
+                 f"replicated; per-GPU scan work (rows/GPU x queries) is fixed as N grows; one NCCL "
+                 f"all-to-all of the per-shard top-R records, query-sliced merge, all-gather of the top-k")),
             "l2": "256 MB L2 flush between timed steps"}
 
 
-def build_index(gv, synth, torch, dev, lo, hi, dim, chunk=131072):
-    idx = gv.GpuIndex(dim, device=dev.index, capacity_rows=hi - lo, row_base=lo)
+def build_index(gv, synth, torch, dev, lo, hi, dim, chunk=131072, row_window=None):
+    idx = gv.GpuIndex(dim, device=dev.index, capacity_rows=hi - lo, row_base=lo, row_window=row_window)
     for i in range(lo, hi, chunk):
         m = min(chunk, hi - i)
         idx.add_device(synth.lowrank_rows_torch(i, m, dim, dev))
@@ -182,16 +196,29 @@ def run_ours(args, rank, world, local_rank):
     K, W = args.steps, args.warmup
     hbm_peak, peak_src, sm_max, bf16_peak = peaks()
 
+    replicated = world > 1 and args.layout in ("replicated-codes", "peer-rows")
+    peer = world > 1 and args.layout == "peer-rows"
     lo, hi = gdist.shard_bounds(n, world, rank)
-    index = build_index(gv, synth, torch, dev, lo, hi, dim)
-    searcher = gdist.ShardedSearcher(index)
     NB = 4
-    q_dev = [synth.lowrank_queries_torch(b * B, B, dim, dev) for b in range(NB)]
-    q_pin = [torch.empty((B, dim), dtype=torch.float32).pin_memory() for _ in range(NB)]
+    if replicated:
+        # all codes on every GPU, f32 rows of this rank's shard only; this rank's OWN query batches
+        index = build_index(gv, synth, torch, dev, 0, n, dim, row_window=(lo, hi - lo))
+        if peer:
+            searcher = gdist.PeerRowsSearcher(index, n)  # CUDA IPC: maps the other ranks' row buffers
+        else:
+            searcher = gdist.QueryParallelSearcher(index, n)
+        Bq = args.batch                                  # queries this rank submits per step
+        q_dev = [synth.lowrank_queries_torch((b * world + rank) * Bq, Bq, dim, dev) for b in range(NB)]
+    else:
+        index = build_index(gv, synth, torch, dev, lo, hi, dim)
+        searcher = gdist.ShardedSearcher(index)
+        Bq = B                                           # the replicated global batch
+        q_dev = [synth.lowrank_queries_torch(b * B, B, dim, dev) for b in range(NB)]
+    q_pin = [torch.empty((Bq, dim), dtype=torch.float32).pin_memory() for _ in range(NB)]
     for a, b in zip(q_pin, q_dev):
         a.copy_(b)
-    ids_out = torch.empty((B, k), dtype=torch.int64, device=dev)
-    sc_out = torch.empty((B, k), dtype=torch.float32, device=dev)
+    ids_out = torch.empty((Bq, k), dtype=torch.int64, device=dev)
+    sc_out = torch.empty((Bq, k), dtype=torch.float32, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
     def barrier():
@@ -245,6 +272,10 @@ def run_ours(args, rank, world, local_rank):
     def e2e_step(b):
         if world == 1:
             return index.search_batch(q_pin[b].numpy(), k, R)          # gvdb_search_batch: H2D + D2H inside
+        if replicated:     # this rank's own batch in, its own answers out
+            qd = q_pin[b].to(dev, non_blocking=True)
+            i_, s_ = searcher.search_batch_device(qd, k, R, ids_out, sc_out)
+            return i_.cpu(), s_.cpu()
         # each rank receives 1/N of the batch from its host (pinned H2D), the ranks all-gather the
         # queries over NVLink, search, and each rank reads back ITS slice of the answers
         per = B // world
@@ -264,9 +295,14 @@ def run_ours(args, rank, world, local_rank):
     e2e = {"value": B * K / e2e_s, "unit": UNIT, "h2d_bytes_per_step": B * dim * 4,
            "d2h_bytes_per_step": B * k * 12, "ms_per_step": 1e3 * e2e_s / K,
            "api": "gvdb_search_batch (host pointers, pinned)" if world == 1 else
-                  "per rank: pinned H2D of its 1/N of the queries + NCCL all-gather of the queries + "
-                  "gvdb_search_shard_sliced_device + NCCL all-to-all + gvdb_merge_shards_device + "
-                  "all-gather of the top-k + D2H of its slice (bytes are whole-job totals)"}
+                  ("per rank: pinned H2D of its own batch + gvdb_search_batch_device (candidate rows read from "
+                   "peer HBM over NVLink) + D2H of its answers (bytes are whole-job totals)") if peer else
+                  ("per rank: pinned H2D of its own batch + all-gather(queries) + gvdb_stage1_device + "
+                   "all-gather(keys) + gvdb_rescore_keys_device + all-to-all(scores) + gvdb_finish_owned_device "
+                   "+ D2H of its answers (bytes are whole-job totals)") if replicated else
+                  ("per rank: pinned H2D of its 1/N of the queries + NCCL all-gather of the queries + "
+                   "gvdb_search_shard_sliced_device + NCCL all-to-all + gvdb_merge_shards_device + "
+                   "all-gather of the top-k + D2H of its slice (bytes are whole-job totals)")}
 
     # ---- roofline of the dominant kernel inside the timed steps ---------------------------------
     # Batches of >= 64 queries run the tcgen05 scan (tc_scan_kernel): a dense int8 contraction,
@@ -343,6 +379,22 @@ def run_ours(args, rank, world, local_rank):
             oracle.multi_stage_search_batch(qs, rows, R, k, codes=codes, nthreads=threads, select=True)
             extra["cpu_baseline_select_variant_qps"] = ns / (time.perf_counter() - t0)
             del rows, codes
+
+    if world > 1 and rank == 0 and not args.no_cpu:
+        # multi-GPU answers checked against the single-index oracle on a few queries of rank 0's
+        # last batch (replicated-codes: rank 0's own batch; row-sharded: the head of the global batch)
+        from oracle import oracle
+        rows = np.concatenate([synth.lowrank_rows_torch(i, min(131072, n - i), dim, dev).cpu().numpy()
+                               for i in range(0, n, 131072)])
+        ns = min(32, Bq)
+        qs = q_pin[last_batch].numpy()[:ns]
+        oi, os_ = oracle.multi_stage_search_batch(qs, rows, R, k, nthreads=oracle.hardware_threads(), select=True)
+        extra["parity"] = {
+            "checked_queries": ns,
+            "topk_ids_bit_exact": bool(np.array_equal(oi, last_ids[:ns])),
+            "scores_bit_exact": bool(np.array_equal(os_.view(np.uint32), last_sc[:ns].view(np.uint32))),
+        }
+        del rows
 
     # ---- the same kernel at its HBM-bound operating point -------------------------------------------
     roofline_stream = None

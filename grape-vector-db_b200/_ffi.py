@@ -24,7 +24,11 @@ GVDB_NO_ID = 0xFFFFFFFFFFFFFFFF
 class GvdbConfig(C.Structure):
     _fields_ = [("struct_size", C.c_uint32), ("dim", C.c_uint32), ("threshold", C.c_float),
                 ("rescore_ratio", C.c_float), ("device", C.c_int32), ("flags", C.c_uint32),
-                ("capacity_rows", C.c_uint64), ("row_base", C.c_uint64)]
+                ("capacity_rows", C.c_uint64), ("row_base", C.c_uint64),
+                ("window_first", C.c_uint64), ("window_count", C.c_uint64)]
+
+
+GVDB_FLAG_ROW_WINDOW = 1
 
 
 class GvdbStats(C.Structure):
@@ -70,6 +74,13 @@ SYMBOLS = {
     "gvdb_search_shard_device": (_i32, [_vp, _vp, _vp, _u32, _u32, _vp]),
     "gvdb_search_shard_sliced_device": (_i32, [_vp, _vp, _vp, _u32, _u32, _u32, _vp]),
     "gvdb_merge_shards_device": (_i32, [_vp, _vp, _u32, _vp, _u32, _u32, _u32, _vp, _vp]),
+    "gvdb_stage1_device": (_i32, [_vp, _vp, _vp, _u32, _u32, _vp]),
+    "gvdb_rescore_keys_device": (_i32, [_vp, _vp, _vp, _u32, _u32, _vp, _vp]),
+    "gvdb_finish_owned_device": (_i32, [_vp, _vp, _vp, _vp, _u32, _u64, _u32, _u32, _u32, _vp, _vp]),
+    "gvdb_export_rows_ipc": (_i32, [_vp, _vp]),
+    "gvdb_attach_peer_rows_ipc": (_i32, [_vp, _u32, _u64, _u32, _vp]),
+    "gvdb_rows_device_ptr": (_vp, [_vp]),
+    "gvdb_attach_peer_rows_ptr": (_i32, [_vp, _u32, _u64, _u32, _vp]),
     "gvdb_profile_enable": (_i32, [_vp, _i32]),
     "gvdb_profile_read": (_i32, [_vp, _vp, _i32]),
 }
@@ -89,7 +100,7 @@ def lib() -> C.CDLL:
             fn = getattr(L, name)  # AttributeError if the library does not export it
             fn.restype = res
             fn.argtypes = args
-        if L.gvdb_abi_version() != 2:
+        if L.gvdb_abi_version() != 3:
             raise RuntimeError("libgvdb.so ABI version mismatch")
         _lib = L
     return _lib

@@ -114,6 +114,17 @@ struct gvdb_index {
     uint4* codes = nullptr;
     float* norms = nullptr;
     uint32_t* live = nullptr;
+    bool windowed = false;           // GVDB_FLAG_ROW_WINDOW: f32 rows kept for [win_first, win_first + win_count) only
+    uint64_t win_first = 0, win_count = 0;
+    // rows[(r - win_first) * dim] is local row r's data; kernels index with the local row number
+    const float* rows_base() const { return windowed ? rows - win_first * (size_t)dim : rows; }
+    bool rows_cover_all() const { return !windowed || (win_first == 0 && win_count >= n_rows); }
+    // peer rows (gvdb_attach_peer_rows_*): owner o's buffer holds rows [o * peer_per, (o+1) * peer_per)
+    const float** peer_rows_dev = nullptr;   // device array of n_peers base pointers (own buffer included)
+    uint32_t n_peers = 0;
+    uint64_t peer_per = 0;
+    std::vector<void*> ipc_opened;
+    bool rows_reachable() const { return rows_cover_all() || (peer_rows_dev && (uint64_t)n_peers * peer_per >= n_rows); }
     int sm_count = 148;
     std::mutex pool_mu;
     std::vector<std::unique_ptr<Workspace>> pool;
@@ -224,7 +235,7 @@ void grow(gvdb_index* h, uint64_t need_rows) {
     new_cap = (new_cap + 31) / 32 * 32;
     float* rows = nullptr; uint4* codes = nullptr; float* norms = nullptr; uint32_t* live = nullptr;
     size_t code_bytes = tiles_for(new_cap) * h->nchunk * 32 * sizeof(uint4);
-    CU(cudaMalloc(&rows, new_cap * (size_t)h->dim * sizeof(float)));
+    if (!h->windowed) CU(cudaMalloc(&rows, new_cap * (size_t)h->dim * sizeof(float)));
     CU(cudaMalloc(&codes, code_bytes));
     CU(cudaMalloc(&norms, new_cap * sizeof(float)));
     CU(cudaMalloc(&live, tiles_for(new_cap) * sizeof(uint32_t)));
@@ -232,17 +243,25 @@ void grow(gvdb_index* h, uint64_t need_rows) {
     CU(cudaMemset(norms, 0, new_cap * sizeof(float)));
     CU(cudaMemset(live, 0, tiles_for(new_cap) * sizeof(uint32_t)));
     if (h->n_rows) {
-        CU(cudaMemcpy(rows, h->rows, h->n_rows * (size_t)h->dim * sizeof(float), cudaMemcpyDeviceToDevice));
+        if (!h->windowed) CU(cudaMemcpy(rows, h->rows, h->n_rows * (size_t)h->dim * sizeof(float), cudaMemcpyDeviceToDevice));
         CU(cudaMemcpy(codes, h->codes, tiles_for(h->n_rows) * h->nchunk * 32 * sizeof(uint4), cudaMemcpyDeviceToDevice));
         CU(cudaMemcpy(norms, h->norms, h->n_rows * sizeof(float), cudaMemcpyDeviceToDevice));
         CU(cudaMemcpy(live, h->live, tiles_for(h->n_rows) * sizeof(uint32_t), cudaMemcpyDeviceToDevice));
     }
     CU(cudaDeviceSynchronize());
-    if (h->rows) cudaFree(h->rows);
+    if (h->rows && !h->windowed) cudaFree(h->rows);
     if (h->codes) cudaFree(h->codes);
     if (h->norms) cudaFree(h->norms);
     if (h->live) cudaFree(h->live);
-    h->rows = rows; h->codes = codes; h->norms = norms; h->live = live; h->cap_rows = new_cap;
+    if (!h->windowed) h->rows = rows;
+    h->codes = codes; h->norms = norms; h->live = live; h->cap_rows = new_cap;
+}
+
+void need_all_rows(const gvdb_index* h) {
+    if (!h->rows_cover_all())
+        fail(GVDB_ERR_INVALID_ARGUMENT,
+             "this entry point needs the f32 data of every row, but the index keeps a row window "
+             "(GVDB_FLAG_ROW_WINDOW): use gvdb_stage1_device / gvdb_rescore_keys_device / gvdb_finish_owned_device");
 }
 
 // ---- kernel dispatch on NCHUNK (and, for tuning, on the carry-save adder count) ------------
@@ -428,7 +447,9 @@ constexpr uint32_t kMaxR = SORT_N / 2;
 // Stage 1 + stage 2 for queries [0,nq) (device pointers): fills rec_* [nq][R].
 void search_core(gvdb_index* h, Workspace* ws, cudaStream_t st, const float* queries_dev,
                  uint32_t nq, uint32_t R, uint32_t* rec_ham, uint64_t* rec_ids, float* rec_score,
-                 bool reset_overflow_flag = true, bool allow_optimistic = true, bool* used_optimistic = nullptr) {
+                 bool reset_overflow_flag = true, bool allow_optimistic = true, bool* used_optimistic = nullptr,
+                 uint64_t* keys_out = nullptr /* stage 1 only: hamming << 40 | global row, nq x R */) {
+    if (!keys_out && !h->rows_reachable()) need_all_rows(h);
     if (h->n_rows == 0) fail(GVDB_ERR_INDEX_NOT_BUILT, "index not built: search before any add");
     if (R == 0) fail(GVDB_ERR_INVALID_ARGUMENT, "rescore_count must be >= 1");
     if (R > kMaxR)
@@ -514,7 +535,11 @@ void search_core(gvdb_index* h, Workspace* ws, cudaStream_t st, const float* que
             lo = hi;
         }
         const uint64_t pairs = (uint64_t)nqt * R;
-        {
+        if (keys_out) {
+            Timed t(h, ws, st, K_RESCORE);
+            emit_keys_kernel<<<(unsigned)((pairs + 255) / 256), 256, 0, st>>>(
+                ws->buf.as<uint64_t>(), cap, ws->cnt.as<uint32_t>(), R, nqt, h->cfg.row_base, keys_out + (size_t)qt0 * R);
+        } else {
             Timed t(h, ws, st, K_RESCORE);
             if ((h->dim & 3) == 0) {
                 const int cols = std::min(h->dim, RS_SLAB);
@@ -524,14 +549,15 @@ void search_core(gvdb_index* h, Workspace* ws, cudaStream_t st, const float* que
                 const size_t smem = (size_t)(32 + q_slots) * stride * sizeof(float);
                 static bool attr = false;   // benign race: idempotent
                 if (!attr) {
-                    CU(cudaFuncSetAttribute(rescore_slab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                    CU(cudaFuncSetAttribute(rescore_slab_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             64 * (RS_SLAB + 4) * (int)sizeof(float)));
                     attr = true;
                 }
-                rescore_slab_kernel<<<(unsigned)((pairs + 31) / 32), 32, smem, st>>>(
+                rescore_slab_kernel<false><<<(unsigned)((pairs + 31) / 32), 32, smem, st>>>(
                     h->rows, h->norms, h->cfg.row_base, h->dim, stride, q_slots, queries_dev + (size_t)qt0 * h->dim,
                     ws->qnorm.as<float>(), ws->buf.as<uint64_t>(), cap, ws->cnt.as<uint32_t>(), R, nqt,
-                    rec_ham + (size_t)qt0 * R, rec_ids + (size_t)qt0 * R, rec_score + (size_t)qt0 * R);
+                    rec_ham + (size_t)qt0 * R, rec_ids + (size_t)qt0 * R, rec_score + (size_t)qt0 * R, 0, 0,
+                    h->rows_cover_all() ? nullptr : h->peer_rows_dev, h->peer_per);
             }
             else
                 rescore_kernel<<<(unsigned)((pairs + STAGE_ROWS - 1) / STAGE_ROWS), STAGE_ROWS, 0, st>>>(
@@ -540,6 +566,15 @@ void search_core(gvdb_index* h, Workspace* ws, cudaStream_t st, const float* que
                     rec_ham + (size_t)qt0 * R, rec_ids + (size_t)qt0 * R, rec_score + (size_t)qt0 * R);
         }
         CU(cudaGetLastError());
+    }
+}
+
+// End of a call that has nothing to read back: synchronise only when per-launch timing is on
+// (the work is ordered on the caller's stream; the stream-ordered contract of the *_device calls).
+void finish_async(gvdb_index* h, Workspace* ws, cudaStream_t st) {
+    if (h->profile_on.load(std::memory_order_relaxed) != 0 || !ws->recs.empty()) {
+        CU(cudaStreamSynchronize(st));
+        flush_profile(h, ws);
     }
 }
 
@@ -576,6 +611,7 @@ void launch_topk(gvdb_index* h, Workspace* ws, cudaStream_t st, const uint64_t* 
 // (distances are produced for chunks of queries).  Same outputs and ordering as search_device.
 void search_big_r(gvdb_index* h, Workspace* ws, cudaStream_t st, const float* q_dev, uint32_t nq, uint32_t k,
                   uint32_t R, uint64_t* ids_out, float* scores_out, uint64_t* cand_ids, uint32_t* cand_ham) {
+    need_all_rows(h);
     if (h->n_rows == 0) fail(GVDB_ERR_INDEX_NOT_BUILT, "index not built: search before any add");
     if ((h->dim & 3) != 0) fail(GVDB_ERR_NOT_IMPLEMENTED, "rescore_count > 2048 needs dim % 4 == 0");
     const uint64_t N = h->n_rows;
@@ -608,7 +644,7 @@ void search_big_r(gvdb_index* h, Workspace* ws, cudaStream_t st, const float* q_
     ws->big_tmp.ensure(std::max(tmp_a, tmp_b) + 256);
     static bool attr = false;   // benign race: idempotent
     if (!attr) {
-        CU(cudaFuncSetAttribute(rescore_slab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        CU(cudaFuncSetAttribute(rescore_slab_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 64 * (RS_SLAB + 4) * (int)sizeof(float)));
         attr = true;
     }
@@ -645,10 +681,10 @@ void search_big_r(gvdb_index* h, Workspace* ws, cudaStream_t st, const float* q_
             }
             // candidates = the first r_eff sorted keys; rescoring writes the query's R records
             const int q_slots = 2;
-            rescore_slab_kernel<<<(R + 31) / 32, 32, (size_t)(32 + q_slots) * stride * sizeof(float), st>>>(
+            rescore_slab_kernel<false><<<(R + 31) / 32, 32, (size_t)(32 + q_slots) * stride * sizeof(float), st>>>(
                 h->rows, h->norms, h->cfg.row_base, h->dim, stride, q_slots, q_dev + (size_t)gq * h->dim,
                 ws->qnorm.as<float>() + qi, ws->big_keys2.as<uint64_t>(), 0, &cut->r_eff, R, 1,
-                ws->rec_ham.as<uint32_t>(), ws->rec_ids.as<uint64_t>(), ws->rec_score.as<float>());
+                ws->rec_ham.as<uint32_t>(), ws->rec_ids.as<uint64_t>(), ws->rec_score.as<float>(), 0, 0);
             cos_key_kernel<<<(R + 255) / 256, 256, 0, st>>>(ws->rec_score.as<float>(), R, k32, v32);
             size_t tb = ws->big_tmp.bytes;
             CU(cub::DeviceRadixSort::SortPairs(ws->big_tmp.p, tb, k32, k32o, v32, v32o, (int64_t)R, 0, 32, st));
@@ -689,6 +725,7 @@ void search_device(gvdb_index* h, Workspace* ws, cudaStream_t st, const float* q
 // Exact flat search: same segment/select machinery with key = image(1 - cos) << 32 | row.
 void flat_device(gvdb_index* h, Workspace* ws, cudaStream_t st, const float* q_dev, uint32_t nq,
                  uint32_t k, uint64_t* ids_out, float* dist_out) {
+    need_all_rows(h);
     if (h->n_rows == 0) fail(GVDB_ERR_INDEX_NOT_BUILT, "index not built: search before any add");
     if (k == 0) fail(GVDB_ERR_INVALID_ARGUMENT, "k must be >= 1");
     if (k > kMaxR) fail(GVDB_ERR_NOT_IMPLEMENTED, "flat search with k > 2048 is not implemented yet");
@@ -723,7 +760,7 @@ void flat_device(gvdb_index* h, Workspace* ws, cudaStream_t st, const float* q_d
             {
                 Timed t(h, ws, st, K_FLAT);
                 flat_scan_kernel<<<grid, FLAT_THREADS, 0, st>>>(
-                    h->rows, h->norms, h->live, lo, hi, h->dim, qd, ws->qnorm.as<float>(), nqt,
+                    h->rows_base(), h->norms, h->live, lo, hi, h->dim, qd, ws->qnorm.as<float>(), nqt,
                     ws->misc.as<uint32_t>(), ws->cnt.as<uint32_t>(), ws->buf.as<uint64_t>(), cap,
                     ws->flag.as<uint32_t>());
             }
@@ -745,17 +782,26 @@ void flat_device(gvdb_index* h, Workspace* ws, cudaStream_t st, const float* q_d
     check_overflow(h, ws, st);
 }
 
-void add_device_impl(gvdb_index* h, cudaStream_t st, const float* rows_dev, uint64_t n,
-                     bool copy_rows, uint64_t* first_out) {
+// Rows [n_rows, n_rows + n) from DEVICE memory `src`: codes + norms + live bits for all of them,
+// f32 copies for the rows the index keeps (all of them, or the window's share).  `src` may be the
+// rows' final place (src_is_final: the host path copies straight into it).
+void add_device_impl(gvdb_index* h, cudaStream_t st, const float* src, uint64_t n, bool src_is_final,
+                     uint64_t* first_out) {
     if (first_out) *first_out = h->n_rows;
     if (n == 0) return;
     if (h->n_rows + n > 0xfffffff0ull) fail(GVDB_ERR_INDEX, "a shard holds at most 2^32-16 rows");
     grow(h, h->n_rows + n);
-    float* dst = h->rows + h->n_rows * (size_t)h->dim;
-    if (copy_rows)
-        CU(cudaMemcpyAsync(dst, rows_dev, n * (size_t)h->dim * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    const uint64_t first = h->n_rows;
+    if (!src_is_final) {
+        uint64_t lo = first, hi = first + n;                 // rows to keep
+        if (h->windowed) { lo = std::max(lo, h->win_first); hi = std::min(hi, h->win_first + h->win_count); }
+        if (lo < hi)
+            CU(cudaMemcpyAsync(h->rows + (lo - (h->windowed ? h->win_first : 0)) * (size_t)h->dim,
+                               src + (lo - first) * (size_t)h->dim, (hi - lo) * (size_t)h->dim * sizeof(float),
+                               cudaMemcpyDeviceToDevice, st));
+    }
     ingest_kernel<false><<<(unsigned)((n + STAGE_ROWS - 1) / STAGE_ROWS), STAGE_ROWS, 0, st>>>(
-        dst, n, h->dim, h->cfg.threshold, h->nchunk, h->n_rows, h->codes, h->norms, h->live, nullptr, 0);
+        src, n, h->dim, h->cfg.threshold, h->nchunk, first, h->codes, h->norms, h->live, nullptr, 0);
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(st));
     h->n_rows += n;
@@ -825,6 +871,12 @@ gvdb_status gvdb_create(const gvdb_config* cfg, gvdb_index** out) {
         if (const char* s = getenv("GVDB_OPT_M")) h->opt_m = (uint32_t)std::max(0, atoi(s));
         if (const char* s = getenv("GVDB_SEG_GROWTH")) h->seg_growth = (uint32_t)std::max(0, atoi(s));
         if (const char* s = getenv("GVDB_SCAN_CTAS_PER_SM")) h->scan_ctas_per_sm = std::max(1, atoi(s));
+        if (cfg->flags & GVDB_FLAG_ROW_WINDOW) {
+            h->windowed = true;
+            h->win_first = cfg->window_first;
+            h->win_count = cfg->window_count;
+            if (h->win_count) CU(cudaMalloc(&h->rows, h->win_count * (size_t)h->dim * sizeof(float)));
+        }
         if (cfg->capacity_rows) grow(h.get(), cfg->capacity_rows);
         *out = h.release();
     });
@@ -836,6 +888,8 @@ void gvdb_destroy(gvdb_index* h) {
     cudaGetDevice(&prev);
     cudaSetDevice(h->cfg.device);
     cudaDeviceSynchronize();
+    for (void* p : h->ipc_opened) cudaIpcCloseMemHandle(p);
+    if (h->peer_rows_dev) cudaFree((void*)h->peer_rows_dev);
     h->pool.clear();
     if (h->rows) cudaFree(h->rows);
     if (h->codes) cudaFree(h->codes);
@@ -862,10 +916,21 @@ gvdb_status gvdb_add(gvdb_index* h, const float* rows, uint64_t n, uint64_t* fir
         if (n == 0) return;
         grow(h, h->n_rows + n);
         WsLease lease(h, nullptr, false);
-        // rows go straight into their final place in HBM; ingest reads them from there
-        CU(cudaMemcpyAsync(h->rows + h->n_rows * (size_t)h->dim, rows, n * (size_t)h->dim * sizeof(float),
-                           cudaMemcpyHostToDevice, lease.stream));
-        add_device_impl(h, lease.stream, nullptr, n, false, nullptr);
+        if (!h->windowed) {
+            // rows go straight into their final place in HBM; ingest reads them from there
+            float* dst = h->rows + h->n_rows * (size_t)h->dim;
+            CU(cudaMemcpyAsync(dst, rows, n * (size_t)h->dim * sizeof(float), cudaMemcpyHostToDevice, lease.stream));
+            add_device_impl(h, lease.stream, dst, n, true, nullptr);
+        } else {
+            // windowed: stage chunks, keep only the window's share
+            const uint64_t chunk = 65536;
+            lease.ws->q_in.ensure(std::min(chunk, n) * (size_t)h->dim * 4);
+            for (uint64_t i0 = 0; i0 < n; i0 += chunk) {
+                const uint64_t m = std::min(chunk, n - i0);
+                CU(cudaMemcpyAsync(lease.ws->q_in.p, rows + i0 * h->dim, m * (size_t)h->dim * 4, cudaMemcpyHostToDevice, lease.stream));
+                add_device_impl(h, lease.stream, lease.ws->q_in.as<float>(), m, false, nullptr);
+            }
+        }
     });
 }
 
@@ -875,7 +940,7 @@ gvdb_status gvdb_add_device(gvdb_index* h, void* stream, const float* rows_dev, 
         need(h, "index");
         if (n) need(rows_dev, "rows_dev");
         DeviceGuard dg(h->cfg.device);
-        add_device_impl(h, (cudaStream_t)stream, rows_dev, n, true, first_row_out);
+        add_device_impl(h, (cudaStream_t)stream, rows_dev, n, false, first_row_out);
     });
 }
 
@@ -970,6 +1035,7 @@ void file_to_dev(FILE* f, void* dev, uint64_t bytes, uint64_t padded, void* stag
 gvdb_status gvdb_save(gvdb_index* h, const char* path) {
     return guarded([&] {
         need(h, "index"); need(path, "path");
+        need_all_rows(h);
         DeviceGuard dg(h->cfg.device);
         CU(cudaDeviceSynchronize());
         File file(path, "wb");
@@ -1318,8 +1384,151 @@ gvdb_status gvdb_merge_shards_device(gvdb_index* h, void* stream, uint32_t n_sha
         }
         CU(cudaGetLastError());
         launch_topk(h, ws, st, ws->rec_ids.as<uint64_t>(), ws->rec_score.as<float>(), nq, R, k, ids_out_dev, scores_out_dev);
-        CU(cudaStreamSynchronize(st));
-        flush_profile(h, ws);
+        finish_async(h, ws, st);
+    });
+}
+
+gvdb_status gvdb_stage1_device(gvdb_index* h, void* stream, const float* queries_dev, uint32_t nq,
+                               uint32_t rescore_count, uint64_t* keys_out_dev) {
+    return guarded([&] {
+        need(h, "index");
+        if (nq == 0) return;
+        need(queries_dev, "queries"); need(keys_out_dev, "keys_out");
+        DeviceGuard dg(h->cfg.device);
+        WsLease lease(h, (cudaStream_t)stream, true);
+        for (int attempt = 0; attempt < 2; ++attempt) {
+            bool optimistic = false;
+            search_core(h, lease.ws, lease.stream, queries_dev, nq, rescore_count, nullptr, nullptr, nullptr, true,
+                        attempt == 0, &optimistic, keys_out_dev);
+            if (!check_overflow(h, lease.ws, lease.stream, optimistic)) break;
+        }
+    });
+}
+
+gvdb_status gvdb_rescore_keys_device(gvdb_index* h, void* stream, const float* queries_dev, uint32_t nq,
+                                     uint32_t rescore_count, const uint64_t* keys_dev, float* scores_out_dev) {
+    return guarded([&] {
+        need(h, "index");
+        if (nq == 0 || rescore_count == 0) return;
+        need(queries_dev, "queries"); need(keys_dev, "keys"); need(scores_out_dev, "scores_out");
+        if ((h->dim & 3) != 0) fail(GVDB_ERR_NOT_IMPLEMENTED, "gvdb_rescore_keys_device needs dim % 4 == 0");
+        DeviceGuard dg(h->cfg.device);
+        WsLease lease(h, (cudaStream_t)stream, true);
+        cudaStream_t st = lease.stream;
+        const uint32_t R = rescore_count;
+        const int cols = std::min(h->dim, RS_SLAB);
+        const int stride = ((cols >> 2) & 1) ? cols : cols + 4;
+        const int q_slots = (int)std::min<uint32_t>(32, 31 / R + 2);
+        static bool attr = false;   // benign race: idempotent
+        if (!attr) {
+            CU(cudaFuncSetAttribute(rescore_slab_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    64 * (RS_SLAB + 4) * (int)sizeof(float)));
+            attr = true;
+        }
+        const uint64_t lo = h->windowed ? h->win_first : 0;
+        const uint64_t hi = h->windowed ? std::min(h->n_rows, h->win_first + h->win_count) : h->n_rows;
+        const uint64_t pairs = (uint64_t)nq * R;
+        {
+            Timed t(h, lease.ws, st, K_RESCORE);
+            rescore_slab_kernel<true><<<(unsigned)((pairs + 31) / 32), 32, (size_t)(32 + q_slots) * stride * sizeof(float), st>>>(
+                h->rows_base(), h->norms, h->cfg.row_base, h->dim, stride, q_slots, queries_dev, nullptr, keys_dev, 0,
+                nullptr, R, nq, nullptr, nullptr, scores_out_dev, lo, hi);
+        }
+        CU(cudaGetLastError());
+        finish_async(h, lease.ws, st);
+    });
+}
+
+gvdb_status gvdb_finish_owned_device(gvdb_index* h, void* stream, const uint64_t* keys_dev,
+                                     const float* scores_by_owner_dev, uint32_t n_owners, uint64_t rows_per_owner,
+                                     uint32_t nq, uint32_t rescore_count, uint32_t k, uint64_t* ids_out_dev,
+                                     float* scores_out_dev) {
+    return guarded([&] {
+        need(h, "index");
+        if (nq == 0) return;
+        need(keys_dev, "keys"); need(scores_by_owner_dev, "scores_by_owner");
+        need(ids_out_dev, "ids_out"); need(scores_out_dev, "scores_out");
+        const uint32_t R = rescore_count;
+        if (R == 0 || R > kMaxR) fail(GVDB_ERR_INVALID_ARGUMENT, "rescore_count must be in [1, 2048]");
+        if (k > R) fail(GVDB_ERR_INVALID_ARGUMENT, "k must be <= rescore_count");
+        if (n_owners == 0 || rows_per_owner == 0) fail(GVDB_ERR_INVALID_ARGUMENT, "n_owners and rows_per_owner must be >= 1");
+        DeviceGuard dg(h->cfg.device);
+        WsLease lease(h, (cudaStream_t)stream, true);
+        Workspace* ws = lease.ws;
+        cudaStream_t st = lease.stream;
+        ws->rec_ids.ensure((size_t)nq * R * 8);
+        ws->rec_score.ensure((size_t)nq * R * 4);
+        const uint64_t pairs = (uint64_t)nq * R;
+        {
+            Timed t(h, ws, st, K_MERGE);
+            gather_owner_scores_kernel<<<(unsigned)((pairs + 255) / 256), 256, 0, st>>>(
+                keys_dev, scores_by_owner_dev, n_owners, rows_per_owner, pairs, ws->rec_ids.as<uint64_t>(),
+                ws->rec_score.as<float>());
+        }
+        CU(cudaGetLastError());
+        launch_topk(h, ws, st, ws->rec_ids.as<uint64_t>(), ws->rec_score.as<float>(), nq, R, k, ids_out_dev, scores_out_dev);
+        finish_async(h, ws, st);
+    });
+}
+
+namespace {
+void attach_peers(gvdb_index* h, uint32_t n_owners, uint64_t rows_per_owner, uint32_t my_owner,
+                  const std::vector<const float*>& ptrs) {
+    if (!h->windowed) fail(GVDB_ERR_INVALID_ARGUMENT, "peer rows need an index created with GVDB_FLAG_ROW_WINDOW");
+    if (n_owners == 0 || rows_per_owner == 0 || my_owner >= n_owners)
+        fail(GVDB_ERR_INVALID_ARGUMENT, "bad owner partition");
+    if (h->win_first != (uint64_t)my_owner * rows_per_owner || h->win_count > rows_per_owner)
+        fail(GVDB_ERR_INVALID_ARGUMENT, "this index's row window is not owner my_owner's share");
+    if (rows_per_owner > 0xffffffffull) fail(GVDB_ERR_INVALID_ARGUMENT, "rows_per_owner too large");
+    if (h->peer_rows_dev) { cudaFree((void*)h->peer_rows_dev); h->peer_rows_dev = nullptr; }
+    CU(cudaMalloc((void**)&h->peer_rows_dev, n_owners * sizeof(float*)));
+    CU(cudaMemcpy((void*)h->peer_rows_dev, ptrs.data(), n_owners * sizeof(float*), cudaMemcpyHostToDevice));
+    h->n_peers = n_owners;
+    h->peer_per = rows_per_owner;
+}
+}  // namespace
+
+gvdb_status gvdb_export_rows_ipc(gvdb_index* h, uint8_t* handle_out) {
+    return guarded([&] {
+        need(h, "index"); need(handle_out, "handle_out");
+        static_assert(sizeof(cudaIpcMemHandle_t) == GVDB_IPC_HANDLE_BYTES, "IPC handle size");
+        if (!h->rows) fail(GVDB_ERR_INDEX_NOT_BUILT, "no f32 rows on this index");
+        DeviceGuard dg(h->cfg.device);
+        cudaIpcMemHandle_t hd;
+        CU(cudaIpcGetMemHandle(&hd, h->rows));
+        memcpy(handle_out, &hd, sizeof(hd));
+    });
+}
+
+gvdb_status gvdb_attach_peer_rows_ipc(gvdb_index* h, uint32_t n_owners, uint64_t rows_per_owner, uint32_t my_owner,
+                                      const uint8_t* handles) {
+    return guarded([&] {
+        need(h, "index"); need(handles, "handles");
+        DeviceGuard dg(h->cfg.device);
+        std::vector<const float*> ptrs(n_owners, nullptr);
+        for (uint32_t o = 0; o < n_owners; ++o) {
+            if (o == my_owner) { ptrs[o] = h->rows; continue; }
+            cudaIpcMemHandle_t hd;
+            memcpy(&hd, handles + (size_t)o * GVDB_IPC_HANDLE_BYTES, sizeof(hd));
+            void* p = nullptr;
+            CU(cudaIpcOpenMemHandle(&p, hd, cudaIpcMemLazyEnablePeerAccess));
+            h->ipc_opened.push_back(p);
+            ptrs[o] = static_cast<const float*>(p);
+        }
+        attach_peers(h, n_owners, rows_per_owner, my_owner, ptrs);
+    });
+}
+
+const void* gvdb_rows_device_ptr(const gvdb_index* h) { return h ? h->rows : nullptr; }
+
+gvdb_status gvdb_attach_peer_rows_ptr(gvdb_index* h, uint32_t n_owners, uint64_t rows_per_owner, uint32_t my_owner,
+                                      const void* const* row_ptrs) {
+    return guarded([&] {
+        need(h, "index"); need(row_ptrs, "row_ptrs");
+        DeviceGuard dg(h->cfg.device);
+        std::vector<const float*> ptrs(n_owners, nullptr);
+        for (uint32_t o = 0; o < n_owners; ++o) ptrs[o] = o == my_owner ? h->rows : static_cast<const float*>(row_ptrs[o]);
+        attach_peers(h, n_owners, rows_per_owner, my_owner, ptrs);
     });
 }
 

@@ -697,12 +697,21 @@ __device__ __forceinline__ void cp_async_wait_all() {
     asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
 }
 
+// OWNED = true (owner-computes rescoring, gvdb_rescore_keys_device): buf holds nq x R keys
+// hamming << 40 | GLOBAL row; a pair is scored iff its row lies in [win_lo, win_hi) (local row
+// numbers, local = global - row_base), everything else gets 0.0f; only out_score is written and
+// the query norms are folded here (qnorm == nullptr).
+template <bool OWNED>
 __global__ void __launch_bounds__(32)
 rescore_slab_kernel(const float* __restrict__ rows, const float* __restrict__ norms, uint64_t row_base,
                     int dim, int stride, int q_slots, const float* __restrict__ queries,
                     const float* __restrict__ qnorm, const uint64_t* __restrict__ buf, uint32_t cap,
                     const uint32_t* __restrict__ cnt, uint32_t R, uint32_t nq, uint32_t* __restrict__ out_ham,
-                    uint64_t* __restrict__ out_ids, float* __restrict__ out_score) {
+                    uint64_t* __restrict__ out_ids, float* __restrict__ out_score,
+                    uint64_t win_lo, uint64_t win_hi,
+                    const float* const* __restrict__ peer_rows = nullptr, uint64_t rows_per_owner = 0) {
+    // peer_rows != nullptr: row r lives in owner r / rows_per_owner's buffer (this GPU's or a
+    // peer's, mapped over NVLink) at offset (r % rows_per_owner) * dim — gvdb_attach_peer_rows_*.
     extern __shared__ __align__(16) float srow[];            // 32 candidate rows, then q_slots query rows
     float* sq = srow + (size_t)32 * stride;
     const int lane = threadIdx.x;
@@ -711,10 +720,24 @@ rescore_slab_kernel(const float* __restrict__ rows, const float* __restrict__ no
     const uint32_t q = (uint32_t)(p / R), r = (uint32_t)(p % R);
     const uint32_t q_first = (uint32_t)(p0 / R);             // the warp's pairs cover queries q_first ...
     const bool slot = q < nq;
-    const bool valid = slot && r < cnt[(size_t)q * CNT_STRIDE];
-    const uint64_t key = valid ? buf[(size_t)q * cap + r] : UINT64_MAX;
-    const uint32_t my_row = (uint32_t)key;
-    float dot = 0.0f;
+    bool valid;
+    uint64_t key;
+    uint32_t my_row;
+    if (OWNED) {
+        key = slot ? buf[(size_t)q * R + r] : UINT64_MAX;
+        const uint64_t local = (key & ((1ull << 40) - 1)) - row_base;
+        valid = key != UINT64_MAX && local >= win_lo && local < win_hi;
+        my_row = valid ? (uint32_t)local : 0xffffffffu;
+    } else {
+        valid = slot && r < cnt[(size_t)q * CNT_STRIDE];
+        key = valid ? buf[(size_t)q * cap + r] : UINT64_MAX;
+        my_row = (uint32_t)key;
+    }
+    float dot = 0.0f, qq2 = 0.0f;
+    if (OWNED && !__any_sync(0xffffffffu, valid)) {          // none of these rows lives here
+        if (slot) out_score[p] = 0.0f;
+        return;
+    }
     for (int c0 = 0; c0 < dim; c0 += RS_SLAB) {
         const int cols = min(RS_SLAB, dim - c0);
         const int nv = cols >> 2;                            // float4 per row in this slab
@@ -722,7 +745,8 @@ rescore_slab_kernel(const float* __restrict__ rows, const float* __restrict__ no
         for (int rr = 0; rr < 32; ++rr) {                    // row rr of the warp, 512 B per request
             const uint32_t grow = __shfl_sync(0xffffffffu, my_row, rr);
             if (grow == 0xffffffffu) continue;               // warp-uniform
-            const float* src = rows + (size_t)grow * dim + c0;
+            const float* src = peer_rows ? peer_rows[grow / rows_per_owner] + (size_t)(grow % rows_per_owner) * dim + c0
+                                         : rows + (size_t)grow * dim + c0;
             const uint32_t dst = smem_u32(srow + (size_t)rr * stride);
             for (int v = lane; v < nv; v += 32) cp_async16(dst + 16u * v, src + 4 * v);
         }
@@ -744,19 +768,62 @@ rescore_slab_kernel(const float* __restrict__ rows, const float* __restrict__ no
                 dot = __fadd_rn(dot, __fmul_rn(a.y, b.y));
                 dot = __fadd_rn(dot, __fmul_rn(a.z, b.z));
                 dot = __fadd_rn(dot, __fmul_rn(a.w, b.w));
+                if (OWNED) {                                 // ||q||^2, the same sequential fold
+                    qq2 = __fadd_rn(qq2, __fmul_rn(a.x, a.x));
+                    qq2 = __fadd_rn(qq2, __fmul_rn(a.y, a.y));
+                    qq2 = __fadd_rn(qq2, __fmul_rn(a.z, a.z));
+                    qq2 = __fadd_rn(qq2, __fmul_rn(a.w, a.w));
+                }
             }
         }
     }
     if (slot) {
-        float cosv = -INFINITY;
-        if (valid) {
-            const float na = qnorm[q], nb = norms[my_row];
-            cosv = (na == 0.0f || nb == 0.0f) ? 0.0f : __fdiv_rn(dot, __fmul_rn(na, nb));
+        if (OWNED) {
+            float cosv = 0.0f;
+            if (valid) {
+                const float na = __fsqrt_rn(qq2), nb = norms[my_row];
+                cosv = (na == 0.0f || nb == 0.0f) ? 0.0f : __fdiv_rn(dot, __fmul_rn(na, nb));
+            }
+            out_score[p] = cosv;
+        } else {
+            float cosv = -INFINITY;
+            if (valid) {
+                const float na = qnorm[q], nb = norms[my_row];
+                cosv = (na == 0.0f || nb == 0.0f) ? 0.0f : __fdiv_rn(dot, __fmul_rn(na, nb));
+            }
+            out_ham[p] = valid ? (uint32_t)(key >> 32) : 0xffffffffu;
+            out_ids[p] = valid ? row_base + my_row : UINT64_MAX;
+            out_score[p] = cosv;
         }
-        out_ham[p] = valid ? (uint32_t)(key >> 32) : 0xffffffffu;
-        out_ids[p] = valid ? row_base + my_row : UINT64_MAX;
-        out_score[p] = cosv;
     }
+}
+
+// stage-1 result as keys hamming << 40 | global row (gvdb_stage1_device)
+__global__ void emit_keys_kernel(const uint64_t* __restrict__ buf, uint32_t cap, const uint32_t* __restrict__ cnt,
+                                 uint32_t R, uint32_t nq, uint64_t row_base, uint64_t* __restrict__ keys_out) {
+    const uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t q = (uint32_t)(p / R), r = (uint32_t)(p % R);
+    if (q >= nq) return;
+    uint64_t out = UINT64_MAX;
+    if (r < cnt[(size_t)q * CNT_STRIDE]) {
+        const uint64_t key = buf[(size_t)q * cap + r];
+        out = ((key >> 32) << 40) | (row_base + (uint32_t)key);
+    }
+    keys_out[p] = out;
+}
+
+// each key takes the score its row's owner computed (gvdb_finish_owned_device)
+__global__ void gather_owner_scores_kernel(const uint64_t* __restrict__ keys, const float* __restrict__ by_owner,
+                                           uint32_t n_owners, uint64_t rows_per_owner, uint64_t n_pairs,
+                                           uint64_t* __restrict__ rec_ids, float* __restrict__ rec_score) {
+    const uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_pairs) return;
+    const uint64_t key = keys[p];
+    if (key == UINT64_MAX) { rec_ids[p] = UINT64_MAX; rec_score[p] = -INFINITY; return; }
+    const uint64_t row = key & ((1ull << 40) - 1);
+    const uint64_t owner = min((uint64_t)n_owners - 1, row / rows_per_owner);
+    rec_ids[p] = row;
+    rec_score[p] = by_owner[owner * n_pairs + p];
 }
 
 // ---------------------------------------------------------------------------------------

@@ -134,3 +134,78 @@ class ShardedSearcher:
             scores_out.copy_(all_sc[:nq])
             return ids_out, scores_out
         return all_ids[:nq], all_sc[:nq]
+
+
+class QueryParallelSearcher:
+    """Codes replicated, f32 rows sharded: the layout for corpora whose 1-bit codes fit every GPU
+    (96 B per 768-d row: 100M rows = 9.6 GB).  Rank g holds the codes of ALL rows and the f32
+    originals of rows [g*per, (g+1)*per) (GpuIndex(row_window=...)); the QUERIES are partitioned,
+    so every per-query stage — scan, cut, rescoring, ordering — divides by the number of GPUs:
+
+      1. all-gather the ranks' query batches (rescoring happens where the row lives);
+      2. stage 1 on the local batch: keys (hamming, global row), exact top R;
+      3. all-gather the keys;
+      4. every rank scores the candidates whose rows it owns (exact sequential-fold cosine);
+      5. all-to-all: rank g receives, from every owner, the scores of ITS queries' candidates;
+      6. each key takes its owner's score; order by (cosine desc, hamming asc, row asc); first k.
+
+    The answer is bit-identical to the single-index search.  `rows_per_owner` = ceil(N / world)."""
+
+    def __init__(self, index, n_total_rows: int, group=None):
+        import torch.distributed as dist
+        self.index = index
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.rows_per_owner = (n_total_rows + self.world - 1) // self.world
+
+    def search_batch_device(self, my_queries_t, k: int, rescore_count: int, ids_out=None, scores_out=None):
+        """my_queries_t: this rank's [nq, dim] batch (same nq on every rank) -> its top-k lists."""
+        import torch
+        import torch.distributed as dist
+        W, R = self.world, rescore_count
+        nq, dim = my_queries_t.shape
+        dev = my_queries_t.device
+        all_q = torch.empty((W * nq, dim), dtype=torch.float32, device=dev)
+        dist.all_gather_into_tensor(all_q, my_queries_t, group=self.group)
+        my_keys = self.index.stage1_device(my_queries_t, R)
+        all_keys = torch.empty((W * nq, R), dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(all_keys, my_keys, group=self.group)
+        part = self.index.rescore_keys_device(all_q, all_keys)          # [W*nq, R], chunk g = rank g's queries
+        by_owner = torch.empty_like(part)
+        dist.all_to_all_single(by_owner, part, group=self.group)         # chunk o = owner o's scores for MY queries
+        return self.index.finish_owned_device(my_keys, by_owner.view(W, nq, R), self.rows_per_owner, k,
+                                              ids_out, scores_out)
+
+
+def attach_peer_rows(index, n_total_rows: int, group=None):
+    """Codes replicated, rows sharded, NO collective per batch: every rank maps the other ranks'
+    f32 row buffers (CUDA IPC handles exchanged once with an all-gather) and its rescoring kernel
+    reads candidate rows straight out of their owner's HBM over NVLink.  After this call
+    index.search_batch_device(...) answers this rank's own queries on its own."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    per = (n_total_rows + world - 1) // world
+    mine = torch.frombuffer(bytearray(index.export_rows_ipc()), dtype=torch.uint8)
+    dev = torch.device("cuda", index.device)
+    allh = torch.empty(world * 64, dtype=torch.uint8, device=dev)
+    dist.all_gather_into_tensor(allh, mine.to(dev), group=group)
+    raw = allh.cpu().numpy().tobytes()
+    index.attach_peer_rows_ipc([raw[i * 64:(i + 1) * 64] for i in range(world)], per, rank)
+    dist.barrier(group)
+    return per
+
+
+class PeerRowsSearcher:
+    """Searcher for the peer-rows layout: after attach_peer_rows() every rank answers its own
+    queries with a plain single-index call; the only cross-GPU traffic is the rescoring kernel's
+    reads of candidate rows from their owner's HBM."""
+
+    def __init__(self, index, n_total_rows: int, group=None):
+        self.index = index
+        self.rows_per_owner = attach_peer_rows(index, n_total_rows, group)
+
+    def search_batch_device(self, my_queries_t, k: int, rescore_count: int, ids_out=None, scores_out=None):
+        return self.index.search_batch_device(my_queries_t, k, rescore_count, ids_out, scores_out)

@@ -28,7 +28,10 @@ class GpuIndex:
     """Rows [row_base, row_base + len) of the corpus: 1-bit codes + f32 originals in HBM."""
 
     def __init__(self, dim: int, threshold: float = 0.0, rescore_ratio: float = 0.1,
-                 device: int = 0, capacity_rows: int = 0, row_base: int = 0):
+                 device: int = 0, capacity_rows: int = 0, row_base: int = 0,
+                 row_window: tuple[int, int] | None = None):
+        """row_window = (first, count): keep the f32 originals only for those local rows (codes and
+        norms are kept for every row) — the "codes replicated, rows sharded" multi-GPU layout."""
         self._lib = _ffi.lib()
         cfg = _ffi.GvdbConfig()
         cfg.struct_size = C.sizeof(_ffi.GvdbConfig)
@@ -39,6 +42,9 @@ class GpuIndex:
         cfg.flags = 0
         cfg.capacity_rows = capacity_rows
         cfg.row_base = row_base
+        if row_window is not None:
+            cfg.flags = _ffi.GVDB_FLAG_ROW_WINDOW
+            cfg.window_first, cfg.window_count = int(row_window[0]), int(row_window[1])
         h = C.c_void_p()
         raise_for_status(self._lib.gvdb_create(C.byref(cfg), C.byref(h)), self._lib)
         self._h = h
@@ -278,6 +284,70 @@ class GpuIndex:
             self._h, C.c_void_p(st), n_shards, C.c_void_p(records_all.data_ptr()), nq,
             rescore_count, k, C.c_void_p(ids_out.data_ptr()), C.c_void_p(scores_out.data_ptr())))
         return ids_out, scores_out
+
+    # -- query-parallel search: replicated codes, row-sharded originals ------------------------
+    def stage1_device(self, queries_t, rescore_count: int, keys_out=None):
+        """Stage 1 only: [nq, R] int64 keys hamming << 40 | global row, ascending, -1 (GVDB_NO_ID) unfilled."""
+        import torch
+        assert queries_t.is_cuda and queries_t.dtype == torch.float32 and queries_t.is_contiguous()
+        nq = queries_t.shape[0]
+        if keys_out is None:
+            keys_out = torch.empty((nq, rescore_count), dtype=torch.int64, device=queries_t.device)
+        st = torch.cuda.current_stream(queries_t.device).cuda_stream
+        self._ok(self._lib.gvdb_stage1_device(self._h, C.c_void_p(st), C.c_void_p(queries_t.data_ptr()), nq,
+                                              rescore_count, C.c_void_p(keys_out.data_ptr())))
+        return keys_out
+
+    def rescore_keys_device(self, queries_t, keys_t, scores_out=None):
+        """Exact cosine for the keys whose row this index holds in f32 (its window), 0.0 elsewhere."""
+        import torch
+        assert queries_t.is_cuda and queries_t.is_contiguous() and keys_t.is_contiguous()
+        nq, R = keys_t.shape
+        assert queries_t.shape[0] == nq
+        if scores_out is None:
+            scores_out = torch.empty((nq, R), dtype=torch.float32, device=queries_t.device)
+        st = torch.cuda.current_stream(queries_t.device).cuda_stream
+        self._ok(self._lib.gvdb_rescore_keys_device(self._h, C.c_void_p(st), C.c_void_p(queries_t.data_ptr()), nq, R,
+                                                    C.c_void_p(keys_t.data_ptr()), C.c_void_p(scores_out.data_ptr())))
+        return scores_out
+
+    def finish_owned_device(self, keys_t, scores_by_owner_t, rows_per_owner: int, k: int, ids_out=None,
+                            scores_out=None):
+        """keys [nq, R]; scores_by_owner [n_owners, nq, R] -> (ids [nq, k] int64, scores [nq, k] f32)."""
+        import torch
+        assert keys_t.is_contiguous() and scores_by_owner_t.is_contiguous()
+        nq, R = keys_t.shape
+        n_owners = scores_by_owner_t.shape[0]
+        assert scores_by_owner_t.numel() == n_owners * nq * R
+        dev = keys_t.device
+        if ids_out is None:
+            ids_out = torch.empty((nq, k), dtype=torch.int64, device=dev)
+        if scores_out is None:
+            scores_out = torch.empty((nq, k), dtype=torch.float32, device=dev)
+        st = torch.cuda.current_stream(dev).cuda_stream
+        self._ok(self._lib.gvdb_finish_owned_device(
+            self._h, C.c_void_p(st), C.c_void_p(keys_t.data_ptr()), C.c_void_p(scores_by_owner_t.data_ptr()),
+            n_owners, rows_per_owner, nq, R, k, C.c_void_p(ids_out.data_ptr()), C.c_void_p(scores_out.data_ptr())))
+        return ids_out, scores_out
+
+    # -- peer rows: rescoring out of the other GPUs' HBM over NVLink -----------------------------
+    def export_rows_ipc(self) -> bytes:
+        buf = (C.c_uint8 * 64)()
+        self._ok(self._lib.gvdb_export_rows_ipc(self._h, buf))
+        return bytes(buf)
+
+    def attach_peer_rows_ipc(self, handles: list[bytes], rows_per_owner: int, my_owner: int):
+        raw = b"".join(handles)
+        assert len(raw) == 64 * len(handles)
+        buf = (C.c_uint8 * len(raw)).from_buffer_copy(raw)
+        self._ok(self._lib.gvdb_attach_peer_rows_ipc(self._h, len(handles), rows_per_owner, my_owner, buf))
+
+    def rows_device_ptr(self) -> int:
+        return int(self._lib.gvdb_rows_device_ptr(self._h) or 0)
+
+    def attach_peer_rows_ptr(self, ptrs: list[int], rows_per_owner: int, my_owner: int):
+        arr = (C.c_void_p * len(ptrs))(*ptrs)
+        self._ok(self._lib.gvdb_attach_peer_rows_ptr(self._h, len(ptrs), rows_per_owner, my_owner, arr))
 
     # -- measurement hooks --------------------------------------------------------------------
     def profile_enable(self, on: bool = True):

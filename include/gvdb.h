@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define GVDB_ABI_VERSION 2u
+#define GVDB_ABI_VERSION 3u
 
 #if defined(__GNUC__)
 #define GVDB_API __attribute__((visibility("default")))
@@ -60,10 +60,20 @@ typedef struct gvdb_config {
     float threshold;         /* BinaryQuantizationConfig::threshold  (default 0.0) */
     float rescore_ratio;     /* BinaryQuantizationConfig::rescore_ratio (default 0.1) */
     int32_t device;          /* CUDA device ordinal */
-    uint32_t flags;          /* reserved, 0 */
+    uint32_t flags;          /* GVDB_FLAG_* */
     uint64_t capacity_rows;  /* rows to reserve in HBM up front (0 = grow on demand) */
     uint64_t row_base;       /* global row number of this shard's local row 0 */
+    /* GVDB_FLAG_ROW_WINDOW: keep the f32 originals only for local rows
+     * [window_first, window_first + window_count); every row still gets its 1-bit code and norm.
+     * This is the "codes replicated, rows sharded" multi-GPU layout (codes are 32x smaller than
+     * the rows): each GPU scans the whole corpus for ITS share of the queries and rescoring is
+     * done by the GPU that owns the row (gvdb_stage1_device / gvdb_rescore_keys_device /
+     * gvdb_finish_owned_device).  Entry points that need every row's f32 data fail with
+     * GVDB_ERR_INVALID_ARGUMENT on a windowed index whose window does not cover all rows. */
+    uint64_t window_first;
+    uint64_t window_count;
 } gvdb_config;
+#define GVDB_FLAG_ROW_WINDOW 1u
 
 /* IndexStats (src/index.rs:82-88) plus the HBM footprint. */
 typedef struct gvdb_stats {
@@ -188,10 +198,50 @@ GVDB_API gvdb_status gvdb_search_shard_sliced_device(gvdb_index* h, void* stream
  * each query keep the global top R by (hamming, global row), then order by (cosine desc,
  * hamming asc, row asc) and emit k.  `records_dev` is n_shards packed buffers back to back,
  * in rank order — exactly what an all-gather of the gvdb_search_shard_device outputs yields. */
+/* gvdb_merge_shards_device, gvdb_rescore_keys_device and gvdb_finish_owned_device are
+ * stream-ordered: they enqueue on `stream` and return; outputs are complete once the stream
+ * reaches that point (they have nothing to read back on the host). */
 GVDB_API gvdb_status gvdb_merge_shards_device(gvdb_index* h, void* stream, uint32_t n_shards,
                                               const void* records_dev, uint32_t nq,
                                               uint32_t rescore_count, uint32_t k,
                                               uint64_t* ids_out_dev, float* scores_out_dev);
+
+/* ---- query-parallel search over replicated codes + row-sharded originals ----------------- */
+/* Keys are hamming << 40 | global row (rows < 2^40), GVDB_NO_ID when unfilled.
+ * Stage 1 only (quantise, Hamming scan, exact top rescore_count by (hamming, row)):
+ *   keys_out_dev  nq x rescore_count u64, ascending per query.   rescore_count <= 2048. */
+GVDB_API gvdb_status gvdb_stage1_device(gvdb_index* h, void* stream, const float* queries_dev, uint32_t nq,
+                                        uint32_t rescore_count, uint64_t* keys_out_dev);
+/* Owner-computes rescoring: for every key whose row lies in THIS index's resident window, the
+ * exact f32 cosine of (queries_dev[q], row) (src/quantization.rs:206-216); 0.0f elsewhere.
+ *   queries_dev nq x dim, keys_dev / scores_out_dev nq x rescore_count. */
+GVDB_API gvdb_status gvdb_rescore_keys_device(gvdb_index* h, void* stream, const float* queries_dev, uint32_t nq,
+                                              uint32_t rescore_count, const uint64_t* keys_dev,
+                                              float* scores_out_dev);
+/* Final order for nq queries: scores_by_owner_dev holds n_owners score arrays (nq x rescore_count
+ * each, back to back, owner g = rows [g * rows_per_owner, (g+1) * rows_per_owner)); each key takes
+ * the score of the owner of its row, then (cosine desc, hamming asc, row asc), first k. */
+GVDB_API gvdb_status gvdb_finish_owned_device(gvdb_index* h, void* stream, const uint64_t* keys_dev,
+                                              const float* scores_by_owner_dev, uint32_t n_owners,
+                                              uint64_t rows_per_owner, uint32_t nq, uint32_t rescore_count,
+                                              uint32_t k, uint64_t* ids_out_dev, float* scores_out_dev);
+
+/* ---- peer rows: rescoring straight out of the other GPUs' HBM over NVLink ------------------ */
+/* With GVDB_FLAG_ROW_WINDOW every GPU holds all codes and one contiguous share of the f32 rows:
+ * owner o keeps rows [o * rows_per_owner, (o+1) * rows_per_owner).  Once the owners' row buffers
+ * are attached, gvdb_search_batch(_device) works on the windowed index: the rescoring kernel
+ * copies each candidate row from its owner's memory (cp.async on the peer-mapped address, i.e.
+ * NVLink/NVSwitch loads inside the kernel) — no collective in the data path.
+ * Across processes: exchange gvdb_export_rows_ipc handles (any transport; this repository
+ * all-gathers them with torch.distributed) and call gvdb_attach_peer_rows_ipc.  Inside one
+ * process (several indexes, tests): gvdb_rows_device_ptr + gvdb_attach_peer_rows_ptr. */
+#define GVDB_IPC_HANDLE_BYTES 64
+GVDB_API gvdb_status gvdb_export_rows_ipc(gvdb_index* h, uint8_t* handle_out /* 64 bytes */);
+GVDB_API gvdb_status gvdb_attach_peer_rows_ipc(gvdb_index* h, uint32_t n_owners, uint64_t rows_per_owner,
+                                               uint32_t my_owner, const uint8_t* handles /* n_owners x 64 */);
+GVDB_API const void* gvdb_rows_device_ptr(const gvdb_index* h);
+GVDB_API gvdb_status gvdb_attach_peer_rows_ptr(gvdb_index* h, uint32_t n_owners, uint64_t rows_per_owner,
+                                               uint32_t my_owner, const void* const* row_ptrs /* n_owners */);
 
 /* ---- measurement hooks ---------------------------------------------------------------- */
 /* When enabled, every kernel the library launches is bracketed by CUDA events on the stream

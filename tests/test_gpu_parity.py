@@ -411,3 +411,71 @@ def test_save_load_round_trip(gv, tmp_path):
     assert np.array_equal(a[0], b[0]) and np.array_equal(_bits(a[1]), _bits(b[1]))
     assert np.array_equal(fa[0], fb[0]) and np.array_equal(_bits(fa[1]), _bits(fb[1]))
     assert int(a[0].min()) >= 5000      # global ids carry the saved row_base
+
+
+def test_query_parallel_replicated_codes_equals_single_index(gv):
+    """The "codes replicated, rows sharded" layout emulated on ONE GPU: G windowed indexes (all
+    codes, f32 rows of one shard each).  Rank g runs stage 1 for ITS queries, every rank scores the
+    candidates it owns, rank g picks each key's owner score and orders: == single index, bit for bit."""
+    import torch
+    from grape_vector_db_b200 import synth
+    dev = torch.device("cuda:0")
+    n, dim, nq_per, R, k = 50_000, 768, 80, 40, 10
+    rows = synth.lowrank_rows(0, n, dim)
+    for G in (2, 3):
+        qs = synth.lowrank_queries(0, nq_per * G, dim)
+        oi, os_ = oracle.multi_stage_search_batch(qs, rows, R, k, nthreads=8)
+        per = (n + G - 1) // G
+        ranks = []
+        for g in range(G):
+            ix = gv.GpuIndex(dim, row_window=(g * per, min(per, n - g * per)))
+            ix.add(rows[:20_000])                        # host path, crosses window edges
+            ix.add_device(torch.from_numpy(rows[20_000:]).to(dev))
+            assert len(ix) == n
+            ranks.append(ix)
+        with pytest.raises(gv.VectorDbError):            # the two-stage call needs every row's f32 data
+            ranks[0].search_batch(qs[:4], k, R)
+        all_q = torch.from_numpy(qs).to(dev)
+        keys = [ranks[g].stage1_device(all_q[g * nq_per:(g + 1) * nq_per].contiguous(), R) for g in range(G)]
+        all_keys = torch.cat(keys).contiguous()
+        parts = [ranks[g].rescore_keys_device(all_q, all_keys) for g in range(G)]     # [G*nq_per, R] each
+        got_i, got_s = [], []
+        for g in range(G):     # what rank g receives from the all-to-all: owner o's scores for its queries
+            by_owner = torch.stack([parts[o][g * nq_per:(g + 1) * nq_per] for o in range(G)]).contiguous()
+            i_, s_ = ranks[g].finish_owned_device(keys[g], by_owner, per, k)
+            got_i.append(i_.cpu().numpy().astype(np.uint64))
+            got_s.append(s_.cpu().numpy())
+        assert np.array_equal(np.concatenate(got_i), oi), f"G={G}"
+        assert np.array_equal(_bits(np.concatenate(got_s)), _bits(os_)), f"G={G}"
+        for ix in ranks:
+            ix.close()
+
+
+def test_peer_rows_rescoring_equals_single_index(gv):
+    """Windowed indexes whose rescoring kernel reads each candidate row from its owner's buffer
+    (gvdb_attach_peer_rows_ptr; across processes the same buffers are mapped with CUDA IPC and the
+    reads travel over NVLink): every "rank" answers its own queries alone, bit-identically."""
+    from grape_vector_db_b200 import synth
+    n, dim, R, k, G = 30_011, 768, 40, 10, 3
+    rows = synth.lowrank_rows(0, n, dim)
+    qs = synth.lowrank_queries(0, 150, dim)
+    oi, os_ = oracle.multi_stage_search_batch(qs, rows, R, k, nthreads=8)
+    per = (n + G - 1) // G
+    ranks = []
+    for g in range(G):
+        ix = gv.GpuIndex(dim, row_window=(g * per, min(per, n - g * per)))
+        ix.add(rows)
+        ranks.append(ix)
+    ptrs = [ix.rows_device_ptr() for ix in ranks]
+    for g, ix in enumerate(ranks):
+        ix.attach_peer_rows_ptr(ptrs, per, g)
+    for g, ix in enumerate(ranks):
+        lo, hi = g * 50, (g + 1) * 50
+        ids, sc = ix.search_batch(qs[lo:hi], k, R)                  # tensor-core scan needs >= 64: CUDA-core path
+        assert np.array_equal(ids, oi[lo:hi]) and np.array_equal(_bits(sc), _bits(os_[lo:hi]))
+    ids, sc = ranks[1].search_batch(qs, k, R)                       # 150 queries: tensor-core scan
+    assert np.array_equal(ids, oi) and np.array_equal(_bits(sc), _bits(os_))
+    with pytest.raises(gv.VectorDbError):                           # flat search still needs local rows
+        ranks[0].flat_search_batch(qs[:2], 5)
+    for ix in ranks:
+        ix.close()
