@@ -136,6 +136,34 @@ class ShardedSearcher:
         return all_ids[:nq], all_sc[:nq]
 
 
+def _all_gather_rows(local, group=None):
+    """[n, ...] from every rank, concatenated along dim 0 in rank order (NCCL or gloo)."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    out = torch.empty((world * local.shape[0],) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    if local.is_cuda:
+        dist.all_gather_into_tensor(out, local, group=group)
+    else:
+        dist.all_gather(list(out.chunk(world)), local, group=group)
+    return out
+
+
+def _all_to_all_rows(send, group=None):
+    """send is `world` equal chunks along dim 0; chunk s goes to rank s (NCCL or gloo)."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    if send.is_cuda:
+        recv = torch.empty_like(send)
+        dist.all_to_all_single(recv, send, group=group)
+        return recv
+    per = send.shape[0] // world
+    everything = _all_gather_rows(send, group)               # [world * world * per, ...]
+    return torch.cat([everything[(r * world + rank) * per:(r * world + rank + 1) * per] for r in range(world)])
+
+
 class QueryParallelSearcher:
     """Codes replicated, f32 rows sharded: the layout for corpora whose 1-bit codes fit every GPU
     (96 B per 768-d row: 100M rows = 9.6 GB).  Rank g holds the codes of ALL rows and the f32
@@ -166,14 +194,11 @@ class QueryParallelSearcher:
         W, R = self.world, rescore_count
         nq, dim = my_queries_t.shape
         dev = my_queries_t.device
-        all_q = torch.empty((W * nq, dim), dtype=torch.float32, device=dev)
-        dist.all_gather_into_tensor(all_q, my_queries_t, group=self.group)
+        all_q = _all_gather_rows(my_queries_t, self.group)
         my_keys = self.index.stage1_device(my_queries_t, R)
-        all_keys = torch.empty((W * nq, R), dtype=torch.int64, device=dev)
-        dist.all_gather_into_tensor(all_keys, my_keys, group=self.group)
+        all_keys = _all_gather_rows(my_keys, self.group)
         part = self.index.rescore_keys_device(all_q, all_keys)          # [W*nq, R], chunk g = rank g's queries
-        by_owner = torch.empty_like(part)
-        dist.all_to_all_single(by_owner, part, group=self.group)         # chunk o = owner o's scores for MY queries
+        by_owner = _all_to_all_rows(part, self.group)                    # chunk o = owner o's scores for MY queries
         return self.index.finish_owned_device(my_keys, by_owner.view(W, nq, R), self.rows_per_owner, k,
                                               ids_out, scores_out)
 

@@ -124,3 +124,94 @@ def test_two_rank_gloo_exchange_and_merge(tmp_path):
     sl_s = np.concatenate([np.load(tmp_path / f"slice_sc_{r}.npy") for r in range(world)])
     assert np.array_equal(sl_i, want_i)
     assert np.array_equal(sl_s.view(np.uint32), want_s.view(np.uint32))
+
+
+class _CpuShard:
+    """Stands in for a windowed GpuIndex on CPU (the product's are CUDA kernels): same three calls
+    QueryParallelSearcher makes, answered by the oracle.  Holds ALL rows' codes, f32 rows of
+    [lo, hi) only."""
+
+    def __init__(self, rows_all, lo, hi):
+        from oracle import oracle
+        self.o = oracle
+        self.codes = oracle.quantize_batch(rows_all)
+        self.lo, self.hi = lo, hi
+        self.rows = rows_all[lo:hi].copy()
+        self.n = rows_all.shape[0]
+
+    def stage1_device(self, q_t, R):
+        import torch
+        q = q_t.numpy()
+        keys = np.full((q.shape[0], R), -1, dtype=np.int64)
+        for i in range(q.shape[0]):
+            ham = self.o.hamming_all(self.o.quantize(q[i]), self.codes).astype(np.int64)
+            order = np.lexsort((np.arange(self.n), ham))[:R]
+            keys[i, :len(order)] = (ham[order] << 40) | order
+        return torch.from_numpy(keys)
+
+    def rescore_keys_device(self, q_t, keys_t):
+        import torch
+        q, keys = q_t.numpy(), keys_t.numpy()
+        out = np.zeros(keys.shape, dtype=np.float32)
+        for i in range(keys.shape[0]):
+            for j in range(keys.shape[1]):
+                if keys[i, j] < 0:
+                    continue
+                row = int(keys[i, j] & ((1 << 40) - 1))
+                if self.lo <= row < self.hi:
+                    out[i, j] = self.o.cosine_similarity(q[i], self.rows[row - self.lo])
+        return torch.from_numpy(out)
+
+    def finish_owned_device(self, keys_t, by_owner_t, rows_per_owner, k, ids_out=None, scores_out=None):
+        import torch
+        keys, by_owner = keys_t.numpy(), by_owner_t.numpy()
+        nq, R = keys.shape
+        ids = np.full((nq, k), np.iinfo(np.uint64).max, dtype=np.uint64)
+        sc = np.full((nq, k), -np.inf, dtype=np.float32)
+        for i in range(nq):
+            valid = keys[i] >= 0
+            rows = (keys[i] & ((1 << 40) - 1))[valid]
+            owner = np.minimum(by_owner.shape[0] - 1, rows // rows_per_owner)
+            score = by_owner[owner, i, np.flatnonzero(valid)]
+            order = np.argsort(-score, kind="stable")[:k]          # stage-1 order breaks ties
+            ids[i, :len(order)] = rows[order].astype(np.uint64)
+            sc[i, :len(order)] = score[order]
+        return torch.from_numpy(ids.view(np.int64)), torch.from_numpy(sc)
+
+
+def _qp_worker(rank, world, port, n, dim, nq_per, R, k, out_dir):
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+    from grape_vector_db_b200 import dist as gdist
+    from grape_vector_db_b200 import synth
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    rows = synth.lowrank_rows(0, n, dim)
+    lo, hi = gdist.shard_bounds(n, world, rank)
+    searcher = gdist.QueryParallelSearcher(_CpuShard(rows, lo, hi), n)
+    assert searcher.rows_per_owner == (n + world - 1) // world
+    my_q = synth.lowrank_queries(rank * nq_per, nq_per, dim)
+    ids, sc = searcher.search_batch_device(torch.from_numpy(my_q), k, R)
+    np.save(os.path.join(out_dir, f"qp_ids_{rank}.npy"), ids.numpy().view(np.uint64))
+    np.save(os.path.join(out_dir, f"qp_sc_{rank}.npy"), sc.numpy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_two_rank_gloo_query_parallel(tmp_path):
+    """dist.QueryParallelSearcher's three collectives (all-gather queries, all-gather keys,
+    all-to-all scores) with two gloo ranks: each rank's answers for ITS queries equal the
+    single-index oracle."""
+    import torch.multiprocessing as mp
+    from grape_vector_db_b200 import synth
+    from oracle import oracle
+    n, dim, nq_per, R, k, world = 3000, 64, 5, 40, 10, 2
+    port = _free_port()
+    mp.spawn(_qp_worker, args=(world, port, n, dim, nq_per, R, k, str(tmp_path)), nprocs=world, join=True)
+    rows = synth.lowrank_rows(0, n, dim)
+    for r in range(world):
+        qs = synth.lowrank_queries(r * nq_per, nq_per, dim)
+        want_i, want_s = oracle.multi_stage_search_batch(qs, rows, R, k)
+        assert np.array_equal(np.load(tmp_path / f"qp_ids_{r}.npy"), want_i)
+        assert np.array_equal(np.load(tmp_path / f"qp_sc_{r}.npy").view(np.uint32), want_s.view(np.uint32))
