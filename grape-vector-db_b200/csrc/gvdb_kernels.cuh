@@ -738,26 +738,36 @@ rescore_slab_kernel(const float* __restrict__ rows, const float* __restrict__ no
         if (slot) out_score[p] = 0.0f;
         return;
     }
+    // Staging: ONE TMA bulk copy per row (lane l fetches its own candidate row, the first q_slots
+    // lanes also fetch a query row), completion on an mbarrier.  Whole-row requests matter when the
+    // row lives in a peer GPU's HBM: NVLink carries them as large packets.
+    __shared__ __align__(8) uint64_t s_bar;
+    const uint32_t bar = smem_u32(&s_bar);
+    if (lane == 0) { mbar_init(bar, 1); fence_mbar_init(); }
+    __syncwarp();
+    uint32_t phase = 0;
+    const bool have_row = my_row != 0xffffffffu;
+    const bool have_q = lane < q_slots && q_first + lane < nq;
+    const uint32_t n_copies = __popc(__ballot_sync(0xffffffffu, have_row)) + __popc(__ballot_sync(0xffffffffu, have_q));
     for (int c0 = 0; c0 < dim; c0 += RS_SLAB) {
         const int cols = min(RS_SLAB, dim - c0);
         const int nv = cols >> 2;                            // float4 per row in this slab
-        if (c0) __syncwarp();
-        for (int rr = 0; rr < 32; ++rr) {                    // row rr of the warp, 512 B per request
-            const uint32_t grow = __shfl_sync(0xffffffffu, my_row, rr);
-            if (grow == 0xffffffffu) continue;               // warp-uniform
-            const float* src = peer_rows ? peer_rows[grow / rows_per_owner] + (size_t)(grow % rows_per_owner) * dim + c0
-                                         : rows + (size_t)grow * dim + c0;
-            const uint32_t dst = smem_u32(srow + (size_t)rr * stride);
-            for (int v = lane; v < nv; v += 32) cp_async16(dst + 16u * v, src + 4 * v);
+        const uint32_t row_bytes = (uint32_t)cols * 4u;
+        if (c0) {                                            // everyone is done reading the previous slab,
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // order those reads before the TMA writes
+            __syncwarp();
         }
-        for (int qq = 0; qq < q_slots; ++qq) {               // the (few) distinct queries of these pairs
-            if (q_first + qq >= nq) break;
-            const float* src = queries + (size_t)(q_first + qq) * dim + c0;
-            const uint32_t dst = smem_u32(sq + (size_t)qq * stride);
-            for (int v = lane; v < nv; v += 32) cp_async16(dst + 16u * v, src + 4 * v);
-        }
-        cp_async_wait_all();
+        if (lane == 0) mbar_expect_tx(bar, n_copies * row_bytes);
         __syncwarp();
+        if (have_row) {
+            const float* src = peer_rows ? peer_rows[my_row / rows_per_owner] + (size_t)(my_row % rows_per_owner) * dim + c0
+                                         : rows + (size_t)my_row * dim + c0;
+            tma_bulk_g2s(smem_u32(srow + (size_t)lane * stride), src, row_bytes, bar);
+        }
+        if (have_q)
+            tma_bulk_g2s(smem_u32(sq + (size_t)lane * stride), queries + (size_t)(q_first + lane) * dim + c0, row_bytes, bar);
+        while (!mbar_try_wait(bar, phase)) {}
+        phase ^= 1u;
         if (valid) {
             const float4* mine = reinterpret_cast<const float4*>(srow + (size_t)lane * stride);
             const float4* myq = reinterpret_cast<const float4*>(sq + (size_t)(q - q_first) * stride);
