@@ -348,7 +348,7 @@ void launch_tc_scan(gvdb_index* h, Workspace* ws, cudaStream_t st, uint32_t tile
     const uint32_t ngroups = (tile_hi - tile_lo + 3) / 4;
     const TcSplit sp = tc_split(h, ngroups, nq_pad);
     const uint32_t grid = sp.grid;
-    const uint32_t nlists = grid * 4;
+    const uint32_t nlists = grid * TC_EPI_WARPS;
     const size_t smem = (size_t)tc_qblocks(h->nchunk) * tc_qblock_bytes(h->nchunk);
     uint32_t rec_cap = 0;
     if (MODE == 0) {
@@ -357,7 +357,7 @@ void launch_tc_scan(gvdb_index* h, Workspace* ws, cudaStream_t st, uint32_t tile
         rec_cap = 4096;
         while (rec_cap < want && rec_cap < 65536) rec_cap <<= 1;
         ws->tc_recs.ensure((size_t)nlists * rec_cap * sizeof(uint2));
-        ws->list_counts.ensure((size_t)h->sm_count * 4 * 4);
+        ws->list_counts.ensure((size_t)h->sm_count * TC_EPI_WARPS * 4);
     }
     const int8_t* qexp = ws->qexp.as<int8_t>();
     const uint32_t* qpop = ws->qpop.as<uint32_t>();
@@ -367,7 +367,7 @@ void launch_tc_scan(gvdb_index* h, Workspace* ws, cudaStream_t st, uint32_t tile
     const double seg_rows = (double)(tile_hi - tile_lo) * 32.0;
     {
     Timed t(h, ws, st, K_TCSCAN, seg_rows * h->nchunk * 16.0 * sp.qslices,
-            seg_rows * (double)nq_pad * (h->nchunk * 128.0 + 32.0));
+            seg_rows * (double)nq_pad * (h->nchunk * 128.0 + 64.0));
 #define GVDB_TC_CASE(N)                                                                              \
     case N: {                                                                                        \
         static bool attr = false;                                                                    \
@@ -383,6 +383,7 @@ void launch_tc_scan(gvdb_index* h, Workspace* ws, cudaStream_t st, uint32_t tile
     }
     switch (h->nchunk) {
         GVDB_TC_CASE(1) GVDB_TC_CASE(2) GVDB_TC_CASE(3) GVDB_TC_CASE(4) GVDB_TC_CASE(6) GVDB_TC_CASE(8) GVDB_TC_CASE(12)
+        GVDB_TC_CASE(16) GVDB_TC_CASE(24)
         default: fail(GVDB_ERR_INDEX, "tcgen05 scan: unsupported code width");
     }
 #undef GVDB_TC_CASE

@@ -2,42 +2,45 @@
 //
 // Used when a corpus pass serves a large query tile (>= 64 queries), where the scan really is a
 // dense contraction: rows x queries x dim.  The CUDA-core kernel (scan_kernel) is then bound by
-// the integer pipes (16 popc + 64 LOP3 per clk per SM); tcgen05.mma.kind::i8 does 8192 MAC/clk/SM
-// (measured with tools/mma_floor.cu: 64 clk per M128 x N128 x K32 MMA, A in TMEM or shared memory,
-// any shared-memory layout, identical for kind::f8f6f4).
+// the integer pipes (16 popc + 64 LOP3 per clk per SM).  A 1-bit code needs no more than 4 bits
+// per element on the tensor core, so the contraction runs on the FP4 path:
+// tcgen05.mma.kind::mxf4 (e2m1 operands, one UE8M0 scale per 32 elements, all scales 1.0, f32
+// accumulation).  Measured with tools/mxf4_probe.cu: 76 clk per M128 x N128 x K64 MMA with A in
+// TMEM = 13.8k MAC/clk/SM; kind::i8 and kind::f8f6f4 do 8.2k (tools/mma_floor.cu: 64 clk per K32).
 //
-// Exactness.  Row codes are expanded on chip to A in {0,-128} (int8), query codes are expanded
-// once per batch to B in {+1,-1} (int8, +1 where the query bit is 1).  Over the code bits,
-//     S = n11 - n10,   sum_k A_k * B_k = -128 * S        (int32 accumulation, exact)
-//     hamming = n10 + n01 = popc(q) - S                  (popc(q) = n11 + n01)
-// so hamming < tau  <=>  S + (tau - popc(q)) > 0.  Pad bits are 0 in A and contribute nothing.
-// The per-query bias v = tau - popc(q) is added ON the tensor core by one extra K=32 MMA per
-// accumulator block (A = 32 x -128 per row, B = 32 int8 digits summing to v), so the accumulator
-// is D = -128 * (S + v), a survivor is simply D < 0, and the epilogue is a pure sign test on
-// registers (a per-element threshold load from shared memory measured 3x slower).
-// -128 rather than 1 because it is the byte's top bit: one row word expands with a LEFT shift
-// (which the compiler may issue on the FMA pipe as IMAD.SHL) plus one LOP3 per output word,
-//     out[8*w + i] = (code_word[w] << (7 - i)) & 0x80808080,
-// so the expansion is spread over two issue pipes.  The K order this implies is a fixed
-// permutation of the code bits applied to rows and queries alike (Hamming distance is invariant).
+// Exactness.  Row codes are expanded on chip to A in {0, 1.0} (nibbles 0x0 / 0x2), query codes
+// once per batch to B in {-1.0, +1.0} (0xA where the query bit is 1, 0x2 where it is 0).  With
+// S = n11 - n10 over the code bits,  sum_k A_k * B_k = -S  and  hamming = popc(q) - S, so
+// hamming < tau  <=>  S + (tau - popc(q)) > 0.  All products and partial sums are integers far
+// below 2^24: the f32 accumulation is exact.  Pad bits are 0 in A and contribute nothing.
+// The per-query bias v = tau - popc(q) is added ON the tensor core by one extra K=64 MMA per
+// accumulator block: A = 64 x 1.0 per row with scale factors (16, 1) for its two 32-element
+// halves, B = 32 coarse + 31 fine e2m1 digits with 16 * coarse + fine = -v, plus one digit 0.5.
+// The accumulator is then D = -(S + v) + 0.5: never zero, and a survivor is simply D < 0, so the
+// epilogue is a pure sign test on registers (a per-element threshold load from shared memory
+// measured 3x slower).
+// One row word expands with a shift + a LOP3 per output word,
+//     out[4*w + i] = ((code_word[w] >> i) << 1) & 0x22222222       (nibble j <- code bit 4j + i),
+// a fixed permutation of the code bits applied to rows and queries alike (Hamming distance is
+// invariant to it).
 //
 // Work decomposition.  item = (query slice, row slice).  A query slice is up to tc_qblocks() blocks
-// of 128 queries whose expanded codes (+ bias digits) stay RESIDENT in shared memory (200 KB at
-// 768 bits: two blocks; 196 KB at 1536 bits: one block) for the whole item; the item's rows stream
-// through TMEM as the A operand, 128 at a time.  (Streaming the queries through a shared-memory ring instead needs 64 B/clk/SM from L2,
-// more than the L2 delivers to 148 SMs at once: that version measured 47 % of the MMA floor.)
+// of 128 queries whose expanded codes (+ bias digits) stay RESIDENT in shared memory (3 blocks x
+// 52 KB at 768 bits) for the whole item; the item's rows stream through TMEM as the A operand, 128
+// at a time.  (Streaming the queries through a shared-memory ring instead needs more L2->SM
+// bandwidth than the L2 delivers to 148 SMs at once: that version measured 47 % of the MMA floor.)
 //
 // Warp roles per CTA (one CTA per SM, persistent over items):
 //   warps 0-3  expanders: lane = row.  Load the row's code (coalesced, blocked layout, next group
 //              prefetched), expand it and write it into TMEM as the A operand (tcgen05.st).  A is a
-//              ring of two slots with their own ready/free barriers; a group goes through it in 2
-//              phases (4 for 1024/1536-bit codes), so rewriting one slot overlaps the MMAs that
-//              still read the other.
-//   warps 4-7  epilogue: read the int32 accumulators back (tcgen05.ld), sign-test them and append
+//              ring of two slots with their own ready/free barriers; a group goes through it in
+//              phases, so rewriting one slot overlaps the MMAs that still read the other.
+//   warps 4-7  epilogue: read the f32 accumulators back (tcgen05.ld), sign-test them and append
 //              survivors to warp-private record lists (MODE 0), or write every distance (MODE 1).
-//   warp 8     warp-uniform control flow, one elected lane: TMA bulk loads of the query slice, then tcgen05.mma issue
-//              (M=128, N=128, K=32; A from TMEM, B from shared memory, D in TMEM, 2 buffers).
-//   mbarriers  b_full/b_free, a_ready/a_free per K half, acc_full/acc_empty per accumulator
+//   warp 8     warp-uniform control flow, one elected lane: TMA bulk loads of the query slice, then
+//              tcgen05.mma issue (M=128, N=128, K=64; A from TMEM, B from shared memory, D in TMEM,
+//              one accumulator buffer per resident block).
+//   mbarriers  b_full/b_free, a_ready/a_free per A slot, acc_full/acc_empty per accumulator
 //              buffer; tcgen05.commit signals MMA completion.
 #pragma once
 #include <cuda_runtime.h>
@@ -49,23 +52,39 @@ namespace gvdb {
 
 constexpr int TC_ROWS = 128;        // rows per group (UMMA M)
 constexpr int TC_NQ = 128;          // queries per accumulator block (UMMA N)
-constexpr int TC_KSTAGE = 128;      // K bytes per 16 KB query sub-block = one 16-byte code chunk
+constexpr int TC_KSTAGE = 128;      // K bytes per 16 KB query sub-block = 256 e2m1 elements = two 16-byte code chunks
 constexpr int TC_STAGE_BYTES = TC_NQ * TC_KSTAGE;   // 16 KB
-// Resident query blocks per item (each has its own TMEM accumulator buffer): two while they fit
-// the 227 KB of shared memory (K <= 768 bits), one for 1024- and 1536-bit codes.
-__host__ __device__ constexpr int tc_qblocks(int nchunk) { return nchunk <= 6 ? 2 : 1; }
-// The A operand lives in a ring of two TMEM slots of tc_slot_chunks() code chunks (32 columns
-// each); a row group is expanded and consumed in phases, phase ph using slot ph & 1.
-__host__ __device__ constexpr int tc_slot_chunks(int nchunk) { return nchunk <= 6 ? (nchunk + 1) / 2 : nchunk / 4; }
-__host__ __device__ constexpr bool tc_supported_chunks(int nchunk) {
-    return nchunk == 1 || nchunk == 2 || nchunk == 3 || nchunk == 4 || nchunk == 6 || nchunk == 8 || nchunk == 12;
-}
-constexpr int TC_THREADS = 288;     // 4 expander warps + 4 epilogue warps + loader/MMA-issuer warp
-constexpr uint32_t TC_TMEM_COLS = 512;
-constexpr int TC_BIAS_BYTES = TC_NQ * 32;           // 4 KB: one K=32 slice of per-query bias digits
+constexpr int TC_BIAS_BYTES = TC_NQ * 32;           // 4 KB: one K=64 slice of per-query bias digits (e2m1)
+constexpr int TC_MAX_QBLOCKS = 3;                   // accumulator buffers that fit TMEM next to A
+__host__ __device__ constexpr int tc_subblocks(int nchunk) { return (nchunk + 1) / 2; }
 __host__ __device__ constexpr size_t tc_qblock_bytes(int nchunk) {
-    return (size_t)nchunk * TC_STAGE_BYTES + TC_BIAS_BYTES;
+    return (size_t)tc_subblocks(nchunk) * TC_STAGE_BYTES + TC_BIAS_BYTES;
 }
+// The A operand lives in a ring of two TMEM slots of tc_slot_chunks() code chunks (16 columns
+// each); a row group is expanded and consumed in phases, phase ph using slot ph & 1.  Up to 1536
+// bits the ring holds the whole group (two phases); longer codes go through it in 8 phases.
+__host__ __device__ constexpr int tc_slot_chunks(int nchunk) {
+    return nchunk <= 12 ? (nchunk + 1) / 2 : (nchunk % 3 == 0 ? 3 : 2);
+}
+__host__ __device__ constexpr int tc_phases(int nchunk) { return (nchunk + tc_slot_chunks(nchunk) - 1) / tc_slot_chunks(nchunk); }
+// Resident query blocks per item (each has its own TMEM accumulator buffer): what fits 216 KB of
+// shared memory and the TMEM columns left next to the A ring, at most three; a single block when
+// the ring cannot hold the whole row group (every block would need all the phases again).
+__host__ __device__ constexpr int tc_qblocks(int nchunk) {
+    int q = (int)((216 * 1024) / tc_qblock_bytes(nchunk));
+    const int by_tmem = (512 - 16 - 2 * tc_slot_chunks(nchunk) * 16) / TC_NQ;
+    if (by_tmem < q) q = by_tmem;
+    if (TC_MAX_QBLOCKS < q) q = TC_MAX_QBLOCKS;
+    if (tc_phases(nchunk) > 2) q = q < 1 ? q : 1;
+    return q;
+}
+__host__ __device__ constexpr bool tc_supported_chunks(int nchunk) {
+    return nchunk == 1 || nchunk == 2 || nchunk == 3 || nchunk == 4 || nchunk == 6 || nchunk == 8 || nchunk == 12 ||
+           nchunk == 16 || nchunk == 24;
+}
+constexpr int TC_EPI_WARPS = 8;      // two sets of four epilogue warps, alternating accumulator blocks
+constexpr int TC_THREADS = 32 * (4 + TC_EPI_WARPS + 1);   // 4 expander warps + epilogue warps + loader/MMA-issuer warp
+constexpr uint32_t TC_TMEM_COLS = 512;
 
 // ---- PTX wrappers ------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
@@ -94,14 +113,15 @@ __device__ __forceinline__ void tc_alloc(uint32_t smem_dst, uint32_t ncols) {
 __device__ __forceinline__ void tc_dealloc(uint32_t taddr, uint32_t ncols) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(taddr), "r"(ncols) : "memory");
 }
-// D[tmem] (+)= A[tmem] * B[smem desc], int8 x int8 -> int32
-__device__ __forceinline__ void tc_mma_i8_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc,
-                                             uint32_t idesc, uint32_t accumulate) {
+// D[tmem] (+)= A[tmem] * B[smem desc], e2m1 x e2m1 -> f32, one UE8M0 scale per 32 elements of K
+// (sfa / sfb: TMEM addresses of the scale words; byte 0 scales K[0,32), byte 1 scales K[32,64)).
+__device__ __forceinline__ void tc_mma_mxf4_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                               uint32_t sfa_tmem, uint32_t sfb_tmem, uint32_t accumulate) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, p;\n\t}"
-        :: "r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::mxf4.block_scale.block32 [%0], [%1], %2, %3, [%4], [%5], p;\n\t}"
+        :: "r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(sfa_tmem), "r"(sfb_tmem), "r"(accumulate) : "memory");
 }
 // 32 lanes x 8 columns per call (each thread: its own lane, 8 consecutive 32-bit columns)
 __device__ __forceinline__ void tc_st8(uint32_t taddr, const uint32_t (&v)[8]) {
@@ -129,40 +149,53 @@ __device__ __forceinline__ uint64_t tc_smem_desc(uint32_t smem_addr, uint32_t lb
     return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) |
            ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46);
 }
-// UMMA instruction descriptor (cute::UMMA::InstrDescriptor): D=S32, A=B=INT8, K-major both.
-__host__ __device__ constexpr uint32_t tc_idesc_i8(int M, int N) {
-    return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+// UMMA block-scaled instruction descriptor (cute::UMMA::InstrDescriptorBlockScaled): A=B=E2M1,
+// K-major both, UE8M0 scales, scale-factor ids 0, dense K=64.
+__host__ __device__ constexpr uint32_t tc_idesc_mxf4(int M, int N) {
+    return (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | (1u << 23) | ((uint32_t)(M >> 4) << 24);
 }
-constexpr uint32_t TC_A_BIT4 = 0x80808080u;   // A = -128 where the code bit is set
+constexpr uint32_t TC_A_ONE8 = 0x22222222u;   // eight e2m1 1.0
+constexpr uint32_t TC_SF_ONE = 0x7F7F7F7Fu;   // UE8M0 1.0 in every byte
+constexpr uint32_t TC_SF_BIAS_A = 0x7F7F7F83u;  // byte 0 = 16.0 (K[0,32) of the bias MMA), byte 1 = 1.0
+constexpr int TC_BIAS_COARSE = 16;
+
+// e2m1 nibble of a magnitude in {0, 0.5, 1, 1.5, 2, 3, 4, 6} given as 2 * value
+__host__ __device__ inline uint32_t tc_e2m1_nibble(int twice, bool negative) {
+    const uint32_t mag = twice == 0 ? 0u : twice == 1 ? 1u : twice == 2 ? 2u : twice == 3 ? 3u : twice == 4 ? 4u
+                       : twice == 6 ? 5u : twice == 8 ? 6u : 7u /* twice == 12 */;
+    return mag | ((negative && twice) ? 8u : 0u);
+}
+// largest integer in {6, 4, 3, 2, 1} not above mag (mag >= 1)
+__host__ __device__ inline int tc_e2m1_int_floor(int mag) { return mag >= 6 ? 6 : mag == 5 ? 4 : mag; }
 
 // ---- query pre-expansion ---------------------------------------------------------------------------
-// qpack (code words + tau, as produced by ingest_kernel<QUERY>) -> qexp, int8 +-1 in the exact byte
-// order the resident blocks need:  sub-block (qb, ks) of 16 KB at qb*tc_qblock_bytes + ks*16384 (the
-// last 4 KB of a query block hold the bias digits, written by tc_bias_kernel), inside a sub-block
+// qpack (code words + tau, as produced by the query prep kernel) -> qexp, e2m1 +-1.0 nibbles in the
+// exact byte order the resident blocks need:  sub-block (qb, sb) of 16 KB at
+// qb*tc_qblock_bytes + sb*16384 (the last 4 KB of a query block hold the bias digits, written by
+// tc_bias_kernel), inside a sub-block
 //   offset(n, kk) = (n/8)*1024 + (kk/16)*128 + (n%8)*16 + (kk%16),  n = query in block, kk = K byte
-// K byte k of a query  <->  code bit (w*32 + 8*b + i) with  k = (8*w + i)*4 + b   (see header).
+// K element e of a query  <->  code bit 32*w + 4*j + i  with  e = (4*w + i)*8 + j  (see header);
+// element e sits in K byte e/2, low nibble for even e.  Query bit 1 -> -1.0 (0xA), 0 -> +1.0 (0x2).
 // Queries beyond nq (padding up to a multiple of 128) are all zero.  Also writes popc(q).
 __global__ void tc_expand_queries_kernel(const uint32_t* __restrict__ qpack, int qs, int nchunk, uint32_t nq,
                                          uint32_t nq_pad, int8_t* __restrict__ qexp,
                                          uint32_t* __restrict__ qpop) {
     const uint32_t q = blockIdx.x;                 // one CTA per (padded) query
     if (q >= nq_pad) return;
-    const int K = nchunk * 128;
     const uint32_t qb = q / TC_NQ, n = q % TC_NQ;
+    const int nwords_out = tc_subblocks(nchunk) * (TC_KSTAGE / 4);   // 32-bit output words per query (incl. pad)
     uint32_t pop = 0;
-    for (int k4 = threadIdx.x; k4 < K / 4; k4 += blockDim.x) {   // one 32-bit output word (4 K bytes)
-        const int w = k4 >> 3, i = k4 & 7;
+    for (int o = threadIdx.x; o < nwords_out; o += blockDim.x) {   // output word o = 4*w + i: 8 elements, 4 K bytes
+        const int w = o >> 2, i = o & 3;
         uint32_t out = 0;
-        if (q < nq) {
+        if (q < nq && w < nchunk * 4) {
             const uint32_t word = qpack[(size_t)q * qs + w];
-            const uint32_t bits = (word >> i) & 0x01010101u;            // byte b = code bit 8b+i
-#pragma unroll
-            for (int b = 0; b < 4; ++b) out |= (((bits >> (8 * b)) & 1u) ? 0x01u : 0xFFu) << (8 * b);
+            out = TC_A_ONE8 | (((word >> i) & 0x11111111u) << 3);       // 0x2 -> 0xA where the bit is set
             if (i == 0) pop += __popc(word);
         }
-        const int k = k4 * 4;
-        const int ks = k / TC_KSTAGE, kk = k % TC_KSTAGE;
-        const size_t off = (size_t)qb * tc_qblock_bytes(nchunk) + (size_t)ks * TC_STAGE_BYTES + (n / 8) * 1024 + (kk / 16) * 128 + (n % 8) * 16 + (kk % 16);
+        const int kb = o * 4;
+        const int sb = kb / TC_KSTAGE, kk = kb % TC_KSTAGE;
+        const size_t off = (size_t)qb * tc_qblock_bytes(nchunk) + (size_t)sb * TC_STAGE_BYTES + (n / 8) * 1024 + (kk / 16) * 128 + (n % 8) * 16 + (kk % 16);
         *reinterpret_cast<uint32_t*>(qexp + off) = out;
     }
     // block reduce popcount (blockDim <= 256)
@@ -178,9 +211,11 @@ __global__ void tc_expand_queries_kernel(const uint32_t* __restrict__ qpack, int
 }
 
 // Per-query bias digits for the current thresholds: v = tau - popc(q) (v = K+1 when tau is
-// TAU_ALL: everything passes; v = -(K+1) for padding queries: nothing passes), written as 32 int8
-// digits in [-127,127] summing to v, in the K-major core-matrix order of a 128 x 32 B block:
-//   offset(n, kk) = (n/8)*256 + (kk/16)*128 + (n%8)*16 + (kk%16).   zero_bias: v = 0 (MODE 1).
+// TAU_ALL: everything passes; v = -(K+1) for padding queries: nothing passes; zero_bias: v = 0,
+// MODE 1).  The bias MMA must add -v + 0.5: 64 e2m1 digits per query, elements [0,32) scaled by
+// 16 (coarse), [32,64) by 1 (fine): 16 * sum(coarse) + sum(fine) = -v, and fine digit 0 is the
+// 0.5.  K-major core-matrix order of a 128 x 32 B block:
+//   offset(n, kb) = (n/8)*256 + (kb/16)*128 + (n%8)*16 + (kb%16),  element e in byte e/2.
 __global__ void tc_bias_kernel(const uint32_t* __restrict__ qpack, int qs, int nchunk,
                                const uint32_t* __restrict__ qpop, uint32_t nq, uint32_t nq_pad,
                                int8_t* __restrict__ qexp, int32_t* __restrict__ qbias, int zero_bias) {
@@ -197,13 +232,25 @@ __global__ void tc_bias_kernel(const uint32_t* __restrict__ qpack, int qs, int n
     if (zero_bias) v = 0;
     qbias[q] = v;
     const uint32_t qb = q / TC_NQ, n = q % TC_NQ;
-    int8_t* blk = qexp + (size_t)qb * tc_qblock_bytes(nchunk) + (size_t)nchunk * TC_STAGE_BYTES;
-    int rest = v;
-    for (int kk = 0; kk < 32; ++kk) {
-        int d = rest > 127 ? 127 : (rest < -127 ? -127 : rest);
-        rest -= d;
-        blk[(n / 8) * 256 + (kk / 16) * 128 + (n % 8) * 16 + (kk % 16)] = (int8_t)d;
+    uint8_t* blk = reinterpret_cast<uint8_t*>(qexp) + (size_t)qb * tc_qblock_bytes(nchunk) + (size_t)tc_subblocks(nchunk) * TC_STAGE_BYTES;
+    const int t = -v;
+    const bool neg = t < 0;
+    int coarse = (neg ? -t : t) / TC_BIAS_COARSE;          // magnitudes; both parts carry t's sign
+    int fine = (neg ? -t : t) % TC_BIAS_COARSE;
+    uint32_t nib[64];
+    for (int e = 0; e < 32; ++e) {                          // coarse digits, integers from {6,4,3,2,1}
+        const int d = coarse > 0 ? tc_e2m1_int_floor(coarse) : 0;
+        coarse -= d;
+        nib[e] = tc_e2m1_nibble(2 * d, neg);
     }
+    nib[32] = tc_e2m1_nibble(1, false);                     // +0.5
+    for (int e = 33; e < 64; ++e) {
+        const int d = fine > 0 ? tc_e2m1_int_floor(fine) : 0;
+        fine -= d;
+        nib[e] = tc_e2m1_nibble(2 * d, neg);
+    }
+    for (int kb = 0; kb < 32; ++kb)
+        blk[(n / 8) * 256 + (kb / 16) * 128 + (n % 8) * 16 + (kb % 16)] = (uint8_t)(nib[2 * kb] | (nib[2 * kb + 1] << 4));
 }
 
 // ---- the scan ------------------------------------------------------------------------------------------
@@ -219,25 +266,29 @@ tc_scan_kernel(const uint4* __restrict__ codes, const uint32_t* __restrict__ liv
                uint32_t* __restrict__ dist_out, uint64_t dist_stride, uint64_t n_rows, int dbg = 0,
                unsigned long long* __restrict__ prof = nullptr) {
     constexpr int QB = tc_qblocks(NCHUNK);     // resident query blocks
+    constexpr int NBUF = QB < 2 ? 2 : QB;      // accumulator buffers (block it uses buffer it % NBUF)
     constexpr int SC = tc_slot_chunks(NCHUNK); // chunks per A slot
     constexpr int PH = (NCHUNK + SC - 1) / SC; // phases per row group
-    constexpr int A_COLS = 2 * SC * 32;        // TMEM columns of the A ring (+8: the bias slice)
-    constexpr uint32_t IDESC = tc_idesc_i8(TC_ROWS, TC_NQ);
+    constexpr int CHUNK_COLS = 16;             // TMEM columns per expanded code chunk (128 e2m1 = 64 B per row)
+    constexpr int A_COLS = 2 * SC * CHUNK_COLS;   // TMEM columns of the A ring
+    // then: 8 columns bias slice (64 x 1.0), 4 columns scale words 1.0, 4 columns the bias MMA's A scales
+    constexpr uint32_t IDESC = tc_idesc_mxf4(TC_ROWS, TC_NQ);
     constexpr uint32_t QBLOCK_BYTES = (uint32_t)tc_qblock_bytes(NCHUNK);
-    static_assert(A_COLS + 8 + 2 * TC_NQ <= 512, "TMEM budget");
-    static_assert(QB * tc_qblock_bytes(NCHUNK) <= 220 * 1024, "shared memory budget");
+    static_assert(QB >= 1, "the resident query block must fit shared memory");
+    static_assert(A_COLS + 16 + NBUF * TC_NQ <= 512, "TMEM budget");
+    static_assert(QB * tc_qblock_bytes(NCHUNK) <= 216 * 1024, "shared memory budget");
 
     extern __shared__ __align__(1024) uint8_t smem[];      // QB resident query blocks
     __shared__ int32_t s_bias[QB * TC_NQ];                   // MODE 1 only
     __shared__ uint32_t s_pop[QB * TC_NQ];
-    __shared__ __align__(8) uint64_t bars[10];
+    __shared__ __align__(8) uint64_t bars[6 + 2 * TC_MAX_QBLOCKS];
     __shared__ uint32_t s_tmem_base;
     const uint32_t bar0 = smem_u32(bars);
     const uint32_t b_full = bar0, b_free = bar0 + 8;
     auto a_ready = [&](int h) { return bar0 + 8u * (2 + h); };
     auto a_free = [&](int h) { return bar0 + 8u * (4 + h); };
     auto acc_full = [&](int b) { return bar0 + 8u * (6 + b); };
-    auto acc_empty = [&](int b) { return bar0 + 8u * (8 + b); };
+    auto acc_empty = [&](int b) { return bar0 + 8u * (6 + TC_MAX_QBLOCKS + b); };
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t nqb = nq_pad / TC_NQ;
@@ -247,16 +298,19 @@ tc_scan_kernel(const uint4* __restrict__ codes, const uint32_t* __restrict__ liv
     if (threadIdx.x == 0) {
         mbar_init(b_full, 1); mbar_init(b_free, 1);
         for (int h = 0; h < 2; ++h) { mbar_init(a_ready(h), 4); mbar_init(a_free(h), 1); }
-        for (int b = 0; b < 2; ++b) { mbar_init(acc_full(b), 1); mbar_init(acc_empty(b), 4); }
+        for (int b = 0; b < NBUF; ++b) { mbar_init(acc_full(b), 1); mbar_init(acc_empty(b), 4); }
         fence_mbar_init();
     }
-    if (warp == 8) tc_alloc(smem_u32(&s_tmem_base), TC_TMEM_COLS);
+    constexpr int MMA_WARP = 4 + TC_EPI_WARPS;
+    if (warp == MMA_WARP) tc_alloc(smem_u32(&s_tmem_base), TC_TMEM_COLS);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = s_tmem_base;
-    const uint32_t tmem_a = tmem;                 // columns [0, A_COLS): codes; [A_COLS, A_COLS+8): bias slice
-    const uint32_t tmem_d = tmem + A_COLS + 8;    // two accumulator buffers of TC_NQ columns
+    const uint32_t tmem_a = tmem;                 // columns [0, A_COLS): the A ring; [A_COLS, A_COLS+8): bias slice
+    const uint32_t tmem_sf_one = tmem + A_COLS + 8;      // 4 columns of scale words 1.0
+    const uint32_t tmem_sf_bias = tmem + A_COLS + 12;    // 4 columns: the bias MMA's A scales (16, 1)
+    const uint32_t tmem_d = tmem + A_COLS + 16;          // NBUF accumulator buffers of TC_NQ columns
     const uint32_t lane_taddr = (uint32_t)((warp & 3) * 32) << 16;
 
     unsigned long long pw[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -278,8 +332,12 @@ tc_scan_kernel(const uint4* __restrict__ codes, const uint32_t* __restrict__ liv
         {
             uint32_t ones[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) ones[i] = TC_A_BIT4;
-            tc_st8(tmem_a + lane_taddr + A_COLS, ones);     // A slice of the bias MMA
+            for (int i = 0; i < 8; ++i) ones[i] = TC_A_ONE8;
+            tc_st8(tmem_a + lane_taddr + A_COLS, ones);     // A slice of the bias MMA: 64 x 1.0
+#pragma unroll
+            for (int i = 0; i < 8; ++i) ones[i] = i < 4 ? TC_SF_ONE : TC_SF_BIAS_A;
+            tc_st8(tmem_sf_one + lane_taddr, ones);         // scale words (read by every MMA)
+            tc_wait_st();
         }
         auto load_codes = [&](uint32_t g, uint4 (&r)[NCHUNK]) {
             const uint32_t tile = tile_lo + g * 4 + warp;
@@ -298,11 +356,15 @@ tc_scan_kernel(const uint4* __restrict__ codes, const uint32_t* __restrict__ liv
                 if (c < c_lo || c >= c_hi) continue;
                 const uint32_t w4[4] = {r[c].x, r[c].y, r[c].z, r[c].w};
 #pragma unroll
-                for (int wi = 0; wi < 4; ++wi) {
+                for (int wp = 0; wp < 2; ++wp) {                  // two code words -> 8 columns (one K=64 MMA)
                     uint32_t v[8];
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) v[i] = (w4[wi] << (7 - i)) & TC_A_BIT4;
-                    tc_st8(tmem_a + lane_taddr + (uint32_t)(h * SC * 32 + ((c - c_lo) * 4 + wi) * 8), v);
+                    for (int i = 0; i < 8; ++i) {
+                        const uint32_t w = w4[wp * 2 + (i >> 2)];
+                        const int sh = i & 3;                        // nibble j <- code bit 4j + sh
+                        v[i] = (sh == 0 ? (w << 1) : (w >> (sh - 1))) & TC_A_ONE8;
+                    }
+                    tc_st8(tmem_a + lane_taddr + (uint32_t)(h * SC * CHUNK_COLS + ((c - c_lo) * 2 + wp) * 8), v);
                 }
             }
             tc_wait_st();
@@ -328,38 +390,40 @@ tc_scan_kernel(const uint4* __restrict__ codes, const uint32_t* __restrict__ liv
         }
         if (prof && blockIdx.x == 0 && threadIdx.x == 0)
             for (int i = 0; i < 4; ++i) prof[i] = pw[i];
-    } else if (warp < 8) {
+    } else if (warp < MMA_WARP) {
         // ===================== epilogue: accumulators -> survivors / distances =====================
-        const int ew = warp - 4;
-        uint32_t full_phase[2] = {0, 0};
-        uint32_t it = 0;                          // running accumulator-block counter (buffer = it & 1)
+        // two sets of four warps (set s takes the accumulator blocks with it % 2 == s): reading and
+        // sign-testing a block takes about as long as the FP4 MMAs that produce it
+        const int ew = warp - 4;                  // 0 .. TC_EPI_WARPS-1; TMEM lane quarter = ew & 3
+        const uint32_t my_set = (uint32_t)(ew >> 2);
+        uint32_t it = 0;                          // running accumulator-block counter (buffer = it % NBUF)
         // Survivor records of this warp: a private list, slots handed out with ballot + popc from a
         // register counter.  No shared memory and no atomics in the epilogue.
-        uint2* my_list = recs + (size_t)(blockIdx.x * 4 + ew) * rec_cap;
+        uint2* my_list = recs + (size_t)(blockIdx.x * TC_EPI_WARPS + ew) * rec_cap;
         uint32_t my_count = 0;
         const uint32_t lane_lt = (1u << lane) - 1u;
         for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x) {
             uint32_t qb0, nb, g_lo, g_hi;
             item_range(item, qb0, nb, g_lo, g_hi);
             if (MODE == 1) {
-                asm volatile("bar.sync 1, 128;" ::: "memory");      // previous item's readers are done
-                for (uint32_t i = threadIdx.x - 128; i < nb * TC_NQ; i += 128) {
+                asm volatile("bar.sync 1, %0;" :: "n"(32 * TC_EPI_WARPS) : "memory");      // previous item's readers are done
+                for (uint32_t i = threadIdx.x - 128; i < nb * TC_NQ; i += 32 * TC_EPI_WARPS) {
                     const uint32_t q = qb0 * TC_NQ + i;
                     s_bias[i] = qbias[q];
                     s_pop[i] = q < nq ? qpop[q] : 0u;
                 }
-                asm volatile("bar.sync 1, 128;" ::: "memory");
+                asm volatile("bar.sync 1, %0;" :: "n"(32 * TC_EPI_WARPS) : "memory");
             }
             for (uint32_t g = g_lo; g < g_hi; ++g) {
-                const uint32_t tile = tile_lo + g * 4 + ew;
+                const uint32_t tile = tile_lo + g * 4 + (ew & 3);
                 const bool in_range = tile < tile_hi;
                 const uint32_t row = tile * 32u + lane;
                 const bool alive = in_range && ((live[in_range ? tile : tile_lo] >> lane) & 1u);
                 for (uint32_t blk = 0; blk < nb; ++blk, ++it) {
-                    const uint32_t b = it & 1u;
+                    if (TC_EPI_WARPS == 8 && (it & 1u) != my_set) continue;
+                    const uint32_t b = it % NBUF;
                     const uint32_t qbase = (qb0 + blk) * TC_NQ, qloc = blk * TC_NQ;
-                    { TC_PROF_T0(); mbar_wait(acc_full(b), full_phase[b]); TC_PROF_ADD(0); }
-                    full_phase[b] ^= 1u;
+                    { TC_PROF_T0(); mbar_wait(acc_full(b), (it / NBUF) & 1u); TC_PROF_ADD(0); }   // buffer b's (it / NBUF)-th use
                     tc_fence_after();
                     TC_PROF_T0();
 #pragma unroll 1
@@ -370,8 +434,8 @@ tc_scan_kernel(const uint4* __restrict__ codes, const uint32_t* __restrict__ liv
                         tc_ld32(col0 + 32, v1);
                         tc_wait_ld();
                         if (MODE == 0) {
-                            // D = -128 (S + bias): a survivor has D < 0.  Collect the 64 sign bits with
-                            // one funnel shift per element (four independent chains); survivors are rare.
+                            // D = -(S + bias) + 0.5 (f32): a survivor has D < 0.  Collect the 64 sign bits
+                            // with one funnel shift per element (four independent chains); survivors are rare.
                             uint32_t ma = 0, mb = 0, mc = 0, md = 0;
 #pragma unroll
                             for (int j = 0; j < 16; ++j) {
@@ -400,8 +464,8 @@ tc_scan_kernel(const uint4* __restrict__ codes, const uint32_t* __restrict__ liv
                             for (int j = 0; j < 64; ++j) {
                                 const uint32_t q = qbase + half * 64 + j;
                                 const uint32_t ql = qloc + half * 64 + j;
-                                const int32_t dv = (int32_t)(j < 32 ? v0[j & 31] : v1[j & 31]) >> 7;   // -(S + bias)
-                                // hamming = popc(q) - S = popc(q) + bias + D/128
+                                const int32_t dv = (int32_t)(__uint_as_float(j < 32 ? v0[j & 31] : v1[j & 31]) - 0.5f);   // -(S + bias)
+                                // hamming = popc(q) - S = popc(q) + bias + (D - 0.5)
                                 if (q < nq && in_range && row < n_rows)
                                     dist_out[(size_t)q * dist_stride + row] = (uint32_t)((int32_t)s_pop[ql] + s_bias[ql] + dv);
                             }
@@ -415,7 +479,7 @@ tc_scan_kernel(const uint4* __restrict__ codes, const uint32_t* __restrict__ liv
             }
         }
         if (MODE == 0 && lane == 0) {
-            list_counts[blockIdx.x * 4 + ew] = min(my_count, rec_cap);
+            list_counts[blockIdx.x * TC_EPI_WARPS + ew] = min(my_count, rec_cap);
             if (my_count > rec_cap) *overflow = 1u;
         }
         if (prof && blockIdx.x == 0 && threadIdx.x == 128)
@@ -424,7 +488,9 @@ tc_scan_kernel(const uint4* __restrict__ codes, const uint32_t* __restrict__ liv
         // ===================== query loader (TMA) + MMA issuer: warp 8, one elected lane issues =====================
         uint32_t bfull_phase = 0, bfree_phase = 0;
         uint32_t ready_phase[2] = {0, 0};
-        uint32_t empty_phase[2] = {1, 1};         // first use of each accumulator buffer passes
+        uint32_t empty_phase[NBUF];               // first use of each accumulator buffer passes
+#pragma unroll
+        for (int b = 0; b < NBUF; ++b) empty_phase[b] = 1u;
         uint32_t it = 0;
         bool first_item = true;
         const long long t_begin = prof ? clock64() : 0;
@@ -453,7 +519,7 @@ tc_scan_kernel(const uint4* __restrict__ codes, const uint32_t* __restrict__ liv
             bfull_phase ^= 1u;
             for (uint32_t g = g_lo; g < g_hi; ++g) {
                 for (uint32_t blk = 0; blk < nb; ++blk, ++it) {
-                    const uint32_t b = it & 1u;
+                    const uint32_t b = it % NBUF;
                     const bool last_blk = blk + 1 == nb;
                     { TC_PROF_T0(); mbar_wait(acc_empty(b), empty_phase[b]); TC_PROF_ADD(0); }
                     empty_phase[b] ^= 1u;
@@ -461,7 +527,7 @@ tc_scan_kernel(const uint4* __restrict__ codes, const uint32_t* __restrict__ liv
                     const uint64_t bdesc0 = tc_smem_desc(smem_u32(smem + blk * QBLOCK_BYTES), 128, 1024);
                     const uint32_t d_addr = tmem_d + b * TC_NQ;
 #pragma unroll
-                    for (int ks = 0; ks < NCHUNK; ++ks) {
+                    for (int ks = 0; ks < NCHUNK; ++ks) {              // one code chunk = 64 K bytes = two K=64 MMAs
                         const int ph = ks / SC, h = ph & 1, kc = ks % SC;   // phase, slot, chunk in slot
                         if (blk == 0 && kc == 0) {
                             { TC_PROF_T0(); mbar_wait(a_ready(h), ready_phase[h]); TC_PROF_ADD(1 + h); }
@@ -470,18 +536,20 @@ tc_scan_kernel(const uint4* __restrict__ codes, const uint32_t* __restrict__ liv
                         }
                         if (elect_one()) {
 #pragma unroll
-                            for (int j = 0; j < TC_KSTAGE / 32; ++j)      // the address field counts 16-byte units
-                                tc_mma_i8_ts(d_addr, tmem_a + (uint32_t)(h * SC * 32 + (kc * (TC_KSTAGE / 32) + j) * 8),
-                                             bdesc0 + (uint64_t)((ks * TC_STAGE_BYTES + j * 256) >> 4), IDESC, (ks | j) != 0 ? 1u : 0u);
+                            for (int j = 0; j < 2; ++j)                 // the address field counts 16-byte units
+                                tc_mma_mxf4_ts(d_addr, tmem_a + (uint32_t)(h * SC * CHUNK_COLS + (kc * 2 + j) * 8),
+                                               bdesc0 + (uint64_t)(((ks / 2) * TC_STAGE_BYTES + ((ks % 2) * 4 + j * 2) * 128) >> 4),
+                                               IDESC, tmem_sf_one, tmem_sf_one, (ks | j) != 0 ? 1u : 0u);
                             // this slot of A may be rewritten once the MMAs issued so far retire
                             if (last_blk && kc == SC - 1 && ks != NCHUNK - 1) tc_commit(a_free(h));
                         }
                         __syncwarp();
                     }
                     if (elect_one()) {
-                        // bias: D += (-128)(128 x 32) * digits(128 queries x 32)
-                        tc_mma_i8_ts(d_addr, tmem_a + A_COLS,
-                                     tc_smem_desc(smem_u32(smem + blk * QBLOCK_BYTES + NCHUNK * TC_STAGE_BYTES), 128, 256), IDESC, 1u);
+                        // bias: D += 1.0(128 x 64, scales 16 | 1) * digits(128 queries x 64) = -v + 0.5
+                        tc_mma_mxf4_ts(d_addr, tmem_a + A_COLS,
+                                       tc_smem_desc(smem_u32(smem + blk * QBLOCK_BYTES + tc_subblocks(NCHUNK) * TC_STAGE_BYTES), 128, 256),
+                                       IDESC, tmem_sf_bias, tmem_sf_one, 1u);
                         if (last_blk) tc_commit(a_free(((NCHUNK - 1) / SC) & 1));   // the last phase's slot
                         tc_commit(acc_full(b));
                     }
@@ -503,7 +571,7 @@ tc_scan_kernel(const uint4* __restrict__ codes, const uint32_t* __restrict__ liv
 #undef TC_PROF_ADD
     tc_fence_before();
     __syncthreads();
-    if (warp == 8) {
+    if (warp == MMA_WARP) {
         __syncwarp();
         tc_dealloc(tmem, TC_TMEM_COLS);
     }

@@ -57,7 +57,7 @@ int main(int argc, char** argv) {
     CK(cudaMalloc(&d_ref, dist_bytes)); CK(cudaMalloc(&d_tc, dist_bytes));
     CK(cudaMalloc(&d_qexp, (size_t)(nq_pad / TC_NQ) * tc_qblock_bytes(NCHUNK))); CK(cudaMalloc(&d_qbias, nq_pad * 4)); CK(cudaMalloc(&d_qpop, nq_pad * 4));
     const uint32_t cap = 8192; const uint32_t rec_cap = 1u << 17;
-    CK(cudaMalloc(&d_recs, (size_t)148 * 4 * rec_cap * 8)); CK(cudaMalloc(&d_ctacnt, 148 * 4 * 4)); CK(cudaMemset(d_ctacnt, 0, 148 * 4 * 4));
+    CK(cudaMalloc(&d_recs, (size_t)148 * TC_EPI_WARPS * rec_cap * 8)); CK(cudaMalloc(&d_ctacnt, 148 * TC_EPI_WARPS * 4)); CK(cudaMemset(d_ctacnt, 0, 148 * TC_EPI_WARPS * 4));
     CK(cudaMalloc(&d_cnt, nq_pad * 4 * CNT_STRIDE)); CK(cudaMalloc(&d_flag, 4)); CK(cudaMalloc(&d_buf, (size_t)nq_pad * cap * 8));
     CK(cudaMemcpy(d_codes, h_codes.data(), code_words * 4, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(d_qpack, h_qpack.data(), h_qpack.size() * 4, cudaMemcpyHostToDevice));
@@ -106,7 +106,7 @@ int main(int argc, char** argv) {
         CK(cudaMemset(d_cnt, 0, nq_pad * 4 * CNT_STRIDE));
         tc_scan_kernel<NCHUNK, 0><<<grid, TC_THREADS, smem>>>(d_codes, d_live, 0, ntiles, d_qexp, d_qpop, d_qbias, nq, nq_pad, n_qsl, n_rsl,
                                                              d_recs, rec_cap, d_ctacnt, d_flag, nullptr, 0, n_rows);
-        tc_scatter_kernel<<<dim3(TC_SCATTER_X, grid * 4), 256>>>(d_recs, rec_cap, d_ctacnt, d_codes, NCHUNK, d_qpack, qs, d_cnt, d_buf2, bigcap, d_flag);
+        tc_scatter_kernel<<<dim3(TC_SCATTER_X, grid * TC_EPI_WARPS), 256>>>(d_recs, rec_cap, d_ctacnt, d_codes, NCHUNK, d_qpack, qs, d_cnt, d_buf2, bigcap, d_flag);
         CK(cudaGetLastError());
         CK(cudaDeviceSynchronize());
         std::vector<uint32_t> h_cnt_s((size_t)nq_pad * CNT_STRIDE), h_cnt(nq_pad);
@@ -149,7 +149,7 @@ int main(int argc, char** argv) {
             cudaMemsetAsync(d_cnt, 0, nq_pad * 4 * CNT_STRIDE);
             tc_scan_kernel<NCHUNK, 0><<<grid, TC_THREADS, smem>>>(d_codes, d_live, 0, ntiles, d_qexp, d_qpop, d_qbias, nq, nq_pad, n_qsl, n_rsl,
                                                                  d_recs, rec_cap, d_ctacnt, d_flag, nullptr, 0, n_rows, dbg, d_prof);
-            if (!(dbg & 1)) tc_scatter_kernel<<<dim3(TC_SCATTER_X, grid * 4), 256>>>(d_recs, rec_cap, d_ctacnt, d_codes, NCHUNK, d_qpack, qs, d_cnt, d_buf, cap, d_flag);
+            if (!(dbg & 1)) tc_scatter_kernel<<<dim3(TC_SCATTER_X, grid * TC_EPI_WARPS), 256>>>(d_recs, rec_cap, d_ctacnt, d_codes, NCHUNK, d_qpack, qs, d_cnt, d_buf, cap, d_flag);
         }
         cudaEventRecord(e1);
         CK(cudaDeviceSynchronize());
