@@ -305,29 +305,31 @@ def run_ours(args, rank, world, local_rank):
                    "all-gather of the top-k + D2H of its slice (bytes are whole-job totals)")}
 
     # ---- roofline of the dominant kernel inside the timed steps ---------------------------------
-    # Batches of >= 64 queries run the tcgen05 scan (tc_scan_kernel): a dense int8 contraction,
-    # bound by the tensor pipe.  achieved = algorithmic int8 ops (2 x rows x padded queries x
-    # (code bits + the 32-wide bias slice)) / summed CUDA-event time of those launches.
-    # peak: MEASURED_PEAKS.json holds no int8 figure; kind::i8 issues at twice the bf16 MAC rate
-    # (tools/mma_floor.cu: 8188 vs 4094 MAC/clk/SM), so peak = 2 x the measured bf16 burst.
+    # Batches of >= 64 queries run the tcgen05 scan (tc_scan_kernel): a dense contraction on the FP4
+    # tensor path (kind::mxf4, e2m1 operands, exact f32 accumulation), bound by the tensor pipe.
+    # achieved = algorithmic ops (2 x rows x padded queries x (code bits + the 64-wide bias slice))
+    # / summed CUDA-event time of those launches.  peak: MEASURED_PEAKS.json holds no FP4 figure;
+    # the dense FP4 rate is 4 x bf16 (9 vs 2.25 PFLOP/s nominal), so peak = 4 x the measured bf16
+    # burst.  frac_of_mma_issue_floor uses the 64 clk per M128 x N128 x K64 MMA the hardware
+    # nominally issues (tools/mxf4_probe.cu measures 76 clk with A in TMEM).
     stage_keys = ("prep_ms", "scan_ms", "tc_ms", "scatter_ms", "select_ms", "rescore_ms", "topk_ms", "merge_ms")
     step_kernel_ms = sum(prof[x] for x in stage_keys)
     sm_mhz = clk.get("sm_mhz") or sm_max
     code_bits = index.stats()["code_bytes_per_row"] * 8
     if prof["tc_launches"] > 0:
         tops = 2.0 * prof["tc_macs"] / (prof["tc_ms"] * 1e-3) / 1e12
-        peak_tops = 2.0 * bf16_peak
+        peak_tops = 4.0 * bf16_peak
         roofline = {
-            "kernel": "tc_scan_kernel<NCHUNK=%d,MODE=0> (tcgen05.mma kind::i8, A in TMEM)" % (code_bits // 128),
+            "kernel": "tc_scan_kernel<NCHUNK=%d,MODE=0> (tcgen05.mma kind::mxf4 block-scaled FP4, A in TMEM)" % (code_bits // 128),
             "bound": "tensor", "achieved": tops, "peak": peak_tops, "unit": "TFLOP/s",
             "frac": tops / peak_tops, "traffic": None,
-            "peak_source": "2 x bf16_tflops (burst) of MEASURED_PEAKS.json; int8 ops counted as flops",
+            "peak_source": "4 x bf16_tflops (burst) of MEASURED_PEAKS.json (dense FP4 = 4 x bf16 rate)",
             "launches": int(prof["tc_launches"]), "ms_per_launch": prof["tc_ms"] / prof["tc_launches"],
             "share_of_step_kernel_time": prof["tc_ms"] / step_kernel_ms if step_kernel_ms else None,
             "algorithmic_ops_per_step": 2.0 * prof["tc_macs"] / K,
             "algorithmic_code_bytes_per_step": prof["tc_bytes"] / K,
-            "frac_of_mma_issue_floor": (prof["tc_macs"] / (prof["tc_ms"] * 1e-3)) / (148 * 8192 * sm_mhz * 1e6),
-            "note": ("frac_of_mma_issue_floor = MAC/s over 148 SMs x 8192 MAC/clk x the SM clock sampled "
+            "frac_of_mma_issue_floor": (prof["tc_macs"] / (prof["tc_ms"] * 1e-3)) / (148 * 16384 * sm_mhz * 1e6),
+            "note": ("frac_of_mma_issue_floor = MAC/s over 148 SMs x 16384 MAC/clk x the SM clock sampled "
                      "during the run; the HBM-bound operating point of the scan (1-2 queries per pass, "
                      "CUDA-core kernel) is roofline_stream."),
             "stage_ms_per_step": {x: prof[x] / K for x in stage_keys},
@@ -428,7 +430,7 @@ def run_ours(args, rank, world, local_rank):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "int8 tensor-core contraction of 1-bit codes -> exact u32 Hamming (scan), f32 (rescoring)", "data": "synthetic",
+            "dtype": "fp4 (e2m1) tensor-core contraction of 1-bit codes, f32 accumulate -> exact Hamming (scan), f32 (rescoring)", "data": "synthetic",
             "config": workload_config(args, world), "clocks": clk,
             "e2e": e2e, "gpu_launches": launches_timed,
             "roofline": roofline, "roofline_stream": roofline_stream, "cpu_baseline": cpu_baseline,

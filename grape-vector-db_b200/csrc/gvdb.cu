@@ -133,6 +133,7 @@ struct gvdb_index {
     int scan_variant = -1;     // GVDB_SCAN_NCSA: adder-count override for tuning (768-d only)
     uint32_t tc_min_q = 64;    // GVDB_TC_MIN_Q: query-tile size from which the tcgen05 scan is used
     uint32_t seg0_rows = 4096; // GVDB_SEG0_ROWS: rows of the first ("emit everything") segment
+    uint32_t tc_qb_force = 0;  // GVDB_TC_QB: force the query blocks per tensor-core work item (0 = model)
     uint32_t opt_m = 5;        // GVDB_OPT_M: order statistic of the optimistic single-pass threshold (0 = off)
     uint32_t seg_growth = 16;  // GVDB_SEG_GROWTH: cap on the geometric segment growth (0 = cap/(4R) only)
     std::atomic<int> profile_on{0};
@@ -322,21 +323,30 @@ bool tc_supported(int nchunk) { return tc_supported_chunks(nchunk); }
 // MODE 1: every distance to dist_out (parity).
 // Work split of one tcgen05 scan launch: items = query slices x row slices, one CTA per SM looping
 // over items.  Pick the row-slice count that fills whole waves of SMs.
-struct TcSplit { uint32_t qslices, rslices, grid; };
+struct TcSplit { uint32_t qslices, rslices, grid, qb_item; };
 TcSplit tc_split(const gvdb_index* h, uint32_t ngroups, uint32_t nq_pad) {
     const uint32_t sms = (uint32_t)h->sm_count;
-    const uint32_t qb = (uint32_t)tc_qblocks(h->nchunk);
-    const uint32_t qsl = (nq_pad / TC_NQ + qb - 1) / qb;
-    const uint32_t rmax = std::max<uint32_t>(1, std::min<uint32_t>(ngroups, std::max<uint32_t>(1, 8 * sms / qsl)));
-    uint32_t best = 1;
-    double best_eff = 0.0;
-    for (uint32_t r = 1; r <= rmax; ++r) {
-        const uint64_t items = (uint64_t)qsl * r;
-        const uint64_t waves = (items + sms - 1) / sms;
-        const double eff = (double)items / (double)(waves * sms);
-        if (eff > best_eff + 1e-9) { best_eff = eff; best = r; }
+    const uint32_t nqb = nq_pad / TC_NQ;
+    uint32_t qb_max = (uint32_t)tc_qblocks(h->nchunk);
+    uint32_t qb_min = 1;
+    if (h->tc_qb_force) qb_min = qb_max = std::min<uint32_t>(qb_max, h->tc_qb_force);   // GVDB_TC_QB (tuning)
+    TcSplit best{1, 1, 1, 1};
+    double best_cost = 1e300;
+    // makespan model: waves x (row groups per item) x (blocks per item + the per-group A expansion share)
+    for (uint32_t qb = qb_min; qb <= qb_max; ++qb) {
+        const uint32_t qsl = (nqb + qb - 1) / qb;
+        const uint32_t rmax = std::max<uint32_t>(1, std::min<uint32_t>(ngroups, std::max<uint32_t>(1, 8 * sms / qsl)));
+        for (uint32_t r = 1; r <= rmax; ++r) {
+            const uint64_t items = (uint64_t)qsl * r;
+            const uint64_t waves = (items + sms - 1) / sms;
+            const double cost = (double)waves * std::ceil((double)ngroups / r) * (qb + 0.2);
+            if (cost < best_cost - 1e-9) {
+                best_cost = cost;
+                best = TcSplit{qsl, r, (uint32_t)std::min<uint64_t>(items, sms), qb};
+            }
+        }
     }
-    return TcSplit{qsl, best, (uint32_t)std::min<uint64_t>((uint64_t)qsl * best, sms)};
+    return best;
 }
 
 // MODE 0: survivors -> warp-private record lists -> tc_scatter_kernel -> per-query buffers.
@@ -377,7 +387,7 @@ void launch_tc_scan(gvdb_index* h, Workspace* ws, cudaStream_t st, uint32_t tile
             attr = true;                                                                             \
         }                                                                                            \
         tc_scan_kernel<N, MODE><<<grid, TC_THREADS, smem, st>>>(h->codes, h->live, tile_lo, tile_hi, qexp, qpop, qbias, \
-                                                               nq, nq_pad, sp.qslices, sp.rslices, recs, rec_cap, lc,  \
+                                                               nq, nq_pad, sp.qslices, sp.rslices, sp.qb_item, recs, rec_cap, lc,  \
                                                                overflow, dist_out, dist_stride, h->n_rows, 0);          \
         break;                                                                                       \
     }
@@ -869,6 +879,7 @@ gvdb_status gvdb_create(const gvdb_config* cfg, gvdb_index** out) {
         if (const char* s = getenv("GVDB_SCAN_NCSA")) h->scan_variant = atoi(s);
         if (const char* s = getenv("GVDB_TC_MIN_Q")) h->tc_min_q = (uint32_t)std::max(1, atoi(s));
         if (const char* s = getenv("GVDB_SEG0_ROWS")) h->seg0_rows = (uint32_t)std::max(32, atoi(s)) / 32 * 32;
+        if (const char* s = getenv("GVDB_TC_QB")) h->tc_qb_force = (uint32_t)std::max(0, atoi(s));
         if (const char* s = getenv("GVDB_OPT_M")) h->opt_m = (uint32_t)std::max(0, atoi(s));
         if (const char* s = getenv("GVDB_SEG_GROWTH")) h->seg_growth = (uint32_t)std::max(0, atoi(s));
         if (const char* s = getenv("GVDB_SCAN_CTAS_PER_SM")) h->scan_ctas_per_sm = std::max(1, atoi(s));

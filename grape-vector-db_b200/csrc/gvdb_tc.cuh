@@ -261,7 +261,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_scan_kernel(const uint4* __restrict__ codes, const uint32_t* __restrict__ live, uint32_t tile_lo,
                uint32_t tile_hi, const int8_t* __restrict__ qexp, const uint32_t* __restrict__ qpop,
                const int32_t* __restrict__ qbias, uint32_t nq, uint32_t nq_pad, uint32_t n_qslices,
-               uint32_t n_rslices, uint2* __restrict__ recs, uint32_t rec_cap,
+               uint32_t n_rslices, uint32_t qb_item /* query blocks per item, <= tc_qblocks(NCHUNK) */,
+               uint2* __restrict__ recs, uint32_t rec_cap,
                uint32_t* __restrict__ list_counts, uint32_t* __restrict__ overflow,
                uint32_t* __restrict__ dist_out, uint64_t dist_stride, uint64_t n_rows, int dbg = 0,
                unsigned long long* __restrict__ prof = nullptr) {
@@ -320,8 +321,8 @@ tc_scan_kernel(const uint4* __restrict__ codes, const uint32_t* __restrict__ liv
     // item -> (query blocks, row groups)
     auto item_range = [&](uint32_t item, uint32_t& qb0, uint32_t& nb, uint32_t& g_lo, uint32_t& g_hi) {
         const uint32_t qsl = item / n_rslices, rsl = item % n_rslices;
-        qb0 = qsl * QB;
-        nb = min((uint32_t)QB, nqb - qb0);
+        qb0 = qsl * qb_item;
+        nb = min(qb_item, nqb - qb0);
         g_lo = (uint32_t)((uint64_t)ngroups * rsl / n_rslices);
         g_hi = (uint32_t)((uint64_t)ngroups * (rsl + 1) / n_rslices);
     };

@@ -68,7 +68,8 @@ int main(int argc, char** argv) {
     CK(cudaGetLastError());
     int sms = 0; CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0));
     uint32_t ngroups = (ntiles + 3) / 4;
-    const uint32_t n_qsl = (nq_pad / TC_NQ + TC_QBLOCKS - 1) / TC_QBLOCKS;
+    const uint32_t qb_item = argc > 6 ? (uint32_t)atoi(argv[6]) : (uint32_t)TC_QBLOCKS;
+    const uint32_t n_qsl = (nq_pad / TC_NQ + qb_item - 1) / qb_item;
     uint32_t n_rsl = argc > 5 ? atoi(argv[5]) : 0;
     if (!n_rsl) { n_rsl = sms / n_qsl; if (!n_rsl) n_rsl = 1; }
     if (n_rsl > ngroups) n_rsl = ngroups;
@@ -80,7 +81,7 @@ int main(int argc, char** argv) {
         tc_bias_kernel<<<(nq_pad + 127) / 128, 128>>>(d_qpack, qs, NCHUNK, d_qpop, nq, nq_pad, d_qexp, d_qbias, 1);
         ref_kernel<NCHUNK><<<(ntiles + 7) / 8, 256>>>(d_codes, ntiles, d_qpack, qs, nq, d_ref, n_rows, n_rows);
         CK(cudaGetLastError());
-        tc_scan_kernel<NCHUNK, 1><<<grid, TC_THREADS, smem>>>(d_codes, d_live, 0, ntiles, d_qexp, d_qpop, d_qbias, nq, nq_pad, n_qsl, n_rsl,
+        tc_scan_kernel<NCHUNK, 1><<<grid, TC_THREADS, smem>>>(d_codes, d_live, 0, ntiles, d_qexp, d_qpop, d_qbias, nq, nq_pad, n_qsl, n_rsl, qb_item,
                                                              d_recs, rec_cap, d_ctacnt, d_flag, d_tc, n_rows, n_rows);
         CK(cudaGetLastError());
         CK(cudaDeviceSynchronize());
@@ -104,7 +105,7 @@ int main(int argc, char** argv) {
         const uint32_t bigcap = 65536;
         uint64_t* d_buf2; CK(cudaMalloc(&d_buf2, (size_t)nq_pad * bigcap * 8));
         CK(cudaMemset(d_cnt, 0, nq_pad * 4 * CNT_STRIDE));
-        tc_scan_kernel<NCHUNK, 0><<<grid, TC_THREADS, smem>>>(d_codes, d_live, 0, ntiles, d_qexp, d_qpop, d_qbias, nq, nq_pad, n_qsl, n_rsl,
+        tc_scan_kernel<NCHUNK, 0><<<grid, TC_THREADS, smem>>>(d_codes, d_live, 0, ntiles, d_qexp, d_qpop, d_qbias, nq, nq_pad, n_qsl, n_rsl, qb_item,
                                                              d_recs, rec_cap, d_ctacnt, d_flag, nullptr, 0, n_rows);
         tc_scatter_kernel<<<dim3(TC_SCATTER_X, grid * TC_EPI_WARPS), 256>>>(d_recs, rec_cap, d_ctacnt, d_codes, NCHUNK, d_qpack, qs, d_cnt, d_buf2, bigcap, d_flag);
         CK(cudaGetLastError());
@@ -138,7 +139,7 @@ int main(int argc, char** argv) {
         CK(cudaFuncSetAttribute(tc_scan_kernel<NCHUNK, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
         for (int rep = 0; rep < 3; ++rep)
-            tc_scan_kernel<NCHUNK, 0><<<grid, TC_THREADS, smem>>>(d_codes, d_live, 0, ntiles, d_qexp, d_qpop, d_qbias, nq, nq_pad, n_qsl, n_rsl,
+            tc_scan_kernel<NCHUNK, 0><<<grid, TC_THREADS, smem>>>(d_codes, d_live, 0, ntiles, d_qexp, d_qpop, d_qbias, nq, nq_pad, n_qsl, n_rsl, qb_item,
                                                                  d_recs, rec_cap, d_ctacnt, d_flag, nullptr, 0, n_rows);
         CK(cudaDeviceSynchronize());
         const int reps = 10;
@@ -147,7 +148,7 @@ int main(int argc, char** argv) {
         cudaEventRecord(e0);
         for (int rep = 0; rep < reps; ++rep) {
             cudaMemsetAsync(d_cnt, 0, nq_pad * 4 * CNT_STRIDE);
-            tc_scan_kernel<NCHUNK, 0><<<grid, TC_THREADS, smem>>>(d_codes, d_live, 0, ntiles, d_qexp, d_qpop, d_qbias, nq, nq_pad, n_qsl, n_rsl,
+            tc_scan_kernel<NCHUNK, 0><<<grid, TC_THREADS, smem>>>(d_codes, d_live, 0, ntiles, d_qexp, d_qpop, d_qbias, nq, nq_pad, n_qsl, n_rsl, qb_item,
                                                                  d_recs, rec_cap, d_ctacnt, d_flag, nullptr, 0, n_rows, dbg, d_prof);
             if (!(dbg & 1)) tc_scatter_kernel<<<dim3(TC_SCATTER_X, grid * TC_EPI_WARPS), 256>>>(d_recs, rec_cap, d_ctacnt, d_codes, NCHUNK, d_qpack, qs, d_cnt, d_buf, cap, d_flag);
         }
