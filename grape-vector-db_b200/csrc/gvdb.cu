@@ -91,11 +91,14 @@ struct Workspace {
     DevBuf tc_recs, list_counts;     // tcgen05 path: warp-private survivor records
     DevBuf big_keys, big_keys2, big_aux, big_k32, big_v32, big_tmp;   // large-R path (gvdb_bigr.cuh)
     uint32_t* h_flag = nullptr;      // pinned
+    void* h_res = nullptr;           // pinned staging for the host-pointer entry point's results
+    size_t h_res_bytes = 0;
     ~Workspace() {
         for (DevBuf* b : {&qpack, &qnorm, &cnt, &flag, &buf, &rec_ham, &rec_ids, &rec_score, &q_in,
                           &ids_out, &sc_out, &codes_tmp, &misc, &qexp, &qpop, &qbias, &tc_recs, &list_counts,
                           &big_keys, &big_keys2, &big_aux, &big_k32, &big_v32, &big_tmp}) b->release();
         if (h_flag) cudaFreeHost(h_flag);
+        if (h_res) cudaFreeHost(h_res);
         for (cudaEvent_t e : ev_pool) cudaEventDestroy(e);
         if (idle) cudaEventDestroy(idle);
         if (stream) cudaStreamDestroy(stream);
@@ -711,12 +714,19 @@ void search_big_r(gvdb_index* h, Workspace* ws, cudaStream_t st, const float* q_
     flush_profile(h, ws);
 }
 
+// h_ids / h_scores (optional, pinned): the k-lists are also copied there BEFORE the call's one
+// synchronisation, so the host-pointer entry point pays a single stream sync.
 void search_device(gvdb_index* h, Workspace* ws, cudaStream_t st, const float* q_dev, uint32_t nq,
                    uint32_t k, uint32_t R, uint64_t* ids_out, float* scores_out, uint64_t* cand_ids,
-                   uint32_t* cand_ham) {
+                   uint32_t* cand_ham, uint64_t* h_ids = nullptr, float* h_scores = nullptr) {
     if (k > R) fail(GVDB_ERR_INVALID_ARGUMENT, "k must be <= rescore_count");
     if (R > kMaxR) {
         search_big_r(h, ws, st, q_dev, nq, k, R, ids_out, scores_out, cand_ids, cand_ham);
+        if (h_ids) {
+            CU(cudaMemcpyAsync(h_ids, ids_out, (size_t)nq * k * 8, cudaMemcpyDeviceToHost, st));
+            CU(cudaMemcpyAsync(h_scores, scores_out, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, st));
+            CU(cudaStreamSynchronize(st));
+        }
         return;
     }
     ws->rec_ham.ensure((size_t)nq * R * 4);
@@ -729,6 +739,10 @@ void search_device(gvdb_index* h, Workspace* ws, cudaStream_t st, const float* q
         launch_topk(h, ws, st, ws->rec_ids.as<uint64_t>(), ws->rec_score.as<float>(), nq, R, k, ids_out, scores_out);
         if (cand_ids) CU(cudaMemcpyAsync(cand_ids, ws->rec_ids.p, (size_t)nq * R * 8, cudaMemcpyDeviceToDevice, st));
         if (cand_ham) CU(cudaMemcpyAsync(cand_ham, ws->rec_ham.p, (size_t)nq * R * 4, cudaMemcpyDeviceToDevice, st));
+        if (h_ids) {
+            CU(cudaMemcpyAsync(h_ids, ids_out, (size_t)nq * k * 8, cudaMemcpyDeviceToHost, st));
+            CU(cudaMemcpyAsync(h_scores, scores_out, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, st));
+        }
         if (!check_overflow(h, ws, st, optimistic)) break;
     }
 }
@@ -1276,10 +1290,21 @@ gvdb_status gvdb_search_batch(gvdb_index* h, const float* queries, uint32_t nq, 
             cand_ids_dev = ws->codes_tmp.as<uint64_t>();
             cand_ham_dev = reinterpret_cast<uint32_t*>(ws->codes_tmp.as<uint8_t>() + (size_t)nq * R * 8);
         }
+        // results land in a pinned staging buffer before the call's single synchronisation
+        const size_t res_bytes = (size_t)nq * k * 12;
+        if (ws->h_res_bytes < res_bytes) {
+            if (ws->h_res) cudaFreeHost(ws->h_res);
+            ws->h_res = nullptr; ws->h_res_bytes = 0;
+            CU(cudaMallocHost(&ws->h_res, res_bytes));
+            ws->h_res_bytes = res_bytes;
+        }
+        uint64_t* h_ids = static_cast<uint64_t*>(ws->h_res);
+        float* h_sc = reinterpret_cast<float*>(static_cast<uint8_t*>(ws->h_res) + (size_t)nq * k * 8);
         search_device(h, ws, st, ws->q_in.as<float>(), nq, k, R, ws->ids_out.as<uint64_t>(),
-                      ws->sc_out.as<float>(), cand_ids_dev, cand_ham_dev);
-        CU(cudaMemcpyAsync(ids_out, ws->ids_out.p, (size_t)nq * k * 8, cudaMemcpyDeviceToHost, st));
-        CU(cudaMemcpyAsync(scores_out, ws->sc_out.p, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, st));
+                      ws->sc_out.as<float>(), cand_ids_dev, cand_ham_dev, h_ids, h_sc);
+        memcpy(ids_out, h_ids, (size_t)nq * k * 8);
+        memcpy(scores_out, h_sc, (size_t)nq * k * 4);
+        if (!cand_ids_out && !cand_ham_out) return;
         if (cand_ids_out) CU(cudaMemcpyAsync(cand_ids_out, cand_ids_dev ? (void*)cand_ids_dev : ws->rec_ids.p, (size_t)nq * R * 8, cudaMemcpyDeviceToHost, st));
         if (cand_ham_out) CU(cudaMemcpyAsync(cand_ham_out, cand_ham_dev ? (void*)cand_ham_dev : ws->rec_ham.p, (size_t)nq * R * 4, cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
