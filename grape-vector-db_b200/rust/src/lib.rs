@@ -22,7 +22,11 @@ pub struct gvdb_config {
     pub flags: u32,
     pub capacity_rows: u64,
     pub row_base: u64,
+    /// GVDB_FLAG_ROW_WINDOW (flags bit 0): f32 rows kept for local rows [window_first, window_first + window_count)
+    pub window_first: u64,
+    pub window_count: u64,
 }
+pub const GVDB_FLAG_ROW_WINDOW: u32 = 1;
 
 #[repr(C)]
 #[derive(Default, Clone, Copy)]
@@ -57,6 +61,11 @@ extern "C" {
                              ids_out: *mut u64, scores_out: *mut f32, cand_ids_out: *mut u64, cand_ham_out: *mut u32) -> i32;
     pub fn gvdb_flat_search_batch(h: *mut gvdb_index, queries: *const f32, nq: u32, k: u32,
                                   ids_out: *mut u64, dist_out: *mut f32) -> i32;
+    pub fn gvdb_save(h: *mut gvdb_index, path: *const std::os::raw::c_char) -> i32;
+    pub fn gvdb_load(path: *const std::os::raw::c_char, device: i32, out: *mut *mut gvdb_index) -> i32;
+    pub fn gvdb_export_rows_ipc(h: *mut gvdb_index, handle_out: *mut u8) -> i32;
+    pub fn gvdb_attach_peer_rows_ipc(h: *mut gvdb_index, n_owners: u32, rows_per_owner: u64, my_owner: u32,
+                                     handles: *const u8) -> i32;
     pub fn gvdb_shard_record_bytes(nq: u32, rescore_count: u32) -> u64;
     pub fn gvdb_search_shard_device(h: *mut gvdb_index, stream: *mut c_void, queries_dev: *const f32, nq: u32,
                                     rescore_count: u32, records_dev: *mut c_void) -> i32;
