@@ -479,3 +479,19 @@ def test_peer_rows_rescoring_equals_single_index(gv):
         ranks[0].flat_search_batch(qs[:2], 5)
     for ix in ranks:
         ix.close()
+
+
+@pytest.mark.timeout(600)
+def test_large_shard_properties(gv):
+    """Size-independent checks at a size the full oracle does not finish quickly (tools/fullsize_check.py
+    runs the same checks on the BASELINE shapes 12.5M x 768 and 10M x 1536): the stage-1 list is the R
+    smallest (hamming, row) keys of a popcount over the stored codes, every score is the oracle's cosine
+    of that row, and the final order is (cosine desc, stage-1 position).  2M rows: the geometric
+    segment schedule on the tensor-core scan (the optimistic single pass stops at ~1.4M rows)."""
+    import subprocess
+    import sys
+    n = int(os.environ.get("GVDB_LARGE_ROWS", "2000000"))
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "fullsize_check.py"), str(n), "768", "256", "3"],
+                         capture_output=True, text=True, timeout=580)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert "FULL-SIZE CHECK PASSED" in out.stdout
