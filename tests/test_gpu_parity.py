@@ -13,6 +13,7 @@ pytestmark = pytest.mark.gpu
 from oracle import oracle  # noqa: E402
 
 GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 @pytest.fixture(scope="module")
