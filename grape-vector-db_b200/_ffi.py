@@ -43,7 +43,8 @@ class GvdbProfile(C.Structure):
                 ("rescore_ms", C.c_double), ("topk_ms", C.c_double), ("prep_ms", C.c_double),
                 ("flat_ms", C.c_double), ("merge_ms", C.c_double), ("tc_launches", C.c_uint64),
                 ("tc_ms", C.c_double), ("tc_macs", C.c_double), ("tc_bytes", C.c_double),
-                ("scatter_ms", C.c_double), ("optimistic_reruns", C.c_uint64)]
+                ("scatter_ms", C.c_double), ("optimistic_reruns", C.c_uint64),
+                ("overflow_fallbacks", C.c_uint64)]
 
 
 # every symbol include/gvdb.h declares: name -> (restype, argtypes)

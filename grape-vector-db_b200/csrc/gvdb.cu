@@ -142,6 +142,7 @@ struct gvdb_index {
     std::atomic<int> profile_on{0};
     std::atomic<uint64_t> launches{0};
     std::atomic<uint64_t> optimistic_reruns{0};
+    std::atomic<uint64_t> overflow_fallbacks{0};
     std::mutex prof_mu;
     gvdb_profile prof{};
 };
@@ -594,18 +595,26 @@ void finish_async(gvdb_index* h, Workspace* ws, cudaStream_t st) {
 
 // Final synchronisation of a search call.  Returns true when the call must be run again without
 // the optimistic threshold (the device refuted the guess, or a candidate buffer overflowed under it).
-bool check_overflow(gvdb_index* h, Workspace* ws, cudaStream_t st, bool was_optimistic = false) {
+// overflowed (optional out): a candidate buffer overflowed under the plain (geometric) schedule —
+// thousands of rows tie below a query's threshold (a heavily duplicated corpus).  Callers that can
+// fall back to the cut by counting (search_big_r, no capacity limit) ask for the flag; the others
+// report IndexError.
+bool check_overflow(gvdb_index* h, Workspace* ws, cudaStream_t st, bool was_optimistic = false,
+                    bool* overflowed = nullptr) {
     CU(cudaMemcpyAsync(ws->h_flag, ws->flag.p, 8, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     flush_profile(h, ws);
+    if (overflowed) *overflowed = false;
     if (was_optimistic && (ws->h_flag[0] || ws->h_flag[1])) {
         h->optimistic_reruns.fetch_add(1, std::memory_order_relaxed);
         return true;
     }
-    if (ws->h_flag[0])
+    if (ws->h_flag[0]) {
+        if (overflowed) { *overflowed = true; return false; }
         fail(GVDB_ERR_INDEX,
-             "candidate buffer overflow in the Hamming scan (heavily duplicated corpus?); "
-             "the exact fallback is not implemented yet");
+             "candidate buffer overflow in the Hamming scan (thousands of rows tie below a query's threshold); "
+             "use gvdb_search_batch(_device), which falls back to the cut by counting");
+    }
     return false;
 }
 
@@ -743,7 +752,21 @@ void search_device(gvdb_index* h, Workspace* ws, cudaStream_t st, const float* q
             CU(cudaMemcpyAsync(h_ids, ids_out, (size_t)nq * k * 8, cudaMemcpyDeviceToHost, st));
             CU(cudaMemcpyAsync(h_scores, scores_out, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, st));
         }
-        if (!check_overflow(h, ws, st, optimistic)) break;
+        bool overflowed = false;
+        if (check_overflow(h, ws, st, optimistic, &overflowed)) continue;
+        if (overflowed) {
+            // exact fallback without capacity limits: the cut by counting (slow path)
+            if ((h->dim & 3) != 0)
+                fail(GVDB_ERR_INDEX, "candidate buffer overflow in the Hamming scan and dim % 4 != 0: no fallback");
+            h->overflow_fallbacks.fetch_add(1, std::memory_order_relaxed);
+            search_big_r(h, ws, st, q_dev, nq, k, R, ids_out, scores_out, cand_ids, cand_ham);
+            if (h_ids) {
+                CU(cudaMemcpyAsync(h_ids, ids_out, (size_t)nq * k * 8, cudaMemcpyDeviceToHost, st));
+                CU(cudaMemcpyAsync(h_scores, scores_out, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, st));
+                CU(cudaStreamSynchronize(st));
+            }
+        }
+        break;
     }
 }
 
@@ -1282,10 +1305,11 @@ gvdb_status gvdb_search_batch(gvdb_index* h, const float* queries, uint32_t nq, 
         ws->ids_out.ensure((size_t)nq * std::max(k, 1u) * 8);
         ws->sc_out.ensure((size_t)nq * std::max(k, 1u) * 4);
         CU(cudaMemcpyAsync(ws->q_in.p, queries, (size_t)nq * h->dim * 4, cudaMemcpyHostToDevice, st));
-        // the large-R path keeps one query's records at a time: give it full candidate buffers
+        // the cut-by-counting path (large R, or the overflow fallback) keeps one query's records at a
+        // time: give the call full candidate buffers whenever candidates are asked for
         uint64_t* cand_ids_dev = nullptr;
         uint32_t* cand_ham_dev = nullptr;
-        if (R > kMaxR && (cand_ids_out || cand_ham_out)) {
+        if (cand_ids_out || cand_ham_out) {
             ws->codes_tmp.ensure((size_t)nq * R * 12);
             cand_ids_dev = ws->codes_tmp.as<uint64_t>();
             cand_ham_dev = reinterpret_cast<uint32_t*>(ws->codes_tmp.as<uint8_t>() + (size_t)nq * R * 8);
@@ -1305,8 +1329,8 @@ gvdb_status gvdb_search_batch(gvdb_index* h, const float* queries, uint32_t nq, 
         memcpy(ids_out, h_ids, (size_t)nq * k * 8);
         memcpy(scores_out, h_sc, (size_t)nq * k * 4);
         if (!cand_ids_out && !cand_ham_out) return;
-        if (cand_ids_out) CU(cudaMemcpyAsync(cand_ids_out, cand_ids_dev ? (void*)cand_ids_dev : ws->rec_ids.p, (size_t)nq * R * 8, cudaMemcpyDeviceToHost, st));
-        if (cand_ham_out) CU(cudaMemcpyAsync(cand_ham_out, cand_ham_dev ? (void*)cand_ham_dev : ws->rec_ham.p, (size_t)nq * R * 4, cudaMemcpyDeviceToHost, st));
+        if (cand_ids_out) CU(cudaMemcpyAsync(cand_ids_out, cand_ids_dev, (size_t)nq * R * 8, cudaMemcpyDeviceToHost, st));
+        if (cand_ham_out) CU(cudaMemcpyAsync(cand_ham_out, cand_ham_dev, (size_t)nq * R * 4, cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
     });
 }
@@ -1582,11 +1606,13 @@ gvdb_status gvdb_profile_read(gvdb_index* h, gvdb_profile* out, int32_t reset) {
         std::lock_guard<std::mutex> lk(h->prof_mu);
         h->prof.launches = h->launches.load();
         h->prof.optimistic_reruns = h->optimistic_reruns.load();
+        h->prof.overflow_fallbacks = h->overflow_fallbacks.load();
         *out = h->prof;
         if (reset) {
             h->prof = gvdb_profile{};
             h->launches.store(0);
             h->optimistic_reruns.store(0);
+            h->overflow_fallbacks.store(0);
         }
     });
 }

@@ -261,6 +261,7 @@ typedef struct gvdb_profile {
     double tc_bytes;          /* code bytes those launches read: rows * code_bytes_per_row * query slices */
     double scatter_ms;        /* tc_scatter_kernel (survivor records -> candidate buffers) */
     uint64_t optimistic_reruns; /* calls repeated because the device refuted the single-pass threshold guess */
+    uint64_t overflow_fallbacks; /* calls answered by the cut by counting after a candidate buffer overflowed */
 } gvdb_profile;
 GVDB_API gvdb_status gvdb_profile_enable(gvdb_index* h, int32_t on);
 GVDB_API gvdb_status gvdb_profile_read(gvdb_index* h, gvdb_profile* out, int32_t reset);

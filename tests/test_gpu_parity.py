@@ -496,3 +496,20 @@ def test_large_shard_properties(gv):
                          capture_output=True, text=True, timeout=580)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     assert "FULL-SIZE CHECK PASSED" in out.stdout
+
+
+def test_heavily_duplicated_corpus_falls_back_exactly(gv):
+    """Tens of thousands of copies of a few vectors: more rows tie below a query's threshold than a
+    candidate buffer holds.  The segment schedule overflows; the call falls back to the cut by
+    counting and still returns the reference's answer (first copies by row number)."""
+    from grape_vector_db_b200 import synth
+    dim = 128
+    base = synth.lowrank_rows(0, 7, dim)
+    rows = np.concatenate([synth.lowrank_rows(100, 5000, dim), np.repeat(base, 10000, axis=0)])   # 75k rows
+    qs = np.concatenate([base[:3] * np.float32(0.5), synth.lowrank_queries(0, 70, dim)])
+    _check_two_stage(gv, rows, qs[:5], 40, 10)           # CUDA-core scan
+    _check_two_stage(gv, rows, qs, 40, 10)               # tensor-core scan (73 queries)
+    with gv.GpuIndex(dim) as idx:                        # ... and the fallback is what answered
+        idx.add(rows)
+        idx.search_batch(qs[:5], 10, 40)
+        assert idx.profile_read()["overflow_fallbacks"] >= 1
