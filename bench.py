@@ -63,6 +63,24 @@ def parse():
     return ap.parse_args()
 
 
+def ncu_traffic(name):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the first launch in a committed ncu summary
+    (profiles/<name>, written by tools/ncu_summary.py from one `ncu --set full` capture), in bytes."""
+    p = os.path.join(ROOT, "profiles", name)
+    if not os.path.exists(p):
+        return None
+    tot, seen = 0.0, 0
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    for line in open(p):
+        c = line.split()
+        if len(c) >= 3 and c[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum") and c[2] in scale:
+            tot += float(c[1]) * scale[c[2]]
+            seen += 1
+            if seen == 2:
+                return tot
+    return None
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -322,7 +340,9 @@ def run_ours(args, rank, world, local_rank):
         roofline = {
             "kernel": "tc_scan_kernel<NCHUNK=%d,MODE=0> (tcgen05.mma kind::mxf4 block-scaled FP4, A in TMEM)" % (code_bits // 128),
             "bound": "tensor", "achieved": tops, "peak": peak_tops, "unit": "TFLOP/s",
-            "frac": tops / peak_tops, "traffic": None,
+            "frac": tops / peak_tops, "traffic": ncu_traffic("r01_tcscan_v3_fp4.txt"),
+            "traffic_note": "DRAM bytes of one full-corpus launch (ncu --set full, profiles/r01_tcscan_v3_fp4.txt): "
+                            "the codes are read from HBM once, the other query slices hit L2",
             "peak_source": "4 x bf16_tflops (burst) of MEASURED_PEAKS.json (dense FP4 = 4 x bf16 rate)",
             "launches": int(prof["tc_launches"]), "ms_per_launch": prof["tc_ms"] / prof["tc_launches"],
             "share_of_step_kernel_time": prof["tc_ms"] / step_kernel_ms if step_kernel_ms else None,
