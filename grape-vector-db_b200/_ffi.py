@@ -71,6 +71,8 @@ SYMBOLS = {
     "gvdb_search_batch_device": (_i32, [_vp, _vp, _vp, _u32, _u32, _u32, _vp, _vp, _vp, _vp]),
     "gvdb_flat_search_batch": (_i32, [_vp, _vp, _u32, _u32, _vp, _vp]),
     "gvdb_flat_search_batch_device": (_i32, [_vp, _vp, _vp, _u32, _u32, _vp, _vp]),
+    "gvdb_similarity_search_batch": (_i32, [_vp, _vp, _u32, _u32, C.c_float, _i32, _vp, _vp]),
+    "gvdb_similarity_search_batch_device": (_i32, [_vp, _vp, _vp, _u32, _u32, C.c_float, _i32, _vp, _vp]),
     "gvdb_shard_record_bytes": (_u64, [_u32, _u32]),
     "gvdb_search_shard_device": (_i32, [_vp, _vp, _vp, _u32, _u32, _vp]),
     "gvdb_search_shard_sliced_device": (_i32, [_vp, _vp, _vp, _u32, _u32, _u32, _vp]),

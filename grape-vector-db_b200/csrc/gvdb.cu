@@ -772,7 +772,8 @@ void search_device(gvdb_index* h, Workspace* ws, cudaStream_t st, const float* q
 
 // Exact flat search: same segment/select machinery with key = image(1 - cos) << 32 | row.
 void flat_device(gvdb_index* h, Workspace* ws, cudaStream_t st, const float* q_dev, uint32_t nq,
-                 uint32_t k, uint64_t* ids_out, float* dist_out) {
+                 uint32_t k, uint64_t* ids_out, float* dist_out, bool sim = false, float sim_threshold = 0.f,
+                 bool use_threshold = false) {
     need_all_rows(h);
     if (h->n_rows == 0) fail(GVDB_ERR_INDEX_NOT_BUILT, "index not built: search before any add");
     if (k == 0) fail(GVDB_ERR_INVALID_ARGUMENT, "k must be >= 1");
@@ -807,10 +808,16 @@ void flat_device(gvdb_index* h, Workspace* ws, cudaStream_t st, const float* q_d
             dim3 grid((unsigned)((hi - lo + FLAT_TM - 1) / FLAT_TM), (nqt + FLAT_TN - 1) / FLAT_TN, 1);
             {
                 Timed t(h, ws, st, K_FLAT);
-                flat_scan_kernel<<<grid, FLAT_THREADS, 0, st>>>(
-                    h->rows_base(), h->norms, h->live, lo, hi, h->dim, qd, ws->qnorm.as<float>(), nqt,
-                    ws->misc.as<uint32_t>(), ws->cnt.as<uint32_t>(), ws->buf.as<uint64_t>(), cap,
-                    ws->flag.as<uint32_t>());
+                if (sim)
+                    flat_scan_kernel<true><<<grid, FLAT_THREADS, 0, st>>>(
+                        h->rows_base(), h->norms, h->live, lo, hi, h->dim, qd, ws->qnorm.as<float>(), nqt,
+                        ws->misc.as<uint32_t>(), ws->cnt.as<uint32_t>(), ws->buf.as<uint64_t>(), cap,
+                        ws->flag.as<uint32_t>(), sim_threshold, use_threshold ? 1 : 0);
+                else
+                    flat_scan_kernel<false><<<grid, FLAT_THREADS, 0, st>>>(
+                        h->rows_base(), h->norms, h->live, lo, hi, h->dim, qd, ws->qnorm.as<float>(), nqt,
+                        ws->misc.as<uint32_t>(), ws->cnt.as<uint32_t>(), ws->buf.as<uint64_t>(), cap,
+                        ws->flag.as<uint32_t>(), 0.f, 0);
             }
             CU(cudaGetLastError());
             {
@@ -824,7 +831,7 @@ void flat_device(gvdb_index* h, Workspace* ws, cudaStream_t st, const float* q_d
         h->launches.fetch_add(1, std::memory_order_relaxed);
         flat_emit_kernel<<<(nqt * k + 255) / 256, 256, 0, st>>>(
             ws->buf.as<uint64_t>(), cap, ws->cnt.as<uint32_t>(), nqt, k, h->cfg.row_base,
-            ids_out + (size_t)qt0 * k, dist_out + (size_t)qt0 * k);
+            ids_out + (size_t)qt0 * k, dist_out + (size_t)qt0 * k, sim ? 1 : 0);
         CU(cudaGetLastError());
     }
     check_overflow(h, ws, st);
@@ -1365,6 +1372,42 @@ gvdb_status gvdb_flat_search_batch(gvdb_index* h, const float* queries, uint32_t
         flat_device(h, ws, st, ws->q_in.as<float>(), nq, k, ws->ids_out.as<uint64_t>(), ws->sc_out.as<float>());
         CU(cudaMemcpyAsync(ids_out, ws->ids_out.p, (size_t)nq * k * 8, cudaMemcpyDeviceToHost, st));
         CU(cudaMemcpyAsync(dist_out, ws->sc_out.p, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+    });
+}
+
+gvdb_status gvdb_similarity_search_batch_device(gvdb_index* h, void* stream, const float* queries_dev, uint32_t nq,
+                                                uint32_t k, float threshold, int32_t use_threshold,
+                                                uint64_t* ids_out_dev, float* sims_out_dev) {
+    return guarded([&] {
+        need(h, "index");
+        if (nq == 0) return;
+        need(queries_dev, "queries"); need(ids_out_dev, "ids_out"); need(sims_out_dev, "sims_out");
+        DeviceGuard dg(h->cfg.device);
+        WsLease lease(h, (cudaStream_t)stream, true);
+        flat_device(h, lease.ws, lease.stream, queries_dev, nq, k, ids_out_dev, sims_out_dev, true, threshold,
+                    use_threshold != 0);
+    });
+}
+
+gvdb_status gvdb_similarity_search_batch(gvdb_index* h, const float* queries, uint32_t nq, uint32_t k,
+                                         float threshold, int32_t use_threshold, uint64_t* ids_out, float* sims_out) {
+    return guarded([&] {
+        need(h, "index");
+        if (nq == 0) return;
+        need(queries, "queries"); need(ids_out, "ids_out"); need(sims_out, "sims_out");
+        DeviceGuard dg(h->cfg.device);
+        WsLease lease(h, nullptr, false);
+        Workspace* ws = lease.ws;
+        cudaStream_t st = lease.stream;
+        ws->q_in.ensure((size_t)nq * h->dim * 4);
+        ws->ids_out.ensure((size_t)nq * std::max(k, 1u) * 8);
+        ws->sc_out.ensure((size_t)nq * std::max(k, 1u) * 4);
+        CU(cudaMemcpyAsync(ws->q_in.p, queries, (size_t)nq * h->dim * 4, cudaMemcpyHostToDevice, st));
+        flat_device(h, ws, st, ws->q_in.as<float>(), nq, k, ws->ids_out.as<uint64_t>(), ws->sc_out.as<float>(), true,
+                    threshold, use_threshold != 0);
+        CU(cudaMemcpyAsync(ids_out, ws->ids_out.p, (size_t)nq * k * 8, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(sims_out, ws->sc_out.p, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
     });
 }

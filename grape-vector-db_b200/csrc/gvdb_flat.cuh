@@ -17,12 +17,18 @@ constexpr int FLAT_TM = 128;       // rows per CTA
 constexpr int FLAT_TN = 64;        // queries per CTA
 constexpr int FLAT_THREADS = 256;  // 16 x 16 threads, 8 rows x 4 queries each
 
+// SIM = false: FaissVectorIndex::search — key image of distance = 1 - cos (+inf on a zero norm), ascending.
+// SIM = true : BasicVectorStore::vector_search (/root/reference/src/storage.rs:296-339 with
+//              cosine_similarity, :851-865) — similarity = cos (0.0 on a zero norm), rows with
+//              similarity < sim_threshold skipped (when use_threshold), descending: key image = ~image(cos).
+template <bool SIM>
 __global__ void __launch_bounds__(FLAT_THREADS)
 flat_scan_kernel(const float* __restrict__ rows, const float* __restrict__ norms,
                  const uint32_t* __restrict__ live, uint64_t row_lo, uint64_t row_hi, int dim,
                  const float* __restrict__ queries, const float* __restrict__ qnorm, uint32_t nq,
                  const uint32_t* __restrict__ tau, uint32_t* __restrict__ cnt,
-                 uint64_t* __restrict__ buf, uint32_t cap, uint32_t* __restrict__ overflow) {
+                 uint64_t* __restrict__ buf, uint32_t cap, uint32_t* __restrict__ overflow,
+                 float sim_threshold, int use_threshold) {
     __shared__ float As[FLAT_TM][33];
     __shared__ float Bs[FLAT_TN][33];
     const int tid = threadIdx.x;
@@ -97,10 +103,17 @@ flat_scan_kernel(const float* __restrict__ rows, const float* __restrict__ norms
         for (int j = 0; j < 4; ++j) {
             const uint32_t q = q0 + j * 16 + tx;
             if (q >= nq) continue;
-            float d = (qn[j] == 0.0f || rn == 0.0f)
-                          ? INFINITY
-                          : __fsub_rn(1.0f, __fdiv_rn(acc[i][j], __fmul_rn(qn[j], rn)));
-            const uint32_t img = f32_asc_key(d);
+            uint32_t img;
+            if (SIM) {
+                const float c = (qn[j] == 0.0f || rn == 0.0f) ? 0.0f : __fdiv_rn(acc[i][j], __fmul_rn(qn[j], rn));
+                if (use_threshold && c < sim_threshold) continue;
+                img = ~f32_asc_key(c);
+            } else {
+                const float d = (qn[j] == 0.0f || rn == 0.0f)
+                                    ? INFINITY
+                                    : __fsub_rn(1.0f, __fdiv_rn(acc[i][j], __fmul_rn(qn[j], rn)));
+                img = f32_asc_key(d);
+            }
             if (img < tq[j]) {
                 const uint32_t pos = atomicAdd(&cnt[(size_t)q * CNT_STRIDE], 1u);
                 if (pos < cap) buf[(size_t)q * cap + pos] = ((uint64_t)img << 32) | (uint32_t)row;
@@ -110,23 +123,25 @@ flat_scan_kernel(const float* __restrict__ rows, const float* __restrict__ norms
     }
 }
 
-// sorted keys -> (global row, distance)
+// sorted keys -> (global row, distance | similarity).  -0.0 comes back as +0.0 (the two tie, as in
+// Rust's partial_cmp, so they share a key image).
 __global__ void flat_emit_kernel(const uint64_t* __restrict__ buf, uint32_t cap,
                                  const uint32_t* __restrict__ cnt, uint32_t nq, uint32_t k,
                                  uint64_t row_base, uint64_t* __restrict__ ids_out,
-                                 float* __restrict__ dist_out) {
+                                 float* __restrict__ dist_out, int sim) {
     uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= nq * k) return;
     uint32_t q = idx / k, t = idx % k;
     if (t < cnt[(size_t)q * CNT_STRIDE]) {
         uint64_t key = buf[(size_t)q * cap + t];
         uint32_t u = (uint32_t)(key >> 32);
+        if (sim) u = ~u;
         uint32_t bits = (u & 0x80000000u) ? (u ^ 0x80000000u) : ~u;
         ids_out[idx] = row_base + (uint32_t)key;
         dist_out[idx] = __uint_as_float(bits);
     } else {
         ids_out[idx] = UINT64_MAX;
-        dist_out[idx] = INFINITY;
+        dist_out[idx] = sim ? -INFINITY : INFINITY;
     }
 }
 

@@ -219,6 +219,20 @@ class GpuIndex:
         self._ok(self._lib.gvdb_flat_search_batch(self._h, _ptr(q), nq, k, _ptr(ids), _ptr(ds)))
         return ids, ds
 
+    def similarity_search_batch(self, queries, k: int, threshold: float | None = None):
+        """BasicVectorStore::vector_search: (ids, cosine similarities) descending, optional threshold."""
+        q = _np(queries, np.float32)
+        if q.ndim != 2 or q.shape[1] != self.dim:
+            from .errors import DimensionMismatch
+            raise DimensionMismatch(self.dim, q.shape[-1] if q.ndim else 0)
+        nq = q.shape[0]
+        ids = np.full((nq, k), NO_ID, dtype=np.uint64)
+        sims = np.full((nq, k), -np.inf, dtype=np.float32)
+        self._ok(self._lib.gvdb_similarity_search_batch(self._h, _ptr(q), nq, k,
+                                                        0.0 if threshold is None else float(threshold),
+                                                        0 if threshold is None else 1, _ptr(ids), _ptr(sims)))
+        return ids, sims
+
     def flat_search_batch_device(self, queries_t, k: int):
         import torch
         assert queries_t.is_cuda and queries_t.dtype == torch.float32 and queries_t.is_contiguous()

@@ -175,6 +175,18 @@ GVDB_API gvdb_status gvdb_flat_search_batch_device(gvdb_index* h, void* stream, 
                                           uint32_t nq, uint32_t k, uint64_t* ids_out_dev,
                                           float* dist_out_dev);
 
+/* BasicVectorStore::vector_search (src/storage.rs:296-339) + its cosine_similarity (:851-865) for a
+ * batch: similarity = cos (0.0 on a zero norm) over all live rows, rows with similarity < threshold
+ * skipped when use_threshold != 0, descending, ties by row (the reference: sled key order), first k.
+ *   ids_out nq x k (GVDB_NO_ID unfilled), sims_out nq x k (-inf unfilled). */
+GVDB_API gvdb_status gvdb_similarity_search_batch(gvdb_index* h, const float* queries, uint32_t nq, uint32_t k,
+                                                  float threshold, int32_t use_threshold,
+                                                  uint64_t* ids_out, float* sims_out);
+GVDB_API gvdb_status gvdb_similarity_search_batch_device(gvdb_index* h, void* stream, const float* queries_dev,
+                                                         uint32_t nq, uint32_t k, float threshold,
+                                                         int32_t use_threshold, uint64_t* ids_out_dev,
+                                                         float* sims_out_dev);
+
 /* ---- row-sharded search: the two halves around the exchange step -------------------- */
 /* A shard's answer for nq queries is ONE packed record buffer (so the exchange is one
  * all-gather):  [ ids u64 nq x R | ham u32 nq x R | score f32 nq x R ],  16 * nq * R bytes.

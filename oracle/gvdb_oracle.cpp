@@ -214,6 +214,35 @@ GVO_API int64_t gvo_flat_search(const float* q, const float* rows, const uint8_t
     return (int64_t)r;
 }
 
+// BasicVectorStore::vector_search — src/storage.rs:296-339 with its own cosine_similarity
+// (:851-865, identical arithmetic to the quantizer's: 0.0 on a zero norm): every stored vector in
+// iteration order (here: row order; the reference iterates sled keys), `continue` when a
+// threshold is given and similarity < threshold (:312-316), stable sort DESCENDING with
+// partial_cmp().unwrap_or(Equal) (:328-332), truncate(limit) (:333).
+GVO_API int64_t gvo_similarity_search(const float* q, const float* rows, const uint8_t* live, size_t n,
+                                      size_t dim, size_t limit, float threshold, int use_threshold,
+                                      uint64_t* out_idx, float* out_sim) {
+    std::vector<std::pair<size_t, float>> res;
+    res.reserve(n);
+    for (size_t i = 0; i < n; ++i) {
+        if (live && !live[i]) continue;
+        float s = gvo_cosine_similarity(q, rows + i * dim, dim);
+        if (std::isnan(s)) return -1;
+        if (use_threshold && s < threshold) continue;
+        res.push_back({i, s});
+    }
+    std::stable_sort(res.begin(), res.end(),
+                     [](const std::pair<size_t, float>& a, const std::pair<size_t, float>& b) {
+                         return a.second > b.second;
+                     });
+    size_t r = limit < res.size() ? limit : res.size();
+    for (size_t t = 0; t < r; ++t) {
+        out_idx[t] = res[t].first;
+        out_sim[t] = res[t].second;
+    }
+    return (int64_t)r;
+}
+
 // ---------------------------------------------------------------------------
 // Batched, multi-threaded drivers for the CPU baseline.  The reference's only
 // parallelism on this path is "one query per rayon task"

@@ -54,6 +54,8 @@ def lib() -> C.CDLL:
         L.gvo_multi_stage_search_select.restype = i64
         L.gvo_flat_search.argtypes = [vp, vp, vp, sz, sz, sz, vp, vp]
         L.gvo_flat_search.restype = i64
+        L.gvo_similarity_search.argtypes = [vp, vp, vp, sz, sz, sz, f32, C.c_int, vp, vp]
+        L.gvo_similarity_search.restype = i64
         L.gvo_multi_stage_search_batch.argtypes = [vp, sz, vp, vp, sz, sz, f32, sz, sz, vp, vp,
                                                    C.c_int, C.c_int]
         L.gvo_multi_stage_search_batch.restype = i64
@@ -193,6 +195,21 @@ def flat_search(q, rows, k: int, live=None):
     if got < 0:
         raise FloatingPointError("NaN distance")
     return idx[:got], ds[:got]
+
+
+def similarity_search(q, rows, limit: int, threshold=None, live=None):
+    """BasicVectorStore::vector_search: (row idx[k'], cosine SIMILARITY[k']) descending."""
+    q, rows = _f32(q), _f32(rows)
+    n, dim = rows.shape
+    lv = None if live is None else np.ascontiguousarray(live, dtype=np.uint8)
+    idx = np.zeros(max(limit, 1), dtype=np.uint64)
+    sm = np.zeros(max(limit, 1), dtype=np.float32)
+    got = lib().gvo_similarity_search(_p(q), _p(rows), _p(lv), n, dim, limit,
+                                      0.0 if threshold is None else float(threshold),
+                                      0 if threshold is None else 1, _p(idx), _p(sm))
+    if got < 0:
+        raise FloatingPointError("NaN similarity")
+    return idx[:got], sm[:got]
 
 
 def flat_search_batch(queries, rows, k: int, live=None, nthreads: int = 1):

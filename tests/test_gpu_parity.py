@@ -513,3 +513,27 @@ def test_heavily_duplicated_corpus_falls_back_exactly(gv):
         idx.add(rows)
         idx.search_batch(qs[:5], 10, 40)
         assert idx.profile_read()["overflow_fallbacks"] >= 1
+
+
+def test_storage_vector_search_semantics(gv):
+    """gvdb_similarity_search_batch == BasicVectorStore::vector_search (src/storage.rs:296-339):
+    similarity descending, zero-norm rows score 0.0, threshold filter, tombstones."""
+    from grape_vector_db_b200 import synth
+    n, dim, k = 6000, 96, 25
+    rows = synth.lowrank_rows(0, n, dim)
+    rows[7] = 0.0
+    rows[11] = rows[3]                                      # exact tie: row order decides
+    qs = synth.lowrank_queries(0, 9, dim)
+    with gv.GpuIndex(dim) as idx:
+        idx.add(rows)
+        idx.remove(5)
+        live = np.ones(n, dtype=bool)
+        live[5] = False
+        for thr in (None, 0.0, 0.4):
+            ids, sims = idx.similarity_search_batch(qs, k, thr)
+            for qi in range(qs.shape[0]):
+                oi, os_ = oracle.similarity_search(qs[qi], rows, k, thr, live=live)
+                r = len(oi)
+                assert np.array_equal(ids[qi, :r], oi), f"ids differ (query {qi}, threshold {thr})"
+                assert np.array_equal(_bits(sims[qi, :r]), _bits(os_))
+                assert np.all(ids[qi, r:] == gv.NO_ID) and np.all(np.isneginf(sims[qi, r:]))

@@ -188,3 +188,20 @@ def test_golden_fixture_roundtrip():
             idx, sc = oracle.multi_stage_search(qs[qi], rows, case["R"], codes=codes)
             assert idx[:case["k"]].tolist() == case["ids"][qi]
             assert sc[:case["k"]].view(np.uint32).tolist() == case["score_bits"][qi]
+
+
+def test_storage_vector_search_kat():
+    """BasicVectorStore::vector_search (src/storage.rs:296-339): cosine similarity, zero norm -> 0.0,
+    `similarity < threshold` skipped, stable descending sort, truncate."""
+    rows = np.array([[1, 0, 0], [0, 1, 0], [1, 1, 0], [0, 0, 0], [-1, 0, 0], [2, 0, 0]], dtype=np.float32)
+    q = np.array([1, 0, 0], dtype=np.float32)
+    idx, sim = oracle.similarity_search(q, rows, 10)
+    # rows 0 and 5 tie at 1.0 (row order kept), then 1/sqrt(2), then the two zeros (row 1 orthogonal,
+    # row 3 zero norm -> 0.0), then -1
+    assert idx.tolist() == [0, 5, 2, 1, 3, 4]
+    assert sim[0] == 1.0 and sim[1] == 1.0 and sim[3] == 0.0 and sim[4] == 0.0 and sim[5] == -1.0
+    assert sim[2] == np.float32(1.0) / (np.float32(1.0) * np.sqrt(np.float32(2.0)))
+    idx, sim = oracle.similarity_search(q, rows, 10, threshold=0.0)      # -1 < 0 is dropped, 0.0 stays
+    assert idx.tolist() == [0, 5, 2, 1, 3]
+    idx, sim = oracle.similarity_search(q, rows, 2, threshold=0.5)
+    assert idx.tolist() == [0, 5]
