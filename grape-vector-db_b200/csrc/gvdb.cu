@@ -1532,7 +1532,34 @@ gvdb_status gvdb_rescore_keys_device(gvdb_index* h, void* stream, const float* q
         const uint64_t lo = h->windowed ? h->win_first : 0;
         const uint64_t hi = h->windowed ? std::min(h->n_rows, h->win_first + h->win_count) : h->n_rows;
         const uint64_t pairs = (uint64_t)nq * R;
-        {
+        if (pairs > 0x7fffffffull) fail(GVDB_ERR_INVALID_ARGUMENT, "nq * rescore_count too large");
+        if (h->windowed && !h->rows_cover_all()) {
+            // this GPU owns a fraction of the rows: compact the owned pairs (stable, ascending), then
+            // score 32 of them per warp — the work is 1/G of the pairs, not 1/G of every warp
+            Workspace* ws = lease.ws;
+            ws->big_v32.ensure(pairs * 4);
+            ws->big_aux.ensure(256);
+            uint32_t* list = ws->big_v32.as<uint32_t>();
+            uint32_t* count = ws->big_aux.as<uint32_t>();
+            cub::CountingInputIterator<uint32_t> it0(0u);
+            OwnedPair pred{keys_dev, h->cfg.row_base, lo, hi};
+            size_t tmp = 0;
+            CU(cub::DeviceSelect::If(nullptr, tmp, it0, list, count, (int)pairs, pred, st));
+            ws->big_tmp.ensure(tmp + 256);
+            size_t tb = ws->big_tmp.bytes;
+            static bool attr2 = false;   // benign race: idempotent
+            if (!attr2) {
+                CU(cudaFuncSetAttribute(rescore_owned_list_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        64 * (RS_SLAB + 4) * (int)sizeof(float)));
+                attr2 = true;
+            }
+            Timed t(h, ws, st, K_RESCORE);
+            CU(cudaMemsetAsync(scores_out_dev, 0, pairs * 4, st));
+            CU(cub::DeviceSelect::If(ws->big_tmp.p, tb, it0, list, count, (int)pairs, pred, st));
+            rescore_owned_list_kernel<<<(unsigned)((pairs + 31) / 32), 32, (size_t)64 * stride * sizeof(float), st>>>(
+                h->rows_base(), h->norms, h->cfg.row_base, h->dim, stride, queries_dev, keys_dev, list, count, R,
+                scores_out_dev);
+        } else {
             Timed t(h, lease.ws, st, K_RESCORE);
             rescore_slab_kernel<true><<<(unsigned)((pairs + 31) / 32), 32, (size_t)(32 + q_slots) * stride * sizeof(float), st>>>(
                 h->rows_base(), h->norms, h->cfg.row_base, h->dim, stride, q_slots, queries_dev, nullptr, keys_dev, 0,

@@ -17,6 +17,8 @@
 #include <stdint.h>
 
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_select.cuh>
+#include <cub/iterator/counting_input_iterator.cuh>
 
 #include "gvdb_kernels.cuh"
 
@@ -127,5 +129,18 @@ __global__ void bigr_fill_tail_kernel(const BigRCut* __restrict__ cut, uint32_t 
     rec_ids[i] = UINT64_MAX;
     rec_score[i] = -INFINITY;
 }
+
+// predicate of the owner-side compaction (gvdb_rescore_keys_device): pair p is scored here iff
+// its key is filled and its row lies in this index's resident window
+struct OwnedPair {
+    const uint64_t* keys;
+    uint64_t row_base, lo, hi;
+    __host__ __device__ bool operator()(uint32_t p) const {
+        const uint64_t key = keys[p];
+        if (key == UINT64_MAX) return false;
+        const uint64_t local = (key & ((1ull << 40) - 1)) - row_base;
+        return local >= lo && local < hi;
+    }
+};
 
 }  // namespace gvdb

@@ -808,6 +808,72 @@ rescore_slab_kernel(const float* __restrict__ rows, const float* __restrict__ no
     }
 }
 
+// rescore_owned_list_kernel: owner-computes rescoring over a COMPACTED list of pair indices
+// (the pairs whose row this GPU holds: 1/G of them, in ascending order).  One warp per 32 list
+// entries; lane l TMA-copies its candidate row and its query row (entries of one warp may belong
+// to many queries), folds ||q||^2 and the dot product left to right, writes out_score[pair].
+__global__ void __launch_bounds__(32)
+rescore_owned_list_kernel(const float* __restrict__ rows, const float* __restrict__ norms, uint64_t row_base,
+                          int dim, int stride, const float* __restrict__ queries, const uint64_t* __restrict__ keys,
+                          const uint32_t* __restrict__ list, const uint32_t* __restrict__ list_count, uint32_t R,
+                          float* __restrict__ out_score) {
+    extern __shared__ __align__(16) float srow[];            // 32 candidate rows, then 32 query rows
+    float* sq = srow + (size_t)32 * stride;
+    const int lane = threadIdx.x;
+    const uint32_t n_list = *list_count;
+    const uint32_t i = blockIdx.x * 32u + lane;
+    if (blockIdx.x * 32u >= n_list) return;                  // warp-uniform
+    const bool valid = i < n_list;
+    const uint32_t p = valid ? list[i] : 0u;
+    const uint32_t q = p / R;
+    const uint64_t key = valid ? keys[p] : 0ull;
+    const uint32_t my_row = (uint32_t)((key & ((1ull << 40) - 1)) - row_base);
+    __shared__ __align__(8) uint64_t s_bar;
+    const uint32_t bar = smem_u32(&s_bar);
+    if (lane == 0) { mbar_init(bar, 1); fence_mbar_init(); }
+    __syncwarp();
+    uint32_t phase = 0;
+    const uint32_t n_copies = 2u * __popc(__ballot_sync(0xffffffffu, valid));
+    float dot = 0.0f, qq2 = 0.0f;
+    for (int c0 = 0; c0 < dim; c0 += RS_SLAB) {
+        const int cols = min(RS_SLAB, dim - c0);
+        const int nv = cols >> 2;
+        const uint32_t row_bytes = (uint32_t)cols * 4u;
+        if (c0) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+        }
+        if (lane == 0) mbar_expect_tx(bar, n_copies * row_bytes);
+        __syncwarp();
+        if (valid) {
+            tma_bulk_g2s(smem_u32(srow + (size_t)lane * stride), rows + (size_t)my_row * dim + c0, row_bytes, bar);
+            tma_bulk_g2s(smem_u32(sq + (size_t)lane * stride), queries + (size_t)q * dim + c0, row_bytes, bar);
+        }
+        while (!mbar_try_wait(bar, phase)) {}
+        phase ^= 1u;
+        if (valid) {
+            const float4* mine = reinterpret_cast<const float4*>(srow + (size_t)lane * stride);
+            const float4* myq = reinterpret_cast<const float4*>(sq + (size_t)lane * stride);
+#pragma unroll 4
+            for (int v = 0; v < nv; ++v) {
+                const float4 a = myq[v], b = mine[v];
+                dot = __fadd_rn(dot, __fmul_rn(a.x, b.x));
+                dot = __fadd_rn(dot, __fmul_rn(a.y, b.y));
+                dot = __fadd_rn(dot, __fmul_rn(a.z, b.z));
+                dot = __fadd_rn(dot, __fmul_rn(a.w, b.w));
+                qq2 = __fadd_rn(qq2, __fmul_rn(a.x, a.x));
+                qq2 = __fadd_rn(qq2, __fmul_rn(a.y, a.y));
+                qq2 = __fadd_rn(qq2, __fmul_rn(a.z, a.z));
+                qq2 = __fadd_rn(qq2, __fmul_rn(a.w, a.w));
+            }
+        }
+    }
+    if (valid) {
+        const float na = __fsqrt_rn(qq2), nb = norms[my_row];
+        out_score[p] = (na == 0.0f || nb == 0.0f) ? 0.0f : __fdiv_rn(dot, __fmul_rn(na, nb));
+    }
+}
+
 // stage-1 result as keys hamming << 40 | global row (gvdb_stage1_device)
 __global__ void emit_keys_kernel(const uint64_t* __restrict__ buf, uint32_t cap, const uint32_t* __restrict__ cnt,
                                  uint32_t R, uint32_t nq, uint64_t row_base, uint64_t* __restrict__ keys_out) {

@@ -61,6 +61,8 @@ extern "C" {
                              ids_out: *mut u64, scores_out: *mut f32, cand_ids_out: *mut u64, cand_ham_out: *mut u32) -> i32;
     pub fn gvdb_flat_search_batch(h: *mut gvdb_index, queries: *const f32, nq: u32, k: u32,
                                   ids_out: *mut u64, dist_out: *mut f32) -> i32;
+    pub fn gvdb_similarity_search_batch(h: *mut gvdb_index, queries: *const f32, nq: u32, k: u32, threshold: f32,
+                                        use_threshold: i32, ids_out: *mut u64, sims_out: *mut f32) -> i32;
     pub fn gvdb_save(h: *mut gvdb_index, path: *const std::os::raw::c_char) -> i32;
     pub fn gvdb_load(path: *const std::os::raw::c_char, device: i32, out: *mut *mut gvdb_index) -> i32;
     pub fn gvdb_export_rows_ipc(h: *mut gvdb_index, handle_out: *mut u8) -> i32;
