@@ -186,6 +186,7 @@ class QueryParallelSearcher:
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
         self.rows_per_owner = (n_total_rows + self.world - 1) // self.world
+        self._side = None
 
     def search_batch_device(self, my_queries_t, k: int, rescore_count: int, ids_out=None, scores_out=None):
         """my_queries_t: this rank's [nq, dim] batch (same nq on every rank) -> its top-k lists."""
@@ -194,8 +195,20 @@ class QueryParallelSearcher:
         W, R = self.world, rescore_count
         nq, dim = my_queries_t.shape
         dev = my_queries_t.device
-        all_q = _all_gather_rows(my_queries_t, self.group)
-        my_keys = self.index.stage1_device(my_queries_t, R)
+        if my_queries_t.is_cuda:
+            # the query all-gather (the big message) runs on a side stream, under stage 1
+            if self._side is None:
+                self._side = torch.cuda.Stream(dev)
+            cur = torch.cuda.current_stream(dev)
+            self._side.wait_stream(cur)
+            with torch.cuda.stream(self._side):
+                all_q = _all_gather_rows(my_queries_t, self.group)
+            my_keys = self.index.stage1_device(my_queries_t, R)
+            cur.wait_stream(self._side)
+            all_q.record_stream(cur)
+        else:
+            all_q = _all_gather_rows(my_queries_t, self.group)
+            my_keys = self.index.stage1_device(my_queries_t, R)
         all_keys = _all_gather_rows(my_keys, self.group)
         part = self.index.rescore_keys_device(all_q, all_keys)          # [W*nq, R], chunk g = rank g's queries
         by_owner = _all_to_all_rows(part, self.group)                    # chunk o = owner o's scores for MY queries
