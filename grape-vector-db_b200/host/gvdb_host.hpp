@@ -426,6 +426,43 @@ private:
     float total_length_ = 0.0f, average_document_length_ = 0.0f;
 };
 
+// ---- HybridSearchEngine (src/hybrid.rs:166-356), dense side behind `VectorIndex` ------------------------------
+// The reference holds the concrete HnswVectorIndex (:191-206); with the field typed as the trait
+//  the GPU index slots in and rrf_fusion consumes its list unchanged.
+struct HybridSearchRequest {                    // src/types.rs HybridSearchRequest, the fields this path reads
+    std::vector<float> dense_vector;            // empty = None
+    SparseVector sparse_vector;                 // empty indices = None
+    size_t limit = 10;
+};
+
+class HybridSearchEngine {
+public:
+    HybridSearchEngine(std::shared_ptr<VectorIndex> dense_engine, std::shared_ptr<SparseIndex> sparse_engine,
+                       float rrf_k = 60.0f)     // FusionStrategy::RRF { k } (:61-66), default 60.0
+        : dense_(std::move(dense_engine)), sparse_(std::move(sparse_engine)), k_(rrf_k) {}
+    // add_document (:225-247)
+    void add_document(const std::string& id, const std::vector<float>& embedding,
+                      const DocumentSparseRepresentation* sparse_repr) {
+        dense_->add_vector(id, embedding);
+        if (sparse_repr) sparse_->add_document(*sparse_repr);
+    }
+    // search (:286-356): dense list of 2*limit (:295-298), BM25 list of 2*limit (:305-308), fusion
+    // (:331-333), first `limit` (:336)
+    std::vector<Fused> search(const HybridSearchRequest& request) const {
+        std::vector<std::pair<std::string, float>> dense_results, sparse_results;
+        if (!request.dense_vector.empty()) dense_results = dense_->search(request.dense_vector, request.limit * 2);
+        if (!request.sparse_vector.indices.empty())
+            sparse_results = sparse_->search_bm25(request.sparse_vector, request.limit * 2);
+        std::vector<Fused> fused = rrf_fusion(dense_results, sparse_results, {}, k_);
+        if (fused.size() > request.limit) fused.resize(request.limit);
+        return fused;
+    }
+private:
+    std::shared_ptr<VectorIndex> dense_;
+    std::shared_ptr<SparseIndex> sparse_;
+    float k_;
+};
+
 // ---- scatter/gather merge rule (src/distributed/shard.rs:776-783) -----------------------------------------------
 inline std::vector<std::pair<std::string, float>> concat_sort_truncate(
     const std::vector<std::vector<std::pair<std::string, float>>>& shard_results, size_t limit) {

@@ -110,6 +110,34 @@ static void test_sparse_bm25() {                    // src/sparse.rs:153-222
     REQUIRE(idf < 0.0f && r[0].second >= r[1].second);
 }
 
+static void test_hybrid_search() {                 // src/hybrid.rs:286-356 on the GPU dense index
+    auto dense = std::make_shared<GpuVectorIndex>(GpuVectorIndex::Mode::Exact, 4);
+    auto sparse = std::make_shared<SparseIndex>();
+    HybridSearchEngine engine(dense, sparse, 60.0f);
+    // dense order for the query (1,0,0): doc1 (cos 1), doc2, doc3, doc4
+    DocumentSparseRepresentation s1{"doc1", {{7, 1.0f}}, 1.0f}, s3{"doc3", {{7, 3.0f}}, 3.0f};
+    engine.add_document("doc1", {1.0f, 0.0f, 0.0f}, &s1);
+    engine.add_document("doc2", {0.9f, 0.2f, 0.0f}, nullptr);
+    engine.add_document("doc3", {0.5f, 0.5f, 0.0f}, &s3);
+    engine.add_document("doc4", {0.0f, 1.0f, 0.0f}, nullptr);
+    HybridSearchRequest req;
+    req.dense_vector = {1.0f, 0.0f, 0.0f};
+    req.sparse_vector = SparseVector{{7}, {1.0f}, 10};
+    req.limit = 3;
+    auto dense_only = dense->search(req.dense_vector, 6);
+    REQUIRE(dense_only.size() == 4 && dense_only[0].first == "doc1" && dense_only[1].first == "doc2" &&
+            dense_only[2].first == "doc3" && dense_only[3].first == "doc4");
+    auto bm25 = sparse->search_bm25(req.sparse_vector, 6);
+    REQUIRE(bm25.size() == 2);
+    // idf = ln((2 - 2 + 0.5) / (2 + 0.5)) < 0: the higher tf scores LOWER, so doc1 leads the sparse list
+    REQUIRE(bm25[0].first == "doc1" && bm25[1].first == "doc3");
+    auto res = engine.search(req);
+    REQUIRE(res.size() == 3);
+    REQUIRE(res[0].id == "doc1" && res[0].score == 1.0f / 61.0f + 1.0f / 61.0f);
+    REQUIRE(res[1].id == "doc3" && res[1].score == 1.0f / 63.0f + 1.0f / 62.0f);
+    REQUIRE(res[2].id == "doc2" && res[2].score == 1.0f / 62.0f);
+}
+
 int main() {
     test_binary_quantization();
     test_hamming_distance();
@@ -117,6 +145,7 @@ int main() {
     test_vector_index_trait();
     test_rrf_fusion();
     test_sparse_bm25();
+    test_hybrid_search();
     std::printf("host mirror tests: all passed\n");
     return 0;
 }
