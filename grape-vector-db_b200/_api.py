@@ -3,7 +3,8 @@ from .errors import (ConfigError, DimensionMismatch, IndexError_, IndexNotBuilt,
                      InvalidVectorDimension, NotImplementedError_, QuantizationError,
                      VectorDbError)
 from .index import NO_ID, GpuIndex  # noqa: F401
+from .sparse import GpuSparseIndex  # noqa: F401
 
-__all__ = ["GpuIndex", "NO_ID", "VectorDbError", "IndexNotBuilt", "DimensionMismatch",
+__all__ = ["GpuIndex", "GpuSparseIndex", "NO_ID", "VectorDbError", "IndexNotBuilt", "DimensionMismatch",
            "InvalidVectorDimension", "QuantizationError", "IndexError_", "ConfigError",
            "NotImplementedError_"]

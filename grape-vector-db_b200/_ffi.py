@@ -84,6 +84,11 @@ SYMBOLS = {
     "gvdb_attach_peer_rows_ipc": (_i32, [_vp, _u32, _u64, _u32, _vp]),
     "gvdb_rows_device_ptr": (_vp, [_vp]),
     "gvdb_attach_peer_rows_ptr": (_i32, [_vp, _u32, _u64, _u32, _vp]),
+    "gvdb_sparse_create": (_i32, [_i32, C.c_float, C.c_float, C.POINTER(_vp)]),
+    "gvdb_sparse_destroy": (None, [_vp]),
+    "gvdb_sparse_build": (_i32, [_vp, _u64, _u32, _vp, _vp, _vp, _vp]),
+    "gvdb_sparse_average_document_length": (C.c_float, [_vp]),
+    "gvdb_sparse_search_bm25_batch": (_i32, [_vp, _u32, _vp, _vp, _vp, _u32, _vp, _vp]),
     "gvdb_profile_enable": (_i32, [_vp, _i32]),
     "gvdb_profile_read": (_i32, [_vp, _vp, _i32]),
 }

@@ -29,6 +29,7 @@
 #include "gvdb_kernels.cuh"
 #include "gvdb_tc.cuh"
 #include "gvdb_bigr.cuh"
+#include "gvdb_sparse.cuh"
 
 namespace {
 
@@ -1660,6 +1661,162 @@ gvdb_status gvdb_attach_peer_rows_ptr(gvdb_index* h, uint32_t n_owners, uint64_t
         std::vector<const float*> ptrs(n_owners, nullptr);
         for (uint32_t o = 0; o < n_owners; ++o) ptrs[o] = o == my_owner ? h->rows : static_cast<const float*>(row_ptrs[o]);
         attach_peers(h, n_owners, rows_per_owner, my_owner, ptrs);
+    });
+}
+
+// ---- BM25 ---------------------------------------------------------------------------------------------
+struct gvdb_sparse {
+    int device = 0;
+    float k1 = 1.2f, b = 0.75f, avg_len = 0.0f;
+    uint64_t n_docs = 0, n_post = 0;
+    uint32_t n_terms = 0;
+    std::vector<uint64_t> h_post_off;          // host copy: document frequencies for the idf
+    DevBuf post_off, post_doc, post_tf, doc_len;
+    DevBuf acc, hist, cut, keys, q_off, q_terms, q_tfs, q_idf, doc_out, score_out;
+    cudaStream_t stream = nullptr;
+    std::mutex mu;                             // one search at a time per handle
+};
+
+gvdb_status gvdb_sparse_create(int32_t device, float k1, float b, gvdb_sparse** out) {
+    return guarded([&] {
+        need(out, "out");
+        *out = nullptr;
+        int ndev = 0;
+        if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+            fail(GVDB_ERR_INDEX, "no usable CUDA device (there is no CPU fallback)");
+        if (device < 0 || device >= ndev) fail(GVDB_ERR_INVALID_ARGUMENT, "bad device ordinal");
+        DeviceGuard dg(device);
+        std::unique_ptr<gvdb_sparse> s(new gvdb_sparse());
+        s->device = device; s->k1 = k1; s->b = b;
+        CU(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+        *out = s.release();
+    });
+}
+
+void gvdb_sparse_destroy(gvdb_sparse* s) {
+    if (!s) return;
+    int prev = 0;
+    cudaGetDevice(&prev);
+    cudaSetDevice(s->device);
+    cudaDeviceSynchronize();
+    for (DevBuf* b : {&s->post_off, &s->post_doc, &s->post_tf, &s->doc_len, &s->acc, &s->hist, &s->cut, &s->keys,
+                      &s->q_off, &s->q_terms, &s->q_tfs, &s->q_idf, &s->doc_out, &s->score_out}) b->release();
+    if (s->stream) cudaStreamDestroy(s->stream);
+    delete s;
+    cudaSetDevice(prev);
+}
+
+gvdb_status gvdb_sparse_build(gvdb_sparse* s, uint64_t n_docs, uint32_t n_terms, const uint64_t* post_off,
+                              const uint32_t* post_doc, const float* post_tf, const float* doc_len) {
+    return guarded([&] {
+        need(s, "sparse index"); need(post_off, "post_off");
+        if (n_docs > 0xfffffff0ull) fail(GVDB_ERR_INVALID_ARGUMENT, "at most 2^32-16 documents");
+        const uint64_t n_post = post_off[n_terms];
+        if (n_post) { need(post_doc, "post_doc"); need(post_tf, "post_tf"); need(doc_len, "doc_len"); }
+        std::lock_guard<std::mutex> lk(s->mu);
+        DeviceGuard dg(s->device);
+        s->h_post_off.assign(post_off, post_off + n_terms + 1);
+        // the reference's average: every postings entry adds its document's length (src/sparse.rs:96-104)
+        float total = 0.0f;
+        for (uint32_t t = 0; t < n_terms; ++t) {
+            if (post_off[t + 1] < post_off[t]) fail(GVDB_ERR_INVALID_ARGUMENT, "post_off must be non-decreasing");
+            for (uint64_t p = post_off[t]; p < post_off[t + 1]; ++p) {
+                if (post_doc[p] >= n_docs) fail(GVDB_ERR_INVALID_ARGUMENT, "posting refers to a document >= n_docs");
+                // one entry per (term, document): the accumulate kernel touches each accumulator once per launch
+                if (p > post_off[t] && post_doc[p] <= post_doc[p - 1])
+                    fail(GVDB_ERR_INVALID_ARGUMENT, "documents must be strictly ascending inside a term's postings");
+                total = total + doc_len[post_doc[p]];
+            }
+        }
+        s->avg_len = n_docs ? total / (float)n_docs : 0.0f;
+        s->n_docs = n_docs; s->n_terms = n_terms; s->n_post = n_post;
+        s->post_off.ensure((size_t)(n_terms + 1) * 8);
+        s->post_doc.ensure(std::max<size_t>(4, n_post * 4));
+        s->post_tf.ensure(std::max<size_t>(4, n_post * 4));
+        s->doc_len.ensure(std::max<size_t>(4, n_docs * 4));
+        CU(cudaMemcpy(s->post_off.p, post_off, (size_t)(n_terms + 1) * 8, cudaMemcpyHostToDevice));
+        if (n_post) {
+            CU(cudaMemcpy(s->post_doc.p, post_doc, n_post * 4, cudaMemcpyHostToDevice));
+            CU(cudaMemcpy(s->post_tf.p, post_tf, n_post * 4, cudaMemcpyHostToDevice));
+        }
+        if (n_docs) CU(cudaMemcpy(s->doc_len.p, doc_len, n_docs * 4, cudaMemcpyHostToDevice));
+    });
+}
+
+float gvdb_sparse_average_document_length(const gvdb_sparse* s) { return s ? s->avg_len : 0.0f; }
+
+gvdb_status gvdb_sparse_search_bm25_batch(gvdb_sparse* s, uint32_t nq, const uint64_t* q_off, const uint32_t* q_terms,
+                                          const float* q_tfs, uint32_t limit, uint64_t* doc_out, float* score_out) {
+    return guarded([&] {
+        need(s, "sparse index");
+        if (nq == 0 || limit == 0) return;
+        need(q_off, "q_off"); need(doc_out, "doc_out"); need(score_out, "score_out");
+        if (limit > (uint32_t)SORT_N) fail(GVDB_ERR_NOT_IMPLEMENTED, "BM25 limit > 4096 is not implemented");
+        std::lock_guard<std::mutex> lk(s->mu);
+        for (uint64_t i = 0; i < (uint64_t)nq * limit; ++i) { doc_out[i] = UINT64_MAX; score_out[i] = -INFINITY; }
+        if (s->n_docs == 0) return;                                   // src/sparse.rs:161-163
+        DeviceGuard dg(s->device);
+        cudaStream_t st = s->stream;
+        const uint64_t nt = q_off[nq];
+        if (nt) { need(q_terms, "q_terms"); need(q_tfs, "q_tfs"); }
+        // idf on the host (libm logf == Rust's f32::ln); absent terms are dropped (:169)
+        std::vector<uint32_t> terms(nt);
+        std::vector<float> idf(nt);
+        uint32_t max_terms = 0;
+        for (uint32_t q = 0; q < nq; ++q) max_terms = std::max<uint32_t>(max_terms, (uint32_t)(q_off[q + 1] - q_off[q]));
+        for (uint64_t i = 0; i < nt; ++i) {
+            const uint32_t t = q_terms[i];
+            const uint64_t df = t < s->n_terms ? s->h_post_off[t + 1] - s->h_post_off[t] : 0;
+            terms[i] = df ? t : s->n_terms;                            // n_terms = "absent"
+            idf[i] = df ? std::log(((float)s->n_docs - (float)df + 0.5f) / ((float)df + 0.5f)) : 0.0f;
+        }
+        const uint32_t QC = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(std::min<uint64_t>(nq, 64), (512ull << 20) / (s->n_docs * 4)));
+        const uint32_t key_cap = SORT_N;
+        s->acc.ensure((size_t)QC * s->n_docs * 4);
+        s->hist.ensure((size_t)QC * BM25_BINS * 4);
+        s->cut.ensure((size_t)QC * sizeof(Bm25Cut));
+        s->keys.ensure((size_t)QC * key_cap * 8);
+        s->q_off.ensure((size_t)(nq + 1) * 8);
+        s->q_terms.ensure(std::max<size_t>(4, nt * 4));
+        s->q_tfs.ensure(std::max<size_t>(4, nt * 4));
+        s->q_idf.ensure(std::max<size_t>(4, nt * 4));
+        s->doc_out.ensure((size_t)QC * limit * 8);
+        s->score_out.ensure((size_t)QC * limit * 4);
+        CU(cudaMemcpyAsync(s->q_off.p, q_off, (size_t)(nq + 1) * 8, cudaMemcpyHostToDevice, st));
+        if (nt) {
+            CU(cudaMemcpyAsync(s->q_terms.p, terms.data(), nt * 4, cudaMemcpyHostToDevice, st));
+            CU(cudaMemcpyAsync(s->q_tfs.p, q_tfs, nt * 4, cudaMemcpyHostToDevice, st));
+            CU(cudaMemcpyAsync(s->q_idf.p, idf.data(), nt * 4, cudaMemcpyHostToDevice, st));
+        }
+        cudaDeviceProp prop;
+        CU(cudaGetDeviceProperties(&prop, s->device));
+        const unsigned gx = (unsigned)prop.multiProcessorCount * 2;
+        for (uint32_t q0 = 0; q0 < nq; q0 += QC) {
+            const uint32_t m = std::min(QC, nq - q0);
+            CU(cudaMemsetAsync(s->acc.p, 0xFF, (size_t)m * s->n_docs * 4, st));
+            CU(cudaMemsetAsync(s->hist.p, 0, (size_t)m * BM25_BINS * 4, st));
+            CU(cudaMemsetAsync(s->cut.p, 0, (size_t)m * sizeof(Bm25Cut), st));
+            for (uint32_t rank = 0; rank < max_terms; ++rank)
+                bm25_accumulate_kernel<<<dim3(gx, m), 256, 0, st>>>(
+                    s->post_off.as<uint64_t>(), s->post_doc.as<uint32_t>(), s->post_tf.as<float>(), s->doc_len.as<float>(),
+                    s->n_terms, s->q_off.as<uint64_t>(), s->q_terms.as<uint32_t>(), s->q_tfs.as<float>(),
+                    s->q_idf.as<float>(), q0, (int)rank, s->k1, s->b, s->avg_len, s->n_docs, s->acc.as<uint32_t>());
+            for (int level = 0; level < 4; ++level) {
+                if (level) CU(cudaMemsetAsync(s->hist.p, 0, (size_t)m * BM25_BINS * 4, st));
+                bm25_hist_kernel<<<dim3(gx, m), 256, 0, st>>>(s->acc.as<uint32_t>(), s->n_docs, limit,
+                                                             s->hist.as<uint32_t>(), s->cut.as<Bm25Cut>(), level);
+                bm25_cut_kernel<<<m, 256, 0, st>>>(s->hist.as<uint32_t>(), limit, s->cut.as<Bm25Cut>(), level);
+            }
+            bm25_compact_kernel<<<dim3(gx, m), 256, 0, st>>>(s->acc.as<uint32_t>(), s->n_docs, s->cut.as<Bm25Cut>(),
+                                                            s->keys.as<uint64_t>(), key_cap);
+            bm25_topk_kernel<<<m, SORT_THREADS, SORT_N * 8, st>>>(s->keys.as<uint64_t>(), key_cap, s->cut.as<Bm25Cut>(),
+                                                                 s->acc.as<uint32_t>(), s->n_docs, limit,
+                                                                 s->doc_out.as<uint64_t>(), s->score_out.as<float>());
+            CU(cudaGetLastError());
+            CU(cudaMemcpyAsync(doc_out + (size_t)q0 * limit, s->doc_out.p, (size_t)m * limit * 8, cudaMemcpyDeviceToHost, st));
+            CU(cudaMemcpyAsync(score_out + (size_t)q0 * limit, s->score_out.p, (size_t)m * limit * 4, cudaMemcpyDeviceToHost, st));
+            CU(cudaStreamSynchronize(st));
+        }
     });
 }
 

@@ -1,0 +1,190 @@
+// gvdb_sparse.cuh — BM25 over CSR postings on the GPU: the sparse list that
+// HybridSearchEngine fuses with the dense one (/root/reference/src/hybrid.rs:305-308).
+// SparseIndex::search_bm25 (/root/reference/src/sparse.rs:153-222), per query:
+//   for each query term i, in query order, for each posting (doc, tf, len) of that term:
+//       score[doc] (inserted as 0.0 on first touch) += q_tf[i] * tf' * idf[i]
+//       tf' = tf * (k1 + 1) / (tf + k1 * (1 - b + b * (len / avg_len)))
+//   sort by score descending, truncate(limit)          (ties: the reference's HashMap order is
+//                                                       unspecified; here doc id ascending)
+// Exactness: idf = ln((N - df + 0.5) / (df + 0.5)) is computed on the HOST (libm logf, as Rust's
+// f32::ln) and passed in; the rest is f32 + - * / in the reference's order (__f*_rn, no FMA).  A
+// document appears at most once in a term's postings, so one launch per term rank touches every
+// accumulator at most once: additions happen in query-term order, like the reference's loop.
+//   bm25_accumulate_kernel   one term rank of every query of the chunk
+//   bm25_hist_kernel         histogram levels: 16 high / 16 low bits of the descending score image,
+//                            then 16 high / 16 low bits of the document number among the ties
+//   bm25_cut_kernel          the exact 32-bit image of the limit-th best score and the last tying
+//                            document kept
+//   bm25_compact_kernel      keys (descending image << 32 | doc) inside the cut: exactly
+//                            min(limit, touched documents), however many documents tie
+//   bm25_topk_kernel         block bitonic sort of those keys, first `limit`
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "gvdb_kernels.cuh"
+
+namespace gvdb {
+
+constexpr uint32_t BM25_ABSENT = 0xFFFFFFFFu;     // accumulator bit pattern of "document not touched" (a NaN)
+constexpr int BM25_BINS = 65536;
+
+// per query: the cut found level by level (see bm25_cut_kernel)
+struct Bm25Cut {
+    uint32_t present;      // documents touched by the query
+    uint32_t bstar, below; // level 0: bin (16 high image bits) holding the want-th best, documents in better bins
+    uint32_t thr32, above; // level 1: exact image of the want-th best score, documents strictly better than it
+    uint32_t m;            //          documents at or above thr32 (m - above tie exactly at the cut)
+    uint32_t dstar, dbelow;// level 2: among the ties, bin (16 high document bits) of the last one kept
+    uint32_t doc_thr;      // level 3: ties are kept up to this document number (ascending = the tie order)
+    uint32_t appended, pad0, pad1;
+};
+
+// grid.y = query of the chunk; the query's rank-th term (if it has one) against its postings
+__global__ void __launch_bounds__(256)
+bm25_accumulate_kernel(const uint64_t* __restrict__ post_off, const uint32_t* __restrict__ post_doc,
+                       const float* __restrict__ post_tf, const float* __restrict__ doc_len, uint32_t n_terms,
+                       const uint64_t* __restrict__ q_off, const uint32_t* __restrict__ q_terms,
+                       const float* __restrict__ q_tfs, const float* __restrict__ q_idf, uint32_t q0, int rank,
+                       float k1, float b, float avg_len, uint64_t n_docs, uint32_t* __restrict__ acc) {
+    const uint32_t q = q0 + blockIdx.y;
+    const uint64_t t0 = q_off[q], t1 = q_off[q + 1];
+    if (t0 + rank >= t1) return;
+    const uint32_t term = q_terms[t0 + rank];
+    if (term >= n_terms) return;
+    const float qtf = q_tfs[t0 + rank], idf = q_idf[t0 + rank];
+    const uint64_t p0 = post_off[term], p1 = post_off[term + 1];
+    uint32_t* mine = acc + (size_t)blockIdx.y * n_docs;
+    const float k1p1 = __fadd_rn(k1, 1.0f), one_minus_b = __fsub_rn(1.0f, b);
+    for (uint64_t p = p0 + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; p < p1; p += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t doc = post_doc[p];
+        const float tf = post_tf[p], len = doc_len[doc];
+        // (tf * (k1 + 1)) / (tf + k1 * (1 - b + b * (len / avg_len)))
+        const float denom = __fadd_rn(tf, __fmul_rn(k1, __fadd_rn(one_minus_b, __fmul_rn(b, __fdiv_rn(len, avg_len)))));
+        const float tfc = __fdiv_rn(__fmul_rn(tf, k1p1), denom);
+        const float s = __fmul_rn(__fmul_rn(qtf, tfc), idf);
+        const uint32_t old = mine[doc];
+        const float base = old == BM25_ABSENT ? 0.0f : __uint_as_float(old);
+        mine[doc] = __float_as_uint(__fadd_rn(base, s));
+    }
+}
+
+// descending image of a present score; a NaN score cannot be produced by finite inputs
+__device__ __forceinline__ uint32_t bm25_desc_image(uint32_t bits) { return ~f32_asc_key(__uint_as_float(bits)); }
+
+// Four histogram levels find the exact cut without sorting the accumulator:
+//   level 0  16 high bits of every present document's image (+ the present count)
+//   level 1  16 low bits of the images inside the level-0 cut bin          -> thr32, above, m
+//   level 2  16 high bits of the DOCUMENT NUMBER of the documents tying at thr32   (only if m > want)
+//   level 3  16 low bits of the document number inside the level-2 bin     -> doc_thr
+// so exactly want = min(limit, present) documents pass "image < thr32 or (image == thr32 and
+// doc <= doc_thr)", however many documents share the cut score (BM25 over tf = count/len data ties
+// by the million).
+__global__ void __launch_bounds__(256)
+bm25_hist_kernel(const uint32_t* __restrict__ acc, uint64_t n_docs, uint32_t limit, uint32_t* __restrict__ hist,
+                 Bm25Cut* __restrict__ cut, int level) {
+    const uint32_t* mine = acc + (size_t)blockIdx.y * n_docs;
+    uint32_t* h = hist + (size_t)blockIdx.y * BM25_BINS;
+    const Bm25Cut c = cut[blockIdx.y];
+    if (level >= 1 && c.present == 0) return;
+    if (level >= 2 && c.m == min(limit, c.present)) return;          // no surplus ties: every tie is kept
+    uint32_t present = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_docs; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t v = mine[i];
+        if (v == BM25_ABSENT) continue;
+        const uint32_t img = bm25_desc_image(v);
+        if (level == 0) { atomicAdd(&h[img >> 16], 1u); ++present; }
+        else if (level == 1) { if ((img >> 16) == c.bstar) atomicAdd(&h[img & 0xffffu], 1u); }
+        else if (img == c.thr32) {
+            const uint32_t d = (uint32_t)i;
+            if (level == 2) atomicAdd(&h[d >> 16], 1u);
+            else if ((d >> 16) == c.dstar) atomicAdd(&h[d & 0xffffu], 1u);
+        }
+    }
+    if (level == 0) {
+        for (int o = 16; o > 0; o >>= 1) present += __shfl_xor_sync(0xffffffffu, present, o);
+        if ((threadIdx.x & 31) == 0 && present) atomicAdd(&cut[blockIdx.y].present, present);
+    }
+}
+
+// one CTA per query: the bin holding the want-th entry of this level's histogram
+__global__ void __launch_bounds__(256)
+bm25_cut_kernel(const uint32_t* __restrict__ hist, uint32_t limit, Bm25Cut* __restrict__ cut, int level) {
+    __shared__ uint32_t part[256];
+    const uint32_t* h = hist + (size_t)blockIdx.x * BM25_BINS;
+    Bm25Cut* c = cut + blockIdx.x;
+    const uint32_t want_all = min(limit, c->present);
+    if (level >= 2 && c->m == want_all) { if (threadIdx.x == 0) c->doc_thr = 0xFFFFFFFFu; return; }
+    const uint32_t want = level == 0 ? want_all : level == 1 ? want_all - c->below
+                        : level == 2 ? want_all - c->above : want_all - c->above - c->dbelow;
+    constexpr int PER = BM25_BINS / 256;
+    uint32_t sum = 0;
+    for (int i = 0; i < PER; ++i) sum += h[threadIdx.x * PER + i];
+    part[threadIdx.x] = sum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (want_all == 0) { c->bstar = 0; c->below = 0; c->thr32 = 0; c->above = 0; c->m = 0; c->doc_thr = 0; return; }
+        uint32_t run = 0;
+        int t = 0;
+        for (; t < 255; ++t) { if (run + part[t] >= want) break; run += part[t]; }
+        for (int i = 0; i < PER; ++i) {
+            const uint32_t hv = h[t * PER + i];
+            if (run + hv >= want) {
+                const uint32_t bin = (uint32_t)(t * PER + i);
+                if (level == 0) { c->bstar = bin; c->below = run; }
+                else if (level == 1) { c->thr32 = (c->bstar << 16) | bin; c->above = c->below + run; c->m = c->below + run + hv; }
+                else if (level == 2) { c->dstar = bin; c->dbelow = run; }
+                else c->doc_thr = (c->dstar << 16) | bin;
+                break;
+            }
+            run += hv;
+        }
+    }
+}
+
+// keys (image << 32 | doc) of the documents inside the cut: exactly min(limit, present) of them
+__global__ void __launch_bounds__(256)
+bm25_compact_kernel(const uint32_t* __restrict__ acc, uint64_t n_docs, Bm25Cut* __restrict__ cut,
+                    uint64_t* __restrict__ keys, uint32_t key_cap) {
+    const uint32_t* mine = acc + (size_t)blockIdx.y * n_docs;
+    Bm25Cut* c = cut + blockIdx.y;
+    if (c->m == 0) return;
+    const uint32_t thr = c->thr32, doc_thr = c->doc_thr;
+    uint64_t* out = keys + (size_t)blockIdx.y * key_cap;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_docs; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t v = mine[i];
+        if (v == BM25_ABSENT) continue;
+        const uint32_t img = bm25_desc_image(v);
+        if (img < thr || (img == thr && (uint32_t)i <= doc_thr)) {
+            const uint32_t pos = atomicAdd(&c->appended, 1u);
+            if (pos < key_cap) out[pos] = ((uint64_t)img << 32) | (uint32_t)i;
+        }
+    }
+}
+
+// one CTA per query: sort the compacted keys (m <= SORT_N), emit (doc, score) for the first `limit`;
+// the exact score bits come back from the accumulator (the image folds -0.0 into +0.0)
+__global__ void __launch_bounds__(SORT_THREADS)
+bm25_topk_kernel(const uint64_t* __restrict__ keys, uint32_t key_cap, const Bm25Cut* __restrict__ cut,
+                 const uint32_t* __restrict__ acc, uint64_t n_docs, uint32_t limit, uint64_t* __restrict__ doc_out,
+                 float* __restrict__ score_out) {
+    extern __shared__ __align__(16) uint64_t skeys[];
+    const uint32_t q = blockIdx.x;
+    const uint32_t m = min(min(cut[q].present, limit), key_cap);
+    const uint32_t n_eff = max(64u, next_pow2(m));
+    for (uint32_t i = threadIdx.x; i < n_eff; i += blockDim.x) skeys[i] = i < m ? keys[(size_t)q * key_cap + i] : UINT64_MAX;
+    __syncthreads();
+    bitonic_sort_smem(skeys, n_eff);
+    for (uint32_t t = threadIdx.x; t < limit; t += blockDim.x) {
+        if (t < m) {
+            const uint32_t doc = (uint32_t)skeys[t];
+            doc_out[(size_t)q * limit + t] = doc;
+            score_out[(size_t)q * limit + t] = __uint_as_float(acc[(size_t)q * n_docs + doc]);
+        } else {
+            doc_out[(size_t)q * limit + t] = UINT64_MAX;
+            score_out[(size_t)q * limit + t] = -INFINITY;
+        }
+    }
+}
+
+}  // namespace gvdb

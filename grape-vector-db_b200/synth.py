@@ -108,3 +108,58 @@ def iid_rows_torch(first: int, n: int, dim: int, device, seed: int = 42, stream:
     import torch
     idx = torch.arange(n * dim, dtype=torch.int64, device=device) + first * dim
     return _draw_t(seed, stream, idx).reshape(n, dim).to(torch.float32).contiguous()
+
+
+# ---- sparse side of the hybrid config ------------------------------
+STREAM_SPARSE_DOC, STREAM_SPARSE_QUERY = 6, 7
+
+
+def _zipf_terms(seed: int, stream: int, first: int, n: int, vocab: int) -> np.ndarray:
+    """n term ids drawn Zipf(1.0) over [0, vocab): inverse CDF on a 32-bit hash uniform."""
+    w = 1.0 / np.arange(1, vocab + 1, dtype=np.float64)
+    cdf = np.cumsum(w)
+    cdf /= cdf[-1]
+    with np.errstate(over="ignore"):
+        base = np.uint64((seed * _M1 + stream * _M2) & 0xFFFFFFFFFFFFFFFF)
+        h = _mix_np(np.arange(n, dtype=np.uint64) + np.uint64(first) + base)
+    u = ((h >> np.uint64(32)).astype(np.float64) + 0.5) / 4294967296.0
+    return np.minimum(np.searchsorted(cdf, u, side="left"), vocab - 1).astype(np.uint32)
+
+
+def sparse_corpus(n_docs: int, vocab: int = 100_000, tokens_per_doc: int = 32, seed: int = 42):
+    """Each document: `tokens_per_doc` Zipf term draws, tf = count / tokens (SimpleTokenizer::tokenize,
+    src/sparse.rs:288-315), document_length = sum of the tfs in ascending term order (:341).
+    Returns CSR postings by term (post_off u64 [vocab+1], post_doc u32, post_tf f32) with documents
+    ascending inside each term, and doc_len f32 [n_docs]."""
+    t = _zipf_terms(seed, STREAM_SPARSE_DOC, 0, n_docs * tokens_per_doc, vocab).reshape(n_docs, tokens_per_doc)
+    t = np.sort(t, axis=1)
+    doc = np.repeat(np.arange(n_docs, dtype=np.uint32), tokens_per_doc).reshape(n_docs, tokens_per_doc)
+    first = np.ones_like(t, dtype=bool)
+    first[:, 1:] = t[:, 1:] != t[:, :-1]
+    flat_first = np.flatnonzero(first.ravel())
+    counts = np.diff(np.append(flat_first, t.size))
+    e_term, e_doc = t.ravel()[flat_first], doc.ravel()[flat_first]
+    e_tf = counts.astype(np.float32) / np.float32(tokens_per_doc)
+    doc_len = np.zeros(n_docs, dtype=np.float32)
+    # sequential f32 sum per document, in ascending term order (at most tokens_per_doc terms)
+    start = np.flatnonzero(np.r_[True, e_doc[1:] != e_doc[:-1]])
+    rank = np.arange(e_doc.size) - np.repeat(start, np.diff(np.append(start, e_doc.size)))
+    for r in range(int(rank.max()) + 1 if rank.size else 0):
+        m = rank == r
+        doc_len[e_doc[m]] = doc_len[e_doc[m]] + e_tf[m]
+    order = np.lexsort((e_doc, e_term))
+    post_doc, post_tf = e_doc[order], e_tf[order]
+    post_off = np.zeros(vocab + 1, dtype=np.uint64)
+    np.cumsum(np.bincount(e_term, minlength=vocab), out=post_off[1:])
+    return post_off, np.ascontiguousarray(post_doc), np.ascontiguousarray(post_tf), doc_len
+
+
+def sparse_queries(nq: int, vocab: int = 100_000, terms_per_query: int = 4, seed: int = 42):
+    """nq queries of `terms_per_query` Zipf term draws, tokenised like a document: distinct terms in
+    ascending order with tf = count / terms_per_query.  Returns a list of (term ids u32, tfs f32)."""
+    t = _zipf_terms(seed, STREAM_SPARSE_QUERY, 0, nq * terms_per_query, vocab).reshape(nq, terms_per_query)
+    out = []
+    for row in t:
+        ids, cnt = np.unique(row, return_counts=True)
+        out.append((ids.astype(np.uint32), cnt.astype(np.float32) / np.float32(terms_per_query)))
+    return out

@@ -255,6 +255,25 @@ GVDB_API const void* gvdb_rows_device_ptr(const gvdb_index* h);
 GVDB_API gvdb_status gvdb_attach_peer_rows_ptr(gvdb_index* h, uint32_t n_owners, uint64_t rows_per_owner,
                                                uint32_t my_owner, const void* const* row_ptrs /* n_owners */);
 
+/* ---- sparse side of the hybrid search: BM25 over CSR postings ---------- */
+/* SparseIndex (src/sparse.rs:31-222) as an immutable snapshot: postings in CSR form by term id,
+ * documents numbered 0..n_docs-1, ascending inside each term's list.
+ *   post_off n_terms+1, post_doc / post_tf one entry per posting, doc_len n_docs (all HOST).
+ * average_document_length follows the reference (:96-104): the sum of document_length over ALL
+ * postings entries (a document counts once per distinct term), in CSR order, divided by n_docs. */
+typedef struct gvdb_sparse gvdb_sparse;
+GVDB_API gvdb_status gvdb_sparse_create(int32_t device, float k1, float b, gvdb_sparse** out);
+GVDB_API void gvdb_sparse_destroy(gvdb_sparse* s);
+GVDB_API gvdb_status gvdb_sparse_build(gvdb_sparse* s, uint64_t n_docs, uint32_t n_terms, const uint64_t* post_off,
+                                       const uint32_t* post_doc, const float* post_tf, const float* doc_len);
+GVDB_API float gvdb_sparse_average_document_length(const gvdb_sparse* s);
+/* SparseIndex::search_bm25 (:153-199) for a batch of sparse query vectors (CSR: q_off nq+1,
+ * q_terms / q_tfs), all HOST.  doc_out nq x limit (GVDB_NO_ID unfilled), score_out nq x limit
+ * (-inf unfilled); order: score descending, ties by document number. */
+GVDB_API gvdb_status gvdb_sparse_search_bm25_batch(gvdb_sparse* s, uint32_t nq, const uint64_t* q_off,
+                                                   const uint32_t* q_terms, const float* q_tfs, uint32_t limit,
+                                                   uint64_t* doc_out, float* score_out);
+
 /* ---- measurement hooks ---------------------------------------------------------------- */
 /* When enabled, every kernel the library launches is bracketed by CUDA events on the stream
  * it is launched on; times are accumulated at the call's final synchronisation. */

@@ -205,3 +205,23 @@ def test_storage_vector_search_kat():
     assert idx.tolist() == [0, 5, 2, 1, 3]
     idx, sim = oracle.similarity_search(q, rows, 2, threshold=0.5)
     assert idx.tolist() == [0, 5]
+
+
+def test_sparse_synthetic_corpus_shape():
+    """The C4 sparse generator: tf = count/tokens, document_length = sum of tfs = 1,
+    CSR postings ascending by document inside a term; the oracle's BM25 runs on it."""
+    from grape_vector_db_b200 import synth
+    post_off, post_doc, post_tf, doc_len = synth.sparse_corpus(2000, vocab=500)
+    assert post_off[-1] == post_doc.size == post_tf.size and doc_len.shape == (2000,)
+    assert np.all(doc_len == np.float32(1.0))
+    for t in range(500):
+        d = post_doc[int(post_off[t]):int(post_off[t + 1])]
+        assert np.all(d[1:] > d[:-1])
+    per_doc = np.zeros(2000)
+    np.add.at(per_doc, post_doc, post_tf.astype(np.float64))
+    assert np.allclose(per_doc, 1.0)
+    again = synth.sparse_corpus(2000, vocab=500)
+    assert all(np.array_equal(a, b) for a, b in zip((post_off, post_doc, post_tf, doc_len), again))
+    q = synth.sparse_queries(8, vocab=500)
+    docs, sc = oracle.bm25_search(q[0][0], q[0][1], post_off, post_doc, post_tf, doc_len, 20)
+    assert len(docs) == 20 and np.all(sc[:-1] >= sc[1:])
