@@ -13,11 +13,13 @@
 //   FaissVectorIndex (Flat)    src/index.rs:330-683             gvdb::GpuVectorIndex (exact or two-stage)
 //   VectorDbError              src/types.rs:859-920             gvdb::VectorDbError
 //   rrf_fusion                 src/hybrid.rs:422-488            gvdb::rrf_fusion
-//   SparseIndex / BM25         src/sparse.rs:31-222             gvdb::SparseIndex
+//   SparseIndex / BM25         src/sparse.rs:31-222             gvdb::SparseIndex (host, as the reference),
+//                                                               gvdb::GpuSparseIndex (postings scored on the GPU)
 //   shard merge                src/distributed/shard.rs:776-783 gvdb::concat_sort_truncate
 //
-// All arithmetic on the dense path runs on the GPU through include/gvdb.h.  RRF and BM25 are
-// host code in the reference and stay host code here ("consumes the GPU top-k unchanged").
+// All arithmetic on the dense path runs on the GPU through include/gvdb.h.  RRF is host code in
+// the reference and stays host code here ("consumes the GPU top-k unchanged"); BM25 is available
+// both as the reference's host loop (SparseIndex) and on the GPU (GpuSparseIndex, gvdb_sparse_*).
 #pragma once
 #include <algorithm>
 #include <cmath>
@@ -380,11 +382,12 @@ struct DocumentSparseRepresentation {
 class SparseIndex {
 public:
     explicit SparseIndex(BM25Parameters p = {}) : params_(p) {}
+    virtual ~SparseIndex() = default;
     // add_document (:71-107).  average_document_length is recomputed as the reference does: the
     // sum of document_length over ALL postings entries (a document counts once per distinct
     // term) divided by total_documents.  The reference sums in HashMap order (unspecified); a
     // running f32 total in insertion order is used here.
-    void add_document(const DocumentSparseRepresentation& doc) {
+    virtual void add_document(const DocumentSparseRepresentation& doc) {
         for (auto& tf : doc.term_frequencies) {
             postings_[tf.first].push_back(Entry{doc.document_id, tf.second, doc.document_length});
             total_length_ = total_length_ + doc.document_length;
@@ -392,10 +395,10 @@ public:
         total_documents_ += 1;
         if (total_documents_ > 0) average_document_length_ = total_length_ / (float)total_documents_;
     }
-    size_t total_documents() const { return total_documents_; }
-    float average_document_length() const { return average_document_length_; }
+    virtual size_t total_documents() const { return total_documents_; }
+    virtual float average_document_length() const { return average_document_length_; }
     // search_bm25 (:153-199)
-    std::vector<std::pair<std::string, float>> search_bm25(const SparseVector& query_vector, size_t limit) const {
+    virtual std::vector<std::pair<std::string, float>> search_bm25(const SparseVector& query_vector, size_t limit) const {
         std::vector<std::pair<std::string, float>> out;
         if (total_documents_ == 0) return out;                                   // :161-163
         std::unordered_map<std::string, size_t> pos;
@@ -418,12 +421,88 @@ public:
         if (out.size() > limit) out.resize(limit);                               // :196
         return out;
     }
+protected:
+    BM25Parameters params_;
 private:
     struct Entry { std::string document_id; float term_frequency; float document_length; };
     std::unordered_map<uint32_t, std::vector<Entry>> postings_;
-    BM25Parameters params_;
     size_t total_documents_ = 0;
     float total_length_ = 0.0f, average_document_length_ = 0.0f;
+};
+
+// SparseIndex with the postings scored on the GPU (gvdb_sparse_*).  Documents
+// are numbered in insertion order; the postings are frozen into CSR and uploaded on the first
+// search after a change.  Score ties come out by document number (the reference's order among
+// ties is its HashMap's, i.e. unspecified).  Batched searches share one call.
+class GpuSparseIndex : public SparseIndex {
+public:
+    explicit GpuSparseIndex(BM25Parameters p = {}, int device = 0) : SparseIndex(p) {
+        check(gvdb_sparse_create(device, p.k1, p.b, &h_));
+    }
+    ~GpuSparseIndex() override { gvdb_sparse_destroy(h_); }
+    GpuSparseIndex(const GpuSparseIndex&) = delete;
+    GpuSparseIndex& operator=(const GpuSparseIndex&) = delete;
+
+    void add_document(const DocumentSparseRepresentation& doc) override {
+        const uint32_t d = (uint32_t)ids_.size();
+        ids_.push_back(doc.document_id);
+        doc_len_.push_back(doc.document_length);
+        for (auto& tf : doc.term_frequencies) {
+            if (tf.first >= by_term_.size()) by_term_.resize((size_t)tf.first + 1);
+            auto& list = by_term_[tf.first];
+            if (!list.empty() && list.back().first == d) continue;    // one entry per (term, document)
+            list.emplace_back(d, tf.second);
+        }
+        dirty_ = true;
+    }
+    size_t total_documents() const override { return ids_.size(); }
+    float average_document_length() const override { freeze(); return gvdb_sparse_average_document_length(h_); }
+
+    std::vector<std::pair<std::string, float>> search_bm25(const SparseVector& query_vector, size_t limit) const override {
+        return search_bm25_batch({query_vector}, limit)[0];
+    }
+    std::vector<std::vector<std::pair<std::string, float>>> search_bm25_batch(const std::vector<SparseVector>& queries,
+                                                                              size_t limit) const {
+        std::vector<std::vector<std::pair<std::string, float>>> out(queries.size());
+        if (queries.empty() || limit == 0 || ids_.empty()) return out;
+        freeze();
+        std::vector<uint64_t> q_off(queries.size() + 1, 0);
+        std::vector<uint32_t> q_terms;
+        std::vector<float> q_tfs;
+        for (size_t q = 0; q < queries.size(); ++q) {
+            const size_t n = std::min(queries[q].indices.size(), queries[q].values.size());     // zip (:166)
+            q_terms.insert(q_terms.end(), queries[q].indices.begin(), queries[q].indices.begin() + n);
+            q_tfs.insert(q_tfs.end(), queries[q].values.begin(), queries[q].values.begin() + n);
+            q_off[q + 1] = q_terms.size();
+        }
+        std::vector<uint64_t> docs(queries.size() * limit);
+        std::vector<float> scores(queries.size() * limit);
+        check(gvdb_sparse_search_bm25_batch(h_, (uint32_t)queries.size(), q_off.data(), q_terms.data(), q_tfs.data(),
+                                            (uint32_t)limit, docs.data(), scores.data()));
+        for (size_t q = 0; q < queries.size(); ++q)
+            for (size_t t = 0; t < limit && docs[q * limit + t] != GVDB_NO_ID; ++t)
+                out[q].emplace_back(ids_[docs[q * limit + t]], scores[q * limit + t]);
+        return out;
+    }
+private:
+    void freeze() const {
+        if (!dirty_) return;
+        std::vector<uint64_t> post_off(by_term_.size() + 1, 0);
+        std::vector<uint32_t> post_doc;
+        std::vector<float> post_tf;
+        for (size_t t = 0; t < by_term_.size(); ++t) {
+            for (auto& e : by_term_[t]) { post_doc.push_back(e.first); post_tf.push_back(e.second); }
+            post_off[t + 1] = post_doc.size();
+        }
+        check(gvdb_sparse_build(h_, ids_.size(), (uint32_t)by_term_.size(), post_off.data(), post_doc.data(),
+                                post_tf.data(), doc_len_.data()));
+        dirty_ = false;
+    }
+    gvdb_sparse* h_ = nullptr;
+    std::vector<std::string> ids_;
+    std::vector<float> doc_len_;
+    std::vector<std::vector<std::pair<uint32_t, float>>> by_term_;
+    mutable bool dirty_ = true;
 };
 
 // ---- HybridSearchEngine (src/hybrid.rs:166-356), dense side behind `VectorIndex` ------------------------------

@@ -10,6 +10,8 @@ use std::ffi::{c_char, c_void, CStr};
 
 #[repr(C)]
 pub struct gvdb_index { _private: [u8; 0] }
+#[repr(C)]
+pub struct gvdb_sparse { _private: [u8; 0] }
 
 #[repr(C)]
 #[derive(Default, Clone, Copy)]
@@ -75,6 +77,14 @@ extern "C" {
                                            rescore_count: u32, n_slices: u32, records_dev: *mut c_void) -> i32;
     pub fn gvdb_merge_shards_device(h: *mut gvdb_index, stream: *mut c_void, n_shards: u32, records_dev: *const c_void,
                                     nq: u32, rescore_count: u32, k: u32, ids_out_dev: *mut u64, scores_out_dev: *mut f32) -> i32;
+    // sparse side of the hybrid search (SparseIndex::search_bm25, reference src/sparse.rs:153-222)
+    pub fn gvdb_sparse_create(device: i32, k1: f32, b: f32, out: *mut *mut gvdb_sparse) -> i32;
+    pub fn gvdb_sparse_destroy(s: *mut gvdb_sparse);
+    pub fn gvdb_sparse_build(s: *mut gvdb_sparse, n_docs: u64, n_terms: u32, post_off: *const u64, post_doc: *const u32,
+                             post_tf: *const f32, doc_len: *const f32) -> i32;
+    pub fn gvdb_sparse_average_document_length(s: *const gvdb_sparse) -> f32;
+    pub fn gvdb_sparse_search_bm25_batch(s: *mut gvdb_sparse, nq: u32, q_off: *const u64, q_terms: *const u32,
+                                         q_tfs: *const f32, limit: u32, doc_out: *mut u64, score_out: *mut f32) -> i32;
 }
 
 /// Owned handle; `Send + Sync` because the C ABI's search entry points are re-entrant and the

@@ -110,9 +110,29 @@ static void test_sparse_bm25() {                    // src/sparse.rs:153-222
     REQUIRE(idf < 0.0f && r[0].second >= r[1].second);
 }
 
+static void test_gpu_sparse_bm25() {                // same documents on the GPU postings index
+    SparseIndex host;
+    GpuSparseIndex gpu;
+    const DocumentSparseRepresentation docs[] = {
+        {"a", {{0, 1.0f}}, 1.0f}, {"b", {{0, 2.0f}, {3, 0.5f}}, 2.5f}, {"c", {{1, 1.0f}}, 1.0f},
+        {"d", {{3, 0.25f}, {1, 0.75f}}, 1.0f}, {"e", {{2, 1.0f}}, 1.0f}};
+    for (auto& d : docs) { host.add_document(d); gpu.add_document(d); }
+    REQUIRE(gpu.total_documents() == 5);
+    // postings are summed in term order on the GPU side, in insertion order on the host side
+    REQUIRE(std::fabs(gpu.average_document_length() - host.average_document_length()) < 1e-6f);
+    for (const SparseVector& q : {SparseVector{{0}, {1.0f}, 10}, SparseVector{{3, 1}, {0.5f, 0.5f}, 10},
+                                  SparseVector{{9}, {1.0f}, 10}, SparseVector{{1, 1, 2}, {0.25f, 0.5f, 0.25f}, 10}}) {
+        auto h = host.search_bm25(q, 3), g = gpu.search_bm25(q, 3);
+        REQUIRE(h.size() == g.size());
+        for (size_t i = 0; i < h.size(); ++i) REQUIRE(std::fabs(h[i].second - g[i].second) <= 1e-6f * std::fabs(h[i].second));
+    }
+    auto batch = gpu.search_bm25_batch({SparseVector{{0}, {1.0f}, 10}, SparseVector{{2}, {1.0f}, 10}}, 4);
+    REQUIRE(batch.size() == 2 && batch[0].size() == 2 && batch[1].size() == 1 && batch[1][0].first == "e");
+}
+
 static void test_hybrid_search() {                 // src/hybrid.rs:286-356 on the GPU dense index
     auto dense = std::make_shared<GpuVectorIndex>(GpuVectorIndex::Mode::Exact, 4);
-    auto sparse = std::make_shared<SparseIndex>();
+    std::shared_ptr<SparseIndex> sparse = std::make_shared<GpuSparseIndex>();     // BM25 list from the GPU too
     HybridSearchEngine engine(dense, sparse, 60.0f);
     // dense order for the query (1,0,0): doc1 (cos 1), doc2, doc3, doc4
     DocumentSparseRepresentation s1{"doc1", {{7, 1.0f}}, 1.0f}, s3{"doc3", {{7, 3.0f}}, 3.0f};
@@ -145,6 +165,7 @@ int main() {
     test_vector_index_trait();
     test_rrf_fusion();
     test_sparse_bm25();
+    test_gpu_sparse_bm25();
     test_hybrid_search();
     std::printf("host mirror tests: all passed\n");
     return 0;
