@@ -44,7 +44,8 @@ class GvdbProfile(C.Structure):
                 ("flat_ms", C.c_double), ("merge_ms", C.c_double), ("tc_launches", C.c_uint64),
                 ("tc_ms", C.c_double), ("tc_macs", C.c_double), ("tc_bytes", C.c_double),
                 ("scatter_ms", C.c_double), ("optimistic_reruns", C.c_uint64),
-                ("overflow_fallbacks", C.c_uint64)]
+                ("overflow_fallbacks", C.c_uint64), ("exchange_ms", C.c_double),
+                ("exchange_wait_ms", C.c_double)]
 
 
 # every symbol include/gvdb.h declares: name -> (restype, argtypes)
@@ -84,6 +85,13 @@ SYMBOLS = {
     "gvdb_attach_peer_rows_ipc": (_i32, [_vp, _u32, _u64, _u32, _vp]),
     "gvdb_rows_device_ptr": (_vp, [_vp]),
     "gvdb_attach_peer_rows_ptr": (_i32, [_vp, _u32, _u64, _u32, _vp]),
+    "gvdb_exchange_create": (_i32, [_vp, _u32, _u32, _u64, _u32, _u32]),
+    "gvdb_exchange_export_ipc": (_i32, [_vp, _vp]),
+    "gvdb_exchange_attach_ipc": (_i32, [_vp, _vp]),
+    "gvdb_exchange_mailbox_ptr": (_vp, [_vp]),
+    "gvdb_exchange_attach_ptr": (_i32, [_vp, _vp]),
+    "gvdb_search_exchange_device": (_i32, [_vp, _vp, _vp, _u32, _u32, _u32, _vp, _vp]),
+    "gvdb_exchange_status": (_i32, [_vp, _vp]),
     "gvdb_sparse_create": (_i32, [_i32, C.c_float, C.c_float, C.POINTER(_vp)]),
     "gvdb_sparse_destroy": (None, [_vp]),
     "gvdb_sparse_build": (_i32, [_vp, _u64, _u32, _vp, _vp, _vp, _vp]),
@@ -108,7 +116,7 @@ def lib() -> C.CDLL:
             fn = getattr(L, name)  # AttributeError if the library does not export it
             fn.restype = res
             fn.argtypes = args
-        if L.gvdb_abi_version() != 3:
+        if L.gvdb_abi_version() != 4:
             raise RuntimeError("libgvdb.so ABI version mismatch")
         _lib = L
     return _lib

@@ -30,6 +30,7 @@
 #include "gvdb_tc.cuh"
 #include "gvdb_bigr.cuh"
 #include "gvdb_sparse.cuh"
+#include "gvdb_xchg.cuh"
 
 namespace {
 
@@ -64,7 +65,7 @@ struct DevBuf {
     template <class T> T* as() const { return reinterpret_cast<T*>(p); }
 };
 
-enum Kind { K_SCAN = 0, K_SELECT, K_RESCORE, K_TOPK, K_PREP, K_FLAT, K_MERGE, K_TCSCAN, K_SCATTER, K_COUNT };
+enum Kind { K_SCAN = 0, K_SELECT, K_RESCORE, K_TOPK, K_PREP, K_FLAT, K_MERGE, K_TCSCAN, K_SCATTER, K_XCHG, K_XCHG_WAIT, K_COUNT };
 struct ProfRec {
     int kind;
     cudaEvent_t e0, e1;
@@ -110,6 +111,25 @@ const int kSupportedChunks[] = {1, 2, 3, 4, 6, 8, 12, 16, 24, 32};
 
 }  // namespace
 
+// Peer exchange state of one rank (gvdb_xchg.cuh has the protocol).
+struct Exchange {
+    uint32_t world = 0, rank = 0, nq_max = 0, r_max = 0;
+    uint64_t rows_per_owner = 0;
+    uint8_t* mailbox = nullptr;            // my mailbox (cudaMalloc), mapped by every peer
+    size_t mailbox_bytes = 0, set_bytes = 0, q_off = 0, keys_off = 0, sc_off = 0, flags_off = 0;
+    std::vector<uint8_t*> peers;           // every rank's mailbox as mapped here (own included)
+    uint8_t** peers_dev = nullptr;
+    std::vector<void*> opened;             // IPC mappings to close
+    bool attached = false;
+    uint32_t epoch = 0;
+    uint64_t limit_ns = 20ull * 1000 * 1000 * 1000;
+    cudaStream_t side = nullptr;
+    cudaEvent_t fork = nullptr, join = nullptr;
+    DevBuf my_keys, part, err;
+    uint32_t* h_err = nullptr;             // pinned copy of err, refreshed at the end of every step
+    std::mutex mu;                         // steps of one rank are issued one at a time
+};
+
 struct gvdb_index {
     gvdb_config cfg{};
     int dim = 0, nchunk = 0, qs = 0, nbytes = 0;
@@ -128,6 +148,7 @@ struct gvdb_index {
     uint32_t n_peers = 0;
     uint64_t peer_per = 0;
     std::vector<void*> ipc_opened;
+    struct Exchange* xchg = nullptr;     // peer exchange (gvdb_exchange_*), see gvdb_xchg.cuh
     bool rows_reachable() const { return rows_cover_all() || (peer_rows_dev && (uint64_t)n_peers * peer_per >= n_rows); }
     int sm_count = 148;
     std::mutex pool_mu;
@@ -197,6 +218,8 @@ void flush_profile(gvdb_index* h, Workspace* ws) {
             case K_TCSCAN: h->prof.tc_ms += ms; h->prof.tc_launches += 1;
                            h->prof.tc_bytes += r.bytes; h->prof.tc_macs += r.pairs; break;
             case K_SCATTER: h->prof.scatter_ms += ms; break;
+            case K_XCHG: h->prof.exchange_ms += ms; break;
+            case K_XCHG_WAIT: h->prof.exchange_wait_ms += ms; break;
         }
     }
     ws->recs.clear();
@@ -947,6 +970,17 @@ void gvdb_destroy(gvdb_index* h) {
     cudaDeviceSynchronize();
     for (void* p : h->ipc_opened) cudaIpcCloseMemHandle(p);
     if (h->peer_rows_dev) cudaFree((void*)h->peer_rows_dev);
+    if (Exchange* x = h->xchg) {
+        for (void* p : x->opened) cudaIpcCloseMemHandle(p);
+        if (x->mailbox) cudaFree(x->mailbox);
+        if (x->peers_dev) cudaFree(x->peers_dev);
+        x->my_keys.release(); x->part.release(); x->err.release();
+        if (x->h_err) cudaFreeHost(x->h_err);
+        if (x->side) cudaStreamDestroy(x->side);
+        if (x->fork) cudaEventDestroy(x->fork);
+        if (x->join) cudaEventDestroy(x->join);
+        delete x;
+    }
     h->pool.clear();
     if (h->rows) cudaFree(h->rows);
     if (h->codes) cudaFree(h->codes);
@@ -1510,64 +1544,89 @@ gvdb_status gvdb_stage1_device(gvdb_index* h, void* stream, const float* queries
     });
 }
 
+namespace {
+// Owner-side rescoring of `nq` queries' candidate keys (all asynchronous on st).
+void rescore_keys_core(gvdb_index* h, Workspace* ws, cudaStream_t st, const float* queries_dev, uint32_t nq,
+                       uint32_t R, const uint64_t* keys_dev, float* scores_out_dev) {
+    if ((h->dim & 3) != 0) fail(GVDB_ERR_NOT_IMPLEMENTED, "owner-side rescoring needs dim % 4 == 0");
+    const int cols = std::min(h->dim, RS_SLAB);
+    const int stride = ((cols >> 2) & 1) ? cols : cols + 4;
+    const int q_slots = (int)std::min<uint32_t>(32, 31 / R + 2);
+    static bool attr = false;   // benign race: idempotent
+    if (!attr) {
+        CU(cudaFuncSetAttribute(rescore_slab_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                64 * (RS_SLAB + 4) * (int)sizeof(float)));
+        attr = true;
+    }
+    const uint64_t lo = h->windowed ? h->win_first : 0;
+    const uint64_t hi = h->windowed ? std::min(h->n_rows, h->win_first + h->win_count) : h->n_rows;
+    const uint64_t pairs = (uint64_t)nq * R;
+    if (pairs > 0x7fffffffull) fail(GVDB_ERR_INVALID_ARGUMENT, "nq * rescore_count too large");
+    if (h->windowed && !h->rows_cover_all()) {
+        // this GPU owns a fraction of the rows: compact the owned pairs (stable, ascending), then
+        // score 32 of them per warp — the work is 1/G of the pairs, not 1/G of every warp
+        ws->big_v32.ensure(pairs * 4);
+        ws->big_aux.ensure(256);
+        uint32_t* list = ws->big_v32.as<uint32_t>();
+        uint32_t* count = ws->big_aux.as<uint32_t>();
+        cub::CountingInputIterator<uint32_t> it0(0u);
+        OwnedPair pred{keys_dev, h->cfg.row_base, lo, hi};
+        size_t tmp = 0;
+        CU(cub::DeviceSelect::If(nullptr, tmp, it0, list, count, (int)pairs, pred, st));
+        ws->big_tmp.ensure(tmp + 256);
+        size_t tb = ws->big_tmp.bytes;
+        static bool attr2 = false;   // benign race: idempotent
+        if (!attr2) {
+            CU(cudaFuncSetAttribute(rescore_owned_list_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    64 * (RS_SLAB + 4) * (int)sizeof(float)));
+            attr2 = true;
+        }
+        Timed t(h, ws, st, K_RESCORE);
+        CU(cudaMemsetAsync(scores_out_dev, 0, pairs * 4, st));
+        CU(cub::DeviceSelect::If(ws->big_tmp.p, tb, it0, list, count, (int)pairs, pred, st));
+        rescore_owned_list_kernel<<<(unsigned)((pairs + 31) / 32), 32, (size_t)64 * stride * sizeof(float), st>>>(
+            h->rows_base(), h->norms, h->cfg.row_base, h->dim, stride, queries_dev, keys_dev, list, count, R,
+            scores_out_dev);
+    } else {
+        Timed t(h, ws, st, K_RESCORE);
+        rescore_slab_kernel<true><<<(unsigned)((pairs + 31) / 32), 32, (size_t)(32 + q_slots) * stride * sizeof(float), st>>>(
+            h->rows_base(), h->norms, h->cfg.row_base, h->dim, stride, q_slots, queries_dev, nullptr, keys_dev, 0,
+            nullptr, R, nq, nullptr, nullptr, scores_out_dev, lo, hi);
+    }
+    CU(cudaGetLastError());
+}
+
+// Each key takes its owner's score; order by (cosine desc, hamming asc, row asc); first k.
+void finish_owned_core(gvdb_index* h, Workspace* ws, cudaStream_t st, const uint64_t* keys_dev,
+                       const float* scores_by_owner_dev, uint32_t n_owners, uint64_t rows_per_owner, uint32_t nq,
+                       uint32_t R, uint32_t k, uint64_t* ids_out_dev, float* scores_out_dev) {
+    if (R == 0 || R > kMaxR) fail(GVDB_ERR_INVALID_ARGUMENT, "rescore_count must be in [1, 2048]");
+    if (k > R) fail(GVDB_ERR_INVALID_ARGUMENT, "k must be <= rescore_count");
+    if (n_owners == 0 || rows_per_owner == 0) fail(GVDB_ERR_INVALID_ARGUMENT, "n_owners and rows_per_owner must be >= 1");
+    ws->rec_ids.ensure((size_t)nq * R * 8);
+    ws->rec_score.ensure((size_t)nq * R * 4);
+    const uint64_t pairs = (uint64_t)nq * R;
+    {
+        Timed t(h, ws, st, K_MERGE);
+        gather_owner_scores_kernel<<<(unsigned)((pairs + 255) / 256), 256, 0, st>>>(
+            keys_dev, scores_by_owner_dev, n_owners, rows_per_owner, pairs, ws->rec_ids.as<uint64_t>(),
+            ws->rec_score.as<float>());
+    }
+    CU(cudaGetLastError());
+    launch_topk(h, ws, st, ws->rec_ids.as<uint64_t>(), ws->rec_score.as<float>(), nq, R, k, ids_out_dev, scores_out_dev);
+}
+}  // namespace
+
 gvdb_status gvdb_rescore_keys_device(gvdb_index* h, void* stream, const float* queries_dev, uint32_t nq,
                                      uint32_t rescore_count, const uint64_t* keys_dev, float* scores_out_dev) {
     return guarded([&] {
         need(h, "index");
         if (nq == 0 || rescore_count == 0) return;
         need(queries_dev, "queries"); need(keys_dev, "keys"); need(scores_out_dev, "scores_out");
-        if ((h->dim & 3) != 0) fail(GVDB_ERR_NOT_IMPLEMENTED, "gvdb_rescore_keys_device needs dim % 4 == 0");
         DeviceGuard dg(h->cfg.device);
         WsLease lease(h, (cudaStream_t)stream, true);
-        cudaStream_t st = lease.stream;
-        const uint32_t R = rescore_count;
-        const int cols = std::min(h->dim, RS_SLAB);
-        const int stride = ((cols >> 2) & 1) ? cols : cols + 4;
-        const int q_slots = (int)std::min<uint32_t>(32, 31 / R + 2);
-        static bool attr = false;   // benign race: idempotent
-        if (!attr) {
-            CU(cudaFuncSetAttribute(rescore_slab_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    64 * (RS_SLAB + 4) * (int)sizeof(float)));
-            attr = true;
-        }
-        const uint64_t lo = h->windowed ? h->win_first : 0;
-        const uint64_t hi = h->windowed ? std::min(h->n_rows, h->win_first + h->win_count) : h->n_rows;
-        const uint64_t pairs = (uint64_t)nq * R;
-        if (pairs > 0x7fffffffull) fail(GVDB_ERR_INVALID_ARGUMENT, "nq * rescore_count too large");
-        if (h->windowed && !h->rows_cover_all()) {
-            // this GPU owns a fraction of the rows: compact the owned pairs (stable, ascending), then
-            // score 32 of them per warp — the work is 1/G of the pairs, not 1/G of every warp
-            Workspace* ws = lease.ws;
-            ws->big_v32.ensure(pairs * 4);
-            ws->big_aux.ensure(256);
-            uint32_t* list = ws->big_v32.as<uint32_t>();
-            uint32_t* count = ws->big_aux.as<uint32_t>();
-            cub::CountingInputIterator<uint32_t> it0(0u);
-            OwnedPair pred{keys_dev, h->cfg.row_base, lo, hi};
-            size_t tmp = 0;
-            CU(cub::DeviceSelect::If(nullptr, tmp, it0, list, count, (int)pairs, pred, st));
-            ws->big_tmp.ensure(tmp + 256);
-            size_t tb = ws->big_tmp.bytes;
-            static bool attr2 = false;   // benign race: idempotent
-            if (!attr2) {
-                CU(cudaFuncSetAttribute(rescore_owned_list_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        64 * (RS_SLAB + 4) * (int)sizeof(float)));
-                attr2 = true;
-            }
-            Timed t(h, ws, st, K_RESCORE);
-            CU(cudaMemsetAsync(scores_out_dev, 0, pairs * 4, st));
-            CU(cub::DeviceSelect::If(ws->big_tmp.p, tb, it0, list, count, (int)pairs, pred, st));
-            rescore_owned_list_kernel<<<(unsigned)((pairs + 31) / 32), 32, (size_t)64 * stride * sizeof(float), st>>>(
-                h->rows_base(), h->norms, h->cfg.row_base, h->dim, stride, queries_dev, keys_dev, list, count, R,
-                scores_out_dev);
-        } else {
-            Timed t(h, lease.ws, st, K_RESCORE);
-            rescore_slab_kernel<true><<<(unsigned)((pairs + 31) / 32), 32, (size_t)(32 + q_slots) * stride * sizeof(float), st>>>(
-                h->rows_base(), h->norms, h->cfg.row_base, h->dim, stride, q_slots, queries_dev, nullptr, keys_dev, 0,
-                nullptr, R, nq, nullptr, nullptr, scores_out_dev, lo, hi);
-        }
-        CU(cudaGetLastError());
-        finish_async(h, lease.ws, st);
+        rescore_keys_core(h, lease.ws, lease.stream, queries_dev, nq, rescore_count, keys_dev, scores_out_dev);
+        finish_async(h, lease.ws, lease.stream);
     });
 }
 
@@ -1580,26 +1639,11 @@ gvdb_status gvdb_finish_owned_device(gvdb_index* h, void* stream, const uint64_t
         if (nq == 0) return;
         need(keys_dev, "keys"); need(scores_by_owner_dev, "scores_by_owner");
         need(ids_out_dev, "ids_out"); need(scores_out_dev, "scores_out");
-        const uint32_t R = rescore_count;
-        if (R == 0 || R > kMaxR) fail(GVDB_ERR_INVALID_ARGUMENT, "rescore_count must be in [1, 2048]");
-        if (k > R) fail(GVDB_ERR_INVALID_ARGUMENT, "k must be <= rescore_count");
-        if (n_owners == 0 || rows_per_owner == 0) fail(GVDB_ERR_INVALID_ARGUMENT, "n_owners and rows_per_owner must be >= 1");
         DeviceGuard dg(h->cfg.device);
         WsLease lease(h, (cudaStream_t)stream, true);
-        Workspace* ws = lease.ws;
-        cudaStream_t st = lease.stream;
-        ws->rec_ids.ensure((size_t)nq * R * 8);
-        ws->rec_score.ensure((size_t)nq * R * 4);
-        const uint64_t pairs = (uint64_t)nq * R;
-        {
-            Timed t(h, ws, st, K_MERGE);
-            gather_owner_scores_kernel<<<(unsigned)((pairs + 255) / 256), 256, 0, st>>>(
-                keys_dev, scores_by_owner_dev, n_owners, rows_per_owner, pairs, ws->rec_ids.as<uint64_t>(),
-                ws->rec_score.as<float>());
-        }
-        CU(cudaGetLastError());
-        launch_topk(h, ws, st, ws->rec_ids.as<uint64_t>(), ws->rec_score.as<float>(), nq, R, k, ids_out_dev, scores_out_dev);
-        finish_async(h, ws, st);
+        finish_owned_core(h, lease.ws, lease.stream, keys_dev, scores_by_owner_dev, n_owners, rows_per_owner, nq,
+                          rescore_count, k, ids_out_dev, scores_out_dev);
+        finish_async(h, lease.ws, lease.stream);
     });
 }
 
@@ -1661,6 +1705,210 @@ gvdb_status gvdb_attach_peer_rows_ptr(gvdb_index* h, uint32_t n_owners, uint64_t
         std::vector<const float*> ptrs(n_owners, nullptr);
         for (uint32_t o = 0; o < n_owners; ++o) ptrs[o] = o == my_owner ? h->rows : static_cast<const float*>(row_ptrs[o]);
         attach_peers(h, n_owners, rows_per_owner, my_owner, ptrs);
+    });
+}
+
+// ---- peer exchange (gvdb_xchg.cuh) -------------------------------------------------------------------
+namespace {
+size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+
+void xchg_push(gvdb_index* h, Workspace* ws, cudaStream_t st, Exchange* x, uint64_t dst_off, const void* src,
+               uint64_t src_stride, uint64_t bytes) {
+    if (bytes == 0) return;
+    const bool wide = ((dst_off | (uint64_t)(uintptr_t)src | src_stride | bytes) & 15) == 0;
+    const uint64_t units = bytes / (wide ? 16 : 4);
+    const unsigned gx = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((units + 255) / 256, 4 * (uint64_t)h->sm_count / x->world + 1));
+    Timed t(h, ws, st, K_XCHG);
+    if (wide)
+        xchg_push_kernel<uint4><<<dim3(gx, x->world), 256, 0, st>>>(x->peers_dev, dst_off, static_cast<const uint8_t*>(src), src_stride, bytes);
+    else
+        xchg_push_kernel<uint32_t><<<dim3(gx, x->world), 256, 0, st>>>(x->peers_dev, dst_off, static_cast<const uint8_t*>(src), src_stride, bytes);
+}
+void xchg_signal(gvdb_index* h, Workspace* ws, cudaStream_t st, Exchange* x, uint32_t kind) {
+    Timed t(h, ws, st, K_XCHG);
+    xchg_signal_kernel<<<1, 32, 0, st>>>(x->peers_dev, x->flags_off, kind, x->world, x->rank, x->epoch);
+}
+void xchg_wait(gvdb_index* h, Workspace* ws, cudaStream_t st, Exchange* x, uint32_t kind_mask) {
+    Timed t(h, ws, st, K_XCHG_WAIT);
+    xchg_wait_kernel<<<1, XCHG_KINDS * XCHG_MAX_WORLD, 0, st>>>(
+        reinterpret_cast<const uint32_t*>(x->mailbox + x->flags_off), kind_mask, x->world, x->epoch, x->limit_ns,
+        x->err.as<uint32_t>());
+}
+}  // namespace
+
+gvdb_status gvdb_exchange_create(gvdb_index* h, uint32_t world, uint32_t rank, uint64_t rows_per_owner,
+                                 uint32_t nq_max, uint32_t rescore_max) {
+    return guarded([&] {
+        need(h, "index");
+        if (h->xchg) fail(GVDB_ERR_INVALID_ARGUMENT, "this index already has a peer exchange");
+        if (world == 0 || world > XCHG_MAX_WORLD || rank >= world) fail(GVDB_ERR_INVALID_ARGUMENT, "bad world / rank");
+        if (nq_max == 0 || rescore_max == 0 || rescore_max > kMaxR)
+            fail(GVDB_ERR_INVALID_ARGUMENT, "nq_max >= 1 and rescore_max in [1, 2048]");
+        if (rows_per_owner == 0) fail(GVDB_ERR_INVALID_ARGUMENT, "rows_per_owner must be >= 1");
+        if ((h->dim & 3) != 0) fail(GVDB_ERR_NOT_IMPLEMENTED, "the peer exchange needs dim % 4 == 0");
+        if (world > 1) {
+            if (!h->windowed) fail(GVDB_ERR_INVALID_ARGUMENT, "the peer exchange needs an index created with GVDB_FLAG_ROW_WINDOW");
+            if (h->win_first != (uint64_t)rank * rows_per_owner || h->win_count > rows_per_owner)
+                fail(GVDB_ERR_INVALID_ARGUMENT, "this index's row window is not owner `rank`'s share");
+        }
+        DeviceGuard dg(h->cfg.device);
+        std::unique_ptr<Exchange> x(new Exchange());
+        x->world = world; x->rank = rank; x->nq_max = nq_max; x->r_max = rescore_max; x->rows_per_owner = rows_per_owner;
+        const size_t slots = (size_t)world * nq_max;
+        x->q_off = 0;
+        x->keys_off = align256(slots * h->dim * 4);
+        x->sc_off = x->keys_off + align256(slots * rescore_max * 8);
+        x->set_bytes = x->sc_off + align256(slots * rescore_max * 4);
+        x->flags_off = 2 * x->set_bytes;
+        x->mailbox_bytes = x->flags_off + (size_t)XCHG_KINDS * world * XCHG_FLAG_STRIDE * 4;
+        if (const char* e = getenv("GVDB_XCHG_TIMEOUT_MS")) x->limit_ns = (uint64_t)std::max(1, atoi(e)) * 1000000ull;
+        // plain cudaMalloc (not a pool allocation): the block is exported with cudaIpcGetMemHandle
+        CU(cudaMalloc((void**)&x->mailbox, x->mailbox_bytes));
+        CU(cudaMemset(x->mailbox, 0, x->mailbox_bytes));
+        CU(cudaMalloc((void**)&x->peers_dev, world * sizeof(uint8_t*)));
+        x->my_keys.ensure((size_t)nq_max * rescore_max * 8);
+        x->part.ensure(slots * rescore_max * 4);
+        x->err.ensure(256);
+        CU(cudaMemset(x->err.p, 0, 256));
+        CU(cudaMallocHost((void**)&x->h_err, 64));
+        x->h_err[0] = 0;
+        CU(cudaStreamCreateWithFlags(&x->side, cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&x->fork, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&x->join, cudaEventDisableTiming));
+        CU(cudaDeviceSynchronize());
+        x->peers.assign(world, nullptr);
+        x->peers[rank] = x->mailbox;
+        if (world == 1) {
+            CU(cudaMemcpy(x->peers_dev, x->peers.data(), sizeof(uint8_t*), cudaMemcpyHostToDevice));
+            x->attached = true;
+        }
+        h->xchg = x.release();
+    });
+}
+
+gvdb_status gvdb_exchange_export_ipc(gvdb_index* h, uint8_t* handle_out) {
+    return guarded([&] {
+        need(h, "index"); need(handle_out, "handle_out");
+        if (!h->xchg) fail(GVDB_ERR_INVALID_ARGUMENT, "call gvdb_exchange_create first");
+        DeviceGuard dg(h->cfg.device);
+        cudaIpcMemHandle_t hd;
+        CU(cudaIpcGetMemHandle(&hd, h->xchg->mailbox));
+        memcpy(handle_out, &hd, sizeof(hd));
+    });
+}
+
+namespace {
+void xchg_attach(gvdb_index* h, const std::vector<uint8_t*>& ptrs) {
+    Exchange* x = h->xchg;
+    for (uint32_t w = 0; w < x->world; ++w) x->peers[w] = w == x->rank ? x->mailbox : ptrs[w];
+    CU(cudaMemcpy(x->peers_dev, x->peers.data(), x->world * sizeof(uint8_t*), cudaMemcpyHostToDevice));
+    x->attached = true;
+}
+}  // namespace
+
+gvdb_status gvdb_exchange_attach_ipc(gvdb_index* h, const uint8_t* handles) {
+    return guarded([&] {
+        need(h, "index"); need(handles, "handles");
+        Exchange* x = h->xchg;
+        if (!x) fail(GVDB_ERR_INVALID_ARGUMENT, "call gvdb_exchange_create first");
+        DeviceGuard dg(h->cfg.device);
+        std::vector<uint8_t*> ptrs(x->world, nullptr);
+        for (uint32_t w = 0; w < x->world; ++w) {
+            if (w == x->rank) continue;
+            cudaIpcMemHandle_t hd;
+            memcpy(&hd, handles + (size_t)w * GVDB_IPC_HANDLE_BYTES, sizeof(hd));
+            void* p = nullptr;
+            CU(cudaIpcOpenMemHandle(&p, hd, cudaIpcMemLazyEnablePeerAccess));
+            x->opened.push_back(p);
+            ptrs[w] = static_cast<uint8_t*>(p);
+        }
+        xchg_attach(h, ptrs);
+    });
+}
+
+void* gvdb_exchange_mailbox_ptr(const gvdb_index* h) { return h && h->xchg ? h->xchg->mailbox : nullptr; }
+
+gvdb_status gvdb_exchange_attach_ptr(gvdb_index* h, void* const* mailboxes) {
+    return guarded([&] {
+        need(h, "index"); need(mailboxes, "mailboxes");
+        Exchange* x = h->xchg;
+        if (!x) fail(GVDB_ERR_INVALID_ARGUMENT, "call gvdb_exchange_create first");
+        DeviceGuard dg(h->cfg.device);
+        std::vector<uint8_t*> ptrs(x->world, nullptr);
+        for (uint32_t w = 0; w < x->world; ++w) {
+            ptrs[w] = static_cast<uint8_t*>(mailboxes[w]);
+            if (w != x->rank && !ptrs[w]) fail(GVDB_ERR_INVALID_ARGUMENT, "null peer mailbox");
+        }
+        xchg_attach(h, ptrs);
+    });
+}
+
+gvdb_status gvdb_exchange_status(gvdb_index* h, uint32_t* timed_out_kinds) {
+    return guarded([&] {
+        need(h, "index");
+        Exchange* x = h->xchg;
+        if (!x) fail(GVDB_ERR_INVALID_ARGUMENT, "call gvdb_exchange_create first");
+        DeviceGuard dg(h->cfg.device);
+        uint32_t e = 0;
+        CU(cudaMemcpy(&e, x->err.p, 4, cudaMemcpyDeviceToHost));   // waits for the steps in flight
+        if (timed_out_kinds) *timed_out_kinds = e;
+        if (e) fail(GVDB_ERR_INDEX, "peer exchange timed out waiting for a peer (kinds bit mask " + std::to_string(e) +
+                                    ": 1 queries, 2 keys, 4 scores); the answers of that step are invalid");
+    });
+}
+
+gvdb_status gvdb_search_exchange_device(gvdb_index* h, void* stream, const float* queries_dev, uint32_t nq,
+                                        uint32_t k, uint32_t rescore_count, uint64_t* ids_out_dev,
+                                        float* scores_out_dev) {
+    return guarded([&] {
+        need(h, "index");
+        Exchange* x = h->xchg;
+        if (!x || !x->attached) fail(GVDB_ERR_INVALID_ARGUMENT, "peer exchange not created / peers not attached");
+        need(queries_dev, "queries"); need(ids_out_dev, "ids_out"); need(scores_out_dev, "scores_out");
+        const uint32_t R = rescore_count, W = x->world;
+        if (nq == 0 || nq > x->nq_max) fail(GVDB_ERR_INVALID_ARGUMENT, "nq must be in [1, nq_max] (every rank calls with the same nq)");
+        if (R == 0 || R > x->r_max) fail(GVDB_ERR_INVALID_ARGUMENT, "rescore_count must be in [1, rescore_max]");
+        if (k > R) fail(GVDB_ERR_INVALID_ARGUMENT, "k must be <= rescore_count");
+        if (h->n_live == 0) fail(GVDB_ERR_INDEX_NOT_BUILT, "index is empty");
+        std::lock_guard<std::mutex> lk(x->mu);
+        if (x->h_err[0]) fail(GVDB_ERR_INDEX, "an earlier peer-exchange step timed out; the exchange is out of step");
+        DeviceGuard dg(h->cfg.device);
+        WsLease lease(h, (cudaStream_t)stream, true);
+        Workspace* ws = lease.ws;
+        cudaStream_t st = lease.stream;
+        x->epoch += 1;
+        uint8_t* set = x->mailbox + (size_t)(x->epoch & 1) * x->set_bytes;
+        const uint64_t set_off = (uint64_t)(x->epoch & 1) * x->set_bytes;
+        const uint64_t q_bytes = (uint64_t)nq * h->dim * 4, key_bytes = (uint64_t)nq * R * 8, sc_bytes = (uint64_t)nq * R * 4;
+        // my queries to every owner, on the side stream, under stage 1
+        CU(cudaEventRecord(x->fork, st));
+        CU(cudaStreamWaitEvent(x->side, x->fork, 0));
+        xchg_push(h, ws, x->side, x, set_off + x->q_off + x->rank * q_bytes, queries_dev, 0, q_bytes);
+        xchg_signal(h, ws, x->side, x, XCHG_Q);
+        CU(cudaEventRecord(x->join, x->side));
+        // stage 1 on my batch
+        uint64_t* my_keys = x->my_keys.as<uint64_t>();
+        for (int attempt = 0; attempt < 2; ++attempt) {
+            bool optimistic = false;
+            search_core(h, ws, st, queries_dev, nq, R, nullptr, nullptr, nullptr, true, attempt == 0, &optimistic, my_keys);
+            if (!check_overflow(h, ws, st, optimistic)) break;
+        }
+        xchg_push(h, ws, st, x, set_off + x->keys_off + x->rank * key_bytes, my_keys, 0, key_bytes);
+        xchg_signal(h, ws, st, x, XCHG_K);
+        CU(cudaStreamWaitEvent(st, x->join, 0));
+        // every rank's queries and keys are here: score the candidates whose rows I own
+        xchg_wait(h, ws, st, x, (1u << XCHG_Q) | (1u << XCHG_K));
+        float* part = x->part.as<float>();
+        rescore_keys_core(h, ws, st, reinterpret_cast<const float*>(set + x->q_off), W * nq, R,
+                          reinterpret_cast<const uint64_t*>(set + x->keys_off), part);
+        xchg_push(h, ws, st, x, set_off + x->sc_off + x->rank * sc_bytes, part, sc_bytes, sc_bytes);
+        xchg_signal(h, ws, st, x, XCHG_S);
+        xchg_wait(h, ws, st, x, 1u << XCHG_S);
+        finish_owned_core(h, ws, st, my_keys, reinterpret_cast<const float*>(set + x->sc_off), W, x->rows_per_owner, nq, R,
+                          k, ids_out_dev, scores_out_dev);
+        CU(cudaMemcpyAsync(x->h_err, x->err.p, 4, cudaMemcpyDeviceToHost, st));
+        CU(cudaGetLastError());
+        finish_async(h, ws, st);
     });
 }
 

@@ -247,3 +247,33 @@ class PeerRowsSearcher:
 
     def search_batch_device(self, my_queries_t, k: int, rescore_count: int, ids_out=None, scores_out=None):
         return self.index.search_batch_device(my_queries_t, k, rescore_count, ids_out, scores_out)
+
+
+class PeerExchangeSearcher:
+    """Codes replicated, rows sharded, queries partitioned — like QueryParallelSearcher, but the
+    three exchanges of a step (queries and candidate keys to the owners, cosines back) are posted
+    stores into the peers' HBM over NVLink ordered by release/acquire flags, all issued by ONE
+    C-ABI call per step (gvdb_search_exchange_device): no collective library and no host work in
+    the data path.  torch.distributed is used once, to hand round the mailboxes' IPC handles."""
+
+    def __init__(self, index, n_total_rows: int, nq_max: int, rescore_max: int, group=None):
+        import torch
+        import torch.distributed as dist
+        self.index = index
+        world = dist.get_world_size(group)
+        rank = dist.get_rank(group)
+        self.rows_per_owner = (n_total_rows + world - 1) // world
+        index.exchange_create(world, rank, self.rows_per_owner, nq_max, rescore_max)
+        mine = torch.frombuffer(bytearray(index.exchange_export_ipc()), dtype=torch.uint8)
+        dev = torch.device("cuda", index.device)
+        allh = torch.empty(world * 64, dtype=torch.uint8, device=dev)
+        dist.all_gather_into_tensor(allh, mine.to(dev), group=group)
+        raw = allh.cpu().numpy().tobytes()
+        index.exchange_attach_ipc([raw[i * 64:(i + 1) * 64] for i in range(world)])
+        dist.barrier(group)
+
+    def search_batch_device(self, my_queries_t, k: int, rescore_count: int, ids_out=None, scores_out=None):
+        return self.index.search_exchange_device(my_queries_t, k, rescore_count, ids_out, scores_out)
+
+    def check(self):
+        self.index.exchange_status()

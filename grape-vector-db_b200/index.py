@@ -363,6 +363,48 @@ class GpuIndex:
         arr = (C.c_void_p * len(ptrs))(*ptrs)
         self._ok(self._lib.gvdb_attach_peer_rows_ptr(self._h, len(ptrs), rows_per_owner, my_owner, arr))
 
+    # -- peer exchange (no collective library in the data path) ---------------------------------
+    def exchange_create(self, world: int, rank: int, rows_per_owner: int, nq_max: int, rescore_max: int):
+        self._ok(self._lib.gvdb_exchange_create(self._h, world, rank, rows_per_owner, nq_max, rescore_max))
+
+    def exchange_export_ipc(self) -> bytes:
+        buf = (C.c_uint8 * 64)()
+        self._ok(self._lib.gvdb_exchange_export_ipc(self._h, buf))
+        return bytes(buf)
+
+    def exchange_attach_ipc(self, handles: list[bytes]):
+        raw = b"".join(handles)
+        assert len(raw) == 64 * len(handles)
+        buf = (C.c_uint8 * len(raw)).from_buffer_copy(raw)
+        self._ok(self._lib.gvdb_exchange_attach_ipc(self._h, buf))
+
+    def exchange_mailbox_ptr(self) -> int:
+        return int(self._lib.gvdb_exchange_mailbox_ptr(self._h) or 0)
+
+    def exchange_attach_ptr(self, ptrs: list[int]):
+        arr = (C.c_void_p * len(ptrs))(*ptrs)
+        self._ok(self._lib.gvdb_exchange_attach_ptr(self._h, arr))
+
+    def search_exchange_device(self, my_queries_t, k: int, rescore_count: int, ids_out=None, scores_out=None):
+        """One step of the peer exchange: every rank calls it with ITS batch (same nq everywhere)."""
+        import torch
+        assert my_queries_t.is_cuda and my_queries_t.dtype == torch.float32 and my_queries_t.is_contiguous()
+        nq = my_queries_t.shape[0]
+        dev = my_queries_t.device
+        if ids_out is None:
+            ids_out = torch.empty((nq, k), dtype=torch.int64, device=dev)
+        if scores_out is None:
+            scores_out = torch.empty((nq, k), dtype=torch.float32, device=dev)
+        st = torch.cuda.current_stream(dev).cuda_stream
+        self._ok(self._lib.gvdb_search_exchange_device(self._h, C.c_void_p(st), C.c_void_p(my_queries_t.data_ptr()),
+                                                       nq, k, rescore_count, C.c_void_p(ids_out.data_ptr()),
+                                                       C.c_void_p(scores_out.data_ptr())))
+        return ids_out, scores_out
+
+    def exchange_status(self):
+        """Waits for the steps in flight; raises IndexError_ if one of them timed out on a peer."""
+        self._ok(self._lib.gvdb_exchange_status(self._h, None))
+
     # -- measurement hooks --------------------------------------------------------------------
     def profile_enable(self, on: bool = True):
         self._ok(self._lib.gvdb_profile_enable(self._h, 1 if on else 0))

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define GVDB_ABI_VERSION 3u
+#define GVDB_ABI_VERSION 4u
 
 #if defined(__GNUC__)
 #define GVDB_API __attribute__((visibility("default")))
@@ -255,6 +255,34 @@ GVDB_API const void* gvdb_rows_device_ptr(const gvdb_index* h);
 GVDB_API gvdb_status gvdb_attach_peer_rows_ptr(gvdb_index* h, uint32_t n_owners, uint64_t rows_per_owner,
                                                uint32_t my_owner, const void* const* row_ptrs /* n_owners */);
 
+/* ---- peer exchange: the same layout with NO collective library in the data path ----------------
+ * Codes replicated, f32 rows sharded, queries partitioned (as gvdb_stage1_device /
+ * gvdb_rescore_keys_device / gvdb_finish_owned_device), but the three exchanges of a step (queries
+ * and candidate keys to the owners, cosines back) are posted stores into the peers' HBM over
+ * NVLink, ordered by release/acquire flags; one call per step, nothing on the host in between.
+ * Replaces the scatter/gather the reference sketches in src/distributed/shard.rs:760-786.
+ *   create   on every rank, after the rows are loaded: allocates this rank's mailbox for batches of
+ *            at most nq_max queries and rescore_max candidates; the index must hold owner `rank`'s
+ *            row window (GVDB_FLAG_ROW_WINDOW, window_first = rank * rows_per_owner)
+ *   export / attach (IPC)   exchange the 64-byte handles (one all-gather, once), attach, then
+ *            BARRIER before the first step
+ *   mailbox_ptr / attach_ptr   the same wiring for several indexes inside one process
+ *   search   every rank calls it once per step with the same nq and rescore_count, each with ITS
+ *            batch; answers land in ids_out_dev / scores_out_dev (nq x k) on `stream`.  A peer
+ *            that does not show up within GVDB_XCHG_TIMEOUT_MS (default 20000) makes the step's
+ *            answers invalid and gvdb_exchange_status (which waits for the steps in flight) and
+ *            every later step return IndexError — never a hang. */
+GVDB_API gvdb_status gvdb_exchange_create(gvdb_index* h, uint32_t world, uint32_t rank, uint64_t rows_per_owner,
+                                          uint32_t nq_max, uint32_t rescore_max);
+GVDB_API gvdb_status gvdb_exchange_export_ipc(gvdb_index* h, uint8_t* handle_out /* GVDB_IPC_HANDLE_BYTES */);
+GVDB_API gvdb_status gvdb_exchange_attach_ipc(gvdb_index* h, const uint8_t* handles /* world * GVDB_IPC_HANDLE_BYTES */);
+GVDB_API void* gvdb_exchange_mailbox_ptr(const gvdb_index* h);
+GVDB_API gvdb_status gvdb_exchange_attach_ptr(gvdb_index* h, void* const* mailboxes /* world */);
+GVDB_API gvdb_status gvdb_search_exchange_device(gvdb_index* h, void* stream, const float* queries_dev, uint32_t nq,
+                                                 uint32_t k, uint32_t rescore_count, uint64_t* ids_out_dev,
+                                                 float* scores_out_dev);
+GVDB_API gvdb_status gvdb_exchange_status(gvdb_index* h, uint32_t* timed_out_kinds /* optional */);
+
 /* ---- sparse side of the hybrid search: BM25 over CSR postings ---------- */
 /* SparseIndex (src/sparse.rs:31-222) as an immutable snapshot: postings in CSR form by term id,
  * documents numbered 0..n_docs-1, ascending inside each term's list.
@@ -293,6 +321,8 @@ typedef struct gvdb_profile {
     double scatter_ms;        /* tc_scatter_kernel (survivor records -> candidate buffers) */
     uint64_t optimistic_reruns; /* calls repeated because the device refuted the single-pass threshold guess */
     uint64_t overflow_fallbacks; /* calls answered by the cut by counting after a candidate buffer overflowed */
+    double exchange_ms;       /* peer exchange: push + signal kernels (gvdb_search_exchange_device) */
+    double exchange_wait_ms;  /* peer exchange: time spent waiting for the peers' flags (rank skew included) */
 } gvdb_profile;
 GVDB_API gvdb_status gvdb_profile_enable(gvdb_index* h, int32_t on);
 GVDB_API gvdb_status gvdb_profile_read(gvdb_index* h, gvdb_profile* out, int32_t reset);

@@ -537,3 +537,88 @@ def test_storage_vector_search_semantics(gv):
                 assert np.array_equal(ids[qi, :r], oi), f"ids differ (query {qi}, threshold {thr})"
                 assert np.array_equal(_bits(sims[qi, :r]), _bits(os_))
                 assert np.all(ids[qi, r:] == gv.NO_ID) and np.all(np.isneginf(sims[qi, r:]))
+
+
+def test_peer_exchange_equals_single_index(gv):
+    """gvdb_search_exchange_device with G "ranks" inside one process on ONE GPU: every rank's step
+    is issued asynchronously on its own stream; the wait kernels spin on the device until the other
+    ranks' pushes (queued behind them by the host) arrive.  Answers == the single index, bit for bit,
+    over several steps (the mailbox sets alternate) and batch sizes."""
+    import torch
+    from grape_vector_db_b200 import synth
+    dev = torch.device("cuda:0")
+    n, dim, R, k = 40_003, 768, 40, 10
+    rows = synth.lowrank_rows(0, n, dim)
+    for G, nq_per in ((1, 96), (2, 80), (3, 70)):
+        qs = synth.lowrank_queries(0, nq_per * G * 3, dim)
+        oi, os_ = oracle.multi_stage_search_batch(qs, rows, R, k, nthreads=8)
+        per = (n + G - 1) // G
+        ranks, streams = [], []
+        for g in range(G):
+            ix = gv.GpuIndex(dim, row_window=(g * per, min(per, n - g * per))) if G > 1 else gv.GpuIndex(dim)
+            ix.add(rows)
+            ix.exchange_create(G, g, per, 96, 64)
+            ranks.append(ix)
+            streams.append(torch.cuda.Stream(dev))
+        ptrs = [ix.exchange_mailbox_ptr() for ix in ranks]
+        for ix in ranks:
+            ix.exchange_attach_ptr(ptrs)
+        all_q = torch.from_numpy(qs).to(dev)
+        # every buffer the step needs is allocated before a wait kernel is in flight: an allocation
+        # synchronises the device, and with all the ranks on one device it would wait for a flag
+        # that only a later launch of this same thread can set (separate processes do not have this)
+        for g, ix in enumerate(ranks):
+            warm_q = all_q[:nq_per].contiguous()
+            keys = ix.stage1_device(warm_q, R)
+            allk = keys.repeat(G, 1).contiguous()
+            part = ix.rescore_keys_device(all_q[:nq_per * G].contiguous(), allk)
+            ix.finish_owned_device(keys, part.view(G, nq_per, R).contiguous(), per, k)
+        torch.cuda.synchronize()
+        q_in = [[all_q[(step * G + g) * nq_per:(step * G + g + 1) * nq_per].contiguous() for g in range(G)]
+                for step in range(3)]
+        outs = [[(torch.empty((nq_per, k), dtype=torch.int64, device=dev),
+                  torch.empty((nq_per, k), dtype=torch.float32, device=dev)) for _ in range(G)] for _ in range(3)]
+        torch.cuda.synchronize()
+        for step in range(3):
+            for g, ix in enumerate(ranks):
+                with torch.cuda.stream(streams[g]):
+                    ix.search_exchange_device(q_in[step][g], k, R, *outs[step][g])
+        torch.cuda.synchronize()
+        for ix in ranks:
+            ix.exchange_status()
+        for step in range(3):
+            for g in range(G):
+                lo = (step * G + g) * nq_per
+                i_, s_ = outs[step][g]
+                assert np.array_equal(i_.cpu().numpy().astype(np.uint64), oi[lo:lo + nq_per]), f"G={G} step={step} rank={g}"
+                assert np.array_equal(_bits(s_.cpu().numpy()), _bits(os_[lo:lo + nq_per])), f"G={G} step={step} rank={g}"
+        for ix in ranks:
+            ix.close()
+
+
+def test_peer_exchange_missing_peer_times_out(gv, monkeypatch):
+    """A peer that never shows up is an error after the time limit, not a hang."""
+    import torch
+    from grape_vector_db_b200 import synth
+    monkeypatch.setenv("GVDB_XCHG_TIMEOUT_MS", "300")
+    dev = torch.device("cuda:0")
+    n, dim, R, k, G = 5_000, 768, 40, 10, 2
+    rows = synth.lowrank_rows(0, n, dim)
+    per = n // G
+    ranks = []
+    for g in range(G):
+        ix = gv.GpuIndex(dim, row_window=(g * per, per))
+        ix.add(rows)
+        ix.exchange_create(G, g, per, 64, 64)
+        ranks.append(ix)
+    ptrs = [ix.exchange_mailbox_ptr() for ix in ranks]
+    for ix in ranks:
+        ix.exchange_attach_ptr(ptrs)
+    q = torch.from_numpy(synth.lowrank_queries(0, 16, dim)).to(dev)
+    ranks[0].search_exchange_device(q, k, R)            # rank 1 never calls
+    with pytest.raises(gv.IndexError_, match="timed out"):
+        ranks[0].exchange_status()
+    with pytest.raises(gv.IndexError_, match="out of step"):
+        ranks[0].search_exchange_device(q, k, R)
+    for ix in ranks:
+        ix.close()
