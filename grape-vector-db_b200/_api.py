@@ -4,7 +4,8 @@ from .errors import (ConfigError, DimensionMismatch, IndexError_, IndexNotBuilt,
                      VectorDbError)
 from .index import NO_ID, GpuIndex  # noqa: F401
 from .sparse import GpuSparseIndex  # noqa: F401
+from .hybrid import HybridSearcher, rrf_fusion_batch  # noqa: F401
 
-__all__ = ["GpuIndex", "GpuSparseIndex", "NO_ID", "VectorDbError", "IndexNotBuilt", "DimensionMismatch",
+__all__ = ["GpuIndex", "GpuSparseIndex", "HybridSearcher", "rrf_fusion_batch", "NO_ID", "VectorDbError", "IndexNotBuilt", "DimensionMismatch",
            "InvalidVectorDimension", "QuantizationError", "IndexError_", "ConfigError",
            "NotImplementedError_"]

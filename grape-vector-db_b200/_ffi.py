@@ -97,6 +97,10 @@ SYMBOLS = {
     "gvdb_sparse_build": (_i32, [_vp, _u64, _u32, _vp, _vp, _vp, _vp]),
     "gvdb_sparse_average_document_length": (C.c_float, [_vp]),
     "gvdb_sparse_search_bm25_batch": (_i32, [_vp, _u32, _vp, _vp, _vp, _u32, _vp, _vp]),
+    "gvdb_sparse_search_bm25_batch_device": (_i32, [_vp, _vp, _u32, _vp, _vp, _vp, _u32, _vp, _vp]),
+    "gvdb_sparse_launches": (_u64, [_vp]),
+    "gvdb_rrf_fusion_batch": (_i32, [_i32, _vp, _u32, _vp, _u32, _vp, _u32, _u32, C.c_float, _u32, _vp, _vp]),
+    "gvdb_rrf_fusion_batch_device": (_i32, [_i32, _vp, _vp, _u32, _vp, _u32, _vp, _u32, _u32, C.c_float, _u32, _vp, _vp]),
     "gvdb_profile_enable": (_i32, [_vp, _i32]),
     "gvdb_profile_read": (_i32, [_vp, _vp, _i32]),
 }

@@ -1922,6 +1922,8 @@ struct gvdb_sparse {
     DevBuf post_off, post_doc, post_tf, doc_len;
     DevBuf acc, hist, cut, keys, q_off, q_terms, q_tfs, q_idf, doc_out, score_out;
     cudaStream_t stream = nullptr;
+    int sm_count = 148;
+    uint64_t launches = 0;                     // kernels launched by the searches of this handle
     std::mutex mu;                             // one search at a time per handle
 };
 
@@ -1936,6 +1938,9 @@ gvdb_status gvdb_sparse_create(int32_t device, float k1, float b, gvdb_sparse** 
         DeviceGuard dg(device);
         std::unique_ptr<gvdb_sparse> s(new gvdb_sparse());
         s->device = device; s->k1 = k1; s->b = b;
+        cudaDeviceProp prop;
+        CU(cudaGetDeviceProperties(&prop, device));
+        s->sm_count = prop.multiProcessorCount;
         CU(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
         *out = s.release();
     });
@@ -1993,78 +1998,173 @@ gvdb_status gvdb_sparse_build(gvdb_sparse* s, uint64_t n_docs, uint32_t n_terms,
 
 float gvdb_sparse_average_document_length(const gvdb_sparse* s) { return s ? s->avg_len : 0.0f; }
 
+namespace {
+// SparseIndex::search_bm25 for a batch; query CSR on the host, answers written to DEVICE buffers on `st`
+// (asynchronous; the caller synchronises).  Holds s->mu.
+void bm25_core(gvdb_sparse* s, cudaStream_t st, uint32_t nq, const uint64_t* q_off, const uint32_t* q_terms,
+               const float* q_tfs, uint32_t limit, uint64_t* doc_out_dev, float* score_out_dev) {
+    if (limit > (uint32_t)SORT_N) fail(GVDB_ERR_NOT_IMPLEMENTED, "BM25 limit > 4096 is not implemented");
+    const uint64_t nt = q_off[nq];
+    if (nt) { need(q_terms, "q_terms"); need(q_tfs, "q_tfs"); }
+    // idf on the host (libm logf == Rust's f32::ln); absent terms are dropped (:169)
+    std::vector<uint32_t> terms(nt);
+    std::vector<float> idf(nt);
+    uint32_t max_terms = 0;
+    for (uint32_t q = 0; q < nq; ++q) max_terms = std::max<uint32_t>(max_terms, (uint32_t)(q_off[q + 1] - q_off[q]));
+    for (uint64_t i = 0; i < nt; ++i) {
+        const uint32_t t = q_terms[i];
+        const uint64_t df = t < s->n_terms ? s->h_post_off[t + 1] - s->h_post_off[t] : 0;
+        terms[i] = df ? t : s->n_terms;                            // n_terms = "absent"
+        idf[i] = df ? std::log(((float)s->n_docs - (float)df + 0.5f) / ((float)df + 0.5f)) : 0.0f;
+    }
+    const uint32_t QC = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(std::min<uint64_t>(nq, 64), (512ull << 20) / (s->n_docs * 4)));
+    const uint32_t key_cap = SORT_N;
+    s->acc.ensure((size_t)QC * s->n_docs * 4);
+    s->hist.ensure((size_t)QC * BM25_BINS * 4);
+    s->cut.ensure((size_t)QC * sizeof(Bm25Cut));
+    s->keys.ensure((size_t)QC * key_cap * 8);
+    s->q_off.ensure((size_t)(nq + 1) * 8);
+    s->q_terms.ensure(std::max<size_t>(4, nt * 4));
+    s->q_tfs.ensure(std::max<size_t>(4, nt * 4));
+    s->q_idf.ensure(std::max<size_t>(4, nt * 4));
+    // pageable host sources: cudaMemcpyAsync stages them before it returns
+    CU(cudaMemcpyAsync(s->q_off.p, q_off, (size_t)(nq + 1) * 8, cudaMemcpyHostToDevice, st));
+    if (nt) {
+        CU(cudaMemcpyAsync(s->q_terms.p, terms.data(), nt * 4, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(s->q_tfs.p, q_tfs, nt * 4, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(s->q_idf.p, idf.data(), nt * 4, cudaMemcpyHostToDevice, st));
+    }
+    const unsigned gx = (unsigned)s->sm_count * 2;
+    for (uint32_t q0 = 0; q0 < nq; q0 += QC) {
+        const uint32_t m = std::min(QC, nq - q0);
+        CU(cudaMemsetAsync(s->acc.p, 0xFF, (size_t)m * s->n_docs * 4, st));
+        CU(cudaMemsetAsync(s->hist.p, 0, (size_t)m * BM25_BINS * 4, st));
+        CU(cudaMemsetAsync(s->cut.p, 0, (size_t)m * sizeof(Bm25Cut), st));
+        for (uint32_t rank = 0; rank < max_terms; ++rank)
+            bm25_accumulate_kernel<<<dim3(gx, m), 256, 0, st>>>(
+                s->post_off.as<uint64_t>(), s->post_doc.as<uint32_t>(), s->post_tf.as<float>(), s->doc_len.as<float>(),
+                s->n_terms, s->q_off.as<uint64_t>(), s->q_terms.as<uint32_t>(), s->q_tfs.as<float>(),
+                s->q_idf.as<float>(), q0, (int)rank, s->k1, s->b, s->avg_len, s->n_docs, s->acc.as<uint32_t>());
+        for (int level = 0; level < 4; ++level) {
+            if (level) CU(cudaMemsetAsync(s->hist.p, 0, (size_t)m * BM25_BINS * 4, st));
+            bm25_hist_kernel<<<dim3(gx, m), 256, 0, st>>>(s->acc.as<uint32_t>(), s->n_docs, limit,
+                                                         s->hist.as<uint32_t>(), s->cut.as<Bm25Cut>(), level);
+            bm25_cut_kernel<<<m, 256, 0, st>>>(s->hist.as<uint32_t>(), limit, s->cut.as<Bm25Cut>(), level);
+        }
+        bm25_compact_kernel<<<dim3(gx, m), 256, 0, st>>>(s->acc.as<uint32_t>(), s->n_docs, s->cut.as<Bm25Cut>(),
+                                                        s->keys.as<uint64_t>(), key_cap);
+        bm25_topk_kernel<<<m, SORT_THREADS, SORT_N * 8, st>>>(s->keys.as<uint64_t>(), key_cap, s->cut.as<Bm25Cut>(),
+                                                             s->acc.as<uint32_t>(), s->n_docs, limit,
+                                                             doc_out_dev + (size_t)q0 * limit, score_out_dev + (size_t)q0 * limit);
+        CU(cudaGetLastError());
+    }
+    s->launches += (uint64_t)((nq + QC - 1) / QC) * (max_terms + 10);
+}
+}  // namespace
+
 gvdb_status gvdb_sparse_search_bm25_batch(gvdb_sparse* s, uint32_t nq, const uint64_t* q_off, const uint32_t* q_terms,
                                           const float* q_tfs, uint32_t limit, uint64_t* doc_out, float* score_out) {
     return guarded([&] {
         need(s, "sparse index");
         if (nq == 0 || limit == 0) return;
         need(q_off, "q_off"); need(doc_out, "doc_out"); need(score_out, "score_out");
-        if (limit > (uint32_t)SORT_N) fail(GVDB_ERR_NOT_IMPLEMENTED, "BM25 limit > 4096 is not implemented");
         std::lock_guard<std::mutex> lk(s->mu);
         for (uint64_t i = 0; i < (uint64_t)nq * limit; ++i) { doc_out[i] = UINT64_MAX; score_out[i] = -INFINITY; }
         if (s->n_docs == 0) return;                                   // src/sparse.rs:161-163
         DeviceGuard dg(s->device);
-        cudaStream_t st = s->stream;
-        const uint64_t nt = q_off[nq];
-        if (nt) { need(q_terms, "q_terms"); need(q_tfs, "q_tfs"); }
-        // idf on the host (libm logf == Rust's f32::ln); absent terms are dropped (:169)
-        std::vector<uint32_t> terms(nt);
-        std::vector<float> idf(nt);
-        uint32_t max_terms = 0;
-        for (uint32_t q = 0; q < nq; ++q) max_terms = std::max<uint32_t>(max_terms, (uint32_t)(q_off[q + 1] - q_off[q]));
-        for (uint64_t i = 0; i < nt; ++i) {
-            const uint32_t t = q_terms[i];
-            const uint64_t df = t < s->n_terms ? s->h_post_off[t + 1] - s->h_post_off[t] : 0;
-            terms[i] = df ? t : s->n_terms;                            // n_terms = "absent"
-            idf[i] = df ? std::log(((float)s->n_docs - (float)df + 0.5f) / ((float)df + 0.5f)) : 0.0f;
+        s->doc_out.ensure((size_t)nq * limit * 8);
+        s->score_out.ensure((size_t)nq * limit * 4);
+        bm25_core(s, s->stream, nq, q_off, q_terms, q_tfs, limit, s->doc_out.as<uint64_t>(), s->score_out.as<float>());
+        CU(cudaMemcpyAsync(doc_out, s->doc_out.p, (size_t)nq * limit * 8, cudaMemcpyDeviceToHost, s->stream));
+        CU(cudaMemcpyAsync(score_out, s->score_out.p, (size_t)nq * limit * 4, cudaMemcpyDeviceToHost, s->stream));
+        CU(cudaStreamSynchronize(s->stream));
+    });
+}
+
+gvdb_status gvdb_sparse_search_bm25_batch_device(gvdb_sparse* s, void* stream, uint32_t nq, const uint64_t* q_off,
+                                                 const uint32_t* q_terms, const float* q_tfs, uint32_t limit,
+                                                 uint64_t* doc_out_dev, float* score_out_dev) {
+    return guarded([&] {
+        need(s, "sparse index");
+        if (nq == 0 || limit == 0) return;
+        need(q_off, "q_off"); need(doc_out_dev, "doc_out"); need(score_out_dev, "score_out");
+        std::lock_guard<std::mutex> lk(s->mu);
+        DeviceGuard dg(s->device);
+        cudaStream_t st = (cudaStream_t)stream;
+        if (s->n_docs == 0) {                                         // src/sparse.rs:161-163
+            CU(cudaMemsetAsync(doc_out_dev, 0xFF, (size_t)nq * limit * 8, st));
+            fill_f32_kernel<<<(unsigned)(((size_t)nq * limit + 255) / 256), 256, 0, st>>>(score_out_dev, (size_t)nq * limit, -INFINITY);
+            return;
         }
-        const uint32_t QC = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(std::min<uint64_t>(nq, 64), (512ull << 20) / (s->n_docs * 4)));
-        const uint32_t key_cap = SORT_N;
-        s->acc.ensure((size_t)QC * s->n_docs * 4);
-        s->hist.ensure((size_t)QC * BM25_BINS * 4);
-        s->cut.ensure((size_t)QC * sizeof(Bm25Cut));
-        s->keys.ensure((size_t)QC * key_cap * 8);
-        s->q_off.ensure((size_t)(nq + 1) * 8);
-        s->q_terms.ensure(std::max<size_t>(4, nt * 4));
-        s->q_tfs.ensure(std::max<size_t>(4, nt * 4));
-        s->q_idf.ensure(std::max<size_t>(4, nt * 4));
-        s->doc_out.ensure((size_t)QC * limit * 8);
-        s->score_out.ensure((size_t)QC * limit * 4);
-        CU(cudaMemcpyAsync(s->q_off.p, q_off, (size_t)(nq + 1) * 8, cudaMemcpyHostToDevice, st));
-        if (nt) {
-            CU(cudaMemcpyAsync(s->q_terms.p, terms.data(), nt * 4, cudaMemcpyHostToDevice, st));
-            CU(cudaMemcpyAsync(s->q_tfs.p, q_tfs, nt * 4, cudaMemcpyHostToDevice, st));
-            CU(cudaMemcpyAsync(s->q_idf.p, idf.data(), nt * 4, cudaMemcpyHostToDevice, st));
-        }
-        cudaDeviceProp prop;
-        CU(cudaGetDeviceProperties(&prop, s->device));
-        const unsigned gx = (unsigned)prop.multiProcessorCount * 2;
-        for (uint32_t q0 = 0; q0 < nq; q0 += QC) {
-            const uint32_t m = std::min(QC, nq - q0);
-            CU(cudaMemsetAsync(s->acc.p, 0xFF, (size_t)m * s->n_docs * 4, st));
-            CU(cudaMemsetAsync(s->hist.p, 0, (size_t)m * BM25_BINS * 4, st));
-            CU(cudaMemsetAsync(s->cut.p, 0, (size_t)m * sizeof(Bm25Cut), st));
-            for (uint32_t rank = 0; rank < max_terms; ++rank)
-                bm25_accumulate_kernel<<<dim3(gx, m), 256, 0, st>>>(
-                    s->post_off.as<uint64_t>(), s->post_doc.as<uint32_t>(), s->post_tf.as<float>(), s->doc_len.as<float>(),
-                    s->n_terms, s->q_off.as<uint64_t>(), s->q_terms.as<uint32_t>(), s->q_tfs.as<float>(),
-                    s->q_idf.as<float>(), q0, (int)rank, s->k1, s->b, s->avg_len, s->n_docs, s->acc.as<uint32_t>());
-            for (int level = 0; level < 4; ++level) {
-                if (level) CU(cudaMemsetAsync(s->hist.p, 0, (size_t)m * BM25_BINS * 4, st));
-                bm25_hist_kernel<<<dim3(gx, m), 256, 0, st>>>(s->acc.as<uint32_t>(), s->n_docs, limit,
-                                                             s->hist.as<uint32_t>(), s->cut.as<Bm25Cut>(), level);
-                bm25_cut_kernel<<<m, 256, 0, st>>>(s->hist.as<uint32_t>(), limit, s->cut.as<Bm25Cut>(), level);
-            }
-            bm25_compact_kernel<<<dim3(gx, m), 256, 0, st>>>(s->acc.as<uint32_t>(), s->n_docs, s->cut.as<Bm25Cut>(),
-                                                            s->keys.as<uint64_t>(), key_cap);
-            bm25_topk_kernel<<<m, SORT_THREADS, SORT_N * 8, st>>>(s->keys.as<uint64_t>(), key_cap, s->cut.as<Bm25Cut>(),
-                                                                 s->acc.as<uint32_t>(), s->n_docs, limit,
-                                                                 s->doc_out.as<uint64_t>(), s->score_out.as<float>());
-            CU(cudaGetLastError());
-            CU(cudaMemcpyAsync(doc_out + (size_t)q0 * limit, s->doc_out.p, (size_t)m * limit * 8, cudaMemcpyDeviceToHost, st));
-            CU(cudaMemcpyAsync(score_out + (size_t)q0 * limit, s->score_out.p, (size_t)m * limit * 4, cudaMemcpyDeviceToHost, st));
-            CU(cudaStreamSynchronize(st));
-        }
+        bm25_core(s, st, nq, q_off, q_terms, q_tfs, limit, doc_out_dev, score_out_dev);
+    });
+}
+
+uint64_t gvdb_sparse_launches(const gvdb_sparse* s) { return s ? s->launches : 0; }
+
+// ---- rrf_fusion ---------------------------------------------------------------------------------------
+namespace {
+void rrf_launch(cudaStream_t st, const uint64_t* dense, uint32_t n_d, const uint64_t* sparse, uint32_t n_s,
+                const uint64_t* text, uint32_t n_t, uint32_t nq, float k, uint32_t limit, uint64_t* ids_out, float* scores_out) {
+    const uint32_t n = n_d + n_s + n_t;
+    if (n == 0 || n > RRF_MAX) fail(GVDB_ERR_INVALID_ARGUMENT, "rrf_fusion: the three list lengths must sum to 1..4096");
+    if ((n_d && !dense) || (n_s && !sparse) || (n_t && !text)) fail(GVDB_ERR_INVALID_ARGUMENT, "rrf_fusion: null list");
+    uint32_t n_eff = 64;
+    while (n_eff < n) n_eff <<= 1;
+    const size_t smem = (size_t)n * 8 + (size_t)n_eff * 8 + (size_t)n * 4;
+    static bool attr = false;   // benign race: idempotent
+    if (!attr) {
+        CU(cudaFuncSetAttribute(rrf_fusion_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(RRF_MAX * 20)));
+        attr = true;
+    }
+    const unsigned threads = n_eff <= 512 ? 256 : SORT_THREADS;
+    rrf_fusion_kernel<<<nq, threads, smem, st>>>(dense, n_d, sparse, n_s, text, n_t, k, limit, ids_out, scores_out);
+    CU(cudaGetLastError());
+}
+}  // namespace
+
+gvdb_status gvdb_rrf_fusion_batch_device(int32_t device, void* stream, const uint64_t* dense_dev, uint32_t n_dense,
+                                         const uint64_t* sparse_dev, uint32_t n_sparse, const uint64_t* text_dev,
+                                         uint32_t n_text, uint32_t nq, float k, uint32_t limit, uint64_t* ids_out_dev,
+                                         float* scores_out_dev) {
+    return guarded([&] {
+        if (nq == 0 || limit == 0) return;
+        need(ids_out_dev, "ids_out"); need(scores_out_dev, "scores_out");
+        DeviceGuard dg(device);
+        rrf_launch((cudaStream_t)stream, dense_dev, n_dense, sparse_dev, n_sparse, text_dev, n_text, nq, k, limit,
+                   ids_out_dev, scores_out_dev);
+    });
+}
+
+gvdb_status gvdb_rrf_fusion_batch(int32_t device, const uint64_t* dense, uint32_t n_dense, const uint64_t* sparse,
+                                  uint32_t n_sparse, const uint64_t* text, uint32_t n_text, uint32_t nq, float k,
+                                  uint32_t limit, uint64_t* ids_out, float* scores_out) {
+    return guarded([&] {
+        if (nq == 0 || limit == 0) return;
+        need(ids_out, "ids_out"); need(scores_out, "scores_out");
+        int ndev = 0;
+        if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+            fail(GVDB_ERR_INDEX, "no usable CUDA device (there is no CPU fallback)");
+        if (device < 0 || device >= ndev) fail(GVDB_ERR_INVALID_ARGUMENT, "bad device ordinal");
+        if ((n_dense && !dense) || (n_sparse && !sparse) || (n_text && !text)) fail(GVDB_ERR_INVALID_ARGUMENT, "rrf_fusion: null list");
+        DeviceGuard dg(device);
+        const size_t nl = (size_t)nq * (n_dense + n_sparse + n_text);
+        DevBuf in, out;
+        struct Rel { DevBuf &a, &b; ~Rel() { a.release(); b.release(); } } rel{in, out};
+        in.ensure(std::max<size_t>(8, nl * 8));
+        out.ensure((size_t)nq * limit * 12);
+        uint64_t* d = in.as<uint64_t>();
+        uint64_t* sp = d + (size_t)nq * n_dense;
+        uint64_t* tx = sp + (size_t)nq * n_sparse;
+        if (n_dense) CU(cudaMemcpy(d, dense, (size_t)nq * n_dense * 8, cudaMemcpyHostToDevice));
+        if (n_sparse) CU(cudaMemcpy(sp, sparse, (size_t)nq * n_sparse * 8, cudaMemcpyHostToDevice));
+        if (n_text) CU(cudaMemcpy(tx, text, (size_t)nq * n_text * 8, cudaMemcpyHostToDevice));
+        uint64_t* oi = out.as<uint64_t>();
+        float* os = reinterpret_cast<float*>(oi + (size_t)nq * limit);
+        rrf_launch(nullptr, n_dense ? d : nullptr, n_dense, n_sparse ? sp : nullptr, n_sparse, n_text ? tx : nullptr, n_text,
+                   nq, k, limit, oi, os);
+        CU(cudaMemcpy(ids_out, oi, (size_t)nq * limit * 8, cudaMemcpyDeviceToHost));
+        CU(cudaMemcpy(scores_out, os, (size_t)nq * limit * 4, cudaMemcpyDeviceToHost));
     });
 }
 

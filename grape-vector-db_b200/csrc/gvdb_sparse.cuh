@@ -187,4 +187,93 @@ bm25_topk_kernel(const uint64_t* __restrict__ keys, uint32_t key_cap, const Bm25
     }
 }
 
+__global__ void fill_f32_kernel(float* __restrict__ p, size_t n, float v) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+// ---- rrf_fusion (/root/reference/src/hybrid.rs:422-488) on the GPU ------------------------------
+// One CTA per query.  The three lists (dense, sparse, text; document numbers, GVDB_NO_ID ends a list
+// early) are laid end to end in shared memory.  Entry p is a HEAD when no earlier entry carries its
+// document; a head's score is built in the reference's order: the dense loop INSERTS 1/(k + rank+1)
+// (a repeated document overwrites), the sparse and text loops add theirs in list order.  Heads are
+// ordered by score descending; exact ties (unspecified in the reference: HashMap iteration) by first
+// appearance.  n_d + n_s + n_t <= RRF_MAX.
+constexpr uint32_t RRF_MAX = 4096;
+
+__global__ void __launch_bounds__(SORT_THREADS)
+rrf_fusion_kernel(const uint64_t* __restrict__ dense, uint32_t n_d, const uint64_t* __restrict__ sparse, uint32_t n_s,
+                  const uint64_t* __restrict__ text, uint32_t n_t, float k, uint32_t limit,
+                  uint64_t* __restrict__ ids_out, float* __restrict__ scores_out) {
+    extern __shared__ __align__(16) uint64_t rrf_smem[];
+    const uint32_t n = n_d + n_s + n_t;
+    const uint32_t n_eff = max(64u, next_pow2(n));
+    uint64_t* ids = rrf_smem;                 // [n]
+    uint64_t* keys = rrf_smem + n;            // [n_eff]
+    float* sc = reinterpret_cast<float*>(keys + n_eff);   // [n]
+    __shared__ uint32_t len[3];
+    const uint32_t q = blockIdx.x;
+    if (threadIdx.x < 3) len[threadIdx.x] = threadIdx.x == 0 ? n_d : threadIdx.x == 1 ? n_s : n_t;
+    __syncthreads();
+    for (uint32_t p = threadIdx.x; p < n; p += blockDim.x) {
+        uint64_t id;
+        if (p < n_d) { id = dense[(size_t)q * n_d + p]; if (id == UINT64_MAX) atomicMin(&len[0], p); }
+        else if (p < n_d + n_s) { id = sparse[(size_t)q * n_s + (p - n_d)]; if (id == UINT64_MAX) atomicMin(&len[1], p - n_d); }
+        else { id = text[(size_t)q * n_t + (p - n_d - n_s)]; if (id == UINT64_MAX) atomicMin(&len[2], p - n_d - n_s); }
+        ids[p] = id;
+    }
+    __syncthreads();
+    const uint32_t l0 = len[0], l1 = len[1], l2 = len[2];
+    for (uint32_t p = threadIdx.x; p < n_eff; p += blockDim.x) {
+        uint64_t key = UINT64_MAX;
+        if (p < n) {
+            const uint32_t pos = p < n_d ? p : p < n_d + n_s ? p - n_d : p - n_d - n_s;
+            const bool valid = p < n_d ? pos < l0 : p < n_d + n_s ? pos < l1 : pos < l2;
+            if (valid) {
+                const uint64_t id = ids[p];
+                bool head = true, have = false;
+                float s = 0.0f;
+                for (uint32_t j = 0; j < l0; ++j)
+                    if (ids[j] == id) {
+                        if (j < p) head = false;
+                        s = __fdiv_rn(1.0f, __fadd_rn(k, (float)(j + 1)));          // insert: overwrites
+                        have = true;
+                    }
+                for (uint32_t j = 0; j < l1 && head; ++j)
+                    if (ids[n_d + j] == id) {
+                        if (n_d + j < p) head = false;
+                        const float r = __fdiv_rn(1.0f, __fadd_rn(k, (float)(j + 1)));
+                        s = have ? __fadd_rn(s, r) : r;
+                        have = true;
+                    }
+                for (uint32_t j = 0; j < l2 && head; ++j)
+                    if (ids[n_d + n_s + j] == id) {
+                        if (n_d + n_s + j < p) head = false;
+                        const float r = __fdiv_rn(1.0f, __fadd_rn(k, (float)(j + 1)));
+                        s = have ? __fadd_rn(s, r) : r;
+                        have = true;
+                    }
+                if (head) {
+                    sc[p] = s;
+                    key = ((uint64_t)(~f32_asc_key(s)) << 32) | p;
+                }
+            }
+        }
+        keys[p] = key;
+    }
+    __syncthreads();
+    bitonic_sort_smem(keys, n_eff);
+    for (uint32_t t = threadIdx.x; t < limit; t += blockDim.x) {
+        const uint64_t key = t < n_eff ? keys[t] : UINT64_MAX;
+        if (key != UINT64_MAX) {
+            const uint32_t p = (uint32_t)key;
+            ids_out[(size_t)q * limit + t] = ids[p];
+            scores_out[(size_t)q * limit + t] = sc[p];
+        } else {
+            ids_out[(size_t)q * limit + t] = UINT64_MAX;
+            scores_out[(size_t)q * limit + t] = -INFINITY;
+        }
+    }
+}
+
 }  // namespace gvdb

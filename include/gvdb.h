@@ -301,6 +301,29 @@ GVDB_API float gvdb_sparse_average_document_length(const gvdb_sparse* s);
 GVDB_API gvdb_status gvdb_sparse_search_bm25_batch(gvdb_sparse* s, uint32_t nq, const uint64_t* q_off,
                                                    const uint32_t* q_terms, const float* q_tfs, uint32_t limit,
                                                    uint64_t* doc_out, float* score_out);
+/* The same with the answers left in DEVICE buffers, asynchronous on `stream` (the query CSR is still
+ * HOST memory: it is a few bytes per query and the idf is computed on the host). */
+GVDB_API gvdb_status gvdb_sparse_search_bm25_batch_device(gvdb_sparse* s, void* stream, uint32_t nq,
+                                                          const uint64_t* q_off, const uint32_t* q_terms,
+                                                          const float* q_tfs, uint32_t limit,
+                                                          uint64_t* doc_out_dev, float* score_out_dev);
+GVDB_API uint64_t gvdb_sparse_launches(const gvdb_sparse* s);   /* kernels launched by this handle's searches */
+
+/* rrf_fusion (src/hybrid.rs:422-488) for nq queries at once.  Each list is nq x n_* document numbers,
+ * best first; GVDB_NO_ID ends a query's list early (the padding the search calls leave); n_* = 0
+ * skips a list.  score(doc) = sum over the lists, in the order dense, sparse, text, of
+ * 1.0 / (k + (rank + 1) as f32): the dense loop inserts, the others add (same f32 order as the
+ * reference).  Output: nq x limit, score descending; exact score ties — unspecified in the
+ * reference, which sorts a HashMap's entries — by first appearance (dense, then sparse, then text).
+ * n_dense + n_sparse + n_text <= 4096. */
+GVDB_API gvdb_status gvdb_rrf_fusion_batch(int32_t device, const uint64_t* dense, uint32_t n_dense,
+                                           const uint64_t* sparse, uint32_t n_sparse, const uint64_t* text,
+                                           uint32_t n_text, uint32_t nq, float k, uint32_t limit,
+                                           uint64_t* ids_out, float* scores_out);
+GVDB_API gvdb_status gvdb_rrf_fusion_batch_device(int32_t device, void* stream, const uint64_t* dense_dev,
+                                                  uint32_t n_dense, const uint64_t* sparse_dev, uint32_t n_sparse,
+                                                  const uint64_t* text_dev, uint32_t n_text, uint32_t nq, float k,
+                                                  uint32_t limit, uint64_t* ids_out_dev, float* scores_out_dev);
 
 /* ---- measurement hooks ---------------------------------------------------------------- */
 /* When enabled, every kernel the library launches is bracketed by CUDA events on the stream

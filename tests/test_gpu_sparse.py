@@ -85,3 +85,76 @@ def test_bm25_empty_index_and_bad_postings(gv):
         with pytest.raises(gv.ConfigError):
             sp.build(np.array([0, 2], dtype=np.uint64), np.array([1, 1], dtype=np.uint32),
                      np.ones(2, dtype=np.float32), np.ones(3, dtype=np.float32))
+
+
+# ---- rrf_fusion on the GPU (src/hybrid.rs:422-488) ---------------------------------------------
+def test_rrf_known_values(gv):
+    # the lists of the reference's test_rrf_fusion (src/hybrid.rs:991-1025) as document numbers:
+    # dense doc1, doc2, doc3; sparse doc2, doc1, doc4
+    ids, sc = gv.rrf_fusion_batch([[1, 2, 3]], [[2, 1, 4]], None, 60.0)
+    one = np.float32(1.0)
+    d1 = one / np.float32(61) + one / np.float32(62)
+    d2 = one / np.float32(62) + one / np.float32(61)
+    assert ids[0, :2].tolist() == [1, 2] and sc[0, 0] == d1 and sc[0, 1] == d2
+    assert ids[0, 2:].tolist() == [3, 4] and sc[0, 2] == sc[0, 3] == one / np.float32(63)   # tie: first appearance
+
+
+def test_rrf_matches_oracle(gv):
+    rng = np.random.default_rng(11)
+    for n_d, n_s, n_t, pool in ((200, 200, 0, 300), (200, 200, 200, 350), (7, 0, 5, 9), (0, 64, 0, 100),
+                                (1500, 1500, 1000, 2500)):
+        nq = 9
+        def lists(n):
+            if n == 0:
+                return None
+            out = np.full((nq, n), gv.NO_ID, dtype=np.uint64)
+            for q in range(nq):
+                m = n if q % 3 else int(rng.integers(0, n + 1))          # some lists end early
+                out[q, :m] = rng.choice(pool, size=min(m, pool), replace=False)[:m].astype(np.uint64) if m <= pool else 0
+            return out
+        d, s, t = lists(n_d), lists(n_s), lists(n_t)
+        limit = 100
+        ids, sc = gv.rrf_fusion_batch(d, s, t, 60.0, limit)
+        for q in range(nq):
+            trim = lambda a: [] if a is None else a[q][a[q] != gv.NO_ID]
+            oi, os_ = oracle.rrf_fusion(trim(d), trim(s), trim(t), 60.0)
+            r = min(limit, len(oi))
+            assert np.array_equal(ids[q, :r], oi[:r]), (n_d, n_s, n_t, q)
+            assert np.array_equal(_bits(sc[q, :r]), _bits(os_[:r]))
+            assert np.all(ids[q, r:] == gv.NO_ID) and np.all(np.isneginf(sc[q, r:]))
+
+
+def test_hybrid_search_matches_oracle_composition(gv):
+    """HybridSearchEngine::search (src/hybrid.rs:286-356) on the GPU == oracle dense list + oracle BM25
+    list + oracle RRF, for two-stage and exact dense lists."""
+    from grape_vector_db_b200 import synth
+    n, dim, vocab, nq, limit = 20_000, 256, 3_000, 70, 25
+    rows = synth.lowrank_rows(0, n, dim)
+    qs = synth.lowrank_queries(0, nq, dim)
+    post = synth.sparse_corpus(n, vocab=vocab)
+    sq = synth.sparse_queries(nq, vocab=vocab)
+    want = 2 * limit
+    with gv.GpuIndex(dim) as dense, gv.GpuSparseIndex() as sparse:
+        dense.add(rows)
+        sparse.build(*post)
+        for exact in (False, True):
+            hy = gv.HybridSearcher(dense, sparse, rrf_k=60.0, oversample=4, exact_dense=exact)
+            ids, sc = hy.search_batch(qs, sq, limit)
+            if exact:
+                od, _ = oracle.flat_search_batch(qs, rows, want)
+            else:
+                od, _ = oracle.multi_stage_search_batch(qs, rows, want * 4, want, nthreads=8)
+            for q in range(nq):
+                ob, _ = oracle.bm25_search(sq[q][0], sq[q][1], *post, want)
+                oi, os_ = oracle.rrf_fusion(od[q], ob, [], 60.0)
+                assert np.array_equal(ids[q], oi[:limit]), (exact, q)
+                assert np.array_equal(_bits(sc[q]), _bits(os_[:limit]))
+        # sparse-only and dense-only requests (the Option fields of HybridSearchRequest)
+        hy = gv.HybridSearcher(dense, sparse)
+        ids, _ = hy.search_batch(None, sq[:8], limit)
+        for q in range(8):
+            ob, _ = oracle.bm25_search(sq[q][0], sq[q][1], *post, want)
+            assert np.array_equal(ids[q, :min(limit, len(ob))], ob[:limit])
+        ids, _ = hy.search_batch(qs[:8], None, limit)
+        od, _ = oracle.multi_stage_search_batch(qs[:8], rows, want * 4, want, nthreads=8)
+        assert np.array_equal(ids, od[:, :limit])
