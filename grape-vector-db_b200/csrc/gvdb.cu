@@ -2017,10 +2017,11 @@ void bm25_core(gvdb_sparse* s, cudaStream_t st, uint32_t nq, const uint64_t* q_o
         terms[i] = df ? t : s->n_terms;                            // n_terms = "absent"
         idf[i] = df ? std::log(((float)s->n_docs - (float)df + 0.5f) / ((float)df + 0.5f)) : 0.0f;
     }
-    const uint32_t QC = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(std::min<uint64_t>(nq, 64), (512ull << 20) / (s->n_docs * 4)));
+    const uint64_t stride = (s->n_docs + 3) / 4 * 4;               // accumulators per query: uint4-readable, padding stays "absent"
+    const uint32_t QC = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(std::min<uint64_t>(nq, 64), (512ull << 20) / (stride * 4)));
     const uint32_t key_cap = SORT_N;
-    s->acc.ensure((size_t)QC * s->n_docs * 4);
-    s->hist.ensure((size_t)QC * BM25_BINS * 4);
+    s->acc.ensure((size_t)QC * stride * 4);
+    s->hist.ensure((size_t)QC * BM25_LEVEL_BINS * 4);
     s->cut.ensure((size_t)QC * sizeof(Bm25Cut));
     s->keys.ensure((size_t)QC * key_cap * 8);
     s->q_off.ensure((size_t)(nq + 1) * 8);
@@ -2037,28 +2038,27 @@ void bm25_core(gvdb_sparse* s, cudaStream_t st, uint32_t nq, const uint64_t* q_o
     const unsigned gx = (unsigned)s->sm_count * 2;
     for (uint32_t q0 = 0; q0 < nq; q0 += QC) {
         const uint32_t m = std::min(QC, nq - q0);
-        CU(cudaMemsetAsync(s->acc.p, 0xFF, (size_t)m * s->n_docs * 4, st));
-        CU(cudaMemsetAsync(s->hist.p, 0, (size_t)m * BM25_BINS * 4, st));
+        CU(cudaMemsetAsync(s->acc.p, 0xFF, (size_t)m * stride * 4, st));
         CU(cudaMemsetAsync(s->cut.p, 0, (size_t)m * sizeof(Bm25Cut), st));
         for (uint32_t rank = 0; rank < max_terms; ++rank)
             bm25_accumulate_kernel<<<dim3(gx, m), 256, 0, st>>>(
                 s->post_off.as<uint64_t>(), s->post_doc.as<uint32_t>(), s->post_tf.as<float>(), s->doc_len.as<float>(),
                 s->n_terms, s->q_off.as<uint64_t>(), s->q_terms.as<uint32_t>(), s->q_tfs.as<float>(),
-                s->q_idf.as<float>(), q0, (int)rank, s->k1, s->b, s->avg_len, s->n_docs, s->acc.as<uint32_t>());
-        for (int level = 0; level < 4; ++level) {
-            if (level) CU(cudaMemsetAsync(s->hist.p, 0, (size_t)m * BM25_BINS * 4, st));
-            bm25_hist_kernel<<<dim3(gx, m), 256, 0, st>>>(s->acc.as<uint32_t>(), s->n_docs, limit,
+                s->q_idf.as<float>(), q0, (int)rank, s->k1, s->b, s->avg_len, stride, s->acc.as<uint32_t>());
+        for (int level = 0; level < 6; ++level) {
+            CU(cudaMemsetAsync(s->hist.p, 0, (size_t)m * BM25_LEVEL_BINS * 4, st));
+            bm25_hist_kernel<<<dim3(gx, m), 256, 0, st>>>(s->acc.as<uint32_t>(), stride, limit,
                                                          s->hist.as<uint32_t>(), s->cut.as<Bm25Cut>(), level);
             bm25_cut_kernel<<<m, 256, 0, st>>>(s->hist.as<uint32_t>(), limit, s->cut.as<Bm25Cut>(), level);
         }
-        bm25_compact_kernel<<<dim3(gx, m), 256, 0, st>>>(s->acc.as<uint32_t>(), s->n_docs, s->cut.as<Bm25Cut>(),
+        bm25_compact_kernel<<<dim3(gx, m), 256, 0, st>>>(s->acc.as<uint32_t>(), stride, s->cut.as<Bm25Cut>(),
                                                         s->keys.as<uint64_t>(), key_cap);
         bm25_topk_kernel<<<m, SORT_THREADS, SORT_N * 8, st>>>(s->keys.as<uint64_t>(), key_cap, s->cut.as<Bm25Cut>(),
-                                                             s->acc.as<uint32_t>(), s->n_docs, limit,
+                                                             s->acc.as<uint32_t>(), stride, limit,
                                                              doc_out_dev + (size_t)q0 * limit, score_out_dev + (size_t)q0 * limit);
         CU(cudaGetLastError());
     }
-    s->launches += (uint64_t)((nq + QC - 1) / QC) * (max_terms + 10);
+    s->launches += (uint64_t)((nq + QC - 1) / QC) * (max_terms + 14);
 }
 }  // namespace
 

@@ -11,8 +11,8 @@
 // document appears at most once in a term's postings, so one launch per term rank touches every
 // accumulator at most once: additions happen in query-term order, like the reference's loop.
 //   bm25_accumulate_kernel   one term rank of every query of the chunk
-//   bm25_hist_kernel         histogram levels: 16 high / 16 low bits of the descending score image,
-//                            then 16 high / 16 low bits of the document number among the ties
+//   bm25_hist_kernel         radix-select levels (11 + 11 + 10 bits): the descending score image, then
+//                            the document number among the documents tying at the cut
 //   bm25_cut_kernel          the exact 32-bit image of the limit-th best score and the last tying
 //                            document kept
 //   bm25_compact_kernel      keys (descending image << 32 | doc) inside the cut: exactly
@@ -27,26 +27,26 @@
 namespace gvdb {
 
 constexpr uint32_t BM25_ABSENT = 0xFFFFFFFFu;     // accumulator bit pattern of "document not touched" (a NaN)
-constexpr int BM25_BINS = 65536;
 
-// per query: the cut found level by level (see bm25_cut_kernel)
+// per query: the cut found level by level (see bm25_hist_kernel)
 struct Bm25Cut {
     uint32_t present;      // documents touched by the query
-    uint32_t bstar, below; // level 0: bin (16 high image bits) holding the want-th best, documents in better bins
-    uint32_t thr32, above; // level 1: exact image of the want-th best score, documents strictly better than it
-    uint32_t m;            //          documents at or above thr32 (m - above tie exactly at the cut)
-    uint32_t dstar, dbelow;// level 2: among the ties, bin (16 high document bits) of the last one kept
-    uint32_t doc_thr;      // level 3: ties are kept up to this document number (ascending = the tie order)
-    uint32_t appended, pad0, pad1;
+    uint32_t want_left;    // rank of the wanted entry inside the current prefix (1-based)
+    uint32_t prefix;       // key bits fixed so far (image levels, then document levels)
+    uint32_t thr32, above; // exact image of the want-th best score, documents strictly better than it
+    uint32_t m;            // documents at or above thr32 (m - above tie exactly at the cut)
+    uint32_t doc_thr;      // ties are kept up to this document number (ascending = the tie order)
+    uint32_t appended;
 };
 
-// grid.y = query of the chunk; the query's rank-th term (if it has one) against its postings
+// grid.y = query of the chunk; the query's rank-th term (if it has one) against its postings.
+// acc_stride = n_docs rounded up to 4 (the later passes read the accumulators as uint4).
 __global__ void __launch_bounds__(256)
 bm25_accumulate_kernel(const uint64_t* __restrict__ post_off, const uint32_t* __restrict__ post_doc,
                        const float* __restrict__ post_tf, const float* __restrict__ doc_len, uint32_t n_terms,
                        const uint64_t* __restrict__ q_off, const uint32_t* __restrict__ q_terms,
                        const float* __restrict__ q_tfs, const float* __restrict__ q_idf, uint32_t q0, int rank,
-                       float k1, float b, float avg_len, uint64_t n_docs, uint32_t* __restrict__ acc) {
+                       float k1, float b, float avg_len, uint64_t acc_stride, uint32_t* __restrict__ acc) {
     const uint32_t q = q0 + blockIdx.y;
     const uint64_t t0 = q_off[q], t1 = q_off[q + 1];
     if (t0 + rank >= t1) return;
@@ -54,56 +54,102 @@ bm25_accumulate_kernel(const uint64_t* __restrict__ post_off, const uint32_t* __
     if (term >= n_terms) return;
     const float qtf = q_tfs[t0 + rank], idf = q_idf[t0 + rank];
     const uint64_t p0 = post_off[term], p1 = post_off[term + 1];
-    uint32_t* mine = acc + (size_t)blockIdx.y * n_docs;
+    uint32_t* mine = acc + (size_t)blockIdx.y * acc_stride;
     const float k1p1 = __fadd_rn(k1, 1.0f), one_minus_b = __fsub_rn(1.0f, b);
-    for (uint64_t p = p0 + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; p < p1; p += (uint64_t)gridDim.x * blockDim.x) {
-        const uint32_t doc = post_doc[p];
-        const float tf = post_tf[p], len = doc_len[doc];
-        // (tf * (k1 + 1)) / (tf + k1 * (1 - b + b * (len / avg_len)))
-        const float denom = __fadd_rn(tf, __fmul_rn(k1, __fadd_rn(one_minus_b, __fmul_rn(b, __fdiv_rn(len, avg_len)))));
-        const float tfc = __fdiv_rn(__fmul_rn(tf, k1p1), denom);
-        const float s = __fmul_rn(__fmul_rn(qtf, tfc), idf);
-        const uint32_t old = mine[doc];
-        const float base = old == BM25_ABSENT ? 0.0f : __uint_as_float(old);
-        mine[doc] = __float_as_uint(__fadd_rn(base, s));
+    constexpr int U = 4;                       // postings in flight per thread (independent loads first)
+    for (uint64_t base = p0 + (uint64_t)blockIdx.x * blockDim.x * U; base < p1; base += (uint64_t)gridDim.x * blockDim.x * U) {
+        uint32_t doc[U], old[U];
+        float tf[U], len[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const uint64_t p = base + (uint64_t)u * blockDim.x + threadIdx.x;
+            doc[u] = p < p1 ? __ldg(post_doc + p) : 0xFFFFFFFFu;
+            tf[u] = p < p1 ? __ldg(post_tf + p) : 0.0f;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+            if (doc[u] != 0xFFFFFFFFu) { len[u] = __ldg(doc_len + doc[u]); old[u] = mine[doc[u]]; }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (doc[u] == 0xFFFFFFFFu) continue;
+            // (tf * (k1 + 1)) / (tf + k1 * (1 - b + b * (len / avg_len)))
+            const float denom = __fadd_rn(tf[u], __fmul_rn(k1, __fadd_rn(one_minus_b, __fmul_rn(b, __fdiv_rn(len[u], avg_len)))));
+            const float tfc = __fdiv_rn(__fmul_rn(tf[u], k1p1), denom);
+            const float sc = __fmul_rn(__fmul_rn(qtf, tfc), idf);
+            const float base_v = old[u] == BM25_ABSENT ? 0.0f : __uint_as_float(old[u]);
+            mine[doc[u]] = __float_as_uint(__fadd_rn(base_v, sc));
+        }
     }
 }
 
 // descending image of a present score; a NaN score cannot be produced by finite inputs
 __device__ __forceinline__ uint32_t bm25_desc_image(uint32_t bits) { return ~f32_asc_key(__uint_as_float(bits)); }
 
-// Four histogram levels find the exact cut without sorting the accumulator:
-//   level 0  16 high bits of every present document's image (+ the present count)
-//   level 1  16 low bits of the images inside the level-0 cut bin          -> thr32, above, m
-//   level 2  16 high bits of the DOCUMENT NUMBER of the documents tying at thr32   (only if m > want)
-//   level 3  16 low bits of the document number inside the level-2 bin     -> doc_thr
-// so exactly want = min(limit, present) documents pass "image < thr32 or (image == thr32 and
-// doc <= doc_thr)", however many documents share the cut score (BM25 over tf = count/len data ties
-// by the million).
+// Radix select of the exact cut without sorting the accumulator.  A 32-bit key is fixed 11 + 11 + 10
+// bits at a time (BM25_LEVEL_BINS = 2048 bins per level): levels 0-2 over the descending score image
+// give thr32 (the want-th best score), above and m; when more documents tie at thr32 than fit
+// (m > want), levels 3-5 do the same over the DOCUMENT NUMBER of the tying documents and give doc_thr.
+// Exactly want = min(limit, present) documents then pass "image < thr32 or (image == thr32 and
+// doc <= doc_thr)", however many share the cut score (BM25 over tf = count/len data ties by the million).
+// Histograms are per CTA in shared memory, lanes with equal bins are combined first (__match_any_sync):
+// tying scores put millions of documents into one bin, which serialises global atomics.
+constexpr int BM25_LEVEL_BINS = 2048;
+__host__ __device__ __forceinline__ int bm25_level_shift(int level) { return (level % 3) == 0 ? 21 : (level % 3) == 1 ? 10 : 0; }
+__host__ __device__ __forceinline__ int bm25_level_bits(int level) { return (level % 3) == 2 ? 10 : 11; }
+
 __global__ void __launch_bounds__(256)
-bm25_hist_kernel(const uint32_t* __restrict__ acc, uint64_t n_docs, uint32_t limit, uint32_t* __restrict__ hist,
+bm25_hist_kernel(const uint32_t* __restrict__ acc, uint64_t acc_stride, uint32_t limit, uint32_t* __restrict__ hist,
                  Bm25Cut* __restrict__ cut, int level) {
-    const uint32_t* mine = acc + (size_t)blockIdx.y * n_docs;
-    uint32_t* h = hist + (size_t)blockIdx.y * BM25_BINS;
+    __shared__ uint32_t sh[BM25_LEVEL_BINS];
+    const uint4* mine = reinterpret_cast<const uint4*>(acc + (size_t)blockIdx.y * acc_stride);
+    uint32_t* h = hist + (size_t)blockIdx.y * BM25_LEVEL_BINS;
     const Bm25Cut c = cut[blockIdx.y];
     if (level >= 1 && c.present == 0) return;
-    if (level >= 2 && c.m == min(limit, c.present)) return;          // no surplus ties: every tie is kept
+    if (level >= 3 && c.m == min(limit, c.present)) return;          // no surplus ties: every tie is kept
+    for (int i = threadIdx.x; i < BM25_LEVEL_BINS; i += blockDim.x) sh[i] = 0;
+    __syncthreads();
+    const int shift = bm25_level_shift(level), bits = bm25_level_bits(level);
+    const bool first = (level % 3) == 0;
+    const uint32_t lane = threadIdx.x & 31;
+    const uint64_t n4 = acc_stride / 4;
     uint32_t present = 0;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_docs; i += (uint64_t)gridDim.x * blockDim.x) {
-        const uint32_t v = mine[i];
-        if (v == BM25_ABSENT) continue;
-        const uint32_t img = bm25_desc_image(v);
-        if (level == 0) { atomicAdd(&h[img >> 16], 1u); ++present; }
-        else if (level == 1) { if ((img >> 16) == c.bstar) atomicAdd(&h[img & 0xffffu], 1u); }
-        else if (img == c.thr32) {
-            const uint32_t d = (uint32_t)i;
-            if (level == 2) atomicAdd(&h[d >> 16], 1u);
-            else if ((d >> 16) == c.dstar) atomicAdd(&h[d & 0xffffu], 1u);
+    // two uint4 (8 accumulators) in flight per thread; the padding past n_docs reads as "absent"
+    for (uint64_t base = (uint64_t)blockIdx.x * blockDim.x * 2; base < n4; base += (uint64_t)gridDim.x * blockDim.x * 2) {
+        uint4 v[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const uint64_t i = base + (uint64_t)u * blockDim.x + threadIdx.x;
+            v[u] = i < n4 ? __ldg(mine + i) : make_uint4(BM25_ABSENT, BM25_ABSENT, BM25_ABSENT, BM25_ABSENT);
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const uint64_t i = base + (uint64_t)u * blockDim.x + threadIdx.x;
+            const uint32_t w[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                bool ok = w[e] != BM25_ABSENT;
+                uint32_t key = 0;
+                if (ok) {
+                    const uint32_t img = bm25_desc_image(w[e]);
+                    if (level < 3) key = img;
+                    else { ok = img == c.thr32; key = (uint32_t)(i * 4 + e); }
+                    if (level == 0) ++present;
+                }
+                if (ok && !first) ok = (key >> (shift + bits)) == c.prefix;
+                const uint32_t bin = ok ? (key >> shift) & ((1u << bits) - 1u) : 0xFFFFFFFFu;
+                if (__any_sync(0xffffffffu, ok)) {
+                    const uint32_t peers = __match_any_sync(0xffffffffu, bin);
+                    if (ok && lane == (uint32_t)(__ffs(peers) - 1)) atomicAdd(&sh[bin], (uint32_t)__popc(peers));
+                }
+            }
         }
     }
+    __syncthreads();
+    for (int i = threadIdx.x; i < BM25_LEVEL_BINS; i += blockDim.x)
+        if (sh[i]) atomicAdd(&h[i], sh[i]);
     if (level == 0) {
         for (int o = 16; o > 0; o >>= 1) present += __shfl_xor_sync(0xffffffffu, present, o);
-        if ((threadIdx.x & 31) == 0 && present) atomicAdd(&cut[blockIdx.y].present, present);
+        if (lane == 0 && present) atomicAdd(&cut[blockIdx.y].present, present);
     }
 }
 
@@ -111,19 +157,18 @@ bm25_hist_kernel(const uint32_t* __restrict__ acc, uint64_t n_docs, uint32_t lim
 __global__ void __launch_bounds__(256)
 bm25_cut_kernel(const uint32_t* __restrict__ hist, uint32_t limit, Bm25Cut* __restrict__ cut, int level) {
     __shared__ uint32_t part[256];
-    const uint32_t* h = hist + (size_t)blockIdx.x * BM25_BINS;
+    const uint32_t* h = hist + (size_t)blockIdx.x * BM25_LEVEL_BINS;
     Bm25Cut* c = cut + blockIdx.x;
     const uint32_t want_all = min(limit, c->present);
-    if (level >= 2 && c->m == want_all) { if (threadIdx.x == 0) c->doc_thr = 0xFFFFFFFFu; return; }
-    const uint32_t want = level == 0 ? want_all : level == 1 ? want_all - c->below
-                        : level == 2 ? want_all - c->above : want_all - c->above - c->dbelow;
-    constexpr int PER = BM25_BINS / 256;
+    if (level >= 3 && c->m == want_all) { if (threadIdx.x == 0) c->doc_thr = 0xFFFFFFFFu; return; }
+    const uint32_t want = level == 0 ? want_all : c->want_left;
+    constexpr int PER = BM25_LEVEL_BINS / 256;
     uint32_t sum = 0;
     for (int i = 0; i < PER; ++i) sum += h[threadIdx.x * PER + i];
     part[threadIdx.x] = sum;
     __syncthreads();
     if (threadIdx.x == 0) {
-        if (want_all == 0) { c->bstar = 0; c->below = 0; c->thr32 = 0; c->above = 0; c->m = 0; c->doc_thr = 0; return; }
+        if (want_all == 0) { c->want_left = 0; c->prefix = 0; c->thr32 = 0; c->above = 0; c->m = 0; c->doc_thr = 0; return; }
         uint32_t run = 0;
         int t = 0;
         for (; t < 255; ++t) { if (run + part[t] >= want) break; run += part[t]; }
@@ -131,10 +176,16 @@ bm25_cut_kernel(const uint32_t* __restrict__ hist, uint32_t limit, Bm25Cut* __re
             const uint32_t hv = h[t * PER + i];
             if (run + hv >= want) {
                 const uint32_t bin = (uint32_t)(t * PER + i);
-                if (level == 0) { c->bstar = bin; c->below = run; }
-                else if (level == 1) { c->thr32 = (c->bstar << 16) | bin; c->above = c->below + run; c->m = c->below + run + hv; }
-                else if (level == 2) { c->dstar = bin; c->dbelow = run; }
-                else c->doc_thr = (c->dstar << 16) | bin;
+                const uint32_t prefix = (level % 3) == 0 ? bin : (c->prefix << bm25_level_bits(level)) | bin;
+                c->prefix = prefix;
+                c->want_left = want - run;                     // rank inside the chosen bin
+                if (level == 2) {                              // the image is complete
+                    c->thr32 = prefix;
+                    c->above = want_all - (want - run);
+                    c->m = want_all - (want - run) + hv;
+                    c->want_left = want - run;                 // ties to keep, if they do not all fit
+                }
+                if (level == 5) c->doc_thr = prefix;
                 break;
             }
             run += hv;
@@ -144,20 +195,35 @@ bm25_cut_kernel(const uint32_t* __restrict__ hist, uint32_t limit, Bm25Cut* __re
 
 // keys (image << 32 | doc) of the documents inside the cut: exactly min(limit, present) of them
 __global__ void __launch_bounds__(256)
-bm25_compact_kernel(const uint32_t* __restrict__ acc, uint64_t n_docs, Bm25Cut* __restrict__ cut,
+bm25_compact_kernel(const uint32_t* __restrict__ acc, uint64_t acc_stride, Bm25Cut* __restrict__ cut,
                     uint64_t* __restrict__ keys, uint32_t key_cap) {
-    const uint32_t* mine = acc + (size_t)blockIdx.y * n_docs;
+    const uint4* mine = reinterpret_cast<const uint4*>(acc + (size_t)blockIdx.y * acc_stride);
     Bm25Cut* c = cut + blockIdx.y;
     if (c->m == 0) return;
     const uint32_t thr = c->thr32, doc_thr = c->doc_thr;
     uint64_t* out = keys + (size_t)blockIdx.y * key_cap;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_docs; i += (uint64_t)gridDim.x * blockDim.x) {
-        const uint32_t v = mine[i];
-        if (v == BM25_ABSENT) continue;
-        const uint32_t img = bm25_desc_image(v);
-        if (img < thr || (img == thr && (uint32_t)i <= doc_thr)) {
-            const uint32_t pos = atomicAdd(&c->appended, 1u);
-            if (pos < key_cap) out[pos] = ((uint64_t)img << 32) | (uint32_t)i;
+    const uint64_t n4 = acc_stride / 4;
+    for (uint64_t base = (uint64_t)blockIdx.x * blockDim.x * 2; base < n4; base += (uint64_t)gridDim.x * blockDim.x * 2) {
+        uint4 v[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const uint64_t i = base + (uint64_t)u * blockDim.x + threadIdx.x;
+            v[u] = i < n4 ? __ldg(mine + i) : make_uint4(BM25_ABSENT, BM25_ABSENT, BM25_ABSENT, BM25_ABSENT);
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const uint64_t i = base + (uint64_t)u * blockDim.x + threadIdx.x;
+            const uint32_t w[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                if (w[e] == BM25_ABSENT) continue;
+                const uint32_t img = bm25_desc_image(w[e]);
+                const uint32_t doc = (uint32_t)(i * 4 + e);
+                if (img < thr || (img == thr && doc <= doc_thr)) {
+                    const uint32_t pos = atomicAdd(&c->appended, 1u);
+                    if (pos < key_cap) out[pos] = ((uint64_t)img << 32) | doc;
+                }
+            }
         }
     }
 }
@@ -166,7 +232,7 @@ bm25_compact_kernel(const uint32_t* __restrict__ acc, uint64_t n_docs, Bm25Cut* 
 // the exact score bits come back from the accumulator (the image folds -0.0 into +0.0)
 __global__ void __launch_bounds__(SORT_THREADS)
 bm25_topk_kernel(const uint64_t* __restrict__ keys, uint32_t key_cap, const Bm25Cut* __restrict__ cut,
-                 const uint32_t* __restrict__ acc, uint64_t n_docs, uint32_t limit, uint64_t* __restrict__ doc_out,
+                 const uint32_t* __restrict__ acc, uint64_t acc_stride, uint32_t limit, uint64_t* __restrict__ doc_out,
                  float* __restrict__ score_out) {
     extern __shared__ __align__(16) uint64_t skeys[];
     const uint32_t q = blockIdx.x;
@@ -179,7 +245,7 @@ bm25_topk_kernel(const uint64_t* __restrict__ keys, uint32_t key_cap, const Bm25
         if (t < m) {
             const uint32_t doc = (uint32_t)skeys[t];
             doc_out[(size_t)q * limit + t] = doc;
-            score_out[(size_t)q * limit + t] = __uint_as_float(acc[(size_t)q * n_docs + doc]);
+            score_out[(size_t)q * limit + t] = __uint_as_float(acc[(size_t)q * acc_stride + doc]);
         } else {
             doc_out[(size_t)q * limit + t] = UINT64_MAX;
             score_out[(size_t)q * limit + t] = -INFINITY;

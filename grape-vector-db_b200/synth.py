@@ -140,14 +140,13 @@ def sparse_corpus(n_docs: int, vocab: int = 100_000, tokens_per_doc: int = 32, s
     counts = np.diff(np.append(flat_first, t.size))
     e_term, e_doc = t.ravel()[flat_first], doc.ravel()[flat_first]
     e_tf = counts.astype(np.float32) / np.float32(tokens_per_doc)
-    doc_len = np.zeros(n_docs, dtype=np.float32)
-    # sequential f32 sum per document, in ascending term order (at most tokens_per_doc terms)
+    # document_length = sum of the document's tfs: multiples of 1/tokens_per_doc with every partial sum
+    # <= 1, exact in f32 in any order when tokens_per_doc is a power of two
+    assert tokens_per_doc & (tokens_per_doc - 1) == 0, "tokens_per_doc must be a power of two (exact f32 sums)"
     start = np.flatnonzero(np.r_[True, e_doc[1:] != e_doc[:-1]])
-    rank = np.arange(e_doc.size) - np.repeat(start, np.diff(np.append(start, e_doc.size)))
-    for r in range(int(rank.max()) + 1 if rank.size else 0):
-        m = rank == r
-        doc_len[e_doc[m]] = doc_len[e_doc[m]] + e_tf[m]
-    order = np.lexsort((e_doc, e_term))
+    doc_len = np.zeros(n_docs, dtype=np.float32)
+    doc_len[e_doc[start]] = np.add.reduceat(e_tf, start)
+    order = np.argsort(e_term.astype(np.uint64) << np.uint64(32) | e_doc.astype(np.uint64), kind="stable")
     post_doc, post_tf = e_doc[order], e_tf[order]
     post_off = np.zeros(vocab + 1, dtype=np.uint64)
     np.cumsum(np.bincount(e_term, minlength=vocab), out=post_off[1:])

@@ -96,7 +96,8 @@ def test_rrf_known_values(gv):
     d1 = one / np.float32(61) + one / np.float32(62)
     d2 = one / np.float32(62) + one / np.float32(61)
     assert ids[0, :2].tolist() == [1, 2] and sc[0, 0] == d1 and sc[0, 1] == d2
-    assert ids[0, 2:].tolist() == [3, 4] and sc[0, 2] == sc[0, 3] == one / np.float32(63)   # tie: first appearance
+    assert ids[0, 2:4].tolist() == [3, 4] and sc[0, 2] == sc[0, 3] == one / np.float32(63)   # tie: first appearance
+    assert np.all(ids[0, 4:] == gv.NO_ID)
 
 
 def test_rrf_matches_oracle(gv):
