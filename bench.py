@@ -355,9 +355,71 @@ def run_ours(args, rank, world, local_rank):
     for s in range(K):
         e2e_step(s % NB)
     torch.cuda.synchronize(); barrier()
-    e2e_s = maxr(time.perf_counter() - t0)
+    e2e_serial_s = maxr(time.perf_counter() - t0)
+
+    # The same K steps issued the way a serving process issues them: copies of one step overlap the search
+    # of another.  N = 1: two caller threads inside gvdb_search_batch (the entry point is re-entrant — the
+    # reference serves searches from many runtime workers under a read guard); N > 1 (one batch per rank):
+    # double-buffered pinned H2D on a copy stream, answers D2H into pinned buffers, one host wait per step.
+    if world == 1:
+        import concurrent.futures as cf
+        pool = cf.ThreadPoolExecutor(2)
+
+        def worker(t):
+            for s in range(t, K, 2):
+                index.search_batch(q_pin[s % NB].numpy(), k, R)
+        list(pool.map(worker, range(2)))                      # warm the second workspace
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        list(pool.map(worker, range(2)))
+        torch.cuda.synchronize()
+        e2e_s = time.perf_counter() - t0
+        pool.shutdown()
+        e2e_mode = "2 concurrent callers of gvdb_search_batch"
+    elif replicated:
+        copy_st = torch.cuda.Stream(dev)
+        cur = torch.cuda.current_stream(dev)
+        qd_buf = [torch.empty((Bq, dim), dtype=torch.float32, device=dev) for _ in range(2)]
+        pin_i = [torch.empty((Bq, k), dtype=torch.int64).pin_memory() for _ in range(2)]
+        pin_s = [torch.empty((Bq, k), dtype=torch.float32).pin_memory() for _ in range(2)]
+        ev_in = [torch.cuda.Event() for _ in range(2)]
+        ev_out = [torch.cuda.Event() for _ in range(2)]
+
+        def h2d(s_):
+            with torch.cuda.stream(copy_st):
+                copy_st.wait_event(ev_out[s_ % 2])             # the buffer's previous search has finished
+                qd_buf[s_ % 2].copy_(q_pin[s_ % NB], non_blocking=True)
+                ev_in[s_ % 2].record(copy_st)
+
+        def run(steps):
+            for e in ev_out:
+                e.record(cur)
+            h2d(0)
+            for s_ in range(steps):
+                if s_ + 1 < steps:
+                    h2d(s_ + 1)
+                cur.wait_event(ev_in[s_ % 2])
+                searcher.search_batch_device(qd_buf[s_ % 2], k, R, ids_out, sc_out)
+                pin_i[s_ % 2].copy_(ids_out, non_blocking=True)
+                pin_s[s_ % 2].copy_(sc_out, non_blocking=True)
+                ev_out[s_ % 2].record(cur)
+                if s_ > 0:
+                    ev_out[(s_ - 1) % 2].synchronize()          # the host has step s-1's answers
+            torch.cuda.synchronize()
+        run(max(2, W))
+        barrier(); torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        run(K)
+        barrier()
+        e2e_s = maxr(time.perf_counter() - t0)
+        e2e_mode = "double-buffered pinned H2D on a copy stream + pinned D2H, one host wait per step"
+    else:
+        e2e_s, e2e_mode = e2e_serial_s, "one step at a time"
+    if e2e_serial_s < e2e_s:
+        e2e_s, e2e_mode = e2e_serial_s, "one step at a time"
     e2e = {"value": B * K / e2e_s, "unit": UNIT, "h2d_bytes_per_step": B * dim * 4,
            "d2h_bytes_per_step": B * k * 12, "ms_per_step": 1e3 * e2e_s / K,
+           "issue": e2e_mode, "one_step_at_a_time_value": B * K / e2e_serial_s,
            "api": "gvdb_search_batch (host pointers, pinned)" if world == 1 else
                   ("per rank: pinned H2D of its own batch + gvdb_search_batch_device (candidate rows read from "
                    "peer HBM over NVLink) + D2H of its answers (bytes are whole-job totals)") if peer else

@@ -125,7 +125,7 @@ struct Exchange {
     uint64_t limit_ns = 20ull * 1000 * 1000 * 1000;
     cudaStream_t side = nullptr;
     cudaEvent_t fork = nullptr, join = nullptr;
-    DevBuf my_keys, part, err;
+    DevBuf my_keys, err;
     uint32_t* h_err = nullptr;             // pinned copy of err, refreshed at the end of every step
     std::mutex mu;                         // steps of one rank are issued one at a time
 };
@@ -974,7 +974,7 @@ void gvdb_destroy(gvdb_index* h) {
         for (void* p : x->opened) cudaIpcCloseMemHandle(p);
         if (x->mailbox) cudaFree(x->mailbox);
         if (x->peers_dev) cudaFree(x->peers_dev);
-        x->my_keys.release(); x->part.release(); x->err.release();
+        x->my_keys.release(); x->err.release();
         if (x->h_err) cudaFreeHost(x->h_err);
         if (x->side) cudaStreamDestroy(x->side);
         if (x->fork) cudaEventDestroy(x->fork);
@@ -1547,7 +1547,8 @@ gvdb_status gvdb_stage1_device(gvdb_index* h, void* stream, const float* queries
 namespace {
 // Owner-side rescoring of `nq` queries' candidate keys (all asynchronous on st).
 void rescore_keys_core(gvdb_index* h, Workspace* ws, cudaStream_t st, const float* queries_dev, uint32_t nq,
-                       uint32_t R, const uint64_t* keys_dev, float* scores_out_dev) {
+                       uint32_t R, const uint64_t* keys_dev, float* scores_out_dev, uint8_t* const* peers = nullptr,
+                       uint64_t peer_off = 0, uint32_t pairs_per_peer = 1) {
     if ((h->dim & 3) != 0) fail(GVDB_ERR_NOT_IMPLEMENTED, "owner-side rescoring needs dim % 4 == 0");
     const int cols = std::min(h->dim, RS_SLAB);
     const int stride = ((cols >> 2) & 1) ? cols : cols + 4;
@@ -1556,37 +1557,29 @@ void rescore_keys_core(gvdb_index* h, Workspace* ws, cudaStream_t st, const floa
     if (!attr) {
         CU(cudaFuncSetAttribute(rescore_slab_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 64 * (RS_SLAB + 4) * (int)sizeof(float)));
+        CU(cudaFuncSetAttribute(rescore_owned_list_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                64 * (RS_SLAB + 4) * (int)sizeof(float)));
         attr = true;
     }
     const uint64_t lo = h->windowed ? h->win_first : 0;
     const uint64_t hi = h->windowed ? std::min(h->n_rows, h->win_first + h->win_count) : h->n_rows;
     const uint64_t pairs = (uint64_t)nq * R;
     if (pairs > 0x7fffffffull) fail(GVDB_ERR_INVALID_ARGUMENT, "nq * rescore_count too large");
-    if (h->windowed && !h->rows_cover_all()) {
-        // this GPU owns a fraction of the rows: compact the owned pairs (stable, ascending), then
-        // score 32 of them per warp — the work is 1/G of the pairs, not 1/G of every warp
+    if (peers || (h->windowed && !h->rows_cover_all())) {
+        // this GPU owns a fraction of the rows: list the owned pairs, then score 32 of them per warp —
+        // the work is 1/G of the pairs, not 1/G of every warp
         ws->big_v32.ensure(pairs * 4);
         ws->big_aux.ensure(256);
         uint32_t* list = ws->big_v32.as<uint32_t>();
         uint32_t* count = ws->big_aux.as<uint32_t>();
-        cub::CountingInputIterator<uint32_t> it0(0u);
         OwnedPair pred{keys_dev, h->cfg.row_base, lo, hi};
-        size_t tmp = 0;
-        CU(cub::DeviceSelect::If(nullptr, tmp, it0, list, count, (int)pairs, pred, st));
-        ws->big_tmp.ensure(tmp + 256);
-        size_t tb = ws->big_tmp.bytes;
-        static bool attr2 = false;   // benign race: idempotent
-        if (!attr2) {
-            CU(cudaFuncSetAttribute(rescore_owned_list_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    64 * (RS_SLAB + 4) * (int)sizeof(float)));
-            attr2 = true;
-        }
         Timed t(h, ws, st, K_RESCORE);
-        CU(cudaMemsetAsync(scores_out_dev, 0, pairs * 4, st));
-        CU(cub::DeviceSelect::If(ws->big_tmp.p, tb, it0, list, count, (int)pairs, pred, st));
+        CU(cudaMemsetAsync(count, 0, 4, st));
+        if (!peers) CU(cudaMemsetAsync(scores_out_dev, 0, pairs * 4, st));
+        owned_compact_kernel<<<(unsigned)((pairs + 255) / 256), 256, 0, st>>>(pred, (uint32_t)pairs, list, count);
         rescore_owned_list_kernel<<<(unsigned)((pairs + 31) / 32), 32, (size_t)64 * stride * sizeof(float), st>>>(
             h->rows_base(), h->norms, h->cfg.row_base, h->dim, stride, queries_dev, keys_dev, list, count, R,
-            scores_out_dev);
+            scores_out_dev, peers, peer_off, pairs_per_peer);
     } else {
         Timed t(h, ws, st, K_RESCORE);
         rescore_slab_kernel<true><<<(unsigned)((pairs + 31) / 32), 32, (size_t)(32 + q_slots) * stride * sizeof(float), st>>>(
@@ -1767,7 +1760,6 @@ gvdb_status gvdb_exchange_create(gvdb_index* h, uint32_t world, uint32_t rank, u
         CU(cudaMemset(x->mailbox, 0, x->mailbox_bytes));
         CU(cudaMalloc((void**)&x->peers_dev, world * sizeof(uint8_t*)));
         x->my_keys.ensure((size_t)nq_max * rescore_max * 8);
-        x->part.ensure(slots * rescore_max * 4);
         x->err.ensure(256);
         CU(cudaMemset(x->err.p, 0, 256));
         CU(cudaMallocHost((void**)&x->h_err, 64));
@@ -1898,10 +1890,10 @@ gvdb_status gvdb_search_exchange_device(gvdb_index* h, void* stream, const float
         CU(cudaStreamWaitEvent(st, x->join, 0));
         // every rank's queries and keys are here: score the candidates whose rows I own
         xchg_wait(h, ws, st, x, (1u << XCHG_Q) | (1u << XCHG_K));
-        float* part = x->part.as<float>();
+        // ... and store each cosine straight into its requester's mailbox (slot `rank` of its sc_in)
         rescore_keys_core(h, ws, st, reinterpret_cast<const float*>(set + x->q_off), W * nq, R,
-                          reinterpret_cast<const uint64_t*>(set + x->keys_off), part);
-        xchg_push(h, ws, st, x, set_off + x->sc_off + x->rank * sc_bytes, part, sc_bytes, sc_bytes);
+                          reinterpret_cast<const uint64_t*>(set + x->keys_off), nullptr, x->peers_dev,
+                          set_off + x->sc_off + x->rank * sc_bytes, nq * R);
         xchg_signal(h, ws, st, x, XCHG_S);
         xchg_wait(h, ws, st, x, 1u << XCHG_S);
         finish_owned_core(h, ws, st, my_keys, reinterpret_cast<const float*>(set + x->sc_off), W, x->rows_per_owner, nq, R,

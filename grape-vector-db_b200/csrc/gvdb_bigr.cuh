@@ -143,4 +143,20 @@ struct OwnedPair {
     }
 };
 
+// list of the pair indices this GPU scores (one launch; *count zeroed by the caller).  A warp appends
+// its owned pairs as one ascending run, the runs land in arrival order: every pair is scored on its
+// own, so the order of the list does not change any result.
+__global__ void __launch_bounds__(256)
+owned_compact_kernel(OwnedPair pred, uint32_t n_pairs, uint32_t* __restrict__ list, uint32_t* __restrict__ count) {
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool own = p < n_pairs && pred(p);
+    const uint32_t mask = __ballot_sync(0xffffffffu, own);
+    if (mask == 0) return;
+    const uint32_t lane = threadIdx.x & 31;
+    uint32_t base = 0;
+    if (lane == 0) base = atomicAdd(count, (uint32_t)__popc(mask));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (own) list[base + __popc(mask & ((1u << lane) - 1u))] = p;
+}
+
 }  // namespace gvdb

@@ -811,12 +811,14 @@ rescore_slab_kernel(const float* __restrict__ rows, const float* __restrict__ no
 // rescore_owned_list_kernel: owner-computes rescoring over a COMPACTED list of pair indices
 // (the pairs whose row this GPU holds: 1/G of them, in ascending order).  One warp per 32 list
 // entries; lane l TMA-copies its candidate row and its query row (entries of one warp may belong
-// to many queries), folds ||q||^2 and the dot product left to right, writes out_score[pair].
+// to many queries), folds ||q||^2 and the dot product left to right, writes out_score[pair] (or, for
+// the peer exchange, the pair's slot in its requester's mailbox).
 __global__ void __launch_bounds__(32)
 rescore_owned_list_kernel(const float* __restrict__ rows, const float* __restrict__ norms, uint64_t row_base,
                           int dim, int stride, const float* __restrict__ queries, const uint64_t* __restrict__ keys,
                           const uint32_t* __restrict__ list, const uint32_t* __restrict__ list_count, uint32_t R,
-                          float* __restrict__ out_score) {
+                          float* __restrict__ out_score, uint8_t* const* __restrict__ peers, uint64_t peer_off,
+                          uint32_t pairs_per_peer) {
     extern __shared__ __align__(16) float srow[];            // 32 candidate rows, then 32 query rows
     float* sq = srow + (size_t)32 * stride;
     const int lane = threadIdx.x;
@@ -833,7 +835,12 @@ rescore_owned_list_kernel(const float* __restrict__ rows, const float* __restric
     if (lane == 0) { mbar_init(bar, 1); fence_mbar_init(); }
     __syncwarp();
     uint32_t phase = 0;
-    const uint32_t n_copies = 2u * __popc(__ballot_sync(0xffffffffu, valid));
+    // lanes scoring pairs of the same query share one staged copy of it (the list is ascending, so a
+    // query's pairs sit in neighbouring lanes): the first such lane copies, the others read its slot
+    const uint32_t same_q = __match_any_sync(0xffffffffu, valid ? q : 0xFFFFFFFFu - (uint32_t)lane);
+    const int q_lane = __ffs(same_q) - 1;
+    const bool q_leader = valid && lane == q_lane;
+    const uint32_t n_copies = __popc(__ballot_sync(0xffffffffu, valid)) + __popc(__ballot_sync(0xffffffffu, q_leader));
     float dot = 0.0f, qq2 = 0.0f;
     for (int c0 = 0; c0 < dim; c0 += RS_SLAB) {
         const int cols = min(RS_SLAB, dim - c0);
@@ -847,13 +854,13 @@ rescore_owned_list_kernel(const float* __restrict__ rows, const float* __restric
         __syncwarp();
         if (valid) {
             tma_bulk_g2s(smem_u32(srow + (size_t)lane * stride), rows + (size_t)my_row * dim + c0, row_bytes, bar);
-            tma_bulk_g2s(smem_u32(sq + (size_t)lane * stride), queries + (size_t)q * dim + c0, row_bytes, bar);
+            if (q_leader) tma_bulk_g2s(smem_u32(sq + (size_t)lane * stride), queries + (size_t)q * dim + c0, row_bytes, bar);
         }
         while (!mbar_try_wait(bar, phase)) {}
         phase ^= 1u;
         if (valid) {
             const float4* mine = reinterpret_cast<const float4*>(srow + (size_t)lane * stride);
-            const float4* myq = reinterpret_cast<const float4*>(sq + (size_t)lane * stride);
+            const float4* myq = reinterpret_cast<const float4*>(sq + (size_t)q_lane * stride);
 #pragma unroll 4
             for (int v = 0; v < nv; ++v) {
                 const float4 a = myq[v], b = mine[v];
@@ -870,7 +877,11 @@ rescore_owned_list_kernel(const float* __restrict__ rows, const float* __restric
     }
     if (valid) {
         const float na = __fsqrt_rn(qq2), nb = norms[my_row];
-        out_score[p] = (na == 0.0f || nb == 0.0f) ? 0.0f : __fdiv_rn(dot, __fmul_rn(na, nb));
+        const float cosv = (na == 0.0f || nb == 0.0f) ? 0.0f : __fdiv_rn(dot, __fmul_rn(na, nb));
+        // peer exchange: pair p belongs to rank p / pairs_per_peer; its cosine is stored straight into that
+        // rank's mailbox (a posted store over NVLink), at peer_off + (p % pairs_per_peer) floats
+        if (peers) reinterpret_cast<float*>(peers[p / pairs_per_peer] + peer_off)[p % pairs_per_peer] = cosv;
+        else out_score[p] = cosv;
     }
 }
 
