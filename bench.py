@@ -178,7 +178,10 @@ def run_reference(args, rank, world):
 
 def workload_config(args, world):
     B = args.batch * world
-    return {"workload": f"configs[1]: {args.rows}x{args.dim} binary-quantized scan + fp32 cosine rerank, "
+    which = ("configs[1]" if (args.rows, args.dim) == (1_000_000, 768) else
+             "configs[2]" if (args.rows, args.dim) == (10_000_000, 1536) else
+             "configs[4]" if (args.rows, args.dim) == (100_000_000, 768) else "custom")
+    return {"workload": f"{which}: {args.rows}x{args.dim} binary-quantized scan + fp32 cosine rerank, "
                         f"batch {args.batch} per GPU, top-{args.k}, oversample {args.oversample}x (R={args.k * args.oversample})",
             "rows": args.rows, "dim": args.dim, "batch": args.batch, "global_batch": B, "k": args.k,
             "rescore_count": args.k * args.oversample, "dataset": "lowrank L=16 integer-exact, seed 42",

@@ -77,6 +77,15 @@ extern "C" {
                                            rescore_count: u32, n_slices: u32, records_dev: *mut c_void) -> i32;
     pub fn gvdb_merge_shards_device(h: *mut gvdb_index, stream: *mut c_void, n_shards: u32, records_dev: *const c_void,
                                     nq: u32, rescore_count: u32, k: u32, ids_out_dev: *mut u64, scores_out_dev: *mut f32) -> i32;
+    // peer exchange: codes replicated, rows sharded, queries partitioned; no collective library in the data path
+    pub fn gvdb_exchange_create(h: *mut gvdb_index, world: u32, rank: u32, rows_per_owner: u64, nq_max: u32, rescore_max: u32) -> i32;
+    pub fn gvdb_exchange_export_ipc(h: *mut gvdb_index, handle_out: *mut u8) -> i32;
+    pub fn gvdb_exchange_attach_ipc(h: *mut gvdb_index, handles: *const u8) -> i32;
+    pub fn gvdb_exchange_mailbox_ptr(h: *const gvdb_index) -> *mut c_void;
+    pub fn gvdb_exchange_attach_ptr(h: *mut gvdb_index, mailboxes: *const *mut c_void) -> i32;
+    pub fn gvdb_search_exchange_device(h: *mut gvdb_index, stream: *mut c_void, queries_dev: *const f32, nq: u32, k: u32,
+                                       rescore_count: u32, ids_out_dev: *mut u64, scores_out_dev: *mut f32) -> i32;
+    pub fn gvdb_exchange_status(h: *mut gvdb_index, timed_out_kinds: *mut u32) -> i32;
     // sparse side of the hybrid search (SparseIndex::search_bm25, reference src/sparse.rs:153-222)
     pub fn gvdb_sparse_create(device: i32, k1: f32, b: f32, out: *mut *mut gvdb_sparse) -> i32;
     pub fn gvdb_sparse_destroy(s: *mut gvdb_sparse);
@@ -85,6 +94,17 @@ extern "C" {
     pub fn gvdb_sparse_average_document_length(s: *const gvdb_sparse) -> f32;
     pub fn gvdb_sparse_search_bm25_batch(s: *mut gvdb_sparse, nq: u32, q_off: *const u64, q_terms: *const u32,
                                          q_tfs: *const f32, limit: u32, doc_out: *mut u64, score_out: *mut f32) -> i32;
+    pub fn gvdb_sparse_search_bm25_batch_device(s: *mut gvdb_sparse, stream: *mut c_void, nq: u32, q_off: *const u64,
+                                                q_terms: *const u32, q_tfs: *const f32, limit: u32,
+                                                doc_out_dev: *mut u64, score_out_dev: *mut f32) -> i32;
+    pub fn gvdb_sparse_launches(s: *const gvdb_sparse) -> u64;
+    // HybridSearchEngine::rrf_fusion (reference src/hybrid.rs:422-488) for a batch of requests
+    pub fn gvdb_rrf_fusion_batch(device: i32, dense: *const u64, n_dense: u32, sparse: *const u64, n_sparse: u32,
+                                 text: *const u64, n_text: u32, nq: u32, k: f32, limit: u32,
+                                 ids_out: *mut u64, scores_out: *mut f32) -> i32;
+    pub fn gvdb_rrf_fusion_batch_device(device: i32, stream: *mut c_void, dense_dev: *const u64, n_dense: u32,
+                                        sparse_dev: *const u64, n_sparse: u32, text_dev: *const u64, n_text: u32,
+                                        nq: u32, k: f32, limit: u32, ids_out_dev: *mut u64, scores_out_dev: *mut f32) -> i32;
 }
 
 /// Owned handle; `Send + Sync` because the C ABI's search entry points are re-entrant and the
