@@ -541,9 +541,21 @@ void search_core(gvdb_index* h, Workspace* ws, cudaStream_t st, const float* que
         // Optimistic single pass: one tensor-core launch over everything after the first segment,
         // thresholded at the m-th smallest distance of the first segment (expected survivors per
         // query m * rows_left / rows_seen <= cap / 4); verified on the device, rerun if refuted.
-        const uint32_t opt_m = (allow_optimistic && use_tc && h->opt_m > 0 && h->opt_m <= R &&
-                                (uint64_t)h->opt_m * (ntiles - seg0_tiles) <= (uint64_t)(cap / 4) * seg0_tiles)
-                                   ? h->opt_m : 0u;
+        // m grows with R: the guess holds iff at least R rows lie below the m-th smallest distance of the
+        // first segment, which fails with probability P(Poisson(R * rows_seen / rows) >= m) per query;
+        // the smallest m >= GVDB_OPT_M keeping that under 1e-6 is used (m = 5 for R = 40 on 1M rows)
+        uint32_t opt_m = 0;
+        if (allow_optimistic && use_tc && h->opt_m > 0) {
+            const double x = (double)R * seg0_tiles / (double)ntiles;
+            double term = std::exp(-x), below = 0.0;            // below = P(Poisson(x) < m)
+            uint32_t m = 0;
+            for (; m < 256; ++m) {
+                if (m >= h->opt_m && 1.0 - below <= 1e-6) break;
+                below += term;
+                term *= x / (double)(m + 1);
+            }
+            if (m < 256 && m <= R && (uint64_t)m * (ntiles - seg0_tiles) <= (uint64_t)(cap / 4) * seg0_tiles) opt_m = m;
+        }
         if (opt_m && used_optimistic) *used_optimistic = true;
         if (use_tc) tc_prepare_queries(h, ws, st, nqt, nq_pad);
         uint32_t lo = 0;
