@@ -85,6 +85,9 @@ SYMBOLS = {
     "gvdb_attach_peer_rows_ipc": (_i32, [_vp, _u32, _u64, _u32, _vp]),
     "gvdb_rows_device_ptr": (_vp, [_vp]),
     "gvdb_attach_peer_rows_ptr": (_i32, [_vp, _u32, _u64, _u32, _vp]),
+    "gvdb_search_batch_filtered": (_i32, [_vp, _vp, _vp, _u32, _u32, _u32, _vp, _vp]),
+    "gvdb_search_batch_filtered_device": (_i32, [_vp, _vp, _vp, _vp, _u32, _u32, _u32, _vp, _vp]),
+    "gvdb_flat_search_batch_filtered": (_i32, [_vp, _vp, _vp, _u32, _u32, _vp, _vp]),
     "gvdb_exchange_create": (_i32, [_vp, _u32, _u32, _u64, _u32, _u32]),
     "gvdb_exchange_export_ipc": (_i32, [_vp, _vp]),
     "gvdb_exchange_attach_ipc": (_i32, [_vp, _vp]),

@@ -93,12 +93,14 @@ struct Workspace {
     DevBuf tc_recs, list_counts;     // tcgen05 path: warp-private survivor records
     DevBuf big_keys, big_keys2, big_aux, big_k32, big_v32, big_tmp;   // large-R path (gvdb_bigr.cuh)
     uint32_t* h_flag = nullptr;      // pinned
+    const uint32_t* live_eff = nullptr;   // per-call row filter ANDed with the tombstone bitmap (filtered searches)
+    DevBuf filt, allow_in;
     void* h_res = nullptr;           // pinned staging for the host-pointer entry point's results
     size_t h_res_bytes = 0;
     ~Workspace() {
         for (DevBuf* b : {&qpack, &qnorm, &cnt, &flag, &buf, &rec_ham, &rec_ids, &rec_score, &q_in,
                           &ids_out, &sc_out, &codes_tmp, &misc, &qexp, &qpop, &qbias, &tc_recs, &list_counts,
-                          &big_keys, &big_keys2, &big_aux, &big_k32, &big_v32, &big_tmp}) b->release();
+                          &big_keys, &big_keys2, &big_aux, &big_k32, &big_v32, &big_tmp, &filt, &allow_in}) b->release();
         if (h_flag) cudaFreeHost(h_flag);
         if (h_res) cudaFreeHost(h_res);
         for (cudaEvent_t e : ev_pool) cudaEventDestroy(e);
@@ -257,6 +259,9 @@ struct WsLease {
 
 size_t tiles_for(uint64_t rows) { return (size_t)((rows + 31) / 32); }
 
+// the row bitmap the scans consult: tombstones, ANDed with the call's filter when there is one
+inline const uint32_t* live_of(const gvdb_index* h, const Workspace* ws) { return ws->live_eff ? ws->live_eff : h->live; }
+
 void grow(gvdb_index* h, uint64_t need_rows) {
     if (need_rows <= h->cap_rows) return;
     uint64_t new_cap = std::max<uint64_t>(need_rows, h->cap_rows + h->cap_rows / 2);
@@ -414,7 +419,7 @@ void launch_tc_scan(gvdb_index* h, Workspace* ws, cudaStream_t st, uint32_t tile
                                     (int)(tc_qblocks(N) * tc_qblock_bytes(N))));                        \
             attr = true;                                                                             \
         }                                                                                            \
-        tc_scan_kernel<N, MODE><<<grid, TC_THREADS, smem, st>>>(h->codes, h->live, tile_lo, tile_hi, qexp, qpop, qbias, \
+        tc_scan_kernel<N, MODE><<<grid, TC_THREADS, smem, st>>>(h->codes, live_of(h, ws), tile_lo, tile_hi, qexp, qpop, qbias, \
                                                                nq, nq_pad, sp.qslices, sp.rslices, sp.qb_item, recs, rec_cap, lc,  \
                                                                overflow, dist_out, dist_stride, h->n_rows, 0);          \
         break;                                                                                       \
@@ -571,7 +576,7 @@ void search_core(gvdb_index* h, Workspace* ws, cudaStream_t st, const float* que
                 const int qg = pick_qgroup(h, hi - lo, nqt);
                 dim3 grid = scan_grid(h, hi - lo, nqt, qg);
                 Timed t(h, ws, st, K_SCAN, seg_rows * h->nchunk * 16.0 * grid.y, seg_rows * nqt);
-                launch_scan<0>(h->nchunk, h->scan_variant, st, grid, (size_t)qg * h->qs * 4, h->codes, h->live, lo, hi,
+                launch_scan<0>(h->nchunk, h->scan_variant, st, grid, (size_t)qg * h->qs * 4, h->codes, live_of(h, ws), lo, hi,
                                ws->qpack.as<uint32_t>(), (int)nqt, qg, ws->cnt.as<uint32_t>(),
                                ws->buf.as<uint64_t>(), cap, ws->flag.as<uint32_t>(), nullptr, 0, h->n_rows);
             }
@@ -718,7 +723,7 @@ void search_big_r(gvdb_index* h, Workspace* ws, cudaStream_t st, const float* q_
         {
             const int qg = pick_qgroup(h, ntiles, m);
             dim3 grid = scan_grid(h, ntiles, m, qg);
-            launch_scan<1>(h->nchunk, -1, st, grid, (size_t)qg * h->qs * 4, h->codes, h->live, 0, ntiles,
+            launch_scan<1>(h->nchunk, -1, st, grid, (size_t)qg * h->qs * 4, h->codes, live_of(h, ws), 0, ntiles,
                            ws->qpack.as<uint32_t>(), (int)m, qg, nullptr, nullptr, 0, nullptr, ws->misc.as<uint32_t>(), N, N);
         }
         h->launches.fetch_add(2, std::memory_order_relaxed);
@@ -726,14 +731,14 @@ void search_big_r(gvdb_index* h, Workspace* ws, cudaStream_t st, const float* q_
             const uint32_t* dist = ws->misc.as<uint32_t>() + (size_t)qi * N;
             const uint32_t gq = q0 + qi;
             CU(cudaMemsetAsync(ws->big_aux.p, 0, ws->big_aux.bytes, st));
-            dist_hist_kernel<<<hist_grid, 256, nbins * 4, st>>>(dist, h->live, N, nbins, hist);
+            dist_hist_kernel<<<hist_grid, 256, nbins * 4, st>>>(dist, live_of(h, ws), N, nbins, hist);
             cut_kernel<<<1, 32, 0, st>>>(hist, nbins, R, cut);
             CU(cudaGetLastError());
             BigRCut hc;
             CU(cudaMemcpyAsync(&hc, cut, sizeof(hc), cudaMemcpyDeviceToHost, st));
             CU(cudaStreamSynchronize(st));
             if (hc.r_eff > 0) {
-                cut_compact_kernel<<<hist_grid, 256, 0, st>>>(dist, h->live, N, cut, ws->big_keys.as<uint64_t>());
+                cut_compact_kernel<<<hist_grid, 256, 0, st>>>(dist, live_of(h, ws), N, cut, ws->big_keys.as<uint64_t>());
                 size_t tb = ws->big_tmp.bytes;
                 CU(cub::DeviceRadixSort::SortKeys(ws->big_tmp.p, tb, ws->big_keys.as<uint64_t>(), ws->big_keys2.as<uint64_t>(),
                                                   (int64_t)hc.m, 0, key_bits, st));
@@ -846,12 +851,12 @@ void flat_device(gvdb_index* h, Workspace* ws, cudaStream_t st, const float* q_d
                 Timed t(h, ws, st, K_FLAT);
                 if (sim)
                     flat_scan_kernel<true><<<grid, FLAT_THREADS, 0, st>>>(
-                        h->rows_base(), h->norms, h->live, lo, hi, h->dim, qd, ws->qnorm.as<float>(), nqt,
+                        h->rows_base(), h->norms, live_of(h, ws), lo, hi, h->dim, qd, ws->qnorm.as<float>(), nqt,
                         ws->misc.as<uint32_t>(), ws->cnt.as<uint32_t>(), ws->buf.as<uint64_t>(), cap,
                         ws->flag.as<uint32_t>(), sim_threshold, use_threshold ? 1 : 0);
                 else
                     flat_scan_kernel<false><<<grid, FLAT_THREADS, 0, st>>>(
-                        h->rows_base(), h->norms, h->live, lo, hi, h->dim, qd, ws->qnorm.as<float>(), nqt,
+                        h->rows_base(), h->norms, live_of(h, ws), lo, hi, h->dim, qd, ws->qnorm.as<float>(), nqt,
                         ws->misc.as<uint32_t>(), ws->cnt.as<uint32_t>(), ws->buf.as<uint64_t>(), cap,
                         ws->flag.as<uint32_t>(), 0.f, 0);
             }
@@ -1416,6 +1421,91 @@ gvdb_status gvdb_flat_search_batch(gvdb_index* h, const float* queries, uint32_t
         ws->ids_out.ensure((size_t)nq * std::max(k, 1u) * 8);
         ws->sc_out.ensure((size_t)nq * std::max(k, 1u) * 4);
         CU(cudaMemcpyAsync(ws->q_in.p, queries, (size_t)nq * h->dim * 4, cudaMemcpyHostToDevice, st));
+        flat_device(h, ws, st, ws->q_in.as<float>(), nq, k, ws->ids_out.as<uint64_t>(), ws->sc_out.as<float>());
+        CU(cudaMemcpyAsync(ids_out, ws->ids_out.p, (size_t)nq * k * 8, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(dist_out, ws->sc_out.p, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+    });
+}
+
+// ---- filtered search: a per-call allow-list ANDed with the tombstones ------------------------------------
+namespace {
+// Sets the workspace's effective row bitmap for the lifetime of the scope.  The allow-list covers the
+// stored rows: bit (r % 32) of word r / 32 = 1 when local row r may be returned (the layout of the
+// tombstone bitmap); ceil(rows / 32) words.
+struct FilterScope {
+    Workspace* ws;
+    FilterScope(gvdb_index* h, Workspace* ws_, cudaStream_t st, const uint32_t* allow_dev) : ws(ws_) {
+        const size_t words = tiles_for(h->n_rows);
+        ws->filt.ensure(std::max<size_t>(4, tiles_for(h->cap_rows) * 4));
+        if (words) {
+            and_bitmap_kernel<<<(unsigned)((words + 255) / 256), 256, 0, st>>>(h->live, allow_dev, words, ws->filt.as<uint32_t>());
+            CU(cudaGetLastError());
+        }
+        ws->live_eff = ws->filt.as<uint32_t>();
+    }
+    ~FilterScope() { ws->live_eff = nullptr; }
+};
+}  // namespace
+
+gvdb_status gvdb_search_batch_filtered_device(gvdb_index* h, void* stream, const float* queries_dev,
+                                              const uint32_t* allow_bits_dev, uint32_t nq, uint32_t k,
+                                              uint32_t rescore_count, uint64_t* ids_out_dev, float* scores_out_dev) {
+    return guarded([&] {
+        need(h, "index");
+        if (nq == 0) return;
+        need(queries_dev, "queries"); need(allow_bits_dev, "allow_bits"); need(ids_out_dev, "ids_out"); need(scores_out_dev, "scores_out");
+        DeviceGuard dg(h->cfg.device);
+        WsLease lease(h, (cudaStream_t)stream, true);
+        FilterScope fs(h, lease.ws, lease.stream, allow_bits_dev);
+        search_device(h, lease.ws, lease.stream, queries_dev, nq, k, rescore_count, ids_out_dev, scores_out_dev, nullptr, nullptr);
+    });
+}
+
+gvdb_status gvdb_search_batch_filtered(gvdb_index* h, const float* queries, const uint32_t* allow_bits, uint32_t nq,
+                                       uint32_t k, uint32_t rescore_count, uint64_t* ids_out, float* scores_out) {
+    return guarded([&] {
+        need(h, "index");
+        if (nq == 0) return;
+        need(queries, "queries"); need(allow_bits, "allow_bits"); need(ids_out, "ids_out"); need(scores_out, "scores_out");
+        DeviceGuard dg(h->cfg.device);
+        WsLease lease(h, nullptr, false);
+        Workspace* ws = lease.ws;
+        cudaStream_t st = lease.stream;
+        const size_t words = tiles_for(h->n_rows);
+        ws->q_in.ensure((size_t)nq * h->dim * 4);
+        ws->ids_out.ensure((size_t)nq * std::max(k, 1u) * 8);
+        ws->sc_out.ensure((size_t)nq * std::max(k, 1u) * 4);
+        ws->allow_in.ensure(std::max<size_t>(4, words * 4));
+        CU(cudaMemcpyAsync(ws->q_in.p, queries, (size_t)nq * h->dim * 4, cudaMemcpyHostToDevice, st));
+        if (words) CU(cudaMemcpyAsync(ws->allow_in.p, allow_bits, words * 4, cudaMemcpyHostToDevice, st));
+        FilterScope fs(h, ws, st, ws->allow_in.as<uint32_t>());
+        search_device(h, ws, st, ws->q_in.as<float>(), nq, k, rescore_count, ws->ids_out.as<uint64_t>(), ws->sc_out.as<float>(),
+                      nullptr, nullptr);
+        CU(cudaMemcpyAsync(ids_out, ws->ids_out.p, (size_t)nq * k * 8, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(scores_out, ws->sc_out.p, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+    });
+}
+
+gvdb_status gvdb_flat_search_batch_filtered(gvdb_index* h, const float* queries, const uint32_t* allow_bits, uint32_t nq,
+                                            uint32_t k, uint64_t* ids_out, float* dist_out) {
+    return guarded([&] {
+        need(h, "index");
+        if (nq == 0) return;
+        need(queries, "queries"); need(allow_bits, "allow_bits"); need(ids_out, "ids_out"); need(dist_out, "dist_out");
+        DeviceGuard dg(h->cfg.device);
+        WsLease lease(h, nullptr, false);
+        Workspace* ws = lease.ws;
+        cudaStream_t st = lease.stream;
+        const size_t words = tiles_for(h->n_rows);
+        ws->q_in.ensure((size_t)nq * h->dim * 4);
+        ws->ids_out.ensure((size_t)nq * std::max(k, 1u) * 8);
+        ws->sc_out.ensure((size_t)nq * std::max(k, 1u) * 4);
+        ws->allow_in.ensure(std::max<size_t>(4, words * 4));
+        CU(cudaMemcpyAsync(ws->q_in.p, queries, (size_t)nq * h->dim * 4, cudaMemcpyHostToDevice, st));
+        if (words) CU(cudaMemcpyAsync(ws->allow_in.p, allow_bits, words * 4, cudaMemcpyHostToDevice, st));
+        FilterScope fs(h, ws, st, ws->allow_in.as<uint32_t>());
         flat_device(h, ws, st, ws->q_in.as<float>(), nq, k, ws->ids_out.as<uint64_t>(), ws->sc_out.as<float>());
         CU(cudaMemcpyAsync(ids_out, ws->ids_out.p, (size_t)nq * k * 8, cudaMemcpyDeviceToHost, st));
         CU(cudaMemcpyAsync(dist_out, ws->sc_out.p, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, st));

@@ -885,6 +885,13 @@ rescore_owned_list_kernel(const float* __restrict__ rows, const float* __restric
     }
 }
 
+// filtered searches: the bitmap the scans consult = tombstones AND the call's allow-list
+__global__ void and_bitmap_kernel(const uint32_t* __restrict__ live, const uint32_t* __restrict__ allow, size_t n_words,
+                                  uint32_t* __restrict__ out) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_words) out[i] = live[i] & allow[i];
+}
+
 // stage-1 result as keys hamming << 40 | global row (gvdb_stage1_device)
 __global__ void emit_keys_kernel(const uint64_t* __restrict__ buf, uint32_t cap, const uint32_t* __restrict__ cnt,
                                  uint32_t R, uint32_t nq, uint64_t row_base, uint64_t* __restrict__ keys_out) {

@@ -363,6 +363,53 @@ class GpuIndex:
         arr = (C.c_void_p * len(ptrs))(*ptrs)
         self._ok(self._lib.gvdb_attach_peer_rows_ptr(self._h, len(ptrs), rows_per_owner, my_owner, arr))
 
+    # -- filtered search -------------------------------------------------------------------------
+    def _allow_bits(self, allowed) -> np.ndarray:
+        """allowed: boolean mask over the stored rows, or an array of allowed local row numbers."""
+        n = self.rows
+        a = np.asarray(allowed)
+        if a.dtype != np.bool_:
+            m = np.zeros(n, dtype=bool)
+            m[a.astype(np.int64)] = True
+            a = m
+        assert a.shape == (n,)
+        pad = np.zeros(((n + 31) // 32) * 32, dtype=bool)
+        pad[:n] = a
+        return np.packbits(pad.reshape(-1, 32), axis=1, bitorder="little").view(np.uint32).ravel().copy()
+
+    def search_batch_filtered(self, queries, allowed, k: int, rescore_count: int):
+        """Two-stage search over the allowed live rows only (gvdb_search_batch_filtered)."""
+        q = _np(queries, np.float32)
+        nq = q.shape[0]
+        bits = self._allow_bits(allowed)
+        ids = np.full((nq, k), NO_ID, dtype=np.uint64)
+        sc = np.full((nq, k), -np.inf, dtype=np.float32)
+        self._ok(self._lib.gvdb_search_batch_filtered(self._h, _ptr(q), _ptr(bits), nq, k, rescore_count, _ptr(ids), _ptr(sc)))
+        return ids, sc
+
+    def flat_search_batch_filtered(self, queries, allowed, k: int):
+        q = _np(queries, np.float32)
+        nq = q.shape[0]
+        bits = self._allow_bits(allowed)
+        ids = np.full((nq, k), NO_ID, dtype=np.uint64)
+        ds = np.full((nq, k), np.inf, dtype=np.float32)
+        self._ok(self._lib.gvdb_flat_search_batch_filtered(self._h, _ptr(q), _ptr(bits), nq, k, _ptr(ids), _ptr(ds)))
+        return ids, ds
+
+    def search_batch_filtered_device(self, queries_t, allow_bits_t, k: int, rescore_count: int):
+        import torch
+        assert queries_t.is_cuda and queries_t.dtype == torch.float32 and queries_t.is_contiguous()
+        assert allow_bits_t.is_cuda and allow_bits_t.dtype == torch.int32 and allow_bits_t.is_contiguous()
+        nq = queries_t.shape[0]
+        dev = queries_t.device
+        ids = torch.empty((nq, k), dtype=torch.int64, device=dev)
+        sc = torch.empty((nq, k), dtype=torch.float32, device=dev)
+        st = torch.cuda.current_stream(dev).cuda_stream
+        self._ok(self._lib.gvdb_search_batch_filtered_device(
+            self._h, C.c_void_p(st), C.c_void_p(queries_t.data_ptr()), C.c_void_p(allow_bits_t.data_ptr()), nq, k,
+            rescore_count, C.c_void_p(ids.data_ptr()), C.c_void_p(sc.data_ptr())))
+        return ids, sc
+
     # -- peer exchange (no collective library in the data path) ---------------------------------
     def exchange_create(self, world: int, rank: int, rows_per_owner: int, nq_max: int, rescore_max: int):
         self._ok(self._lib.gvdb_exchange_create(self._h, world, rank, rows_per_owner, nq_max, rescore_max))

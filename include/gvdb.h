@@ -255,6 +255,22 @@ GVDB_API const void* gvdb_rows_device_ptr(const gvdb_index* h);
 GVDB_API gvdb_status gvdb_attach_peer_rows_ptr(gvdb_index* h, uint32_t n_owners, uint64_t rows_per_owner,
                                                uint32_t my_owner, const void* const* row_ptrs /* n_owners */);
 
+/* ---- filtered search --------------------------------------------------
+ * The row bitmap the scans consult — today the tombstones of remove_vector (src/index.rs:629,642-650)
+ * — ANDed with a per-call allow-list, e.g. the ids FilterEngine::execute_filter returns
+ * (src/filtering.rs:374) mapped to row numbers.  allow_bits: ceil(rows / 32) words, bit (r % 32) of
+ * word r / 32 set when local row r may be returned.  The answer is the search over the sub-corpus of
+ * allowed live rows (same order, same scores); rescore_count counts allowed rows. */
+GVDB_API gvdb_status gvdb_search_batch_filtered(gvdb_index* h, const float* queries, const uint32_t* allow_bits,
+                                                uint32_t nq, uint32_t k, uint32_t rescore_count,
+                                                uint64_t* ids_out, float* scores_out);
+GVDB_API gvdb_status gvdb_search_batch_filtered_device(gvdb_index* h, void* stream, const float* queries_dev,
+                                                       const uint32_t* allow_bits_dev, uint32_t nq, uint32_t k,
+                                                       uint32_t rescore_count, uint64_t* ids_out_dev,
+                                                       float* scores_out_dev);
+GVDB_API gvdb_status gvdb_flat_search_batch_filtered(gvdb_index* h, const float* queries, const uint32_t* allow_bits,
+                                                     uint32_t nq, uint32_t k, uint64_t* ids_out, float* dist_out);
+
 /* ---- peer exchange: the same layout with NO collective library in the data path ----------------
  * Codes replicated, f32 rows sharded, queries partitioned (as gvdb_stage1_device /
  * gvdb_rescore_keys_device / gvdb_finish_owned_device), but the three exchanges of a step (queries

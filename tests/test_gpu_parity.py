@@ -622,3 +622,47 @@ def test_peer_exchange_missing_peer_times_out(gv, monkeypatch):
         ranks[0].search_exchange_device(q, k, R)
     for ix in ranks:
         ix.close()
+
+
+def test_filtered_search_equals_search_over_the_allowed_rows(gv):
+    """gvdb_search_batch_filtered / gvdb_flat_search_batch_filtered: the answer is the reference's search
+    over the sub-corpus of allowed, live rows (ids mapped back), for dense and very sparse allow-lists,
+    few queries (CUDA-core scan) and many (tensor-core scan), and together with tombstones."""
+    import torch
+    from grape_vector_db_b200 import synth
+    n, dim, R, k = 60_000, 768, 40, 10
+    rows = synth.lowrank_rows(0, n, dim)
+    qs = synth.lowrank_queries(0, 96, dim)
+    rng = np.random.default_rng(3)
+    with gv.GpuIndex(dim) as idx:
+        idx.add(rows)
+        dead = rng.choice(n, size=500, replace=False)
+        for r in dead[:50]:
+            idx.remove(int(r))
+        live = np.ones(n, dtype=bool)
+        live[dead[:50]] = False
+        for frac, nq in ((0.5, 96), (0.5, 5), (0.01, 96), (0.0005, 70), (1.0, 80)):
+            allow = rng.random(n) < frac
+            sub = np.flatnonzero(allow & live)
+            ids, sc = idx.search_batch_filtered(qs[:nq], allow, k, R)
+            oi, os_ = oracle.multi_stage_search_batch(qs[:nq], rows[sub], R, k, nthreads=8)
+            r = min(k, len(sub))
+            mapped = np.where(oi[:, :r] == gv.NO_ID, gv.NO_ID, sub[np.minimum(oi[:, :r], len(sub) - 1).astype(np.int64)].astype(np.uint64))
+            assert np.array_equal(ids[:, :r], mapped), (frac, nq)
+            assert np.array_equal(_bits(sc[:, :r]), _bits(os_[:, :r])), (frac, nq)
+            assert np.all(ids[:, r:] == gv.NO_ID)
+            # the same filter through the device-pointer entry point, allowed rows given as row numbers
+            bits = torch.from_numpy(idx._allow_bits(np.flatnonzero(allow)).view(np.int32)).cuda()
+            di, ds = idx.search_batch_filtered_device(torch.from_numpy(qs[:nq]).cuda(), bits, k, R)
+            assert np.array_equal(di.cpu().numpy().astype(np.uint64), ids) and np.array_equal(_bits(ds.cpu().numpy()), _bits(sc))
+        allow = rng.random(n) < 0.05
+        sub = np.flatnonzero(allow & live)
+        fi, fd = idx.flat_search_batch_filtered(qs[:7], allow, k)
+        ofi, ofd = oracle.flat_search_batch(qs[:7], rows[sub], k)
+        assert np.array_equal(fi, sub[ofi.astype(np.int64)].astype(np.uint64)) and np.array_equal(_bits(fd), _bits(ofd))
+        # an empty allow-list answers nothing; the unfiltered search is untouched afterwards
+        ids, sc = idx.search_batch_filtered(qs[:4], np.zeros(n, dtype=bool), k, R)
+        assert np.all(ids == gv.NO_ID)
+        ids, sc = idx.search_batch(qs[:4], k, R)
+        oi, os_ = oracle.multi_stage_search_batch(qs[:4], rows[np.flatnonzero(live)], R, k)
+        assert np.array_equal(ids, np.flatnonzero(live)[oi.astype(np.int64)].astype(np.uint64))
