@@ -642,6 +642,10 @@ __device__ __forceinline__ float4 ldg_f4(const float* p) { return __ldg(reinterp
 
 // queries -> qpack (code words, then [tau = TAU_ALL, 0, 0, 0]) + sequential-fold norms.
 // Same outputs as ingest_kernel<true>; one thread per query, 32 queries per CTA.
+// 32 float4 in flight per thread: a 768-d query is six global-memory round trips (was 24 with
+// DIRECT_DEPTH = 8; the kernel is latency-bound, 1024 threads on the whole GPU)
+constexpr int QPREP_DEPTH = 32;
+
 __global__ void __launch_bounds__(32)
 query_prep_direct_kernel(const float* __restrict__ x, uint32_t n, int dim, float thr, int nchunk,
                          float* __restrict__ norms, uint32_t* __restrict__ qpack, int qs) {
@@ -652,13 +656,13 @@ query_prep_direct_kernel(const float* __restrict__ x, uint32_t n, int dim, float
     float ss = 0.0f;
     uint32_t word = 0;
     uint32_t* out = qpack + (size_t)i * qs;
-    for (int v0 = 0; v0 < nv; v0 += DIRECT_DEPTH) {
-        float4 buf[DIRECT_DEPTH];
+    for (int v0 = 0; v0 < nv; v0 += QPREP_DEPTH) {
+        float4 buf[QPREP_DEPTH];
 #pragma unroll
-        for (int u = 0; u < DIRECT_DEPTH; ++u)
+        for (int u = 0; u < QPREP_DEPTH; ++u)
             buf[u] = v0 + u < nv ? ldg_f4(row + 4 * (v0 + u)) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-        for (int u = 0; u < DIRECT_DEPTH; ++u) {
+        for (int u = 0; u < QPREP_DEPTH; ++u) {
             if (v0 + u < nv) {
                 const float e4[4] = {buf[u].x, buf[u].y, buf[u].z, buf[u].w};
                 const int j0 = 4 * (v0 + u);

@@ -159,3 +159,30 @@ def test_hybrid_search_matches_oracle_composition(gv):
         ids, _ = hy.search_batch(qs[:8], None, limit)
         od, _ = oracle.multi_stage_search_batch(qs[:8], rows, want * 4, want, nthreads=8)
         assert np.array_equal(ids, od[:, :limit])
+
+
+def test_golden_hybrid_fixture(gv):
+    """The CUDA path against the committed fixture tests/golden/kat_hybrid.json (BM25 lists, fused lists,
+    a filtered two-stage search)."""
+    import json
+    import os
+    from grape_vector_db_b200 import synth
+    g = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "kat_hybrid.json")))["hybrid"]
+    n, dim, nq, limit = g["n"], g["dim"], g["nq"], g["limit"]
+    rows, qs = synth.lowrank_rows(0, n, dim), synth.lowrank_queries(0, nq, dim)
+    post = synth.sparse_corpus(n, vocab=g["vocab"])
+    sq = synth.sparse_queries(nq, vocab=g["vocab"])
+    with gv.GpuIndex(dim) as dense, gv.GpuSparseIndex() as sparse:
+        dense.add(rows)
+        sparse.build(*post)
+        assert int(sparse.average_document_length.view(np.uint32)) == g["avg_len_bits"]
+        docs, sc = sparse.search_bm25_batch(sq, 2 * limit)
+        for q in range(nq):
+            r = len(g["bm25"][q]["docs"])
+            assert docs[q, :r].tolist() == g["bm25"][q]["docs"] and _bits(sc[q, :r]).tolist() == g["bm25"][q]["score_bits"]
+        ids, fs = gv.HybridSearcher(dense, sparse, rrf_k=g["rrf_k"], oversample=g["oversample"]).search_batch(qs, sq, limit)
+        for q in range(nq):
+            assert ids[q].tolist() == g["fused"][q]["ids"] and _bits(fs[q]).tolist() == g["fused"][q]["score_bits"]
+        f = g["filtered"]
+        fi, fsc = dense.search_batch_filtered(qs, (np.arange(n) % 7) < 2, f["k"], f["R"])
+        assert fi.tolist() == f["ids"] and _bits(fsc).tolist() == f["score_bits"]

@@ -225,3 +225,24 @@ def test_sparse_synthetic_corpus_shape():
     q = synth.sparse_queries(8, vocab=500)
     docs, sc = oracle.bm25_search(q[0][0], q[0][1], post_off, post_doc, post_tf, doc_len, 20)
     assert len(docs) == 20 and np.all(sc[:-1] >= sc[1:])
+
+
+def test_golden_hybrid_fixture_roundtrip():
+    """tests/golden/kat_hybrid.json freezes the oracle's BM25 lists, fused lists and a filtered search on
+    seeded inputs (same generator script); the GPU tests check the CUDA path against the same file."""
+    from grape_vector_db_b200 import synth
+    g = json.load(open(os.path.join(GOLDEN, "kat_hybrid.json")))["hybrid"]
+    n, dim, nq, limit = g["n"], g["dim"], g["nq"], g["limit"]
+    rows, qs = synth.lowrank_rows(0, n, dim), synth.lowrank_queries(0, nq, dim)
+    post = synth.sparse_corpus(n, vocab=g["vocab"])
+    sq = synth.sparse_queries(nq, vocab=g["vocab"])
+    assert int(post[0][-1]) == g["postings"]
+    assert int(np.float32(oracle.bm25_avg_len(post[0], post[1], post[3])).view(np.uint32)) == g["avg_len_bits"]
+    want = 2 * limit
+    dense_ids, _ = oracle.multi_stage_search_batch(qs, rows, want * g["oversample"], want)
+    for q in range(nq):
+        d, s = oracle.bm25_search(sq[q][0], sq[q][1], *post, want)
+        assert d.tolist() == g["bm25"][q]["docs"] and s.view(np.uint32).tolist() == g["bm25"][q]["score_bits"]
+        fi, fs = oracle.rrf_fusion(dense_ids[q], d, [], g["rrf_k"])
+        assert fi[:limit].tolist() == g["fused"][q]["ids"]
+        assert fs[:limit].view(np.uint32).tolist() == g["fused"][q]["score_bits"]
