@@ -2014,7 +2014,7 @@ struct gvdb_sparse {
     uint32_t n_terms = 0;
     std::vector<uint64_t> h_post_off;          // host copy: document frequencies for the idf
     DevBuf post_off, post_doc, post_tf, doc_len;
-    DevBuf acc, hist, cut, keys, q_off, q_terms, q_tfs, q_idf, doc_out, score_out;
+    DevBuf acc, hist, cut, keys, tie_counts, q_off, q_terms, q_tfs, q_idf, doc_out, score_out;
     cudaStream_t stream = nullptr;
     int sm_count = 148;
     uint64_t launches = 0;                     // kernels launched by the searches of this handle
@@ -2046,7 +2046,7 @@ void gvdb_sparse_destroy(gvdb_sparse* s) {
     cudaGetDevice(&prev);
     cudaSetDevice(s->device);
     cudaDeviceSynchronize();
-    for (DevBuf* b : {&s->post_off, &s->post_doc, &s->post_tf, &s->doc_len, &s->acc, &s->hist, &s->cut, &s->keys,
+    for (DevBuf* b : {&s->post_off, &s->post_doc, &s->post_tf, &s->doc_len, &s->acc, &s->hist, &s->cut, &s->keys, &s->tie_counts,
                       &s->q_off, &s->q_terms, &s->q_tfs, &s->q_idf, &s->doc_out, &s->score_out}) b->release();
     if (s->stream) cudaStreamDestroy(s->stream);
     delete s;
@@ -2118,6 +2118,7 @@ void bm25_core(gvdb_sparse* s, cudaStream_t st, uint32_t nq, const uint64_t* q_o
     s->hist.ensure((size_t)QC * BM25_LEVEL_BINS * 4);
     s->cut.ensure((size_t)QC * sizeof(Bm25Cut));
     s->keys.ensure((size_t)QC * key_cap * 8);
+    s->tie_counts.ensure((size_t)QC * s->sm_count * 2 * 4);
     s->q_off.ensure((size_t)(nq + 1) * 8);
     s->q_terms.ensure(std::max<size_t>(4, nt * 4));
     s->q_tfs.ensure(std::max<size_t>(4, nt * 4));
@@ -2139,12 +2140,20 @@ void bm25_core(gvdb_sparse* s, cudaStream_t st, uint32_t nq, const uint64_t* q_o
                 s->post_off.as<uint64_t>(), s->post_doc.as<uint32_t>(), s->post_tf.as<float>(), s->doc_len.as<float>(),
                 s->n_terms, s->q_off.as<uint64_t>(), s->q_terms.as<uint32_t>(), s->q_tfs.as<float>(),
                 s->q_idf.as<float>(), q0, (int)rank, s->k1, s->b, s->avg_len, stride, s->acc.as<uint32_t>());
-        for (int level = 0; level < 6; ++level) {
+        for (int level = 0; level < 3; ++level) {
             CU(cudaMemsetAsync(s->hist.p, 0, (size_t)m * BM25_LEVEL_BINS * 4, st));
-            bm25_hist_kernel<<<dim3(gx, m), 256, 0, st>>>(s->acc.as<uint32_t>(), stride, limit,
-                                                         s->hist.as<uint32_t>(), s->cut.as<Bm25Cut>(), level);
-            bm25_cut_kernel<<<m, 256, 0, st>>>(s->hist.as<uint32_t>(), limit, s->cut.as<Bm25Cut>(), level);
+            uint32_t* hist = s->hist.as<uint32_t>();
+            Bm25Cut* cut = s->cut.as<Bm25Cut>();
+            if (level == 0) bm25_hist_kernel<0><<<dim3(gx, m), 256, 0, st>>>(s->acc.as<uint32_t>(), stride, hist, cut);
+            else if (level == 1) bm25_hist_kernel<1><<<dim3(gx, m), 256, 0, st>>>(s->acc.as<uint32_t>(), stride, hist, cut);
+            else bm25_hist_kernel<2><<<dim3(gx, m), 256, 0, st>>>(s->acc.as<uint32_t>(), stride, hist, cut);
+            bm25_cut_kernel<<<m, 256, 0, st>>>(hist, limit, cut, level);
         }
+        // surplus ties at the cut score: the lowest document numbers are kept (both kernels return at once otherwise)
+        bm25_tiecount_kernel<<<dim3(gx, m), 256, 0, st>>>(s->acc.as<uint32_t>(), stride, limit, s->cut.as<Bm25Cut>(),
+                                                         s->tie_counts.as<uint32_t>());
+        bm25_tiecut_kernel<<<m, 256, 0, st>>>(s->acc.as<uint32_t>(), stride, limit, s->cut.as<Bm25Cut>(),
+                                             s->tie_counts.as<uint32_t>(), gx);
         bm25_compact_kernel<<<dim3(gx, m), 256, 0, st>>>(s->acc.as<uint32_t>(), stride, s->cut.as<Bm25Cut>(),
                                                         s->keys.as<uint64_t>(), key_cap);
         bm25_topk_kernel<<<m, SORT_THREADS, SORT_N * 8, st>>>(s->keys.as<uint64_t>(), key_cap, s->cut.as<Bm25Cut>(),
@@ -2152,7 +2161,7 @@ void bm25_core(gvdb_sparse* s, cudaStream_t st, uint32_t nq, const uint64_t* q_o
                                                              doc_out_dev + (size_t)q0 * limit, score_out_dev + (size_t)q0 * limit);
         CU(cudaGetLastError());
     }
-    s->launches += (uint64_t)((nq + QC - 1) / QC) * (max_terms + 14);
+    s->launches += (uint64_t)((nq + QC - 1) / QC) * (max_terms + 10);
 }
 }  // namespace
 

@@ -11,10 +11,9 @@
 // document appears at most once in a term's postings, so one launch per term rank touches every
 // accumulator at most once: additions happen in query-term order, like the reference's loop.
 //   bm25_accumulate_kernel   one term rank of every query of the chunk
-//   bm25_hist_kernel         radix-select levels (11 + 11 + 10 bits): the descending score image, then
-//                            the document number among the documents tying at the cut
-//   bm25_cut_kernel          the exact 32-bit image of the limit-th best score and the last tying
-//                            document kept
+//   bm25_hist_kernel         radix-select levels (11 + 11 + 10 bits) over the descending score image
+//   bm25_cut_kernel          the exact 32-bit image of the limit-th best score
+//   bm25_tiecount / tiecut   when more documents tie at that score than fit: the last document kept
 //   bm25_compact_kernel      keys (descending image << 32 | doc) inside the cut: exactly
 //                            min(limit, touched documents), however many documents tie
 //   bm25_topk_kernel         block bitonic sort of those keys, first `limit`
@@ -85,31 +84,32 @@ bm25_accumulate_kernel(const uint64_t* __restrict__ post_off, const uint32_t* __
 // descending image of a present score; a NaN score cannot be produced by finite inputs
 __device__ __forceinline__ uint32_t bm25_desc_image(uint32_t bits) { return ~f32_asc_key(__uint_as_float(bits)); }
 
-// Radix select of the exact cut without sorting the accumulator.  A 32-bit key is fixed 11 + 11 + 10
-// bits at a time (BM25_LEVEL_BINS = 2048 bins per level): levels 0-2 over the descending score image
-// give thr32 (the want-th best score), above and m; when more documents tie at thr32 than fit
-// (m > want), levels 3-5 do the same over the DOCUMENT NUMBER of the tying documents and give doc_thr.
-// Exactly want = min(limit, present) documents then pass "image < thr32 or (image == thr32 and
-// doc <= doc_thr)", however many share the cut score (BM25 over tf = count/len data ties by the million).
+// Exact cut without sorting the accumulator.  The descending score image is fixed 11 + 11 + 10 bits at a
+// time (radix select, BM25_LEVEL_BINS = 2048 bins per level, three uint4 passes over the accumulators):
+// thr32 = the image of the want-th best score, above = documents strictly better, m = documents at or
+// above it.  When more documents tie at thr32 than fit (m > want), the lowest document numbers win:
+// bm25_tiecount_kernel counts the ties of each CTA's CONTIGUOUS slice of the documents (one more pass),
+// bm25_tiecut_kernel finds the slice holding the last tie kept and walks it for doc_thr.  Exactly
+// want = min(limit, present) documents then pass "image < thr32 or (image == thr32 and doc <= doc_thr)",
+// however many share the cut score (BM25 over tf = count/len data ties by the million).
 // Histograms are per CTA in shared memory, lanes with equal bins are combined first (__match_any_sync):
 // tying scores put millions of documents into one bin, which serialises global atomics.
 constexpr int BM25_LEVEL_BINS = 2048;
-__host__ __device__ __forceinline__ int bm25_level_shift(int level) { return (level % 3) == 0 ? 21 : (level % 3) == 1 ? 10 : 0; }
-__host__ __device__ __forceinline__ int bm25_level_bits(int level) { return (level % 3) == 2 ? 10 : 11; }
+__host__ __device__ __forceinline__ constexpr int bm25_level_shift(int level) { return level == 0 ? 21 : level == 1 ? 10 : 0; }
+__host__ __device__ __forceinline__ constexpr int bm25_level_bits(int level) { return level == 2 ? 10 : 11; }
 
+template <int LEVEL>
 __global__ void __launch_bounds__(256)
-bm25_hist_kernel(const uint32_t* __restrict__ acc, uint64_t acc_stride, uint32_t limit, uint32_t* __restrict__ hist,
-                 Bm25Cut* __restrict__ cut, int level) {
+bm25_hist_kernel(const uint32_t* __restrict__ acc, uint64_t acc_stride, uint32_t* __restrict__ hist,
+                 Bm25Cut* __restrict__ cut) {
     __shared__ uint32_t sh[BM25_LEVEL_BINS];
     const uint4* mine = reinterpret_cast<const uint4*>(acc + (size_t)blockIdx.y * acc_stride);
     uint32_t* h = hist + (size_t)blockIdx.y * BM25_LEVEL_BINS;
-    const Bm25Cut c = cut[blockIdx.y];
-    if (level >= 1 && c.present == 0) return;
-    if (level >= 3 && c.m == min(limit, c.present)) return;          // no surplus ties: every tie is kept
+    const uint32_t prefix = cut[blockIdx.y].prefix;
+    if (LEVEL >= 1 && cut[blockIdx.y].present == 0) return;
     for (int i = threadIdx.x; i < BM25_LEVEL_BINS; i += blockDim.x) sh[i] = 0;
     __syncthreads();
-    const int shift = bm25_level_shift(level), bits = bm25_level_bits(level);
-    const bool first = (level % 3) == 0;
+    constexpr int shift = bm25_level_shift(LEVEL), bits = bm25_level_bits(LEVEL);
     const uint32_t lane = threadIdx.x & 31;
     const uint64_t n4 = acc_stride / 4;
     uint32_t present = 0;
@@ -123,20 +123,14 @@ bm25_hist_kernel(const uint32_t* __restrict__ acc, uint64_t acc_stride, uint32_t
         }
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
-            const uint64_t i = base + (uint64_t)u * blockDim.x + threadIdx.x;
             const uint32_t w[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
                 bool ok = w[e] != BM25_ABSENT;
-                uint32_t key = 0;
-                if (ok) {
-                    const uint32_t img = bm25_desc_image(w[e]);
-                    if (level < 3) key = img;
-                    else { ok = img == c.thr32; key = (uint32_t)(i * 4 + e); }
-                    if (level == 0) ++present;
-                }
-                if (ok && !first) ok = (key >> (shift + bits)) == c.prefix;
-                const uint32_t bin = ok ? (key >> shift) & ((1u << bits) - 1u) : 0xFFFFFFFFu;
+                const uint32_t img = bm25_desc_image(w[e]);
+                if (LEVEL == 0) present += ok;
+                else ok = ok && (img >> (shift + bits)) == prefix;
+                const uint32_t bin = ok ? (img >> shift) & ((1u << bits) - 1u) : 0xFFFFFFFFu;
                 if (__any_sync(0xffffffffu, ok)) {
                     const uint32_t peers = __match_any_sync(0xffffffffu, bin);
                     if (ok && lane == (uint32_t)(__ffs(peers) - 1)) atomicAdd(&sh[bin], (uint32_t)__popc(peers));
@@ -147,20 +141,19 @@ bm25_hist_kernel(const uint32_t* __restrict__ acc, uint64_t acc_stride, uint32_t
     __syncthreads();
     for (int i = threadIdx.x; i < BM25_LEVEL_BINS; i += blockDim.x)
         if (sh[i]) atomicAdd(&h[i], sh[i]);
-    if (level == 0) {
+    if (LEVEL == 0) {
         for (int o = 16; o > 0; o >>= 1) present += __shfl_xor_sync(0xffffffffu, present, o);
         if (lane == 0 && present) atomicAdd(&cut[blockIdx.y].present, present);
     }
 }
 
-// one CTA per query: the bin holding the want-th entry of this level's histogram
+// one CTA per query: the bin holding the want-th entry of this level's histogram (level 0..2)
 __global__ void __launch_bounds__(256)
 bm25_cut_kernel(const uint32_t* __restrict__ hist, uint32_t limit, Bm25Cut* __restrict__ cut, int level) {
     __shared__ uint32_t part[256];
     const uint32_t* h = hist + (size_t)blockIdx.x * BM25_LEVEL_BINS;
     Bm25Cut* c = cut + blockIdx.x;
     const uint32_t want_all = min(limit, c->present);
-    if (level >= 3 && c->m == want_all) { if (threadIdx.x == 0) c->doc_thr = 0xFFFFFFFFu; return; }
     const uint32_t want = level == 0 ? want_all : c->want_left;
     constexpr int PER = BM25_LEVEL_BINS / 256;
     uint32_t sum = 0;
@@ -176,21 +169,107 @@ bm25_cut_kernel(const uint32_t* __restrict__ hist, uint32_t limit, Bm25Cut* __re
             const uint32_t hv = h[t * PER + i];
             if (run + hv >= want) {
                 const uint32_t bin = (uint32_t)(t * PER + i);
-                const uint32_t prefix = (level % 3) == 0 ? bin : (c->prefix << bm25_level_bits(level)) | bin;
+                const uint32_t prefix = level == 0 ? bin : (c->prefix << bm25_level_bits(level)) | bin;
                 c->prefix = prefix;
                 c->want_left = want - run;                     // rank inside the chosen bin
                 if (level == 2) {                              // the image is complete
                     c->thr32 = prefix;
                     c->above = want_all - (want - run);
                     c->m = want_all - (want - run) + hv;
-                    c->want_left = want - run;                 // ties to keep, if they do not all fit
+                    c->doc_thr = 0xFFFFFFFFu;                  // every tie is kept unless bm25_tiecut_kernel says otherwise
                 }
-                if (level == 5) c->doc_thr = prefix;
                 break;
             }
             run += hv;
         }
     }
+}
+
+// surplus ties only (m > want): ties inside CTA x's contiguous slice of query y's accumulators
+__global__ void __launch_bounds__(256)
+bm25_tiecount_kernel(const uint32_t* __restrict__ acc, uint64_t acc_stride, uint32_t limit, const Bm25Cut* __restrict__ cut,
+                     uint32_t* __restrict__ counts) {
+    const Bm25Cut c = cut[blockIdx.y];
+    if (c.m == min(limit, c.present)) return;
+    const uint4* mine = reinterpret_cast<const uint4*>(acc + (size_t)blockIdx.y * acc_stride);
+    const uint64_t n4 = acc_stride / 4, per = (n4 + gridDim.x - 1) / gridDim.x;
+    const uint64_t lo = (uint64_t)blockIdx.x * per, hi = min(n4, lo + per);
+    // the stored bit pattern whose image is thr32 is unique up to -0.0 / +0.0: compare images
+    uint32_t n = 0;
+    for (uint64_t base = lo; base < hi; base += (uint64_t)blockDim.x * 2) {
+        uint4 v[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const uint64_t i = base + (uint64_t)u * blockDim.x + threadIdx.x;
+            v[u] = i < hi ? __ldg(mine + i) : make_uint4(BM25_ABSENT, BM25_ABSENT, BM25_ABSENT, BM25_ABSENT);
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const uint32_t w[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) n += (w[e] != BM25_ABSENT && bm25_desc_image(w[e]) == c.thr32) ? 1u : 0u;
+        }
+    }
+    __shared__ uint32_t warp_n[8];
+    for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(0xffffffffu, n, o);
+    if ((threadIdx.x & 31) == 0) warp_n[threadIdx.x >> 5] = n;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t t = 0;
+        for (int w = 0; w < 8; ++w) t += warp_n[w];
+        counts[(size_t)blockIdx.y * gridDim.x + blockIdx.x] = t;
+    }
+}
+
+// one CTA per query: the slice holding the want_left-th tie (document order), then that document
+__global__ void __launch_bounds__(256)
+bm25_tiecut_kernel(const uint32_t* __restrict__ acc, uint64_t acc_stride, uint32_t limit, Bm25Cut* __restrict__ cut,
+                   const uint32_t* __restrict__ counts, uint32_t n_slices) {
+    Bm25Cut* c = cut + blockIdx.x;
+    const uint32_t thr = c->thr32;
+    if (c->m == min(limit, c->present)) return;                  // doc_thr stays "all ties"
+    __shared__ uint32_t s_slice, s_rank, s_warp[8], s_found;
+    if (threadIdx.x == 0) {
+        uint32_t run = 0, want = c->want_left, b = 0;
+        for (; b + 1 < n_slices; ++b) {
+            const uint32_t t = counts[(size_t)blockIdx.x * n_slices + b];
+            if (run + t >= want) break;
+            run += t;
+        }
+        s_slice = b; s_rank = want - run; s_found = 0xFFFFFFFFu;
+    }
+    __syncthreads();
+    const uint4* mine = reinterpret_cast<const uint4*>(acc + (size_t)blockIdx.x * acc_stride);
+    const uint64_t n4 = acc_stride / 4, per = (n4 + n_slices - 1) / n_slices;
+    const uint64_t lo = (uint64_t)s_slice * per, hi = min(n4, lo + per);
+    uint32_t need = s_rank;                                       // ties still to pass, block-uniform
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (uint64_t base = lo; base < hi; base += blockDim.x) {
+        const uint64_t i = base + threadIdx.x;
+        const uint4 v = i < hi ? __ldg(mine + i) : make_uint4(BM25_ABSENT, BM25_ABSENT, BM25_ABSENT, BM25_ABSENT);
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+        uint32_t tie[4], mine_n = 0;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { tie[e] = (w[e] != BM25_ABSENT && bm25_desc_image(w[e]) == thr) ? 1u : 0u; mine_n += tie[e]; }
+        uint32_t incl = mine_n;                                   // inclusive scan over the CTA, thread order = document order
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if ((int)lane >= o) incl += t; }
+        if (lane == 31) s_warp[wid] = incl;
+        __syncthreads();
+        uint32_t before = 0, total = 0;
+        for (int w8 = 0; w8 < 8; ++w8) { if (w8 < (int)wid) before += s_warp[w8]; total += s_warp[w8]; }
+        const uint32_t excl = before + incl - mine_n;
+        if (mine_n && excl < need && excl + mine_n >= need) {      // the need-th tie is one of my four
+            uint32_t seen = excl;
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+                if (tie[e] && ++seen == need) s_found = (uint32_t)(i * 4 + e);
+        }
+        __syncthreads();
+        if (s_found != 0xFFFFFFFFu || total >= need) break;       // block-uniform
+        need -= total;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && s_found != 0xFFFFFFFFu) c->doc_thr = s_found;
 }
 
 // keys (image << 32 | doc) of the documents inside the cut: exactly min(limit, present) of them
