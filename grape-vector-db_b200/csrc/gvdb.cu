@@ -129,7 +129,18 @@ struct Exchange {
     cudaEvent_t fork = nullptr, join = nullptr;
     DevBuf my_keys, err;
     uint32_t* h_err = nullptr;             // pinned copy of err, refreshed at the end of every step
+    bool broken = false;                   // a step failed on the host after its epoch began: peers are out of step
     std::mutex mu;                         // steps of one rank are issued one at a time
+    ~Exchange() {                          // the device of the owning index is current (gvdb_destroy / create)
+        for (void* p : opened) cudaIpcCloseMemHandle(p);
+        if (mailbox) cudaFree(mailbox);
+        if (peers_dev) cudaFree(peers_dev);
+        my_keys.release(); err.release();
+        if (h_err) cudaFreeHost(h_err);
+        if (side) cudaStreamDestroy(side);
+        if (fork) cudaEventDestroy(fork);
+        if (join) cudaEventDestroy(join);
+    }
 };
 
 struct gvdb_index {
@@ -987,17 +998,7 @@ void gvdb_destroy(gvdb_index* h) {
     cudaDeviceSynchronize();
     for (void* p : h->ipc_opened) cudaIpcCloseMemHandle(p);
     if (h->peer_rows_dev) cudaFree((void*)h->peer_rows_dev);
-    if (Exchange* x = h->xchg) {
-        for (void* p : x->opened) cudaIpcCloseMemHandle(p);
-        if (x->mailbox) cudaFree(x->mailbox);
-        if (x->peers_dev) cudaFree(x->peers_dev);
-        x->my_keys.release(); x->err.release();
-        if (x->h_err) cudaFreeHost(x->h_err);
-        if (x->side) cudaStreamDestroy(x->side);
-        if (x->fork) cudaEventDestroy(x->fork);
-        if (x->join) cudaEventDestroy(x->join);
-        delete x;
-    }
+    delete h->xchg;
     h->pool.clear();
     if (h->rows) cudaFree(h->rows);
     if (h->codes) cudaFree(h->codes);
@@ -1965,12 +1966,16 @@ gvdb_status gvdb_search_exchange_device(gvdb_index* h, void* stream, const float
         if (k > R) fail(GVDB_ERR_INVALID_ARGUMENT, "k must be <= rescore_count");
         if (h->n_live == 0) fail(GVDB_ERR_INDEX_NOT_BUILT, "index is empty");
         std::lock_guard<std::mutex> lk(x->mu);
-        if (x->h_err[0]) fail(GVDB_ERR_INDEX, "an earlier peer-exchange step timed out; the exchange is out of step");
+        if (x->h_err[0] || x->broken)
+            fail(GVDB_ERR_INDEX, "an earlier peer-exchange step timed out or failed; the exchange is out of step");
         DeviceGuard dg(h->cfg.device);
         WsLease lease(h, (cudaStream_t)stream, true);
         Workspace* ws = lease.ws;
         cudaStream_t st = lease.stream;
         x->epoch += 1;
+        // from here on the peers expect this rank's pushes for the epoch: a host-side failure leaves them
+        // waiting (they time out) and this rank out of step, which later calls report at once
+        struct Guard { Exchange* x; bool ok = false; ~Guard() { if (!ok) x->broken = true; } } guard{x};
         uint8_t* set = x->mailbox + (size_t)(x->epoch & 1) * x->set_bytes;
         const uint64_t set_off = (uint64_t)(x->epoch & 1) * x->set_bytes;
         const uint64_t q_bytes = (uint64_t)nq * h->dim * 4, key_bytes = (uint64_t)nq * R * 8, sc_bytes = (uint64_t)nq * R * 4;
@@ -2002,6 +2007,7 @@ gvdb_status gvdb_search_exchange_device(gvdb_index* h, void* stream, const float
                           k, ids_out_dev, scores_out_dev);
         CU(cudaMemcpyAsync(x->h_err, x->err.p, 4, cudaMemcpyDeviceToHost, st));
         CU(cudaGetLastError());
+        guard.ok = true;
         finish_async(h, ws, st);
     });
 }
@@ -2017,6 +2023,8 @@ struct gvdb_sparse {
     DevBuf acc, hist, cut, keys, tie_counts, q_off, q_terms, q_tfs, q_idf, doc_out, score_out;
     cudaStream_t stream = nullptr;
     int sm_count = 148;
+    cudaEvent_t idle = nullptr;                // recorded after the last kernel that touched the scratch buffers
+    bool used = false;
     uint64_t launches = 0;                     // kernels launched by the searches of this handle
     std::mutex mu;                             // one search at a time per handle
 };
@@ -2036,6 +2044,7 @@ gvdb_status gvdb_sparse_create(int32_t device, float k1, float b, gvdb_sparse** 
         CU(cudaGetDeviceProperties(&prop, device));
         s->sm_count = prop.multiProcessorCount;
         CU(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&s->idle, cudaEventDisableTiming));
         *out = s.release();
     });
 }
@@ -2049,6 +2058,7 @@ void gvdb_sparse_destroy(gvdb_sparse* s) {
     for (DevBuf* b : {&s->post_off, &s->post_doc, &s->post_tf, &s->doc_len, &s->acc, &s->hist, &s->cut, &s->keys, &s->tie_counts,
                       &s->q_off, &s->q_terms, &s->q_tfs, &s->q_idf, &s->doc_out, &s->score_out}) b->release();
     if (s->stream) cudaStreamDestroy(s->stream);
+    if (s->idle) cudaEventDestroy(s->idle);
     delete s;
     cudaSetDevice(prev);
 }
@@ -2098,6 +2108,9 @@ namespace {
 void bm25_core(gvdb_sparse* s, cudaStream_t st, uint32_t nq, const uint64_t* q_off, const uint32_t* q_terms,
                const float* q_tfs, uint32_t limit, uint64_t* doc_out_dev, float* score_out_dev) {
     if (limit > (uint32_t)SORT_N) fail(GVDB_ERR_NOT_IMPLEMENTED, "BM25 limit > 4096 is not implemented");
+    // the scratch buffers are shared by every call on this handle: a call on another stream waits for the last one
+    if (s->used) CU(cudaStreamWaitEvent(st, s->idle, 0));
+    struct Done { gvdb_sparse* s; cudaStream_t st; ~Done() { cudaEventRecord(s->idle, st); s->used = true; } } done{s, st};
     const uint64_t nt = q_off[nq];
     if (nt) { need(q_terms, "q_terms"); need(q_tfs, "q_tfs"); }
     // idf on the host (libm logf == Rust's f32::ln); absent terms are dropped (:169)

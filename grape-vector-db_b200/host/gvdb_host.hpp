@@ -289,6 +289,34 @@ public:
         }
         return out;
     }
+    // search restricted to the documents a filter allows — the id list FilterEngine::execute_filter returns
+    // (src/filtering.rs:374).  Unknown ids are ignored; the answer is the search over the allowed live rows.
+    std::vector<std::pair<std::string, float>> search_filtered(const std::vector<float>& query, size_t k,
+                                                               const std::vector<std::string>& allowed_ids) {
+        if (!h_) throw VectorDbError(VectorDbError::IndexNotBuilt, "index not built");
+        if (query.size() != dim_)
+            throw VectorDbError(VectorDbError::DimensionMismatch, "dimension mismatch", dim_, query.size());
+        std::vector<std::pair<std::string, float>> out;
+        if (k == 0) return out;
+        gvdb_stats st{};
+        check(gvdb_get_stats(h_->get(), &st));
+        std::vector<uint32_t> allow((st.rows + 31) / 32, 0u);
+        for (const std::string& id : allowed_ids) {
+            auto it = id_to_index_.find(id);
+            if (it != id_to_index_.end()) allow[it->second >> 5] |= 1u << (it->second & 31);
+        }
+        std::vector<uint64_t> ids(k);
+        std::vector<float> val(k);
+        if (mode_ == Mode::Exact) {
+            check(gvdb_flat_search_batch_filtered(h_->get(), query.data(), allow.data(), 1, (uint32_t)k, ids.data(), val.data()));
+            for (size_t t = 0; t < k && ids[t] != GVDB_NO_ID; ++t) out.emplace_back(index_to_id_.at(ids[t]), val[t]);
+        } else {
+            const uint32_t r = (uint32_t)(k * oversample_);
+            check(gvdb_search_batch_filtered(h_->get(), query.data(), allow.data(), 1, (uint32_t)k, r, ids.data(), val.data()));
+            for (size_t t = 0; t < k && ids[t] != GVDB_NO_ID; ++t) out.emplace_back(index_to_id_.at(ids[t]), 1.0f - val[t]);
+        }
+        return out;
+    }
     bool remove_vector(const std::string& id) override {                                       // :642-650
         auto it = id_to_index_.find(id);
         if (it == id_to_index_.end()) return false;

@@ -83,6 +83,24 @@ static void test_vector_index_trait() {             // trait VectorIndex, src/in
     }
 }
 
+static void test_filtered_search() {                // FilterEngine::execute_filter ids as a pre-filter
+    GpuVectorIndex exact(GpuVectorIndex::Mode::Exact, 4), two_stage(GpuVectorIndex::Mode::TwoStage, 4);
+    for (GpuVectorIndex* idx : {&exact, &two_stage}) {
+        idx->add_vector("a", {1.0f, 0.0f, 0.0f, 0.0f});
+        idx->add_vector("b", {0.9f, 0.1f, 0.0f, 0.0f});
+        idx->add_vector("c", {0.0f, 1.0f, 0.0f, 0.0f});
+        idx->add_vector("d", {0.7f, 0.7f, 0.0f, 0.0f});
+        auto all = idx->search({1.0f, 0.0f, 0.0f, 0.0f}, 2);
+        REQUIRE(all.size() == 2 && all[0].first == "a" && all[1].first == "b");
+        auto some = idx->search_filtered({1.0f, 0.0f, 0.0f, 0.0f}, 2, {"c", "d", "nobody"});
+        REQUIRE(some.size() == 2 && some[0].first == "d" && some[1].first == "c");
+        REQUIRE(idx->search_filtered({1.0f, 0.0f, 0.0f, 0.0f}, 2, {}).empty());
+        REQUIRE(idx->remove_vector("d"));
+        auto left = idx->search_filtered({1.0f, 0.0f, 0.0f, 0.0f}, 2, {"c", "d"});
+        REQUIRE(left.size() == 1 && left[0].first == "c");
+    }
+}
+
 static void test_rrf_fusion() {                     // src/hybrid.rs:991-1025
     std::vector<std::pair<std::string, float>> dense = {{"doc1", 0.9f}, {"doc2", 0.8f}, {"doc3", 0.7f}};
     std::vector<std::pair<std::string, float>> sparse = {{"doc2", 0.95f}, {"doc1", 0.85f}, {"doc4", 0.75f}};
@@ -163,6 +181,7 @@ int main() {
     test_hamming_distance();
     test_multi_stage_search();
     test_vector_index_trait();
+    test_filtered_search();
     test_rrf_fusion();
     test_sparse_bm25();
     test_gpu_sparse_bm25();
