@@ -77,6 +77,14 @@ extern "C" {
                                            rescore_count: u32, n_slices: u32, records_dev: *mut c_void) -> i32;
     pub fn gvdb_merge_shards_device(h: *mut gvdb_index, stream: *mut c_void, n_shards: u32, records_dev: *const c_void,
                                     nq: u32, rescore_count: u32, k: u32, ids_out_dev: *mut u64, scores_out_dev: *mut f32) -> i32;
+    // filtered searches: allow_bits has ceil(rows / 32) words, bit (r % 32) of word r / 32 = row r may be returned
+    pub fn gvdb_search_batch_filtered(h: *mut gvdb_index, queries: *const f32, allow_bits: *const u32, nq: u32, k: u32,
+                                      rescore_count: u32, ids_out: *mut u64, scores_out: *mut f32) -> i32;
+    pub fn gvdb_search_batch_filtered_device(h: *mut gvdb_index, stream: *mut c_void, queries_dev: *const f32,
+                                             allow_bits_dev: *const u32, nq: u32, k: u32, rescore_count: u32,
+                                             ids_out_dev: *mut u64, scores_out_dev: *mut f32) -> i32;
+    pub fn gvdb_flat_search_batch_filtered(h: *mut gvdb_index, queries: *const f32, allow_bits: *const u32, nq: u32, k: u32,
+                                           ids_out: *mut u64, dist_out: *mut f32) -> i32;
     // peer exchange: codes replicated, rows sharded, queries partitioned; no collective library in the data path
     pub fn gvdb_exchange_create(h: *mut gvdb_index, world: u32, rank: u32, rows_per_owner: u64, nq_max: u32, rescore_max: u32) -> i32;
     pub fn gvdb_exchange_export_ipc(h: *mut gvdb_index, handle_out: *mut u8) -> i32;
@@ -237,3 +245,84 @@ mod trait_impl {
 }
 #[cfg(feature = "vector-index")]
 pub use trait_impl::GpuVectorIndex;
+
+/// `BinaryQuantizer` with the reference's signatures (src/quantization.rs:67-241), arithmetic on the GPU.
+/// In the reference's crate this replaces the body of `impl BinaryQuantizer`; `BinaryVector`,
+/// `BinaryQuantizationConfig` and the error type stay the reference's own.
+#[cfg(feature = "vector-index")]
+mod quantizer_shim {
+    use super::*;
+    use grape_vector_db::quantization::{BinaryQuantizationConfig, BinaryVector};
+    use grape_vector_db::types::VectorDbError;
+
+    pub struct BinaryQuantizer { config: BinaryQuantizationConfig, device: i32 }
+
+    fn err(st: i32) -> VectorDbError {
+        match st {
+            3 => VectorDbError::InvalidVectorDimension,
+            4 => VectorDbError::QuantizationError(last_error()),
+            _ => VectorDbError::IndexError(last_error()),
+        }
+    }
+
+    fn create(dim: usize, cfg: &BinaryQuantizationConfig, device: i32, capacity: u64) -> Result<GpuIndex, VectorDbError> {
+        let c = gvdb_config { struct_size: std::mem::size_of::<gvdb_config>() as u32, dim: dim as u32, threshold: cfg.threshold,
+                              rescore_ratio: cfg.rescore_ratio, device, capacity_rows: capacity, ..Default::default() };
+        let mut h = std::ptr::null_mut();
+        let st = unsafe { gvdb_create(&c, &mut h) };
+        if st != 0 { return Err(err(st)); }
+        Ok(GpuIndex { h, dim })
+    }
+
+    impl BinaryQuantizer {
+        pub fn new(config: BinaryQuantizationConfig) -> Self { Self { config, device: 0 } }
+
+        /// :86-122 — bit = value > threshold, Msb0 bytes; the cache of the reference is not needed
+        pub fn quantize(&mut self, vector: &[f32]) -> Result<BinaryVector, VectorDbError> {
+            Ok(self.quantize_batch(&[vector.to_vec()])?.pop().unwrap())
+        }
+
+        /// :125-127 — one GPU call for a batch of equal dimension
+        pub fn quantize_batch(&mut self, vectors: &[Vec<f32>]) -> Result<Vec<BinaryVector>, VectorDbError> {
+            let Some(first) = vectors.first() else { return Ok(Vec::new()) };
+            let dim = first.len();
+            if dim == 0 || vectors.iter().any(|v| v.len() != dim) { return Err(VectorDbError::InvalidVectorDimension); }
+            let ix = create(dim, &self.config, self.device, 0)?;
+            let flat: Vec<f32> = vectors.iter().flatten().copied().collect();
+            let nb = (dim + 7) / 8;
+            let mut codes = vec![0u8; vectors.len() * nb];
+            let st = unsafe { gvdb_quantize(ix.h, flat.as_ptr(), vectors.len() as u64, codes.as_mut_ptr()) };
+            if st != 0 { return Err(err(st)); }
+            // from_bytes sets the bit length to 8 * bytes (:59-62); the dimension is restored here
+            Ok(codes.chunks(nb).map(|c| { let mut b = BinaryVector::from_bytes(c.to_vec()); b.dimension = dim; b }).collect())
+        }
+
+        /// :151-193 — stage 1 over every candidate, R = (n as f32 * rescore_ratio) as usize, exact rescoring of
+        /// the R kept, both stable sorts; returns all R (index, cosine) pairs like the reference
+        pub fn multi_stage_search(&self, _query_binary: &BinaryVector, candidates_binary: &[BinaryVector],
+                                  original_query: &[f32], original_candidates: &[Vec<f32>])
+                                  -> Result<Vec<(usize, f32)>, VectorDbError> {
+            if candidates_binary.len() != original_candidates.len() {
+                return Err(VectorDbError::QuantizationError("Mismatch between binary and original candidate counts".into()));
+            }
+            let n = original_candidates.len();
+            let r = unsafe { gvdb_rescore_count(n as u64, self.config.rescore_ratio) } as usize;
+            if n == 0 || r == 0 { return Ok(Vec::new()); }
+            let ix = create(original_query.len(), &self.config, self.device, n as u64)?;
+            let flat: Vec<f32> = original_candidates.iter().flatten().copied().collect();
+            if flat.len() != n * ix.dim { return Err(VectorDbError::InvalidVectorDimension); }
+            let mut first = 0u64;
+            let st = unsafe { gvdb_add(ix.h, flat.as_ptr(), n as u64, &mut first) };
+            if st != 0 { return Err(err(st)); }
+            let (mut ids, mut sc) = (vec![GVDB_NO_ID; r], vec![0f32; r]);
+            let st = unsafe { gvdb_search_batch(ix.h, original_query.as_ptr(), 1, r as u32, r as u32, ids.as_mut_ptr(),
+                                                sc.as_mut_ptr(), std::ptr::null_mut(), std::ptr::null_mut()) };
+            if st != 0 { return Err(err(st)); }
+            Ok(ids.iter().zip(sc.iter()).take_while(|(i, _)| **i != GVDB_NO_ID).map(|(i, s)| (*i as usize, *s)).collect())
+        }
+
+        pub fn clear_cache(&mut self) {}
+    }
+}
+#[cfg(feature = "vector-index")]
+pub use quantizer_shim::BinaryQuantizer;
