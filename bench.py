@@ -430,6 +430,10 @@ def run_ours(args, rank, world, local_rank):
     e2e = {"value": B * K / e2e_s, "unit": UNIT, "h2d_bytes_per_step": B * dim * 4,
            "d2h_bytes_per_step": B * k * 12, "ms_per_step": 1e3 * e2e_s / K,
            "issue": e2e_mode, "one_step_at_a_time_value": B * K / e2e_serial_s,
+           "l2": ("no explicit flush between end-to-end steps: a step touches %d MB of codes + %d MB of gathered f32 "
+                  "candidate rows + the queries, more than the 126 MB L2; the device-timed `value` flushes L2 before "
+                  "every step and runs one step at a time, so it can sit below this figure"
+                  % ((hi - lo if not replicated else n) * dim // 8 >> 20, Bq * R * dim * 4 >> 20)),
            "api": "gvdb_search_batch (host pointers, pinned)" if world == 1 else
                   ("per rank: pinned H2D of its own batch + gvdb_search_batch_device (candidate rows read from "
                    "peer HBM over NVLink) + D2H of its answers (bytes are whole-job totals)") if peer else
