@@ -24,6 +24,21 @@ def _ptr(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
 
 
+def pack_allow_bits(allowed, n_rows: int) -> np.ndarray:
+    """Allow-list of a filtered search as the uint32 bitmap the C ABI takes: bit (r % 32) of word r / 32 = 1
+    when local row r may be returned (the tombstone bitmap's layout).  `allowed` is a boolean mask over the
+    stored rows or an array of allowed local row numbers."""
+    a = np.asarray(allowed)
+    if a.dtype != np.bool_:
+        m = np.zeros(n_rows, dtype=bool)
+        m[a.astype(np.int64)] = True
+        a = m
+    assert a.shape == (n_rows,)
+    pad = np.zeros(((n_rows + 31) // 32) * 32, dtype=bool)
+    pad[:n_rows] = a
+    return np.packbits(pad.reshape(-1, 32), axis=1, bitorder="little").view(np.uint32).ravel().copy()
+
+
 class GpuIndex:
     """Rows [row_base, row_base + len) of the corpus: 1-bit codes + f32 originals in HBM."""
 
@@ -365,17 +380,7 @@ class GpuIndex:
 
     # -- filtered search -------------------------------------------------------------------------
     def _allow_bits(self, allowed) -> np.ndarray:
-        """allowed: boolean mask over the stored rows, or an array of allowed local row numbers."""
-        n = self.rows
-        a = np.asarray(allowed)
-        if a.dtype != np.bool_:
-            m = np.zeros(n, dtype=bool)
-            m[a.astype(np.int64)] = True
-            a = m
-        assert a.shape == (n,)
-        pad = np.zeros(((n + 31) // 32) * 32, dtype=bool)
-        pad[:n] = a
-        return np.packbits(pad.reshape(-1, 32), axis=1, bitorder="little").view(np.uint32).ravel().copy()
+        return pack_allow_bits(allowed, self.rows)
 
     def search_batch_filtered(self, queries, allowed, k: int, rescore_count: int):
         """Two-stage search over the allowed live rows only (gvdb_search_batch_filtered)."""

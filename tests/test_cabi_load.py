@@ -69,3 +69,27 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".hpp", ".h", ".rs")):
                 src = open(os.path.join(dirpath, f), errors="replace").read()
                 assert "oracle" not in src.lower().replace("test oracle", ""), f"{f} mentions the oracle"
+
+
+def test_sparse_and_fusion_entry_points_refuse_without_gpu(built):
+    """The sparse side and the fusion have no CPU path either."""
+    import numpy as np
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    import grape_vector_db_b200 as gv
+    with pytest.raises(gv.IndexError_, match="no usable CUDA device"):
+        gv.GpuSparseIndex()
+    with pytest.raises(gv.IndexError_, match="no usable CUDA device"):
+        gv.rrf_fusion_batch(np.array([[1, 2, 3]], dtype=np.uint64), np.array([[2, 1, 4]], dtype=np.uint64))
+
+
+def test_allow_bits_packing():
+    """Row r of an allow-list lands in bit (r % 32) of word r / 32 (the tombstone bitmap's layout)."""
+    import numpy as np
+    from grape_vector_db_b200.index import pack_allow_bits
+    assert pack_allow_bits([0, 5, 31, 32, 69], 70).tolist() == [0x80000021, 0x1, 0x20]
+    mask = np.zeros(70, dtype=bool)
+    mask[[0, 5, 31, 32, 69]] = True
+    assert pack_allow_bits(mask, 70).tolist() == [0x80000021, 0x1, 0x20]
+    assert pack_allow_bits([], 0).size == 0
