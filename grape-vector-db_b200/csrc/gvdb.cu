@@ -193,6 +193,18 @@ struct DeviceGuard {
     ~DeviceGuard() { cudaSetDevice(prev); }
 };
 
+// cudaFuncSetAttribute applies to the CURRENT device: one flag bit per device ordinal, so a process that
+// drives several GPUs (one thread each) raises the limit on every one of them.
+template <class F>
+void ensure_dyn_smem(std::atomic<uint64_t>& done, F kernel, int bytes) {
+    int dev = 0;
+    CU(cudaGetDevice(&dev));
+    const uint64_t bit = 1ull << (dev & 63);
+    if (done.load(std::memory_order_acquire) & bit) return;
+    CU(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    done.fetch_or(bit, std::memory_order_release);
+}
+
 // Brackets one kernel launch with events (only when profiling is on) and counts it.
 struct Timed {
     Workspace* ws; cudaStream_t st; bool on; ProfRec rec;
@@ -315,11 +327,8 @@ void launch_scan_t(cudaStream_t st, dim3 grid, size_t smem, const uint4* codes, 
                    uint32_t tile_lo, uint32_t tile_hi, const uint32_t* qpack, int nq, int qgroup,
                    uint32_t* cnt, uint64_t* buf, uint32_t cap, uint32_t* overflow, uint32_t* dist_out,
                    uint64_t dist_stride, uint64_t n_rows) {
-    static bool attr_set = false;   // benign race: idempotent
-    if (!attr_set) {
-        CU(cudaFuncSetAttribute(scan_kernel<NCHUNK, MODE, NCSA, AGG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-        attr_set = true;
-    }
+    static std::atomic<uint64_t> attr_done{0};
+    ensure_dyn_smem(attr_done, scan_kernel<NCHUNK, MODE, NCSA, AGG>, 100 * 1024);
     scan_kernel<NCHUNK, MODE, NCSA, AGG><<<grid, SCAN_THREADS, smem, st>>>(
         codes, live, tile_lo, tile_hi, qpack, nq, qgroup, cnt, buf, cap, overflow, dist_out,
         dist_stride, n_rows);
@@ -424,12 +433,8 @@ void launch_tc_scan(gvdb_index* h, Workspace* ws, cudaStream_t st, uint32_t tile
             seg_rows * (double)nq_pad * (h->nchunk * 128.0 + 64.0));
 #define GVDB_TC_CASE(N)                                                                              \
     case N: {                                                                                        \
-        static bool attr = false;                                                                    \
-        if (!attr) {                                                                                 \
-            CU(cudaFuncSetAttribute(tc_scan_kernel<N, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                    (int)(tc_qblocks(N) * tc_qblock_bytes(N))));                        \
-            attr = true;                                                                             \
-        }                                                                                            \
+        static std::atomic<uint64_t> attr_done{0};                                                   \
+        ensure_dyn_smem(attr_done, tc_scan_kernel<N, MODE>, (int)(tc_qblocks(N) * tc_qblock_bytes(N))); \
         tc_scan_kernel<N, MODE><<<grid, TC_THREADS, smem, st>>>(h->codes, live_of(h, ws), tile_lo, tile_hi, qexp, qpop, qbias, \
                                                                nq, nq_pad, sp.qslices, sp.rslices, sp.qb_item, recs, rec_cap, lc,  \
                                                                overflow, dist_out, dist_stride, h->n_rows, 0);          \
@@ -529,11 +534,8 @@ void search_core(gvdb_index* h, Workspace* ws, cudaStream_t st, const float* que
     const uint32_t nbins = (uint32_t)h->nchunk * 128 + 1;
     const size_t selh_smem = (size_t)r_pow2 * 8 + (size_t)SORT_N * 8 + (size_t)nbins * 4;
     {
-        static bool attr = false;   // benign race: idempotent
-        if (!attr) {
-            CU(cudaFuncSetAttribute(select_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
-            attr = true;
-        }
+        static std::atomic<uint64_t> attr_done{0};
+        ensure_dyn_smem(attr_done, select_hist_kernel, 72 * 1024);
     }
     for (uint32_t qt0 = 0; qt0 < nq; qt0 += QT) {
         const uint32_t nqt = std::min(QT, nq - qt0);
@@ -614,12 +616,8 @@ void search_core(gvdb_index* h, Workspace* ws, cudaStream_t st, const float* que
                 // 32 consecutive pairs touch at most 31/R + 2 consecutive queries
                 const int q_slots = (int)std::min<uint32_t>(32, 31 / R + 2);
                 const size_t smem = (size_t)(32 + q_slots) * stride * sizeof(float);
-                static bool attr = false;   // benign race: idempotent
-                if (!attr) {
-                    CU(cudaFuncSetAttribute(rescore_slab_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            64 * (RS_SLAB + 4) * (int)sizeof(float)));
-                    attr = true;
-                }
+                static std::atomic<uint64_t> attr_done{0};
+                ensure_dyn_smem(attr_done, rescore_slab_kernel<false>, 64 * (RS_SLAB + 4) * (int)sizeof(float));
                 rescore_slab_kernel<false><<<(unsigned)((pairs + 31) / 32), 32, smem, st>>>(
                     h->rows, h->norms, h->cfg.row_base, h->dim, stride, q_slots, queries_dev + (size_t)qt0 * h->dim,
                     ws->qnorm.as<float>(), ws->buf.as<uint64_t>(), cap, ws->cnt.as<uint32_t>(), R, nqt,
@@ -717,12 +715,8 @@ void search_big_r(gvdb_index* h, Workspace* ws, cudaStream_t st, const float* q_
                                       (int64_t)N, 0, key_bits, st));
     CU(cub::DeviceRadixSort::SortPairs(nullptr, tmp_b, k32, k32o, v32, v32o, (int64_t)R, 0, 32, st));
     ws->big_tmp.ensure(std::max(tmp_a, tmp_b) + 256);
-    static bool attr = false;   // benign race: idempotent
-    if (!attr) {
-        CU(cudaFuncSetAttribute(rescore_slab_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                64 * (RS_SLAB + 4) * (int)sizeof(float)));
-        attr = true;
-    }
+    static std::atomic<uint64_t> attr_done{0};
+    ensure_dyn_smem(attr_done, rescore_slab_kernel<false>, 64 * (RS_SLAB + 4) * (int)sizeof(float));
     const int cols = std::min(h->dim, RS_SLAB);
     const int stride = ((cols >> 2) & 1) ? cols : cols + 4;
     const int hist_grid = (int)std::min<uint64_t>((N + 255) / 256, (uint64_t)h->sm_count * 8);
@@ -1656,14 +1650,9 @@ void rescore_keys_core(gvdb_index* h, Workspace* ws, cudaStream_t st, const floa
     const int cols = std::min(h->dim, RS_SLAB);
     const int stride = ((cols >> 2) & 1) ? cols : cols + 4;
     const int q_slots = (int)std::min<uint32_t>(32, 31 / R + 2);
-    static bool attr = false;   // benign race: idempotent
-    if (!attr) {
-        CU(cudaFuncSetAttribute(rescore_slab_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                64 * (RS_SLAB + 4) * (int)sizeof(float)));
-        CU(cudaFuncSetAttribute(rescore_owned_list_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                64 * (RS_SLAB + 4) * (int)sizeof(float)));
-        attr = true;
-    }
+    static std::atomic<uint64_t> attr_done_a{0}, attr_done_b{0};
+    ensure_dyn_smem(attr_done_a, rescore_slab_kernel<true>, 64 * (RS_SLAB + 4) * (int)sizeof(float));
+    ensure_dyn_smem(attr_done_b, rescore_owned_list_kernel, 64 * (RS_SLAB + 4) * (int)sizeof(float));
     const uint64_t lo = h->windowed ? h->win_first : 0;
     const uint64_t hi = h->windowed ? std::min(h->n_rows, h->win_first + h->win_count) : h->n_rows;
     const uint64_t pairs = (uint64_t)nq * R;
@@ -2228,11 +2217,8 @@ void rrf_launch(cudaStream_t st, const uint64_t* dense, uint32_t n_d, const uint
     uint32_t n_eff = 64;
     while (n_eff < n) n_eff <<= 1;
     const size_t smem = (size_t)n * 8 + (size_t)n_eff * 8 + (size_t)n * 4;
-    static bool attr = false;   // benign race: idempotent
-    if (!attr) {
-        CU(cudaFuncSetAttribute(rrf_fusion_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(RRF_MAX * 20)));
-        attr = true;
-    }
+    static std::atomic<uint64_t> attr_done{0};
+    ensure_dyn_smem(attr_done, rrf_fusion_kernel, (int)(RRF_MAX * 20));
     const unsigned threads = n_eff <= 512 ? 256 : SORT_THREADS;
     rrf_fusion_kernel<<<nq, threads, smem, st>>>(dense, n_d, sparse, n_s, text, n_t, k, limit, ids_out, scores_out);
     CU(cudaGetLastError());
