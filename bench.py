@@ -455,7 +455,7 @@ def run_ours(args, rank, world, local_rank):
     # the dense FP4 rate is 4 x bf16 (9 vs 2.25 PFLOP/s nominal), so peak = 4 x the measured bf16
     # burst.  frac_of_mma_issue_floor uses the 64 clk per M128 x N128 x K64 MMA the hardware
     # nominally issues (tools/mxf4_probe.cu measures 76 clk with A in TMEM).
-    stage_keys = ("prep_ms", "scan_ms", "tc_ms", "scatter_ms", "select_ms", "rescore_ms", "topk_ms", "merge_ms",
+    stage_keys = ("prep_ms", "scan_ms", "sample_ms", "tc_ms", "scatter_ms", "select_ms", "rescore_ms", "topk_ms", "merge_ms",
                   "exchange_ms", "exchange_wait_ms")
     step_kernel_ms = sum(prof[x] for x in stage_keys)
     sm_mhz = clk.get("sm_mhz") or sm_max

@@ -45,7 +45,7 @@ class GvdbProfile(C.Structure):
                 ("tc_ms", C.c_double), ("tc_macs", C.c_double), ("tc_bytes", C.c_double),
                 ("scatter_ms", C.c_double), ("optimistic_reruns", C.c_uint64),
                 ("overflow_fallbacks", C.c_uint64), ("exchange_ms", C.c_double),
-                ("exchange_wait_ms", C.c_double)]
+                ("exchange_wait_ms", C.c_double), ("sample_ms", C.c_double)]
 
 
 # every symbol include/gvdb.h declares: name -> (restype, argtypes)
@@ -123,7 +123,7 @@ def lib() -> C.CDLL:
             fn = getattr(L, name)  # AttributeError if the library does not export it
             fn.restype = res
             fn.argtypes = args
-        if L.gvdb_abi_version() != 4:
+        if L.gvdb_abi_version() != 5:
             raise RuntimeError("libgvdb.so ABI version mismatch")
         _lib = L
     return _lib

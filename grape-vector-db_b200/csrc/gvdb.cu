@@ -65,7 +65,7 @@ struct DevBuf {
     template <class T> T* as() const { return reinterpret_cast<T*>(p); }
 };
 
-enum Kind { K_SCAN = 0, K_SELECT, K_RESCORE, K_TOPK, K_PREP, K_FLAT, K_MERGE, K_TCSCAN, K_SCATTER, K_XCHG, K_XCHG_WAIT, K_COUNT };
+enum Kind { K_SCAN = 0, K_SELECT, K_RESCORE, K_TOPK, K_PREP, K_FLAT, K_MERGE, K_TCSCAN, K_SAMPLE, K_SCATTER, K_XCHG, K_XCHG_WAIT, K_COUNT };
 struct ProfRec {
     int kind;
     cudaEvent_t e0, e1;
@@ -89,7 +89,8 @@ struct Workspace {
     bool used = false;
     DevBuf qpack, qnorm, cnt, flag, buf, rec_ham, rec_ids, rec_score;
     DevBuf q_in, ids_out, sc_out, codes_tmp, misc;
-    DevBuf qexp, qpop, qbias;        // tcgen05 path: pre-expanded queries, popcounts, biases
+    DevBuf qexp, qpop, qbase;        // tcgen05 path: pre-expanded queries (+ bias digits), popc(q), popc(q) + bias
+    DevBuf tilemin;                  // tcgen05 path: per-(sample tile, query) minima of the single-pass search
     DevBuf tc_recs, list_counts;     // tcgen05 path: warp-private survivor records
     DevBuf big_keys, big_keys2, big_aux, big_k32, big_v32, big_tmp;   // large-R path (gvdb_bigr.cuh)
     uint32_t* h_flag = nullptr;      // pinned
@@ -99,7 +100,7 @@ struct Workspace {
     size_t h_res_bytes = 0;
     ~Workspace() {
         for (DevBuf* b : {&qpack, &qnorm, &cnt, &flag, &buf, &rec_ham, &rec_ids, &rec_score, &q_in,
-                          &ids_out, &sc_out, &codes_tmp, &misc, &qexp, &qpop, &qbias, &tc_recs, &list_counts,
+                          &ids_out, &sc_out, &codes_tmp, &misc, &qexp, &qpop, &qbase, &tilemin, &tc_recs, &list_counts,
                           &big_keys, &big_keys2, &big_aux, &big_k32, &big_v32, &big_tmp, &filt, &allow_in}) b->release();
         if (h_flag) cudaFreeHost(h_flag);
         if (h_res) cudaFreeHost(h_res);
@@ -172,7 +173,8 @@ struct gvdb_index {
     uint32_t tc_min_q = 64;    // GVDB_TC_MIN_Q: query-tile size from which the tcgen05 scan is used
     uint32_t seg0_rows = 4096; // GVDB_SEG0_ROWS: rows of the first ("emit everything") segment
     uint32_t tc_qb_force = 0;  // GVDB_TC_QB: force the query blocks per tensor-core work item (0 = model)
-    uint32_t opt_m = 5;        // GVDB_OPT_M: order statistic of the optimistic single-pass threshold (0 = off)
+    uint32_t opt_m = 5;        // GVDB_OPT_M: smallest order statistic of the single-pass threshold (0 = single pass off)
+    uint32_t sample_div = 16;  // GVDB_SAMPLE_DIV: the single-pass sample is 1/sample_div of the row groups
     uint32_t seg_growth = 16;  // GVDB_SEG_GROWTH: cap on the geometric segment growth (0 = cap/(4R) only)
     std::atomic<int> profile_on{0};
     std::atomic<uint64_t> launches{0};
@@ -242,6 +244,7 @@ void flush_profile(gvdb_index* h, Workspace* ws) {
             case K_MERGE: h->prof.merge_ms += ms; break;
             case K_TCSCAN: h->prof.tc_ms += ms; h->prof.tc_launches += 1;
                            h->prof.tc_bytes += r.bytes; h->prof.tc_macs += r.pairs; break;
+            case K_SAMPLE: h->prof.sample_ms += ms; break;
             case K_SCATTER: h->prof.scatter_ms += ms; break;
             case K_XCHG: h->prof.exchange_ms += ms; break;
             case K_XCHG_WAIT: h->prof.exchange_wait_ms += ms; break;
@@ -372,8 +375,6 @@ void launch_scan(int nchunk, int variant, cudaStream_t st, dim3 grid, size_t sme
 // ---- tcgen05 scan dispatch (codes up to 1536 bits: the resident query block must fit shared memory) ---
 bool tc_supported(int nchunk) { return tc_supported_chunks(nchunk); }
 
-// MODE 0: survivors -> warp-private record lists -> tc_scatter_kernel -> per-query buffers.
-// MODE 1: every distance to dist_out (parity).
 // Work split of one tcgen05 scan launch: items = query slices x row slices, one CTA per SM looping
 // over items.  Pick the row-slice count that fills whole waves of SMs.
 struct TcSplit { uint32_t qslices, rslices, grid, qb_item; };
@@ -392,7 +393,7 @@ TcSplit tc_split(const gvdb_index* h, uint32_t ngroups, uint32_t nq_pad) {
         for (uint32_t r = 1; r <= rmax; ++r) {
             const uint64_t items = (uint64_t)qsl * r;
             const uint64_t waves = (items + sms - 1) / sms;
-            const double cost = (double)waves * std::ceil((double)ngroups / r) * (qb + 0.2);
+            const double cost = (double)waves * (std::ceil((double)ngroups / r) * (qb + 0.1) + 6.0 * qb);
             if (cost < best_cost - 1e-9) {
                 best_cost = cost;
                 best = TcSplit{qsl, r, (uint32_t)std::min<uint64_t>(items, sms), qb};
@@ -402,42 +403,46 @@ TcSplit tc_split(const gvdb_index* h, uint32_t ngroups, uint32_t nq_pad) {
     return best;
 }
 
-// MODE 0: survivors -> warp-private record lists -> tc_scatter_kernel -> per-query buffers.
+// MODE 0: survivors (hamming < tau, qthr holds the per-query constants) -> per-query candidate buffers.
 // MODE 1: every distance to dist_out (parity).
+// MODE 2: per-(tile, query) minima of the strided sample -> ws->tilemin.
+// Row groups: `ngroups` groups of 128 rows starting at tile_lo, `group_stride` groups apart.
+// expect_per_query (MODE 0): survivors the caller expects per query, sizes the record lists.
 template <int MODE>
 void launch_tc_scan(gvdb_index* h, Workspace* ws, cudaStream_t st, uint32_t tile_lo, uint32_t tile_hi,
-                    uint32_t nq, uint32_t nq_pad, uint32_t* cnt, uint64_t* buf, uint32_t cap,
-                    uint32_t* overflow, uint32_t* dist_out, uint64_t dist_stride) {
-    const uint32_t ngroups = (tile_hi - tile_lo + 3) / 4;
+                    uint32_t ngroups, uint32_t group_stride, uint32_t nq, uint32_t nq_pad, uint32_t* cnt,
+                    uint64_t* buf, uint32_t cap, uint32_t* overflow, uint32_t* dist_out, uint64_t dist_stride,
+                    uint32_t expect_per_query = 0) {
     const TcSplit sp = tc_split(h, ngroups, nq_pad);
     const uint32_t grid = sp.grid;
     const uint32_t nlists = grid * TC_EPI_WARPS;
     const size_t smem = (size_t)tc_qblocks(h->nchunk) * tc_qblock_bytes(h->nchunk);
     uint32_t rec_cap = 0;
     if (MODE == 0) {
-        // expected survivors per launch <= nq * cap / 4 (segment sizing); 4x head-room per list
-        uint64_t want = 4ull * ((uint64_t)nq * cap / 4) / nlists;
-        rec_cap = 4096;
-        while (rec_cap < want && rec_cap < 65536) rec_cap <<= 1;
+        // 4x head-room over the expected survivors per list (a list that fills up raises the overflow flag)
+        const uint64_t want = 4ull * ((uint64_t)nq * std::max<uint32_t>(expect_per_query, 64)) / nlists;
+        rec_cap = 2048;
+        while (rec_cap < want && rec_cap < (1u << 20)) rec_cap <<= 1;
         ws->tc_recs.ensure((size_t)nlists * rec_cap * sizeof(uint2));
         ws->list_counts.ensure((size_t)h->sm_count * TC_EPI_WARPS * 4);
     }
     const int8_t* qexp = ws->qexp.as<int8_t>();
-    const uint32_t* qpop = ws->qpop.as<uint32_t>();
-    const int32_t* qbias = ws->qbias.as<int32_t>();
+    const int32_t* qbase = ws->qbase.as<int32_t>();
+    int32_t* tilemin = ws->tilemin.as<int32_t>();
     uint2* recs = ws->tc_recs.as<uint2>();
     uint32_t* lc = ws->list_counts.as<uint32_t>();
-    const double seg_rows = (double)(tile_hi - tile_lo) * 32.0;
+    const double rows = (double)ngroups * TC_ROWS;
     {
-    Timed t(h, ws, st, K_TCSCAN, seg_rows * h->nchunk * 16.0 * sp.qslices,
-            seg_rows * (double)nq_pad * (h->nchunk * 128.0 + 64.0));
+    // algorithmic work of the launch: rows x padded queries x code bits (one MAC per code bit and pair)
+    Timed t(h, ws, st, MODE == 2 ? K_SAMPLE : K_TCSCAN, rows * h->nchunk * 16.0 * sp.qslices,
+            rows * (double)nq_pad * (h->nchunk * 128.0));
 #define GVDB_TC_CASE(N)                                                                              \
     case N: {                                                                                        \
         static std::atomic<uint64_t> attr_done{0};                                                   \
         ensure_dyn_smem(attr_done, tc_scan_kernel<N, MODE>, (int)(tc_qblocks(N) * tc_qblock_bytes(N))); \
-        tc_scan_kernel<N, MODE><<<grid, TC_THREADS, smem, st>>>(h->codes, live_of(h, ws), tile_lo, tile_hi, qexp, qpop, qbias, \
-                                                               nq, nq_pad, sp.qslices, sp.rslices, sp.qb_item, recs, rec_cap, lc,  \
-                                                               overflow, dist_out, dist_stride, h->n_rows, 0);          \
+        tc_scan_kernel<N, MODE><<<grid, TC_THREADS, smem, st>>>(h->codes, live_of(h, ws), tile_lo, tile_hi, ngroups, group_stride, \
+                                                               qexp, qbase, nq, nq_pad, sp.qslices, sp.rslices, sp.qb_item,        \
+                                                               recs, rec_cap, lc, overflow, dist_out, dist_stride, h->n_rows, tilemin, 0); \
         break;                                                                                       \
     }
     switch (h->nchunk) {
@@ -456,20 +461,27 @@ void launch_tc_scan(gvdb_index* h, Workspace* ws, cudaStream_t st, uint32_t tile
     }
 }
 
-void tc_prepare_queries(gvdb_index* h, Workspace* ws, cudaStream_t st, uint32_t nq, uint32_t nq_pad) {
+void tc_ensure_query_buffers(gvdb_index* h, Workspace* ws, uint32_t nq_pad) {
     ws->qexp.ensure((size_t)(nq_pad / TC_NQ) * tc_qblock_bytes(h->nchunk));
     ws->qpop.ensure((size_t)nq_pad * 4);
-    ws->qbias.ensure((size_t)nq_pad * 4);
+    ws->qbase.ensure((size_t)nq_pad * 4);
+}
+
+// qpack -> expanded query blocks + popcounts (the multi-segment schedule and gvdb_hamming; the single-pass
+// search does this inside query_prep_tc_kernel)
+void tc_prepare_queries(gvdb_index* h, Workspace* ws, cudaStream_t st, uint32_t nq, uint32_t nq_pad) {
+    tc_ensure_query_buffers(h, ws, nq_pad);
     h->launches.fetch_add(1, std::memory_order_relaxed);
     tc_expand_queries_kernel<<<nq_pad, 64, 0, st>>>(ws->qpack.as<uint32_t>(), h->qs, h->nchunk, nq, nq_pad,
                                                     ws->qexp.as<int8_t>(), ws->qpop.as<uint32_t>());
     CU(cudaGetLastError());
 }
 
+// the current tau words of qpack -> the bias digits of the resident blocks + popc(q) + bias (zero_bias: MODE 1)
 void tc_update_bias(gvdb_index* h, Workspace* ws, cudaStream_t st, uint32_t nq, uint32_t nq_pad, int zero_bias) {
     h->launches.fetch_add(1, std::memory_order_relaxed);
-    tc_bias_kernel<<<(nq_pad + 127) / 128, 128, 0, st>>>(ws->qpack.as<uint32_t>(), h->qs, h->nchunk, ws->qpop.as<uint32_t>(),
-                                                         nq, nq_pad, ws->qexp.as<int8_t>(), ws->qbias.as<int32_t>(), zero_bias);
+    tc_bias_kernel<<<(nq_pad + 7) / 8, 256, 0, st>>>(ws->qpack.as<uint32_t>(), h->qs, h->nchunk, ws->qpop.as<uint32_t>(),
+                                                     nq, nq_pad, ws->qexp.as<int8_t>(), ws->qbase.as<int32_t>(), zero_bias);
     CU(cudaGetLastError());
 }
 
@@ -503,6 +515,40 @@ uint32_t next_pow2_host(uint32_t v) {
 }
 uint32_t pick_cap(uint32_t R) { return R <= 1024 ? 8192u : 16384u; }
 constexpr uint32_t kMaxR = SORT_N / 2;
+
+// Plan of the single-pass search (tensor-core scan): a strided SAMPLE of the row groups gives, per query,
+// the minima of its 32-row tiles; the m-th smallest of them + 1 is the threshold of ONE pass over all rows
+// (tc_tau_kernel).  Expected survivors per query: m * rows / sampled rows; the pass found the true top R iff
+// at least R candidates came out (checked on the device, the call is rerun with the segment schedule otherwise).
+//   sample = every row (small corpora): m = R and the guarantee is deterministic — the m-th smallest tile
+//            minimum is at least the m-th smallest distance, so at least R rows lie at or below it.
+//   else:    the pass misses iff m of the true top R rows fall into the sample, probability
+//            P(Poisson(R * sampled fraction) >= m); the smallest m >= GVDB_OPT_M keeping that under 1e-6.
+struct SinglePass { bool ok; uint32_t n_sgroups, gstride, m; };
+SinglePass plan_single_pass(const gvdb_index* h, uint32_t ntiles, uint32_t R, uint32_t cap) {
+    SinglePass sp{false, 0, 1, 0};
+    if (h->opt_m == 0) return sp;
+    const uint32_t ngroups = (ntiles + 3) / 4;
+    uint32_t n_s = std::min<uint32_t>(1024, std::max<uint32_t>(64, ngroups / h->sample_div));
+    if (n_s >= ngroups) {                                     // the sample is the corpus
+        if (ngroups > 1024 || 2ull * R > 4ull * ngroups) return sp;
+        sp = SinglePass{true, ngroups, 1, R};
+        return sp;
+    }
+    const uint32_t gstride = ngroups / n_s;
+    const double x = (double)R * n_s / (double)ngroups;
+    double term = std::exp(-x), below = 0.0;                  // below = P(Poisson(x) < m)
+    uint32_t m = 0;
+    for (; m < 1024; ++m) {
+        if (m >= h->opt_m && 1.0 - below <= 1e-6) break;
+        below += term;
+        term *= x / (double)(m + 1);
+    }
+    if (m >= 1024 || m > n_s) return sp;                      // m tiles out of 4 * n_s: collisions stay rare
+    if ((double)m * ngroups / n_s > cap / 3.0) return sp;     // expected survivors per query
+    sp = SinglePass{true, n_s, gstride, m};
+    return sp;
+}
 
 // Stage 1 + stage 2 for queries [0,nq) (device pointers): fills rec_* [nq][R].
 void search_core(gvdb_index* h, Workspace* ws, cudaStream_t st, const float* queries_dev,
@@ -539,69 +585,94 @@ void search_core(gvdb_index* h, Workspace* ws, cudaStream_t st, const float* que
     }
     for (uint32_t qt0 = 0; qt0 < nq; qt0 += QT) {
         const uint32_t nqt = std::min(QT, nq - qt0);
-        {
-            Timed t(h, ws, st, K_PREP);
-            if ((h->dim & 3) == 0)
-                query_prep_direct_kernel<<<(nqt + 31) / 32, 32, 0, st>>>(
-                    queries_dev + (size_t)qt0 * h->dim, nqt, h->dim, h->cfg.threshold, h->nchunk,
-                    ws->qnorm.as<float>(), ws->qpack.as<uint32_t>(), h->qs);
-            else
-                ingest_kernel<true><<<(nqt + STAGE_ROWS - 1) / STAGE_ROWS, STAGE_ROWS, 0, st>>>(
-                    queries_dev + (size_t)qt0 * h->dim, nqt, h->dim, h->cfg.threshold, h->nchunk, 0, nullptr,
-                    ws->qnorm.as<float>(), nullptr, ws->qpack.as<uint32_t>(), h->qs);
-        }
-        CU(cudaGetLastError());
-        CU(cudaMemsetAsync(ws->cnt.p, 0, (size_t)nqt * 4 * CNT_STRIDE, st));
-        // Large query tiles: the scan is a dense contraction -> tcgen05 (gvdb_tc.cuh).  The first
-        // segment (tau = "emit all", 4096 rows) always runs on the popc kernel.
-        const bool use_tc = nqt >= h->tc_min_q && tc_supported(h->nchunk) && ntiles > seg0_tiles;
+        // Large query tiles: the scan is a dense contraction -> tcgen05 (gvdb_tc.cuh).
+        const bool tc_ok = nqt >= h->tc_min_q && tc_supported(h->nchunk);
         const uint32_t nq_pad = (nqt + TC_NQ - 1) / TC_NQ * TC_NQ;
-        // Optimistic single pass: one tensor-core launch over everything after the first segment,
-        // thresholded at the m-th smallest distance of the first segment (expected survivors per
-        // query m * rows_left / rows_seen <= cap / 4); verified on the device, rerun if refuted.
-        // m grows with R: the guess holds iff at least R rows lie below the m-th smallest distance of the
-        // first segment, which fails with probability P(Poisson(R * rows_seen / rows) >= m) per query;
-        // the smallest m >= GVDB_OPT_M keeping that under 1e-6 is used (m = 5 for R = 40 on 1M rows)
-        uint32_t opt_m = 0;
-        if (allow_optimistic && use_tc && h->opt_m > 0) {
-            const double x = (double)R * seg0_tiles / (double)ntiles;
-            double term = std::exp(-x), below = 0.0;            // below = P(Poisson(x) < m)
-            uint32_t m = 0;
-            for (; m < 256; ++m) {
-                if (m >= h->opt_m && 1.0 - below <= 1e-6) break;
-                below += term;
-                term *= x / (double)(m + 1);
+        SinglePass sp{false, 0, 1, 0};
+        if (allow_optimistic && tc_ok && (h->dim & 3) == 0) sp = plan_single_pass(h, ntiles, R, cap);
+        if (sp.ok) {
+            // ---- single pass: prep -> sample (tile minima) -> thresholds -> one scan over all rows -> cut ----
+            if (used_optimistic) *used_optimistic = true;
+            tc_ensure_query_buffers(h, ws, nq_pad);
+            const uint32_t n_stiles = sp.n_sgroups * 4;
+            ws->tilemin.ensure((size_t)n_stiles * nq_pad * 4);
+            {
+                Timed t(h, ws, st, K_PREP);
+                const size_t smem = (size_t)QPT_WARPS * ((size_t)h->dim * 4 + (size_t)h->nchunk * 16);
+                static std::atomic<uint64_t> attr_done{0};
+                ensure_dyn_smem(attr_done, query_prep_tc_kernel, QPT_WARPS * (4096 * 4 + 32 * 16));
+                query_prep_tc_kernel<<<(nq_pad + QPT_WARPS - 1) / QPT_WARPS, 32 * QPT_WARPS, smem, st>>>(
+                    queries_dev + (size_t)qt0 * h->dim, nqt, nq_pad, h->dim, h->cfg.threshold, h->nchunk,
+                    ws->qnorm.as<float>(), ws->qpack.as<uint32_t>(), h->qs, ws->qexp.as<int8_t>(), ws->qpop.as<uint32_t>(),
+                    ws->cnt.as<uint32_t>(), nullptr);
             }
-            if (m < 256 && m <= R && (uint64_t)m * (ntiles - seg0_tiles) <= (uint64_t)(cap / 4) * seg0_tiles) opt_m = m;
-        }
-        if (opt_m && used_optimistic) *used_optimistic = true;
-        if (use_tc) tc_prepare_queries(h, ws, st, nqt, nq_pad);
-        uint32_t lo = 0;
-        while (lo < ntiles) {
-            uint64_t hi64 = lo == 0 ? seg0_tiles : (opt_m ? (uint64_t)ntiles : (uint64_t)lo * g);
-            uint32_t hi = (uint32_t)std::min<uint64_t>(hi64, ntiles);
-            const double seg_rows = (double)(hi - lo) * 32.0;
-            if (use_tc && lo > 0) {
-                tc_update_bias(h, ws, st, nqt, nq_pad, 0);
-                launch_tc_scan<0>(h, ws, st, lo, hi, nqt, nq_pad, ws->cnt.as<uint32_t>(), ws->buf.as<uint64_t>(), cap,
-                                  ws->flag.as<uint32_t>(), nullptr, 0);
-            } else {
-                const int qg = pick_qgroup(h, hi - lo, nqt);
-                dim3 grid = scan_grid(h, hi - lo, nqt, qg);
-                Timed t(h, ws, st, K_SCAN, seg_rows * h->nchunk * 16.0 * grid.y, seg_rows * nqt);
-                launch_scan<0>(h->nchunk, h->scan_variant, st, grid, (size_t)qg * h->qs * 4, h->codes, live_of(h, ws), lo, hi,
-                               ws->qpack.as<uint32_t>(), (int)nqt, qg, ws->cnt.as<uint32_t>(),
-                               ws->buf.as<uint64_t>(), cap, ws->flag.as<uint32_t>(), nullptr, 0, h->n_rows);
+            CU(cudaGetLastError());
+            launch_tc_scan<2>(h, ws, st, 0, ntiles, sp.n_sgroups, sp.gstride, nqt, nq_pad, nullptr, nullptr, 0,
+                              ws->flag.as<uint32_t>(), nullptr, 0);
+            {
+                Timed t(h, ws, st, K_SAMPLE);
+                static std::atomic<uint64_t> attr_done{0};
+                ensure_dyn_smem(attr_done, tc_tau_kernel, TC_TAU_WARPS * TC_TAU_MAX_TILES * 2);
+                tc_tau_kernel<<<(nq_pad + TC_TAU_WARPS - 1) / TC_TAU_WARPS, 32 * TC_TAU_WARPS,
+                                (size_t)TC_TAU_WARPS * n_stiles * 2, st>>>(
+                    ws->tilemin.as<int32_t>(), n_stiles, nqt, nq_pad, sp.m, ws->qpop.as<uint32_t>(),
+                    ws->qpack.as<uint32_t>(), h->qs, h->nchunk, ws->qexp.as<int8_t>(), ws->qbase.as<int32_t>());
             }
+            CU(cudaGetLastError());
+            launch_tc_scan<0>(h, ws, st, 0, ntiles, (ntiles + 3) / 4, 1, nqt, nq_pad, ws->cnt.as<uint32_t>(),
+                              ws->buf.as<uint64_t>(), cap, ws->flag.as<uint32_t>(), nullptr, 0,
+                              (uint32_t)std::min<uint64_t>(cap, (uint64_t)sp.m * ((ntiles + 3) / 4) / sp.n_sgroups + 1));
             {
                 Timed t(h, ws, st, K_SELECT);
                 select_hist_kernel<<<nqt, SELH_THREADS, selh_smem, st>>>(
                     ws->buf.as<uint64_t>(), cap, ws->cnt.as<uint32_t>(), R, r_pow2, nbins,
-                    ws->qpack.as<uint32_t>(), h->qs, h->nchunk * 4, lo == 0 ? opt_m : 0u,
-                    (opt_m && lo > 0) ? 1 : 0, ws->flag.as<uint32_t>());
+                    ws->qpack.as<uint32_t>(), h->qs, h->nchunk * 4, 0u, 2, ws->flag.as<uint32_t>());
             }
             CU(cudaGetLastError());
-            lo = hi;
+        } else {
+            // ---- segment schedule: the first segment emits every row, later ones only rows below the exact
+            //      R-th smallest distance so far (tcgen05 scan for large tiles, xor + popc otherwise) ----
+            {
+                Timed t(h, ws, st, K_PREP);
+                if ((h->dim & 3) == 0)
+                    query_prep_direct_kernel<<<(nqt + 31) / 32, 32, 0, st>>>(
+                        queries_dev + (size_t)qt0 * h->dim, nqt, h->dim, h->cfg.threshold, h->nchunk,
+                        ws->qnorm.as<float>(), ws->qpack.as<uint32_t>(), h->qs);
+                else
+                    ingest_kernel<true><<<(nqt + STAGE_ROWS - 1) / STAGE_ROWS, STAGE_ROWS, 0, st>>>(
+                        queries_dev + (size_t)qt0 * h->dim, nqt, h->dim, h->cfg.threshold, h->nchunk, 0, nullptr,
+                        ws->qnorm.as<float>(), nullptr, ws->qpack.as<uint32_t>(), h->qs);
+            }
+            CU(cudaGetLastError());
+            CU(cudaMemsetAsync(ws->cnt.p, 0, (size_t)nqt * 4 * CNT_STRIDE, st));
+            const bool use_tc = tc_ok && ntiles > seg0_tiles;
+            if (use_tc) tc_prepare_queries(h, ws, st, nqt, nq_pad);
+            uint32_t lo = 0;
+            while (lo < ntiles) {
+                uint64_t hi64 = lo == 0 ? seg0_tiles : (uint64_t)lo * g;
+                uint32_t hi = (uint32_t)std::min<uint64_t>(hi64, ntiles);
+                const double seg_rows = (double)(hi - lo) * 32.0;
+                if (use_tc && lo > 0) {
+                    tc_update_bias(h, ws, st, nqt, nq_pad, 0);
+                    launch_tc_scan<0>(h, ws, st, lo, hi, (hi - lo + 3) / 4, 1, nqt, nq_pad, ws->cnt.as<uint32_t>(),
+                                      ws->buf.as<uint64_t>(), cap, ws->flag.as<uint32_t>(), nullptr, 0, cap / 4);
+                } else {
+                    const int qg = pick_qgroup(h, hi - lo, nqt);
+                    dim3 grid = scan_grid(h, hi - lo, nqt, qg);
+                    Timed t(h, ws, st, K_SCAN, seg_rows * h->nchunk * 16.0 * grid.y, seg_rows * nqt);
+                    launch_scan<0>(h->nchunk, h->scan_variant, st, grid, (size_t)qg * h->qs * 4, h->codes, live_of(h, ws), lo, hi,
+                                   ws->qpack.as<uint32_t>(), (int)nqt, qg, ws->cnt.as<uint32_t>(),
+                                   ws->buf.as<uint64_t>(), cap, ws->flag.as<uint32_t>(), nullptr, 0, h->n_rows);
+                }
+                {
+                    Timed t(h, ws, st, K_SELECT);
+                    select_hist_kernel<<<nqt, SELH_THREADS, selh_smem, st>>>(
+                        ws->buf.as<uint64_t>(), cap, ws->cnt.as<uint32_t>(), R, r_pow2, nbins,
+                        ws->qpack.as<uint32_t>(), h->qs, h->nchunk * 4, 0u, 0, ws->flag.as<uint32_t>());
+                }
+                CU(cudaGetLastError());
+                lo = hi;
+            }
         }
         const uint64_t pairs = (uint64_t)nqt * R;
         if (keys_out) {
@@ -971,6 +1042,8 @@ gvdb_status gvdb_create(const gvdb_config* cfg, gvdb_index** out) {
         if (const char* s = getenv("GVDB_SEG0_ROWS")) h->seg0_rows = (uint32_t)std::max(32, atoi(s)) / 32 * 32;
         if (const char* s = getenv("GVDB_TC_QB")) h->tc_qb_force = (uint32_t)std::max(0, atoi(s));
         if (const char* s = getenv("GVDB_OPT_M")) h->opt_m = (uint32_t)std::max(0, atoi(s));
+        if (const char* s = getenv("GVDB_SAMPLE_DIV")) h->sample_div = (uint32_t)std::max(1, atoi(s));
+        h->query_tile = std::min<uint32_t>(h->query_tile, 32768);   // survivor records carry the query in 16 bits
         if (const char* s = getenv("GVDB_SEG_GROWTH")) h->seg_growth = (uint32_t)std::max(0, atoi(s));
         if (const char* s = getenv("GVDB_SCAN_CTAS_PER_SM")) h->scan_ctas_per_sm = std::max(1, atoi(s));
         if (cfg->flags & GVDB_FLAG_ROW_WINDOW) {
@@ -1315,7 +1388,8 @@ gvdb_status gvdb_hamming(gvdb_index* h, const uint8_t* q_codes, uint32_t nq, uin
                 const uint32_t m_pad = (m + TC_NQ - 1) / TC_NQ * TC_NQ;
                 tc_prepare_queries(h, ws, st, m, m_pad);
                 tc_update_bias(h, ws, st, m, m_pad, 1);
-                launch_tc_scan<1>(h, ws, st, 0, ntiles, m, m_pad, nullptr, nullptr, 0, nullptr, ws->misc.as<uint32_t>(), N);
+                launch_tc_scan<1>(h, ws, st, 0, ntiles, (ntiles + 3) / 4, 1, m, m_pad, nullptr, nullptr, 0, nullptr,
+                                  ws->misc.as<uint32_t>(), N);
             } else {
                 dim3 grid = scan_grid(h, ntiles, m);
                 launch_scan<1>(h->nchunk, -1, st, grid, (size_t)kQGroup * h->qs * 4, h->codes, h->live, 0, ntiles,

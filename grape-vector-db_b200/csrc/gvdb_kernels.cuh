@@ -430,11 +430,18 @@ constexpr int SELH_THREADS = 256;
 //             smallest distance of the rows seen so far, remembered in tau[1].  If the rows seen so
 //             far are a fair sample, about m * (rows left / rows seen) rows lie below it.  The
 //             guess is checked, not trusted:
-//   verify  after the pass: the top R is exact iff at least R candidates lie strictly below tau[1]
+//   verify  1: after the pass: the top R is exact iff at least R candidates lie strictly below tau[1]
 //             (then every row of the true top R was emitted); otherwise flags[1] asks for a rerun.
+//           2: single pass over ALL rows under tau[1] (tc_tau_kernel): every candidate lies below
+//             tau[1], so the top R is exact iff R of them were emitted, or tau[1] let everything pass.
 __device__ __forceinline__ void select_set_tau(const uint64_t* sel, uint32_t have, uint32_t R, uint32_t* tau,
                                                uint32_t opt_m, int verify, uint32_t* flags) {
     const uint32_t tau_r = (have >= R && R > 0) ? (uint32_t)(sel[R - 1] >> 32) : TAU_ALL;
+    if (verify == 2) {
+        if (!(have >= R || tau[1] == TAU_ALL)) flags[1] = 1u;
+        tau[0] = tau_r;
+        return;
+    }
     if (verify) {
         if (!(have >= R && tau_r < tau[1])) flags[1] = 1u;
         tau[0] = tau_r;

@@ -5,43 +5,49 @@
 // the integer pipes (16 popc + 64 LOP3 per clk per SM).  A 1-bit code needs no more than 4 bits
 // per element on the tensor core, so the contraction runs on the FP4 path:
 // tcgen05.mma.kind::mxf4 (e2m1 operands, one UE8M0 scale per 32 elements, all scales 1.0, f32
-// accumulation).  Measured with tools/mxf4_probe.cu: 76 clk per M128 x N128 x K64 MMA with A in
-// TMEM = 13.8k MAC/clk/SM; kind::i8 and kind::f8f6f4 do 8.2k (tools/mma_floor.cu: 64 clk per K32).
+// accumulation).  Measured with tools/mxf4_probe.cu: one M128 x N128 x K64 MMA with A in TMEM
+// retires every 64.1 clk = 16.35k MAC/clk/SM (107 clk with A in shared memory; kind::i8 and
+// kind::f8f6f4 do 8.2k, tools/mma_floor.cu).
 //
 // Exactness.  Row codes are expanded on chip to A in {0, 1.0} (nibbles 0x0 / 0x2), query codes
 // once per batch to B in {-1.0, +1.0} (0xA where the query bit is 1, 0x2 where it is 0).  With
-// S = n11 - n10 over the code bits,  sum_k A_k * B_k = -S  and  hamming = popc(q) - S, so
-// hamming < tau  <=>  S + (tau - popc(q)) > 0.  All products and partial sums are integers far
-// below 2^24: the f32 accumulation is exact.  Pad bits are 0 in A and contribute nothing.
-// The per-query bias v = tau - popc(q) is added ON the tensor core by one extra K=64 MMA per
-// accumulator block: A = 64 x 1.0 per row with scale factors (16, 1) for its two 32-element
-// halves, B = 32 coarse + 31 fine e2m1 digits with 16 * coarse + fine = -v, plus one digit 0.5.
-// The accumulator is then D = -(S + v) + 0.5: never zero, and a survivor is simply D < 0, so the
-// epilogue is a pure sign test on registers (a per-element threshold load from shared memory
-// measured 3x slower).
+// S = n11 - n10 over the code bits,  D = sum_k A_k * B_k = -S  and  hamming = popc(q) - S
+// = popc(q) + D.  All products and partial sums are integers far below 2^24: the f32
+// accumulation is exact.  Pad bits are 0 in A and contribute nothing.
 // One row word expands with a shift + a LOP3 per output word,
 //     out[4*w + i] = ((code_word[w] >> i) << 1) & 0x22222222       (nibble j <- code bit 4j + i),
 // a fixed permutation of the code bits applied to rows and queries alike (Hamming distance is
 // invariant to it).
 //
+// Three epilogues on the same mainloop:
+//   MODE 0  search: one extra K=64 MMA per block adds the per-query bias -(tau - popc(q)) + 0.5, so
+//           hamming < tau  <=>  D < 0: the epilogue ORs raw register bits and looks closer only where
+//           a sign bit shows up.  Survivors (row, query) leave through per-warp record lists
+//           (coalesced stores, no atomics); tc_scatter_kernel turns them into candidate keys.
+//   MODE 1  every distance to dist_out (gvdb_hamming, parity tests).
+//   MODE 2  sample: the minimum of D over each 32-row tile, per query (tilemin[tile][q]) — the
+//           threshold estimate of the single-pass search comes from these (tc_tau_kernel).
+//
 // Work decomposition.  item = (query slice, row slice).  A query slice is up to tc_qblocks() blocks
-// of 128 queries whose expanded codes (+ bias digits) stay RESIDENT in shared memory (3 blocks x
-// 52 KB at 768 bits) for the whole item; the item's rows stream through TMEM as the A operand, 128
-// at a time.  (Streaming the queries through a shared-memory ring instead needs more L2->SM
-// bandwidth than the L2 delivers to 148 SMs at once: that version measured 47 % of the MMA floor.)
+// of 128 queries whose expanded codes stay RESIDENT in shared memory (4 blocks x 48 KB at 768 bits)
+// for the whole item; the item's rows stream through TMEM as the A operand, 128 at a time.
+// (Streaming the queries through a shared-memory ring instead needs more L2->SM bandwidth than the
+// L2 delivers to 148 SMs at once: that version measured 47 % of the MMA floor.)
 //
 // Warp roles per CTA (one CTA per SM, persistent over items):
-//   warps 0-3  expanders: lane = row.  Load the row's code (coalesced, blocked layout, next group
-//              prefetched), expand it and write it into TMEM as the A operand (tcgen05.st).  A is a
-//              ring of two slots with their own ready/free barriers; a group goes through it in
-//              phases, so rewriting one slot overlaps the MMAs that still read the other.
-//   warps 4-7  epilogue: read the f32 accumulators back (tcgen05.ld), sign-test them and append
-//              survivors to warp-private record lists (MODE 0), or write every distance (MODE 1).
-//   warp 8     warp-uniform control flow, one elected lane: TMA bulk loads of the query slice, then
-//              tcgen05.mma issue (M=128, N=128, K=64; A from TMEM, B from shared memory, D in TMEM,
-//              one accumulator buffer per resident block).
-//   mbarriers  b_full/b_free, a_ready/a_free per A slot, acc_full/acc_empty per accumulator
-//              buffer; tcgen05.commit signals MMA completion.
+//   warps 0-3   expanders: lane = row.  Load the row's code (coalesced, blocked layout, next group
+//               prefetched), expand it and write it into TMEM as the A operand (tcgen05.st).  A is a
+//               ring of FOUR slots of tc_slot_chunks() code chunks with their own ready/free
+//               barriers: up to 768 bits the ring holds two whole row groups, so expanding group
+//               g + 1 overlaps every MMA of group g.
+//   warps 4-11  epilogue, two sets of four (set s owns accumulator buffer s): tcgen05.ld, test,
+//               append / write / reduce.
+//   warp 12     query loader (TMA bulk copies) + MMA issuer: M=128, N=128, K=64; A from TMEM, B from
+//               shared memory, D in TMEM (two accumulator buffers).  The TMEM base is the constant 0
+//               (the CTA allocates all 512 columns), so every operand of the unrolled MMA sequence is
+//               a uniform-register value and the issue loop stays ahead of the tensor pipe.
+//   mbarriers   b_full/b_free, a_ready/a_free per A slot, acc_full/acc_empty per accumulator
+//               buffer; tcgen05.commit signals MMA completion.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -55,36 +61,44 @@ constexpr int TC_NQ = 128;          // queries per accumulator block (UMMA N)
 constexpr int TC_KSTAGE = 128;      // K bytes per 16 KB query sub-block = 256 e2m1 elements = two 16-byte code chunks
 constexpr int TC_STAGE_BYTES = TC_NQ * TC_KSTAGE;   // 16 KB
 constexpr int TC_BIAS_BYTES = TC_NQ * 32;           // 4 KB: one K=64 slice of per-query bias digits (e2m1)
-constexpr int TC_MAX_QBLOCKS = 3;                   // accumulator buffers that fit TMEM next to A
+constexpr int TC_MAX_QBLOCKS = 4;                   // resident query blocks per item (shared memory)
 __host__ __device__ constexpr int tc_subblocks(int nchunk) { return (nchunk + 1) / 2; }
 __host__ __device__ constexpr size_t tc_qblock_bytes(int nchunk) {
     return (size_t)tc_subblocks(nchunk) * TC_STAGE_BYTES + TC_BIAS_BYTES;
 }
-// The A operand lives in a ring of two TMEM slots of tc_slot_chunks() code chunks (16 columns
-// each); a row group is expanded and consumed in phases, phase ph using slot ph & 1.  Up to 1536
-// bits the ring holds the whole group (two phases); longer codes go through it in 8 phases.
+// The A operand lives in a ring of FOUR TMEM slots of tc_slot_chunks() code chunks (16 columns each, at
+// most 3 chunks: 4 x 48 = 192 columns); a row group is expanded and consumed in tc_phases() phases,
+// phase p (a running counter over groups and items) using slot p % 4.  Up to 768 bits the ring holds
+// two whole row groups: expanding group g + 1 overlaps every MMA of group g.
+// Next to it: 16 scale columns and TWO accumulator buffers of 128 columns.  What was measured on the way
+// (1M x 1024 x 768, tools/tc_probe): three accumulators + a one-group ring 0.31 ms; one-chunk slots (12 of
+// them) + three accumulators 0.36 ms (the refill chain of a slot is longer than five chunks of MMAs);
+// accumulators of 64 columns 0.44 ms (an N = 64 MMA takes as long as an N = 128 one when A changes).
+// With two accumulators the epilogue must hand a buffer back fast: every epilogue warp copies its
+// 64 columns to registers and releases the buffer BEFORE testing them.
+constexpr int TC_NBUF = 2;
+constexpr int TC_NSLOT = 4;
 __host__ __device__ constexpr int tc_slot_chunks(int nchunk) {
-    return nchunk <= 12 ? (nchunk + 1) / 2 : (nchunk % 3 == 0 ? 3 : 2);
+    return nchunk <= 6 ? (nchunk + 1) / 2 : (nchunk % 3 == 0 ? 3 : 2);
 }
 __host__ __device__ constexpr int tc_phases(int nchunk) { return (nchunk + tc_slot_chunks(nchunk) - 1) / tc_slot_chunks(nchunk); }
-// Resident query blocks per item (each has its own TMEM accumulator buffer): what fits 216 KB of
-// shared memory and the TMEM columns left next to the A ring, at most three; a single block when
-// the ring cannot hold the whole row group (every block would need all the phases again).
+// Resident query blocks per item: what fits 216 KB of shared memory, at most four; a single block
+// when the ring cannot hold a whole row group (every further block would need all the phases again).
 __host__ __device__ constexpr int tc_qblocks(int nchunk) {
     int q = (int)((216 * 1024) / tc_qblock_bytes(nchunk));
-    const int by_tmem = (512 - 16 - 2 * tc_slot_chunks(nchunk) * 16) / TC_NQ;
-    if (by_tmem < q) q = by_tmem;
     if (TC_MAX_QBLOCKS < q) q = TC_MAX_QBLOCKS;
-    if (tc_phases(nchunk) > 2) q = q < 1 ? q : 1;
+    if (tc_phases(nchunk) > TC_NSLOT) q = q < 1 ? q : 1;
     return q;
 }
 __host__ __device__ constexpr bool tc_supported_chunks(int nchunk) {
     return nchunk == 1 || nchunk == 2 || nchunk == 3 || nchunk == 4 || nchunk == 6 || nchunk == 8 || nchunk == 12 ||
            nchunk == 16 || nchunk == 24;
 }
-constexpr int TC_EPI_WARPS = 8;      // two sets of four epilogue warps, alternating accumulator blocks
+constexpr int TC_EPI_WARPS = 8;      // two sets of four epilogue warps, one per accumulator buffer
 constexpr int TC_THREADS = 32 * (4 + TC_EPI_WARPS + 1);   // 4 expander warps + epilogue warps + loader/MMA-issuer warp
 constexpr uint32_t TC_TMEM_COLS = 512;
+constexpr int TC_QUEUE = 64;         // survivor queue entries per epilogue warp (MODE 0)
+constexpr int32_t TC_TILEMIN_NONE = 0x7fffffff;     // MODE 2: no live row in the tile
 
 // ---- PTX wrappers ------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
@@ -93,9 +107,7 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     while (!mbar_try_wait(bar, parity)) {}
 }
-// One lane of a converged warp; the compiler keeps the surrounding control flow warp-uniform, so
-// descriptors and TMEM addresses stay in uniform registers (an `if (lane == 0)` around the MMA
-// loop costs a register-to-uniform waterfall per MMA: ~72 clk per issue, above the 64 clk floor).
+// One lane of a converged warp; the surrounding control flow stays warp-uniform.
 __device__ __forceinline__ bool elect_one() {
     uint32_t pred;
     asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
@@ -142,6 +154,12 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
           "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
         : "r"(taddr) : "memory");
 }
+// one column: lane l gets TMEM[lane quarter base + l][col]
+__device__ __forceinline__ uint32_t tc_ld1(uint32_t taddr) {
+    uint32_t v;
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(v) : "r"(taddr) : "memory");
+    return v;
+}
 
 // UMMA shared-memory descriptor, K-major, no swizzle: 8x16 B core matrices (128 B contiguous);
 // LBO = byte stride between core matrices along K, SBO = along N.  (cute::UMMA::SmemDescriptor)
@@ -165,24 +183,72 @@ __host__ __device__ inline uint32_t tc_e2m1_nibble(int twice, bool negative) {
                        : twice == 6 ? 5u : twice == 8 ? 6u : 7u /* twice == 12 */;
     return mag | ((negative && twice) ? 8u : 0u);
 }
-// largest integer in {6, 4, 3, 2, 1} not above mag (mag >= 1)
-__host__ __device__ inline int tc_e2m1_int_floor(int mag) { return mag >= 6 ? 6 : mag == 5 ? 4 : mag; }
+// digit e (0, 1, 2, ...) of the greedy decomposition of a magnitude into e2m1 integers {6, 4, 3, 2, 1}:
+// mag / 6 sixes, then the remainder r < 6 as one digit (r = 5: 4 then 1)
+__host__ __device__ inline int tc_bias_digit(int mag, int e) {
+    const int n6 = mag / 6, r = mag % 6;
+    if (e < n6) return 6;
+    if (e == n6) return r == 5 ? 4 : r;
+    if (e == n6 + 1) return r == 5 ? 1 : 0;
+    return 0;
+}
+// Per-query bias of the search epilogue, added ON the tensor core by one extra K=64 MMA per accumulator
+// block: A = 64 x 1.0 per row with scale factors (16, 1) for its two 32-element halves, B = 32 coarse +
+// 31 fine e2m1 digits with 16 * coarse + fine = -v, plus one digit 0.5.  With v = tau - popc(q) the
+// accumulator becomes D = -(S + v) + 0.5: never zero, and hamming < tau <=> D < 0 — the epilogue is a
+// sign test on raw register bits (no per-element threshold arithmetic, which costs the issue slots the
+// MMA warp needs: tools/mma_contention_probe.cu).  v = K+1: everything passes (tau = TAU_ALL);
+// v = -(K+1): nothing does (padding queries); v = 0: MODE 1, hamming = popc(q) + D - 0.5.
+// One WARP writes the 32 digit bytes of query q (lane = K byte) in the K-major core-matrix order of a
+// 128 x 32 B block:  offset(n, kb) = (n/8)*256 + (kb/16)*128 + (n%8)*16 + (kb%16),  element e in byte e/2.
+__device__ __forceinline__ void tc_write_bias_digits(int8_t* __restrict__ qexp, int nchunk, uint32_t q, int v, int lane) {
+    const uint32_t qb = q / TC_NQ, n = q % TC_NQ;
+    uint8_t* blk = reinterpret_cast<uint8_t*>(qexp) + (size_t)qb * tc_qblock_bytes(nchunk) + (size_t)tc_subblocks(nchunk) * TC_STAGE_BYTES;
+    const int t = -v;
+    const bool neg = t < 0;
+    const int mag = neg ? -t : t;
+    const int coarse = mag / TC_BIAS_COARSE, fine = mag % TC_BIAS_COARSE;
+    uint32_t nib[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int e = 2 * lane + h;                         // element 0..63
+        if (e < 32) nib[h] = tc_e2m1_nibble(2 * tc_bias_digit(coarse, e), neg);
+        else if (e == 32) nib[h] = tc_e2m1_nibble(1, false);            // +0.5
+        else nib[h] = tc_e2m1_nibble(2 * tc_bias_digit(fine, e - 33), neg);
+    }
+    blk[(n / 8) * 256 + (lane / 16) * 128 + (n % 8) * 16 + (lane % 16)] = (uint8_t)(nib[0] | (nib[1] << 4));
+}
+__host__ __device__ inline int tc_bias_v(uint32_t tau, uint32_t pop, int K) {
+    if (tau == TAU_ALL) return K + 1;
+    int v = (int)min(tau, 1u << 20) - (int)pop;
+    return v > K + 1 ? K + 1 : (v < -(K + 1) ? -(K + 1) : v);
+}
 
-// ---- query pre-expansion ---------------------------------------------------------------------------
-// qpack (code words + tau, as produced by the query prep kernel) -> qexp, e2m1 +-1.0 nibbles in the
-// exact byte order the resident blocks need:  sub-block (qb, sb) of 16 KB at
-// qb*tc_qblock_bytes + sb*16384 (the last 4 KB of a query block hold the bias digits, written by
-// tc_bias_kernel), inside a sub-block
+// Byte offset, inside qexp, of output word o (= 4*w + i: code word w, shift i; 8 K elements = 4 K bytes)
+// of query q.  Sub-block (qb, sb) of 16 KB at qb*tc_qblock_bytes + sb*16384; inside a sub-block
 //   offset(n, kk) = (n/8)*1024 + (kk/16)*128 + (n%8)*16 + (kk%16),  n = query in block, kk = K byte
 // K element e of a query  <->  code bit 32*w + 4*j + i  with  e = (4*w + i)*8 + j  (see header);
-// element e sits in K byte e/2, low nibble for even e.  Query bit 1 -> -1.0 (0xA), 0 -> +1.0 (0x2).
-// Queries beyond nq (padding up to a multiple of 128) are all zero.  Also writes popc(q).
+// element e sits in K byte e/2, low nibble for even e.
+__host__ __device__ inline size_t tc_qexp_offset(uint32_t q, int o, int nchunk) {
+    const uint32_t qb = q / TC_NQ, n = q % TC_NQ;
+    const int kb = o * 4;
+    const int sb = kb / TC_KSTAGE, kk = kb % TC_KSTAGE;
+    return (size_t)qb * tc_qblock_bytes(nchunk) + (size_t)sb * TC_STAGE_BYTES + (n / 8) * 1024 + (kk / 16) * 128 +
+           (n % 8) * 16 + (kk % 16);
+}
+// Query bit 1 -> -1.0 (0xA), 0 -> +1.0 (0x2).
+__device__ __forceinline__ uint32_t tc_qexp_word(uint32_t code_word, int i) {
+    return TC_A_ONE8 | (((code_word >> i) & 0x11111111u) << 3);
+}
+
+// ---- query pre-expansion (standalone: gvdb_hamming and the multi-segment schedule) ----------------------
+// qpack (code words + tau, as produced by the query prep kernels) -> qexp (e2m1 +-1.0 nibbles in the byte
+// order the resident blocks need) + popc(q).  Queries beyond nq (padding up to a multiple of 128) are all zero.
 __global__ void tc_expand_queries_kernel(const uint32_t* __restrict__ qpack, int qs, int nchunk, uint32_t nq,
                                          uint32_t nq_pad, int8_t* __restrict__ qexp,
                                          uint32_t* __restrict__ qpop) {
     const uint32_t q = blockIdx.x;                 // one CTA per (padded) query
     if (q >= nq_pad) return;
-    const uint32_t qb = q / TC_NQ, n = q % TC_NQ;
     const int nwords_out = tc_subblocks(nchunk) * (TC_KSTAGE / 4);   // 32-bit output words per query (incl. pad)
     uint32_t pop = 0;
     for (int o = threadIdx.x; o < nwords_out; o += blockDim.x) {   // output word o = 4*w + i: 8 elements, 4 K bytes
@@ -190,13 +256,10 @@ __global__ void tc_expand_queries_kernel(const uint32_t* __restrict__ qpack, int
         uint32_t out = 0;
         if (q < nq && w < nchunk * 4) {
             const uint32_t word = qpack[(size_t)q * qs + w];
-            out = TC_A_ONE8 | (((word >> i) & 0x11111111u) << 3);       // 0x2 -> 0xA where the bit is set
+            out = tc_qexp_word(word, i);
             if (i == 0) pop += __popc(word);
         }
-        const int kb = o * 4;
-        const int sb = kb / TC_KSTAGE, kk = kb % TC_KSTAGE;
-        const size_t off = (size_t)qb * tc_qblock_bytes(nchunk) + (size_t)sb * TC_STAGE_BYTES + (n / 8) * 1024 + (kk / 16) * 128 + (n % 8) * 16 + (kk % 16);
-        *reinterpret_cast<uint32_t*>(qexp + off) = out;
+        *reinterpret_cast<uint32_t*>(qexp + tc_qexp_offset(q, o, nchunk)) = out;
     }
     // block reduce popcount (blockDim <= 256)
     __shared__ uint32_t red[8];
@@ -210,96 +273,209 @@ __global__ void tc_expand_queries_kernel(const uint32_t* __restrict__ qpack, int
     }
 }
 
-// Per-query bias digits for the current thresholds: v = tau - popc(q) (v = K+1 when tau is
-// TAU_ALL: everything passes; v = -(K+1) for padding queries: nothing passes; zero_bias: v = 0,
-// MODE 1).  The bias MMA must add -v + 0.5: 64 e2m1 digits per query, elements [0,32) scaled by
-// 16 (coarse), [32,64) by 1 (fine): 16 * sum(coarse) + sum(fine) = -v, and fine digit 0 is the
-// 0.5.  K-major core-matrix order of a 128 x 32 B block:
-//   offset(n, kb) = (n/8)*256 + (kb/16)*128 + (n%8)*16 + (kb%16),  element e in byte e/2.
-__global__ void tc_bias_kernel(const uint32_t* __restrict__ qpack, int qs, int nchunk,
-                               const uint32_t* __restrict__ qpop, uint32_t nq, uint32_t nq_pad,
-                               int8_t* __restrict__ qexp, int32_t* __restrict__ qbias, int zero_bias) {
-    const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+// Bias digits + qbase[q] = popc(q) + v for the current tau words of qpack (one warp per padded query).
+// zero_bias: v = 0 (MODE 1).
+__global__ void __launch_bounds__(256)
+tc_bias_kernel(const uint32_t* __restrict__ qpack, int qs, int nchunk, const uint32_t* __restrict__ qpop,
+               uint32_t nq, uint32_t nq_pad, int8_t* __restrict__ qexp, int32_t* __restrict__ qbase, int zero_bias) {
+    const uint32_t q = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
     if (q >= nq_pad) return;
     const int K = nchunk * 128;
     int v = -(K + 1);
-    if (q < nq) {
-        const uint32_t tau = qpack[(size_t)q * qs + nchunk * 4];
-        v = tau == TAU_ALL ? K + 1 : (int)tau - (int)qpop[q];
-        if (v > K + 1) v = K + 1;
-        if (v < -(K + 1)) v = -(K + 1);
-    }
+    if (q < nq) v = tc_bias_v(qpack[(size_t)q * qs + nchunk * 4], qpop[q], K);
     if (zero_bias) v = 0;
-    qbias[q] = v;
-    const uint32_t qb = q / TC_NQ, n = q % TC_NQ;
-    uint8_t* blk = reinterpret_cast<uint8_t*>(qexp) + (size_t)qb * tc_qblock_bytes(nchunk) + (size_t)tc_subblocks(nchunk) * TC_STAGE_BYTES;
-    const int t = -v;
-    const bool neg = t < 0;
-    int coarse = (neg ? -t : t) / TC_BIAS_COARSE;          // magnitudes; both parts carry t's sign
-    int fine = (neg ? -t : t) % TC_BIAS_COARSE;
-    uint32_t nib[64];
-    for (int e = 0; e < 32; ++e) {                          // coarse digits, integers from {6,4,3,2,1}
-        const int d = coarse > 0 ? tc_e2m1_int_floor(coarse) : 0;
-        coarse -= d;
-        nib[e] = tc_e2m1_nibble(2 * d, neg);
+    if (lane == 0) qbase[q] = (q < nq ? (int32_t)qpop[q] : 0) + v;
+    tc_write_bias_digits(qexp, nchunk, q, v, lane);
+}
+
+// ---- fused query preparation of the single-pass search (dim % 4 == 0) --------------------------------------
+// One WARP per (padded) query: the row is read once with coalesced 128-bit loads and staged in shared
+// memory; the lanes build the code words (strict '>' threshold, Msb0 bytes as BinaryVector::to_bytes(),
+// /root/reference/src/quantization.rs:97-101), lane 0 folds ||q||^2 strictly left to right (separately
+// rounded multiply and add: the reference's iterator sum, :208), then all lanes write qpack (code words
+// + [tau = TAU_ALL, 0, 0, 0]), popc(q), the expanded e2m1 block entries and the query's zeroed candidate
+// counter.  Replaces query_prep_direct_kernel + tc_expand_queries_kernel + a memset.
+constexpr int QPT_WARPS = 8;
+__global__ void __launch_bounds__(32 * QPT_WARPS)
+query_prep_tc_kernel(const float* __restrict__ x, uint32_t nq, uint32_t nq_pad, int dim, float thr, int nchunk,
+                     float* __restrict__ norms, uint32_t* __restrict__ qpack, int qs, int8_t* __restrict__ qexp,
+                     uint32_t* __restrict__ qpop, uint32_t* __restrict__ cnt, uint32_t* __restrict__ flags) {
+    extern __shared__ __align__(16) float s_rows[];           // QPT_WARPS x dim floats, then QPT_WARPS x nchunk*4 words
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (blockIdx.x == 0 && threadIdx.x < 8 && flags) flags[threadIdx.x] = 0u;
+    const uint32_t q = blockIdx.x * QPT_WARPS + warp;
+    if (q >= nq_pad) return;
+    const int nw = nchunk * 4;
+    float* mine = s_rows + (size_t)warp * dim;
+    uint32_t* words = reinterpret_cast<uint32_t*>(s_rows + (size_t)QPT_WARPS * dim) + warp * nw;
+    const bool real = q < nq;
+    for (int w = lane; w < nw; w += 32) words[w] = 0u;
+    __syncwarp();
+    if (real) {
+        const float4* src = reinterpret_cast<const float4*>(x + (size_t)q * dim);
+        const int nv = dim >> 2;
+        for (int v0 = 0; v0 < nv; v0 += 32) {
+            const int v = v0 + lane;
+            uint32_t bits = 0;
+            if (v < nv) {
+                const float4 f = __ldg(src + v);
+                reinterpret_cast<float4*>(mine)[v] = f;
+                const int e0 = (v & 7) * 4;               // element index inside the 32-bit word
+                const float e4[4] = {f.x, f.y, f.z, f.w};
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    const int e = e0 + t;
+                    bits |= (uint32_t)(e4[t] > thr) << ((e & ~7) | (7 - (e & 7)));
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {                   // lanes 8k .. 8k+7 make word v0/8 + k
+                const uint32_t wk = __reduce_or_sync(0xffffffffu, (lane >> 3) == k ? bits : 0u);
+                if (lane == k && (v0 >> 3) + k < nw) words[(v0 >> 3) + k] = wk;
+            }
+        }
     }
-    nib[32] = tc_e2m1_nibble(1, false);                     // +0.5
-    for (int e = 33; e < 64; ++e) {
-        const int d = fine > 0 ? tc_e2m1_int_floor(fine) : 0;
-        fine -= d;
-        nib[e] = tc_e2m1_nibble(2 * d, neg);
+    __syncwarp();
+    if (real && lane == 0) {
+        float ss = 0.0f;
+        const float4* m4 = reinterpret_cast<const float4*>(mine);
+        for (int v = 0; v < (dim >> 2); ++v) {
+            const float4 f = m4[v];
+            ss = __fadd_rn(ss, __fmul_rn(f.x, f.x));
+            ss = __fadd_rn(ss, __fmul_rn(f.y, f.y));
+            ss = __fadd_rn(ss, __fmul_rn(f.z, f.z));
+            ss = __fadd_rn(ss, __fmul_rn(f.w, f.w));
+        }
+        norms[q] = __fsqrt_rn(ss);
+        uint32_t* tau = qpack + (size_t)q * qs + nw;
+        tau[0] = TAU_ALL; tau[1] = 0u; tau[2] = 0u; tau[3] = 0u;
+        cnt[(size_t)q * CNT_STRIDE] = 0u;
     }
-    for (int kb = 0; kb < 32; ++kb)
-        blk[(n / 8) * 256 + (kb / 16) * 128 + (n % 8) * 16 + (kb % 16)] = (uint8_t)(nib[2 * kb] | (nib[2 * kb + 1] << 4));
+    uint32_t pop = 0;
+    for (int w = lane; w < nw; w += 32) {
+        const uint32_t word = words[w];
+        if (real) qpack[(size_t)q * qs + w] = word;
+        pop += __popc(word);
+    }
+    pop = __reduce_add_sync(0xffffffffu, pop);
+    if (lane == 0) qpop[q] = pop;
+    const int nwords_out = tc_subblocks(nchunk) * (TC_KSTAGE / 4);
+    for (int o = lane; o < nwords_out; o += 32) {
+        const int w = o >> 2, i = o & 3;
+        const uint32_t out = (real && w < nw) ? tc_qexp_word(words[w], i) : 0u;
+        *reinterpret_cast<uint32_t*>(qexp + tc_qexp_offset(q, o, nchunk)) = out;
+    }
+}
+
+// ---- single-pass threshold from the sample's tile minima ------------------------------------------------
+// One warp per query.  tilemin[t * nq_pad + q] (MODE 2) = min over the live rows of sample tile t of
+// D = hamming - popc(q) (TC_TILEMIN_NONE: no live row).  The minima of different tiles belong to
+// different rows, so the m-th smallest of them, t_m, is an upper bound of the m-th smallest distance
+// among the sampled rows (and equals it unless two of the m closest sampled rows share a tile):
+//     tau_opt = popc(q) + t_m + 1      (TAU_ALL while fewer than m tiles hold a live row)
+// Written to qpack's tau words [tau, tau_opt], as the bias digits of v = t_m + 1 and as qbase = popc(q) + v.
+// Whether the pass under tau_opt found the true top R is checked afterwards (select_hist_kernel, verify 2).
+constexpr int TC_TAU_WARPS = 8;
+constexpr int TC_TAU_MAX_TILES = 4096;
+__global__ void __launch_bounds__(32 * TC_TAU_WARPS)
+tc_tau_kernel(const int32_t* __restrict__ tilemin, uint32_t n_tiles, uint32_t nq, uint32_t nq_pad, uint32_t m,
+              const uint32_t* __restrict__ qpop, uint32_t* __restrict__ qpack, int qs, int nchunk,
+              int8_t* __restrict__ qexp, int32_t* __restrict__ qbase) {
+    extern __shared__ int16_t s_min[];                         // TC_TAU_WARPS x n_tiles
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t q = blockIdx.x * TC_TAU_WARPS + warp;
+    if (q >= nq_pad) return;
+    const int K = nchunk * 128;
+    if (q >= nq) {                                             // padding query: nothing passes
+        if (lane == 0) qbase[q] = -(K + 1);
+        tc_write_bias_digits(qexp, nchunk, q, -(K + 1), lane);
+        return;
+    }
+    int16_t* mine = s_min + (size_t)warp * n_tiles;
+    for (uint32_t t = lane; t < n_tiles; t += 32) {
+        const int32_t v = tilemin[(size_t)t * nq_pad + q];
+        mine[t] = v == TC_TILEMIN_NONE ? (int16_t)0x7fff : (int16_t)v;
+    }
+    __syncwarp();
+    int32_t tm = 0x7fff;
+    for (uint32_t it = 0; it < m; ++it) {                      // extract the smallest, m times
+        int32_t best = 0x7fff;
+        uint32_t at = 0xffffffffu;
+        for (uint32_t t = lane; t < n_tiles; t += 32) {
+            const int32_t v = mine[t];
+            if (v < best) { best = v; at = t; }
+        }
+        const int32_t wmin = __reduce_min_sync(0xffffffffu, best);
+        tm = wmin;
+        if (wmin == 0x7fff) break;                             // fewer than m live tiles
+        const uint32_t owner = __ffs(__ballot_sync(0xffffffffu, best == wmin && at != 0xffffffffu)) - 1;
+        if ((uint32_t)lane == owner) mine[at] = (int16_t)0x7fff;
+        __syncwarp();
+    }
+    tm = __shfl_sync(0xffffffffu, tm, 0);
+    const int32_t pop = (int32_t)qpop[q];
+    int v = K + 1;                                             // fewer than m live tiles: everything passes
+    uint32_t t = TAU_ALL;
+    if (tm != 0x7fff) { t = (uint32_t)max(pop + tm + 1, 0); v = tc_bias_v(t, (uint32_t)pop, K); }
+    if (lane == 0) {
+        uint32_t* tau = qpack + (size_t)q * qs + nchunk * 4;
+        tau[0] = t; tau[1] = t;
+        qbase[q] = pop + v;
+    }
+    tc_write_bias_digits(qexp, nchunk, q, v, lane);
 }
 
 // ---- the scan ------------------------------------------------------------------------------------------
-// MODE 0: append survivors (search).  MODE 1: write all distances (dist_out[q*stride + row]).
-// prof (optional, tools/tc_probe): cycle accounting of CTA 0.
+// Row groups: logical group g in [0, ngroups) covers tiles tile_lo + g * group_stride * 4 + {0,1,2,3}
+// (group_stride = 1: a contiguous range; > 1: the strided sample of MODE 2).
+// prof (optional, tools/tc_probe): cycle accounting of CTA 0.  dbg: timing experiments of tools/tc_probe
+// (1 no accumulator reads, 2 no A stores) — 0 in the library.
 template <int NCHUNK, int MODE>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_scan_kernel(const uint4* __restrict__ codes, const uint32_t* __restrict__ live, uint32_t tile_lo,
-               uint32_t tile_hi, const int8_t* __restrict__ qexp, const uint32_t* __restrict__ qpop,
-               const int32_t* __restrict__ qbias, uint32_t nq, uint32_t nq_pad, uint32_t n_qslices,
-               uint32_t n_rslices, uint32_t qb_item /* query blocks per item, <= tc_qblocks(NCHUNK) */,
-               uint2* __restrict__ recs, uint32_t rec_cap,
-               uint32_t* __restrict__ list_counts, uint32_t* __restrict__ overflow,
-               uint32_t* __restrict__ dist_out, uint64_t dist_stride, uint64_t n_rows, int dbg = 0,
-               unsigned long long* __restrict__ prof = nullptr) {
+               uint32_t tile_hi, uint32_t ngroups, uint32_t group_stride, const int8_t* __restrict__ qexp,
+               const int32_t* __restrict__ qbase /* popc(q) + v, v = the bias of the query (MODE 0, 1) */, uint32_t nq, uint32_t nq_pad,
+               uint32_t n_qslices, uint32_t n_rslices, uint32_t qb_item /* query blocks per item, <= tc_qblocks(NCHUNK) */,
+               uint2* __restrict__ recs, uint32_t rec_cap, uint32_t* __restrict__ list_counts, uint32_t* __restrict__ overflow,
+               uint32_t* __restrict__ dist_out, uint64_t dist_stride, uint64_t n_rows,
+               int32_t* __restrict__ tilemin, int dbg = 0, unsigned long long* __restrict__ prof = nullptr) {
     constexpr int QB = tc_qblocks(NCHUNK);     // resident query blocks
-    constexpr int NBUF = QB < 2 ? 2 : QB;      // accumulator buffers (block it uses buffer it % NBUF)
+    constexpr int NBUF = TC_NBUF;              // accumulator buffers
+    constexpr int NSLOT = TC_NSLOT;            // A ring slots
     constexpr int SC = tc_slot_chunks(NCHUNK); // chunks per A slot
     constexpr int PH = (NCHUNK + SC - 1) / SC; // phases per row group
     constexpr int CHUNK_COLS = 16;             // TMEM columns per expanded code chunk (128 e2m1 = 64 B per row)
-    constexpr int A_COLS = 2 * SC * CHUNK_COLS;   // TMEM columns of the A ring
-    // then: 8 columns bias slice (64 x 1.0), 4 columns scale words 1.0, 4 columns the bias MMA's A scales
+    constexpr int SLOT_COLS = SC * CHUNK_COLS;
+    constexpr int A_COLS = NSLOT * SLOT_COLS;  // TMEM columns of the A ring
     constexpr uint32_t IDESC = tc_idesc_mxf4(TC_ROWS, TC_NQ);
     constexpr uint32_t QBLOCK_BYTES = (uint32_t)tc_qblock_bytes(NCHUNK);
     static_assert(QB >= 1, "the resident query block must fit shared memory");
-    static_assert(A_COLS + 16 + NBUF * TC_NQ <= 512, "TMEM budget");
+    static_assert(NBUF >= 2 && A_COLS + 16 + NBUF * TC_NQ <= 512, "TMEM budget");
     static_assert(QB * tc_qblock_bytes(NCHUNK) <= 216 * 1024, "shared memory budget");
+    static_assert(QB == 1 || PH <= NSLOT, "several resident blocks need the whole row group in the A ring");
 
     extern __shared__ __align__(1024) uint8_t smem[];      // QB resident query blocks
-    __shared__ int32_t s_bias[QB * TC_NQ];                   // MODE 1 only
-    __shared__ uint32_t s_pop[QB * TC_NQ];
-    __shared__ __align__(8) uint64_t bars[6 + 2 * TC_MAX_QBLOCKS];
+    __shared__ int32_t s_base[QB * TC_NQ];                   // MODE 0, 1: popc(q) + v of the item's queries
+    __shared__ uint32_t s_qrow[MODE == 0 ? TC_EPI_WARPS * TC_QUEUE : 1];   // MODE 0: survivor queues
+    __shared__ uint32_t s_qq[MODE == 0 ? TC_EPI_WARPS * TC_QUEUE : 1];
+    __shared__ __align__(8) uint64_t bars[2 + 2 * NSLOT + 2 * NBUF];
     __shared__ uint32_t s_tmem_base;
     const uint32_t bar0 = smem_u32(bars);
     const uint32_t b_full = bar0, b_free = bar0 + 8;
-    auto a_ready = [&](int h) { return bar0 + 8u * (2 + h); };
-    auto a_free = [&](int h) { return bar0 + 8u * (4 + h); };
-    auto acc_full = [&](int b) { return bar0 + 8u * (6 + b); };
-    auto acc_empty = [&](int b) { return bar0 + 8u * (6 + TC_MAX_QBLOCKS + b); };
+    auto a_ready = [&](uint32_t s) { return bar0 + 8u * (2 + s); };
+    auto a_free = [&](uint32_t s) { return bar0 + 8u * (2 + NSLOT + s); };
+    auto acc_full = [&](uint32_t b) { return bar0 + 8u * (2 + 2 * NSLOT + b); };
+    auto acc_empty = [&](uint32_t b) { return bar0 + 8u * (2 + 2 * NSLOT + NBUF + b); };
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t nqb = nq_pad / TC_NQ;
-    const uint32_t ngroups = (tile_hi - tile_lo + 3) / 4;
     const uint32_t n_items = n_qslices * n_rslices;
 
     if (threadIdx.x == 0) {
         mbar_init(b_full, 1); mbar_init(b_free, 1);
-        for (int h = 0; h < 2; ++h) { mbar_init(a_ready(h), 4); mbar_init(a_free(h), 1); }
-        for (int b = 0; b < NBUF; ++b) { mbar_init(acc_full(b), 1); mbar_init(acc_empty(b), 4); }
+        for (int s = 0; s < NSLOT; ++s) { mbar_init(a_ready(s), 4); mbar_init(a_free(s), 1); }
+        for (int b = 0; b < NBUF; ++b) { mbar_init(acc_full(b), 1); mbar_init(acc_empty(b), TC_EPI_WARPS); }
         fence_mbar_init();
     }
     constexpr int MMA_WARP = 4 + TC_EPI_WARPS;
@@ -307,11 +483,14 @@ tc_scan_kernel(const uint4* __restrict__ codes, const uint32_t* __restrict__ liv
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem = s_tmem_base;
-    const uint32_t tmem_a = tmem;                 // columns [0, A_COLS): the A ring; [A_COLS, A_COLS+8): bias slice
-    const uint32_t tmem_sf_one = tmem + A_COLS + 8;      // 4 columns of scale words 1.0
-    const uint32_t tmem_sf_bias = tmem + A_COLS + 12;    // 4 columns: the bias MMA's A scales (16, 1)
-    const uint32_t tmem_d = tmem + A_COLS + 16;          // NBUF accumulator buffers of TC_NQ columns
+    // The CTA owns all 512 columns (one CTA per SM: the shared memory does not admit a second one),
+    // so the allocation starts at lane 0, column 0.  Using the constant keeps every TMEM address of
+    // the MMA sequence in uniform registers.
+    if (s_tmem_base != 0u) { if (threadIdx.x == 0 && overflow) overflow[2] = 1u; __trap(); }
+    constexpr uint32_t tmem_a = 0;                       // columns [0, A_COLS): the A ring; [A_COLS, A_COLS+8): bias slice
+    constexpr uint32_t tmem_sf_one = A_COLS + 8;         // 4 columns of scale words 1.0 (read by every MMA)
+    constexpr uint32_t tmem_sf_bias = A_COLS + 12;       // 4 columns: the bias MMA's A scales (16, 1)
+    constexpr uint32_t tmem_d = A_COLS + 16;             // NBUF accumulator buffers of TC_NQ columns
     const uint32_t lane_taddr = (uint32_t)((warp & 3) * 32) << 16;
 
     unsigned long long pw[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -326,10 +505,10 @@ tc_scan_kernel(const uint4* __restrict__ codes, const uint32_t* __restrict__ liv
         g_lo = (uint32_t)((uint64_t)ngroups * rsl / n_rslices);
         g_hi = (uint32_t)((uint64_t)ngroups * (rsl + 1) / n_rslices);
     };
+    auto group_tile = [&](uint32_t g) { return tile_lo + g * group_stride * 4u; };
 
     if (warp < 4) {
         // ===================== expanders: codes -> A operand in TMEM =====================
-        uint32_t free_phase[2] = {1, 1};          // first wait on a fresh barrier passes
         {
             uint32_t ones[8];
 #pragma unroll
@@ -340,16 +519,17 @@ tc_scan_kernel(const uint4* __restrict__ codes, const uint32_t* __restrict__ liv
             tc_st8(tmem_sf_one + lane_taddr, ones);         // scale words (read by every MMA)
             tc_wait_st();
         }
+        uint32_t p = 0;                                     // running phase counter: slot p % NSLOT
         auto load_codes = [&](uint32_t g, uint4 (&r)[NCHUNK]) {
-            const uint32_t tile = tile_lo + g * 4 + warp;
+            const uint32_t tile = group_tile(g) + warp;
             const bool in_range = tile < tile_hi;
 #pragma unroll
             for (int c = 0; c < NCHUNK; ++c)
                 r[c] = in_range ? ldg_stream(codes + ((size_t)tile * NCHUNK + c) * 32 + lane) : make_uint4(0, 0, 0, 0);
         };
-        auto expand = [&](const uint4 (&r)[NCHUNK], int c_lo, int c_hi, int h) {   // chunks [c_lo, c_hi) -> slot h
-            { TC_PROF_T0(); mbar_wait(a_free(h), free_phase[h]); TC_PROF_ADD(h); }   // MMAs that read this half have retired
-            free_phase[h] ^= 1u;
+        auto expand = [&](const uint4 (&r)[NCHUNK], int c_lo, int c_hi) {   // chunks [c_lo, c_hi) -> slot p % NSLOT
+            const uint32_t s = p % NSLOT;
+            { TC_PROF_T0(); mbar_wait(a_free(s), ((p / NSLOT) & 1u) ^ 1u); TC_PROF_ADD(0); }   // the MMAs that read this slot have retired
             tc_fence_after();
             TC_PROF_T0();
 #pragma unroll
@@ -365,14 +545,15 @@ tc_scan_kernel(const uint4* __restrict__ codes, const uint32_t* __restrict__ liv
                         const int sh = i & 3;                        // nibble j <- code bit 4j + sh
                         v[i] = (sh == 0 ? (w << 1) : (w >> (sh - 1))) & TC_A_ONE8;
                     }
-                    tc_st8(tmem_a + lane_taddr + (uint32_t)(h * SC * CHUNK_COLS + ((c - c_lo) * 2 + wp) * 8), v);
+                    if (!(dbg & 2)) tc_st8(tmem_a + lane_taddr + s * SLOT_COLS + (uint32_t)(((c - c_lo) * 2 + wp) * 8), v);
                 }
             }
             tc_wait_st();
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(a_ready(h));
-            TC_PROF_ADD(2 + h);
+            if (lane == 0) mbar_arrive(a_ready(s));
+            ++p;
+            TC_PROF_ADD(2);
         };
         for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x) {
             uint32_t qb0, nb, g_lo, g_hi;
@@ -384,7 +565,7 @@ tc_scan_kernel(const uint4* __restrict__ codes, const uint32_t* __restrict__ liv
                 if (g + 1 < g_hi) load_codes(g + 1, rn);       // in flight while this group expands
 #pragma unroll
                 for (int ph = 0; ph < PH; ++ph)
-                    expand(r, ph * SC, (ph + 1) * SC < NCHUNK ? (ph + 1) * SC : NCHUNK, ph & 1);
+                    expand(r, ph * SC, (ph + 1) * SC < NCHUNK ? (ph + 1) * SC : NCHUNK);
 #pragma unroll
                 for (int c = 0; c < NCHUNK; ++c) r[c] = rn[c];
             }
@@ -392,111 +573,157 @@ tc_scan_kernel(const uint4* __restrict__ codes, const uint32_t* __restrict__ liv
         if (prof && blockIdx.x == 0 && threadIdx.x == 0)
             for (int i = 0; i < 4; ++i) prof[i] = pw[i];
     } else if (warp < MMA_WARP) {
-        // ===================== epilogue: accumulators -> survivors / distances =====================
-        // two sets of four warps (set s takes the accumulator blocks with it % 2 == s): reading and
-        // sign-testing a block takes about as long as the FP4 MMAs that produce it
-        const int ew = warp - 4;                  // 0 .. TC_EPI_WARPS-1; TMEM lane quarter = ew & 3
-        const uint32_t my_set = (uint32_t)(ew >> 2);
+        // ===================== epilogue: accumulators -> survivors / distances / tile minima =====================
+        // Eight warps: warp ew owns TMEM lane quarter ew & 3 (32 rows) and column half ew >> 2 (64 queries)
+        // of EVERY accumulator block.  It copies its 64 values to registers, hands the buffer back
+        // (acc_empty counts all eight warps) and only then tests them: with two accumulator buffers
+        // the MMAs of block i + 2 wait for this hand-over, not for the tests.
+        const int ew = warp - 4;                  // 0 .. TC_EPI_WARPS-1
+        const uint32_t half = (uint32_t)(ew >> 2);
         uint32_t it = 0;                          // running accumulator-block counter (buffer = it % NBUF)
-        // Survivor records of this warp: a private list, slots handed out with ballot + popc from a
-        // register counter.  No shared memory and no atomics in the epilogue.
+        // MODE 0: survivors (row, query) wait in a per-warp shared-memory queue and leave 32 at a time as
+        // one coalesced 256-byte store to the warp's private record list in global memory: no atomics,
+        // no loads, nothing the epilogue has to wait for.  tc_scatter_kernel turns the records into keys.
+        uint32_t* q_row = s_qrow + (MODE == 0 ? ew * TC_QUEUE : 0);
+        uint32_t* q_q = s_qq + (MODE == 0 ? ew * TC_QUEUE : 0);
+        uint32_t q_head = 0, q_count = 0, n_written = 0;
         uint2* my_list = recs + (size_t)(blockIdx.x * TC_EPI_WARPS + ew) * rec_cap;
-        uint32_t my_count = 0;
         const uint32_t lane_lt = (1u << lane) - 1u;
+        auto flush = [&](uint32_t n_take) {                 // warp-collective: write the first n_take queued survivors
+            __syncwarp();
+            if ((uint32_t)lane < n_take && n_written + lane < rec_cap && !(dbg & 4)) {
+                const uint32_t at = (q_head + lane) % TC_QUEUE;
+                my_list[n_written + lane] = make_uint2(q_row[at], q_q[at]);
+            }
+            n_written += n_take;
+            q_head = (q_head + n_take) % TC_QUEUE;
+            q_count -= n_take;
+            __syncwarp();
+        };
         for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x) {
             uint32_t qb0, nb, g_lo, g_hi;
             item_range(item, qb0, nb, g_lo, g_hi);
-            if (MODE == 1) {
+            if (MODE != 2) {
                 asm volatile("bar.sync 1, %0;" :: "n"(32 * TC_EPI_WARPS) : "memory");      // previous item's readers are done
-                for (uint32_t i = threadIdx.x - 128; i < nb * TC_NQ; i += 32 * TC_EPI_WARPS) {
-                    const uint32_t q = qb0 * TC_NQ + i;
-                    s_bias[i] = qbias[q];
-                    s_pop[i] = q < nq ? qpop[q] : 0u;
-                }
+                for (uint32_t i = threadIdx.x - 128; i < nb * TC_NQ; i += 32 * TC_EPI_WARPS)
+                    s_base[i] = qbase[qb0 * TC_NQ + i];
                 asm volatile("bar.sync 1, %0;" :: "n"(32 * TC_EPI_WARPS) : "memory");
             }
+            // the tombstone word of the NEXT group is fetched while this one is processed (an L2 round trip)
+            auto live_word = [&](uint32_t g) {
+                const uint32_t tile = group_tile(g) + (ew & 3);
+                return (g < g_hi && tile < tile_hi) ? __ldg(live + tile) : 0u;
+            };
+            uint32_t live_next = live_word(g_lo);
             for (uint32_t g = g_lo; g < g_hi; ++g) {
-                const uint32_t tile = tile_lo + g * 4 + (ew & 3);
+                const uint32_t tile = group_tile(g) + (ew & 3);
                 const bool in_range = tile < tile_hi;
                 const uint32_t row = tile * 32u + lane;
-                const bool alive = in_range && ((live[in_range ? tile : tile_lo] >> lane) & 1u);
+                const bool alive = (live_next >> lane) & 1u;
+                live_next = live_word(g + 1);
                 for (uint32_t blk = 0; blk < nb; ++blk, ++it) {
-                    if (TC_EPI_WARPS == 8 && (it & 1u) != my_set) continue;
                     const uint32_t b = it % NBUF;
-                    const uint32_t qbase = (qb0 + blk) * TC_NQ, qloc = blk * TC_NQ;
+                    const uint32_t qbase_q = (qb0 + blk) * TC_NQ + half * 64, qloc = blk * TC_NQ + half * 64;
                     { TC_PROF_T0(); mbar_wait(acc_full(b), (it / NBUF) & 1u); TC_PROF_ADD(0); }   // buffer b's (it / NBUF)-th use
                     tc_fence_after();
                     TC_PROF_T0();
-#pragma unroll 1
-                    for (int half = 0; half < ((dbg & 1) ? 0 : 2); ++half) {
+                    uint32_t v[64];
+                    if (!(dbg & 1)) {
                         uint32_t v0[32], v1[32];
                         const uint32_t col0 = tmem_d + lane_taddr + b * TC_NQ + half * 64;
                         tc_ld32(col0, v0);
                         tc_ld32(col0 + 32, v1);
                         tc_wait_ld();
-                        if (MODE == 0) {
-                            // D = -(S + bias) + 0.5 (f32): a survivor has D < 0.  Collect the 64 sign bits
-                            // with one funnel shift per element (four independent chains); survivors are rare.
-                            uint32_t ma = 0, mb = 0, mc = 0, md = 0;
 #pragma unroll
-                            for (int j = 0; j < 16; ++j) {
-                                ma = __funnelshift_l(v0[j], ma, 1);
-                                mb = __funnelshift_l(v0[16 + j], mb, 1);
-                                mc = __funnelshift_l(v1[j], mc, 1);
-                                md = __funnelshift_l(v1[16 + j], md, 1);
-                            }
-                            // element e of this half-block sits at bit 63 - e
-                            uint64_t mask = ((uint64_t)((ma << 16) | mb) << 32) | (uint64_t)((mc << 16) | md);
-                            if (!alive) mask = 0;
-                            const uint32_t q0 = qbase + half * 64;
-                            while (__any_sync(0xffffffffu, mask != 0)) {
-                                const bool has = mask != 0;
-                                const uint32_t m = __ballot_sync(0xffffffffu, has);
-                                if (has) {
-                                    const int e = __clzll((long long)mask);
-                                    mask &= ~(0x8000000000000000ull >> e);
-                                    const uint32_t slot = my_count + __popc(m & lane_lt);
-                                    if (slot < rec_cap) my_list[slot] = make_uint2(row, q0 + e);
-                                }
-                                my_count += __popc(m);
-                            }
-                        } else {
+                        for (int j = 0; j < 32; ++j) { v[j] = v0[j]; v[32 + j] = v1[j]; }
+                    } else {
 #pragma unroll
-                            for (int j = 0; j < 64; ++j) {
-                                const uint32_t q = qbase + half * 64 + j;
-                                const uint32_t ql = qloc + half * 64 + j;
-                                const int32_t dv = (int32_t)(__uint_as_float(j < 32 ? v0[j & 31] : v1[j & 31]) - 0.5f);   // -(S + bias)
-                                // hamming = popc(q) - S = popc(q) + bias + (D - 0.5)
-                                if (q < nq && in_range && row < n_rows)
-                                    dist_out[(size_t)q * dist_stride + row] = (uint32_t)((int32_t)s_pop[ql] + s_bias[ql] + dv);
-                            }
-                        }
+                        for (int j = 0; j < 64; ++j) v[j] = 0x3f800000u;
                     }
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(acc_empty(b));
+                    if (lane == 0) mbar_arrive(acc_empty(b));      // the values are in registers: the buffer is free
+                    TC_PROF_ADD(2);
+                    if (MODE == 0) {
+                        // D = -(S + v) + 0.5 (f32): a survivor has D < 0, i.e. its sign bit set.  Survivors are
+                        // rare: OR the raw bits of each quarter (16 columns) with three-input LOP3s and look
+                        // closer only where some lane of the warp saw a sign bit.
+                        uint64_t mask = 0;                         // element e of this half-block sits at bit 63 - e
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            uint32_t o = v[16 * k];
+#pragma unroll
+                            for (int j = 1; j < 15; j += 2) o |= v[16 * k + j] | v[16 * k + j + 1];
+                            o |= v[16 * k + 15];
+                            if (__any_sync(0xffffffffu, (int32_t)o < 0 && alive)) {
+                                uint32_t mk = 0;
+#pragma unroll
+                                for (int j = 0; j < 16; ++j) mk = __funnelshift_l(v[16 * k + j], mk, 1);
+                                if (alive) mask |= (uint64_t)mk << (48 - 16 * k);
+                            }
+                        }
+                        // every lane files its own survivors (usually none, rarely more than one)
+                        while (__any_sync(0xffffffffu, mask != 0)) {
+                            const bool has = mask != 0;
+                            const uint32_t m = __ballot_sync(0xffffffffu, has);
+                            if (has) {
+                                const int e = __clzll((long long)mask);
+                                mask &= ~(0x8000000000000000ull >> e);
+                                const uint32_t at = (q_head + q_count + __popc(m & lane_lt)) % TC_QUEUE;
+                                q_row[at] = row;
+                                q_q[at] = qbase_q + (uint32_t)e;
+                            }
+                            q_count += __popc(m);
+                            if (q_count >= 32) flush(32);
+                        }
+                    } else if (MODE == 1) {
+#pragma unroll
+                        for (int j = 0; j < 64; ++j) {
+                            const uint32_t q = qbase_q + j;
+                            const int32_t dv = (int32_t)(__uint_as_float(v[j]) - 0.5f);   // -(S + v), v = 0
+                            if (q < nq && in_range && row < n_rows)
+                                dist_out[(size_t)q * dist_stride + row] = (uint32_t)(s_base[qloc + j] + dv);
+                        }
+                    } else {
+                        // minimum of D over the tile's live rows, per column.  D is an integer in
+                        // [-K, K]: (D + 1.5 * 2^23) keeps it in the mantissa, so the u32 order of the
+                        // sums is the order of D and one redux.min per column does it.
+                        int32_t keep[2] = {TC_TILEMIN_NONE, TC_TILEMIN_NONE};
+#pragma unroll
+                        for (int j = 0; j < 64; ++j) {
+                            const uint32_t u = alive ? __float_as_uint(__uint_as_float(v[j]) + 12582912.0f) : 0xffffffffu;
+                            const uint32_t mn = __reduce_min_sync(0xffffffffu, u);
+                            if ((j & 31) == lane)
+                                keep[j >> 5] = mn == 0xffffffffu ? TC_TILEMIN_NONE : (int32_t)(mn - 0x4B400000u);
+                        }
+                        // a tile past the end reports "no live row"
+                        const size_t t_idx = (size_t)(g * 4u + (uint32_t)(ew & 3));
+#pragma unroll
+                        for (int i = 0; i < 2; ++i) tilemin[t_idx * nq_pad + qbase_q + i * 32 + lane] = keep[i];
+                    }
                     TC_PROF_ADD(1);
                 }
             }
         }
-        if (MODE == 0 && lane == 0) {
-            list_counts[blockIdx.x * TC_EPI_WARPS + ew] = min(my_count, rec_cap);
-            if (my_count > rec_cap) *overflow = 1u;
+        if (MODE == 0) {
+            if (q_count) flush(q_count);
+            if (lane == 0) {
+                list_counts[blockIdx.x * TC_EPI_WARPS + ew] = min(n_written, rec_cap);
+                if (n_written > rec_cap) *overflow = 1u;
+            }
         }
         if (prof && blockIdx.x == 0 && threadIdx.x == 128)
-            for (int i = 0; i < 2; ++i) prof[4 + i] = pw[i];
+            for (int i = 0; i < 4; ++i) prof[4 + i] = pw[i];
     } else {
-        // ===================== query loader (TMA) + MMA issuer: warp 8, one elected lane issues =====================
+        // ===================== query loader (TMA) + MMA issuer: one elected lane issues =====================
         uint32_t bfull_phase = 0, bfree_phase = 0;
-        uint32_t ready_phase[2] = {0, 0};
-        uint32_t empty_phase[NBUF];               // first use of each accumulator buffer passes
-#pragma unroll
-        for (int b = 0; b < NBUF; ++b) empty_phase[b] = 1u;
-        uint32_t it = 0;
+        uint32_t it = 0;                          // running accumulator-block counter
+        uint32_t p = 0;                           // running phase counter (as in the expanders)
         bool first_item = true;
         const long long t_begin = prof ? clock64() : 0;
         unsigned long long ns_begin = 0;
         if (prof) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns_begin));
+        const uint32_t smem_base = smem_u32(smem);
         for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x) {
             uint32_t qb0, nb, g_lo, g_hi;
             item_range(item, qb0, nb, g_lo, g_hi);
@@ -510,7 +737,7 @@ tc_scan_kernel(const uint4* __restrict__ codes, const uint32_t* __restrict__ liv
                 mbar_expect_tx(b_full, nb * QBLOCK_BYTES);
                 for (uint32_t blk = 0; blk < nb; ++blk) {
                     const int8_t* src = qexp + (size_t)(qb0 + blk) * QBLOCK_BYTES;
-                    const uint32_t dst = smem_u32(smem + blk * QBLOCK_BYTES);
+                    const uint32_t dst = smem_base + blk * QBLOCK_BYTES;
                     for (uint32_t off = 0; off < QBLOCK_BYTES; off += TC_STAGE_BYTES)
                         tma_bulk_g2s(dst + off, src + off, min((uint32_t)TC_STAGE_BYTES, QBLOCK_BYTES - off), b_full);
                 }
@@ -518,43 +745,47 @@ tc_scan_kernel(const uint4* __restrict__ codes, const uint32_t* __restrict__ liv
             __syncwarp();
             { TC_PROF_T0(); mbar_wait(b_full, bfull_phase); TC_PROF_ADD(3); }
             bfull_phase ^= 1u;
-            for (uint32_t g = g_lo; g < g_hi; ++g) {
+            for (uint32_t g = g_lo; g < g_hi; ++g, p += PH) {
                 for (uint32_t blk = 0; blk < nb; ++blk, ++it) {
                     const uint32_t b = it % NBUF;
                     const bool last_blk = blk + 1 == nb;
-                    { TC_PROF_T0(); mbar_wait(acc_empty(b), empty_phase[b]); TC_PROF_ADD(0); }
-                    empty_phase[b] ^= 1u;
+                    { TC_PROF_T0(); mbar_wait(acc_empty(b), ((it / NBUF) & 1u) ^ 1u); TC_PROF_ADD(0); }
                     tc_fence_after();
-                    const uint64_t bdesc0 = tc_smem_desc(smem_u32(smem + blk * QBLOCK_BYTES), 128, 1024);
+                    const uint64_t bdesc0 = tc_smem_desc(smem_base + blk * QBLOCK_BYTES, 128, 1024);
                     const uint32_t d_addr = tmem_d + b * TC_NQ;
 #pragma unroll
-                    for (int ks = 0; ks < NCHUNK; ++ks) {              // one code chunk = 64 K bytes = two K=64 MMAs
-                        const int ph = ks / SC, h = ph & 1, kc = ks % SC;   // phase, slot, chunk in slot
-                        if (blk == 0 && kc == 0) {
-                            { TC_PROF_T0(); mbar_wait(a_ready(h), ready_phase[h]); TC_PROF_ADD(1 + h); }
-                            ready_phase[h] ^= 1u;
+                    for (int ph = 0; ph < PH; ++ph) {
+                        const uint32_t s = (p + ph) % NSLOT;
+                        if (blk == 0) {
+                            { TC_PROF_T0(); mbar_wait(a_ready(s), ((p + ph) / NSLOT) & 1u); TC_PROF_ADD(1); }
                             tc_fence_after();
                         }
                         if (elect_one()) {
+                            const uint32_t a_addr = tmem_a + s * SLOT_COLS;
 #pragma unroll
-                            for (int j = 0; j < 2; ++j)                 // the address field counts 16-byte units
-                                tc_mma_mxf4_ts(d_addr, tmem_a + (uint32_t)(h * SC * CHUNK_COLS + (kc * 2 + j) * 8),
-                                               bdesc0 + (uint64_t)(((ks / 2) * TC_STAGE_BYTES + ((ks % 2) * 4 + j * 2) * 128) >> 4),
-                                               IDESC, tmem_sf_one, tmem_sf_one, (ks | j) != 0 ? 1u : 0u);
+                            for (int kc = 0; kc < SC; ++kc) {           // one code chunk = 64 K bytes = two K=64 MMAs
+                                const int ks = ph * SC + kc;
+                                if (ks < NCHUNK) {
+#pragma unroll
+                                    for (int j = 0; j < 2; ++j)         // the address field counts 16-byte units
+                                        tc_mma_mxf4_ts(d_addr, a_addr + (uint32_t)((kc * 2 + j) * 8),
+                                                       bdesc0 + (uint64_t)(((ks / 2) * TC_STAGE_BYTES + ((ks % 2) * 4 + j * 2) * 128) >> 4),
+                                                       IDESC, tmem_sf_one, tmem_sf_one, (ks | j) != 0 ? 1u : 0u);
+                                }
+                            }
                             // this slot of A may be rewritten once the MMAs issued so far retire
-                            if (last_blk && kc == SC - 1 && ks != NCHUNK - 1) tc_commit(a_free(h));
+                            if (last_blk) tc_commit(a_free(s));
+                            if (ph == PH - 1) {
+                                // bias: D += 1.0(128 x 64, scales 16 | 1) * digits(128 queries x 64) = -v + 0.5
+                                if (MODE != 2)
+                                    tc_mma_mxf4_ts(d_addr, tmem_a + A_COLS,
+                                                   tc_smem_desc(smem_base + blk * QBLOCK_BYTES + tc_subblocks(NCHUNK) * TC_STAGE_BYTES, 128, 256),
+                                                   IDESC, tmem_sf_bias, tmem_sf_one, 1u);
+                                tc_commit(acc_full(b));
+                            }
                         }
                         __syncwarp();
                     }
-                    if (elect_one()) {
-                        // bias: D += 1.0(128 x 64, scales 16 | 1) * digits(128 queries x 64) = -v + 0.5
-                        tc_mma_mxf4_ts(d_addr, tmem_a + A_COLS,
-                                       tc_smem_desc(smem_u32(smem + blk * QBLOCK_BYTES + tc_subblocks(NCHUNK) * TC_STAGE_BYTES), 128, 256),
-                                       IDESC, tmem_sf_bias, tmem_sf_one, 1u);
-                        if (last_blk) tc_commit(a_free(((NCHUNK - 1) / SC) & 1));   // the last phase's slot
-                        tc_commit(acc_full(b));
-                    }
-                    __syncwarp();
                 }
             }
             if (elect_one()) tc_commit(b_free);
@@ -574,20 +805,20 @@ tc_scan_kernel(const uint4* __restrict__ codes, const uint32_t* __restrict__ liv
     __syncthreads();
     if (warp == MMA_WARP) {
         __syncwarp();
-        tc_dealloc(tmem, TC_TMEM_COLS);
+        tc_dealloc(0u, TC_TMEM_COLS);
     }
 }
 
-// Warp-private survivor records (row, query) -> per-query candidate buffers, same contract as
+// Warp-private survivor records (row, query) -> per-query candidate buffers, the contract of
 // scan_kernel: key = hamming << 32 | row.  The distance is recomputed from the codes (xor + popc
 // over nchunk*4 words, served from L2) — cheaper than carrying it through the epilogue.
-// grid = (TC_SCATTER_X, number of lists = 4 x scan CTAs), each CTA strides over its list.
-constexpr int TC_SCATTER_X = 4;
-__global__ void tc_scatter_kernel(const uint2* __restrict__ recs, uint32_t rec_cap,
-                                  const uint32_t* __restrict__ list_counts, const uint4* __restrict__ codes,
-                                  int nchunk, const uint32_t* __restrict__ qpack, int qs,
-                                  uint32_t* __restrict__ cnt, uint64_t* __restrict__ buf, uint32_t cap,
-                                  uint32_t* __restrict__ overflow) {
+// grid = (TC_SCATTER_X, number of lists = 8 x scan CTAs), each CTA strides over its list.
+constexpr int TC_SCATTER_X = 2;
+__global__ void __launch_bounds__(256)
+tc_scatter_kernel(const uint2* __restrict__ recs, uint32_t rec_cap, const uint32_t* __restrict__ list_counts,
+                  const uint4* __restrict__ codes, int nchunk, const uint32_t* __restrict__ qpack, int qs,
+                  uint32_t* __restrict__ cnt, uint64_t* __restrict__ buf, uint32_t cap,
+                  uint32_t* __restrict__ overflow) {
     const uint32_t n_list = list_counts[blockIdx.y];
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_list; i += gridDim.x * blockDim.x) {
         const uint2 r = recs[(size_t)blockIdx.y * rec_cap + i];

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define GVDB_ABI_VERSION 4u
+#define GVDB_ABI_VERSION 5u
 
 #if defined(__GNUC__)
 #define GVDB_API __attribute__((visibility("default")))
@@ -354,14 +354,15 @@ typedef struct gvdb_profile {
     double select_ms, rescore_ms, topk_ms, prep_ms, flat_ms, merge_ms;
     uint64_t tc_launches;     /* tc_scan_kernel (tcgen05) launches */
     double tc_ms;             /* summed tc_scan_kernel device time */
-    double tc_macs;           /* int8 multiply-accumulates those launches performed:
-                                 rows_in_segment * padded queries * code bits (+ the bias slice) */
+    double tc_macs;           /* algorithmic multiply-accumulates of those launches:
+                                 rows * padded queries * code bits (one per code bit and pair) */
     double tc_bytes;          /* code bytes those launches read: rows * code_bytes_per_row * query slices */
-    double scatter_ms;        /* tc_scatter_kernel (survivor records -> candidate buffers) */
+    double scatter_ms;        /* tc_scatter_kernel (survivor records -> candidate keys) */
     uint64_t optimistic_reruns; /* calls repeated because the device refuted the single-pass threshold guess */
     uint64_t overflow_fallbacks; /* calls answered by the cut by counting after a candidate buffer overflowed */
     double exchange_ms;       /* peer exchange: push + signal kernels (gvdb_search_exchange_device) */
     double exchange_wait_ms;  /* peer exchange: time spent waiting for the peers' flags (rank skew included) */
+    double sample_ms;         /* tc_scan_kernel in sample mode + tc_tau_kernel (single-pass threshold estimate) */
 } gvdb_profile;
 GVDB_API gvdb_status gvdb_profile_enable(gvdb_index* h, int32_t on);
 GVDB_API gvdb_status gvdb_profile_read(gvdb_index* h, gvdb_profile* out, int32_t reset);

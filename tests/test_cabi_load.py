@@ -28,7 +28,7 @@ def test_header_symbols_all_exported(built):
 def test_abi_version_and_rescore_count(built):
     from grape_vector_db_b200 import _ffi
     L = _ffi.lib()
-    assert L.gvdb_abi_version() == 4
+    assert L.gvdb_abi_version() == 5
     assert L.gvdb_rescore_count(10_000, 0.1) == 1000
     assert L.gvdb_rescore_count(7, 0.1) == 0
     assert L.gvdb_rescore_count(10, 2.0) == 10

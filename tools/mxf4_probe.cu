@@ -27,7 +27,8 @@ __device__ __forceinline__ void mma_mxf4_ts(uint32_t d, uint32_t a_tmem, uint64_
 // mode 0: SS check, 1: TS check, 2: SS timing, 3: TS timing
 __global__ void __launch_bounds__(128, 1) probe_kernel(const uint8_t* __restrict__ a_bytes, const uint8_t* __restrict__ b_bytes,
                                                         float* __restrict__ d_out, int mode, int niter, long long* clk_out,
-                                                        uint32_t sfword_a = 0x7F7F7F7Fu, uint32_t sfword_b = 0x7F7F7F7Fu, uint32_t sf_id_bits = 0) {
+                                                        uint32_t sfword_a = 0x7F7F7F7Fu, uint32_t sfword_b = 0x7F7F7F7Fu, uint32_t sf_id_bits = 0,
+                                                        uint32_t nprobe = 128, uint32_t nacc = 2) {
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ __align__(8) uint64_t bar;
     __shared__ uint32_t s_tmem;
@@ -72,6 +73,16 @@ __global__ void __launch_bounds__(128, 1) probe_kernel(const uint8_t* __restrict
                 else mma_mxf4_ss(tmem, adesc, bdesc, IDESC_MXF4 | sf_id_bits, sfa, sfb, 0u);
             }
             __syncwarp();
+        } else if (mode == 4) {
+            // issue rate for other N (timing only: B rows beyond the 4 KB that were filled read whatever follows in smem)
+            const uint32_t idesc_n = (1u << 7) | (1u << 10) | ((nprobe >> 3) << 17) | (1u << 23) | ((128u >> 4) << 24);
+            if (elect_one()) {
+                for (int it = 0; it < niter; it += 8) {
+#pragma unroll
+                    for (int u = 0; u < 8; ++u)
+                        mma_mxf4_ts(tmem + (u % nacc) * nprobe, tmem + 400, bdesc, idesc_n, sfa, sfb, 1u);
+                }
+            }
         } else if (elect_one()) {
             for (int it = 0; it < niter; it += 8) {
 #pragma unroll
@@ -168,6 +179,19 @@ int main() {
         long long clk; CK(cudaMemcpy(&clk, dclk, 8, cudaMemcpyDeviceToHost));
         printf("%s rate: %.1f clk per M128 x N128 x K64 MMA = %.0f MAC/clk/SM\n", (mode & 1) ? "TS" : "SS", (double)clk / niter,
                128.0 * 128 * 64 * niter / clk);
+    }
+    // issue rate against N (accumulators of N columns; A, scales at columns >= 384, so N * nacc <= 384)
+    for (uint32_t np : {64u, 128u, 192u, 256u}) {
+        for (uint32_t nacc : {1u, 2u}) {
+            if (np * nacc > 384) continue;
+            const int niter = 4000;
+            for (int rep = 0; rep < 2; ++rep)
+                probe_kernel<<<148, 128, 16384>>>(da, db, dd, 4, niter, dclk, 0x7F7F7F7Fu, 0x7F7F7F7Fu, 0, np, nacc);
+            CK(cudaDeviceSynchronize());
+            long long clk; CK(cudaMemcpy(&clk, dclk, 8, cudaMemcpyDeviceToHost));
+            printf("TS rate N=%u, %u accumulator(s): %.1f clk per M128 x N%u x K64 MMA = %.0f MAC/clk/SM\n", np, nacc, (double)clk / niter, np,
+                   128.0 * np * 64 * niter / clk);
+        }
     }
     printf("OK\n");
     return 0;

@@ -50,24 +50,26 @@ int main(int argc, char** argv) {
         h_qpack[(size_t)q * qs + NCHUNK * 4] = TAU_ALL;
         for (int w = 1; w < 4; ++w) h_qpack[(size_t)q * qs + NCHUNK * 4 + w] = 0;
     }
-    uint4* d_codes; uint32_t *d_qpack, *d_live, *d_ref, *d_tc, *d_qpop, *d_cnt, *d_flag; int8_t* d_qexp; int32_t* d_qbias; uint2* d_recs; uint32_t* d_ctacnt; uint64_t* d_buf;
+    uint4* d_codes; uint32_t *d_qpack, *d_live, *d_ref, *d_tc, *d_qpop, *d_cnt, *d_flag; int8_t* d_qexp; int32_t* d_qbase; uint64_t* d_buf; int32_t* d_tilemin; uint2* d_recs; uint32_t* d_lc;
     CK(cudaMalloc(&d_codes, code_words * 4)); CK(cudaMalloc(&d_qpack, h_qpack.size() * 4)); CK(cudaMalloc(&d_live, ntiles * 4));
     const bool check = !timing;
     size_t dist_bytes = check ? (size_t)nq * n_rows * 4 : 4;
     CK(cudaMalloc(&d_ref, dist_bytes)); CK(cudaMalloc(&d_tc, dist_bytes));
-    CK(cudaMalloc(&d_qexp, (size_t)(nq_pad / TC_NQ) * tc_qblock_bytes(NCHUNK))); CK(cudaMalloc(&d_qbias, nq_pad * 4)); CK(cudaMalloc(&d_qpop, nq_pad * 4));
-    const uint32_t cap = 8192; const uint32_t rec_cap = 1u << 17;
-    CK(cudaMalloc(&d_recs, (size_t)148 * TC_EPI_WARPS * rec_cap * 8)); CK(cudaMalloc(&d_ctacnt, 148 * TC_EPI_WARPS * 4)); CK(cudaMemset(d_ctacnt, 0, 148 * TC_EPI_WARPS * 4));
-    CK(cudaMalloc(&d_cnt, nq_pad * 4 * CNT_STRIDE)); CK(cudaMalloc(&d_flag, 4)); CK(cudaMalloc(&d_buf, (size_t)nq_pad * cap * 8));
+    CK(cudaMalloc(&d_qexp, (size_t)(nq_pad / TC_NQ) * tc_qblock_bytes(NCHUNK))); CK(cudaMalloc(&d_qbase, nq_pad * 4)); CK(cudaMalloc(&d_qpop, nq_pad * 4));
+    const uint32_t cap = 8192;
+    const uint32_t rec_cap = 1u << 17;
+    CK(cudaMalloc(&d_recs, (size_t)148 * TC_EPI_WARPS * rec_cap * 8)); CK(cudaMalloc(&d_lc, 148 * TC_EPI_WARPS * 4)); CK(cudaMemset(d_lc, 0, 148 * TC_EPI_WARPS * 4));
+    CK(cudaMalloc(&d_cnt, nq_pad * 4 * CNT_STRIDE)); CK(cudaMalloc(&d_flag, 256)); CK(cudaMalloc(&d_buf, (size_t)nq_pad * cap * 8));
     CK(cudaMemcpy(d_codes, h_codes.data(), code_words * 4, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(d_qpack, h_qpack.data(), h_qpack.size() * 4, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(d_live, h_live.data(), ntiles * 4, cudaMemcpyHostToDevice));
-    CK(cudaMemset(d_tc, 0xff, dist_bytes)); CK(cudaMemset(d_cnt, 0, nq_pad * 4 * CNT_STRIDE)); CK(cudaMemset(d_flag, 0, 4));
+    CK(cudaMemset(d_tc, 0xff, dist_bytes)); CK(cudaMemset(d_cnt, 0, nq_pad * 4 * CNT_STRIDE)); CK(cudaMemset(d_flag, 0, 256));
 
     tc_expand_queries_kernel<<<nq_pad, 64>>>(d_qpack, qs, NCHUNK, nq, nq_pad, d_qexp, d_qpop);
     CK(cudaGetLastError());
     int sms = 0; CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0));
     uint32_t ngroups = (ntiles + 3) / 4;
+    CK(cudaMalloc(&d_tilemin, (size_t)ngroups * 4 * nq_pad * 4));
     const uint32_t qb_item = argc > 6 ? (uint32_t)atoi(argv[6]) : (uint32_t)TC_QBLOCKS;
     const uint32_t n_qsl = (nq_pad / TC_NQ + qb_item - 1) / qb_item;
     uint32_t n_rsl = argc > 5 ? atoi(argv[5]) : 0;
@@ -78,11 +80,11 @@ int main(int argc, char** argv) {
     printf("split: %u query slices x %u row slices, grid %u\n", n_qsl, n_rsl, grid);
     if (check) {
         CK(cudaFuncSetAttribute(tc_scan_kernel<NCHUNK, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        tc_bias_kernel<<<(nq_pad + 127) / 128, 128>>>(d_qpack, qs, NCHUNK, d_qpop, nq, nq_pad, d_qexp, d_qbias, 1);
+        tc_bias_kernel<<<(nq_pad + 7) / 8, 256>>>(d_qpack, qs, NCHUNK, d_qpop, nq, nq_pad, d_qexp, d_qbase, 1);
         ref_kernel<NCHUNK><<<(ntiles + 7) / 8, 256>>>(d_codes, ntiles, d_qpack, qs, nq, d_ref, n_rows, n_rows);
         CK(cudaGetLastError());
-        tc_scan_kernel<NCHUNK, 1><<<grid, TC_THREADS, smem>>>(d_codes, d_live, 0, ntiles, d_qexp, d_qpop, d_qbias, nq, nq_pad, n_qsl, n_rsl, qb_item,
-                                                             d_recs, rec_cap, d_ctacnt, d_flag, d_tc, n_rows, n_rows);
+        tc_scan_kernel<NCHUNK, 1><<<grid, TC_THREADS, smem>>>(d_codes, d_live, 0, ntiles, ngroups, 1, d_qexp, d_qbase, nq, nq_pad, n_qsl, n_rsl, qb_item,
+                                                             nullptr, 0, nullptr, d_flag, d_tc, n_rows, n_rows, nullptr);
         CK(cudaGetLastError());
         CK(cudaDeviceSynchronize());
         std::vector<uint32_t> a((size_t)nq * n_rows), b((size_t)nq * n_rows);
@@ -96,18 +98,42 @@ int main(int argc, char** argv) {
             for (int i = 0; i < 8; ++i) printf("  [%d] ref=%u tc=%u\n", i, a[i], b[i]);
             return 1;
         }
+        // ---- sample mode (MODE 2): tile minima of D = hamming - popc(q) over every tile ----
+        std::vector<uint32_t> h_pop(nq_pad);
+        CK(cudaMemcpy(h_pop.data(), d_qpop, nq_pad * 4, cudaMemcpyDeviceToHost));
+        CK(cudaFuncSetAttribute(tc_scan_kernel<NCHUNK, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        tc_scan_kernel<NCHUNK, 2><<<grid, TC_THREADS, smem>>>(d_codes, d_live, 0, ntiles, ngroups, 1, d_qexp, d_qbase, nq, nq_pad, n_qsl, n_rsl, qb_item,
+                                                             nullptr, 0, nullptr, d_flag, nullptr, 0, n_rows, d_tilemin);
+        CK(cudaGetLastError());
+        CK(cudaDeviceSynchronize());
+        {
+            std::vector<int32_t> tm((size_t)ngroups * 4 * nq_pad);
+            CK(cudaMemcpy(tm.data(), d_tilemin, tm.size() * 4, cudaMemcpyDeviceToHost));
+            size_t badt = 0;
+            for (uint32_t t = 0; t < ngroups * 4; ++t)
+                for (uint32_t q = 0; q < nq; ++q) {
+                    int32_t want = TC_TILEMIN_NONE;
+                    for (uint32_t l = 0; l < 32; ++l) {
+                        const uint64_t r = (uint64_t)t * 32 + l;
+                        if (r < n_rows) want = std::min<int32_t>(want, (int32_t)a[(size_t)q * n_rows + r] - (int32_t)h_pop[q]);
+                    }
+                    if (tm[(size_t)t * nq_pad + q] != want) { if (!badt) printf("tile-min mismatch t=%u q=%u got=%d want=%d\n", t, q, tm[(size_t)t * nq_pad + q], want); ++badt; }
+                }
+            printf("sample-mode check: %u tiles x %u queries, mismatches=%zu\n", ngroups * 4, nq, badt);
+            if (badt) return 1;
+        }
         // ---- search mode (MODE 0): survivors of a finite threshold must be exactly {ham < tau} ----
-        const uint32_t tau = 352;
+        const uint32_t tau = NCHUNK * 64 - 32;
         for (uint32_t q = 0; q < nq; ++q) h_qpack[(size_t)q * qs + NCHUNK * 4] = (q % 7 == 3) ? TAU_ALL : tau + (q % 5);
         CK(cudaMemcpy(d_qpack, h_qpack.data(), h_qpack.size() * 4, cudaMemcpyHostToDevice));
-        tc_bias_kernel<<<(nq_pad + 127) / 128, 128>>>(d_qpack, qs, NCHUNK, d_qpop, nq, nq_pad, d_qexp, d_qbias, 0);
+        tc_bias_kernel<<<(nq_pad + 7) / 8, 256>>>(d_qpack, qs, NCHUNK, d_qpop, nq, nq_pad, d_qexp, d_qbase, 0);
         CK(cudaFuncSetAttribute(tc_scan_kernel<NCHUNK, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         const uint32_t bigcap = 65536;
         uint64_t* d_buf2; CK(cudaMalloc(&d_buf2, (size_t)nq_pad * bigcap * 8));
         CK(cudaMemset(d_cnt, 0, nq_pad * 4 * CNT_STRIDE));
-        tc_scan_kernel<NCHUNK, 0><<<grid, TC_THREADS, smem>>>(d_codes, d_live, 0, ntiles, d_qexp, d_qpop, d_qbias, nq, nq_pad, n_qsl, n_rsl, qb_item,
-                                                             d_recs, rec_cap, d_ctacnt, d_flag, nullptr, 0, n_rows);
-        tc_scatter_kernel<<<dim3(TC_SCATTER_X, grid * TC_EPI_WARPS), 256>>>(d_recs, rec_cap, d_ctacnt, d_codes, NCHUNK, d_qpack, qs, d_cnt, d_buf2, bigcap, d_flag);
+        tc_scan_kernel<NCHUNK, 0><<<grid, TC_THREADS, smem>>>(d_codes, d_live, 0, ntiles, ngroups, 1, d_qexp, d_qbase, nq, nq_pad, n_qsl, n_rsl, qb_item,
+                                                             d_recs, rec_cap, d_lc, d_flag, nullptr, 0, n_rows, nullptr);
+        tc_scatter_kernel<<<dim3(TC_SCATTER_X, grid * TC_EPI_WARPS), 256>>>(d_recs, rec_cap, d_lc, d_codes, NCHUNK, d_qpack, qs, d_cnt, d_buf2, bigcap, d_flag);
         CK(cudaGetLastError());
         CK(cudaDeviceSynchronize());
         std::vector<uint32_t> h_cnt_s((size_t)nq_pad * CNT_STRIDE), h_cnt(nq_pad);
@@ -131,38 +157,48 @@ int main(int argc, char** argv) {
         printf("search-mode check: %zu survivors, bad queries=%zu\n", total, badq);
         if (badq) return 1;
     } else {
-        // timing in search mode with a threshold that lets nothing through (tau = 0)
-        const uint32_t tau_t = argc > 4 ? atoi(argv[4]) : 200;   // 200: no survivors; 352: ~1%; 335: ~2e-4
+        // timing in search mode; tau (argv[4]) relative to NCHUNK*64: 768 bits: 200 no survivors, 352 ~1%, 335 ~2e-4
+        const uint32_t tau_t = argc > 4 ? atoi(argv[4]) : 200;
         for (uint32_t q = 0; q < nq; ++q) h_qpack[(size_t)q * qs + NCHUNK * 4] = tau_t;
         CK(cudaMemcpy(d_qpack, h_qpack.data(), h_qpack.size() * 4, cudaMemcpyHostToDevice));
-        tc_bias_kernel<<<(nq_pad + 127) / 128, 128>>>(d_qpack, qs, NCHUNK, d_qpop, nq, nq_pad, d_qexp, d_qbias, 0);
+        tc_bias_kernel<<<(nq_pad + 7) / 8, 256>>>(d_qpack, qs, NCHUNK, d_qpop, nq, nq_pad, d_qexp, d_qbase, 0);
         CK(cudaFuncSetAttribute(tc_scan_kernel<NCHUNK, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
         for (int rep = 0; rep < 3; ++rep)
-            tc_scan_kernel<NCHUNK, 0><<<grid, TC_THREADS, smem>>>(d_codes, d_live, 0, ntiles, d_qexp, d_qpop, d_qbias, nq, nq_pad, n_qsl, n_rsl, qb_item,
-                                                                 d_recs, rec_cap, d_ctacnt, d_flag, nullptr, 0, n_rows);
+            tc_scan_kernel<NCHUNK, 0><<<grid, TC_THREADS, smem>>>(d_codes, d_live, 0, ntiles, ngroups, 1, d_qexp, d_qbase, nq, nq_pad, n_qsl, n_rsl, qb_item,
+                                                                 d_recs, rec_cap, d_lc, d_flag, nullptr, 0, n_rows, nullptr);
         CK(cudaDeviceSynchronize());
         const int reps = 10;
         unsigned long long* d_prof; CK(cudaMalloc(&d_prof, 16 * 8)); CK(cudaMemset(d_prof, 0, 16 * 8));
-        for (int dbg : {0, 1}) {
+        for (int dbg : {0, 4, 1}) {
+        // the cycle accounting costs time (clock reads in every warp): one launch with it, the timed ones without
+        cudaMemsetAsync(d_cnt, 0, nq_pad * 4 * CNT_STRIDE);
+        tc_scan_kernel<NCHUNK, 0><<<grid, TC_THREADS, smem>>>(d_codes, d_live, 0, ntiles, ngroups, 1, d_qexp, d_qbase, nq, nq_pad, n_qsl, n_rsl, qb_item,
+                                                             d_recs, rec_cap, d_lc, d_flag, nullptr, 0, n_rows, nullptr, dbg, d_prof);
         cudaEventRecord(e0);
         for (int rep = 0; rep < reps; ++rep) {
             cudaMemsetAsync(d_cnt, 0, nq_pad * 4 * CNT_STRIDE);
-            tc_scan_kernel<NCHUNK, 0><<<grid, TC_THREADS, smem>>>(d_codes, d_live, 0, ntiles, d_qexp, d_qpop, d_qbias, nq, nq_pad, n_qsl, n_rsl, qb_item,
-                                                                 d_recs, rec_cap, d_ctacnt, d_flag, nullptr, 0, n_rows, dbg, d_prof);
-            if (!(dbg & 1)) tc_scatter_kernel<<<dim3(TC_SCATTER_X, grid * TC_EPI_WARPS), 256>>>(d_recs, rec_cap, d_ctacnt, d_codes, NCHUNK, d_qpack, qs, d_cnt, d_buf, cap, d_flag);
+            tc_scan_kernel<NCHUNK, 0><<<grid, TC_THREADS, smem>>>(d_codes, d_live, 0, ntiles, ngroups, 1, d_qexp, d_qbase, nq, nq_pad, n_qsl, n_rsl, qb_item,
+                                                                 d_recs, rec_cap, d_lc, d_flag, nullptr, 0, n_rows, nullptr, dbg, nullptr);
         }
         cudaEventRecord(e1);
+        cudaEvent_t e2; cudaEventCreate(&e2);
+        tc_scatter_kernel<<<dim3(TC_SCATTER_X, grid * TC_EPI_WARPS), 256>>>(d_recs, rec_cap, d_lc, d_codes, NCHUNK, d_qpack, qs, d_cnt, d_buf, cap, d_flag);
+        cudaEventRecord(e2);
         CK(cudaDeviceSynchronize());
         float ms = 0; cudaEventElapsedTime(&ms, e0, e1); ms /= reps;
+        float ms_sc = 0; cudaEventElapsedTime(&ms_sc, e1, e2);
+        { std::vector<uint32_t> lc(grid * TC_EPI_WARPS); CK(cudaMemcpy(lc.data(), d_lc, lc.size() * 4, cudaMemcpyDeviceToHost)); unsigned long long tot = 0; for (auto c : lc) tot += c;
+          printf("  survivors %llu (%.1f per query), scatter kernel %.3f ms\n", tot, (double)tot / nq, ms_sc); }
         double macs = (double)n_rows * nq_pad * NCHUNK * 128;
         unsigned long long hp[16]; CK(cudaMemcpy(hp, d_prof, 16 * 8, cudaMemcpyDeviceToHost));
         const double grp = (double)((ntiles + 3) / 4) / n_rsl * ((n_qsl * n_rsl + grid - 1) / grid);
-        printf("  per group (clk): expander: wait a_free lo %.0f hi %.0f  expand lo %.0f hi %.0f | epilogue: wait acc_full %.0f  work %.0f | mma: wait acc_empty %.0f  a_ready lo %.0f hi %.0f  b_full(total) %llu | total %.0f clk/group, SM clock %.0f MHz\n",
-               hp[0] / grp, hp[1] / grp, hp[2] / grp, hp[3] / grp, hp[4] / grp, hp[5] / grp, hp[8] / grp, hp[9] / grp, hp[10] / grp, hp[11],
+        printf("  per group (clk): expander: wait a_free %.0f  expand %.0f | epilogue(one warp): wait acc_full %.0f  work %.0f (loads + hand-back %.0f) | mma: wait acc_empty %.0f  a_ready %.0f  b_full(total) %llu | total %.0f clk/group, SM clock %.0f MHz\n",
+               hp[0] / grp, hp[2] / grp, hp[4] / grp, hp[5] / grp, hp[6] / grp, hp[8] / grp, hp[9] / grp, hp[11],
                hp[14] / grp, hp[15] ? 1e3 * (double)hp[14] / (double)hp[15] : 0.0);
-        printf("timing dbg=%d (1=no-epilogue 2=no-tma 8=ldtm-only): rows=%llu nq=%u  %.3f ms/launch  %.1f TMAC/s (int8)  = %.1f%% of 148 SMs x 8192 MAC/clk @1.965GHz\n",
-               dbg, (unsigned long long)n_rows, nq, ms, macs / ms / 1e9, 100.0 * macs / (ms * 1e-3) / (148.0 * 8192 * 1.965e9));
+        printf("timing dbg=%d (1=no-accumulator-reads 2=no-A-stores): rows=%llu nq=%u  %.3f ms/launch  %.1f TMAC/s = %.1f%% of 148 SMs x 16384 MAC/clk @1.965GHz\n",
+               dbg, (unsigned long long)n_rows, nq, ms, macs / ms / 1e9, 100.0 * macs / (ms * 1e-3) / (148.0 * 16384 * 1.965e9));
+        CK(cudaMemset(d_prof, 0, 16 * 8));
         }
         uint32_t flag = 0, c0 = 0; CK(cudaMemcpy(&flag, d_flag, 4, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(&c0, d_cnt, 4, cudaMemcpyDeviceToHost));
         printf("overflow=%u cnt[0]=%u\n", flag, c0);
