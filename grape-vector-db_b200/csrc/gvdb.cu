@@ -378,9 +378,14 @@ bool tc_supported(int nchunk) { return tc_supported_chunks(nchunk); }
 // Work split of one tcgen05 scan launch: items = query slices x row slices, one CTA per SM looping
 // over items.  Pick the row-slice count that fills whole waves of SMs.
 struct TcSplit { uint32_t qslices, rslices, grid, qb_item; };
-TcSplit tc_split(const gvdb_index* h, uint32_t ngroups, uint32_t nq_pad) {
+constexpr uint32_t kSampleMaxSlices = TC_TAU_MAX_TILES / 32;    // sample mode: 32 row classes per row slice
+TcSplit tc_split(const gvdb_index* h, uint32_t ngroups, uint32_t nq_pad, bool sample = false) {
     const uint32_t sms = (uint32_t)h->sm_count;
     const uint32_t nqb = nq_pad / TC_NQ;
+    if (sample) {      // one query block per item (the running minima live in registers), <= 128 row slices
+        const uint32_t r = std::max<uint32_t>(1, std::min<uint32_t>(std::min<uint32_t>(ngroups, kSampleMaxSlices), std::max<uint32_t>(1, sms / nqb)));
+        return TcSplit{nqb, r, (uint32_t)std::min<uint64_t>((uint64_t)nqb * r, sms), 1};
+    }
     uint32_t qb_max = (uint32_t)tc_qblocks(h->nchunk);
     uint32_t qb_min = 1;
     if (h->tc_qb_force) qb_min = qb_max = std::min<uint32_t>(qb_max, h->tc_qb_force);   // GVDB_TC_QB (tuning)
@@ -413,7 +418,7 @@ void launch_tc_scan(gvdb_index* h, Workspace* ws, cudaStream_t st, uint32_t tile
                     uint32_t ngroups, uint32_t group_stride, uint32_t nq, uint32_t nq_pad, uint32_t* cnt,
                     uint64_t* buf, uint32_t cap, uint32_t* overflow, uint32_t* dist_out, uint64_t dist_stride,
                     uint32_t expect_per_query = 0) {
-    const TcSplit sp = tc_split(h, ngroups, nq_pad);
+    const TcSplit sp = tc_split(h, ngroups, nq_pad, MODE == 2);
     const uint32_t grid = sp.grid;
     const uint32_t nlists = grid * TC_EPI_WARPS;
     const size_t smem = (size_t)tc_qblocks(h->nchunk) * tc_qblock_bytes(h->nchunk);
@@ -531,7 +536,8 @@ SinglePass plan_single_pass(const gvdb_index* h, uint32_t ntiles, uint32_t R, ui
     const uint32_t ngroups = (ntiles + 3) / 4;
     uint32_t n_s = std::min<uint32_t>(1024, std::max<uint32_t>(64, ngroups / h->sample_div));
     if (n_s >= ngroups) {                                     // the sample is the corpus
-        if (ngroups > 1024 || 2ull * R > 4ull * ngroups) return sp;
+        // the rows fall into at most min(ngroups, 128) x 32 classes: want R of them to be plenty
+        if (4ull * R > 32ull * std::min<uint32_t>(ngroups, kSampleMaxSlices)) return sp;
         sp = SinglePass{true, ngroups, 1, R};
         return sp;
     }
@@ -544,17 +550,35 @@ SinglePass plan_single_pass(const gvdb_index* h, uint32_t ntiles, uint32_t R, ui
         below += term;
         term *= x / (double)(m + 1);
     }
-    if (m >= 1024 || m > n_s) return sp;                      // m tiles out of 4 * n_s: collisions stay rare
+    if (m >= 1024 || m > 128) return sp;                      // m classes out of several hundred: collisions stay rare
     if ((double)m * ngroups / n_s > cap / 3.0) return sp;     // expected survivors per query
     sp = SinglePass{true, n_s, gstride, m};
     return sp;
+}
+
+// Final ordering fused into the rescoring kernel (rescore_topk_kernel): the caller's k-lists are written
+// by search_core itself and the record arrays only when asked for.  `done` reports whether the fused
+// kernel ran (it needs dim % 4 == 0 and a rescore count whose staging fits shared memory).
+struct FusedTopk {
+    uint32_t k = 0;
+    uint64_t* ids_out = nullptr;
+    float* scores_out = nullptr;
+    bool want_records = true;
+    bool done = false;
+};
+size_t rescore_topk_smem(int dim, uint32_t R) {
+    const uint32_t nwarps = (R + 31) / 32;
+    uint32_t n_eff = 64;
+    while (n_eff < R) n_eff <<= 1;
+    return ((size_t)dim + (size_t)nwarps * 2 * 32 * RT_STRIDE) * sizeof(float) + (size_t)n_eff * 8;
 }
 
 // Stage 1 + stage 2 for queries [0,nq) (device pointers): fills rec_* [nq][R].
 void search_core(gvdb_index* h, Workspace* ws, cudaStream_t st, const float* queries_dev,
                  uint32_t nq, uint32_t R, uint32_t* rec_ham, uint64_t* rec_ids, float* rec_score,
                  bool reset_overflow_flag = true, bool allow_optimistic = true, bool* used_optimistic = nullptr,
-                 uint64_t* keys_out = nullptr /* stage 1 only: hamming << 40 | global row, nq x R */) {
+                 uint64_t* keys_out = nullptr /* stage 1 only: hamming << 40 | global row, nq x R */,
+                 FusedTopk* fused = nullptr) {
     if (!keys_out && !h->rows_reachable()) need_all_rows(h);
     if (h->n_rows == 0) fail(GVDB_ERR_INDEX_NOT_BUILT, "index not built: search before any add");
     if (R == 0) fail(GVDB_ERR_INVALID_ARGUMENT, "rescore_count must be >= 1");
@@ -594,7 +618,7 @@ void search_core(gvdb_index* h, Workspace* ws, cudaStream_t st, const float* que
             // ---- single pass: prep -> sample (tile minima) -> thresholds -> one scan over all rows -> cut ----
             if (used_optimistic) *used_optimistic = true;
             tc_ensure_query_buffers(h, ws, nq_pad);
-            const uint32_t n_stiles = sp.n_sgroups * 4;
+            const uint32_t n_stiles = tc_split(h, sp.n_sgroups, nq_pad, true).rslices * 32;    // row classes of the sample
             ws->tilemin.ensure((size_t)n_stiles * nq_pad * 4);
             {
                 Timed t(h, ws, st, K_PREP);
@@ -612,9 +636,9 @@ void search_core(gvdb_index* h, Workspace* ws, cudaStream_t st, const float* que
             {
                 Timed t(h, ws, st, K_SAMPLE);
                 static std::atomic<uint64_t> attr_done{0};
-                ensure_dyn_smem(attr_done, tc_tau_kernel, TC_TAU_WARPS * TC_TAU_MAX_TILES * 2);
+                ensure_dyn_smem(attr_done, tc_tau_kernel, TC_TAU_WARPS * (TC_TAU_MAX_TILES + 2) * 2);
                 tc_tau_kernel<<<(nq_pad + TC_TAU_WARPS - 1) / TC_TAU_WARPS, 32 * TC_TAU_WARPS,
-                                (size_t)TC_TAU_WARPS * n_stiles * 2, st>>>(
+                                (size_t)TC_TAU_WARPS * (n_stiles + 2) * 2, st>>>(
                     ws->tilemin.as<int32_t>(), n_stiles, nqt, nq_pad, sp.m, ws->qpop.as<uint32_t>(),
                     ws->qpack.as<uint32_t>(), h->qs, h->nchunk, ws->qexp.as<int8_t>(), ws->qbase.as<int32_t>());
             }
@@ -679,6 +703,24 @@ void search_core(gvdb_index* h, Workspace* ws, cudaStream_t st, const float* que
             Timed t(h, ws, st, K_RESCORE);
             emit_keys_kernel<<<(unsigned)((pairs + 255) / 256), 256, 0, st>>>(
                 ws->buf.as<uint64_t>(), cap, ws->cnt.as<uint32_t>(), R, nqt, h->cfg.row_base, keys_out + (size_t)qt0 * R);
+        } else if ((h->dim & 3) == 0 && R <= (uint32_t)RT_MAX_R && rescore_topk_smem(h->dim, R) <= 200 * 1024) {
+            // rescoring (+ the final ordering when the caller handed its k-lists down): one CTA per query
+            Timed t(h, ws, st, K_RESCORE);
+            static std::atomic<uint64_t> attr_done{0};
+            ensure_dyn_smem(attr_done, rescore_topk_kernel, 200 * 1024);
+            uint32_t n_eff = 64;
+            while (n_eff < R) n_eff <<= 1;
+            const bool topk = fused && fused->k > 0;
+            const bool recs = !fused || fused->want_records;
+            const uint32_t k = topk ? fused->k : 0u;
+            rescore_topk_kernel<<<nqt, 32 * ((R + 31) / 32), rescore_topk_smem(h->dim, R), st>>>(
+                h->rows, h->norms, h->cfg.row_base, h->dim, queries_dev + (size_t)qt0 * h->dim, ws->qnorm.as<float>(),
+                ws->buf.as<uint64_t>(), cap, ws->cnt.as<uint32_t>(), R, n_eff, k,
+                topk ? fused->ids_out + (size_t)qt0 * k : nullptr, topk ? fused->scores_out + (size_t)qt0 * k : nullptr,
+                recs ? rec_ham + (size_t)qt0 * R : nullptr, recs ? rec_ids + (size_t)qt0 * R : nullptr,
+                recs ? rec_score + (size_t)qt0 * R : nullptr,
+                h->rows_cover_all() ? nullptr : h->peer_rows_dev, h->peer_per);
+            if (fused) fused->done = true;
         } else {
             Timed t(h, ws, st, K_RESCORE);
             if ((h->dim & 3) == 0) {
@@ -860,9 +902,13 @@ void search_device(gvdb_index* h, Workspace* ws, cudaStream_t st, const float* q
     ws->rec_score.ensure((size_t)nq * R * 4);
     for (int attempt = 0; attempt < 2; ++attempt) {
         bool optimistic = false;
+        FusedTopk fused;
+        fused.k = k; fused.ids_out = ids_out; fused.scores_out = scores_out;
+        fused.want_records = cand_ids != nullptr || cand_ham != nullptr;
         search_core(h, ws, st, q_dev, nq, R, ws->rec_ham.as<uint32_t>(), ws->rec_ids.as<uint64_t>(),
-                    ws->rec_score.as<float>(), true, attempt == 0, &optimistic);
-        launch_topk(h, ws, st, ws->rec_ids.as<uint64_t>(), ws->rec_score.as<float>(), nq, R, k, ids_out, scores_out);
+                    ws->rec_score.as<float>(), true, attempt == 0, &optimistic, nullptr, k > 0 ? &fused : nullptr);
+        if (!fused.done)
+            launch_topk(h, ws, st, ws->rec_ids.as<uint64_t>(), ws->rec_score.as<float>(), nq, R, k, ids_out, scores_out);
         if (cand_ids) CU(cudaMemcpyAsync(cand_ids, ws->rec_ids.p, (size_t)nq * R * 8, cudaMemcpyDeviceToDevice, st));
         if (cand_ham) CU(cudaMemcpyAsync(cand_ham, ws->rec_ham.p, (size_t)nq * R * 4, cudaMemcpyDeviceToDevice, st));
         if (h_ids) {

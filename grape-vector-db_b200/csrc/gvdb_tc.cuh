@@ -25,8 +25,9 @@
 //           a sign bit shows up.  Survivors (row, query) leave through per-warp record lists
 //           (coalesced stores, no atomics); tc_scatter_kernel turns them into candidate keys.
 //   MODE 1  every distance to dist_out (gvdb_hamming, parity tests).
-//   MODE 2  sample: the minimum of D over each 32-row tile, per query (tilemin[tile][q]) — the
-//           threshold estimate of the single-pass search comes from these (tc_tau_kernel).
+//   MODE 2  sample: per query, the minimum of D over each ROW CLASS (the rows four neighbouring lanes of
+//           one CTA see: four rows of every group of its row slice) — tilemin[class][q], one FMNMX per
+//           element.  The threshold estimate of the single-pass search comes from these (tc_tau_kernel).
 //
 // Work decomposition.  item = (query slice, row slice).  A query slice is up to tc_qblocks() blocks
 // of 128 queries whose expanded codes stay RESIDENT in shared memory (4 blocks x 48 KB at 768 bits)
@@ -369,10 +370,10 @@ query_prep_tc_kernel(const float* __restrict__ x, uint32_t nq, uint32_t nq_pad, 
 }
 
 // ---- single-pass threshold from the sample's tile minima ------------------------------------------------
-// One warp per query.  tilemin[t * nq_pad + q] (MODE 2) = min over the live rows of sample tile t of
-// D = hamming - popc(q) (TC_TILEMIN_NONE: no live row).  The minima of different tiles belong to
+// One warp per query.  tilemin[t * nq_pad + q] (MODE 2) = min over the live rows of sample class t of
+// D = hamming - popc(q) (TC_TILEMIN_NONE: no live row).  The minima of different classes belong to
 // different rows, so the m-th smallest of them, t_m, is an upper bound of the m-th smallest distance
-// among the sampled rows (and equals it unless two of the m closest sampled rows share a tile):
+// among the sampled rows (and equals it unless two of the m closest sampled rows share a class):
 //     tau_opt = popc(q) + t_m + 1      (TAU_ALL while fewer than m tiles hold a live row)
 // Written to qpack's tau words [tau, tau_opt], as the bias digits of v = t_m + 1 and as qbase = popc(q) + v.
 // Whether the pass under tau_opt found the true top R is checked afterwards (select_hist_kernel, verify 2).
@@ -382,22 +383,25 @@ __global__ void __launch_bounds__(32 * TC_TAU_WARPS)
 tc_tau_kernel(const int32_t* __restrict__ tilemin, uint32_t n_tiles, uint32_t nq, uint32_t nq_pad, uint32_t m,
               const uint32_t* __restrict__ qpop, uint32_t* __restrict__ qpack, int qs, int nchunk,
               int8_t* __restrict__ qexp, int32_t* __restrict__ qbase) {
-    extern __shared__ int16_t s_min[];                         // TC_TAU_WARPS x n_tiles
+    extern __shared__ int16_t s_min[];                         // TC_TAU_WARPS x (n_tiles + 2)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t q = blockIdx.x * TC_TAU_WARPS + warp;
-    if (q >= nq_pad) return;
+    const uint32_t q0 = blockIdx.x * TC_TAU_WARPS;
+    const uint32_t q = q0 + warp;
     const int K = nchunk * 128;
+    // the CTA's eight queries are neighbours in tilemin's rows: eight threads read one 32-byte sector
+    for (uint32_t i = threadIdx.x; i < n_tiles * TC_TAU_WARPS; i += blockDim.x) {
+        const uint32_t t = i / TC_TAU_WARPS, w = i % TC_TAU_WARPS;
+        const int32_t v = q0 + w < nq_pad ? tilemin[(size_t)t * nq_pad + q0 + w] : TC_TILEMIN_NONE;
+        s_min[(size_t)w * (n_tiles + 2) + t] = v == TC_TILEMIN_NONE ? (int16_t)0x7fff : (int16_t)v;   // odd word stride
+    }
+    __syncthreads();
+    if (q >= nq_pad) return;
     if (q >= nq) {                                             // padding query: nothing passes
         if (lane == 0) qbase[q] = -(K + 1);
         tc_write_bias_digits(qexp, nchunk, q, -(K + 1), lane);
         return;
     }
-    int16_t* mine = s_min + (size_t)warp * n_tiles;
-    for (uint32_t t = lane; t < n_tiles; t += 32) {
-        const int32_t v = tilemin[(size_t)t * nq_pad + q];
-        mine[t] = v == TC_TILEMIN_NONE ? (int16_t)0x7fff : (int16_t)v;
-    }
-    __syncwarp();
+    int16_t* mine = s_min + (size_t)warp * (n_tiles + 2);
     int32_t tm = 0x7fff;
     for (uint32_t it = 0; it < m; ++it) {                      // extract the smallest, m times
         int32_t best = 0x7fff;
@@ -615,6 +619,11 @@ tc_scan_kernel(const uint4* __restrict__ codes, const uint32_t* __restrict__ liv
                 return (g < g_hi && tile < tile_hi) ? __ldg(live + tile) : 0u;
             };
             uint32_t live_next = live_word(g_lo);
+            float run_min[MODE == 2 ? 64 : 1];                // MODE 2 (one block per item): minima of this lane's rows
+            if (MODE == 2) {
+#pragma unroll
+                for (int j = 0; j < 64; ++j) run_min[j < (MODE == 2 ? 64 : 1) ? j : 0] = __int_as_float(0x7f800000);
+            }
             for (uint32_t g = g_lo; g < g_hi; ++g) {
                 const uint32_t tile = group_tile(g) + (ew & 3);
                 const bool in_range = tile < tile_hi;
@@ -627,6 +636,29 @@ tc_scan_kernel(const uint4* __restrict__ codes, const uint32_t* __restrict__ liv
                     { TC_PROF_T0(); mbar_wait(acc_full(b), (it / NBUF) & 1u); TC_PROF_ADD(0); }   // buffer b's (it / NBUF)-th use
                     tc_fence_after();
                     TC_PROF_T0();
+                    if (MODE == 2) {
+                        // sample mode keeps 64 running minima in registers: take the accumulator in two
+                        // halves of 32 columns, then hand the buffer back
+                        const uint32_t col0 = tmem_d + lane_taddr + b * TC_NQ + half * 64;
+#pragma unroll
+                        for (int h2 = 0; h2 < 2; ++h2) {
+                            uint32_t w[32];
+                            tc_ld32(col0 + h2 * 32, w);
+                            tc_wait_ld();
+                            if (alive) {
+#pragma unroll
+                                for (int j = 0; j < 32; ++j) {
+                                    const int jj = MODE == 2 ? h2 * 32 + j : 0;
+                                    run_min[jj] = fminf(run_min[jj], __uint_as_float(w[j]));
+                                }
+                            }
+                        }
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(acc_empty(b));
+                        TC_PROF_ADD(1);
+                        continue;
+                    }
                     uint32_t v[64];
                     if (!(dbg & 1)) {
                         uint32_t v0[32], v1[32];
@@ -684,24 +716,35 @@ tc_scan_kernel(const uint4* __restrict__ codes, const uint32_t* __restrict__ liv
                             if (q < nq && in_range && row < n_rows)
                                 dist_out[(size_t)q * dist_stride + row] = (uint32_t)(s_base[qloc + j] + dv);
                         }
-                    } else {
-                        // minimum of D over the tile's live rows, per column.  D is an integer in
-                        // [-K, K]: (D + 1.5 * 2^23) keeps it in the mantissa, so the u32 order of the
-                        // sums is the order of D and one redux.min per column does it.
-                        int32_t keep[2] = {TC_TILEMIN_NONE, TC_TILEMIN_NONE};
-#pragma unroll
-                        for (int j = 0; j < 64; ++j) {
-                            const uint32_t u = alive ? __float_as_uint(__uint_as_float(v[j]) + 12582912.0f) : 0xffffffffu;
-                            const uint32_t mn = __reduce_min_sync(0xffffffffu, u);
-                            if ((j & 31) == lane)
-                                keep[j >> 5] = mn == 0xffffffffu ? TC_TILEMIN_NONE : (int32_t)(mn - 0x4B400000u);
-                        }
-                        // a tile past the end reports "no live row"
-                        const size_t t_idx = (size_t)(g * 4u + (uint32_t)(ew & 3));
-#pragma unroll
-                        for (int i = 0; i < 2; ++i) tilemin[t_idx * nq_pad + qbase_q + i * 32 + lane] = keep[i];
                     }
                     TC_PROF_ADD(1);
+                }
+            }
+            if (MODE == 2) {
+                // row class = (row slice, lane quarter, lane / 4): the minima of four neighbouring lanes are
+                // folded with two shuffle steps (once per item), leaving 32 classes per row slice; a class
+                // that saw no live row reports TC_TILEMIN_NONE.  Lanes 0, 4, 8, ... write 64 consecutive
+                // queries (256 B) each.
+#pragma unroll
+                for (int j = 0; j < 64; ++j) {
+                    const int jj = MODE == 2 ? j : 0;
+                    float x = run_min[jj];
+                    x = fminf(x, __shfl_xor_sync(0xffffffffu, x, 1));
+                    x = fminf(x, __shfl_xor_sync(0xffffffffu, x, 2));
+                    run_min[jj] = x;
+                }
+                const uint32_t rsl = item % n_rslices;
+                const size_t cls = ((size_t)rsl * 4u + (uint32_t)(ew & 3)) * 8u + (uint32_t)(lane >> 2);
+                int32_t* out = tilemin + cls * nq_pad + (size_t)qb0 * TC_NQ + half * 64;
+                if ((lane & 3) == 0)
+#pragma unroll
+                for (int j4 = 0; j4 < 16; ++j4) {
+                    int4 o;
+                    const float a = run_min[(MODE == 2) ? 4 * j4 : 0], b = run_min[(MODE == 2) ? 4 * j4 + 1 : 0];
+                    const float c = run_min[(MODE == 2) ? 4 * j4 + 2 : 0], d = run_min[(MODE == 2) ? 4 * j4 + 3 : 0];
+                    o.x = a < 1e30f ? (int32_t)a : TC_TILEMIN_NONE; o.y = b < 1e30f ? (int32_t)b : TC_TILEMIN_NONE;
+                    o.z = c < 1e30f ? (int32_t)c : TC_TILEMIN_NONE; o.w = d < 1e30f ? (int32_t)d : TC_TILEMIN_NONE;
+                    reinterpret_cast<int4*>(out)[j4] = o;
                 }
             }
         }

@@ -69,7 +69,7 @@ int main(int argc, char** argv) {
     CK(cudaGetLastError());
     int sms = 0; CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0));
     uint32_t ngroups = (ntiles + 3) / 4;
-    CK(cudaMalloc(&d_tilemin, (size_t)ngroups * 4 * nq_pad * 4));
+    CK(cudaMalloc(&d_tilemin, (size_t)32 * 128 * nq_pad * 4));
     const uint32_t qb_item = argc > 6 ? (uint32_t)atoi(argv[6]) : (uint32_t)TC_QBLOCKS;
     const uint32_t n_qsl = (nq_pad / TC_NQ + qb_item - 1) / qb_item;
     uint32_t n_rsl = argc > 5 ? atoi(argv[5]) : 0;
@@ -98,28 +98,36 @@ int main(int argc, char** argv) {
             for (int i = 0; i < 8; ++i) printf("  [%d] ref=%u tc=%u\n", i, a[i], b[i]);
             return 1;
         }
-        // ---- sample mode (MODE 2): tile minima of D = hamming - popc(q) over every tile ----
+        // ---- sample mode (MODE 2): per-class minima of D = hamming - popc(q); class = (row slice, row % 128) ----
         std::vector<uint32_t> h_pop(nq_pad);
         CK(cudaMemcpy(h_pop.data(), d_qpop, nq_pad * 4, cudaMemcpyDeviceToHost));
         CK(cudaFuncSetAttribute(tc_scan_kernel<NCHUNK, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        tc_scan_kernel<NCHUNK, 2><<<grid, TC_THREADS, smem>>>(d_codes, d_live, 0, ntiles, ngroups, 1, d_qexp, d_qbase, nq, nq_pad, n_qsl, n_rsl, qb_item,
-                                                             nullptr, 0, nullptr, d_flag, nullptr, 0, n_rows, d_tilemin);
-        CK(cudaGetLastError());
-        CK(cudaDeviceSynchronize());
         {
-            std::vector<int32_t> tm((size_t)ngroups * 4 * nq_pad);
+            const uint32_t nqb = nq_pad / TC_NQ;
+            uint32_t rs = (uint32_t)sms / nqb; if (rs < 1) rs = 1; if (rs > 128) rs = 128; if (rs > ngroups) rs = ngroups;
+            const uint32_t g2 = nqb * rs < (uint32_t)sms ? nqb * rs : (uint32_t)sms;
+            tc_scan_kernel<NCHUNK, 2><<<g2, TC_THREADS, smem>>>(d_codes, d_live, 0, ntiles, ngroups, 1, d_qexp, d_qbase, nq, nq_pad, nqb, rs, 1,
+                                                               nullptr, 0, nullptr, d_flag, nullptr, 0, n_rows, d_tilemin);
+            CK(cudaGetLastError());
+            CK(cudaDeviceSynchronize());
+            std::vector<int32_t> tm((size_t)rs * 32 * nq_pad);
             CK(cudaMemcpy(tm.data(), d_tilemin, tm.size() * 4, cudaMemcpyDeviceToHost));
             size_t badt = 0;
-            for (uint32_t t = 0; t < ngroups * 4; ++t)
-                for (uint32_t q = 0; q < nq; ++q) {
-                    int32_t want = TC_TILEMIN_NONE;
-                    for (uint32_t l = 0; l < 32; ++l) {
-                        const uint64_t r = (uint64_t)t * 32 + l;
-                        if (r < n_rows) want = std::min<int32_t>(want, (int32_t)a[(size_t)q * n_rows + r] - (int32_t)h_pop[q]);
+            for (uint32_t sl = 0; sl < rs; ++sl) {
+                const uint64_t g_lo = (uint64_t)ngroups * sl / rs, g_hi = (uint64_t)ngroups * (sl + 1) / rs;
+                for (uint32_t c = 0; c < 32; ++c)             // class c: rows 4c .. 4c+3 of every group
+                    for (uint32_t q = 0; q < nq; ++q) {
+                        int32_t want = TC_TILEMIN_NONE;
+                        for (uint64_t g = g_lo; g < g_hi; ++g)
+                            for (uint32_t k = 0; k < 4; ++k) {
+                                const uint64_t r = g * 128 + c * 4 + k;
+                                if (r < n_rows) want = std::min<int32_t>(want, (int32_t)a[(size_t)q * n_rows + r] - (int32_t)h_pop[q]);
+                            }
+                        const int32_t got = tm[((size_t)sl * 32 + c) * nq_pad + q];
+                        if (got != want) { if (!badt) printf("class-min mismatch slice=%u class=%u q=%u got=%d want=%d\n", sl, c, q, got, want); ++badt; }
                     }
-                    if (tm[(size_t)t * nq_pad + q] != want) { if (!badt) printf("tile-min mismatch t=%u q=%u got=%d want=%d\n", t, q, tm[(size_t)t * nq_pad + q], want); ++badt; }
-                }
-            printf("sample-mode check: %u tiles x %u queries, mismatches=%zu\n", ngroups * 4, nq, badt);
+            }
+            printf("sample-mode check: %u classes x %u queries, mismatches=%zu\n", rs * 32, nq, badt);
             if (badt) return 1;
         }
         // ---- search mode (MODE 0): survivors of a finite threshold must be exactly {ham < tau} ----
