@@ -472,7 +472,9 @@ tc_scan_kernel(const uint4* __restrict__ codes, const uint32_t* __restrict__ liv
     auto acc_full = [&](uint32_t b) { return bar0 + 8u * (2 + 2 * NSLOT + b); };
     auto acc_empty = [&](uint32_t b) { return bar0 + 8u * (2 + 2 * NSLOT + NBUF + b); };
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // the shuffle tells the compiler the warp index is warp-uniform: the role branches below and everything
+    // derived from loop counters inside them can then live in uniform registers
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     const uint32_t nqb = nq_pad / TC_NQ;
     const uint32_t n_items = n_qslices * n_rslices;
 

@@ -193,6 +193,24 @@ int main() {
                    128.0 * np * 64 * niter / clk);
         }
     }
+    // the same loop timed with CUDA events over ~10 ms on every SM: the FP4 MMA rate in TIME units, i.e. at the
+    // SM clock the part actually sustains under this load (the roofline denominator bench.py quotes)
+    {
+        const int niter = 40000;
+        cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+        probe_kernel<<<148, 128, 16384>>>(da, db, dd, 4, niter, dclk, 0x7F7F7F7Fu, 0x7F7F7F7Fu, 0, 128, 2);
+        CK(cudaDeviceSynchronize());
+        cudaEventRecord(e0);
+        for (int rep = 0; rep < 4; ++rep) probe_kernel<<<148, 128, 16384>>>(da, db, dd, 4, niter, dclk, 0x7F7F7F7Fu, 0x7F7F7F7Fu, 0, 128, 2);
+        cudaEventRecord(e1);
+        CK(cudaDeviceSynchronize());
+        float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+        long long clk; CK(cudaMemcpy(&clk, dclk, 8, cudaMemcpyDeviceToHost));
+        const double macs = 4.0 * 148 * (double)niter * 128 * 128 * 64;
+        printf("sustained: %.1f clk per MMA, %.2f ms for 4 launches -> %.1f TMAC/s = %.2f PFLOP/s dense FP4 on 148 SMs (implied SM clock %.0f MHz)\n",
+               (double)clk / niter, ms, macs / (ms * 1e-3) / 1e12, 2 * macs / (ms * 1e-3) / 1e15,
+               4.0 * clk / (ms * 1e-3) / 1e6);
+    }
     printf("OK\n");
     return 0;
 }
