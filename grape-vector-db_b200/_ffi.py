@@ -52,6 +52,7 @@ class GvdbProfile(C.Structure):
 _vp, _u32, _u64, _i32 = C.c_void_p, C.c_uint32, C.c_uint64, C.c_int32
 SYMBOLS = {
     "gvdb_abi_version": (_u32, []),
+    "gvdb_measure_fp4_mma_rate": (_i32, [_i32, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "gvdb_last_error": (C.c_char_p, []),
     "gvdb_create": (_i32, [C.POINTER(GvdbConfig), C.POINTER(_vp)]),
     "gvdb_destroy": (None, [_vp]),

@@ -564,13 +564,19 @@ struct FusedTopk {
     uint64_t* ids_out = nullptr;
     float* scores_out = nullptr;
     bool want_records = true;
+    uint32_t slice_q = 0;        // > 0: records packed per slice of slice_q queries at rec_ids (gvdb_search_shard_sliced_device)
     bool done = false;
 };
+bool rescore_topk_fits(const gvdb_index* h, uint32_t R);
 size_t rescore_topk_smem(int dim, uint32_t R) {
     const uint32_t nwarps = (R + 31) / 32;
     uint32_t n_eff = 64;
     while (n_eff < R) n_eff <<= 1;
     return ((size_t)dim + (size_t)nwarps * 2 * 32 * RT_STRIDE) * sizeof(float) + (size_t)n_eff * 8;
+}
+
+bool rescore_topk_fits(const gvdb_index* h, uint32_t R) {
+    return (h->dim & 3) == 0 && R <= (uint32_t)RT_MAX_R && rescore_topk_smem(h->dim, R) <= 200 * 1024;
 }
 
 // Stage 1 + stage 2 for queries [0,nq) (device pointers): fills rec_* [nq][R].
@@ -703,7 +709,7 @@ void search_core(gvdb_index* h, Workspace* ws, cudaStream_t st, const float* que
             Timed t(h, ws, st, K_RESCORE);
             emit_keys_kernel<<<(unsigned)((pairs + 255) / 256), 256, 0, st>>>(
                 ws->buf.as<uint64_t>(), cap, ws->cnt.as<uint32_t>(), R, nqt, h->cfg.row_base, keys_out + (size_t)qt0 * R);
-        } else if ((h->dim & 3) == 0 && R <= (uint32_t)RT_MAX_R && rescore_topk_smem(h->dim, R) <= 200 * 1024) {
+        } else if (rescore_topk_fits(h, R)) {
             // rescoring (+ the final ordering when the caller handed its k-lists down): one CTA per query
             Timed t(h, ws, st, K_RESCORE);
             static std::atomic<uint64_t> attr_done{0};
@@ -713,13 +719,20 @@ void search_core(gvdb_index* h, Workspace* ws, cudaStream_t st, const float* que
             const bool topk = fused && fused->k > 0;
             const bool recs = !fused || fused->want_records;
             const uint32_t k = topk ? fused->k : 0u;
+            const uint32_t slice_q = fused ? fused->slice_q : 0u;
+            if (slice_q && (qt0 % slice_q != 0 || QT % slice_q != 0))
+                fail(GVDB_ERR_INVALID_ARGUMENT, "queries per slice must divide the query tile");
+            // sliced layout: the tile starts at slice qt0 / slice_q of the packed buffer
+            uint64_t* ids_base = !recs ? nullptr
+                               : slice_q ? reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(rec_ids) + (size_t)(qt0 / slice_q) * slice_q * R * 16)
+                                         : rec_ids + (size_t)qt0 * R;
             rescore_topk_kernel<<<nqt, 32 * ((R + 31) / 32), rescore_topk_smem(h->dim, R), st>>>(
                 h->rows, h->norms, h->cfg.row_base, h->dim, queries_dev + (size_t)qt0 * h->dim, ws->qnorm.as<float>(),
                 ws->buf.as<uint64_t>(), cap, ws->cnt.as<uint32_t>(), R, n_eff, k,
                 topk ? fused->ids_out + (size_t)qt0 * k : nullptr, topk ? fused->scores_out + (size_t)qt0 * k : nullptr,
-                recs ? rec_ham + (size_t)qt0 * R : nullptr, recs ? rec_ids + (size_t)qt0 * R : nullptr,
-                recs ? rec_score + (size_t)qt0 * R : nullptr,
-                h->rows_cover_all() ? nullptr : h->peer_rows_dev, h->peer_per);
+                recs && !slice_q ? rec_ham + (size_t)qt0 * R : nullptr, ids_base,
+                recs && !slice_q ? rec_score + (size_t)qt0 * R : nullptr,
+                h->rows_cover_all() ? nullptr : h->peer_rows_dev, h->peer_per, slice_q);
             if (fused) fused->done = true;
         } else {
             Timed t(h, ws, st, K_RESCORE);
@@ -1700,6 +1713,18 @@ gvdb_status gvdb_search_shard_sliced_device(gvdb_index* h, void* stream, const f
         WsLease lease(h, (cudaStream_t)stream, true);
         const uint32_t per = nq / n_slices;
         const uint64_t nr = (uint64_t)per * rescore_count;
+        if (rescore_count >= 1 && rescore_count <= kMaxR && rescore_topk_fits(h, rescore_count) && h->query_tile % per == 0) {
+            // one pass over the shard for ALL queries; the rescoring kernel writes the slice-packed layout
+            for (int attempt = 0; attempt < 2; ++attempt) {
+                bool optimistic = false;
+                FusedTopk fused;
+                fused.slice_q = per;
+                search_core(h, lease.ws, lease.stream, queries_dev, nq, rescore_count, nullptr,
+                            static_cast<uint64_t*>(records_dev), nullptr, true, attempt == 0, &optimistic, nullptr, &fused);
+                if (!check_overflow(h, lease.ws, lease.stream, optimistic)) break;
+            }
+            return;
+        }
         for (int attempt = 0; attempt < 2; ++attempt) {
             bool optimistic = false;
             for (uint32_t s = 0; s < n_slices; ++s) {
@@ -2387,6 +2412,39 @@ gvdb_status gvdb_rrf_fusion_batch(int32_t device, const uint64_t* dense, uint32_
                    nq, k, limit, oi, os);
         CU(cudaMemcpy(ids_out, oi, (size_t)nq * limit * 8, cudaMemcpyDeviceToHost));
         CU(cudaMemcpy(scores_out, os, (size_t)nq * limit * 4, cudaMemcpyDeviceToHost));
+    });
+}
+
+gvdb_status gvdb_measure_fp4_mma_rate(int32_t device, double* tmacs_per_s_out, double* clk_per_mma_out) {
+    return guarded([&] {
+        int ndev = 0;
+        if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+            fail(GVDB_ERR_INDEX, "no usable CUDA device (there is no CPU fallback)");
+        if (device < 0 || device >= ndev) fail(GVDB_ERR_INVALID_ARGUMENT, "bad device ordinal");
+        DeviceGuard dg(device);
+        cudaDeviceProp prop;
+        CU(cudaGetDeviceProperties(&prop, device));
+        const int sms = prop.multiProcessorCount;
+        DevBuf clk;
+        struct Rel { DevBuf& b; ~Rel() { b.release(); } } rel{clk};
+        clk.ensure(64);
+        cudaEvent_t e0 = nullptr, e1 = nullptr;
+        CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+        struct Ev { cudaEvent_t a, b; ~Ev() { cudaEventDestroy(a); cudaEventDestroy(b); } } ev{e0, e1};
+        const int niter = 40000, reps = 4;                       // ~1.4 ms per launch at 64 clk per MMA
+        tc_mma_rate_kernel<<<sms, 128, 4096>>>(niter, clk.as<long long>());      // warm-up
+        CU(cudaGetLastError());
+        CU(cudaEventRecord(e0));
+        for (int r = 0; r < reps; ++r) tc_mma_rate_kernel<<<sms, 128, 4096>>>(niter, clk.as<long long>());
+        CU(cudaEventRecord(e1));
+        CU(cudaDeviceSynchronize());
+        float ms = 0.f;
+        CU(cudaEventElapsedTime(&ms, e0, e1));
+        long long c = 0;
+        CU(cudaMemcpy(&c, clk.p, 8, cudaMemcpyDeviceToHost));
+        const double macs = (double)reps * sms * niter * 128.0 * 128.0 * 64.0;
+        if (tmacs_per_s_out) *tmacs_per_s_out = macs / (ms * 1e-3) / 1e12;
+        if (clk_per_mma_out) *clk_per_mma_out = (double)c / niter;
     });
 }
 

@@ -840,7 +840,8 @@ rescore_topk_kernel(const float* __restrict__ rows, const float* __restrict__ no
                     const uint64_t* __restrict__ buf, uint32_t cap, const uint32_t* __restrict__ cnt, uint32_t R,
                     uint32_t n_eff, uint32_t k, uint64_t* __restrict__ ids_out, float* __restrict__ scores_out,
                     uint32_t* __restrict__ rec_ham, uint64_t* __restrict__ rec_ids, float* __restrict__ rec_score,
-                    const float* const* __restrict__ peer_rows, uint64_t rows_per_owner) {
+                    const float* const* __restrict__ peer_rows, uint64_t rows_per_owner,
+                    uint32_t slice_q /* > 0: packed shard records grouped by slices of slice_q queries, rec_ids = base */) {
     extern __shared__ __align__(16) float rt_smem[];         // query row | per warp: 2 slabs of 32 x RT_STRIDE | sort keys
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nwarps = blockDim.x >> 5;
@@ -913,10 +914,21 @@ rescore_topk_kernel(const float* __restrict__ rows, const float* __restrict__ no
         cosv = (na == 0.0f || nb == 0.0f) ? 0.0f : __fdiv_rn(dot, __fmul_rn(na, nb));
     }
     if (rec_ids && r < R) {
-        const size_t p = (size_t)q * R + r;
-        rec_ham[p] = valid ? (uint32_t)(key >> 32) : 0xffffffffu;
-        rec_ids[p] = valid ? row_base + my_row : UINT64_MAX;
-        rec_score[p] = cosv;
+        uint64_t* o_ids = rec_ids; uint32_t* o_ham = rec_ham; float* o_sc = rec_score;
+        size_t p = (size_t)q * R + r;
+        if (slice_q) {
+            // slice s = q / slice_q is one packed buffer [ids u64 | ham u32 | score f32] x slice_q x R
+            // (the layout gvdb_merge_shards_device consumes after the all-to-all)
+            const size_t nr = (size_t)slice_q * R;
+            uint8_t* base = reinterpret_cast<uint8_t*>(rec_ids) + (size_t)(q / slice_q) * nr * 16;
+            o_ids = reinterpret_cast<uint64_t*>(base);
+            o_ham = reinterpret_cast<uint32_t*>(base + nr * 8);
+            o_sc = reinterpret_cast<float*>(base + nr * 12);
+            p = (size_t)(q % slice_q) * R + r;
+        }
+        o_ham[p] = valid ? (uint32_t)(key >> 32) : 0xffffffffu;
+        o_ids[p] = valid ? row_base + my_row : UINT64_MAX;
+        o_sc[p] = cosv;
     }
     if (k == 0) return;
     // order: descending cosine image, then stage-1 position

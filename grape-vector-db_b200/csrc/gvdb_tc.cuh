@@ -881,4 +881,53 @@ tc_scatter_kernel(const uint2* __restrict__ recs, uint32_t rec_cap, const uint32
     }
 }
 
+// ---- the FP4 MMA rate of this part, measured (the roofline denominator of the tensor-core scan) ------------------
+// Back-to-back tcgen05.mma kind::mxf4 (M128 x N128 x K64, A in TMEM, B from shared memory, all scales 1.0)
+// issued by one thread per SM, alternating between two accumulators; nothing else runs.  clk_out[0] = SM
+// clocks CTA 0 needed for `niter` MMAs.  Operand contents do not matter.
+__global__ void __launch_bounds__(128, 1)
+tc_mma_rate_kernel(int niter, long long* __restrict__ clk_out) {
+    extern __shared__ __align__(1024) uint8_t smem[];      // 4 KB B tile (whatever it holds)
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ uint32_t s_tmem;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) { mbar_init(smem_u32(&bar), 1); fence_mbar_init(); }
+    if (warp == 0) tc_alloc(smem_u32(&s_tmem), 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = s_tmem;
+    {
+        uint32_t v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = TC_SF_ONE;
+        tc_st8(tmem + ((uint32_t)(warp * 32) << 16) + 384, v);        // scale words
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = TC_A_ONE8;
+        tc_st8(tmem + ((uint32_t)(warp * 32) << 16) + 400, v);        // A: 64 x 1.0 per row
+        tc_wait_st();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (warp == 1) {
+        const uint64_t bdesc = tc_smem_desc(smem_u32(smem), 128, 256);
+        const long long t0 = clock64();
+        if (elect_one()) {
+            for (int it = 0; it < niter; it += 8) {
+#pragma unroll
+                for (int u = 0; u < 8; ++u)
+                    tc_mma_mxf4_ts(tmem + (u & 1) * 128, tmem + 400, bdesc, tc_idesc_mxf4(128, 128), tmem + 384, tmem + 388, 1u);
+            }
+            tc_commit(smem_u32(&bar));
+        }
+        __syncwarp();
+        mbar_wait(smem_u32(&bar), 0);
+        if (lane == 0 && blockIdx.x == 0) clk_out[0] = clock64() - t0;
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tc_dealloc(tmem, 512);
+}
+
 }  // namespace gvdb

@@ -465,3 +465,12 @@ class GpuIndex:
         p = _ffi.GvdbProfile()
         self._ok(self._lib.gvdb_profile_read(self._h, C.byref(p), 1 if reset else 0))
         return {f: getattr(p, f) for f, _ in p._fields_}
+
+
+def measure_fp4_mma_rate(device: int = 0) -> dict:
+    """gvdb_measure_fp4_mma_rate: the dense FP4 tensor-core rate of `device`, measured (TMAC/s and
+    SM clocks per M128 x N128 x K64 MMA) — the roofline denominator of the tensor-core scan."""
+    lib = _ffi.lib()
+    t, c = C.c_double(0.0), C.c_double(0.0)
+    raise_for_status(lib.gvdb_measure_fp4_mma_rate(device, C.byref(t), C.byref(c)), lib)
+    return {"tmacs_per_s": t.value, "clk_per_mma": c.value}

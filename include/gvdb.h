@@ -365,6 +365,12 @@ typedef struct gvdb_profile {
     double sample_ms;         /* tc_scan_kernel in sample mode + tc_tau_kernel (single-pass threshold estimate) */
 } gvdb_profile;
 GVDB_API gvdb_status gvdb_profile_enable(gvdb_index* h, int32_t on);
+/* The dense FP4 tensor-core rate of `device`, measured: back-to-back tcgen05.mma kind::mxf4
+ * (M128 x N128 x K64, A in TMEM) on every SM for a few milliseconds, nothing else running.
+ * tmacs_per_s_out: multiply-accumulates per second / 1e12 (x2 = FLOP/s); clk_per_mma_out: SM clocks
+ * per MMA on one SM (64 = the pipe's rate).  The denominator of the tensor-core scan's roofline:
+ * MEASURED_PEAKS.json holds no FP4 figure. */
+GVDB_API gvdb_status gvdb_measure_fp4_mma_rate(int32_t device, double* tmacs_per_s_out, double* clk_per_mma_out);
 GVDB_API gvdb_status gvdb_profile_read(gvdb_index* h, gvdb_profile* out, int32_t reset);
 
 #ifdef __cplusplus
