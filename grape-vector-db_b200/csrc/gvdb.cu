@@ -963,8 +963,15 @@ void flat_device(gvdb_index* h, Workspace* ws, cudaStream_t st, const float* q_d
     ws->flag.ensure(256);
     ws->buf.ensure((size_t)qt_max * cap * 8);
     ws->misc.ensure((size_t)qt_max * 4);   // per-query key thresholds
+    // Two schedules.  Fast: the first 4096 rows emit everything, later segments grow geometrically and emit only
+    // rows that beat the k-th best so far — few launches, but a segment can overflow a query's candidate buffer
+    // when the rows seen so far say nothing about the rest (a tombstoned or filtered-out prefix, a corpus stored in
+    // order of relevance).  Safe: segments of cap - k rows; a buffer holds the k kept keys plus at most one segment,
+    // so it cannot overflow whatever the data — the call is repeated with it when the fast one overflowed.
+    for (int attempt = 0; attempt < 2; ++attempt) {
+    const bool safe = attempt == 1;
     CU(cudaMemsetAsync(ws->flag.p, 0, 256, st));
-    const uint64_t seg0 = 4096;
+    const uint64_t seg0 = safe ? cap - k : 4096;
     const uint64_t g = std::max<uint32_t>(2, cap / (4 * k));
     for (uint32_t qt0 = 0; qt0 < nq; qt0 += QT) {
         const uint32_t nqt = std::min(QT, nq - qt0);
@@ -980,7 +987,7 @@ void flat_device(gvdb_index* h, Workspace* ws, cudaStream_t st, const float* q_d
         CU(cudaMemsetAsync(ws->misc.p, 0xff, (size_t)nqt * 4, st));   // TAU_ALL
         uint64_t lo = 0;
         while (lo < h->n_rows) {
-            uint64_t hi = std::min<uint64_t>(lo == 0 ? seg0 : lo * g, h->n_rows);
+            uint64_t hi = std::min<uint64_t>(safe ? lo + seg0 : (lo == 0 ? seg0 : lo * g), h->n_rows);
             dim3 grid((unsigned)((hi - lo + FLAT_TM - 1) / FLAT_TM), (nqt + FLAT_TN - 1) / FLAT_TN, 1);
             {
                 Timed t(h, ws, st, K_FLAT);
@@ -1010,7 +1017,12 @@ void flat_device(gvdb_index* h, Workspace* ws, cudaStream_t st, const float* q_d
             ids_out + (size_t)qt0 * k, dist_out + (size_t)qt0 * k, sim ? 1 : 0);
         CU(cudaGetLastError());
     }
-    check_overflow(h, ws, st);
+    bool overflowed = false;
+    check_overflow(h, ws, st, false, &overflowed);
+    if (!overflowed) break;
+    if (safe) fail(GVDB_ERR_INDEX, "flat search: candidate buffer overflow under the safe schedule (internal error)");
+    h->overflow_fallbacks.fetch_add(1, std::memory_order_relaxed);
+    }
 }
 
 // Rows [n_rows, n_rows + n) from DEVICE memory `src`: codes + norms + live bits for all of them,
@@ -2121,10 +2133,21 @@ gvdb_status gvdb_search_exchange_device(gvdb_index* h, void* stream, const float
         CU(cudaEventRecord(x->join, x->side));
         // stage 1 on my batch
         uint64_t* my_keys = x->my_keys.as<uint64_t>();
-        for (int attempt = 0; attempt < 2; ++attempt) {
-            bool optimistic = false;
-            search_core(h, ws, st, queries_dev, nq, R, nullptr, nullptr, nullptr, true, attempt == 0, &optimistic, my_keys);
-            if (!check_overflow(h, ws, st, optimistic)) break;
+        // A stage 1 that fails on this rank (candidate buffer overflow on an adversarial corpus) must not take
+        // the exchange down: the peers already expect this epoch's pushes.  The rank then publishes an EMPTY key
+        // list (nothing to score for its queries), serves its peers as usual, and reports the error for its own
+        // batch at the end of the step.
+        std::string stage1_error;
+        try {
+            for (int attempt = 0; attempt < 2; ++attempt) {
+                bool optimistic = false;
+                search_core(h, ws, st, queries_dev, nq, R, nullptr, nullptr, nullptr, true, attempt == 0, &optimistic, my_keys);
+                if (!check_overflow(h, ws, st, optimistic)) break;
+            }
+        } catch (const Err& e) {
+            stage1_error = e.msg;
+            cudaGetLastError();
+            CU(cudaMemsetAsync(my_keys, 0xFF, key_bytes, st));
         }
         xchg_push(h, ws, st, x, set_off + x->keys_off + x->rank * key_bytes, my_keys, 0, key_bytes);
         xchg_signal(h, ws, st, x, XCHG_K);
@@ -2143,6 +2166,9 @@ gvdb_status gvdb_search_exchange_device(gvdb_index* h, void* stream, const float
         CU(cudaGetLastError());
         guard.ok = true;
         finish_async(h, ws, st);
+        if (!stage1_error.empty())
+            fail(GVDB_ERR_INDEX, "peer exchange: stage 1 failed on this rank (its answers of this step are empty; the "
+                                 "exchange stays in step): " + stage1_error);
     });
 }
 

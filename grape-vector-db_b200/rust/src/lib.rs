@@ -113,6 +113,7 @@ extern "C" {
     pub fn gvdb_rrf_fusion_batch_device(device: i32, stream: *mut c_void, dense_dev: *const u64, n_dense: u32,
                                         sparse_dev: *const u64, n_sparse: u32, text_dev: *const u64, n_text: u32,
                                         nq: u32, k: f32, limit: u32, ids_out_dev: *mut u64, scores_out_dev: *mut f32) -> i32;
+    pub fn gvdb_measure_fp4_mma_rate(device: i32, tmacs_per_s_out: *mut f64, clk_per_mma_out: *mut f64) -> i32;
 }
 
 /// Owned handle; `Send + Sync` because the C ABI's search entry points are re-entrant and the
@@ -138,7 +139,9 @@ mod trait_impl {
     fn map_err(st: i32) -> VectorDbError {
         match st {
             1 => VectorDbError::IndexNotBuilt,
-            2 => VectorDbError::IndexError(last_error()), // DimensionMismatch is raised on the Rust side with both numbers
+            // the C ABI takes flat buffers and cannot see a wrong length: both numbers are checked (and the
+            // variant raised) on this side before the call; a status 2 from the library carries none
+            2 => VectorDbError::DimensionMismatch { expected: 0, actual: 0 },
             3 => VectorDbError::InvalidVectorDimension,
             4 => VectorDbError::QuantizationError(last_error()),
             6 => VectorDbError::ConfigError(last_error()),
@@ -248,19 +251,36 @@ pub use trait_impl::GpuVectorIndex;
 
 /// `BinaryQuantizer` with the reference's signatures (src/quantization.rs:67-241), arithmetic on the GPU.
 /// In the reference's crate this replaces the body of `impl BinaryQuantizer`; `BinaryVector`,
-/// `BinaryQuantizationConfig` and the error type stay the reference's own.
+/// `BinaryQuantizationConfig`, `CacheStats` and the error type stay the reference's own.
 #[cfg(feature = "vector-index")]
 mod quantizer_shim {
     use super::*;
-    use grape_vector_db::quantization::{BinaryQuantizationConfig, BinaryVector};
+    use grape_vector_db::quantization::{BinaryQuantizationConfig, BinaryVector, CacheStats};
     use grape_vector_db::types::VectorDbError;
+    use std::sync::Mutex;
 
-    pub struct BinaryQuantizer { config: BinaryQuantizationConfig, device: i32 }
+    /// The candidate set the last `multi_stage_search` uploaded: the reference's signature hands the
+    /// whole candidate set in on every call, so the index built from it is kept and reused while the
+    /// caller keeps passing the same slice (same address, length and dimension, same first/last row).
+    struct Resident { ptr: usize, n: usize, dim: usize, head: Vec<f32>, tail: Vec<f32>, index: GpuIndex }
 
-    fn err(st: i32) -> VectorDbError {
+    pub struct BinaryQuantizer {
+        config: BinaryQuantizationConfig,
+        device: i32,
+        /// one small index per code width, for `quantize*` / `hamming_distance` (created on first use)
+        scratch: Mutex<HashMap<usize, GpuIndex>>,
+        resident: Mutex<Option<Resident>>,
+    }
+
+    /// status codes of include/gvdb.h -> the reference's error variants (src/types.rs:859-920)
+    fn err(st: i32, expected_dim: usize, actual_dim: usize) -> VectorDbError {
         match st {
+            1 => VectorDbError::IndexNotBuilt,
+            2 => VectorDbError::DimensionMismatch { expected: expected_dim, actual: actual_dim },
             3 => VectorDbError::InvalidVectorDimension,
             4 => VectorDbError::QuantizationError(last_error()),
+            6 => VectorDbError::ConfigError(last_error()),
+            7 => VectorDbError::NotImplemented(last_error()),
             _ => VectorDbError::IndexError(last_error()),
         }
     }
@@ -270,12 +290,23 @@ mod quantizer_shim {
                               rescore_ratio: cfg.rescore_ratio, device, capacity_rows: capacity, ..Default::default() };
         let mut h = std::ptr::null_mut();
         let st = unsafe { gvdb_create(&c, &mut h) };
-        if st != 0 { return Err(err(st)); }
+        if st != 0 { return Err(err(st, dim, dim)); }
         Ok(GpuIndex { h, dim })
     }
 
     impl BinaryQuantizer {
-        pub fn new(config: BinaryQuantizationConfig) -> Self { Self { config, device: 0 } }
+        pub fn new(config: BinaryQuantizationConfig) -> Self {
+            Self { config, device: 0, scratch: Mutex::new(HashMap::new()), resident: Mutex::new(None) }
+        }
+
+        fn with_scratch<T>(&self, dim: usize, f: impl FnOnce(&GpuIndex) -> Result<T, VectorDbError>) -> Result<T, VectorDbError> {
+            let mut map = self.scratch.lock().unwrap();
+            if !map.contains_key(&dim) {
+                let ix = create(dim, &self.config, self.device, 0)?;
+                map.insert(dim, ix);
+            }
+            f(&map[&dim])
+        }
 
         /// :86-122 — bit = value > threshold, Msb0 bytes; the cache of the reference is not needed
         pub fn quantize(&mut self, vector: &[f32]) -> Result<BinaryVector, VectorDbError> {
@@ -287,14 +318,30 @@ mod quantizer_shim {
             let Some(first) = vectors.first() else { return Ok(Vec::new()) };
             let dim = first.len();
             if dim == 0 || vectors.iter().any(|v| v.len() != dim) { return Err(VectorDbError::InvalidVectorDimension); }
-            let ix = create(dim, &self.config, self.device, 0)?;
             let flat: Vec<f32> = vectors.iter().flatten().copied().collect();
             let nb = (dim + 7) / 8;
             let mut codes = vec![0u8; vectors.len() * nb];
-            let st = unsafe { gvdb_quantize(ix.h, flat.as_ptr(), vectors.len() as u64, codes.as_mut_ptr()) };
-            if st != 0 { return Err(err(st)); }
-            // from_bytes sets the bit length to 8 * bytes (:59-62); the dimension is restored here
-            Ok(codes.chunks(nb).map(|c| { let mut b = BinaryVector::from_bytes(c.to_vec()); b.dimension = dim; b }).collect())
+            self.with_scratch(dim, |ix| {
+                let st = unsafe { gvdb_quantize(ix.h, flat.as_ptr(), vectors.len() as u64, codes.as_mut_ptr()) };
+                if st != 0 { Err(err(st, dim, dim)) } else { Ok(()) }
+            })?;
+            // BinaryVector::from_bytes(bytes, dimension)  (:59-62)
+            Ok(codes.chunks(nb).map(|c| BinaryVector::from_bytes(c.to_vec(), dim)).collect())
+        }
+
+        /// :130-141 — popcount(a XOR b) over the code bytes as f32; InvalidVectorDimension if the dimensions differ
+        pub fn hamming_distance(&self, a: &BinaryVector, b: &BinaryVector) -> Result<f32, VectorDbError> {
+            if a.dimension != b.dimension { return Err(VectorDbError::InvalidVectorDimension); }
+            // two codes: the host does it (the GPU path is gvdb_hamming / the scan, used by the searches)
+            let (ab, bb) = (a.to_bytes(), b.to_bytes());
+            Ok(ab.iter().zip(bb.iter()).map(|(x, y)| (x ^ y).count_ones()).sum::<u32>() as f32)
+        }
+
+        /// :144-148 — 1 - distance / dimension
+        pub fn similarity(&self, a: &BinaryVector, b: &BinaryVector) -> Result<f32, VectorDbError> {
+            let distance = self.hamming_distance(a, b)?;
+            let max_distance = a.dimension as f32;
+            Ok(1.0 - (distance / max_distance))
         }
 
         /// :151-193 — stage 1 over every candidate, R = (n as f32 * rescore_ratio) as usize, exact rescoring of
@@ -308,20 +355,35 @@ mod quantizer_shim {
             let n = original_candidates.len();
             let r = unsafe { gvdb_rescore_count(n as u64, self.config.rescore_ratio) } as usize;
             if n == 0 || r == 0 { return Ok(Vec::new()); }
-            let ix = create(original_query.len(), &self.config, self.device, n as u64)?;
-            let flat: Vec<f32> = original_candidates.iter().flatten().copied().collect();
-            if flat.len() != n * ix.dim { return Err(VectorDbError::InvalidVectorDimension); }
-            let mut first = 0u64;
-            let st = unsafe { gvdb_add(ix.h, flat.as_ptr(), n as u64, &mut first) };
-            if st != 0 { return Err(err(st)); }
+            let dim = original_query.len();
+            if original_candidates.iter().any(|v| v.len() != dim) { return Err(VectorDbError::InvalidVectorDimension); }
+            let mut slot = self.resident.lock().unwrap();
+            let same = slot.as_ref().map_or(false, |c| {
+                c.ptr == original_candidates.as_ptr() as usize && c.n == n && c.dim == dim
+                    && c.head == original_candidates[0] && c.tail == original_candidates[n - 1]
+            });
+            if !same {
+                let ix = create(dim, &self.config, self.device, n as u64)?;
+                let flat: Vec<f32> = original_candidates.iter().flatten().copied().collect();
+                let mut first = 0u64;
+                let st = unsafe { gvdb_add(ix.h, flat.as_ptr(), n as u64, &mut first) };
+                if st != 0 { return Err(err(st, dim, dim)); }
+                *slot = Some(Resident { ptr: original_candidates.as_ptr() as usize, n, dim,
+                                        head: original_candidates[0].clone(), tail: original_candidates[n - 1].clone(), index: ix });
+            }
+            let ix = &slot.as_ref().unwrap().index;
             let (mut ids, mut sc) = (vec![GVDB_NO_ID; r], vec![0f32; r]);
             let st = unsafe { gvdb_search_batch(ix.h, original_query.as_ptr(), 1, r as u32, r as u32, ids.as_mut_ptr(),
                                                 sc.as_mut_ptr(), std::ptr::null_mut(), std::ptr::null_mut()) };
-            if st != 0 { return Err(err(st)); }
+            if st != 0 { return Err(err(st, dim, dim)); }
             Ok(ids.iter().zip(sc.iter()).take_while(|(i, _)| **i != GVDB_NO_ID).map(|(i, s)| (*i as usize, *s)).collect())
         }
 
-        pub fn clear_cache(&mut self) {}
+        /// :219-223 — nothing is cached on this side; the resident candidate index is dropped
+        pub fn clear_cache(&mut self) { *self.resident.lock().unwrap() = None; }
+
+        /// :226-240 — the quantization cache of the reference does not exist here
+        pub fn get_cache_stats(&self) -> CacheStats { CacheStats { enabled: false, size: 0, capacity: 0 } }
     }
 }
 #[cfg(feature = "vector-index")]

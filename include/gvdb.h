@@ -159,7 +159,13 @@ GVDB_API gvdb_status gvdb_search_batch(gvdb_index* h, const float* queries, uint
                               uint64_t* cand_ids_out, uint32_t* cand_ham_out);
 /* Device-pointer form: every pointer is DEVICE memory on h's GPU; kernels are enqueued on
  * `stream`; the call returns after the stream has been checked for candidate-buffer
- * overflow (one 4-byte read-back), so results are complete on return. */
+ * overflow (one 4-byte read-back), so results are complete on return.
+ * Both forms always answer exactly: a batch of >= 64 queries runs ONE tensor-core pass under per-query
+ * thresholds estimated from a strided sample of the rows; the device checks that every query got its
+ * rescore_count candidates and the call is repeated with an exact segment schedule otherwise
+ * (gvdb_profile.optimistic_reruns), and a corpus on which even that overflows a candidate buffer
+ * (thousands of rows tying below a query's threshold, a tombstoned or filtered-out prefix) is answered by
+ * the cut by counting, which has no capacity limit (gvdb_profile.overflow_fallbacks). */
 GVDB_API gvdb_status gvdb_search_batch_device(gvdb_index* h, void* stream, const float* queries_dev,
                                      uint32_t nq, uint32_t k, uint32_t rescore_count,
                                      uint64_t* ids_out_dev, float* scores_out_dev,
@@ -168,7 +174,11 @@ GVDB_API gvdb_status gvdb_search_batch_device(gvdb_index* h, void* stream, const
 /* ---- exact flat search (re-entrant) ------------------------------------------------- */
 /* FaissVectorIndex::search (src/index.rs:620-640) + cosine_distance (:686-700) for a batch:
  * distance = 1 - cos (+inf on a zero norm) over all live rows, ascending, ties by row.
- *   ids_out nq x k (GVDB_NO_ID unfilled), dist_out nq x k (+inf unfilled). */
+ *   ids_out nq x k (GVDB_NO_ID unfilled), dist_out nq x k (+inf unfilled).
+ * Always answers, like the reference: rows are scanned in growing segments under the k-th best distance
+ * so far; when that schedule overflows a candidate buffer (the rows seen first say nothing about the rest:
+ * a tombstoned or filtered-out prefix, a corpus stored in order of relevance) the call is repeated with
+ * fixed segments that cannot overflow (slower; gvdb_profile.overflow_fallbacks counts it). */
 GVDB_API gvdb_status gvdb_flat_search_batch(gvdb_index* h, const float* queries, uint32_t nq, uint32_t k,
                                    uint64_t* ids_out, float* dist_out);
 GVDB_API gvdb_status gvdb_flat_search_batch_device(gvdb_index* h, void* stream, const float* queries_dev,
@@ -188,6 +198,11 @@ GVDB_API gvdb_status gvdb_similarity_search_batch_device(gvdb_index* h, void* st
                                                          float* sims_out_dev);
 
 /* ---- row-sharded search: the two halves around the exchange step -------------------- */
+/* Failure mode of the sharded / staged entry points (gvdb_search_shard[_sliced]_device, gvdb_stage1_device,
+ * gvdb_search_exchange_device): rescore_count <= 2048, and they have no cut-by-counting fallback — a shard on
+ * which the exact segment schedule overflows a candidate buffer (see above) returns GVDB_ERR_INDEX for that
+ * call.  In the peer exchange such a rank publishes an empty candidate list for the step, keeps serving
+ * its peers and reports the error for its own batch only; the exchange stays in step. */
 /* A shard's answer for nq queries is ONE packed record buffer (so the exchange is one
  * all-gather):  [ ids u64 nq x R | ham u32 nq x R | score f32 nq x R ],  16 * nq * R bytes.
  * Per query the R records are in (hamming asc, global row asc) order; unfilled slots are

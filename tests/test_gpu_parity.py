@@ -666,3 +666,122 @@ def test_filtered_search_equals_search_over_the_allowed_rows(gv):
         ids, sc = idx.search_batch(qs[:4], k, R)
         oi, os_ = oracle.multi_stage_search_batch(qs[:4], rows[np.flatnonzero(live)], R, k)
         assert np.array_equal(ids, np.flatnonzero(live)[oi.astype(np.int64)].astype(np.uint64))
+
+
+# ---- corpora on which a threshold learnt from the rows seen first says nothing about the rest ------------------
+def _ordered_corpus(n, dim, qs):
+    """Rows sorted from the farthest to the nearest (cosine to the first query): every later row beats
+    every earlier one, the worst case for any prefix-bootstrapped threshold."""
+    from grape_vector_db_b200 import synth
+    rows = synth.lowrank_rows(0, n, dim)
+    q = qs[0].astype(np.float64)
+    cos = rows.astype(np.float64) @ q / (np.linalg.norm(rows.astype(np.float64), axis=1) * np.linalg.norm(q) + 1e-30)
+    return np.ascontiguousarray(rows[np.argsort(cos, kind="stable")])
+
+
+def test_flat_search_on_a_relevance_ordered_corpus_and_a_tombstoned_prefix(gv):
+    """ADVICE r1 (high): FaissVectorIndex::search always answers (src/index.rs:620-640); so must the GPU
+    flat search when the fast schedule's candidate buffers overflow."""
+    from grape_vector_db_b200 import synth
+    dim, n, k = 64, 60_000, 10
+    qs = synth.lowrank_queries(0, 5, dim)
+    rows = _ordered_corpus(n, dim, qs)
+    with gv.GpuIndex(dim) as idx:
+        idx.add(rows)
+        ids, ds = idx.flat_search_batch(qs, k)
+        fallbacks = idx.profile_read()["overflow_fallbacks"]
+        oi, od = oracle.flat_search_batch(qs, rows, k, nthreads=4)
+        assert np.array_equal(ids, oi) and np.array_equal(_bits(ds), _bits(od))
+        assert fallbacks >= 1, "the ordered corpus was meant to overflow the fast schedule"
+        # rows [0, 8192) removed: the first segment yields nothing, the threshold stays 'everything'
+        for r in range(8192):
+            idx.remove(r)
+        ids, ds = idx.flat_search_batch(qs, k)
+        live = np.ones(n, dtype=bool); live[:8192] = False
+        oi, od = oracle.flat_search_batch(qs, rows, k, live=live, nthreads=4)
+        assert np.array_equal(ids, oi) and np.array_equal(_bits(ds), _bits(od))
+
+
+def test_two_stage_on_a_relevance_ordered_corpus_and_a_tombstoned_prefix(gv):
+    """The single-pass threshold comes from a STRIDED sample, so an ordered corpus costs nothing; a dead
+    prefix or a tiny allow-list leaves sample classes empty and the verified reruns / fallbacks answer."""
+    from grape_vector_db_b200 import synth
+    dim, n, k, R = 128, 80_000, 10, 40
+    qs = synth.lowrank_queries(0, 96, dim)
+    rows = _ordered_corpus(n, dim, qs)
+    with gv.GpuIndex(dim) as idx:
+        idx.add(rows)
+        ids, sc = idx.search_batch(qs, k, R)
+        oi, os_ = oracle.multi_stage_search_batch(qs, rows, R, k, nthreads=8)
+        assert np.array_equal(ids, oi) and np.array_equal(_bits(sc), _bits(os_))
+        for r in range(20_000):
+            idx.remove(r)
+        ids, sc = idx.search_batch(qs, k, R)
+        oi, os_ = oracle.multi_stage_search_batch(qs, rows[20_000:], R, k, nthreads=8)
+        assert np.array_equal(ids, oi + np.uint64(20_000)) and np.array_equal(_bits(sc), _bits(os_))
+
+
+def test_concurrent_callers_get_the_serial_answers(gv):
+    """VectorIndex: Send + Sync — searches run under a read guard from many runtime workers
+    (src/lib.rs:469-477).  Four threads call gvdb_search_batch on one index at once, each with its own
+    batches (tensor-core and CUDA-core sized); every answer must equal the serial one and the oracle's."""
+    import threading
+    from grape_vector_db_b200 import synth
+    dim, n, k, R = 768, 50_000, 10, 40
+    rows = synth.lowrank_rows(0, n, dim)
+    batches = [synth.lowrank_queries(100 * t, nq, dim) for t, nq in enumerate((96, 7, 130, 1, 64, 33, 200, 2))]
+    with gv.GpuIndex(dim) as idx:
+        idx.add(rows)
+        serial = [idx.search_batch(b, k, R) for b in batches]
+        got = [None] * len(batches)
+        errs = []
+
+        def worker(t):
+            try:
+                for rep in range(6):
+                    for j in range(t, len(batches), 4):
+                        got[j] = idx.search_batch(batches[j], k, R)
+                        assert np.array_equal(got[j][0], serial[j][0]) and np.array_equal(_bits(got[j][1]), _bits(serial[j][1]))
+            except Exception as e:  # noqa: BLE001
+                errs.append(repr(e))
+        th = [threading.Thread(target=worker, args=(t,)) for t in range(4)]
+        [t.start() for t in th]
+        [t.join() for t in th]
+        assert not errs, errs
+    for j in (0, 2, 6):
+        oi, os_ = oracle.multi_stage_search_batch(batches[j], rows, R, k, nthreads=8)
+        assert np.array_equal(serial[j][0], oi) and np.array_equal(_bits(serial[j][1]), _bits(os_))
+
+
+def test_configs2_sized_shard_properties(gv):
+    """BASELINE configs[2] at full size on one GPU (10M x 1536, 61 GB of f32 rows): a 1024-query batch; a sample
+    of the queries is verified without holding the rows on the host — stage 1 == the R smallest (hamming, row)
+    keys of a host popcount over the codes read back from the index, scores == the oracle's cosine on those rows
+    (regenerated), order == (cosine desc, stage-1 position)."""
+    import torch
+    from grape_vector_db_b200 import synth
+    free, _ = torch.cuda.mem_get_info(0)
+    n, dim, nq, k, R, checked = 10_000_000, 1536, 1024, 10, 40, 3
+    if free < 75 * 2**30:
+        pytest.skip("needs ~70 GB of free HBM")
+    dev = torch.device("cuda", 0)
+    with gv.GpuIndex(dim, device=0, capacity_rows=n) as idx:
+        for i in range(0, n, 131072):
+            idx.add_device(synth.lowrank_rows_torch(i, min(131072, n - i), dim, dev))
+        qs = synth.lowrank_queries(0, nq, dim)
+        ids_t, sc_t = idx.search_batch_device(torch.from_numpy(qs).to(dev), k, R)
+        torch.cuda.synchronize()
+        ids, sc, ci, ch = idx.search_batch(qs[:checked], k, R, want_candidates=True)
+        assert np.array_equal(ids, ids_t[:checked].cpu().numpy().astype(np.uint64))
+        assert np.array_equal(_bits(sc), _bits(sc_t[:checked].cpu().numpy()))
+        codes = idx.get_codes()
+    for qi in range(checked):
+        qc = oracle.quantize(qs[qi])
+        ham = np.bitwise_count(np.bitwise_xor(codes.view(np.uint64), qc.view(np.uint64)[None, :])).sum(axis=1, dtype=np.int64)
+        assert np.array_equal(ham[:500], oracle.hamming_all(qc, codes[:500]).astype(np.int64))
+        key = (ham << 32) | np.arange(n, dtype=np.int64)
+        order = np.sort(np.partition(key, R)[:R]) & 0xFFFFFFFF
+        assert np.array_equal(ci[qi], order.astype(np.uint64)) and np.array_equal(ch[qi], ham[order].astype(np.uint32))
+        cos = np.array([oracle.cosine_similarity(qs[qi], synth.lowrank_rows(int(r), 1, dim)[0]) for r in order], dtype=np.float32)
+        fin = np.argsort(-cos, kind="stable")[:k]
+        assert np.array_equal(ids[qi], order[fin].astype(np.uint64)) and np.array_equal(_bits(sc[qi]), _bits(cos[fin]))
