@@ -960,18 +960,42 @@ rescore_topk_kernel(const float* __restrict__ rows, const float* __restrict__ no
 // entries; lane l TMA-copies its candidate row and its query row (entries of one warp may belong
 // to many queries), folds ||q||^2 and the dot product left to right, writes out_score[pair] (or, for
 // the peer exchange, the pair's slot in its requester's mailbox).
+// done_counter / flag fields (peer exchange): the last block to finish publishes flag[kind][rank] := epoch in
+// every peer's mailbox — the cosines this kernel stored into the peers' mailboxes are complete.
+struct OwnedSignal {
+    uint64_t flags_off;
+    uint32_t kind, world, rank, epoch, flag_stride;
+    uint32_t* done;          // nullptr: no signal
+};
+__device__ __forceinline__ void owned_block_done(const OwnedSignal& sg, uint8_t* const* peers, uint32_t total_blocks) {
+    if (!sg.done) return;
+    __threadfence_system();
+    __syncwarp();
+    if (threadIdx.x == 0) {
+        const uint32_t prev = atomicAdd(sg.done, 1u);
+        if (prev + 1 == total_blocks) {
+            __threadfence_system();
+            for (uint32_t w = 0; w < sg.world; ++w) {
+                uint32_t* f = reinterpret_cast<uint32_t*>(peers[w] + sg.flags_off) + (size_t)(sg.kind * sg.world + sg.rank) * sg.flag_stride;
+                asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(f), "r"(sg.epoch) : "memory");
+            }
+            *sg.done = 0u;
+        }
+    }
+}
+
 __global__ void __launch_bounds__(32)
 rescore_owned_list_kernel(const float* __restrict__ rows, const float* __restrict__ norms, uint64_t row_base,
                           int dim, int stride, const float* __restrict__ queries, const uint64_t* __restrict__ keys,
                           const uint32_t* __restrict__ list, const uint32_t* __restrict__ list_count, uint32_t R,
                           float* __restrict__ out_score, uint8_t* const* __restrict__ peers, uint64_t peer_off,
-                          uint32_t pairs_per_peer) {
+                          uint32_t pairs_per_peer, OwnedSignal sg) {
     extern __shared__ __align__(16) float srow[];            // 32 candidate rows, then 32 query rows
     float* sq = srow + (size_t)32 * stride;
     const int lane = threadIdx.x;
     const uint32_t n_list = *list_count;
     const uint32_t i = blockIdx.x * 32u + lane;
-    if (blockIdx.x * 32u >= n_list) return;                  // warp-uniform
+    if (blockIdx.x * 32u >= n_list) { owned_block_done(sg, peers, gridDim.x); return; }   // warp-uniform
     const bool valid = i < n_list;
     const uint32_t p = valid ? list[i] : 0u;
     const uint32_t q = p / R;
@@ -1027,6 +1051,109 @@ rescore_owned_list_kernel(const float* __restrict__ rows, const float* __restric
         const float cosv = (na == 0.0f || nb == 0.0f) ? 0.0f : __fdiv_rn(dot, __fmul_rn(na, nb));
         // peer exchange: pair p belongs to rank p / pairs_per_peer; its cosine is stored straight into that
         // rank's mailbox (a posted store over NVLink), at peer_off + (p % pairs_per_peer) floats
+        if (peers) reinterpret_cast<float*>(peers[p / pairs_per_peer] + peer_off)[p % pairs_per_peer] = cosv;
+        else out_score[p] = cosv;
+    }
+    owned_block_done(sg, peers, gridDim.x);
+}
+
+// rescore_owned_ring_kernel: rescore_owned_list_kernel with the staging of rescore_topk_kernel — one warp per
+// 32 list entries, rows AND query rows streamed through a two-deep ring of RO_SLAB-column slabs (one TMA
+// bulk copy per row and slab), so that ten warps fit an SM instead of one.  Entries of a warp that share a
+// query share one staged copy of it (the list is nearly sorted by query); a warp whose entries span more
+// than RO_QSLOTS queries goes through its entries in rounds of RO_QSLOTS queries.
+constexpr int RO_SLAB = 64;
+constexpr int RO_STRIDE = RO_SLAB + 4;
+constexpr int RO_QSLOTS = 8;
+constexpr int RO_WARPS = 2;
+constexpr size_t RO_SMEM = (size_t)RO_WARPS * 2 * (32 + RO_QSLOTS) * RO_STRIDE * sizeof(float);
+
+__global__ void __launch_bounds__(32 * RO_WARPS)
+rescore_owned_ring_kernel(const float* __restrict__ rows, const float* __restrict__ norms, uint64_t row_base, int dim,
+                          const float* __restrict__ queries, const uint64_t* __restrict__ keys,
+                          const uint32_t* __restrict__ list, const uint32_t* __restrict__ list_count, uint32_t R,
+                          float* __restrict__ out_score, uint8_t* const* __restrict__ peers, uint64_t peer_off,
+                          uint32_t pairs_per_peer) {
+    extern __shared__ __align__(16) float ro_smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float* s_ring = ro_smem + (size_t)warp * 2 * (32 + RO_QSLOTS) * RO_STRIDE;     // slot s: 32 rows then RO_QSLOTS queries
+    __shared__ __align__(8) uint64_t s_bar[2 * RO_WARPS];
+    const uint32_t bar0 = smem_u32(&s_bar[2 * warp]);
+    if (lane == 0) { mbar_init(bar0, 1); mbar_init(bar0 + 8, 1); fence_mbar_init(); }
+    __syncwarp();
+    const uint32_t n_list = *list_count;
+    const uint32_t i = (blockIdx.x * RO_WARPS + warp) * 32u + lane;
+    if ((blockIdx.x * RO_WARPS + warp) * 32u >= n_list) return;          // warp-uniform
+    const bool valid = i < n_list;
+    const uint32_t p = valid ? list[i] : 0u;
+    const uint32_t q = p / R;
+    const uint64_t key = valid ? keys[p] : 0ull;
+    const uint32_t my_row = (uint32_t)((key & ((1ull << 40) - 1)) - row_base);
+    // slot of my query among the warp's distinct queries (leaders in lane order)
+    const uint32_t same_q = __match_any_sync(0xffffffffu, valid ? q : 0xFFFFFFFFu - (uint32_t)lane);
+    const int q_lane = __ffs(same_q) - 1;
+    const bool q_leader = valid && lane == q_lane;
+    const uint32_t leaders = __ballot_sync(0xffffffffu, q_leader);
+    const int my_slot = __popc(leaders & ((1u << q_lane) - 1u));
+    const int n_rounds = (__popc(leaders) + RO_QSLOTS - 1) / RO_QSLOTS;
+    const int n_slabs = (dim + RO_SLAB - 1) / RO_SLAB;
+    uint32_t uses = 0;                                       // ring slot uses so far (barrier phases)
+    float cosv = 0.0f;
+    for (int round = 0; round < n_rounds; ++round) {
+        const bool mine = valid && my_slot / RO_QSLOTS == round;
+        const bool lead = q_leader && my_slot / RO_QSLOTS == round;
+        const int qs = my_slot % RO_QSLOTS;
+        const uint32_t n_copies = __popc(__ballot_sync(0xffffffffu, mine)) + __popc(__ballot_sync(0xffffffffu, lead));
+        auto issue = [&](int sl, uint32_t u) {
+            const int c0 = sl * RO_SLAB;
+            const uint32_t bytes = (uint32_t)min(RO_SLAB, dim - c0) * 4u;
+            const uint32_t bar = bar0 + 8u * (u & 1u);
+            float* base = s_ring + (size_t)(u & 1u) * (32 + RO_QSLOTS) * RO_STRIDE;
+            if (lane == 0) mbar_expect_tx(bar, n_copies * bytes);
+            __syncwarp();
+            if (mine) tma_bulk_g2s(smem_u32(base + (size_t)lane * RO_STRIDE), rows + (size_t)my_row * dim + c0, bytes, bar);
+            if (lead) tma_bulk_g2s(smem_u32(base + (size_t)(32 + qs) * RO_STRIDE), queries + (size_t)q * dim + c0, bytes, bar);
+        };
+        float dot = 0.0f, qq2 = 0.0f;
+        if (n_copies) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            issue(0, uses);
+            for (int sl = 0; sl < n_slabs; ++sl) {
+                const uint32_t u = uses + (uint32_t)sl;
+                if (sl + 1 < n_slabs) {
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    __syncwarp();
+                    issue(sl + 1, u + 1);
+                }
+                while (!mbar_try_wait(bar0 + 8u * (u & 1u), (u >> 1) & 1u)) {}
+                if (mine) {
+                    const float* base = s_ring + (size_t)(u & 1u) * (32 + RO_QSLOTS) * RO_STRIDE;
+                    const int nv = min(RO_SLAB, dim - sl * RO_SLAB) >> 2;
+                    const float4* r4 = reinterpret_cast<const float4*>(base + (size_t)lane * RO_STRIDE);
+                    const float4* q4 = reinterpret_cast<const float4*>(base + (size_t)(32 + qs) * RO_STRIDE);
+#pragma unroll 8
+                    for (int v = 0; v < nv; ++v) {
+                        const float4 a = q4[v], b = r4[v];
+                        dot = __fadd_rn(dot, __fmul_rn(a.x, b.x));
+                        dot = __fadd_rn(dot, __fmul_rn(a.y, b.y));
+                        dot = __fadd_rn(dot, __fmul_rn(a.z, b.z));
+                        dot = __fadd_rn(dot, __fmul_rn(a.w, b.w));
+                        qq2 = __fadd_rn(qq2, __fmul_rn(a.x, a.x));
+                        qq2 = __fadd_rn(qq2, __fmul_rn(a.y, a.y));
+                        qq2 = __fadd_rn(qq2, __fmul_rn(a.z, a.z));
+                        qq2 = __fadd_rn(qq2, __fmul_rn(a.w, a.w));
+                    }
+                }
+            }
+            uses += (uint32_t)n_slabs;
+        }
+        if (mine) {
+            const float na = __fsqrt_rn(qq2), nb = norms[my_row];
+            cosv = (na == 0.0f || nb == 0.0f) ? 0.0f : __fdiv_rn(dot, __fmul_rn(na, nb));
+        }
+    }
+    if (valid) {
         if (peers) reinterpret_cast<float*>(peers[p / pairs_per_peer] + peer_off)[p % pairs_per_peer] = cosv;
         else out_score[p] = cosv;
     }
@@ -1094,6 +1221,44 @@ __global__ void topk_kernel(const uint64_t* __restrict__ rec_ids, const float* _
             uint32_t pos = (uint32_t)key;
             ids_out[(size_t)q * k + t] = ids[pos];
             scores_out[(size_t)q * k + t] = sc[pos];
+        }
+    }
+}
+
+// topk_owned_kernel: topk_kernel for the owner-computes layouts with gather_owner_scores_kernel folded in: the
+// score of candidate i of query q is the one its row's owner computed, by_owner[owner][q * R + i].
+__global__ void topk_owned_kernel(const uint64_t* __restrict__ keys, const float* __restrict__ by_owner,
+                                  uint32_t n_owners, uint64_t rows_per_owner, uint32_t nq, uint32_t R, uint32_t n_eff,
+                                  uint32_t k, uint64_t* __restrict__ ids_out, float* __restrict__ scores_out) {
+    extern __shared__ __align__(16) uint64_t skeys[];
+    const uint32_t q = blockIdx.x;
+    const size_t n_pairs = (size_t)nq * R;
+    auto score_of = [&](uint32_t i, uint64_t& row) {
+        const uint64_t key = keys[(size_t)q * R + i];
+        row = key & ((1ull << 40) - 1);
+        const uint64_t owner = min((uint64_t)n_owners - 1, row / rows_per_owner);
+        return by_owner[owner * n_pairs + (size_t)q * R + i];
+    };
+    for (uint32_t i = threadIdx.x; i < n_eff; i += blockDim.x) {
+        uint64_t key = UINT64_MAX;
+        if (i < R && keys[(size_t)q * R + i] != UINT64_MAX) {
+            uint64_t row;
+            key = ((uint64_t)(~f32_asc_key(score_of(i, row))) << 32) | i;
+        }
+        skeys[i] = key;
+    }
+    __syncthreads();
+    bitonic_sort_smem(skeys, n_eff);
+    for (uint32_t t = threadIdx.x; t < k; t += blockDim.x) {
+        const uint64_t key = t < n_eff ? skeys[t] : UINT64_MAX;
+        if (key == UINT64_MAX) {
+            ids_out[(size_t)q * k + t] = UINT64_MAX;
+            scores_out[(size_t)q * k + t] = -INFINITY;
+        } else {
+            uint64_t row;
+            const float sc = score_of((uint32_t)key, row);
+            ids_out[(size_t)q * k + t] = row;
+            scores_out[(size_t)q * k + t] = sc;
         }
     }
 }
