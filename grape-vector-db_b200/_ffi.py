@@ -45,13 +45,15 @@ class GvdbProfile(C.Structure):
                 ("tc_ms", C.c_double), ("tc_macs", C.c_double), ("tc_bytes", C.c_double),
                 ("scatter_ms", C.c_double), ("optimistic_reruns", C.c_uint64),
                 ("overflow_fallbacks", C.c_uint64), ("exchange_ms", C.c_double),
-                ("exchange_wait_ms", C.c_double), ("sample_ms", C.c_double)]
+                ("exchange_wait_ms", C.c_double), ("sample_ms", C.c_double), ("dot_ms", C.c_double),
+                ("dot_launches", C.c_uint64), ("dot_macs", C.c_double), ("ratio_fallback_queries", C.c_uint64)]
 
 
 # every symbol include/gvdb.h declares: name -> (restype, argtypes)
 _vp, _u32, _u64, _i32 = C.c_void_p, C.c_uint32, C.c_uint64, C.c_int32
 SYMBOLS = {
     "gvdb_abi_version": (_u32, []),
+    "gvdb_approx_dot": (_i32, [_vp, _vp, _u32, _vp]),
     "gvdb_measure_fp4_mma_rate": (_i32, [_i32, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "gvdb_last_error": (C.c_char_p, []),
     "gvdb_create": (_i32, [C.POINTER(GvdbConfig), C.POINTER(_vp)]),

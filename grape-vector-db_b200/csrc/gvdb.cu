@@ -31,6 +31,7 @@
 #include "gvdb_bigr.cuh"
 #include "gvdb_sparse.cuh"
 #include "gvdb_xchg.cuh"
+#include "gvdb_ratio.cuh"
 
 namespace {
 
@@ -65,7 +66,7 @@ struct DevBuf {
     template <class T> T* as() const { return reinterpret_cast<T*>(p); }
 };
 
-enum Kind { K_SCAN = 0, K_SELECT, K_RESCORE, K_TOPK, K_PREP, K_FLAT, K_MERGE, K_TCSCAN, K_SAMPLE, K_SCATTER, K_XCHG, K_XCHG_WAIT, K_COUNT };
+enum Kind { K_SCAN = 0, K_SELECT, K_RESCORE, K_TOPK, K_PREP, K_FLAT, K_MERGE, K_TCSCAN, K_SAMPLE, K_SCATTER, K_XCHG, K_XCHG_WAIT, K_TCDOT, K_COUNT };
 struct ProfRec {
     int kind;
     cudaEvent_t e0, e1;
@@ -92,6 +93,9 @@ struct Workspace {
     DevBuf qexp, qpop, qbase;        // tcgen05 path: pre-expanded queries (+ bias digits), popc(q), popc(q) + bias
     DevBuf tilemin;                  // tcgen05 path: per-(sample tile, query) minima of the single-pass search
     DevBuf tc_recs, list_counts;     // tcgen05 path: warp-private survivor records
+    DevBuf r_q16, r_thr, r_state, r_counts, r_ecnt, r_ekeys, r_esc, r_fb, r_topk_i, r_topk_s, r_list, r_misc;   // ratio mode (gvdb_ratio.cuh)
+    uint32_t* h_fb = nullptr;        // pinned: per-query fallback flags of a ratio-mode tile
+    size_t h_fb_bytes = 0;
     DevBuf big_keys, big_keys2, big_aux, big_k32, big_v32, big_tmp;   // large-R path (gvdb_bigr.cuh)
     uint32_t* h_flag = nullptr;      // pinned
     const uint32_t* live_eff = nullptr;   // per-call row filter ANDed with the tombstone bitmap (filtered searches)
@@ -100,10 +104,12 @@ struct Workspace {
     size_t h_res_bytes = 0;
     ~Workspace() {
         for (DevBuf* b : {&qpack, &qnorm, &cnt, &flag, &buf, &rec_ham, &rec_ids, &rec_score, &q_in,
-                          &ids_out, &sc_out, &codes_tmp, &misc, &qexp, &qpop, &qbase, &tilemin, &tc_recs, &list_counts,
+                          &ids_out, &sc_out, &codes_tmp, &misc, &qexp, &qpop, &qbase, &tilemin, &tc_recs, &list_counts, &r_q16, &r_thr, &r_state, &r_counts, &r_ecnt, &r_ekeys,
+                          &r_esc, &r_fb, &r_topk_i, &r_topk_s, &r_list, &r_misc,
                           &big_keys, &big_keys2, &big_aux, &big_k32, &big_v32, &big_tmp, &filt, &allow_in}) b->release();
         if (h_flag) cudaFreeHost(h_flag);
         if (h_res) cudaFreeHost(h_res);
+        if (h_fb) cudaFreeHost(h_fb);
         for (cudaEvent_t e : ev_pool) cudaEventDestroy(e);
         if (idle) cudaEventDestroy(idle);
         if (stream) cudaStreamDestroy(stream);
@@ -152,6 +158,12 @@ struct gvdb_index {
     uint4* codes = nullptr;
     float* norms = nullptr;
     uint32_t* live = nullptr;
+    // ratio mode (gvdb_ratio.cuh): bf16 copy of the rows blocked for the tensor-core pass + 1 / |row|, built on
+    // first use and rebuilt after the row count changed
+    uint4* rows16 = nullptr;
+    float* rinv = nullptr;
+    uint64_t rows16_rows = 0, rows16_cap = 0;
+    std::mutex rows16_mu;
     bool windowed = false;           // GVDB_FLAG_ROW_WINDOW: f32 rows kept for [win_first, win_first + win_count) only
     uint64_t win_first = 0, win_count = 0;
     // rows[(r - win_first) * dim] is local row r's data; kernels index with the local row number
@@ -174,6 +186,7 @@ struct gvdb_index {
     uint32_t seg0_rows = 4096; // GVDB_SEG0_ROWS: rows of the first ("emit everything") segment
     uint32_t tc_qb_force = 0;  // GVDB_TC_QB: force the query blocks per tensor-core work item (0 = model)
     uint32_t opt_m = 5;        // GVDB_OPT_M: smallest order statistic of the single-pass threshold (0 = single pass off)
+    bool ratio_tc = true;      // GVDB_RATIO_TC=0: ratio mode always by the cut by counting
     uint32_t sample_div = 16;  // GVDB_SAMPLE_DIV: the single-pass sample is 1/sample_div of the row groups
     uint32_t seg_growth = 16;  // GVDB_SEG_GROWTH: cap on the geometric segment growth (0 = cap/(4R) only)
     std::atomic<int> profile_on{0};
@@ -246,6 +259,7 @@ void flush_profile(gvdb_index* h, Workspace* ws) {
                            h->prof.tc_bytes += r.bytes; h->prof.tc_macs += r.pairs; break;
             case K_SAMPLE: h->prof.sample_ms += ms; break;
             case K_SCATTER: h->prof.scatter_ms += ms; break;
+            case K_TCDOT: h->prof.dot_ms += ms; h->prof.dot_launches += 1; h->prof.dot_macs += r.pairs; break;
             case K_XCHG: h->prof.exchange_ms += ms; break;
             case K_XCHG_WAIT: h->prof.exchange_wait_ms += ms; break;
         }
@@ -418,7 +432,7 @@ void launch_tc_scan(gvdb_index* h, Workspace* ws, cudaStream_t st, uint32_t tile
                     uint32_t ngroups, uint32_t group_stride, uint32_t nq, uint32_t nq_pad, uint32_t* cnt,
                     uint64_t* buf, uint32_t cap, uint32_t* overflow, uint32_t* dist_out, uint64_t dist_stride,
                     uint32_t expect_per_query = 0) {
-    const TcSplit sp = tc_split(h, ngroups, nq_pad, MODE == 2);
+    const TcSplit sp = tc_split(h, ngroups, nq_pad, MODE == 2 || MODE == 3);   // one query block per item: per-lane state
     const uint32_t grid = sp.grid;
     const uint32_t nlists = grid * TC_EPI_WARPS;
     const size_t smem = (size_t)tc_qblocks(h->nchunk) * tc_qblock_bytes(h->nchunk);
@@ -895,6 +909,223 @@ void search_big_r(gvdb_index* h, Workspace* ws, cudaStream_t st, const float* q_
     flush_profile(h, ws);
 }
 
+__global__ void ratio_rinv_kernel(const float* __restrict__ norms, uint64_t n, float* __restrict__ rinv) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) rinv[i] = norms[i] > 0.0f ? 1.0f / norms[i] : 0.0f;
+}
+int ratio_units(const gvdb_index* h) { return (h->dim + 31) / 32; }
+bool ratio_supported(const gvdb_index* h) {
+    const int nu = ratio_units(h);
+    return !h->windowed && (h->dim & 3) == 0 && (nu == 2 || nu == 4 || nu == 8 || nu == 12 || nu == 16 || nu == 24) &&
+           tc_supported(h->nchunk);
+}
+// bf16 rows + reciprocal norms for every stored row (rebuilt when rows were added; searches hold the caller's read guard)
+void ensure_rows16(gvdb_index* h, cudaStream_t st) {
+    std::lock_guard<std::mutex> lk(h->rows16_mu);
+    if (h->rows16_rows == h->n_rows) return;
+    const int nu = ratio_units(h);
+    if (h->rows16_cap < h->n_rows) {
+        if (h->rows16) CU(cudaFree(h->rows16));
+        if (h->rinv) CU(cudaFree(h->rinv));
+        h->rows16 = nullptr; h->rinv = nullptr; h->rows16_cap = 0;
+        const uint64_t cap = (std::max<uint64_t>(h->cap_rows, h->n_rows) + 31) / 32 * 32;
+        CU(cudaMalloc((void**)&h->rows16, cap * (size_t)nu * 64));
+        CU(cudaMalloc((void**)&h->rinv, cap * sizeof(float)));
+        h->rows16_cap = cap;
+        h->rows16_rows = 0;
+    }
+    const uint64_t first = h->rows16_rows, n = h->n_rows - first;
+    // rows of a partially filled last tile are rewritten together with the new ones (their slots hold stale data otherwise)
+    if (first == 0) CU(cudaMemsetAsync(h->rows16, 0, h->rows16_cap * (size_t)nu * 64, st));
+    const uint64_t work = n * (uint64_t)nu;
+    ratio_rows16_kernel<<<(unsigned)((work + 255) / 256), 256, 0, st>>>(h->rows, first, n, h->dim, nu, h->rows16);
+    ratio_rinv_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(h->norms + first, n, h->rinv + first);
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(st));
+    h->rows16_rows = h->n_rows;
+}
+
+template <int MODE>
+void launch_tc_dot(gvdb_index* h, Workspace* ws, cudaStream_t st, const int8_t* q16, const float* thr, uint32_t nq,
+                   uint32_t nq_pad, uint2* recs, uint32_t rec_cap, uint32_t* list_counts, uint32_t* overflow,
+                   float* dot_out, uint64_t dot_stride, uint32_t* grid_out) {
+    const int nu = ratio_units(h);
+    const uint32_t n_tiles = (uint32_t)tiles_for(h->n_rows), ngroups = (n_tiles + 3) / 4, nqb = nq_pad / TC_NQ;
+    const uint32_t sms = (uint32_t)h->sm_count;
+    // row slices: a few items per CTA, never more than one slice per row group
+    const uint32_t rsl = std::max<uint32_t>(1, std::min<uint32_t>(ngroups, (4 * sms + nqb - 1) / nqb));
+    const uint32_t grid = (uint32_t)std::min<uint64_t>((uint64_t)rsl * nqb, sms);
+    if (grid_out) *grid_out = grid;
+    const size_t smem = (size_t)((nu + 1) / 2) * TC_STAGE_BYTES;
+    Timed t(h, ws, st, K_TCDOT, (double)h->n_rows * nu * 64.0 * nqb, (double)h->n_rows * nq_pad * (nu * 32.0));
+#define GVDB_DOT_CASE(N)                                                                             \
+    case N: {                                                                                        \
+        static std::atomic<uint64_t> attr_done{0};                                                   \
+        ensure_dyn_smem(attr_done, tc_dot_kernel<N, MODE>, (int)(((N + 1) / 2) * TC_STAGE_BYTES));   \
+        tc_dot_kernel<N, MODE><<<grid, TC_THREADS, smem, st>>>(h->rows16, live_of(h, ws), h->rinv, n_tiles, ngroups, q16, thr, nq, \
+                                                               nq_pad, rsl, recs, rec_cap, list_counts, overflow, dot_out,        \
+                                                               dot_stride, h->n_rows);                                            \
+        break;                                                                                       \
+    }
+    switch (nu) {
+        GVDB_DOT_CASE(2) GVDB_DOT_CASE(4) GVDB_DOT_CASE(8) GVDB_DOT_CASE(12) GVDB_DOT_CASE(16) GVDB_DOT_CASE(24)
+        default: fail(GVDB_ERR_NOT_IMPLEMENTED, "tensor-core dot products: unsupported dimension");
+    }
+#undef GVDB_DOT_CASE
+    CU(cudaGetLastError());
+}
+
+// ---- ratio mode on the tensor cores (gvdb_ratio.cuh): one tile of <= query_tile queries ------------------------------
+// Returns false when the tile was not handled (the caller runs the cut by counting for it).
+bool search_ratio_tile(gvdb_index* h, Workspace* ws, cudaStream_t st, const float* q_dev, uint32_t nq, uint32_t k, uint32_t R,
+                       uint64_t* ids_out, float* scores_out) {
+    constexpr uint32_t Rf = 256;                              // rescore count of the fast path that seeds the bound
+    const uint32_t K = (uint32_t)h->nchunk * 128;
+    const uint32_t nq_pad = (nq + TC_NQ - 1) / TC_NQ * TC_NQ;
+    const uint32_t ntiles = (uint32_t)tiles_for(h->n_rows), ngroups = (ntiles + 3) / 4;
+    const int nu = ratio_units(h);
+    // 1. fast path: records (stage-1 order) + top k of the Rf closest rows in Hamming distance
+    ws->rec_ham.ensure((size_t)nq * Rf * 4);
+    ws->rec_ids.ensure((size_t)nq * Rf * 8);
+    ws->rec_score.ensure((size_t)nq * Rf * 4);
+    ws->r_topk_i.ensure((size_t)nq * k * 8);
+    ws->r_topk_s.ensure((size_t)nq * k * 4);
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        bool optimistic = false;
+        FusedTopk fused;
+        fused.k = k; fused.ids_out = ws->r_topk_i.as<uint64_t>(); fused.scores_out = ws->r_topk_s.as<float>();
+        fused.want_records = true;
+        search_core(h, ws, st, q_dev, nq, Rf, ws->rec_ham.as<uint32_t>(), ws->rec_ids.as<uint64_t>(), ws->rec_score.as<float>(),
+                    true, attempt == 0, &optimistic, nullptr, &fused);
+        if (!fused.done)
+            launch_topk(h, ws, st, ws->rec_ids.as<uint64_t>(), ws->rec_score.as<float>(), nq, Rf, k, ws->r_topk_i.as<uint64_t>(),
+                        ws->r_topk_s.as<float>());
+        bool overflowed = false;
+        if (check_overflow(h, ws, st, optimistic, &overflowed)) continue;
+        if (overflowed) return false;
+        break;
+    }
+    ensure_rows16(h, st);
+    // 2. b*: counting passes of the FP4 scan.  The query blocks (ws->qexp, qpop) are the fast path's; the first guess
+    //    comes from the distances of a strided sample of row groups.
+    ws->r_state.ensure((size_t)nq * sizeof(RatioState));
+    ws->r_counts.ensure((size_t)nq_pad * 4 + 256);
+    ws->r_fb.ensure((size_t)nq_pad * 4);
+    CU(cudaMemsetAsync(ws->r_fb.p, 0, (size_t)nq_pad * 4, st));
+    uint32_t* n_active = ws->r_counts.as<uint32_t>() + nq_pad;      // one word behind the counts
+    {
+        const uint32_t n_s = std::min<uint32_t>(ngroups, 64), stride_g = std::max<uint32_t>(1, ngroups / n_s);
+        const uint32_t n_sample = n_s * TC_ROWS;
+        ws->r_misc.ensure((size_t)nq * n_sample * 4);
+        tc_update_bias(h, ws, st, nq, nq_pad, 1);
+        // group_stride 1 writes by row number: the compact form needs a stride > 1; a corpus of <= 64 groups is its own sample
+        if (stride_g > 1)
+            launch_tc_scan<1>(h, ws, st, 0, ntiles, n_s, stride_g, nq, nq_pad, nullptr, nullptr, 0, nullptr, ws->r_misc.as<uint32_t>(), n_sample);
+        else {
+            CU(cudaMemsetAsync(ws->r_misc.p, 0xFF, (size_t)nq * n_sample * 4, st));
+            launch_tc_scan<1>(h, ws, st, 0, ntiles, ngroups, 1, nq, nq_pad, nullptr, nullptr, 0, nullptr, ws->r_misc.as<uint32_t>(), n_sample);
+        }
+        ratio_bstar_init_kernel<<<nq, 256, (K + 1) * 4, st>>>(ws->r_misc.as<uint32_t>(), n_sample, stride_g > 1 ? n_sample : (uint32_t)std::min<uint64_t>(n_sample, h->n_rows),
+                                                              K + 1, R, stride_g > 1 ? h->n_rows : h->n_rows, ws->r_state.as<RatioState>(),
+                                                              ws->qpack.as<uint32_t>(), h->qs, h->nchunk * 4);
+        CU(cudaGetLastError());
+    }
+    bool converged = false;
+    for (int pass = 0; pass < 24 && !converged; ++pass) {
+        tc_update_bias(h, ws, st, nq, nq_pad, 0);
+        CU(cudaMemsetAsync(ws->r_counts.p, 0, (size_t)nq_pad * 4 + 256, st));
+        launch_tc_scan<3>(h, ws, st, 0, ntiles, ngroups, 1, nq, nq_pad, nullptr, nullptr, 0, nullptr, ws->r_counts.as<uint32_t>(), 0);
+        ratio_bstar_update_kernel<<<(nq + 127) / 128, 128, 0, st>>>(ws->r_state.as<RatioState>(), ws->r_counts.as<uint32_t>(), nq, R, K,
+                                                                   ws->qpack.as<uint32_t>(), h->qs, h->nchunk * 4, n_active);
+        CU(cudaGetLastError());
+        CU(cudaMemcpyAsync(ws->h_flag + 4, n_active, 4, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        converged = ws->h_flag[4] == 0;
+    }
+    if (!converged) return false;
+    // 3. the dense filter: rows whose approximate cosine beats (the fast path's k-th best) - eps
+    ws->r_thr.ensure((size_t)nq_pad * 4);
+    ratio_threshold_kernel<<<(nq_pad + 127) / 128, 128, 0, st>>>(ws->r_topk_s.as<float>(), k, ws->qnorm.as<float>(), nq, nq_pad, RATIO_EPS,
+                                                                ws->r_thr.as<float>(), ws->r_fb.as<uint32_t>());
+    ws->r_q16.ensure((size_t)(nq_pad / TC_NQ) * tc_qblock_bytes(nu));
+    {
+        const uint64_t words = (uint64_t)nq_pad * nu * 16;
+        ratio_q16_kernel<<<(unsigned)((words + 255) / 256), 256, 0, st>>>(q_dev, nq, nq_pad, h->dim, nu, ws->r_q16.as<int8_t>());
+    }
+    const uint32_t rec_cap = 16384;
+    const uint32_t nlists_max = (uint32_t)h->sm_count * TC_EPI_WARPS;
+    ws->tc_recs.ensure((size_t)nlists_max * rec_cap * sizeof(uint2));
+    ws->list_counts.ensure((size_t)nlists_max * 4);
+    CU(cudaMemsetAsync(ws->list_counts.p, 0, (size_t)nlists_max * 4, st));
+    uint32_t grid = 0;
+    launch_tc_dot<0>(h, ws, st, ws->r_q16.as<int8_t>(), ws->r_thr.as<float>(), nq, nq_pad, ws->tc_recs.as<uint2>(), rec_cap,
+                     ws->list_counts.as<uint32_t>(), ws->flag.as<uint32_t>(), nullptr, 0, &grid);
+    // 4. survivors -> E lists -> exact rescoring -> merge with the fast path's records
+    ws->r_ecnt.ensure((size_t)nq * 4);
+    ws->r_ekeys.ensure((size_t)nq * RATIO_E_CAP * 8);
+    ws->r_esc.ensure((size_t)nq * RATIO_E_CAP * 4);
+    CU(cudaMemsetAsync(ws->r_ecnt.p, 0, (size_t)nq * 4, st));
+    CU(cudaMemsetAsync(ws->r_ekeys.p, 0xFF, (size_t)nq * RATIO_E_CAP * 8, st));
+    h->launches.fetch_add(6, std::memory_order_relaxed);
+    ratio_scatter_kernel<<<dim3(4, grid * TC_EPI_WARPS), 256, 0, st>>>(
+        ws->tc_recs.as<uint2>(), rec_cap, ws->list_counts.as<uint32_t>(), h->codes, h->nchunk, ws->qpack.as<uint32_t>(), h->qs,
+        ws->r_state.as<RatioState>(), ws->rec_ham.as<uint32_t>(), ws->rec_ids.as<uint64_t>(), Rf, h->cfg.row_base, K,
+        ws->r_ecnt.as<uint32_t>(), ws->r_ekeys.as<uint64_t>(), RATIO_E_CAP, ws->r_fb.as<uint32_t>());
+    CU(cudaGetLastError());
+    {
+        const uint64_t pairs = (uint64_t)nq * RATIO_E_CAP;
+        ws->r_list.ensure(pairs * 4 + 256);
+        uint32_t* list = ws->r_list.as<uint32_t>() + 64;
+        uint32_t* count = ws->r_list.as<uint32_t>();
+        CU(cudaMemsetAsync(count, 0, 4, st));
+        OwnedPair pred{ws->r_ekeys.as<uint64_t>(), h->cfg.row_base, 0, h->n_rows};
+        owned_compact_kernel<<<(unsigned)((pairs + 255) / 256), 256, 0, st>>>(pred, (uint32_t)pairs, list, count);
+        static std::atomic<uint64_t> attr_done{0};
+        ensure_dyn_smem(attr_done, rescore_owned_ring_kernel, (int)RO_SMEM);
+        Timed t(h, ws, st, K_RESCORE);
+        // the list is short (a few survivors per query): 4096 warps cover 131072 entries, the kernel's warps beyond the list exit
+        const unsigned blocks = (unsigned)std::min<uint64_t>((pairs + 32 * RO_WARPS - 1) / (32 * RO_WARPS), 65536);
+        rescore_owned_ring_kernel<<<blocks, 32 * RO_WARPS, RO_SMEM, st>>>(
+            h->rows_base(), h->norms, h->cfg.row_base, h->dim, q_dev, ws->r_ekeys.as<uint64_t>(), list, count, RATIO_E_CAP,
+            ws->r_esc.as<float>(), nullptr, 0, 1);
+    }
+    CU(cudaGetLastError());
+    {
+        uint32_t n_eff = 64;
+        while (n_eff < Rf + RATIO_E_CAP) n_eff <<= 1;
+        static std::atomic<uint64_t> attr_done{0};
+        ensure_dyn_smem(attr_done, ratio_finish_kernel, (int)((RATIO_E_CAP + 4096) * 8));
+        Timed t(h, ws, st, K_TOPK);
+        ratio_finish_kernel<<<nq, 1024, (size_t)(RATIO_E_CAP + n_eff) * 8, st>>>(
+            ws->rec_ids.as<uint64_t>(), ws->rec_score.as<float>(), Rf, ws->r_ekeys.as<uint64_t>(), ws->r_esc.as<float>(),
+            ws->r_ecnt.as<uint32_t>(), RATIO_E_CAP, n_eff, ws->r_fb.as<uint32_t>(), k, ids_out, scores_out);
+    }
+    CU(cudaGetLastError());
+    // 5. queries the filter could not vouch for (a tie at b*, a full list, a non-positive bound): the cut by counting
+    if (ws->h_fb_bytes < (size_t)nq * 4) {
+        if (ws->h_fb) cudaFreeHost(ws->h_fb);
+        ws->h_fb = nullptr; ws->h_fb_bytes = 0;
+        CU(cudaMallocHost((void**)&ws->h_fb, (size_t)nq * 4));
+        ws->h_fb_bytes = (size_t)nq * 4;
+    }
+    CU(cudaMemcpyAsync(ws->h_fb, ws->r_fb.p, (size_t)nq * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(ws->h_flag, ws->flag.p, 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    flush_profile(h, ws);
+    if (ws->h_flag[0]) return false;                          // a record list of the dense pass overflowed
+    uint64_t n_fb = 0;
+    for (uint32_t q = 0; q < nq; ++q)
+        if (ws->h_fb[q]) {
+            ++n_fb;
+            search_big_r(h, ws, st, q_dev + (size_t)q * h->dim, 1, k, R, ids_out + (size_t)q * k, scores_out + (size_t)q * k, nullptr, nullptr);
+        }
+    if (n_fb) {
+        std::lock_guard<std::mutex> lk(h->prof_mu);
+        h->prof.ratio_fallback_queries += n_fb;
+    }
+    return true;
+}
+
 // h_ids / h_scores (optional, pinned): the k-lists are also copied there BEFORE the call's one
 // synchronisation, so the host-pointer entry point pays a single stream sync.
 void search_device(gvdb_index* h, Workspace* ws, cudaStream_t st, const float* q_dev, uint32_t nq,
@@ -902,6 +1133,20 @@ void search_device(gvdb_index* h, Workspace* ws, cudaStream_t st, const float* q
                    uint32_t* cand_ham, uint64_t* h_ids = nullptr, float* h_scores = nullptr) {
     if (k > R) fail(GVDB_ERR_INVALID_ARGUMENT, "k must be <= rescore_count");
     if (R > kMaxR) {
+        // ratio mode: batches the tensor cores are worth it for go through the dense filter (gvdb_ratio.cuh), tile by tile;
+        // everything else (few queries, candidate lists asked for, k > 256, dims it does not support) is the cut by counting
+        const bool dense = h->ratio_tc && ratio_supported(h) && nq >= h->tc_min_q && !cand_ids && !cand_ham && k >= 1 && k <= 256 &&
+                           h->n_rows >= 65536 && (uint64_t)R <= h->n_rows;
+        if (dense) {
+            const uint32_t QT = h->query_tile;
+            for (uint32_t q0 = 0; q0 < nq; q0 += QT) {
+                const uint32_t m = std::min(QT, nq - q0);
+                if (m < h->tc_min_q || !search_ratio_tile(h, ws, st, q_dev + (size_t)q0 * h->dim, m, k, R, ids_out + (size_t)q0 * k,
+                                                          scores_out + (size_t)q0 * k))
+                    search_big_r(h, ws, st, q_dev + (size_t)q0 * h->dim, m, k, R, ids_out + (size_t)q0 * k, scores_out + (size_t)q0 * k,
+                                 nullptr, nullptr);
+            }
+        } else
         search_big_r(h, ws, st, q_dev, nq, k, R, ids_out, scores_out, cand_ids, cand_ham);
         if (h_ids) {
             CU(cudaMemcpyAsync(h_ids, ids_out, (size_t)nq * k * 8, cudaMemcpyDeviceToHost, st));
@@ -1114,6 +1359,7 @@ gvdb_status gvdb_create(const gvdb_config* cfg, gvdb_index** out) {
         if (const char* s = getenv("GVDB_TC_QB")) h->tc_qb_force = (uint32_t)std::max(0, atoi(s));
         if (const char* s = getenv("GVDB_OPT_M")) h->opt_m = (uint32_t)std::max(0, atoi(s));
         if (const char* s = getenv("GVDB_SAMPLE_DIV")) h->sample_div = (uint32_t)std::max(1, atoi(s));
+        if (const char* s = getenv("GVDB_RATIO_TC")) h->ratio_tc = atoi(s) != 0;
         h->query_tile = std::min<uint32_t>(h->query_tile, 32768);   // survivor records carry the query in 16 bits
         if (const char* s = getenv("GVDB_SEG_GROWTH")) h->seg_growth = (uint32_t)std::max(0, atoi(s));
         if (const char* s = getenv("GVDB_SCAN_CTAS_PER_SM")) h->scan_ctas_per_sm = std::max(1, atoi(s));
@@ -1142,6 +1388,8 @@ void gvdb_destroy(gvdb_index* h) {
     if (h->codes) cudaFree(h->codes);
     if (h->norms) cudaFree(h->norms);
     if (h->live) cudaFree(h->live);
+    if (h->rows16) cudaFree(h->rows16);
+    if (h->rinv) cudaFree(h->rinv);
     delete h;
     cudaSetDevice(prev);
 }
@@ -2443,6 +2691,37 @@ gvdb_status gvdb_rrf_fusion_batch(int32_t device, const uint64_t* dense, uint32_
                    nq, k, limit, oi, os);
         CU(cudaMemcpy(ids_out, oi, (size_t)nq * limit * 8, cudaMemcpyDeviceToHost));
         CU(cudaMemcpy(scores_out, os, (size_t)nq * limit * 4, cudaMemcpyDeviceToHost));
+    });
+}
+
+
+gvdb_status gvdb_approx_dot(gvdb_index* h, const float* queries, uint32_t nq, float* dot_out) {
+    return guarded([&] {
+        need(h, "index");
+        if (nq == 0 || h->n_rows == 0) return;
+        need(queries, "queries"); need(dot_out, "dot_out");
+        if (!ratio_supported(h)) fail(GVDB_ERR_NOT_IMPLEMENTED, "tensor-core dot products need dim % 64 == 0, dim <= 768 and an index without a row window");
+        DeviceGuard dg(h->cfg.device);
+        WsLease lease(h, nullptr, false);
+        Workspace* ws = lease.ws;
+        cudaStream_t st = lease.stream;
+        ensure_rows16(h, st);
+        const int nu = ratio_units(h);
+        const uint64_t N = h->n_rows;
+        const uint32_t qchunk = (uint32_t)std::max<uint64_t>(TC_NQ, std::min<uint64_t>(1024, ((256ull << 20) / (N * 4)) / TC_NQ * TC_NQ));
+        ws->q_in.ensure((size_t)qchunk * h->dim * 4);
+        ws->qexp.ensure((size_t)(qchunk / TC_NQ) * tc_qblock_bytes(nu));
+        ws->misc.ensure((size_t)qchunk * N * 4);
+        for (uint32_t q0 = 0; q0 < nq; q0 += qchunk) {
+            const uint32_t m = std::min(qchunk, nq - q0), m_pad = (m + TC_NQ - 1) / TC_NQ * TC_NQ;
+            CU(cudaMemcpyAsync(ws->q_in.p, queries + (size_t)q0 * h->dim, (size_t)m * h->dim * 4, cudaMemcpyHostToDevice, st));
+            const uint64_t words = (uint64_t)m_pad * nu * 16;
+            ratio_q16_kernel<<<(unsigned)((words + 255) / 256), 256, 0, st>>>(ws->q_in.as<float>(), m, m_pad, h->dim, nu, ws->qexp.as<int8_t>());
+            launch_tc_dot<1>(h, ws, st, ws->qexp.as<int8_t>(), nullptr, m, m_pad, nullptr, 0, nullptr, nullptr, ws->misc.as<float>(), N, nullptr);
+            CU(cudaMemcpyAsync(dot_out + (size_t)q0 * N, ws->misc.p, (size_t)m * N * 4, cudaMemcpyDeviceToHost, st));
+            CU(cudaStreamSynchronize(st));
+        }
+        flush_profile(h, ws);
     });
 }
 

@@ -830,7 +830,7 @@ rescore_slab_kernel(const float* __restrict__ rows, const float* __restrict__ no
 // the first k leave as the answer.  rec_* (optional): the shard records in stage-1 order.
 // Replaces rescore_slab_kernel + topk_kernel on the single-index path: twice the rows in flight per SM
 // and no record round trip through HBM.
-constexpr int RT_SLAB = 128;           // columns per slab: 32 rows x 512 B per warp and slab
+constexpr int RT_SLAB = 64;            // columns per slab: 32 rows x 256 B per warp and slab (ten warps per SM)
 constexpr int RT_MAX_R = 256;          // up to 8 warps per CTA
 constexpr int RT_STRIDE = RT_SLAB + 4; // floats between staged rows: stride / 4 odd -> conflict-free LDS.128
 

@@ -25,6 +25,8 @@
 //           a sign bit shows up.  Survivors (row, query) leave through per-warp record lists
 //           (coalesced stores, no atomics); tc_scatter_kernel turns them into candidate keys.
 //   MODE 1  every distance to dist_out (gvdb_hamming, parity tests).
+//   MODE 3  count: per query, the number of live rows below its threshold -> dist_out[q] (atomic adds of
+//           bit-sliced per-lane counters): the b* search of ratio mode (gvdb_ratio.cuh).
 //   MODE 2  sample: per query, the minimum of D over each ROW CLASS (the rows four neighbouring lanes of
 //           one CTA see: four rows of every group of its row slice) — tilemin[class][q], one FMNMX per
 //           element.  The threshold estimate of the single-pass search comes from these (tc_tau_kernel).
@@ -595,6 +597,23 @@ tc_scan_kernel(const uint4* __restrict__ codes, const uint32_t* __restrict__ liv
         uint32_t q_head = 0, q_count = 0, n_written = 0;
         uint2* my_list = recs + (size_t)(blockIdx.x * TC_EPI_WARPS + ew) * rec_cap;
         const uint32_t lane_lt = (1u << lane) - 1u;
+        // MODE 3: bit-sliced per-column counters of this lane; they belong to ONE (query block, column half) at a time
+        uint64_t planes[MODE == 3 ? 7 : 1];
+#pragma unroll
+        for (int i = 0; i < (MODE == 3 ? 7 : 1); ++i) planes[i] = 0ull;
+        uint32_t plane_rows = 0, plane_q = 0;
+        auto flush_counts = [&](uint32_t qbase_cols) {      // warp-collective: counts of columns qbase_cols .. +63 -> dist_out[q]
+#pragma unroll 4
+            for (int j = 0; j < 64; ++j) {
+                uint32_t c = 0;
+#pragma unroll
+                for (int i = 0; i < (MODE == 3 ? 7 : 1); ++i) c |= (uint32_t)((planes[i] >> (63 - j)) & 1ull) << i;
+                const uint32_t tot = __reduce_add_sync(0xffffffffu, c);
+                if (lane == (j & 31) && tot) atomicAdd(&dist_out[qbase_cols + j], tot);
+            }
+#pragma unroll
+            for (int i = 0; i < (MODE == 3 ? 7 : 1); ++i) planes[i] = 0ull;
+        };
         auto flush = [&](uint32_t n_take) {                 // warp-collective: write the first n_take queued survivors
             __syncwarp();
             if ((uint32_t)lane < n_take && n_written + lane < rec_cap && !(dbg & 4)) {
@@ -635,6 +654,7 @@ tc_scan_kernel(const uint4* __restrict__ codes, const uint32_t* __restrict__ liv
                 for (uint32_t blk = 0; blk < nb; ++blk, ++it) {
                     const uint32_t b = it % NBUF;
                     const uint32_t qbase_q = (qb0 + blk) * TC_NQ + half * 64, qloc = blk * TC_NQ + half * 64;
+                    if (MODE == 3 && plane_rows && plane_q != qbase_q) { flush_counts(plane_q); plane_rows = 0; }
                     { TC_PROF_T0(); mbar_wait(acc_full(b), (it / NBUF) & 1u); TC_PROF_ADD(0); }   // buffer b's (it / NBUF)-th use
                     tc_fence_after();
                     TC_PROF_T0();
@@ -710,13 +730,37 @@ tc_scan_kernel(const uint4* __restrict__ codes, const uint32_t* __restrict__ liv
                             q_count += __popc(m);
                             if (q_count >= 32) flush(32);
                         }
+                    } else if (MODE == 3) {
+                        // count, per query, the live rows below its threshold: the 64 sign bits of this lane's row
+                        // are added into bit-sliced counters (7 planes: up to 127 rows per lane between flushes)
+                        uint32_t ma = 0, mb = 0, mc = 0, md = 0;
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            ma = __funnelshift_l(v[j], ma, 1);
+                            mb = __funnelshift_l(v[16 + j], mb, 1);
+                            mc = __funnelshift_l(v[32 + j], mc, 1);
+                            md = __funnelshift_l(v[48 + j], md, 1);
+                        }
+                        uint64_t carry = alive ? (((uint64_t)((ma << 16) | mb) << 32) | (uint64_t)((mc << 16) | md)) : 0ull;
+#pragma unroll
+                        for (int i = 0; i < 7; ++i) {
+                            const uint64_t t = planes[MODE == 3 ? i : 0] & carry;
+                            planes[MODE == 3 ? i : 0] ^= carry;
+                            carry = t;
+                        }
+                        if (++plane_rows == 127u) { flush_counts(qbase_q); plane_rows = 0; }
+                        plane_q = qbase_q;
                     } else if (MODE == 1) {
+                        // a strided sample (group_stride > 1) is written compactly: column g * 128 + row-in-group
+                        const size_t col = group_stride > 1 ? (size_t)g * TC_ROWS + (uint32_t)(ew & 3) * 32u + lane : (size_t)row;
 #pragma unroll
                         for (int j = 0; j < 64; ++j) {
                             const uint32_t q = qbase_q + j;
                             const int32_t dv = (int32_t)(__uint_as_float(v[j]) - 0.5f);   // -(S + v), v = 0
                             if (q < nq && in_range && row < n_rows)
-                                dist_out[(size_t)q * dist_stride + row] = (uint32_t)(s_base[qloc + j] + dv);
+                                dist_out[(size_t)q * dist_stride + col] = (uint32_t)(s_base[qloc + j] + dv);
+                            else if (q < nq && group_stride > 1)
+                                dist_out[(size_t)q * dist_stride + col] = 0xffffffffu;       // no such row in the sample
                         }
                     }
                     TC_PROF_ADD(1);
@@ -750,6 +794,7 @@ tc_scan_kernel(const uint4* __restrict__ codes, const uint32_t* __restrict__ liv
                 }
             }
         }
+        if (MODE == 3 && plane_rows) flush_counts(plane_q);
         if (MODE == 0) {
             if (q_count) flush(q_count);
             if (lane == 0) {

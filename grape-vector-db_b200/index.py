@@ -457,6 +457,15 @@ class GpuIndex:
         """Waits for the steps in flight; raises IndexError_ if one of them timed out on a peer."""
         self._ok(self._lib.gvdb_exchange_status(self._h, None))
 
+    def approx_dot(self, queries) -> np.ndarray:
+        """gvdb_approx_dot: the bf16 tensor-core dot products of the ratio-mode filter, [nq, rows] f32."""
+        q = np.ascontiguousarray(queries, dtype=np.float32)
+        if q.ndim == 1:
+            q = q[None, :]
+        out = np.empty((q.shape[0], self.rows), dtype=np.float32)
+        self._ok(self._lib.gvdb_approx_dot(self._h, q.ctypes.data_as(C.c_void_p), q.shape[0], out.ctypes.data_as(C.c_void_p)))
+        return out
+
     # -- measurement hooks --------------------------------------------------------------------
     def profile_enable(self, on: bool = True):
         self._ok(self._lib.gvdb_profile_enable(self._h, 1 if on else 0))

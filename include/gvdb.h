@@ -378,7 +378,15 @@ typedef struct gvdb_profile {
     double exchange_ms;       /* peer exchange: push + signal kernels (gvdb_search_exchange_device) */
     double exchange_wait_ms;  /* peer exchange: time spent waiting for the peers' flags (rank skew included) */
     double sample_ms;         /* tc_scan_kernel in sample mode + tc_tau_kernel (single-pass threshold estimate) */
+    double dot_ms;            /* tc_dot_kernel (ratio mode: bf16 tcgen05 GEMM of queries x rows) */
+    uint64_t dot_launches;
+    double dot_macs;          /* rows x padded queries x padded dims of those launches */
+    uint64_t ratio_fallback_queries; /* ratio-mode queries answered by the cut by counting (the filter could not vouch for them) */
 } gvdb_profile;
+/* Parity / diagnostics of the ratio-mode filter (gvdb_ratio.cuh): dot_out[q * rows + r] = the bf16 tensor-core dot
+ * product of query q and stored row r (f32 accumulation; operands rounded to bf16, so |error| <= 2^-8 |q||r|).
+ * dim % 64 == 0 (or 96), dim <= 768, no row window. */
+GVDB_API gvdb_status gvdb_approx_dot(gvdb_index* h, const float* queries, uint32_t nq, float* dot_out);
 GVDB_API gvdb_status gvdb_profile_enable(gvdb_index* h, int32_t on);
 /* The dense FP4 tensor-core rate of `device`, measured: back-to-back tcgen05.mma kind::mxf4
  * (M128 x N128 x K64, A in TMEM) on every SM for a few milliseconds, nothing else running.

@@ -785,3 +785,54 @@ def test_configs2_sized_shard_properties(gv):
         cos = np.array([oracle.cosine_similarity(qs[qi], synth.lowrank_rows(int(r), 1, dim)[0]) for r in order], dtype=np.float32)
         fin = np.argsort(-cos, kind="stable")[:k]
         assert np.array_equal(ids[qi], order[fin].astype(np.uint64)) and np.array_equal(_bits(sc[qi]), _bits(cos[fin]))
+
+
+@pytest.mark.parametrize("dataset", ["lowrank", "iid"])
+def test_ratio_mode_tensor_core_filter(gv, dataset):
+    """K3b: rescore_count = (N as f32 * 0.1) as usize (the reference's default ratio, src/quantization.rs:22-31,
+    178-179) for a batch of queries: the dense tcgen05 bf16 pass filters, the survivors are rescored exactly — ids
+    and score bits equal the oracle's (stricter than the 1e-3 relative the north star allows)."""
+    from grape_vector_db_b200 import synth
+    n, dim, nq, k = 80_000, 768, 96, 10
+    gen, genq = (synth.lowrank_rows, synth.lowrank_queries) if dataset == "lowrank" else (synth.iid_rows, synth.iid_queries)
+    rows, qs = gen(0, n, dim), genq(0, nq, dim)
+    R = oracle.rescore_count(n, 0.1)
+    assert R == 8000
+    with gv.GpuIndex(dim) as idx:
+        idx.add(rows)
+        idx.profile_enable(True)
+        ids, sc = idx.search_batch(qs, k, R)
+        prof = idx.profile_read()
+        assert prof["dot_launches"] >= 1, "the dense tensor-core pass did not run"
+        assert prof["ratio_fallback_queries"] <= nq // 4, prof["ratio_fallback_queries"]
+        # a tombstoned block of rows: candidates are the LIVE rows only
+        for r in range(1000, 1400):
+            idx.remove(r)
+        ids2, sc2 = idx.search_batch(qs, k, R)
+    oi, os_ = oracle.multi_stage_search_batch(qs, rows, R, k, nthreads=8)
+    assert np.array_equal(ids, oi), "top-k ids differ from the oracle"
+    assert np.array_equal(_bits(sc), _bits(os_))
+    live = np.ones(n, dtype=bool); live[1000:1400] = False
+    keep = np.flatnonzero(live)
+    oi2, os2 = oracle.multi_stage_search_batch(qs, rows[keep], R, k, nthreads=8)
+    assert np.array_equal(ids2, keep[oi2.astype(np.int64)].astype(np.uint64)) and np.array_equal(_bits(sc2), _bits(os2))
+
+
+def test_approx_dot_matches_bf16_reference(gv):
+    """gvdb_approx_dot: bf16 operands, f32 accumulation — equal to the bf16-rounded dot product up to f32
+    summation order, within 2^-8 |q||r| of the exact one (the bound the ratio-mode filter relies on)."""
+    from grape_vector_db_b200 import synth
+
+    def bf16(x):
+        u = np.ascontiguousarray(x, dtype=np.float32).view(np.uint32).astype(np.uint64)
+        return ((((u + 0x7FFF + ((u >> 16) & 1)) >> 16) << 16).astype(np.uint32)).view(np.float32)
+    for dim, n, nq in ((768, 3000, 130), (256, 700, 70)):
+        rows, qs = synth.iid_rows(0, n, dim), synth.iid_queries(0, nq, dim)
+        with gv.GpuIndex(dim) as idx:
+            idx.add(rows)
+            d = idx.approx_dot(qs)
+        scale = np.linalg.norm(qs.astype(np.float64), axis=1)[:, None] * np.linalg.norm(rows.astype(np.float64), axis=1)[None, :]
+        ref = bf16(qs).astype(np.float64) @ bf16(rows).astype(np.float64).T
+        exact = qs.astype(np.float64) @ rows.astype(np.float64).T
+        assert np.max(np.abs(d - ref) / scale) < 1e-5
+        assert np.max(np.abs(d - exact) / scale) < 2.0 ** -8
