@@ -246,7 +246,7 @@ def run_north_star_c2(args, rank, world, dev, gv, gdist, synth, torch, dist, bar
     Checked on rank 0: a few queries against the CPU oracle over codes read back from every shard."""
     import numpy as np
     n, dim, k, R, B = args.ns_rows, args.ns_dim, args.k, args.k * args.oversample, args.ns_batch
-    K = max(3, min(args.steps, 10))
+    K = max(3, min(args.steps, 20))
     lo, hi = gdist.shard_bounds(n, world, rank)
     t0 = time.perf_counter()
     index = build_index(gv, synth, torch, dev, lo, hi, dim, chunk=65536)
@@ -258,7 +258,7 @@ def run_north_star_c2(args, rank, world, dev, gv, gdist, synth, torch, dist, bar
     ids_out = torch.empty((B, k), dtype=torch.int64, device=dev)
     sc_out = torch.empty((B, k), dtype=torch.float32, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    for w in range(3):
+    for w in range(6):
         searcher.search_batch_device(q_dev[w % NBq], k, R, ids_out, sc_out)
     torch.cuda.synchronize(); barrier()
     index.profile_read(reset=True)
@@ -269,6 +269,8 @@ def run_north_star_c2(args, rank, world, dev, gv, gdist, synth, torch, dist, bar
         searcher.search_batch_device(q_dev[s_ % NBq], k, R, ids_out, sc_out)
         ev[s_][1].record()
     torch.cuda.synchronize(); barrier()
+    if os.environ.get("BENCH_NS_DEBUG"):
+        print(f"[north star] rank {rank} per-step ms: " + " ".join(f"{a.elapsed_time(b):.3f}" for a, b in ev), file=sys.stderr, flush=True)
     dev_ms = maxr(sum(a.elapsed_time(b) for a, b in ev))
     # per-stage kernel times of this rank (per-launch events on; not part of the timed pass)
     index.profile_enable(True)

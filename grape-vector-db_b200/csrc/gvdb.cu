@@ -186,6 +186,8 @@ struct gvdb_index {
     uint32_t seg0_rows = 4096; // GVDB_SEG0_ROWS: rows of the first ("emit everything") segment
     uint32_t tc_qb_force = 0;  // GVDB_TC_QB: force the query blocks per tensor-core work item (0 = model)
     uint32_t opt_m = 5;        // GVDB_OPT_M: smallest order statistic of the single-pass threshold (0 = single pass off)
+    uint32_t* h_async_flag = nullptr;   // pinned: flags of the last gvdb_search_shard_sliced_enqueue_device
+    bool async_pending = false;
     bool ratio_tc = true;      // GVDB_RATIO_TC=0: ratio mode always by the cut by counting
     uint32_t sample_div = 16;  // GVDB_SAMPLE_DIV: the single-pass sample is 1/sample_div of the row groups
     uint32_t seg_growth = 16;  // GVDB_SEG_GROWTH: cap on the geometric segment growth (0 = cap/(4R) only)
@@ -1390,6 +1392,7 @@ void gvdb_destroy(gvdb_index* h) {
     if (h->live) cudaFree(h->live);
     if (h->rows16) cudaFree(h->rows16);
     if (h->rinv) cudaFree(h->rinv);
+    if (h->h_async_flag) cudaFreeHost(h->h_async_flag);
     delete h;
     cudaSetDevice(prev);
 }
@@ -1994,6 +1997,54 @@ gvdb_status gvdb_search_shard_sliced_device(gvdb_index* h, void* stream, const f
                             reinterpret_cast<float*>(base + nr * 12), s == 0, attempt == 0, &optimistic);
             }
             if (!check_overflow(h, lease.ws, lease.stream, optimistic)) break;
+        }
+    });
+}
+
+// The sliced shard search WITHOUT its host synchronisation: the single pass is enqueued on `stream` together with
+// a copy of its verdict flags into pinned memory, and the call returns — the caller can queue the exchange and the
+// merge behind it at once.  gvdb_search_shard_verify (after the step's other work was enqueued) waits for the
+// stream and says whether the device accepted the pass; if not, the step must be repeated with the synchronous
+// entry point.  One enqueue in flight per index.
+gvdb_status gvdb_search_shard_sliced_enqueue_device(gvdb_index* h, void* stream, const float* queries_dev, uint32_t nq,
+                                                    uint32_t rescore_count, uint32_t n_slices, void* records_dev) {
+    return guarded([&] {
+        need(h, "index");
+        if (nq == 0) return;
+        need(queries_dev, "queries"); need(records_dev, "records");
+        if (n_slices == 0 || nq % n_slices != 0)
+            fail(GVDB_ERR_INVALID_ARGUMENT, "nq must be a positive multiple of n_slices");
+        const uint32_t per = nq / n_slices;
+        if (!(rescore_count >= 1 && rescore_count <= kMaxR && rescore_topk_fits(h, rescore_count) && h->query_tile % per == 0))
+            fail(GVDB_ERR_NOT_IMPLEMENTED, "the enqueue form needs dim % 4 == 0, rescore_count <= 256 and slices that divide the query tile");
+        DeviceGuard dg(h->cfg.device);
+        if (!h->h_async_flag) CU(cudaMallocHost((void**)&h->h_async_flag, 64));
+        WsLease lease(h, (cudaStream_t)stream, true);
+        bool optimistic = false;
+        FusedTopk fused;
+        fused.slice_q = per;
+        search_core(h, lease.ws, lease.stream, queries_dev, nq, rescore_count, nullptr, static_cast<uint64_t*>(records_dev), nullptr,
+                    true, true, &optimistic, nullptr, &fused);
+        CU(cudaMemcpyAsync(h->h_async_flag, lease.ws->flag.p, 8, cudaMemcpyDeviceToHost, lease.stream));
+        h->async_pending = true;
+        if (h->profile_on.load(std::memory_order_relaxed) != 0) {   // per-launch timing wants the events resolved
+            CU(cudaStreamSynchronize(lease.stream));
+            flush_profile(h, lease.ws);
+        }
+    });
+}
+
+gvdb_status gvdb_search_shard_verify(gvdb_index* h, void* stream, int32_t* rerun_out) {
+    return guarded([&] {
+        need(h, "index"); need(rerun_out, "rerun_out");
+        *rerun_out = 0;
+        if (!h->async_pending) return;
+        DeviceGuard dg(h->cfg.device);
+        CU(cudaStreamSynchronize((cudaStream_t)stream));
+        h->async_pending = false;
+        if (h->h_async_flag[0] || h->h_async_flag[1]) {
+            *rerun_out = 1;
+            h->optimistic_reruns.fetch_add(1, std::memory_order_relaxed);
         }
     });
 }

@@ -19,7 +19,7 @@
 //      rows the fast path already holds, and marks the query for the exact fallback if a tie at b* shows up
 //      or a list overflows; the survivors are rescored EXACTLY (sequential-fold f32 cosine,
 //      rescore_owned_ring_kernel) and merged with the fast path's records (ratio_finish_kernel).
-// The answer is the reference's: ids and score bits equal to the oracle's; queries the filter cannot vouch
+// The answer is the reference's, bit for bit (ids and cosines); queries the filter cannot vouch
 // for fall back to the cut by counting (gvdb_bigr.cuh).
 #pragma once
 #include <cuda_runtime.h>

@@ -122,13 +122,26 @@ class ShardedSearcher:
         nbytes = W * self.index.shard_record_bytes(per, rescore_count)
         if self._send is None or self._send.numel() != nbytes:
             self._send = torch.empty(nbytes, dtype=torch.uint8, device=queries_t.device)
-        self.index.search_shard_sliced_device(queries_t, rescore_count, W, records_out=self._send)
-        recv = all_to_all_records(self._send, self.group)
-        my_ids, my_sc = self.index.merge_shards_device(recv, W, per, rescore_count, k)
-        all_ids = torch.empty((nqp, k), dtype=torch.int64, device=queries_t.device)
-        all_sc = torch.empty((nqp, k), dtype=torch.float32, device=queries_t.device)
-        dist.all_gather_into_tensor(all_ids, my_ids, group=self.group)
-        dist.all_gather_into_tensor(all_sc, my_sc, group=self.group)
+        # the whole step is enqueued before the host waits: scan -> all-to-all -> merge -> all-gathers, then ONE
+        # synchronisation that also reads the scan's verdict (repeat the step synchronously if it was refused)
+        enq = queries_t.is_cuda and self.index.search_shard_sliced_enqueue_device(queries_t, rescore_count, W, self._send)
+        for attempt in range(2):
+            if not enq or attempt == 1:
+                self.index.search_shard_sliced_device(queries_t, rescore_count, W, records_out=self._send)
+            recv = all_to_all_records(self._send, self.group)
+            my_ids, my_sc = self.index.merge_shards_device(recv, W, per, rescore_count, k)
+            all_ids = torch.empty((nqp, k), dtype=torch.int64, device=queries_t.device)
+            all_sc = torch.empty((nqp, k), dtype=torch.float32, device=queries_t.device)
+            dist.all_gather_into_tensor(all_ids, my_ids, group=self.group)
+            dist.all_gather_into_tensor(all_sc, my_sc, group=self.group)
+            if not enq or attempt == 1:
+                break
+            # every rank must take the same branch: a refused pass anywhere repeats the step everywhere
+            flag = torch.tensor([1 if self.index.search_shard_verify(queries_t.device) else 0], dtype=torch.int32,
+                                device=queries_t.device)
+            dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=self.group)
+            if int(flag.item()) == 0:
+                break
         if ids_out is not None:
             ids_out.copy_(all_ids[:nq])
             scores_out.copy_(all_sc[:nq])

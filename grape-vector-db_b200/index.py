@@ -297,6 +297,27 @@ class GpuIndex:
             C.c_void_p(records_out.data_ptr())))
         return records_out
 
+    def search_shard_sliced_enqueue_device(self, queries_t, rescore_count: int, n_slices: int, records_out) -> bool:
+        """The sliced shard search enqueued without a host synchronisation; False when this index / rescore count
+        has no such form (use search_shard_sliced_device).  Follow with search_shard_verify()."""
+        import torch
+        nq = queries_t.shape[0]
+        if (self.dim & 3) or rescore_count > 256 or nq % n_slices or 1024 % (nq // n_slices):
+            return False
+        st = torch.cuda.current_stream(queries_t.device).cuda_stream
+        self._ok(self._lib.gvdb_search_shard_sliced_enqueue_device(
+            self._h, C.c_void_p(st), C.c_void_p(queries_t.data_ptr()), nq, rescore_count, n_slices,
+            C.c_void_p(records_out.data_ptr())))
+        return True
+
+    def search_shard_verify(self, device) -> bool:
+        """Waits for the stream; True when the enqueued pass must be repeated synchronously."""
+        import torch
+        rerun = C.c_int32(0)
+        st = torch.cuda.current_stream(device).cuda_stream
+        self._ok(self._lib.gvdb_search_shard_verify(self._h, C.c_void_p(st), C.byref(rerun)))
+        return bool(rerun.value)
+
     def merge_shards_device(self, records_all, n_shards: int, nq: int, rescore_count: int, k: int,
                             ids_out=None, scores_out=None):
         """n_shards packed record buffers back to back -> (ids [nq,k] int64, scores [nq,k] f32)."""

@@ -220,6 +220,15 @@ GVDB_API gvdb_status gvdb_search_shard_device(gvdb_index* h, void* stream, const
 GVDB_API gvdb_status gvdb_search_shard_sliced_device(gvdb_index* h, void* stream, const float* queries_dev,
                                                      uint32_t nq, uint32_t rescore_count, uint32_t n_slices,
                                                      void* records_dev);
+/* gvdb_search_shard_sliced_device without its host synchronisation (dim % 4 == 0, rescore_count <= 256): the
+ * single pass is enqueued on `stream` and the call returns, so the exchange and the merge can be queued behind it
+ * without the GPU idling on the host.  gvdb_search_shard_verify, called once the step's other work is enqueued,
+ * waits for the stream; *rerun_out = 1 means the device refused the pass's thresholds (rare) and the step must be
+ * repeated with gvdb_search_shard_sliced_device.  One enqueue in flight per index. */
+GVDB_API gvdb_status gvdb_search_shard_sliced_enqueue_device(gvdb_index* h, void* stream, const float* queries_dev,
+                                                             uint32_t nq, uint32_t rescore_count, uint32_t n_slices,
+                                                             void* records_dev);
+GVDB_API gvdb_status gvdb_search_shard_verify(gvdb_index* h, void* stream, int32_t* rerun_out);
 /* Replaces the gather side (concat + sort + truncate, src/distributed/shard.rs:776-783) with the
  * rule that reproduces the single-index result: over the n_shards x R gathered records of
  * each query keep the global top R by (hamming, global row), then order by (cosine desc,
