@@ -2007,7 +2007,8 @@ gvdb_status gvdb_search_shard_sliced_device(gvdb_index* h, void* stream, const f
 // stream and says whether the device accepted the pass; if not, the step must be repeated with the synchronous
 // entry point.  One enqueue in flight per index.
 gvdb_status gvdb_search_shard_sliced_enqueue_device(gvdb_index* h, void* stream, const float* queries_dev, uint32_t nq,
-                                                    uint32_t rescore_count, uint32_t n_slices, void* records_dev) {
+                                                    uint32_t rescore_count, uint32_t n_slices, void* records_dev,
+                                                    uint32_t* verdict_out_dev) {
     return guarded([&] {
         need(h, "index");
         if (nq == 0) return;
@@ -2026,6 +2027,8 @@ gvdb_status gvdb_search_shard_sliced_enqueue_device(gvdb_index* h, void* stream,
         search_core(h, lease.ws, lease.stream, queries_dev, nq, rescore_count, nullptr, static_cast<uint64_t*>(records_dev), nullptr,
                     true, true, &optimistic, nullptr, &fused);
         CU(cudaMemcpyAsync(h->h_async_flag, lease.ws->flag.p, 8, cudaMemcpyDeviceToHost, lease.stream));
+        if (verdict_out_dev)
+            CU(cudaMemcpyAsync(verdict_out_dev, lease.ws->flag.p, 8, cudaMemcpyDeviceToDevice, lease.stream));
         h->async_pending = true;
         if (h->profile_on.load(std::memory_order_relaxed) != 0) {   // per-launch timing wants the events resolved
             CU(cudaStreamSynchronize(lease.stream));

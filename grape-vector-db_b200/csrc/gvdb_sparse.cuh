@@ -38,14 +38,30 @@ struct Bm25Cut {
     uint32_t appended;
 };
 
+// tf' of every posting, once per index (k1, b and the average length are fixed when the postings are built):
+//   (tf * (k1 + 1)) / (tf + k1 * (1 - b + b * (len / avg_len)))       src/sparse.rs:180-186, same operation order
+__global__ void __launch_bounds__(256)
+bm25_weight_kernel(const uint32_t* __restrict__ post_doc, const float* __restrict__ post_tf,
+                   const float* __restrict__ doc_len, uint64_t n_post, float k1, float b, float avg_len,
+                   float* __restrict__ post_w) {
+    const float k1p1 = __fadd_rn(k1, 1.0f), one_minus_b = __fsub_rn(1.0f, b);
+    for (uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n_post; p += (uint64_t)gridDim.x * blockDim.x) {
+        const float tf = post_tf[p], len = __ldg(doc_len + post_doc[p]);
+        const float denom = __fadd_rn(tf, __fmul_rn(k1, __fadd_rn(one_minus_b, __fmul_rn(b, __fdiv_rn(len, avg_len)))));
+        post_w[p] = __fdiv_rn(__fmul_rn(tf, k1p1), denom);
+    }
+}
+
 // grid.y = query of the chunk; the query's rank-th term (if it has one) against its postings.
 // acc_stride = n_docs rounded up to 4 (the later passes read the accumulators as uint4).
+// (The dense-accumulator path: queries of more than BMB_MAX_TERMS terms or limits above BMB_MAX_LIMIT; everything
+// else runs bm25_block_kernel below.)
 __global__ void __launch_bounds__(256)
 bm25_accumulate_kernel(const uint64_t* __restrict__ post_off, const uint32_t* __restrict__ post_doc,
-                       const float* __restrict__ post_tf, const float* __restrict__ doc_len, uint32_t n_terms,
+                       const float* __restrict__ post_w, uint32_t n_terms,
                        const uint64_t* __restrict__ q_off, const uint32_t* __restrict__ q_terms,
                        const float* __restrict__ q_tfs, const float* __restrict__ q_idf, uint32_t q0, int rank,
-                       float k1, float b, float avg_len, uint64_t acc_stride, uint32_t* __restrict__ acc) {
+                       uint64_t acc_stride, uint32_t* __restrict__ acc) {
     const uint32_t q = q0 + blockIdx.y;
     const uint64_t t0 = q_off[q], t1 = q_off[q + 1];
     if (t0 + rank >= t1) return;
@@ -54,27 +70,23 @@ bm25_accumulate_kernel(const uint64_t* __restrict__ post_off, const uint32_t* __
     const float qtf = q_tfs[t0 + rank], idf = q_idf[t0 + rank];
     const uint64_t p0 = post_off[term], p1 = post_off[term + 1];
     uint32_t* mine = acc + (size_t)blockIdx.y * acc_stride;
-    const float k1p1 = __fadd_rn(k1, 1.0f), one_minus_b = __fsub_rn(1.0f, b);
     constexpr int U = 4;                       // postings in flight per thread (independent loads first)
     for (uint64_t base = p0 + (uint64_t)blockIdx.x * blockDim.x * U; base < p1; base += (uint64_t)gridDim.x * blockDim.x * U) {
         uint32_t doc[U], old[U];
-        float tf[U], len[U];
+        float w[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const uint64_t p = base + (uint64_t)u * blockDim.x + threadIdx.x;
             doc[u] = p < p1 ? __ldg(post_doc + p) : 0xFFFFFFFFu;
-            tf[u] = p < p1 ? __ldg(post_tf + p) : 0.0f;
+            w[u] = p < p1 ? __ldg(post_w + p) : 0.0f;
         }
 #pragma unroll
         for (int u = 0; u < U; ++u)
-            if (doc[u] != 0xFFFFFFFFu) { len[u] = __ldg(doc_len + doc[u]); old[u] = mine[doc[u]]; }
+            if (doc[u] != 0xFFFFFFFFu) old[u] = mine[doc[u]];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             if (doc[u] == 0xFFFFFFFFu) continue;
-            // (tf * (k1 + 1)) / (tf + k1 * (1 - b + b * (len / avg_len)))
-            const float denom = __fadd_rn(tf[u], __fmul_rn(k1, __fadd_rn(one_minus_b, __fmul_rn(b, __fdiv_rn(len[u], avg_len)))));
-            const float tfc = __fdiv_rn(__fmul_rn(tf[u], k1p1), denom);
-            const float sc = __fmul_rn(__fmul_rn(qtf, tfc), idf);
+            const float sc = __fmul_rn(__fmul_rn(qtf, w[u]), idf);
             const float base_v = old[u] == BM25_ABSENT ? 0.0f : __uint_as_float(old[u]);
             mine[doc[u]] = __float_as_uint(__fadd_rn(base_v, sc));
         }
@@ -325,6 +337,324 @@ bm25_topk_kernel(const uint64_t* __restrict__ keys, uint32_t key_cap, const Bm25
             const uint32_t doc = (uint32_t)skeys[t];
             doc_out[(size_t)q * limit + t] = doc;
             score_out[(size_t)q * limit + t] = __uint_as_float(acc[(size_t)q * acc_stride + doc]);
+        } else {
+            doc_out[(size_t)q * limit + t] = UINT64_MAX;
+            score_out[(size_t)q * limit + t] = -INFINITY;
+        }
+    }
+}
+
+// ---- the blocked path (round 2): accumulators in shared memory, no per-query image of the corpus in HBM --------
+// The dense path above costs ~450 MB of memory traffic per query on 5M documents (a 20 MB accumulator array that is
+// cleared, read-modify-written through 32-byte sectors and read five more times by the cut).  Here the documents are
+// cut into blocks of BMB_DOCS; a CTA owns (query, segment of consecutive blocks) and, block after block, keeps the
+// block's accumulators in SHARED memory:
+//   * at the start it finds, for every query term, where each of its blocks begins inside the term's postings
+//     (documents ascend inside a term: one binary search per (term, block boundary), all in parallel);
+//   * per block: the postings of all terms inside the block form one index space that the threads read BMB_U deep
+//     (coalesced 4-byte loads of document and weight, independent of one another), then add term by term — a
+//     __syncthreads between terms keeps every accumulator's additions in query-term order, the reference's order;
+//   * the block's candidates — present scores whose key (descending score image << 32 | document) is not above the
+//     running bound — are appended in document order (ballot compaction, no atomics) to a candidate buffer of 2 x LP
+//     keys; when it fills, a bitonic sort keeps the best `limit` and the limit-th key becomes the new bound (shared
+//     with the query's other segments through one atomicMin).  A block with more candidates than the buffer holds
+//     (the first block of a segment; corpora whose scores tie by the thousand) first finds its own limit-th key
+//     exactly with a 4 x 8-bit radix select over the block and a walk of the ties in document order.
+// Every segment ends with its best `limit` keys; bm25_merge_kernel orders the segments' keys and rebuilds the score
+// bits from the image (the image is one-to-one here: sums that start from +0.0 never produce -0.0).
+// Items are ordered segment-major, so the CTAs running together work on the same blocks for different queries and
+// share the postings of common terms in L2.
+constexpr int BMB_DOCS = 16384;
+constexpr int BMB_THREADS = 512;
+constexpr int BMB_WARPS = BMB_THREADS / 32;
+constexpr int BMB_PER_WARP = BMB_DOCS / BMB_WARPS;      // 1024 consecutive documents per warp
+constexpr int BMB_STEPS = BMB_PER_WARP / 32;            // 32 steps of 32 lanes
+constexpr int BMB_U = 4;
+constexpr int BMB_MAX_TERMS = 64;
+constexpr int BMB_MAX_LIMIT = 1024;
+constexpr int BMB_MAX_BPS = 40;                         // blocks per segment (boundary table in shared memory)
+
+__host__ __device__ inline size_t bmb_smem_bytes(uint32_t LP, uint32_t t_cap, uint32_t bps) {
+    size_t b = (size_t)BMB_DOCS * 4 + (size_t)2 * LP * 8 + 256 * 4;         // acc, cand, hist
+    b += (size_t)t_cap * 8;                                                 // s_p0
+    b += (size_t)t_cap * (bps + 1) * 4 + (size_t)(t_cap + 1) * 4;           // tb, pre
+    b += (size_t)t_cap * 12;                                                // s_len, s_qtf, s_idf
+    return b + 64;
+}
+
+__device__ __forceinline__ bool bmb_pass(uint32_t bits, uint32_t doc, uint64_t bound, uint64_t& key) {
+    if (bits == BM25_ABSENT) return false;
+    key = ((uint64_t)bm25_desc_image(bits) << 32) | doc;
+    return key <= bound;
+}
+
+__global__ void __launch_bounds__(BMB_THREADS)
+bm25_block_kernel(const uint64_t* __restrict__ post_off, const uint32_t* __restrict__ post_doc,
+                  const float* __restrict__ post_w, uint32_t n_terms, const uint64_t* __restrict__ q_off,
+                  const uint32_t* __restrict__ q_terms, const float* __restrict__ q_tfs, const float* __restrict__ q_idf,
+                  uint32_t nq, uint32_t n_blocks, uint32_t n_seg, uint32_t bps, uint32_t t_cap, uint32_t limit,
+                  uint32_t LP, unsigned long long* __restrict__ bound, uint64_t* __restrict__ seg_keys) {
+    extern __shared__ __align__(16) uint8_t bmb_smem[];
+    uint32_t* acc = reinterpret_cast<uint32_t*>(bmb_smem);
+    uint64_t* cand = reinterpret_cast<uint64_t*>(acc + BMB_DOCS);
+    uint64_t* s_p0 = cand + 2 * LP;
+    uint32_t* hist = reinterpret_cast<uint32_t*>(s_p0 + t_cap);
+    uint32_t* tb = hist + 256;
+    uint32_t* pre = tb + (size_t)t_cap * (bps + 1);
+    uint32_t* s_len = pre + t_cap + 1;
+    float* s_qtf = reinterpret_cast<float*>(s_len + t_cap);
+    float* s_idf = s_qtf + t_cap;
+    __shared__ uint32_t s_warp[BMB_WARPS];
+    __shared__ uint32_t s_bin, s_need, s_thr_idx;
+    __shared__ unsigned long long s_gb;
+
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t seg = blockIdx.x / nq, q = blockIdx.x % nq;
+    const uint32_t b0 = seg * bps, b1 = min(n_blocks, b0 + bps), nb = b1 - b0;
+    uint64_t* out = seg_keys + ((size_t)q * n_seg + seg) * limit;
+    const uint64_t t0 = q_off[q];
+    const uint32_t T = (uint32_t)min((uint64_t)t_cap, q_off[q + 1] - t0);
+
+    for (uint32_t i = tid; i < T; i += BMB_THREADS) {
+        const uint32_t term = q_terms[t0 + i];
+        const uint64_t p0 = term < n_terms ? post_off[term] : 0, p1 = term < n_terms ? post_off[term + 1] : 0;
+        s_p0[i] = p0; s_len[i] = (uint32_t)(p1 - p0);
+        s_qtf[i] = q_tfs[t0 + i]; s_idf[i] = q_idf[t0 + i];
+    }
+    __syncthreads();
+    // where block b0 + j begins inside term i's postings
+    for (uint32_t x = tid; x < T * (nb + 1); x += BMB_THREADS) {
+        const uint32_t i = x / (nb + 1), j = x % (nb + 1);
+        const uint64_t target = (uint64_t)(b0 + j) * BMB_DOCS;
+        const uint32_t* docs = post_doc + s_p0[i];
+        uint32_t lo = 0, hi = s_len[i];
+        while (lo < hi) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if ((uint64_t)__ldg(docs + mid) < target) lo = mid + 1; else hi = mid;
+        }
+        tb[(size_t)i * (bps + 1) + j] = lo;
+    }
+    uint32_t n_cand = 0;
+    uint64_t bound_key = UINT64_MAX;
+
+    auto sort_truncate = [&]() {
+        for (uint32_t i = n_cand + tid; i < 2 * LP; i += BMB_THREADS) cand[i] = UINT64_MAX;
+        __syncthreads();
+        bitonic_sort_smem(cand, 2 * LP);
+        n_cand = min(n_cand, limit);
+        if (n_cand == limit) {
+            const uint64_t nbk = cand[limit - 1];
+            if (nbk < bound_key) {
+                bound_key = nbk;
+                if (tid == 0) atomicMin(bound + q, (unsigned long long)nbk);
+            }
+        }
+    };
+
+    for (uint32_t j = 0; j < nb; ++j) {
+        __syncthreads();                                        // the previous block is done with pre / acc / s_warp
+        const uint32_t block_start = (b0 + j) * BMB_DOCS;
+        if (warp == 0) {                                        // postings per term inside this block, prefix sums
+            uint32_t run = 0;
+            for (uint32_t i0 = 0; i0 < T; i0 += 32) {
+                const uint32_t i = i0 + lane;
+                const uint32_t c = i < T ? tb[(size_t)i * (bps + 1) + j + 1] - tb[(size_t)i * (bps + 1) + j] : 0u;
+                uint32_t incl = c;
+                for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if ((int)lane >= o) incl += t; }
+                if (i < T) pre[i + 1] = run + incl;
+                run += __shfl_sync(0xffffffffu, incl, 31);
+            }
+            if (lane == 0) { pre[0] = 0; s_gb = *reinterpret_cast<volatile unsigned long long*>(bound + q); }
+        }
+        {
+            uint4* a4 = reinterpret_cast<uint4*>(acc);
+            const uint4 absent = make_uint4(BM25_ABSENT, BM25_ABSENT, BM25_ABSENT, BM25_ABSENT);
+#pragma unroll
+            for (int i = 0; i < BMB_DOCS / 4 / BMB_THREADS; ++i) a4[i * BMB_THREADS + tid] = absent;
+        }
+        __syncthreads();
+        const uint32_t total = pre[T];
+        if (total == 0) continue;
+        if ((uint64_t)s_gb < bound_key) bound_key = s_gb;
+
+        // ---- accumulate: all terms' postings of this block as one index space, BMB_U loads in flight per thread ----
+        uint32_t i_lo = 0;
+        for (uint32_t base = 0; base < total; base += BMB_THREADS * BMB_U) {
+            const uint32_t wend = min(total, base + BMB_THREADS * BMB_U);
+            while (pre[i_lo + 1] <= base) ++i_lo;               // term holding `base`
+            uint32_t i_hi = i_lo;
+            while (pre[i_hi + 1] < wend) ++i_hi;                // term holding wend - 1
+            uint32_t d[BMB_U], ti[BMB_U];
+            float w[BMB_U];
+#pragma unroll
+            for (int u = 0; u < BMB_U; ++u) {
+                const uint32_t v = base + u * BMB_THREADS + tid;
+                ti[u] = 0xFFFFFFFFu;
+                if (v < wend) {
+                    uint32_t i = i_lo;
+                    while (pre[i + 1] <= v) ++i;
+                    const uint64_t p = s_p0[i] + tb[(size_t)i * (bps + 1) + j] + (v - pre[i]);
+                    d[u] = __ldg(post_doc + p) - block_start;
+                    w[u] = __ldg(post_w + p);
+                    ti[u] = i;
+                }
+            }
+            for (uint32_t i = i_lo; i <= i_hi; ++i) {
+                if (pre[i + 1] == pre[i]) continue;             // block-uniform
+                const float qtf = s_qtf[i], idf = s_idf[i];
+#pragma unroll
+                for (int u = 0; u < BMB_U; ++u)
+                    if (ti[u] == i) {
+                        const uint32_t old = acc[d[u]];
+                        const float sc = __fmul_rn(__fmul_rn(qtf, w[u]), idf);
+                        acc[d[u]] = __float_as_uint(__fadd_rn(old == BM25_ABSENT ? 0.0f : __uint_as_float(old), sc));
+                    }
+                __syncthreads();
+            }
+        }
+
+        // ---- candidates: warp w owns documents [w * 1024, (w + 1) * 1024) of the block, 32 steps of 32 lanes ----
+        const uint32_t wbase = warp * BMB_PER_WARP;
+        for (int round = 0;; ++round) {
+            if (round) __syncthreads();                         // s_warp of the previous round was read
+            uint32_t mymask = 0, wcount = 0;
+#pragma unroll 4
+            for (int e = 0; e < BMB_STEPS; ++e) {
+                const uint32_t idx = wbase + e * 32 + lane;
+                uint64_t key;
+                const uint32_t m = __ballot_sync(0xffffffffu, bmb_pass(acc[idx], block_start + idx, bound_key, key));
+                if ((int)lane == e) mymask = m;
+                wcount += __popc(m);
+            }
+            if (lane == 0) s_warp[warp] = wcount;
+            __syncthreads();
+            uint32_t total_c = 0, woff = 0;
+#pragma unroll
+            for (int w8 = 0; w8 < BMB_WARPS; ++w8) { const uint32_t c = s_warp[w8]; total_c += c; if (w8 < (int)warp) woff += c; }
+            if (total_c == 0) break;
+            if (total_c <= 2 * LP - n_cand) {                   // append in document order
+                uint32_t off = n_cand + woff;
+                for (int e = 0; e < BMB_STEPS; ++e) {
+                    const uint32_t m = __shfl_sync(0xffffffffu, mymask, e);
+                    if (m == 0) continue;
+                    if ((m >> lane) & 1u) {
+                        const uint32_t idx = wbase + e * 32 + lane;
+                        cand[off + __popc(m & ((1u << lane) - 1u))] =
+                            ((uint64_t)bm25_desc_image(acc[idx]) << 32) | (block_start + idx);
+                    }
+                    off += __popc(m);
+                }
+                n_cand += total_c;
+                break;
+            }
+            if (n_cand > limit) {                               // make room: keep the best `limit`, tighten the bound
+                __syncthreads();
+                sort_truncate();
+                continue;
+            }
+            // more candidates in this one block than the buffer holds: the block's own limit-th key, exactly
+            uint32_t prefix = 0, need = limit;
+            for (int level = 0; level < 4; ++level) {
+                const int shift = 24 - 8 * level;
+                __syncthreads();
+                if (tid < 256) hist[tid] = 0;
+                __syncthreads();
+                for (int e = 0; e < BMB_STEPS; ++e) {
+                    const uint32_t idx = wbase + e * 32 + lane;
+                    uint64_t key;
+                    bool ok = bmb_pass(acc[idx], block_start + idx, bound_key, key);
+                    const uint32_t img = (uint32_t)(key >> 32);
+                    if (level > 0) ok = ok && (img >> (shift + 8)) == prefix;
+                    const uint32_t bin = ok ? (img >> shift) & 255u : 0xFFFFFFFFu;
+                    if (__any_sync(0xffffffffu, ok)) {
+                        const uint32_t peers = __match_any_sync(0xffffffffu, bin);
+                        if (ok && lane == (uint32_t)(__ffs(peers) - 1)) atomicAdd(&hist[bin], (uint32_t)__popc(peers));
+                    }
+                }
+                __syncthreads();
+                if (warp == 0) {                                // the bin holding the need-th key of this level
+                    uint32_t sum = 0;
+                    for (int i = 0; i < 8; ++i) sum += hist[lane * 8 + i];
+                    uint32_t incl = sum;
+                    for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if ((int)lane >= o) incl += t; }
+                    const uint32_t before = incl - sum;
+                    if (before < need && need <= incl) {
+                        uint32_t run = before;
+                        for (int i = 0; i < 8; ++i) {
+                            const uint32_t hv = hist[lane * 8 + i];
+                            if (run + hv >= need) { s_bin = lane * 8 + i; s_need = need - run; break; }
+                            run += hv;
+                        }
+                    }
+                }
+                __syncthreads();
+                prefix = (prefix << 8) | s_bin;
+                need = s_need;
+            }
+            // ties at the image `prefix`: the first `need` of them in document order stay
+            {
+                uint32_t tmask = 0, tcount = 0;
+                for (int e = 0; e < BMB_STEPS; ++e) {
+                    const uint32_t idx = wbase + e * 32 + lane;
+                    uint64_t key;
+                    const bool ok = bmb_pass(acc[idx], block_start + idx, bound_key, key) && (uint32_t)(key >> 32) == prefix;
+                    const uint32_t m = __ballot_sync(0xffffffffu, ok);
+                    if ((int)lane == e) tmask = m;
+                    tcount += __popc(m);
+                }
+                __syncthreads();
+                if (lane == 0) s_warp[warp] = tcount;
+                __syncthreads();
+                uint32_t before = 0;
+                for (int w8 = 0; w8 < (int)warp; ++w8) before += s_warp[w8];
+                if (before < need && need <= before + tcount) { // this warp holds the last tie kept
+                    uint32_t r = need - before;
+                    for (int e = 0; e < BMB_STEPS; ++e) {
+                        const uint32_t m = __shfl_sync(0xffffffffu, tmask, e);
+                        const uint32_t c = __popc(m);
+                        if (r <= c) {
+                            if (lane == 0) {
+                                uint32_t mm = m;
+                                for (uint32_t x = 1; x < r; ++x) mm &= mm - 1;
+                                s_thr_idx = wbase + e * 32 + (uint32_t)(__ffs(mm) - 1);
+                            }
+                            break;
+                        }
+                        r -= c;
+                    }
+                }
+                __syncthreads();
+                const uint64_t nbk = ((uint64_t)prefix << 32) | (block_start + s_thr_idx);
+                bound_key = nbk;                                // <= the old bound: it is one of the passing keys
+                if (tid == 0) atomicMin(bound + q, (unsigned long long)nbk);
+            }
+        }
+    }
+    __syncthreads();
+    sort_truncate();
+    for (uint32_t i = tid; i < limit; i += BMB_THREADS) out[i] = i < n_cand ? cand[i] : UINT64_MAX;
+}
+
+// one CTA per query: the segments' keys -> the best `limit`, in order; scores rebuilt from the image
+__global__ void __launch_bounds__(256)
+bm25_merge_kernel(const uint64_t* __restrict__ seg_keys, uint32_t n_seg, uint32_t limit, uint32_t LP,
+                  uint64_t* __restrict__ doc_out, float* __restrict__ score_out) {
+    extern __shared__ __align__(16) uint64_t mk[];               // 2 x LP
+    const uint32_t q = blockIdx.x, total = n_seg * limit;
+    const uint64_t* in = seg_keys + (size_t)q * total;
+    for (uint32_t i = threadIdx.x; i < LP; i += blockDim.x) mk[i] = UINT64_MAX;
+    for (uint32_t c0 = 0; c0 < total; c0 += LP) {
+        for (uint32_t i = threadIdx.x; i < LP; i += blockDim.x) mk[LP + i] = c0 + i < total ? in[c0 + i] : UINT64_MAX;
+        __syncthreads();
+        bitonic_sort_smem(mk, 2 * LP);
+    }
+    for (uint32_t t = threadIdx.x; t < limit; t += blockDim.x) {
+        const uint64_t key = mk[t];
+        if (key != UINT64_MAX) {
+            const uint32_t asc = ~(uint32_t)(key >> 32);         // f32_asc_key of the score
+            const uint32_t bits = (asc & 0x80000000u) ? (asc & 0x7fffffffu) : ~asc;
+            doc_out[(size_t)q * limit + t] = (uint32_t)key;
+            score_out[(size_t)q * limit + t] = __uint_as_float(bits);
         } else {
             doc_out[(size_t)q * limit + t] = UINT64_MAX;
             score_out[(size_t)q * limit + t] = -INFINITY;

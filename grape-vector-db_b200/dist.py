@@ -48,13 +48,14 @@ def unpack_records(buf: np.ndarray, nq: int, r: int):
     return ids, ham, score
 
 
-def all_gather_records(local, group=None):
+def all_gather_records(local, group=None, out=None):
     """One collective: every rank's packed buffer, concatenated in rank order.
     `local` is a 1-D uint8 torch tensor (CUDA under NCCL, CPU under gloo)."""
     import torch
     import torch.distributed as dist
     world = dist.get_world_size(group)
-    out = torch.empty(world * local.numel(), dtype=local.dtype, device=local.device)
+    if out is None:
+        out = torch.empty(world * local.numel(), dtype=local.dtype, device=local.device)
     if local.is_cuda:
         dist.all_gather_into_tensor(out, local, group=group)
     else:  # gloo
@@ -95,7 +96,10 @@ class ShardedSearcher:
     Every rank holds the same (replicated) query batch.  Each rank scans ITS rows for all the
     queries and writes its local top-R records grouped by query slice; one all-to-all gives
     rank r every shard's records for query slice r; rank r merges those (global stage-1 cut +
-    final order) and a last small all-gather makes the top-k lists complete on every rank."""
+    final order) and ONE all-gather makes the top-k lists complete on every rank.  The gathered
+    message carries, behind each rank's k-lists, the verdict of that rank's single scan pass, so
+    the ranks agree on a (rare) repeat of the step without a collective or a host round trip of
+    its own: per step two collectives and one host wait."""
 
     def __init__(self, index, group=None):
         import torch.distributed as dist
@@ -105,48 +109,77 @@ class ShardedSearcher:
         self.world = dist.get_world_size(group) if self.distributed else 1
         self.rank = dist.get_rank(group) if self.distributed else 0
         self._send = None
+        self._mine = None
+        self._all = None
+        self._verdict_host = None
+        self.reruns = 0
+
+    @staticmethod
+    def answer_layout(per: int, k: int) -> tuple[int, int, int, int]:
+        """One rank's part of the gathered message: (ids offset, scores offset, verdict offset, stride) in bytes —
+        per*k u64 ids | per*k f32 scores | 2 x u32 verdict, padded to a multiple of 16."""
+        lk = per * k
+        return 0, lk * 8, lk * 12, (lk * 12 + 8 + 15) // 16 * 16
 
     def search_batch_device(self, queries_t, k: int, rescore_count: int, ids_out=None,
                             scores_out=None):
         import torch
-        import torch.distributed as dist
         if self.world == 1:
             return self.index.search_batch_device(queries_t, k, rescore_count, ids_out, scores_out)
         nq = queries_t.shape[0]
         W = self.world
+        dev = queries_t.device
         pad = (-nq) % W
         if pad:   # equal slices: repeat the last query, drop its answers below
             queries_t = torch.cat([queries_t, queries_t[-1:].expand(pad, -1)]).contiguous()
         nqp = nq + pad
         per = nqp // W
+        lk = per * k
+        o_ids, o_sc, o_vd, stride = self.answer_layout(per, k)
         nbytes = W * self.index.shard_record_bytes(per, rescore_count)
-        if self._send is None or self._send.numel() != nbytes:
-            self._send = torch.empty(nbytes, dtype=torch.uint8, device=queries_t.device)
-        # the whole step is enqueued before the host waits: scan -> all-to-all -> merge -> all-gathers, then ONE
-        # synchronisation that also reads the scan's verdict (repeat the step synchronously if it was refused)
-        enq = queries_t.is_cuda and self.index.search_shard_sliced_enqueue_device(queries_t, rescore_count, W, self._send)
+        if self._send is None or self._send.numel() != nbytes or self._send.device != dev:
+            self._send = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        if self._mine is None or self._mine.numel() != stride or self._mine.device != dev:
+            self._mine = torch.zeros(stride, dtype=torch.uint8, device=dev)
+            self._all = torch.empty(W * stride, dtype=torch.uint8, device=dev)
+            self._verdict_host = torch.zeros((W, 8), dtype=torch.uint8)
+            if dev.type == "cuda":
+                self._verdict_host = self._verdict_host.pin_memory()
+        mine, allb = self._mine, self._all
+        my_ids = mine[o_ids:o_ids + lk * 8].view(torch.int64).view(per, k)
+        my_sc = mine[o_sc:o_sc + lk * 4].view(torch.float32).view(per, k)
+        my_vd = mine[o_vd:o_vd + 8]
+        # the whole step is enqueued before the host waits: scan -> all-to-all -> merge -> all-gather -> verdicts
+        # to pinned memory, then ONE synchronisation (the step is repeated synchronously if any rank's pass was refused)
+        enq = self.index.search_shard_sliced_enqueue_device(queries_t, rescore_count, W, self._send, my_vd)
         for attempt in range(2):
             if not enq or attempt == 1:
+                my_vd.zero_()
                 self.index.search_shard_sliced_device(queries_t, rescore_count, W, records_out=self._send)
             recv = all_to_all_records(self._send, self.group)
-            my_ids, my_sc = self.index.merge_shards_device(recv, W, per, rescore_count, k)
-            all_ids = torch.empty((nqp, k), dtype=torch.int64, device=queries_t.device)
-            all_sc = torch.empty((nqp, k), dtype=torch.float32, device=queries_t.device)
-            dist.all_gather_into_tensor(all_ids, my_ids, group=self.group)
-            dist.all_gather_into_tensor(all_sc, my_sc, group=self.group)
+            self.index.merge_shards_device(recv, W, per, rescore_count, k, my_ids, my_sc)
+            gathered = all_gather_records(mine, self.group, out=allb).view(W, stride)
             if not enq or attempt == 1:
                 break
-            # every rank must take the same branch: a refused pass anywhere repeats the step everywhere
-            flag = torch.tensor([1 if self.index.search_shard_verify(queries_t.device) else 0], dtype=torch.int32,
-                                device=queries_t.device)
-            dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=self.group)
-            if int(flag.item()) == 0:
+            self._verdict_host.copy_(gathered[:, o_vd:o_vd + 8], non_blocking=True)
+            if dev.type == "cuda":
+                torch.cuda.current_stream(dev).synchronize()
+            self.index.search_shard_verify(dev)            # the stream is idle: clears the index's pending state
+            if not bool(self._verdict_host.any()):
                 break
-        if ids_out is not None:
-            ids_out.copy_(all_ids[:nq])
-            scores_out.copy_(all_sc[:nq])
-            return ids_out, scores_out
-        return all_ids[:nq], all_sc[:nq]
+            self.reruns += 1
+        if ids_out is None:
+            ids_out = torch.empty((nq, k), dtype=torch.int64, device=dev)
+            scores_out = torch.empty((nq, k), dtype=torch.float32, device=dev)
+        all_ids = gathered[:, o_ids:o_ids + lk * 8].view(torch.int64)      # [W, per*k] (strided rows)
+        all_sc = gathered[:, o_sc:o_sc + lk * 4].view(torch.float32)
+        if pad == 0:
+            ids_out.view(W, lk).copy_(all_ids)
+            scores_out.view(W, lk).copy_(all_sc)
+        else:
+            ids_out.copy_(all_ids.reshape(nqp, k)[:nq])
+            scores_out.copy_(all_sc.reshape(nqp, k)[:nq])
+        return ids_out, scores_out
 
 
 def _all_gather_rows(local, group=None):

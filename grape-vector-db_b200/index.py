@@ -297,9 +297,11 @@ class GpuIndex:
             C.c_void_p(records_out.data_ptr())))
         return records_out
 
-    def search_shard_sliced_enqueue_device(self, queries_t, rescore_count: int, n_slices: int, records_out) -> bool:
+    def search_shard_sliced_enqueue_device(self, queries_t, rescore_count: int, n_slices: int, records_out,
+                                           verdict_out=None) -> bool:
         """The sliced shard search enqueued without a host synchronisation; False when this index / rescore count
-        has no such form (use search_shard_sliced_device).  Follow with search_shard_verify()."""
+        has no such form (use search_shard_sliced_device).  Follow with search_shard_verify().  verdict_out: optional
+        device tensor (>= 8 bytes) that receives the pass's verdict words on the stream (nonzero = repeat)."""
         import torch
         nq = queries_t.shape[0]
         if (self.dim & 3) or rescore_count > 256 or nq % n_slices or 1024 % (nq // n_slices):
@@ -307,7 +309,7 @@ class GpuIndex:
         st = torch.cuda.current_stream(queries_t.device).cuda_stream
         self._ok(self._lib.gvdb_search_shard_sliced_enqueue_device(
             self._h, C.c_void_p(st), C.c_void_p(queries_t.data_ptr()), nq, rescore_count, n_slices,
-            C.c_void_p(records_out.data_ptr())))
+            C.c_void_p(records_out.data_ptr()), C.c_void_p(verdict_out.data_ptr() if verdict_out is not None else None)))
         return True
 
     def search_shard_verify(self, device) -> bool:

@@ -224,10 +224,13 @@ GVDB_API gvdb_status gvdb_search_shard_sliced_device(gvdb_index* h, void* stream
  * single pass is enqueued on `stream` and the call returns, so the exchange and the merge can be queued behind it
  * without the GPU idling on the host.  gvdb_search_shard_verify, called once the step's other work is enqueued,
  * waits for the stream; *rerun_out = 1 means the device refused the pass's thresholds (rare) and the step must be
- * repeated with gvdb_search_shard_sliced_device.  One enqueue in flight per index. */
+ * repeated with gvdb_search_shard_sliced_device.  One enqueue in flight per index.
+ * verdict_out_dev (optional, DEVICE, 2 x u32): the same verdict written on the stream (any word nonzero = repeat),
+ * so that the ranks of a sharded deployment can pass their verdicts round with the answers (one collective, one
+ * host wait per step) instead of agreeing through the host. */
 GVDB_API gvdb_status gvdb_search_shard_sliced_enqueue_device(gvdb_index* h, void* stream, const float* queries_dev,
                                                              uint32_t nq, uint32_t rescore_count, uint32_t n_slices,
-                                                             void* records_dev);
+                                                             void* records_dev, uint32_t* verdict_out_dev);
 GVDB_API gvdb_status gvdb_search_shard_verify(gvdb_index* h, void* stream, int32_t* rerun_out);
 /* Replaces the gather side (concat + sort + truncate, src/distributed/shard.rs:776-783) with the
  * rule that reproduces the single-index result: over the n_shards x R gathered records of

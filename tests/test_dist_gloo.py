@@ -215,3 +215,112 @@ def test_two_rank_gloo_query_parallel(tmp_path):
         want_i, want_s = oracle.multi_stage_search_batch(qs, rows, R, k)
         assert np.array_equal(np.load(tmp_path / f"qp_ids_{r}.npy"), want_i)
         assert np.array_equal(np.load(tmp_path / f"qp_sc_{r}.npy").view(np.uint32), want_s.view(np.uint32))
+
+
+class _CpuRowShard:
+    """Stands in for a row-sharded GpuIndex on CPU (the product's shard search and merge are CUDA kernels): the
+    calls ShardedSearcher makes, answered by the oracle.  `refuse_first` makes the first enqueued pass leave garbage
+    records and a nonzero verdict, as a refused single pass would."""
+
+    def __init__(self, rows, lo, refuse_first):
+        self.rows, self.lo, self.refuse = rows, lo, refuse_first
+        self.enqueued = self.synchronous = 0
+
+    def shard_record_bytes(self, nq, R):
+        return nq * R * 16
+
+    def _records(self, q_t, R, W, out):
+        from grape_vector_db_b200 import dist as gdist
+        from oracle import oracle
+        qs = q_t.numpy()
+        nq = qs.shape[0]
+        ids = np.full((nq, R), np.iinfo(np.uint64).max, dtype=np.uint64)
+        ham = np.full((nq, R), 0xFFFFFFFF, dtype=np.uint32)
+        sc = np.full((nq, R), -np.inf, dtype=np.float32)
+        for qi in range(nq):
+            i, s, ci, ch = oracle.multi_stage_search(qs[qi], self.rows, R, want_candidates=True)
+            by = {int(c): t for t, c in enumerate(ci)}
+            ids[qi, :len(ci)] = ci + np.uint64(self.lo)
+            ham[qi, :len(ci)] = ch
+            for ii, ss in zip(i, s):
+                sc[qi, by[int(ii)]] = ss
+        per = nq // W
+        import torch
+        out.copy_(torch.from_numpy(np.concatenate([
+            gdist.pack_records(ids[s * per:(s + 1) * per], ham[s * per:(s + 1) * per], sc[s * per:(s + 1) * per])
+            for s in range(W)])))
+
+    def search_shard_sliced_enqueue_device(self, q_t, R, W, send, verdict_out=None):
+        self.enqueued += 1
+        if self.refuse and self.enqueued == 1:
+            send.fill_(0x5A)
+            verdict_out[4] = 1
+        else:
+            self._records(q_t, R, W, send)
+            verdict_out.zero_()
+        return True
+
+    def search_shard_sliced_device(self, q_t, R, W, records_out=None):
+        self.synchronous += 1
+        self._records(q_t, R, W, records_out)
+        return records_out
+
+    def search_shard_verify(self, device):
+        return False
+
+    def merge_shards_device(self, recv, W, per, R, k, ids_out, sc_out):
+        import torch
+        from grape_vector_db_b200 import dist as gdist
+        from oracle import oracle
+        buf = recv.numpy()
+        pb = self.shard_record_bytes(per, R)
+        parts = [gdist.unpack_records(buf[s * pb:(s + 1) * pb], per, R) for s in range(W)]
+        for qi in range(per):
+            gi, gs = oracle.shard_merge(np.concatenate([p[1][qi] for p in parts]), np.concatenate([p[0][qi] for p in parts]),
+                                        np.concatenate([p[2][qi] for p in parts]), R, k)
+            ids_out[qi, :len(gi)] = torch.from_numpy(gi.astype(np.int64))
+            sc_out[qi, :len(gs)] = torch.from_numpy(gs)
+        return ids_out, sc_out
+
+
+def _sharded_worker(rank, world, port, n, dim, nq, R, k, out_dir):
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+    from grape_vector_db_b200 import dist as gdist
+    from grape_vector_db_b200 import synth
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    lo, hi = gdist.shard_bounds(n, world, rank)
+    shard = _CpuRowShard(synth.lowrank_rows(lo, hi - lo, dim), lo, refuse_first=(rank == 1))
+    searcher = gdist.ShardedSearcher(shard)
+    qs = torch.from_numpy(synth.lowrank_queries(0, nq, dim))
+    ids1, sc1 = searcher.search_batch_device(qs, k, R)            # rank 1 refuses its pass: every rank repeats the step
+    assert searcher.reruns == 1 and shard.synchronous == 1, (searcher.reruns, shard.synchronous)
+    ids2, sc2 = searcher.search_batch_device(qs[:nq - 1], k, R)   # nq not a multiple of the world size; no rerun
+    assert searcher.reruns == 1 and shard.synchronous == 1
+    np.save(os.path.join(out_dir, f"a_ids_{rank}.npy"), ids1.numpy())
+    np.save(os.path.join(out_dir, f"a_sc_{rank}.npy"), sc1.numpy())
+    np.save(os.path.join(out_dir, f"b_ids_{rank}.npy"), ids2.numpy())
+    np.save(os.path.join(out_dir, f"b_sc_{rank}.npy"), sc2.numpy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_two_rank_gloo_sharded_searcher_one_gather_and_verdicts(tmp_path):
+    """ShardedSearcher itself on two gloo ranks: packed k-lists + verdict words in ONE all-gather, a refused pass on
+    one rank repeats the step on every rank, ragged batch sizes; every rank ends with the single-index answer."""
+    import torch.multiprocessing as mp
+    from grape_vector_db_b200 import synth
+    from oracle import oracle
+    n, dim, nq, R, k, world = 3000, 128, 8, 20, 5, 2
+    port = _free_port()
+    mp.spawn(_sharded_worker, args=(world, port, n, dim, nq, R, k, str(tmp_path)), nprocs=world, join=True)
+    rows = synth.lowrank_rows(0, n, dim)
+    qs = synth.lowrank_queries(0, nq, dim)
+    want_i, want_s = oracle.multi_stage_search_batch(qs, rows, R, k)
+    for r in range(world):
+        assert np.array_equal(np.load(tmp_path / f"a_ids_{r}.npy").astype(np.uint64), want_i)
+        assert np.array_equal(np.load(tmp_path / f"a_sc_{r}.npy").view(np.uint32), want_s.view(np.uint32))
+        assert np.array_equal(np.load(tmp_path / f"b_ids_{r}.npy").astype(np.uint64), want_i[:nq - 1])
+        assert np.array_equal(np.load(tmp_path / f"b_sc_{r}.npy").view(np.uint32), want_s[:nq - 1].view(np.uint32))
