@@ -2486,13 +2486,15 @@ struct gvdb_sparse {
     uint64_t n_docs = 0, n_post = 0;
     uint32_t n_terms = 0;
     std::vector<uint64_t> h_post_off;          // host copy: document frequencies for the idf
-    DevBuf post_off, post_doc, post_tf, doc_len;
+    DevBuf post_off, post_doc, post_w;         // CSR postings: documents and tf' (bm25_weight_kernel), by term
     DevBuf acc, hist, cut, keys, tie_counts, q_off, q_terms, q_tfs, q_idf, doc_out, score_out;
+    DevBuf bound, seg_keys;                    // blocked path: per-query bound, per-(query, segment) best keys
     cudaStream_t stream = nullptr;
     int sm_count = 148;
     cudaEvent_t idle = nullptr;                // recorded after the last kernel that touched the scratch buffers
     bool used = false;
     uint64_t launches = 0;                     // kernels launched by the searches of this handle
+    bool force_dense = false;                  // GVDB_BM25_DENSE=1: the dense-accumulator path for every query (tests)
     std::mutex mu;                             // one search at a time per handle
 };
 
@@ -2507,6 +2509,7 @@ gvdb_status gvdb_sparse_create(int32_t device, float k1, float b, gvdb_sparse** 
         DeviceGuard dg(device);
         std::unique_ptr<gvdb_sparse> s(new gvdb_sparse());
         s->device = device; s->k1 = k1; s->b = b;
+        if (const char* e = std::getenv("GVDB_BM25_DENSE")) s->force_dense = e[0] == '1';
         cudaDeviceProp prop;
         CU(cudaGetDeviceProperties(&prop, device));
         s->sm_count = prop.multiProcessorCount;
@@ -2522,8 +2525,8 @@ void gvdb_sparse_destroy(gvdb_sparse* s) {
     cudaGetDevice(&prev);
     cudaSetDevice(s->device);
     cudaDeviceSynchronize();
-    for (DevBuf* b : {&s->post_off, &s->post_doc, &s->post_tf, &s->doc_len, &s->acc, &s->hist, &s->cut, &s->keys, &s->tie_counts,
-                      &s->q_off, &s->q_terms, &s->q_tfs, &s->q_idf, &s->doc_out, &s->score_out}) b->release();
+    for (DevBuf* b : {&s->post_off, &s->post_doc, &s->post_w, &s->acc, &s->hist, &s->cut, &s->keys, &s->tie_counts,
+                      &s->q_off, &s->q_terms, &s->q_tfs, &s->q_idf, &s->doc_out, &s->score_out, &s->bound, &s->seg_keys}) b->release();
     if (s->stream) cudaStreamDestroy(s->stream);
     if (s->idle) cudaEventDestroy(s->idle);
     delete s;
@@ -2556,14 +2559,24 @@ gvdb_status gvdb_sparse_build(gvdb_sparse* s, uint64_t n_docs, uint32_t n_terms,
         s->n_docs = n_docs; s->n_terms = n_terms; s->n_post = n_post;
         s->post_off.ensure((size_t)(n_terms + 1) * 8);
         s->post_doc.ensure(std::max<size_t>(4, n_post * 4));
-        s->post_tf.ensure(std::max<size_t>(4, n_post * 4));
-        s->doc_len.ensure(std::max<size_t>(4, n_docs * 4));
+        s->post_w.ensure(std::max<size_t>(4, n_post * 4));
         CU(cudaMemcpy(s->post_off.p, post_off, (size_t)(n_terms + 1) * 8, cudaMemcpyHostToDevice));
         if (n_post) {
+            // k1, b and the average length are fixed from here on: the tf' factor of every posting is computed once
+            // (the operations of src/sparse.rs:180-186 in their order); tfs and lengths need not stay in HBM
+            DevBuf tf_tmp, len_tmp;
+            struct Rel { DevBuf& a; DevBuf& b; ~Rel() { a.release(); b.release(); } } rel{tf_tmp, len_tmp};
+            tf_tmp.ensure(n_post * 4);
+            len_tmp.ensure(std::max<size_t>(4, n_docs * 4));
             CU(cudaMemcpy(s->post_doc.p, post_doc, n_post * 4, cudaMemcpyHostToDevice));
-            CU(cudaMemcpy(s->post_tf.p, post_tf, n_post * 4, cudaMemcpyHostToDevice));
+            CU(cudaMemcpy(tf_tmp.p, post_tf, n_post * 4, cudaMemcpyHostToDevice));
+            CU(cudaMemcpy(len_tmp.p, doc_len, n_docs * 4, cudaMemcpyHostToDevice));
+            bm25_weight_kernel<<<(unsigned)s->sm_count * 8, 256, 0, s->stream>>>(
+                s->post_doc.as<uint32_t>(), tf_tmp.as<float>(), len_tmp.as<float>(), n_post, s->k1, s->b, s->avg_len,
+                s->post_w.as<float>());
+            CU(cudaGetLastError());
+            CU(cudaStreamSynchronize(s->stream));
         }
-        if (n_docs) CU(cudaMemcpy(s->doc_len.p, doc_len, n_docs * 4, cudaMemcpyHostToDevice));
     });
 }
 
@@ -2591,14 +2604,6 @@ void bm25_core(gvdb_sparse* s, cudaStream_t st, uint32_t nq, const uint64_t* q_o
         terms[i] = df ? t : s->n_terms;                            // n_terms = "absent"
         idf[i] = df ? std::log(((float)s->n_docs - (float)df + 0.5f) / ((float)df + 0.5f)) : 0.0f;
     }
-    const uint64_t stride = (s->n_docs + 3) / 4 * 4;               // accumulators per query: uint4-readable, padding stays "absent"
-    const uint32_t QC = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(std::min<uint64_t>(nq, 64), (512ull << 20) / (stride * 4)));
-    const uint32_t key_cap = SORT_N;
-    s->acc.ensure((size_t)QC * stride * 4);
-    s->hist.ensure((size_t)QC * BM25_LEVEL_BINS * 4);
-    s->cut.ensure((size_t)QC * sizeof(Bm25Cut));
-    s->keys.ensure((size_t)QC * key_cap * 8);
-    s->tie_counts.ensure((size_t)QC * s->sm_count * 2 * 4);
     s->q_off.ensure((size_t)(nq + 1) * 8);
     s->q_terms.ensure(std::max<size_t>(4, nt * 4));
     s->q_tfs.ensure(std::max<size_t>(4, nt * 4));
@@ -2610,6 +2615,40 @@ void bm25_core(gvdb_sparse* s, cudaStream_t st, uint32_t nq, const uint64_t* q_o
         CU(cudaMemcpyAsync(s->q_tfs.p, q_tfs, nt * 4, cudaMemcpyHostToDevice, st));
         CU(cudaMemcpyAsync(s->q_idf.p, idf.data(), nt * 4, cudaMemcpyHostToDevice, st));
     }
+    if (limit <= (uint32_t)BMB_MAX_LIMIT && max_terms <= (uint32_t)BMB_MAX_TERMS && !s->force_dense) {
+        // ---- the blocked path: accumulators in shared memory, two launches per batch (gvdb_sparse.cuh) ----
+        const uint32_t n_blocks = (uint32_t)((s->n_docs + BMB_DOCS - 1) / BMB_DOCS);
+        const uint32_t want_seg = (uint32_t)std::min<uint64_t>(n_blocks, std::max<uint64_t>(1, ((uint64_t)s->sm_count * 8 + nq - 1) / nq));
+        const uint32_t bps = std::min<uint32_t>(BMB_MAX_BPS, (n_blocks + want_seg - 1) / want_seg);
+        const uint32_t n_seg = (n_blocks + bps - 1) / bps;
+        const uint32_t t_cap = std::max<uint32_t>(1, max_terms);
+        uint32_t LP = 64;
+        while (LP < limit) LP <<= 1;
+        const size_t smem = bmb_smem_bytes(LP, t_cap, bps);
+        static std::atomic<uint64_t> attr_a{0}, attr_b{0};
+        ensure_dyn_smem(attr_a, bm25_block_kernel, 200 * 1024);
+        ensure_dyn_smem(attr_b, bm25_merge_kernel, 2 * BMB_MAX_LIMIT * 8);
+        s->bound.ensure((size_t)nq * 8);
+        s->seg_keys.ensure((size_t)nq * n_seg * limit * 8);
+        CU(cudaMemsetAsync(s->bound.p, 0xFF, (size_t)nq * 8, st));
+        bm25_block_kernel<<<n_seg * nq, BMB_THREADS, smem, st>>>(
+            s->post_off.as<uint64_t>(), s->post_doc.as<uint32_t>(), s->post_w.as<float>(), s->n_terms,
+            s->q_off.as<uint64_t>(), s->q_terms.as<uint32_t>(), s->q_tfs.as<float>(), s->q_idf.as<float>(), nq, n_blocks,
+            n_seg, bps, t_cap, limit, LP, s->bound.as<unsigned long long>(), s->seg_keys.as<uint64_t>());
+        bm25_merge_kernel<<<nq, 256, (size_t)2 * LP * 8, st>>>(s->seg_keys.as<uint64_t>(), n_seg, limit, LP, doc_out_dev,
+                                                             score_out_dev);
+        CU(cudaGetLastError());
+        s->launches += 2;
+        return;
+    }
+    const uint64_t stride = (s->n_docs + 3) / 4 * 4;               // accumulators per query: uint4-readable, padding stays "absent"
+    const uint32_t QC = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(std::min<uint64_t>(nq, 64), (512ull << 20) / (stride * 4)));
+    const uint32_t key_cap = SORT_N;
+    s->acc.ensure((size_t)QC * stride * 4);
+    s->hist.ensure((size_t)QC * BM25_LEVEL_BINS * 4);
+    s->cut.ensure((size_t)QC * sizeof(Bm25Cut));
+    s->keys.ensure((size_t)QC * key_cap * 8);
+    s->tie_counts.ensure((size_t)QC * s->sm_count * 2 * 4);
     const unsigned gx = (unsigned)s->sm_count * 2;
     for (uint32_t q0 = 0; q0 < nq; q0 += QC) {
         const uint32_t m = std::min(QC, nq - q0);
@@ -2617,9 +2656,9 @@ void bm25_core(gvdb_sparse* s, cudaStream_t st, uint32_t nq, const uint64_t* q_o
         CU(cudaMemsetAsync(s->cut.p, 0, (size_t)m * sizeof(Bm25Cut), st));
         for (uint32_t rank = 0; rank < max_terms; ++rank)
             bm25_accumulate_kernel<<<dim3(gx, m), 256, 0, st>>>(
-                s->post_off.as<uint64_t>(), s->post_doc.as<uint32_t>(), s->post_tf.as<float>(), s->doc_len.as<float>(),
+                s->post_off.as<uint64_t>(), s->post_doc.as<uint32_t>(), s->post_w.as<float>(),
                 s->n_terms, s->q_off.as<uint64_t>(), s->q_terms.as<uint32_t>(), s->q_tfs.as<float>(),
-                s->q_idf.as<float>(), q0, (int)rank, s->k1, s->b, s->avg_len, stride, s->acc.as<uint32_t>());
+                s->q_idf.as<float>(), q0, (int)rank, stride, s->acc.as<uint32_t>());
         for (int level = 0; level < 3; ++level) {
             CU(cudaMemsetAsync(s->hist.p, 0, (size_t)m * BM25_LEVEL_BINS * 4, st));
             uint32_t* hist = s->hist.as<uint32_t>();

@@ -388,7 +388,7 @@ __device__ __forceinline__ bool bmb_pass(uint32_t bits, uint32_t doc, uint64_t b
     return key <= bound;
 }
 
-__global__ void __launch_bounds__(BMB_THREADS)
+__global__ void __launch_bounds__(BMB_THREADS, 2)
 bm25_block_kernel(const uint64_t* __restrict__ post_off, const uint32_t* __restrict__ post_doc,
                   const float* __restrict__ post_w, uint32_t n_terms, const uint64_t* __restrict__ q_off,
                   const uint32_t* __restrict__ q_terms, const float* __restrict__ q_tfs, const float* __restrict__ q_idf,
