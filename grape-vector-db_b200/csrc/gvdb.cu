@@ -2558,8 +2558,8 @@ gvdb_status gvdb_sparse_build(gvdb_sparse* s, uint64_t n_docs, uint32_t n_terms,
         s->avg_len = n_docs ? total / (float)n_docs : 0.0f;
         s->n_docs = n_docs; s->n_terms = n_terms; s->n_post = n_post;
         s->post_off.ensure((size_t)(n_terms + 1) * 8);
-        s->post_doc.ensure(std::max<size_t>(4, n_post * 4));
-        s->post_w.ensure(std::max<size_t>(4, n_post * 4));
+        s->post_doc.ensure(n_post * 4 + 16);                          // + 16: the staged copies round their end up to 16 bytes
+        s->post_w.ensure(n_post * 4 + 16);
         CU(cudaMemcpy(s->post_off.p, post_off, (size_t)(n_terms + 1) * 8, cudaMemcpyHostToDevice));
         if (n_post) {
             // k1, b and the average length are fixed from here on: the tf' factor of every posting is computed once
@@ -2619,7 +2619,9 @@ void bm25_core(gvdb_sparse* s, cudaStream_t st, uint32_t nq, const uint64_t* q_o
         // ---- the blocked path: accumulators in shared memory, two launches per batch (gvdb_sparse.cuh) ----
         const uint32_t n_blocks = (uint32_t)((s->n_docs + BMB_DOCS - 1) / BMB_DOCS);
         const uint32_t want_seg = (uint32_t)std::min<uint64_t>(n_blocks, std::max<uint64_t>(1, ((uint64_t)s->sm_count * 8 + nq - 1) / nq));
-        const uint32_t bps = std::min<uint32_t>(BMB_MAX_BPS, (n_blocks + want_seg - 1) / want_seg);
+        uint32_t max_bps = BMB_MAX_BPS;
+        if (const char* e = std::getenv("GVDB_BM25_BPS")) max_bps = std::max(1, std::min(BMB_MAX_BPS, atoi(e)));
+        const uint32_t bps = std::min<uint32_t>(max_bps, (n_blocks + want_seg - 1) / want_seg);
         const uint32_t n_seg = (n_blocks + bps - 1) / bps;
         const uint32_t t_cap = std::max<uint32_t>(1, max_terms);
         uint32_t LP = 64;

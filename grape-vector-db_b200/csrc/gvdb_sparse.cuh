@@ -22,6 +22,7 @@
 #include <stdint.h>
 
 #include "gvdb_kernels.cuh"
+#include "gvdb_tc.cuh"
 
 namespace gvdb {
 
@@ -351,41 +352,83 @@ bm25_topk_kernel(const uint64_t* __restrict__ keys, uint32_t key_cap, const Bm25
 // block's accumulators in SHARED memory:
 //   * at the start it finds, for every query term, where each of its blocks begins inside the term's postings
 //     (documents ascend inside a term: one binary search per (term, block boundary), all in parallel);
-//   * per block: the postings of all terms inside the block form one index space that the threads read BMB_U deep
-//     (coalesced 4-byte loads of document and weight, independent of one another), then add term by term — a
-//     __syncthreads between terms keeps every accumulator's additions in query-term order, the reference's order;
+//   * the segment's postings then form ONE stream of pieces (block, term, <= BMB_CH postings) that thread 0 keeps
+//     BMB_NS pieces ahead of the consumers with TMA bulk copies (documents and weights, two copies per piece into a
+//     shared-memory ring, completion on an mbarrier): the stream runs on across block boundaries, so the memory
+//     latency is paid once per segment, not once per term and block.  The threads add a piece's postings into the
+//     accumulators (documents are distinct inside a term: no conflicts); the __syncthreads after every piece frees
+//     its stage AND keeps each accumulator's additions in query-term order, the reference's order;
 //   * the block's candidates — present scores whose key (descending score image << 32 | document) is not above the
-//     running bound — are appended in document order (ballot compaction, no atomics) to a candidate buffer of 2 x LP
-//     keys; when it fills, a bitonic sort keeps the best `limit` and the limit-th key becomes the new bound (shared
-//     with the query's other segments through one atomicMin).  A block with more candidates than the buffer holds
-//     (the first block of a segment; corpora whose scores tie by the thousand) first finds its own limit-th key
+//     running bound — are counted with float compares (an absent accumulator is a NaN and fails them), four
+//     documents per lane and step, and appended in document order (warp scans, no atomics) to a candidate buffer of
+//     2 x LP keys; when it fills, a bitonic sort keeps the best `limit` and the limit-th key becomes the new bound
+//     (shared with the query's other segments through one atomicMin).  A block with more candidates than the buffer
+//     holds (the first block of a segment; corpora whose scores tie by the thousand) first finds its own limit-th key
 //     exactly with a 4 x 8-bit radix select over the block and a walk of the ties in document order.
 // Every segment ends with its best `limit` keys; bm25_merge_kernel orders the segments' keys and rebuilds the score
 // bits from the image (the image is one-to-one here: sums that start from +0.0 never produce -0.0).
 // Items are ordered segment-major, so the CTAs running together work on the same blocks for different queries and
 // share the postings of common terms in L2.
 constexpr int BMB_DOCS = 16384;
-constexpr int BMB_THREADS = 512;
-constexpr int BMB_WARPS = BMB_THREADS / 32;
-constexpr int BMB_PER_WARP = BMB_DOCS / BMB_WARPS;      // 1024 consecutive documents per warp
-constexpr int BMB_STEPS = BMB_PER_WARP / 32;            // 32 steps of 32 lanes
-constexpr int BMB_U = 4;
+constexpr int BMB_WARPS = 8;                            // consumer warps
+constexpr int BMB_CONSUMERS = 32 * BMB_WARPS;
+constexpr int BMB_THREADS = BMB_CONSUMERS + 32;         // + the producer warp (one lane issues the TMA copies)
+constexpr int BMB_PER_WARP = BMB_DOCS / BMB_WARPS;      // 2048 consecutive documents per warp
+constexpr int BMB_STEPS = BMB_PER_WARP / 32;            // block select: 64 steps of 32 lanes
+constexpr int BMB_CSTEPS = BMB_PER_WARP / 128;          // candidate count: 16 steps of 32 lanes x 4 documents
+constexpr int BMB_CH = 1024;                            // postings per staged piece
+constexpr int BMB_NS = 4;                               // pieces in flight (shared-memory ring)
 constexpr int BMB_MAX_TERMS = 64;
 constexpr int BMB_MAX_LIMIT = 1024;
 constexpr int BMB_MAX_BPS = 40;                         // blocks per segment (boundary table in shared memory)
+constexpr uint32_t BMB_END = 0xFFFFFFFFu;               // piece descriptor: the stream is over
 
 __host__ __device__ inline size_t bmb_smem_bytes(uint32_t LP, uint32_t t_cap, uint32_t bps) {
-    size_t b = (size_t)BMB_DOCS * 4 + (size_t)2 * LP * 8 + 256 * 4;         // acc, cand, hist
-    b += (size_t)t_cap * 8;                                                 // s_p0
-    b += (size_t)t_cap * (bps + 1) * 4 + (size_t)(t_cap + 1) * 4;           // tb, pre
-    b += (size_t)t_cap * 12;                                                // s_len, s_qtf, s_idf
+    size_t b = (size_t)BMB_DOCS * 4 + (size_t)BMB_NS * BMB_CH * 8 + (size_t)2 * LP * 8;   // acc, ring, cand
+    b += (size_t)t_cap * 8 + 2 * BMB_NS * 8 + BMB_NS * 16 + 256 * 4;                     // s_p0, barriers, descriptors, hist
+    b += (size_t)t_cap * (bps + 1) * 4;                                                  // tb
+    b += (size_t)t_cap * 12;                                                             // s_len, s_qtf, s_idf
     return b + 64;
 }
 
 __device__ __forceinline__ bool bmb_pass(uint32_t bits, uint32_t doc, uint64_t bound, uint64_t& key) {
-    if (bits == BM25_ABSENT) return false;
     key = ((uint64_t)bm25_desc_image(bits) << 32) | doc;
-    return key <= bound;
+    return bits != BM25_ABSENT && key <= bound;
+}
+// barrier of the consumer warps only (the producer warp never joins it)
+__device__ __forceinline__ void bmb_sync() { asm volatile("bar.sync 1, %0;" :: "n"(BMB_CONSUMERS) : "memory"); }
+__device__ __forceinline__ void bmb_sort(uint64_t* s, uint32_t n, uint32_t tid) {   // bitonic_sort_smem for the consumers
+    for (uint32_t k = 2; k <= n; k <<= 1)
+        for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+            for (uint32_t t = tid; t < (n >> 1); t += BMB_CONSUMERS) {
+                const uint32_t i = ((t & ~(j - 1)) << 1) | (t & (j - 1)), l = i | j;
+                const bool up = (i & k) == 0;
+                const uint64_t a = s[i], b = s[l];
+                if ((a > b) == up) { s[i] = b; s[l] = a; }
+            }
+            bmb_sync();
+        }
+}
+
+// the pieces of a segment in (block, term, offset) order
+struct BmbIter { uint32_t j, i, rel; bool started; };
+__device__ __forceinline__ bool bmb_next(BmbIter& it, uint32_t nb, uint32_t T, const uint32_t* tb, uint32_t tbs,
+                                         const uint64_t* s_p0, uint64_t& ga, uint32_t& n_el, uint32_t& pj, uint32_t& pi) {
+    while (it.j < nb) {
+        const uint32_t lo = tb[it.i * tbs + it.j], hi = tb[it.i * tbs + it.j + 1];
+        if (!it.started) { it.rel = lo; it.started = true; }
+        if (it.rel < hi) {
+            ga = s_p0[it.i] + it.rel;
+            const uint64_t ge = min((uint64_t)(s_p0[it.i] + hi), (uint64_t)((ga & ~(uint64_t)3) + BMB_CH));   // copies start 16-byte aligned
+            n_el = (uint32_t)(ge - ga);
+            pj = it.j; pi = it.i;
+            it.rel += n_el;
+            return true;
+        }
+        it.started = false;
+        if (++it.i >= T) { it.i = 0; ++it.j; }
+    }
+    return false;
 }
 
 __global__ void __launch_bounds__(BMB_THREADS, 2)
@@ -394,14 +437,18 @@ bm25_block_kernel(const uint64_t* __restrict__ post_off, const uint32_t* __restr
                   const uint32_t* __restrict__ q_terms, const float* __restrict__ q_tfs, const float* __restrict__ q_idf,
                   uint32_t nq, uint32_t n_blocks, uint32_t n_seg, uint32_t bps, uint32_t t_cap, uint32_t limit,
                   uint32_t LP, unsigned long long* __restrict__ bound, uint64_t* __restrict__ seg_keys) {
-    extern __shared__ __align__(16) uint8_t bmb_smem[];
+    extern __shared__ __align__(128) uint8_t bmb_smem[];
     uint32_t* acc = reinterpret_cast<uint32_t*>(bmb_smem);
-    uint64_t* cand = reinterpret_cast<uint64_t*>(acc + BMB_DOCS);
-    uint64_t* s_p0 = cand + 2 * LP;
+    uint32_t* sdoc = acc + BMB_DOCS;                              // [BMB_NS][BMB_CH]
+    float* sw = reinterpret_cast<float*>(sdoc + BMB_NS * BMB_CH); // [BMB_NS][BMB_CH]
+    uint64_t* cand = reinterpret_cast<uint64_t*>(sw + BMB_NS * BMB_CH);
+    uint4* desc = reinterpret_cast<uint4*>(cand + 2 * LP);        // per stage: {postings, offset of the first, term, block}
+    uint64_t* full = reinterpret_cast<uint64_t*>(desc + BMB_NS);  // BMB_NS "piece landed" barriers
+    uint64_t* empty = full + BMB_NS;                              // BMB_NS "stage free" barriers (one arrival per consumer warp)
+    uint64_t* s_p0 = empty + BMB_NS;
     uint32_t* hist = reinterpret_cast<uint32_t*>(s_p0 + t_cap);
     uint32_t* tb = hist + 256;
-    uint32_t* pre = tb + (size_t)t_cap * (bps + 1);
-    uint32_t* s_len = pre + t_cap + 1;
+    uint32_t* s_len = tb + (size_t)t_cap * (bps + 1);
     float* s_qtf = reinterpret_cast<float*>(s_len + t_cap);
     float* s_idf = s_qtf + t_cap;
     __shared__ uint32_t s_warp[BMB_WARPS];
@@ -410,10 +457,12 @@ bm25_block_kernel(const uint64_t* __restrict__ post_off, const uint32_t* __restr
 
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t seg = blockIdx.x / nq, q = blockIdx.x % nq;
-    const uint32_t b0 = seg * bps, b1 = min(n_blocks, b0 + bps), nb = b1 - b0;
+    const uint32_t b0 = seg * bps, b1 = min(n_blocks, b0 + bps);
+    const uint32_t tbs = bps + 1;
     uint64_t* out = seg_keys + ((size_t)q * n_seg + seg) * limit;
     const uint64_t t0 = q_off[q];
     const uint32_t T = (uint32_t)min((uint64_t)t_cap, q_off[q + 1] - t0);
+    const uint32_t nb = T ? b1 - b0 : 0u;
 
     for (uint32_t i = tid; i < T; i += BMB_THREADS) {
         const uint32_t term = q_terms[t0 + i];
@@ -421,8 +470,12 @@ bm25_block_kernel(const uint64_t* __restrict__ post_off, const uint32_t* __restr
         s_p0[i] = p0; s_len[i] = (uint32_t)(p1 - p0);
         s_qtf[i] = q_tfs[t0 + i]; s_idf[i] = q_idf[t0 + i];
     }
+    if (tid == 0) {
+        for (int s_ = 0; s_ < BMB_NS; ++s_) { mbar_init(smem_u32(full + s_), 1); mbar_init(smem_u32(empty + s_), BMB_WARPS); }
+        fence_mbar_init();
+    }
     __syncthreads();
-    // where block b0 + j begins inside term i's postings
+    // where block b0 + j begins inside term i's postings (j = nb: where the segment ends)
     for (uint32_t x = tid; x < T * (nb + 1); x += BMB_THREADS) {
         const uint32_t i = x / (nb + 1), j = x % (nb + 1);
         const uint64_t target = (uint64_t)(b0 + j) * BMB_DOCS;
@@ -432,15 +485,44 @@ bm25_block_kernel(const uint64_t* __restrict__ post_off, const uint32_t* __restr
             const uint32_t mid = (lo + hi) >> 1;
             if ((uint64_t)__ldg(docs + mid) < target) lo = mid + 1; else hi = mid;
         }
-        tb[(size_t)i * (bps + 1) + j] = lo;
+        tb[i * tbs + j] = lo;
     }
+    __syncthreads();
+
+    if (warp == BMB_WARPS) {
+        // ===================== producer: one lane keeps the ring full =====================
+        if (lane == 0) {
+            BmbIter it{0, 0, 0, false};
+            uint64_t ga; uint32_t n_el, pj, pi, n = 0;
+            for (;; ++n) {
+                const bool have = bmb_next(it, nb, T, tb, tbs, s_p0, ga, n_el, pj, pi);
+                const uint32_t s_ = n % BMB_NS;
+                if (n >= BMB_NS) mbar_wait(smem_u32(empty + s_), ((n / BMB_NS) - 1) & 1u);
+                const uint32_t bar = smem_u32(full + s_);
+                if (!have) {
+                    desc[s_] = make_uint4(BMB_END, 0, 0, 0);
+                    mbar_arrive(bar);
+                    break;
+                }
+                const uint64_t g0 = ga & ~(uint64_t)3;
+                const uint32_t bytes = (uint32_t)(((ga - g0) + n_el + 3) & ~(uint64_t)3) * 4u;
+                desc[s_] = make_uint4(n_el, (uint32_t)(ga - g0), pi, pj);
+                mbar_expect_tx(bar, 2 * bytes);
+                tma_bulk_g2s(smem_u32(sdoc + s_ * BMB_CH), post_doc + g0, bytes, bar);
+                tma_bulk_g2s(smem_u32(sw + s_ * BMB_CH), post_w + g0, bytes, bar);
+            }
+        }
+        return;
+    }
+
+    // ===================== consumers =====================
     uint32_t n_cand = 0;
     uint64_t bound_key = UINT64_MAX;
 
     auto sort_truncate = [&]() {
-        for (uint32_t i = n_cand + tid; i < 2 * LP; i += BMB_THREADS) cand[i] = UINT64_MAX;
-        __syncthreads();
-        bitonic_sort_smem(cand, 2 * LP);
+        for (uint32_t i = n_cand + tid; i < 2 * LP; i += BMB_CONSUMERS) cand[i] = UINT64_MAX;
+        bmb_sync();
+        bmb_sort(cand, 2 * LP, tid);
         n_cand = min(n_cand, limit);
         if (n_cand == limit) {
             const uint64_t nbk = cand[limit - 1];
@@ -451,104 +533,79 @@ bm25_block_kernel(const uint64_t* __restrict__ post_off, const uint32_t* __restr
         }
     };
 
-    for (uint32_t j = 0; j < nb; ++j) {
-        __syncthreads();                                        // the previous block is done with pre / acc / s_warp
-        const uint32_t block_start = (b0 + j) * BMB_DOCS;
-        if (warp == 0) {                                        // postings per term inside this block, prefix sums
-            uint32_t run = 0;
-            for (uint32_t i0 = 0; i0 < T; i0 += 32) {
-                const uint32_t i = i0 + lane;
-                const uint32_t c = i < T ? tb[(size_t)i * (bps + 1) + j + 1] - tb[(size_t)i * (bps + 1) + j] : 0u;
-                uint32_t incl = c;
-                for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if ((int)lane >= o) incl += t; }
-                if (i < T) pre[i + 1] = run + incl;
-                run += __shfl_sync(0xffffffffu, incl, 31);
-            }
-            if (lane == 0) { pre[0] = 0; s_gb = *reinterpret_cast<volatile unsigned long long*>(bound + q); }
-        }
-        {
-            uint4* a4 = reinterpret_cast<uint4*>(acc);
-            const uint4 absent = make_uint4(BM25_ABSENT, BM25_ABSENT, BM25_ABSENT, BM25_ABSENT);
-#pragma unroll
-            for (int i = 0; i < BMB_DOCS / 4 / BMB_THREADS; ++i) a4[i * BMB_THREADS + tid] = absent;
-        }
-        __syncthreads();
-        const uint32_t total = pre[T];
-        if (total == 0) continue;
+    // ---- candidates of the finished block: warp w owns documents [w * 2048, (w + 1) * 2048) ----
+    auto candidates = [&](uint32_t block_start) {
         if ((uint64_t)s_gb < bound_key) bound_key = s_gb;
-
-        // ---- accumulate: all terms' postings of this block as one index space, BMB_U loads in flight per thread ----
-        uint32_t i_lo = 0;
-        for (uint32_t base = 0; base < total; base += BMB_THREADS * BMB_U) {
-            const uint32_t wend = min(total, base + BMB_THREADS * BMB_U);
-            while (pre[i_lo + 1] <= base) ++i_lo;               // term holding `base`
-            uint32_t i_hi = i_lo;
-            while (pre[i_hi + 1] < wend) ++i_hi;                // term holding wend - 1
-            uint32_t d[BMB_U], ti[BMB_U];
-            float w[BMB_U];
-#pragma unroll
-            for (int u = 0; u < BMB_U; ++u) {
-                const uint32_t v = base + u * BMB_THREADS + tid;
-                ti[u] = 0xFFFFFFFFu;
-                if (v < wend) {
-                    uint32_t i = i_lo;
-                    while (pre[i + 1] <= v) ++i;
-                    const uint64_t p = s_p0[i] + tb[(size_t)i * (bps + 1) + j] + (v - pre[i]);
-                    d[u] = __ldg(post_doc + p) - block_start;
-                    w[u] = __ldg(post_w + p);
-                    ti[u] = i;
-                }
-            }
-            for (uint32_t i = i_lo; i <= i_hi; ++i) {
-                if (pre[i + 1] == pre[i]) continue;             // block-uniform
-                const float qtf = s_qtf[i], idf = s_idf[i];
-#pragma unroll
-                for (int u = 0; u < BMB_U; ++u)
-                    if (ti[u] == i) {
-                        const uint32_t old = acc[d[u]];
-                        const float sc = __fmul_rn(__fmul_rn(qtf, w[u]), idf);
-                        acc[d[u]] = __float_as_uint(__fadd_rn(old == BM25_ABSENT ? 0.0f : __uint_as_float(old), sc));
-                    }
-                __syncthreads();
-            }
-        }
-
-        // ---- candidates: warp w owns documents [w * 1024, (w + 1) * 1024) of the block, 32 steps of 32 lanes ----
         const uint32_t wbase = warp * BMB_PER_WARP;
+        const uint4* a4 = reinterpret_cast<const uint4*>(acc + wbase) + lane;
         for (int round = 0;; ++round) {
-            if (round) __syncthreads();                         // s_warp of the previous round was read
-            uint32_t mymask = 0, wcount = 0;
-#pragma unroll 4
-            for (int e = 0; e < BMB_STEPS; ++e) {
-                const uint32_t idx = wbase + e * 32 + lane;
-                uint64_t key;
-                const uint32_t m = __ballot_sync(0xffffffffu, bmb_pass(acc[idx], block_start + idx, bound_key, key));
-                if ((int)lane == e) mymask = m;
-                wcount += __popc(m);
+            if (round) bmb_sync();                              // s_warp of the previous round was read
+            // pass <=> score > thr, or score == thr and document <= bdoc (an absent accumulator is a NaN: fails both)
+            float thr_f = -INFINITY;
+            uint32_t bdoc = 0xFFFFFFFFu;
+            if (bound_key != UINT64_MAX) {
+                const uint32_t asc = ~(uint32_t)(bound_key >> 32);
+                thr_f = __uint_as_float((asc & 0x80000000u) ? (asc & 0x7fffffffu) : ~asc);
+                bdoc = (uint32_t)bound_key;
+            }
+            // cheap look first: the warp's best score (fmaxf drops NaNs) against the threshold
+            float best = -INFINITY;
+#pragma unroll
+            for (int e = 0; e < BMB_CSTEPS; ++e) {
+                const uint4 v = a4[e * 32];
+                best = fmaxf(fmaxf(best, fmaxf(__uint_as_float(v.x), __uint_as_float(v.y))),
+                             fmaxf(__uint_as_float(v.z), __uint_as_float(v.w)));
+            }
+            uint32_t wcount = 0;
+            if (__any_sync(0xffffffffu, best >= thr_f)) {
+                uint32_t cnt = 0;
+#pragma unroll
+                for (int e = 0; e < BMB_CSTEPS; ++e) {
+                    const uint4 v = a4[e * 32];
+                    const uint32_t doc0 = block_start + wbase + e * 128 + lane * 4;
+                    const float f0 = __uint_as_float(v.x), f1 = __uint_as_float(v.y), f2 = __uint_as_float(v.z), f3 = __uint_as_float(v.w);
+                    cnt += (f0 > thr_f || (f0 == thr_f && doc0 <= bdoc)) ? 1u : 0u;
+                    cnt += (f1 > thr_f || (f1 == thr_f && doc0 + 1 <= bdoc)) ? 1u : 0u;
+                    cnt += (f2 > thr_f || (f2 == thr_f && doc0 + 2 <= bdoc)) ? 1u : 0u;
+                    cnt += (f3 > thr_f || (f3 == thr_f && doc0 + 3 <= bdoc)) ? 1u : 0u;
+                }
+                wcount = __reduce_add_sync(0xffffffffu, cnt);
             }
             if (lane == 0) s_warp[warp] = wcount;
-            __syncthreads();
+            bmb_sync();
             uint32_t total_c = 0, woff = 0;
 #pragma unroll
             for (int w8 = 0; w8 < BMB_WARPS; ++w8) { const uint32_t c = s_warp[w8]; total_c += c; if (w8 < (int)warp) woff += c; }
             if (total_c == 0) break;
             if (total_c <= 2 * LP - n_cand) {                   // append in document order
-                uint32_t off = n_cand + woff;
-                for (int e = 0; e < BMB_STEPS; ++e) {
-                    const uint32_t m = __shfl_sync(0xffffffffu, mymask, e);
-                    if (m == 0) continue;
-                    if ((m >> lane) & 1u) {
-                        const uint32_t idx = wbase + e * 32 + lane;
-                        cand[off + __popc(m & ((1u << lane) - 1u))] =
-                            ((uint64_t)bm25_desc_image(acc[idx]) << 32) | (block_start + idx);
+                if (wcount) {
+                    uint32_t off = n_cand + woff;
+                    for (int e = 0; e < BMB_CSTEPS; ++e) {
+                        const uint4 v = a4[e * 32];
+                        const uint32_t doc0 = block_start + wbase + e * 128 + lane * 4;
+                        const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+                        uint32_t pm = 0;
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) {
+                            const float f = __uint_as_float(w4[c]);
+                            pm |= (f > thr_f || (f == thr_f && doc0 + c <= bdoc)) ? (1u << c) : 0u;
+                        }
+                        if (!__any_sync(0xffffffffu, pm != 0)) continue;
+                        const uint32_t mine_n = __popc(pm);
+                        uint32_t incl = mine_n;
+                        for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if ((int)lane >= o) incl += t; }
+                        uint32_t at = off + incl - mine_n;
+#pragma unroll
+                        for (int c = 0; c < 4; ++c)
+                            if ((pm >> c) & 1u) cand[at++] = ((uint64_t)bm25_desc_image(w4[c]) << 32) | (doc0 + c);
+                        off += __shfl_sync(0xffffffffu, incl, 31);
                     }
-                    off += __popc(m);
                 }
                 n_cand += total_c;
                 break;
             }
             if (n_cand > limit) {                               // make room: keep the best `limit`, tighten the bound
-                __syncthreads();
+                bmb_sync();
                 sort_truncate();
                 continue;
             }
@@ -556,9 +613,9 @@ bm25_block_kernel(const uint64_t* __restrict__ post_off, const uint32_t* __restr
             uint32_t prefix = 0, need = limit;
             for (int level = 0; level < 4; ++level) {
                 const int shift = 24 - 8 * level;
-                __syncthreads();
+                bmb_sync();
                 if (tid < 256) hist[tid] = 0;
-                __syncthreads();
+                bmb_sync();
                 for (int e = 0; e < BMB_STEPS; ++e) {
                     const uint32_t idx = wbase + e * 32 + lane;
                     uint64_t key;
@@ -571,7 +628,7 @@ bm25_block_kernel(const uint64_t* __restrict__ post_off, const uint32_t* __restr
                         if (ok && lane == (uint32_t)(__ffs(peers) - 1)) atomicAdd(&hist[bin], (uint32_t)__popc(peers));
                     }
                 }
-                __syncthreads();
+                bmb_sync();
                 if (warp == 0) {                                // the bin holding the need-th key of this level
                     uint32_t sum = 0;
                     for (int i = 0; i < 8; ++i) sum += hist[lane * 8 + i];
@@ -587,30 +644,37 @@ bm25_block_kernel(const uint64_t* __restrict__ post_off, const uint32_t* __restr
                         }
                     }
                 }
-                __syncthreads();
+                bmb_sync();
                 prefix = (prefix << 8) | s_bin;
                 need = s_need;
             }
             // ties at the image `prefix`: the first `need` of them in document order stay
             {
-                uint32_t tmask = 0, tcount = 0;
+                uint32_t tmask[BMB_STEPS / 32] = {}, tcount = 0;
                 for (int e = 0; e < BMB_STEPS; ++e) {
                     const uint32_t idx = wbase + e * 32 + lane;
                     uint64_t key;
                     const bool ok = bmb_pass(acc[idx], block_start + idx, bound_key, key) && (uint32_t)(key >> 32) == prefix;
                     const uint32_t m = __ballot_sync(0xffffffffu, ok);
-                    if ((int)lane == e) tmask = m;
+#pragma unroll
+                    for (int h2 = 0; h2 < BMB_STEPS / 32; ++h2)
+                        if ((int)lane + 32 * h2 == e) tmask[h2] = m;
                     tcount += __popc(m);
                 }
-                __syncthreads();
+                bmb_sync();
                 if (lane == 0) s_warp[warp] = tcount;
-                __syncthreads();
+                bmb_sync();
                 uint32_t before = 0;
                 for (int w8 = 0; w8 < (int)warp; ++w8) before += s_warp[w8];
                 if (before < need && need <= before + tcount) { // this warp holds the last tie kept
                     uint32_t r = need - before;
                     for (int e = 0; e < BMB_STEPS; ++e) {
-                        const uint32_t m = __shfl_sync(0xffffffffu, tmask, e);
+                        uint32_t m = 0;
+#pragma unroll
+                        for (int h2 = 0; h2 < BMB_STEPS / 32; ++h2) {
+                            const uint32_t mm = __shfl_sync(0xffffffffu, tmask[h2], e & 31);
+                            if ((e >> 5) == h2) m = mm;
+                        }
                         const uint32_t c = __popc(m);
                         if (r <= c) {
                             if (lane == 0) {
@@ -623,16 +687,56 @@ bm25_block_kernel(const uint64_t* __restrict__ post_off, const uint32_t* __restr
                         r -= c;
                     }
                 }
-                __syncthreads();
+                bmb_sync();
                 const uint64_t nbk = ((uint64_t)prefix << 32) | (block_start + s_thr_idx);
                 bound_key = nbk;                                // <= the old bound: it is one of the passing keys
                 if (tid == 0) atomicMin(bound + q, (unsigned long long)nbk);
             }
         }
+    };
+
+    // ---- the posting stream ----
+    uint32_t cur_j = 0xFFFFFFFFu, cur_i = 0;
+    for (uint32_t n = 0;; ++n) {
+        const uint32_t s_ = n % BMB_NS;
+        mbar_wait(smem_u32(full + s_), (n / BMB_NS) & 1u);
+        const uint4 d = desc[s_];                                // {postings, offset of the first, term, block}
+        if (d.x == BMB_END || d.w != cur_j) {
+            bmb_sync();                                          // every warp has added the previous block's last piece
+            if (cur_j != 0xFFFFFFFFu) { candidates((b0 + cur_j) * BMB_DOCS); bmb_sync(); }
+            if (d.x == BMB_END) break;
+            cur_j = d.w; cur_i = d.z;
+            uint4* a4 = reinterpret_cast<uint4*>(acc);
+            const uint4 absent = make_uint4(BM25_ABSENT, BM25_ABSENT, BM25_ABSENT, BM25_ABSENT);
+#pragma unroll
+            for (int i = 0; i < BMB_DOCS / 4 / BMB_CONSUMERS; ++i) a4[i * BMB_CONSUMERS + tid] = absent;
+            if (tid == 0) s_gb = *reinterpret_cast<volatile unsigned long long*>(bound + q);
+            bmb_sync();
+        } else if (d.z != cur_i) {
+            bmb_sync();                                          // additions stay in query-term order
+            cur_i = d.z;
+        }
+        {
+            const uint32_t block_start = (b0 + cur_j) * BMB_DOCS;
+            const uint32_t* sd = sdoc + s_ * BMB_CH + d.y;
+            const float* swp = sw + s_ * BMB_CH + d.y;
+            const float qtf = s_qtf[d.z], idf = s_idf[d.z];
+#pragma unroll
+            for (int r = 0; r < BMB_CH / BMB_CONSUMERS; ++r) {
+                const uint32_t x = r * BMB_CONSUMERS + tid;
+                if (x < d.x) {
+                    const uint32_t dd = sd[x] - block_start;
+                    const float sc = __fmul_rn(__fmul_rn(qtf, swp[x]), idf);
+                    const uint32_t old = acc[dd];
+                    acc[dd] = __float_as_uint(__fadd_rn(old == BM25_ABSENT ? 0.0f : __uint_as_float(old), sc));
+                }
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(empty + s_));        // this warp is done with the stage
     }
-    __syncthreads();
     sort_truncate();
-    for (uint32_t i = tid; i < limit; i += BMB_THREADS) out[i] = i < n_cand ? cand[i] : UINT64_MAX;
+    for (uint32_t i = tid; i < limit; i += BMB_CONSUMERS) out[i] = i < n_cand ? cand[i] : UINT64_MAX;
 }
 
 // one CTA per query: the segments' keys -> the best `limit`, in order; scores rebuilt from the image

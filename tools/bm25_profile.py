@@ -16,6 +16,7 @@ def main():
     ap.add_argument("--queries", type=int, default=25)
     ap.add_argument("--limit", type=int, default=200)
     ap.add_argument("--reps", type=int, default=2)
+    ap.add_argument("--bps-list", default="", help="comma list of GVDB_BM25_BPS values to time one after another")
     args = ap.parse_args()
     import grape_vector_db_b200 as gv
     from grape_vector_db_b200 import synth
@@ -23,8 +24,18 @@ def main():
     qs = synth.sparse_queries(args.queries, vocab=args.vocab)
     with gv.GpuSparseIndex() as sp:
         sp.build(*post)
+        import time
+        for bps in [b for b in args.bps_list.split(",") if b]:
+            os.environ["GVDB_BM25_BPS"] = bps
+            for _ in range(args.reps):
+                t0 = time.perf_counter()
+                docs, sc = sp.search_bm25_batch(qs, args.limit)
+                print(f"bps {bps}: bm25 {args.queries} queries: {1e3 * (time.perf_counter() - t0):.2f} ms", flush=True)
+        os.environ.pop("GVDB_BM25_BPS", None)
         for _ in range(args.reps):
+            t0 = time.perf_counter()
             docs, sc = sp.search_bm25_batch(qs, args.limit)
+            print(f"bm25 {args.queries} queries: {1e3 * (time.perf_counter() - t0):.2f} ms (host arrays in and out)", flush=True)
     print("ok", int((docs[:, 0] != gv.NO_ID).sum()), "queries answered")
 
 
