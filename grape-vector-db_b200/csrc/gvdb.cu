@@ -2621,6 +2621,7 @@ void bm25_core(gvdb_sparse* s, cudaStream_t st, uint32_t nq, const uint64_t* q_o
         const uint32_t want_seg = (uint32_t)std::min<uint64_t>(n_blocks, std::max<uint64_t>(1, ((uint64_t)s->sm_count * 8 + nq - 1) / nq));
         uint32_t max_bps = BMB_MAX_BPS;
         if (const char* e = std::getenv("GVDB_BM25_BPS")) max_bps = std::max(1, std::min(BMB_MAX_BPS, atoi(e)));
+        max_bps = std::max<uint32_t>(1, std::min<uint32_t>(max_bps, 4096 / std::max<uint32_t>(1, max_terms) - 1));   // boundary table <= 16 KB
         const uint32_t bps = std::min<uint32_t>(max_bps, (n_blocks + want_seg - 1) / want_seg);
         const uint32_t n_seg = (n_blocks + bps - 1) / bps;
         const uint32_t t_cap = std::max<uint32_t>(1, max_terms);

@@ -369,18 +369,18 @@ bm25_topk_kernel(const uint64_t* __restrict__ keys, uint32_t key_cap, const Bm25
 // bits from the image (the image is one-to-one here: sums that start from +0.0 never produce -0.0).
 // Items are ordered segment-major, so the CTAs running together work on the same blocks for different queries and
 // share the postings of common terms in L2.
-constexpr int BMB_DOCS = 16384;
-constexpr int BMB_WARPS = 8;                            // consumer warps
+constexpr int BMB_DOCS = 8192;
+constexpr int BMB_WARPS = 4;                            // consumer warps
 constexpr int BMB_CONSUMERS = 32 * BMB_WARPS;
 constexpr int BMB_THREADS = BMB_CONSUMERS + 32;         // + the producer warp (one lane issues the TMA copies)
 constexpr int BMB_PER_WARP = BMB_DOCS / BMB_WARPS;      // 2048 consecutive documents per warp
 constexpr int BMB_STEPS = BMB_PER_WARP / 32;            // block select: 64 steps of 32 lanes
 constexpr int BMB_CSTEPS = BMB_PER_WARP / 128;          // candidate count: 16 steps of 32 lanes x 4 documents
-constexpr int BMB_CH = 1024;                            // postings per staged piece
+constexpr int BMB_CH = 512;                             // postings per staged piece
 constexpr int BMB_NS = 4;                               // pieces in flight (shared-memory ring)
 constexpr int BMB_MAX_TERMS = 64;
 constexpr int BMB_MAX_LIMIT = 1024;
-constexpr int BMB_MAX_BPS = 40;                         // blocks per segment (boundary table in shared memory)
+constexpr int BMB_MAX_BPS = 80;                         // blocks per segment (boundary table in shared memory)
 constexpr uint32_t BMB_END = 0xFFFFFFFFu;               // piece descriptor: the stream is over
 
 __host__ __device__ inline size_t bmb_smem_bytes(uint32_t LP, uint32_t t_cap, uint32_t bps) {
@@ -394,6 +394,16 @@ __host__ __device__ inline size_t bmb_smem_bytes(uint32_t LP, uint32_t t_cap, ui
 __device__ __forceinline__ bool bmb_pass(uint32_t bits, uint32_t doc, uint64_t bound, uint64_t& key) {
     key = ((uint64_t)bm25_desc_image(bits) << 32) | doc;
     return bits != BM25_ABSENT && key <= bound;
+}
+// mbarrier wait that lets the hardware park the thread (suspend-time hint in ns) instead of spinning on issue slots
+__device__ __forceinline__ void bmb_wait_parked(uint32_t bar, uint32_t parity) {
+    uint32_t ok = 0;
+    while (!ok)
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok) : "r"(bar), "r"(parity), "r"(100000u) : "memory");
 }
 // barrier of the consumer warps only (the producer warp never joins it)
 __device__ __forceinline__ void bmb_sync() { asm volatile("bar.sync 1, %0;" :: "n"(BMB_CONSUMERS) : "memory"); }
@@ -431,7 +441,7 @@ __device__ __forceinline__ bool bmb_next(BmbIter& it, uint32_t nb, uint32_t T, c
     return false;
 }
 
-__global__ void __launch_bounds__(BMB_THREADS, 2)
+__global__ void __launch_bounds__(BMB_THREADS, 4)
 bm25_block_kernel(const uint64_t* __restrict__ post_off, const uint32_t* __restrict__ post_doc,
                   const float* __restrict__ post_w, uint32_t n_terms, const uint64_t* __restrict__ q_off,
                   const uint32_t* __restrict__ q_terms, const float* __restrict__ q_tfs, const float* __restrict__ q_idf,
@@ -497,7 +507,7 @@ bm25_block_kernel(const uint64_t* __restrict__ post_off, const uint32_t* __restr
             for (;; ++n) {
                 const bool have = bmb_next(it, nb, T, tb, tbs, s_p0, ga, n_el, pj, pi);
                 const uint32_t s_ = n % BMB_NS;
-                if (n >= BMB_NS) mbar_wait(smem_u32(empty + s_), ((n / BMB_NS) - 1) & 1u);
+                if (n >= BMB_NS) bmb_wait_parked(smem_u32(empty + s_), ((n / BMB_NS) - 1) & 1u);
                 const uint32_t bar = smem_u32(full + s_);
                 if (!have) {
                     desc[s_] = make_uint4(BMB_END, 0, 0, 0);
@@ -614,7 +624,7 @@ bm25_block_kernel(const uint64_t* __restrict__ post_off, const uint32_t* __restr
             for (int level = 0; level < 4; ++level) {
                 const int shift = 24 - 8 * level;
                 bmb_sync();
-                if (tid < 256) hist[tid] = 0;
+                for (uint32_t i = tid; i < 256; i += BMB_CONSUMERS) hist[i] = 0;
                 bmb_sync();
                 for (int e = 0; e < BMB_STEPS; ++e) {
                     const uint32_t idx = wbase + e * 32 + lane;
@@ -721,16 +731,27 @@ bm25_block_kernel(const uint64_t* __restrict__ post_off, const uint32_t* __restr
             const uint32_t* sd = sdoc + s_ * BMB_CH + d.y;
             const float* swp = sw + s_ * BMB_CH + d.y;
             const float qtf = s_qtf[d.z], idf = s_idf[d.z];
+            // documents are distinct inside a term: the four read-modify-writes of a thread are independent, so
+            // all loads go first (the compiler cannot know and would chain them)
+            constexpr int R = BMB_CH / BMB_CONSUMERS;
+            const uint32_t rtid = (tid + 32u * n) % BMB_CONSUMERS;   // partial pieces start at a different warp each time
+            uint32_t dd[R], old[R];
+            float sc[R];
 #pragma unroll
-            for (int r = 0; r < BMB_CH / BMB_CONSUMERS; ++r) {
-                const uint32_t x = r * BMB_CONSUMERS + tid;
-                if (x < d.x) {
-                    const uint32_t dd = sd[x] - block_start;
-                    const float sc = __fmul_rn(__fmul_rn(qtf, swp[x]), idf);
-                    const uint32_t old = acc[dd];
-                    acc[dd] = __float_as_uint(__fadd_rn(old == BM25_ABSENT ? 0.0f : __uint_as_float(old), sc));
-                }
+            for (int r = 0; r < R; ++r) {
+                const uint32_t x = r * BMB_CONSUMERS + rtid;
+                dd[r] = x < d.x ? sd[x] - block_start : 0xFFFFFFFFu;
+                sc[r] = x < d.x ? swp[x] : 0.0f;
             }
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                old[r] = dd[r] != 0xFFFFFFFFu ? acc[dd[r]] : 0u;
+                sc[r] = __fmul_rn(__fmul_rn(qtf, sc[r]), idf);
+            }
+#pragma unroll
+            for (int r = 0; r < R; ++r)
+                if (dd[r] != 0xFFFFFFFFu)
+                    acc[dd[r]] = __float_as_uint(__fadd_rn(old[r] == BM25_ABSENT ? 0.0f : __uint_as_float(old[r]), sc[r]));
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(empty + s_));        // this warp is done with the stage

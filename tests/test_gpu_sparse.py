@@ -78,6 +78,30 @@ def test_bm25_negative_idf_and_repeated_terms(gv):
     _check(gv, post_off, post_doc, post_tf, doc_len, queries, 300, k1=1.5, b=0.6)
 
 
+def test_bm25_both_paths_and_their_limits(gv, monkeypatch):
+    """The blocked path (shared-memory accumulators: limit <= 1024, <= 64 query terms) and the dense-accumulator
+    path (everything else, or GVDB_BM25_DENSE=1) answer alike: a query of exactly 64 terms, one of 70, limits on
+    both sides of 1024, a single-query batch (every document block its own segment), ties with a large limit."""
+    from grape_vector_db_b200 import synth
+    n_docs, vocab = 60_000, 3_000
+    post = synth.sparse_corpus(n_docs, vocab=vocab)
+    rng = np.random.default_rng(11)
+    def many(nt):
+        t = rng.choice(vocab, size=nt, replace=False).astype(np.uint32)
+        return t, np.full(nt, 1.0 / nt, dtype=np.float32)
+    queries = synth.sparse_queries(6, vocab=vocab) + [many(64), many(70)]
+    _check(gv, *post, queries[:7], 1000)          # blocked, LP = 1024
+    _check(gv, *post, queries, 50)                # a 70-term query sends the batch down the dense path
+    _check(gv, *post, queries[:7], 1500)          # limit > 1024: dense
+    _check(gv, *post, queries[:1], 200)           # one query: many segments of one block each
+    monkeypatch.setenv("GVDB_BM25_DENSE", "1")
+    _check(gv, *post, queries[:7], 200)           # the dense path on what the blocked path normally answers
+    monkeypatch.delenv("GVDB_BM25_DENSE")
+    n = 70_000                                    # all scores tie: the block select walks ties in document order
+    _check(gv, np.array([0, n], dtype=np.uint64), np.arange(n, dtype=np.uint32), np.full(n, 0.25, dtype=np.float32),
+           np.ones(n, dtype=np.float32), [([0], [1.0])], 1000)
+
+
 def test_bm25_empty_index_and_bad_postings(gv):
     with gv.GpuSparseIndex() as sp:
         docs, sc = sp.search_bm25_batch([([0], [1.0])], 5)          # src/sparse.rs:161-163
