@@ -20,7 +20,11 @@ A "step" is one pass of the hot path over one batch of 1024 synthetic queries pe
   cpu_baseline  the oracle port of the reference algorithm timed on the host cores (N=1, rank 0)
   north_star_c2 (extra key)  BASELINE configs[2], 10M x 1536, in the north star's own layout: corpus
             row-sharded over the N GPUs, one NCCL all-to-all of the per-shard top-R records + merge,
-            all-gather of the k-lists; global batch 1024 (strong scaling); N=1: the single index
+            one all-gather of the k-lists; global batch 1024 (strong scaling); N=1: the single index
+  north_star_c4 (extra key)  BASELINE configs[4] in the same layout: 12.5M x 768 rows PER GPU (N=8: the
+            100M x 768 corpus), batch 10k queries (weak scaling: the corpus grows with N, the batch does not);
+            both keys carry recall@10 against the exact sharded flat search and use the smallest
+            oversampling factor that reaches 0.95
 
 N > 1 (default layout peer-exchange): every GPU holds all 1-bit codes and 1/N of the f32 rows and
 searches its own batch of 1024 queries ("scaling": "weak").
@@ -68,6 +72,10 @@ def parse():
     ap.add_argument("--ns-dim", type=int, default=1536)
     ap.add_argument("--ns-batch", type=int, default=1024)
     ap.add_argument("--ns-checked", type=int, default=4)
+    ap.add_argument("--ns4-rows-per-gpu", type=int, default=12_500_000,
+                    help="BASELINE configs[4] (100M x 768 on 8 GPUs) in the row-sharded layout: this many rows per GPU "
+                         "(extra key north_star_c4, weak scaling: N GPUs hold N x 12.5M rows); 0: skip")
+    ap.add_argument("--ns4-batch", type=int, default=10_240, help="configs[4]: batch 10k queries")
     ap.add_argument("--layout", default="peer-exchange",
                     choices=["peer-exchange", "peer-rows", "replicated-codes", "row-sharded"],
                     help="N > 1.  'peer-exchange' / 'peer-rows' / 'replicated-codes': every GPU holds all 1-bit codes "
@@ -237,16 +245,19 @@ def build_index(gv, synth, torch, dev, lo, hi, dim, chunk=131072, row_window=Non
     return idx
 
 
-def run_north_star_c2(args, rank, world, dev, gv, gdist, synth, torch, dist, barrier, maxr):
-    """BASELINE configs[2] in the north star's layout: 10M x 1536, corpus row-sharded over the N GPUs (codes AND
-    f32 rows), the global batch of 1024 queries replicated; every rank scans its shard for all queries, ONE NCCL
-    all-to-all moves the per-shard top-R records to the rank owning the query slice, gvdb_merge_shards_device applies
-    the global stage-1 cut and orders, an all-gather completes the k-lists
-    (the shape of /root/reference/src/distributed/shard.rs:760-786).  Total work is fixed as N grows: strong scaling.
+def run_north_star(args, rank, world, dev, gv, gdist, synth, torch, dist, barrier, maxr, *, label, n, dim, B, scaling,
+                   oversamples, max_steps):
+    """A BASELINE config in the north star's layout: corpus row-sharded over the N GPUs (codes AND f32 rows), the
+    global batch replicated; every rank scans its shard for all queries, ONE NCCL all-to-all moves the per-shard
+    top-R records to the rank owning the query slice, gvdb_merge_shards_device applies the global stage-1 cut and
+    orders, ONE all-gather completes the k-lists and carries the scan verdicts
+    (the shape of /root/reference/src/distributed/shard.rs:760-786).
+    recall@10 is measured against the exact answer (flat f32 search of every shard + merge) for each oversampling
+    factor in `oversamples` until one reaches 0.95; the timed run uses that factor.
     Checked on rank 0: a few queries against the CPU oracle over codes read back from every shard."""
     import numpy as np
-    n, dim, k, R, B = args.ns_rows, args.ns_dim, args.k, args.k * args.oversample, args.ns_batch
-    K = max(3, min(args.steps, 20))
+    k = args.k
+    K = max(3, min(args.steps, max_steps))
     lo, hi = gdist.shard_bounds(n, world, rank)
     t0 = time.perf_counter()
     index = build_index(gv, synth, torch, dev, lo, hi, dim, chunk=65536)
@@ -257,8 +268,38 @@ def run_north_star_c2(args, rank, world, dev, gv, gdist, synth, torch, dist, bar
     q_dev = [synth.lowrank_queries_torch(b * B, B, dim, dev) for b in range(NBq)]
     ids_out = torch.empty((B, k), dtype=torch.int64, device=dev)
     sc_out = torch.empty((B, k), dtype=torch.float32, device=dev)
+    # ---- recall: exact top-k of the first queries = flat f32 search of every shard, merged on (distance, row) ----
+    nrq = min(args.recall_queries, B)
+    recall_by = {}
+    oversample = oversamples[0]
+    if nrq > 0:
+        qr = q_dev[0][:nrq].contiguous()
+        fi, fd = index.flat_search_batch_device(qr, k)
+        fi = fi.to(torch.int64)
+        if world > 1:
+            gi = torch.empty((world,) + tuple(fi.shape), dtype=fi.dtype, device=dev)
+            gd = torch.empty((world,) + tuple(fd.shape), dtype=fd.dtype, device=dev)
+            dist.all_gather_into_tensor(gi, fi.contiguous())
+            dist.all_gather_into_tensor(gd, fd.contiguous())
+            gi = gi.permute(1, 0, 2).reshape(nrq, world * k).cpu().numpy()
+            gd = gd.permute(1, 0, 2).reshape(nrq, world * k).cpu().numpy()
+        else:
+            gi, gd = fi.cpu().numpy(), fd.cpu().numpy()
+        truth = []
+        for qi in range(nrq):
+            order = np.lexsort((gi[qi], gd[qi]))[:k]
+            truth.append(set(int(x) for x in gi[qi][order] if x >= 0))
+        for ov in oversamples:
+            oversample = ov
+            got, _ = searcher.search_batch_device(qr, k, k * ov)
+            got = got.cpu().numpy()
+            rec = float(np.mean([len(truth[qi] & set(int(x) for x in got[qi])) / max(1, len(truth[qi])) for qi in range(nrq)]))
+            recall_by[str(ov)] = rec
+            if rec >= 0.95:
+                break
+    R = k * oversample
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    for w in range(6):
+    for w in range(4):
         searcher.search_batch_device(q_dev[w % NBq], k, R, ids_out, sc_out)
     torch.cuda.synchronize(); barrier()
     index.profile_read(reset=True)
@@ -346,19 +387,26 @@ def run_north_star_c2(args, rank, world, dev, gv, gdist, synth, torch, dist, bar
                       "how": "stage 1 by a host popcount over every shard's stored codes (gvdb_get_codes) merged on "
                              "(hamming, global row); stage 2 by the oracle's cosine on the regenerated rows"}
     out = {
-        "workload": f"configs[2]: {n}x{dim} binary-quantized scan + fp32 cosine rerank, global batch {B}, top-{k}, "
-                    f"oversample {args.oversample}x (R={R})",
+        "workload": f"{label}: {n}x{dim} binary-quantized scan + fp32 cosine rerank, global batch {B}, top-{k}, "
+                    f"oversample {oversample}x (R={R})",
         "layout": ("single index on one GPU" if world == 1 else
                    f"corpus row-sharded x{world} ({hi - lo} rows per GPU: codes and f32 rows), queries replicated, "
-                   "NCCL all-to-all of the per-shard top-R records + merge kernel + all-gather of the k-lists"),
-        "scaling": "strong", "value": B * K / (dev_ms * 1e-3), "unit": UNIT, "ms_per_step": dev_ms / K, "steps": K,
+                   "NCCL all-to-all of the per-shard top-R records + merge kernel + ONE all-gather of the k-lists and "
+                   "the scan verdicts"),
+        "scaling": scaling, "rows": n, "rows_per_gpu": hi - lo,
+        "value": B * K / (dev_ms * 1e-3), "unit": UNIT, "ms_per_step": dev_ms / K, "steps": K,
+        "recall_at_10": recall_by.get(str(oversample)), "recall_by_oversample": recall_by, "recall_queries": nrq,
+        "recall_truth": "exact f32 flat search of every shard (gvdb_flat_search), merged on (distance, row)",
         "e2e": {"value": B * K / e2e_s, "unit": UNIT, "h2d_bytes_per_step": B * dim * 4, "d2h_bytes_per_step": B * k * 12,
                 "how": "rank 0: pinned H2D of the batch, NCCL broadcast, search, D2H of the k-lists"},
         "stage_ms_per_step_rank0": {x: prof[x] / K for x in stage_keys},
-        "optimistic_reruns": int(prof["optimistic_reruns"]), "build_s": build_s, "parity": parity,
+        "optimistic_reruns": int(prof["optimistic_reruns"]) + int(getattr(searcher, "reruns", 0)),
+        "build_s": build_s, "parity": parity,
         "l2": "256 MB L2 flush between timed steps",
     }
     index.close()
+    del index, searcher, flush
+    torch.cuda.empty_cache()
     return out
 
 
@@ -768,7 +816,7 @@ def run_ours(args, rank, world, local_rank):
                            "by_queries_per_pass": out}
         big.close()
 
-    north_star = None
+    north_star = north_star4 = None
     if args.north_star:
         try:
             index.close()
@@ -776,10 +824,19 @@ def run_ours(args, rank, world, local_rank):
             pass
         del index, searcher
         torch.cuda.empty_cache()
-        north_star = run_north_star_c2(args, rank, world, dev, gv, gdist, synth, torch, dist, barrier, maxr)
+        north_star = run_north_star(args, rank, world, dev, gv, gdist, synth, torch, dist, barrier, maxr,
+                                    label="configs[2]", n=args.ns_rows, dim=args.ns_dim, B=args.ns_batch, scaling="strong",
+                                    oversamples=(4, 8, 16), max_steps=20)
+        if args.ns4_rows_per_gpu > 0:
+            north_star4 = run_north_star(args, rank, world, dev, gv, gdist, synth, torch, dist, barrier, maxr,
+                                         label="configs[4]" + ("" if world == 8 else f" at {world}/8 of its size"),
+                                         n=args.ns4_rows_per_gpu * world, dim=args.dim, B=args.ns4_batch, scaling="weak",
+                                         oversamples=(4, 8, 16), max_steps=5)
     if rank == 0:
         if north_star is not None:
             extra["north_star_c2"] = north_star
+        if north_star4 is not None:
+            extra["north_star_c4"] = north_star4
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

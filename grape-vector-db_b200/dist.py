@@ -101,6 +101,8 @@ class ShardedSearcher:
     the ranks agree on a (rare) repeat of the step without a collective or a host round trip of
     its own: per step two collectives and one host wait."""
 
+    QUERY_TILE = 1024          # queries per exchange (the library's query tile)
+
     def __init__(self, index, group=None):
         import torch.distributed as dist
         self.index = index
@@ -129,6 +131,15 @@ class ShardedSearcher:
         nq = queries_t.shape[0]
         W = self.world
         dev = queries_t.device
+        if nq > self.QUERY_TILE:
+            # one exchange per query tile: every tile is a full step (scan -> all-to-all -> merge -> all-gather)
+            if ids_out is None:
+                ids_out = torch.empty((nq, k), dtype=torch.int64, device=dev)
+                scores_out = torch.empty((nq, k), dtype=torch.float32, device=dev)
+            for q0 in range(0, nq, self.QUERY_TILE):
+                q1 = min(nq, q0 + self.QUERY_TILE)
+                self.search_batch_device(queries_t[q0:q1], k, rescore_count, ids_out[q0:q1], scores_out[q0:q1])
+            return ids_out, scores_out
         pad = (-nq) % W
         if pad:   # equal slices: repeat the last query, drop its answers below
             queries_t = torch.cat([queries_t, queries_t[-1:].expand(pad, -1)]).contiguous()
