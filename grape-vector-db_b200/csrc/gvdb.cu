@@ -24,6 +24,8 @@
 #include <string>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>   // header-only NVTX 3: ranges cost a pointer test unless a tool (nsys, ncu --nvtx) is attached
+
 #include "gvdb.h"
 #include "gvdb_flat.cuh"
 #include "gvdb_kernels.cuh"
@@ -223,10 +225,19 @@ void ensure_dyn_smem(std::atomic<uint64_t>& done, F kernel, int bytes) {
 }
 
 // Brackets one kernel launch with events (only when profiling is on) and counts it.
+// NVTX range names of the stages (tracing), one per Kind
+const char* const kKindName[K_COUNT] = {"gvdb:scan(popc)", "gvdb:select", "gvdb:rescore", "gvdb:topk", "gvdb:query_prep", "gvdb:flat_scan",
+                                        "gvdb:merge_shards", "gvdb:scan(tcgen05)", "gvdb:sample+thresholds", "gvdb:scatter",
+                                        "gvdb:exchange", "gvdb:exchange_wait", "gvdb:ratio_filter(tcgen05 bf16)"};
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
+
 struct Timed {
-    Workspace* ws; cudaStream_t st; bool on; ProfRec rec;
+    Workspace* ws; cudaStream_t st; bool on; ProfRec rec; NvtxRange nv;
     Timed(gvdb_index* h, Workspace* ws_, cudaStream_t st_, int kind, double bytes = 0, double pairs = 0)
-        : ws(ws_), st(st_), on(h->profile_on.load(std::memory_order_relaxed) != 0) {
+        : ws(ws_), st(st_), on(h->profile_on.load(std::memory_order_relaxed) != 0), nv(kKindName[kind]) {
         h->launches.fetch_add(1, std::memory_order_relaxed);
         if (on) {
             rec = ProfRec{kind, ws->next_event(), ws->next_event(), bytes, pairs};
@@ -1407,6 +1418,7 @@ gvdb_status gvdb_reserve(gvdb_index* h, uint64_t capacity_rows) {
 
 gvdb_status gvdb_add(gvdb_index* h, const float* rows, uint64_t n, uint64_t* first_row_out) {
     return guarded([&] {
+        NvtxRange nvtx_call("gvdb_add");
         need(h, "index");
         if (n) need(rows, "rows");
         DeviceGuard dg(h->cfg.device);
@@ -1729,6 +1741,7 @@ gvdb_status gvdb_search_batch_device(gvdb_index* h, void* stream, const float* q
                                      float* scores_out_dev, uint64_t* cand_ids_out_dev,
                                      uint32_t* cand_ham_out_dev) {
     return guarded([&] {
+        NvtxRange nvtx_call("gvdb_search_batch_device");
         need(h, "index");
         if (nq == 0) return;
         need(queries_dev, "queries"); need(ids_out_dev, "ids_out"); need(scores_out_dev, "scores_out");
@@ -1743,6 +1756,7 @@ gvdb_status gvdb_search_batch(gvdb_index* h, const float* queries, uint32_t nq, 
                               uint32_t rescore_count, uint64_t* ids_out, float* scores_out,
                               uint64_t* cand_ids_out, uint32_t* cand_ham_out) {
     return guarded([&] {
+        NvtxRange nvtx_call("gvdb_search_batch");
         need(h, "index");
         if (nq == 0) return;
         need(queries, "queries"); need(ids_out, "ids_out"); need(scores_out, "scores_out");
@@ -1789,6 +1803,7 @@ gvdb_status gvdb_flat_search_batch_device(gvdb_index* h, void* stream, const flo
                                           uint32_t nq, uint32_t k, uint64_t* ids_out_dev,
                                           float* dist_out_dev) {
     return guarded([&] {
+        NvtxRange nvtx_call("gvdb_flat_search_batch_device");
         need(h, "index");
         if (nq == 0) return;
         need(queries_dev, "queries"); need(ids_out_dev, "ids_out"); need(dist_out_dev, "dist_out");
@@ -1801,6 +1816,7 @@ gvdb_status gvdb_flat_search_batch_device(gvdb_index* h, void* stream, const flo
 gvdb_status gvdb_flat_search_batch(gvdb_index* h, const float* queries, uint32_t nq, uint32_t k,
                                    uint64_t* ids_out, float* dist_out) {
     return guarded([&] {
+        NvtxRange nvtx_call("gvdb_flat_search_batch");
         need(h, "index");
         if (nq == 0) return;
         need(queries, "queries"); need(ids_out, "ids_out"); need(dist_out, "dist_out");
@@ -1843,6 +1859,7 @@ gvdb_status gvdb_search_batch_filtered_device(gvdb_index* h, void* stream, const
                                               const uint32_t* allow_bits_dev, uint32_t nq, uint32_t k,
                                               uint32_t rescore_count, uint64_t* ids_out_dev, float* scores_out_dev) {
     return guarded([&] {
+        NvtxRange nvtx_call("gvdb_search_batch_filtered_device");
         need(h, "index");
         if (nq == 0) return;
         need(queries_dev, "queries"); need(allow_bits_dev, "allow_bits"); need(ids_out_dev, "ids_out"); need(scores_out_dev, "scores_out");
@@ -1856,6 +1873,7 @@ gvdb_status gvdb_search_batch_filtered_device(gvdb_index* h, void* stream, const
 gvdb_status gvdb_search_batch_filtered(gvdb_index* h, const float* queries, const uint32_t* allow_bits, uint32_t nq,
                                        uint32_t k, uint32_t rescore_count, uint64_t* ids_out, float* scores_out) {
     return guarded([&] {
+        NvtxRange nvtx_call("gvdb_search_batch_filtered");
         need(h, "index");
         if (nq == 0) return;
         need(queries, "queries"); need(allow_bits, "allow_bits"); need(ids_out, "ids_out"); need(scores_out, "scores_out");
@@ -1921,6 +1939,7 @@ gvdb_status gvdb_similarity_search_batch_device(gvdb_index* h, void* stream, con
 gvdb_status gvdb_similarity_search_batch(gvdb_index* h, const float* queries, uint32_t nq, uint32_t k,
                                          float threshold, int32_t use_threshold, uint64_t* ids_out, float* sims_out) {
     return guarded([&] {
+        NvtxRange nvtx_call("gvdb_similarity_search_batch");
         need(h, "index");
         if (nq == 0) return;
         need(queries, "queries"); need(ids_out, "ids_out"); need(sims_out, "sims_out");
@@ -1967,6 +1986,7 @@ gvdb_status gvdb_search_shard_device(gvdb_index* h, void* stream, const float* q
 gvdb_status gvdb_search_shard_sliced_device(gvdb_index* h, void* stream, const float* queries_dev, uint32_t nq,
                                             uint32_t rescore_count, uint32_t n_slices, void* records_dev) {
     return guarded([&] {
+        NvtxRange nvtx_call("gvdb_search_shard_sliced_device");
         need(h, "index");
         if (nq == 0) return;
         need(queries_dev, "queries"); need(records_dev, "records");
@@ -2010,6 +2030,7 @@ gvdb_status gvdb_search_shard_sliced_enqueue_device(gvdb_index* h, void* stream,
                                                     uint32_t rescore_count, uint32_t n_slices, void* records_dev,
                                                     uint32_t* verdict_out_dev) {
     return guarded([&] {
+        NvtxRange nvtx_call("gvdb_search_shard_sliced_enqueue_device");
         need(h, "index");
         if (nq == 0) return;
         need(queries_dev, "queries"); need(records_dev, "records");
@@ -2056,6 +2077,7 @@ gvdb_status gvdb_merge_shards_device(gvdb_index* h, void* stream, uint32_t n_sha
                                      const void* records_dev, uint32_t nq, uint32_t rescore_count,
                                      uint32_t k, uint64_t* ids_out_dev, float* scores_out_dev) {
     return guarded([&] {
+        NvtxRange nvtx_call("gvdb_merge_shards_device");
         need(h, "index");
         if (nq == 0) return;
         need(records_dev, "records"); need(ids_out_dev, "ids_out"); need(scores_out_dev, "scores_out");
@@ -2409,6 +2431,7 @@ gvdb_status gvdb_search_exchange_device(gvdb_index* h, void* stream, const float
                                         uint32_t k, uint32_t rescore_count, uint64_t* ids_out_dev,
                                         float* scores_out_dev) {
     return guarded([&] {
+        NvtxRange nvtx_call("gvdb_search_exchange_device");
         need(h, "index");
         Exchange* x = h->xchg;
         if (!x || !x->attached) fail(GVDB_ERR_INVALID_ARGUMENT, "peer exchange not created / peers not attached");
@@ -2690,6 +2713,7 @@ void bm25_core(gvdb_sparse* s, cudaStream_t st, uint32_t nq, const uint64_t* q_o
 gvdb_status gvdb_sparse_search_bm25_batch(gvdb_sparse* s, uint32_t nq, const uint64_t* q_off, const uint32_t* q_terms,
                                           const float* q_tfs, uint32_t limit, uint64_t* doc_out, float* score_out) {
     return guarded([&] {
+        NvtxRange nvtx_call("gvdb_sparse_search_bm25_batch");
         need(s, "sparse index");
         if (nq == 0 || limit == 0) return;
         need(q_off, "q_off"); need(doc_out, "doc_out"); need(score_out, "score_out");
@@ -2710,6 +2734,7 @@ gvdb_status gvdb_sparse_search_bm25_batch_device(gvdb_sparse* s, void* stream, u
                                                  const uint32_t* q_terms, const float* q_tfs, uint32_t limit,
                                                  uint64_t* doc_out_dev, float* score_out_dev) {
     return guarded([&] {
+        NvtxRange nvtx_call("gvdb_sparse_search_bm25_batch_device");
         need(s, "sparse index");
         if (nq == 0 || limit == 0) return;
         need(q_off, "q_off"); need(doc_out_dev, "doc_out"); need(score_out_dev, "score_out");

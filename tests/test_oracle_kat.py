@@ -246,3 +246,35 @@ def test_golden_hybrid_fixture_roundtrip():
         fi, fs = oracle.rrf_fusion(dense_ids[q], d, [], g["rrf_k"])
         assert fi[:limit].tolist() == g["fused"][q]["ids"]
         assert fs[:limit].view(np.uint32).tolist() == g["fused"][q]["score_bits"]
+
+
+def test_msb0_packing_and_hamming_against_numpy_packbits():
+    """An independent pin of the two conventions everything else rests on: BitVec<u8, Msb0>
+    packing (src/quantization.rs:98-109: bit i of the vector is bit 7 - i % 8 of byte i / 8) is numpy's
+    packbits(bitorder="big"), and hamming::distance (crate hamming 0.1.3, :137-139) is the popcount of the XOR,
+    i.e. the number of differing unpacked bits — on the reference's own test inputs (:361-386) and on random
+    vectors of ragged dimensions, without going through the oracle's own packing code."""
+    cases = [np.array([0.5, -0.3, 0.8, -0.1, 0.2], dtype=np.float32),          # test_binary_quantization
+             np.array([1.0, -1.0, 1.0, -1.0], dtype=np.float32),                # test_hamming_distance, vec1
+             np.array([1.0, 1.0, -1.0, -1.0], dtype=np.float32),                # test_hamming_distance, vec2
+             np.array([0.1, 0.2, 0.3], dtype=np.float32)]                       # test_binary_vector_store
+    rng = np.random.default_rng(7)
+    for dim in (1, 7, 8, 9, 63, 64, 65, 100, 768, 1000, 1536):
+        cases.append(rng.standard_normal(dim).astype(np.float32))
+        cases.append(rng.standard_normal(dim).astype(np.float32))
+    for x in cases:
+        want = np.packbits((x > np.float32(0.0)).astype(np.uint8), bitorder="big")
+        got = oracle.quantize(x)
+        assert got.dtype == np.uint8 and np.array_equal(got[:want.size], want) and not got[want.size:].any()
+    assert oracle.quantize(cases[0])[0] == 0b10101000                           # [1, 0, 1, 0, 1] -> 0xA8
+    for a, b in zip(cases[1::2], cases[2::2]):
+        if a.size != b.size:
+            continue
+        ba, bb = (a > 0).astype(np.uint8), (b > 0).astype(np.uint8)
+        d = int(np.count_nonzero(ba != bb))
+        ca, cb = oracle.quantize(a), oracle.quantize(b)
+        assert oracle.hamming(ca, cb) == d
+        assert d == int(np.unpackbits(np.bitwise_xor(ca, cb)).sum())
+        assert oracle.similarity(ca, cb, a.size) == np.float32(1.0) - np.float32(d) / np.float32(a.size)
+    # the reference's test_hamming_distance pair: two of four signs differ
+    assert oracle.hamming(oracle.quantize(cases[1]), oracle.quantize(cases[2])) == 2
