@@ -73,6 +73,13 @@ __device__ __forceinline__ void tma_bulk_g2s(uint32_t dst, const void* src, uint
         :: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
 
+// Programmatic dependent launch (the hot single-pass chain is launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization): a kernel lets its successor's CTAs be scheduled as soon as every
+// CTA of its own has started, and waits for its predecessor to have completed (and flushed) before it touches global
+// memory.  Both are no-ops in a normally launched kernel.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // Orderable image of an f32: ascending u32 order == ascending float order; -0.0 and +0.0
 // share one image (Rust's partial_cmp calls them Equal, so they must tie).
 __device__ __forceinline__ uint32_t f32_asc_key(float f) {
@@ -460,6 +467,8 @@ __global__ void __launch_bounds__(SELH_THREADS)
 select_hist_kernel(uint64_t* __restrict__ buf, uint32_t cap, uint32_t* __restrict__ cnt, uint32_t R,
                    uint32_t r_pow2, uint32_t nbins, uint32_t* __restrict__ qpack, int qs, int tau_word,
                    uint32_t opt_m, int verify, uint32_t* __restrict__ flags) {
+    pdl_launch_dependents();
+    pdl_wait();
     extern __shared__ __align__(16) uint64_t sel[];
     uint64_t* tie = sel + r_pow2;
     uint32_t* hist = reinterpret_cast<uint32_t*>(tie + SORT_N);
@@ -842,6 +851,8 @@ rescore_topk_kernel(const float* __restrict__ rows, const float* __restrict__ no
                     uint32_t* __restrict__ rec_ham, uint64_t* __restrict__ rec_ids, float* __restrict__ rec_score,
                     const float* const* __restrict__ peer_rows, uint64_t rows_per_owner,
                     uint32_t slice_q /* > 0: packed shard records grouped by slices of slice_q queries, rec_ids = base */) {
+    pdl_launch_dependents();
+    pdl_wait();
     extern __shared__ __align__(16) float rt_smem[];         // query row | per warp: 2 slabs of 32 x RT_STRIDE | sort keys
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nwarps = blockDim.x >> 5;

@@ -304,6 +304,8 @@ __global__ void __launch_bounds__(32 * QPT_WARPS)
 query_prep_tc_kernel(const float* __restrict__ x, uint32_t nq, uint32_t nq_pad, int dim, float thr, int nchunk,
                      float* __restrict__ norms, uint32_t* __restrict__ qpack, int qs, int8_t* __restrict__ qexp,
                      uint32_t* __restrict__ qpop, uint32_t* __restrict__ cnt, uint32_t* __restrict__ flags) {
+    pdl_launch_dependents();
+    pdl_wait();
     extern __shared__ __align__(16) float s_rows[];           // QPT_WARPS x dim floats, then QPT_WARPS x nchunk*4 words
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (blockIdx.x == 0 && threadIdx.x < 8 && flags) flags[threadIdx.x] = 0u;
@@ -385,6 +387,8 @@ __global__ void __launch_bounds__(32 * TC_TAU_WARPS)
 tc_tau_kernel(const int32_t* __restrict__ tilemin, uint32_t n_tiles, uint32_t nq, uint32_t nq_pad, uint32_t m,
               const uint32_t* __restrict__ qpop, uint32_t* __restrict__ qpack, int qs, int nchunk,
               int8_t* __restrict__ qexp, int32_t* __restrict__ qbase) {
+    pdl_launch_dependents();
+    pdl_wait();
     extern __shared__ int16_t s_min[];                         // TC_TAU_WARPS x (n_tiles + 2)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t q0 = blockIdx.x * TC_TAU_WARPS;
@@ -446,6 +450,9 @@ tc_scan_kernel(const uint4* __restrict__ codes, const uint32_t* __restrict__ liv
                uint2* __restrict__ recs, uint32_t rec_cap, uint32_t* __restrict__ list_counts, uint32_t* __restrict__ overflow,
                uint32_t* __restrict__ dist_out, uint64_t dist_stride, uint64_t n_rows,
                int32_t* __restrict__ tilemin, int dbg = 0, unsigned long long* __restrict__ prof = nullptr) {
+    // the sample pass lets the (small) threshold kernel in early; the main pass does not: scatter CTAs resident beside
+    // it cost the MMA warp issue slots (measured: 0.507 ms per step with, 0.441 without)
+    if (MODE == 2) pdl_launch_dependents();
     constexpr int QB = tc_qblocks(NCHUNK);     // resident query blocks
     constexpr int NBUF = TC_NBUF;              // accumulator buffers
     constexpr int NSLOT = TC_NSLOT;            // A ring slots
@@ -491,6 +498,7 @@ tc_scan_kernel(const uint4* __restrict__ codes, const uint32_t* __restrict__ liv
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    pdl_wait();                                          // barriers and TMEM are set up under the predecessor's tail
     // The CTA owns all 512 columns (one CTA per SM: the shared memory does not admit a second one),
     // so the allocation starts at lane 0, column 0.  Using the constant keeps every TMEM address of
     // the MMA sequence in uniform registers.
@@ -909,6 +917,8 @@ tc_scatter_kernel(const uint2* __restrict__ recs, uint32_t rec_cap, const uint32
                   const uint4* __restrict__ codes, int nchunk, const uint32_t* __restrict__ qpack, int qs,
                   uint32_t* __restrict__ cnt, uint64_t* __restrict__ buf, uint32_t cap,
                   uint32_t* __restrict__ overflow) {
+    pdl_launch_dependents();
+    pdl_wait();
     const uint32_t n_list = list_counts[blockIdx.y];
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_list; i += gridDim.x * blockDim.x) {
         const uint2 r = recs[(size_t)blockIdx.y * rec_cap + i];

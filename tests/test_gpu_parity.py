@@ -412,6 +412,28 @@ def test_save_load_round_trip(gv, tmp_path):
     assert np.array_equal(a[0], b[0]) and np.array_equal(_bits(a[1]), _bits(b[1]))
     assert np.array_equal(fa[0], fb[0]) and np.array_equal(_bits(fa[1]), _bits(fb[1]))
     assert int(a[0].min()) >= 5000      # global ids carry the saved row_base
+    # the file is written beside the target and renamed over it: nothing else is left behind
+    import os
+    assert sorted(os.listdir(tmp_path)) == ["shard.gvdb"]
+    # a header whose live count disagrees with the tombstone bitmap, or whose row count is out of range, is refused;
+    # stray bits past the last row are cleared (n = 9001: the last word of the bitmap has 9 valid bits)
+    hdr_live = 32                   # offsets inside the 64-byte header: rows @24, live_rows @32
+    bad = raw.copy(); bad[hdr_live:hdr_live + 8] = np.frombuffer(np.uint64(n).tobytes(), dtype=np.uint8)
+    bad.tofile(tmp_path / "bad_live.gvdb")
+    with pytest.raises(gv.VectorDbError):
+        gv.GpuIndex.load(str(tmp_path / "bad_live.gvdb"))
+    bad = raw.copy(); bad[24:32] = np.frombuffer(np.uint64(1 << 33).tobytes(), dtype=np.uint8)
+    bad.tofile(tmp_path / "bad_rows.gvdb")
+    with pytest.raises(gv.VectorDbError):
+        gv.GpuIndex.load(str(tmp_path / "bad_rows.gvdb"))
+    pad64 = lambda x: (x + 63) // 64 * 64
+    live_off = 64 + pad64(n * nb) + pad64(n * 4)
+    stray = raw.copy(); stray[live_off + (n // 32) * 4 + 3] |= 0x80          # bit 31 of the last word: row 9023 does not exist
+    stray.tofile(tmp_path / "stray.gvdb")
+    with gv.GpuIndex.load(str(tmp_path / "stray.gvdb")) as idx3:
+        assert len(idx3) == n - 4
+        c = idx3.search_batch(qs, 10, 40)
+    assert np.array_equal(a[0], c[0]) and np.array_equal(_bits(a[1]), _bits(c[1]))
 
 
 def test_query_parallel_replicated_codes_equals_single_index(gv):
