@@ -108,6 +108,10 @@ SYMBOLS = {
     "gvdb_sparse_search_bm25_batch_device": (_i32, [_vp, _vp, _u32, _vp, _vp, _vp, _u32, _vp, _vp]),
     "gvdb_sparse_launches": (_u64, [_vp]),
     "gvdb_rrf_fusion_batch": (_i32, [_i32, _vp, _u32, _vp, _u32, _vp, _u32, _u32, C.c_float, _u32, _vp, _vp]),
+    "gvdb_weighted_fusion_batch": (_i32, [_i32, _vp, _vp, _u32, _vp, _vp, _u32, _vp, _vp, _u32, _u32, C.c_float, C.c_float, C.c_float,
+                                           _i32, _u32, _vp, _vp]),
+    "gvdb_weighted_fusion_batch_device": (_i32, [_i32, _vp, _vp, _vp, _u32, _vp, _vp, _u32, _vp, _vp, _u32, _u32, C.c_float, C.c_float,
+                                                  C.c_float, _i32, _u32, _vp, _vp]),
     "gvdb_rrf_fusion_batch_device": (_i32, [_i32, _vp, _vp, _u32, _vp, _u32, _vp, _u32, _u32, C.c_float, _u32, _vp, _vp]),
     "gvdb_profile_enable": (_i32, [_vp, _i32]),
     "gvdb_profile_read": (_i32, [_vp, _vp, _i32]),

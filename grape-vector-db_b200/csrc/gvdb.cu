@@ -2804,19 +2804,74 @@ uint64_t gvdb_sparse_launches(const gvdb_sparse* s) { return s ? s->launches : 0
 
 // ---- rrf_fusion ---------------------------------------------------------------------------------------
 namespace {
-void rrf_launch(cudaStream_t st, const uint64_t* dense, uint32_t n_d, const uint64_t* sparse, uint32_t n_s,
-                const uint64_t* text, uint32_t n_t, uint32_t nq, float k, uint32_t limit, uint64_t* ids_out, float* scores_out) {
+// mode 0: rrf_fusion; 1: linear_fusion; 2: normalized_fusion (gvdb_sparse.cuh)
+void fusion_launch(int mode, cudaStream_t st, const uint64_t* dense, uint32_t n_d, const uint64_t* sparse, uint32_t n_s,
+                   const uint64_t* text, uint32_t n_t, uint32_t nq, float k, FusionScores fs, uint32_t limit,
+                   uint64_t* ids_out, float* scores_out) {
     const uint32_t n = n_d + n_s + n_t;
-    if (n == 0 || n > RRF_MAX) fail(GVDB_ERR_INVALID_ARGUMENT, "rrf_fusion: the three list lengths must sum to 1..4096");
-    if ((n_d && !dense) || (n_s && !sparse) || (n_t && !text)) fail(GVDB_ERR_INVALID_ARGUMENT, "rrf_fusion: null list");
+    if (n == 0 || n > RRF_MAX) fail(GVDB_ERR_INVALID_ARGUMENT, "fusion: the three list lengths must sum to 1..4096");
+    if ((n_d && !dense) || (n_s && !sparse) || (n_t && !text)) fail(GVDB_ERR_INVALID_ARGUMENT, "fusion: null list");
+    if (mode != 0 && ((n_d && !fs.dense) || (n_s && !fs.sparse) || (n_t && !fs.text)))
+        fail(GVDB_ERR_INVALID_ARGUMENT, "fusion: null score list");
     uint32_t n_eff = 64;
     while (n_eff < n) n_eff <<= 1;
-    const size_t smem = (size_t)n * 8 + (size_t)n_eff * 8 + (size_t)n * 4;
-    static std::atomic<uint64_t> attr_done{0};
-    ensure_dyn_smem(attr_done, rrf_fusion_kernel, (int)(RRF_MAX * 20));
+    const size_t smem = (size_t)n * 8 + (size_t)n_eff * 8 + (size_t)n * 8;
+    static std::atomic<uint64_t> attr0{0}, attr1{0}, attr2{0};
     const unsigned threads = n_eff <= 512 ? 256 : SORT_THREADS;
-    rrf_fusion_kernel<<<nq, threads, smem, st>>>(dense, n_d, sparse, n_s, text, n_t, k, limit, ids_out, scores_out);
+    if (mode == 0) {
+        ensure_dyn_smem(attr0, list_fusion_kernel<0>, (int)(RRF_MAX * 24));
+        list_fusion_kernel<0><<<nq, threads, smem, st>>>(dense, n_d, sparse, n_s, text, n_t, k, fs, limit, ids_out, scores_out);
+    } else if (mode == 1) {
+        ensure_dyn_smem(attr1, list_fusion_kernel<1>, (int)(RRF_MAX * 24));
+        list_fusion_kernel<1><<<nq, threads, smem, st>>>(dense, n_d, sparse, n_s, text, n_t, k, fs, limit, ids_out, scores_out);
+    } else {
+        ensure_dyn_smem(attr2, list_fusion_kernel<2>, (int)(RRF_MAX * 24));
+        list_fusion_kernel<2><<<nq, threads, smem, st>>>(dense, n_d, sparse, n_s, text, n_t, k, fs, limit, ids_out, scores_out);
+    }
     CU(cudaGetLastError());
+}
+
+// host lists in, host lists out (shared by the rrf and the weighted entry points)
+void fusion_host(int mode, int32_t device, const uint64_t* dense, const float* dense_sc, uint32_t n_dense,
+                 const uint64_t* sparse, const float* sparse_sc, uint32_t n_sparse, const uint64_t* text,
+                 const float* text_sc, uint32_t n_text, uint32_t nq, float k, float w_d, float w_s, float w_t,
+                 uint32_t limit, uint64_t* ids_out, float* scores_out) {
+    if (nq == 0 || limit == 0) return;
+    need(ids_out, "ids_out"); need(scores_out, "scores_out");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        fail(GVDB_ERR_INDEX, "no usable CUDA device (there is no CPU fallback)");
+    if (device < 0 || device >= ndev) fail(GVDB_ERR_INVALID_ARGUMENT, "bad device ordinal");
+    if ((n_dense && !dense) || (n_sparse && !sparse) || (n_text && !text)) fail(GVDB_ERR_INVALID_ARGUMENT, "fusion: null list");
+    if (mode != 0 && ((n_dense && !dense_sc) || (n_sparse && !sparse_sc) || (n_text && !text_sc)))
+        fail(GVDB_ERR_INVALID_ARGUMENT, "fusion: null score list");
+    DeviceGuard dg(device);
+    const size_t nl = (size_t)nq * (n_dense + n_sparse + n_text);
+    DevBuf in, insc, out;
+    struct Rel { DevBuf &a, &b, &c; ~Rel() { a.release(); b.release(); c.release(); } } rel{in, insc, out};
+    in.ensure(std::max<size_t>(8, nl * 8));
+    insc.ensure(std::max<size_t>(8, nl * 4));
+    out.ensure((size_t)nq * limit * 12);
+    uint64_t* d = in.as<uint64_t>();
+    uint64_t* sp = d + (size_t)nq * n_dense;
+    uint64_t* tx = sp + (size_t)nq * n_sparse;
+    float* ds = insc.as<float>();
+    float* ss = ds + (size_t)nq * n_dense;
+    float* ts = ss + (size_t)nq * n_sparse;
+    if (n_dense) CU(cudaMemcpy(d, dense, (size_t)nq * n_dense * 8, cudaMemcpyHostToDevice));
+    if (n_sparse) CU(cudaMemcpy(sp, sparse, (size_t)nq * n_sparse * 8, cudaMemcpyHostToDevice));
+    if (n_text) CU(cudaMemcpy(tx, text, (size_t)nq * n_text * 8, cudaMemcpyHostToDevice));
+    if (mode != 0) {
+        if (n_dense) CU(cudaMemcpy(ds, dense_sc, (size_t)nq * n_dense * 4, cudaMemcpyHostToDevice));
+        if (n_sparse) CU(cudaMemcpy(ss, sparse_sc, (size_t)nq * n_sparse * 4, cudaMemcpyHostToDevice));
+        if (n_text) CU(cudaMemcpy(ts, text_sc, (size_t)nq * n_text * 4, cudaMemcpyHostToDevice));
+    }
+    uint64_t* oi = out.as<uint64_t>();
+    float* os = reinterpret_cast<float*>(oi + (size_t)nq * limit);
+    fusion_launch(mode, nullptr, n_dense ? d : nullptr, n_dense, n_sparse ? sp : nullptr, n_sparse, n_text ? tx : nullptr, n_text,
+                  nq, k, FusionScores{ds, ss, ts, w_d, w_s, w_t}, limit, oi, os);
+    CU(cudaMemcpy(ids_out, oi, (size_t)nq * limit * 8, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(scores_out, os, (size_t)nq * limit * 4, cudaMemcpyDeviceToHost));
 }
 }  // namespace
 
@@ -2828,8 +2883,8 @@ gvdb_status gvdb_rrf_fusion_batch_device(int32_t device, void* stream, const uin
         if (nq == 0 || limit == 0) return;
         need(ids_out_dev, "ids_out"); need(scores_out_dev, "scores_out");
         DeviceGuard dg(device);
-        rrf_launch((cudaStream_t)stream, dense_dev, n_dense, sparse_dev, n_sparse, text_dev, n_text, nq, k, limit,
-                   ids_out_dev, scores_out_dev);
+        fusion_launch(0, (cudaStream_t)stream, dense_dev, n_dense, sparse_dev, n_sparse, text_dev, n_text, nq, k,
+                      FusionScores{nullptr, nullptr, nullptr, 0.f, 0.f, 0.f}, limit, ids_out_dev, scores_out_dev);
     });
 }
 
@@ -2837,31 +2892,35 @@ gvdb_status gvdb_rrf_fusion_batch(int32_t device, const uint64_t* dense, uint32_
                                   uint32_t n_sparse, const uint64_t* text, uint32_t n_text, uint32_t nq, float k,
                                   uint32_t limit, uint64_t* ids_out, float* scores_out) {
     return guarded([&] {
+        fusion_host(0, device, dense, nullptr, n_dense, sparse, nullptr, n_sparse, text, nullptr, n_text, nq, k, 0.f, 0.f, 0.f,
+                    limit, ids_out, scores_out);
+    });
+}
+
+gvdb_status gvdb_weighted_fusion_batch_device(int32_t device, void* stream, const uint64_t* dense_dev,
+                                              const float* dense_scores_dev, uint32_t n_dense, const uint64_t* sparse_dev,
+                                              const float* sparse_scores_dev, uint32_t n_sparse, const uint64_t* text_dev,
+                                              const float* text_scores_dev, uint32_t n_text, uint32_t nq, float dense_weight,
+                                              float sparse_weight, float text_weight, int32_t normalize, uint32_t limit,
+                                              uint64_t* ids_out_dev, float* scores_out_dev) {
+    return guarded([&] {
         if (nq == 0 || limit == 0) return;
-        need(ids_out, "ids_out"); need(scores_out, "scores_out");
-        int ndev = 0;
-        if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
-            fail(GVDB_ERR_INDEX, "no usable CUDA device (there is no CPU fallback)");
-        if (device < 0 || device >= ndev) fail(GVDB_ERR_INVALID_ARGUMENT, "bad device ordinal");
-        if ((n_dense && !dense) || (n_sparse && !sparse) || (n_text && !text)) fail(GVDB_ERR_INVALID_ARGUMENT, "rrf_fusion: null list");
+        need(ids_out_dev, "ids_out"); need(scores_out_dev, "scores_out");
         DeviceGuard dg(device);
-        const size_t nl = (size_t)nq * (n_dense + n_sparse + n_text);
-        DevBuf in, out;
-        struct Rel { DevBuf &a, &b; ~Rel() { a.release(); b.release(); } } rel{in, out};
-        in.ensure(std::max<size_t>(8, nl * 8));
-        out.ensure((size_t)nq * limit * 12);
-        uint64_t* d = in.as<uint64_t>();
-        uint64_t* sp = d + (size_t)nq * n_dense;
-        uint64_t* tx = sp + (size_t)nq * n_sparse;
-        if (n_dense) CU(cudaMemcpy(d, dense, (size_t)nq * n_dense * 8, cudaMemcpyHostToDevice));
-        if (n_sparse) CU(cudaMemcpy(sp, sparse, (size_t)nq * n_sparse * 8, cudaMemcpyHostToDevice));
-        if (n_text) CU(cudaMemcpy(tx, text, (size_t)nq * n_text * 8, cudaMemcpyHostToDevice));
-        uint64_t* oi = out.as<uint64_t>();
-        float* os = reinterpret_cast<float*>(oi + (size_t)nq * limit);
-        rrf_launch(nullptr, n_dense ? d : nullptr, n_dense, n_sparse ? sp : nullptr, n_sparse, n_text ? tx : nullptr, n_text,
-                   nq, k, limit, oi, os);
-        CU(cudaMemcpy(ids_out, oi, (size_t)nq * limit * 8, cudaMemcpyDeviceToHost));
-        CU(cudaMemcpy(scores_out, os, (size_t)nq * limit * 4, cudaMemcpyDeviceToHost));
+        fusion_launch(normalize ? 2 : 1, (cudaStream_t)stream, dense_dev, n_dense, sparse_dev, n_sparse, text_dev, n_text, nq, 0.f,
+                      FusionScores{dense_scores_dev, sparse_scores_dev, text_scores_dev, dense_weight, sparse_weight, text_weight},
+                      limit, ids_out_dev, scores_out_dev);
+    });
+}
+
+gvdb_status gvdb_weighted_fusion_batch(int32_t device, const uint64_t* dense, const float* dense_scores, uint32_t n_dense,
+                                       const uint64_t* sparse, const float* sparse_scores, uint32_t n_sparse,
+                                       const uint64_t* text, const float* text_scores, uint32_t n_text, uint32_t nq,
+                                       float dense_weight, float sparse_weight, float text_weight, int32_t normalize,
+                                       uint32_t limit, uint64_t* ids_out, float* scores_out) {
+    return guarded([&] {
+        fusion_host(normalize ? 2 : 1, device, dense, dense_scores, n_dense, sparse, sparse_scores, n_sparse, text, text_scores,
+                    n_text, nq, 0.f, dense_weight, sparse_weight, text_weight, limit, ids_out, scores_out);
     });
 }
 

@@ -792,28 +792,43 @@ __global__ void fill_f32_kernel(float* __restrict__ p, size_t n, float v) {
     if (i < n) p[i] = v;
 }
 
-// ---- rrf_fusion (/root/reference/src/hybrid.rs:422-488) on the GPU ------------------------------
+// ---- rrf_fusion / linear_fusion / normalized_fusion (/root/reference/src/hybrid.rs:422-616) on the GPU ----------
 // One CTA per query.  The three lists (dense, sparse, text; document numbers, GVDB_NO_ID ends a list
-// early) are laid end to end in shared memory.  Entry p is a HEAD when no earlier entry carries its
-// document; a head's score is built in the reference's order: the dense loop INSERTS 1/(k + rank+1)
-// (a repeated document overwrites), the sparse and text loops add theirs in list order.  Heads are
-// ordered by score descending; exact ties (unspecified in the reference: HashMap iteration) by first
-// appearance.  n_d + n_s + n_t <= RRF_MAX.
+// early) are laid end to end in shared memory.  Every entry first gets its CONTRIBUTION:
+//   MODE 0 (rrf_fusion, :422-488)         1 / (k + rank + 1)
+//   MODE 1 (linear_fusion, :491-566)      score * weight of its list
+//   MODE 2 (normalized_fusion, :568-616)  normalize_scores first: (score - min) / (max - min) over the list's valid
+//                                         entries (1.0 when max - min is not > 0), then * weight
+// Entry p is a HEAD when no earlier entry carries its document; a head's score is built in the reference's order:
+// the dense loop INSERTS its contribution (a repeated document overwrites), the sparse and text loops add theirs in
+// list order.  Heads are ordered by score descending; exact ties (unspecified in the reference: HashMap iteration)
+// by first appearance.  n_d + n_s + n_t <= RRF_MAX.
 constexpr uint32_t RRF_MAX = 4096;
 
+struct FusionScores {                     // MODE 1, 2: the lists' scores and weights (unused by MODE 0)
+    const float* dense; const float* sparse; const float* text;
+    float w_dense, w_sparse, w_text;
+};
+
+template <int MODE>
 __global__ void __launch_bounds__(SORT_THREADS)
-rrf_fusion_kernel(const uint64_t* __restrict__ dense, uint32_t n_d, const uint64_t* __restrict__ sparse, uint32_t n_s,
-                  const uint64_t* __restrict__ text, uint32_t n_t, float k, uint32_t limit,
-                  uint64_t* __restrict__ ids_out, float* __restrict__ scores_out) {
+list_fusion_kernel(const uint64_t* __restrict__ dense, uint32_t n_d, const uint64_t* __restrict__ sparse, uint32_t n_s,
+                   const uint64_t* __restrict__ text, uint32_t n_t, float k, FusionScores fs, uint32_t limit,
+                   uint64_t* __restrict__ ids_out, float* __restrict__ scores_out) {
     extern __shared__ __align__(16) uint64_t rrf_smem[];
     const uint32_t n = n_d + n_s + n_t;
     const uint32_t n_eff = max(64u, next_pow2(n));
     uint64_t* ids = rrf_smem;                 // [n]
     uint64_t* keys = rrf_smem + n;            // [n_eff]
-    float* sc = reinterpret_cast<float*>(keys + n_eff);   // [n]
+    float* sc = reinterpret_cast<float*>(keys + n_eff);   // [n] fused score of a head
+    float* con = sc + n;                      // [n] contribution of an entry
     __shared__ uint32_t len[3];
+    __shared__ uint32_t s_min[3], s_max[3];   // MODE 2: ascending images of the lists' min / max score
     const uint32_t q = blockIdx.x;
-    if (threadIdx.x < 3) len[threadIdx.x] = threadIdx.x == 0 ? n_d : threadIdx.x == 1 ? n_s : n_t;
+    if (threadIdx.x < 3) {
+        len[threadIdx.x] = threadIdx.x == 0 ? n_d : threadIdx.x == 1 ? n_s : n_t;
+        s_min[threadIdx.x] = f32_asc_key(INFINITY); s_max[threadIdx.x] = f32_asc_key(-INFINITY);   // the folds' start values
+    }
     __syncthreads();
     for (uint32_t p = threadIdx.x; p < n; p += blockDim.x) {
         uint64_t id;
@@ -824,6 +839,41 @@ rrf_fusion_kernel(const uint64_t* __restrict__ dense, uint32_t n_d, const uint64
     }
     __syncthreads();
     const uint32_t l0 = len[0], l1 = len[1], l2 = len[2];
+    auto list_of = [&](uint32_t p, uint32_t& pos) { if (p < n_d) { pos = p; return 0; } if (p < n_d + n_s) { pos = p - n_d; return 1; } pos = p - n_d - n_s; return 2; };
+    auto score_of = [&](int l, uint32_t pos) {
+        return l == 0 ? fs.dense[(size_t)q * n_d + pos] : l == 1 ? fs.sparse[(size_t)q * n_s + pos] : fs.text[(size_t)q * n_t + pos];
+    };
+    if (MODE == 2) {
+        // fold(NEG_INFINITY, f32::max) / fold(INFINITY, f32::min) over the list's valid entries (NaNs are ignored by both)
+        for (uint32_t p = threadIdx.x; p < n; p += blockDim.x) {
+            uint32_t pos; const int l = list_of(p, pos);
+            if (pos < len[l]) {
+                const float v = score_of(l, pos);
+                if (v == v) { atomicMin(&s_min[l], f32_asc_key(v)); atomicMax(&s_max[l], f32_asc_key(v)); }
+            }
+        }
+        __syncthreads();
+    }
+    for (uint32_t p = threadIdx.x; p < n; p += blockDim.x) {
+        uint32_t pos; const int l = list_of(p, pos);
+        float c = 0.0f;
+        if (pos < len[l]) {
+            if (MODE == 0) c = __fdiv_rn(1.0f, __fadd_rn(k, (float)(pos + 1)));
+            else {
+                float v = score_of(l, pos);
+                if (MODE == 2) {
+                    const uint32_t a = s_min[l], b = s_max[l];                       // images back to floats (+0.0 for either zero)
+                    const float mn = __uint_as_float((a & 0x80000000u) ? (a & 0x7fffffffu) : ~a);
+                    const float mx = __uint_as_float((b & 0x80000000u) ? (b & 0x7fffffffu) : ~b);
+                    const float range = __fsub_rn(mx, mn);
+                    v = range > 0.0f ? __fdiv_rn(__fsub_rn(v, mn), range) : 1.0f;
+                }
+                c = __fmul_rn(v, l == 0 ? fs.w_dense : l == 1 ? fs.w_sparse : fs.w_text);
+            }
+        }
+        con[p] = c;
+    }
+    __syncthreads();
     for (uint32_t p = threadIdx.x; p < n_eff; p += blockDim.x) {
         uint64_t key = UINT64_MAX;
         if (p < n) {
@@ -836,20 +886,20 @@ rrf_fusion_kernel(const uint64_t* __restrict__ dense, uint32_t n_d, const uint64
                 for (uint32_t j = 0; j < l0; ++j)
                     if (ids[j] == id) {
                         if (j < p) head = false;
-                        s = __fdiv_rn(1.0f, __fadd_rn(k, (float)(j + 1)));          // insert: overwrites
+                        s = con[j];                                                     // insert: overwrites
                         have = true;
                     }
                 for (uint32_t j = 0; j < l1 && head; ++j)
                     if (ids[n_d + j] == id) {
                         if (n_d + j < p) head = false;
-                        const float r = __fdiv_rn(1.0f, __fadd_rn(k, (float)(j + 1)));
+                        const float r = con[n_d + j];
                         s = have ? __fadd_rn(s, r) : r;
                         have = true;
                     }
                 for (uint32_t j = 0; j < l2 && head; ++j)
                     if (ids[n_d + n_s + j] == id) {
                         if (n_d + n_s + j < p) head = false;
-                        const float r = __fdiv_rn(1.0f, __fadd_rn(k, (float)(j + 1)));
+                        const float r = con[n_d + n_s + j];
                         s = have ? __fadd_rn(s, r) : r;
                         have = true;
                     }

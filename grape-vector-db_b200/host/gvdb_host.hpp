@@ -13,6 +13,7 @@
 //   FaissVectorIndex (Flat)    src/index.rs:330-683             gvdb::GpuVectorIndex (exact or two-stage)
 //   VectorDbError              src/types.rs:859-920             gvdb::VectorDbError
 //   rrf_fusion                 src/hybrid.rs:422-488            gvdb::rrf_fusion
+//   linear_ / normalized_fusion src/hybrid.rs:491-616           gvdb::linear_fusion, gvdb::normalized_fusion (GPU: gvdb_weighted_fusion_batch)
 //   SparseIndex / BM25         src/sparse.rs:31-222             gvdb::SparseIndex (host, as the reference),
 //                                                               gvdb::GpuSparseIndex (postings scored on the GPU)
 //   shard merge                src/distributed/shard.rs:776-783 gvdb::concat_sort_truncate
@@ -396,6 +397,78 @@ inline std::vector<Fused> rrf_fusion(const std::vector<std::pair<std::string, fl
     add(text_results, 2);
     std::stable_sort(docs.begin(), docs.end(), [](const Fused& a, const Fused& b) { return a.score > b.score; });
     return docs;
+}
+
+// ---- linear_fusion / normalized_fusion (src/hybrid.rs:491-616) on the GPU -----------------------------------------
+// The String ids are numbered by first appearance, the three lists go to gvdb_weighted_fusion_batch (one request),
+// and the fused order comes back; the ScoreBreakdown is filled from the input lists as the reference does
+// (dense_score / sparse_score / text_score = the list's score — the normalised one for normalized_fusion —,
+// final_score = the fused score).
+namespace detail {
+inline std::vector<float> normalize_scores(const std::vector<std::pair<std::string, float>>& r) {   // :589-616, for the breakdown
+    std::vector<float> out(r.size());
+    if (r.empty()) return out;
+    float mx = -INFINITY, mn = INFINITY;
+    for (auto& e : r) { if (e.second == e.second) { mx = e.second > mx ? e.second : mx; mn = e.second < mn ? e.second : mn; } }
+    const float range = mx - mn;
+    for (size_t i = 0; i < r.size(); ++i) out[i] = range > 0.0f ? (r[i].second - mn) / range : 1.0f;
+    return out;
+}
+inline std::vector<Fused> weighted_fusion(const std::vector<std::pair<std::string, float>>& dense_results,
+                                          const std::vector<std::pair<std::string, float>>& sparse_results,
+                                          const std::vector<std::pair<std::string, float>>& text_results,
+                                          float dense_weight, float sparse_weight, float text_weight, bool normalize, int device) {
+    const std::vector<std::pair<std::string, float>>* lists[3] = {&dense_results, &sparse_results, &text_results};
+    std::unordered_map<std::string, uint64_t> number;
+    std::vector<std::string> name;
+    std::vector<uint64_t> ids[3];
+    std::vector<float> sc[3], shown[3];
+    for (int l = 0; l < 3; ++l) {
+        shown[l] = normalize ? normalize_scores(*lists[l]) : std::vector<float>();
+        for (size_t i = 0; i < lists[l]->size(); ++i) {
+            auto it = number.find((*lists[l])[i].first);
+            if (it == number.end()) { it = number.emplace((*lists[l])[i].first, (uint64_t)name.size()).first; name.push_back((*lists[l])[i].first); }
+            ids[l].push_back(it->second);
+            sc[l].push_back((*lists[l])[i].second);
+            if (!normalize) shown[l].push_back((*lists[l])[i].second);
+        }
+    }
+    std::vector<Fused> out;
+    if (name.empty()) return out;
+    std::vector<uint64_t> oi(name.size());
+    std::vector<float> os(name.size());
+    check(gvdb_weighted_fusion_batch(device, ids[0].data(), sc[0].data(), (uint32_t)ids[0].size(), ids[1].data(), sc[1].data(),
+                                     (uint32_t)ids[1].size(), ids[2].data(), sc[2].data(), (uint32_t)ids[2].size(), 1,
+                                     dense_weight, sparse_weight, text_weight, normalize ? 1 : 0, (uint32_t)name.size(),
+                                     oi.data(), os.data()));
+    std::unordered_map<uint64_t, size_t> at;
+    for (size_t t = 0; t < oi.size() && oi[t] != GVDB_NO_ID; ++t) {
+        ScoreBreakdown b; b.final_score = os[t];
+        at[oi[t]] = out.size();
+        out.push_back({name[oi[t]], os[t], b});
+    }
+    for (int l = 0; l < 3; ++l)
+        for (size_t i = 0; i < ids[l].size(); ++i) {
+            ScoreBreakdown& b = out[at[ids[l][i]]].breakdown;
+            if (l == 0) { b.has_dense = true; b.dense_score = shown[l][i]; }
+            else if (l == 1) { b.has_sparse = true; b.sparse_score = shown[l][i]; }
+            else { b.has_text = true; b.text_score = shown[l][i]; }
+        }
+    return out;
+}
+}  // namespace detail
+
+inline std::vector<Fused> linear_fusion(const std::vector<std::pair<std::string, float>>& dense_results,
+                                        const std::vector<std::pair<std::string, float>>& sparse_results,
+                                        const std::vector<std::pair<std::string, float>>& text_results,
+                                        float dense_weight, float sparse_weight, float text_weight, int device = 0) {
+    return detail::weighted_fusion(dense_results, sparse_results, text_results, dense_weight, sparse_weight, text_weight, false, device);
+}
+inline std::vector<Fused> normalized_fusion(const std::vector<std::pair<std::string, float>>& dense_results,
+                                            const std::vector<std::pair<std::string, float>>& sparse_results,
+                                            const std::vector<std::pair<std::string, float>>& text_results,
+                                            float dense_weight, float sparse_weight, float text_weight, int device = 0) {
+    return detail::weighted_fusion(dense_results, sparse_results, text_results, dense_weight, sparse_weight, text_weight, true, device);
 }
 
 // ---- SparseIndex / BM25 (src/sparse.rs:31-222) --------------------------------------------------------------

@@ -44,6 +44,33 @@ def rrf_fusion_batch(dense, sparse, text=None, k: float = 60.0, limit: int | Non
     return ids, sc
 
 
+def weighted_fusion_batch(dense, dense_scores, sparse, sparse_scores, text=None, text_scores=None,
+                          weights=(0.7, 0.2, 0.1), normalize: bool = False, limit: int | None = None, device: int = 0):
+    """linear_fusion / normalized_fusion (src/hybrid.rs:491-616) for nq queries with HOST lists: document numbers
+    (nq x n uint64, NO_ID ends a list early) and their scores (nq x n float32)."""
+    lib = _ffi.lib()
+    lists, scores = [], []
+    nq = None
+    for a, sc in ((dense, dense_scores), (sparse, sparse_scores), (text, text_scores)):
+        if a is None:
+            lists.append(None); scores.append(None)
+            continue
+        a = _np(a, np.uint64)
+        a = a.reshape(1, -1) if a.ndim == 1 else a
+        sc = _np(sc, np.float32).reshape(a.shape)
+        nq = a.shape[0] if nq is None else nq
+        assert a.shape[0] == nq
+        lists.append(a if a.shape[1] else None); scores.append(sc if a.shape[1] else None)
+    n = [0 if a is None else a.shape[1] for a in lists]
+    limit = sum(n) if limit is None else limit
+    ids = np.full((nq, limit), NO_ID, dtype=np.uint64)
+    out = np.full((nq, limit), -np.inf, dtype=np.float32)
+    raise_for_status(lib.gvdb_weighted_fusion_batch(
+        device, _ptr(lists[0]), _ptr(scores[0]), n[0], _ptr(lists[1]), _ptr(scores[1]), n[1], _ptr(lists[2]), _ptr(scores[2]), n[2],
+        nq, weights[0], weights[1], weights[2], int(normalize), limit, _ptr(ids), _ptr(out)), lib)
+    return ids, out
+
+
 class HybridSearcher:
     """dense GpuIndex + GpuSparseIndex + RRF, all on one GPU."""
 

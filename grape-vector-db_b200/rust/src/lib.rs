@@ -113,6 +113,18 @@ extern "C" {
     pub fn gvdb_rrf_fusion_batch_device(device: i32, stream: *mut c_void, dense_dev: *const u64, n_dense: u32,
                                         sparse_dev: *const u64, n_sparse: u32, text_dev: *const u64, n_text: u32,
                                         nq: u32, k: f32, limit: u32, ids_out_dev: *mut u64, scores_out_dev: *mut f32) -> i32;
+    // HybridSearchEngine::linear_fusion / normalized_fusion (reference src/hybrid.rs:491-616) for a batch of requests
+    pub fn gvdb_weighted_fusion_batch(device: i32, dense: *const u64, dense_scores: *const f32, n_dense: u32,
+                                      sparse: *const u64, sparse_scores: *const f32, n_sparse: u32,
+                                      text: *const u64, text_scores: *const f32, n_text: u32, nq: u32,
+                                      dense_weight: f32, sparse_weight: f32, text_weight: f32, normalize: i32,
+                                      limit: u32, ids_out: *mut u64, scores_out: *mut f32) -> i32;
+    pub fn gvdb_weighted_fusion_batch_device(device: i32, stream: *mut c_void, dense_dev: *const u64,
+                                             dense_scores_dev: *const f32, n_dense: u32, sparse_dev: *const u64,
+                                             sparse_scores_dev: *const f32, n_sparse: u32, text_dev: *const u64,
+                                             text_scores_dev: *const f32, n_text: u32, nq: u32, dense_weight: f32,
+                                             sparse_weight: f32, text_weight: f32, normalize: i32, limit: u32,
+                                             ids_out_dev: *mut u64, scores_out_dev: *mut f32) -> i32;
     pub fn gvdb_measure_fp4_mma_rate(device: i32, tmacs_per_s_out: *mut f64, clk_per_mma_out: *mut f64) -> i32;
 }
 

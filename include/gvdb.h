@@ -368,6 +368,27 @@ GVDB_API gvdb_status gvdb_rrf_fusion_batch_device(int32_t device, void* stream, 
                                                   const uint64_t* text_dev, uint32_t n_text, uint32_t nq, float k,
                                                   uint32_t limit, uint64_t* ids_out_dev, float* scores_out_dev);
 
+/* linear_fusion (src/hybrid.rs:491-566) and normalized_fusion (:568-616; normalize != 0: every list's scores go through
+ * normalize_scores first — (score - min) / (max - min) over the list, 1.0 when max - min is not > 0) for nq queries at
+ * once.  Lists as for rrf_fusion, each with its scores (nq x n_* f32: the dense similarities, the BM25 scores, the
+ * text scores).  A document's fused score is built in the reference's order: the dense loop inserts
+ * similarity * dense_weight (a repeated document overwrites), the sparse and the text loop add theirs; output ordered
+ * by fused score descending, exact ties by first appearance (the reference's order among ties is its HashMap's). */
+GVDB_API gvdb_status gvdb_weighted_fusion_batch(int32_t device, const uint64_t* dense, const float* dense_scores,
+                                                uint32_t n_dense, const uint64_t* sparse, const float* sparse_scores,
+                                                uint32_t n_sparse, const uint64_t* text, const float* text_scores,
+                                                uint32_t n_text, uint32_t nq, float dense_weight, float sparse_weight,
+                                                float text_weight, int32_t normalize, uint32_t limit,
+                                                uint64_t* ids_out, float* scores_out);
+GVDB_API gvdb_status gvdb_weighted_fusion_batch_device(int32_t device, void* stream, const uint64_t* dense_dev,
+                                                       const float* dense_scores_dev, uint32_t n_dense,
+                                                       const uint64_t* sparse_dev, const float* sparse_scores_dev,
+                                                       uint32_t n_sparse, const uint64_t* text_dev,
+                                                       const float* text_scores_dev, uint32_t n_text, uint32_t nq,
+                                                       float dense_weight, float sparse_weight, float text_weight,
+                                                       int32_t normalize, uint32_t limit, uint64_t* ids_out_dev,
+                                                       float* scores_out_dev);
+
 /* ---- measurement hooks ---------------------------------------------------------------- */
 /* When enabled, every kernel the library launches is bracketed by CUDA events on the stream
  * it is launched on; times are accumulated at the call's final synchronisation. */

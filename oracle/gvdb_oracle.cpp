@@ -405,6 +405,63 @@ GVO_API int64_t gvo_rrf_fusion(const uint64_t* dense, size_t nd, const uint64_t*
 }
 
 // ---------------------------------------------------------------------------
+// linear_fusion — src/hybrid.rs:491-566 — and normalized_fusion — :568-587 with normalize_scores
+// :589-616.  weighted = score * weight; the dense loop INSERTS (a duplicate overwrites, :511), the
+// sparse and the text loop add (`*current_score += weighted`, :518,:535) or insert; the result is
+// sorted by score descending (ties: HashMap order in the reference, first appearance here).
+// normalize != 0: each list goes through normalize_scores first: max = fold(NEG_INFINITY, f32::max),
+// min = fold(INFINITY, f32::min), range = max - min, score' = range > 0 ? (score - min) / range : 1.0.
+static std::vector<float> gvo_normalize_scores(const float* sc, size_t n) {
+    std::vector<float> out(n);
+    if (n == 0) return out;
+    float mx = -INFINITY, mn = INFINITY;
+    for (size_t i = 0; i < n; ++i) { if (!(sc[i] != sc[i])) { mx = sc[i] > mx ? sc[i] : mx; mn = sc[i] < mn ? sc[i] : mn; } }   // f32::max / f32::min ignore NaN
+    const float range = mx - mn;
+    for (size_t i = 0; i < n; ++i) out[i] = range > 0.0f ? (sc[i] - mn) / range : 1.0f;
+    return out;
+}
+
+GVO_API int64_t gvo_weighted_fusion(const uint64_t* dense, const float* dense_sc, size_t nd, const uint64_t* sparse,
+                                    const float* sparse_sc, size_t ns, const uint64_t* text, const float* text_sc,
+                                    size_t nt, float w_dense, float w_sparse, float w_text, int normalize,
+                                    uint64_t* out_idx, float* out_score, size_t out_cap) {
+    std::vector<float> nd_sc, ns_sc, nt_sc;
+    if (normalize) {
+        nd_sc = gvo_normalize_scores(dense_sc, nd); ns_sc = gvo_normalize_scores(sparse_sc, ns); nt_sc = gvo_normalize_scores(text_sc, nt);
+        dense_sc = nd_sc.data(); sparse_sc = ns_sc.data(); text_sc = nt_sc.data();
+    }
+    std::unordered_map<uint64_t, size_t> pos;
+    std::vector<uint64_t> ids;
+    std::vector<float> sc;
+    for (size_t i = 0; i < nd; ++i) {
+        const float w = dense_sc[i] * w_dense;
+        auto it = pos.find(dense[i]);
+        if (it == pos.end()) { pos[dense[i]] = ids.size(); ids.push_back(dense[i]); sc.push_back(w); }
+        else sc[it->second] = w;                          // HashMap::insert overwrites
+    }
+    const uint64_t* lists[2] = {sparse, text};
+    const float* lsc[2] = {sparse_sc, text_sc};
+    const float lw[2] = {w_sparse, w_text};
+    size_t lens[2] = {ns, nt};
+    for (int l = 0; l < 2; ++l)
+        for (size_t i = 0; i < lens[l]; ++i) {
+            const float w = lsc[l][i] * lw[l];
+            auto it = pos.find(lists[l][i]);
+            if (it == pos.end()) { pos[lists[l][i]] = ids.size(); ids.push_back(lists[l][i]); sc.push_back(w); }
+            else sc[it->second] = sc[it->second] + w;
+        }
+    std::vector<size_t> ord(ids.size());
+    std::iota(ord.begin(), ord.end(), (size_t)0);
+    std::stable_sort(ord.begin(), ord.end(), [&](size_t a, size_t b) { return sc[a] > sc[b]; });
+    size_t r = out_cap < ord.size() ? out_cap : ord.size();
+    for (size_t t = 0; t < r; ++t) {
+        out_idx[t] = ids[ord[t]];
+        out_score[t] = sc[ord[t]];
+    }
+    return (int64_t)ids.size();
+}
+
+// ---------------------------------------------------------------------------
 // BM25 — src/sparse.rs:153-222 over a CSR restatement of the inverted index
 // (HashMap<u32, Vec<InvertedIndexEntry>>, :31-38).  For term t the postings are
 // post_doc/post_tf[post_off[t] .. post_off[t+1]) in insertion (document) order;

@@ -67,6 +67,8 @@ def lib() -> C.CDLL:
         L.gvo_concat_sort_truncate.restype = i64
         L.gvo_rrf_fusion.argtypes = [vp, sz, vp, sz, vp, sz, f32, vp, vp, sz]
         L.gvo_rrf_fusion.restype = i64
+        L.gvo_weighted_fusion.argtypes = [vp, vp, sz, vp, vp, sz, vp, vp, sz, f32, f32, f32, C.c_int, vp, vp, sz]
+        L.gvo_weighted_fusion.restype = i64
         L.gvo_bm25_avg_len.argtypes = [vp, vp, vp, sz, sz]
         L.gvo_bm25_avg_len.restype = f32
         L.gvo_bm25_search.argtypes = [vp, vp, sz, vp, vp, vp, vp, sz, sz, f32, f32, f32, sz, vp, vp]
@@ -254,6 +256,20 @@ def rrf_fusion(dense, sparse, text, k: float = 60.0):
     oi = np.zeros(max(cap, 1), dtype=np.uint64)
     os_ = np.zeros(max(cap, 1), dtype=np.float32)
     got = lib().gvo_rrf_fusion(_p(d), d.size, _p(s), s.size, _p(t), t.size, k, _p(oi), _p(os_), cap)
+    return oi[:got], os_[:got]
+
+
+def weighted_fusion(dense, dense_sc, sparse, sparse_sc, text, text_sc, weights=(0.7, 0.2, 0.1), normalize: bool = False):
+    """linear_fusion (normalize=False) / normalized_fusion (normalize=True), src/hybrid.rs:491-616."""
+    d = np.ascontiguousarray(dense, dtype=np.uint64); ds = np.ascontiguousarray(dense_sc, dtype=np.float32)
+    s = np.ascontiguousarray(sparse, dtype=np.uint64); ss = np.ascontiguousarray(sparse_sc, dtype=np.float32)
+    t = np.ascontiguousarray(text, dtype=np.uint64); ts = np.ascontiguousarray(text_sc, dtype=np.float32)
+    assert d.size == ds.size and s.size == ss.size and t.size == ts.size
+    cap = d.size + s.size + t.size
+    oi = np.zeros(max(cap, 1), dtype=np.uint64)
+    os_ = np.zeros(max(cap, 1), dtype=np.float32)
+    got = lib().gvo_weighted_fusion(_p(d), _p(ds), d.size, _p(s), _p(ss), s.size, _p(t), _p(ts), t.size,
+                                    weights[0], weights[1], weights[2], int(normalize), _p(oi), _p(os_), cap)
     return oi[:got], os_[:got]
 
 

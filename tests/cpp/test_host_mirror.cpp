@@ -114,6 +114,19 @@ static void test_rrf_fusion() {                     // src/hybrid.rs:991-1025
     REQUIRE(result.size() == 4 && result[0].id == "doc1" && result[1].id == "doc2");
 }
 
+static void test_weighted_fusions() {               // src/hybrid.rs:491-616, through the GPU library
+    std::vector<std::pair<std::string, float>> dense = {{"doc1", 0.9f}, {"doc2", 0.5f}};
+    std::vector<std::pair<std::string, float>> sparse = {{"doc2", 4.0f}, {"doc3", 1.0f}};
+    auto lin = linear_fusion(dense, sparse, {}, 0.7f, 0.2f, 0.1f);
+    REQUIRE(lin.size() == 3 && lin[0].id == "doc2" && lin[1].id == "doc1" && lin[2].id == "doc3");
+    REQUIRE(lin[0].score == 0.5f * 0.7f + 4.0f * 0.2f && lin[1].score == 0.9f * 0.7f && lin[2].score == 1.0f * 0.2f);
+    REQUIRE(lin[0].breakdown.has_dense && lin[0].breakdown.has_sparse && lin[0].breakdown.sparse_score == 4.0f);
+    auto nrm = normalized_fusion(dense, sparse, {{"doc7", 123.0f}}, 0.7f, 0.2f, 0.1f);
+    REQUIRE(nrm.size() == 4 && nrm[0].id == "doc1" && nrm[1].id == "doc2" && nrm[2].id == "doc7" && nrm[3].id == "doc3");
+    REQUIRE(nrm[0].score == 0.7f && nrm[1].score == 0.0f + 0.2f && nrm[2].score == 0.1f && nrm[3].score == 0.0f);
+    REQUIRE(nrm[2].breakdown.has_text && nrm[2].breakdown.text_score == 1.0f);
+}
+
 static void test_sparse_bm25() {                    // src/sparse.rs:153-222
     SparseIndex idx;
     idx.add_document({"a", {{0, 1.0f}}, 1.0f});
@@ -183,6 +196,7 @@ int main() {
     test_vector_index_trait();
     test_filtered_search();
     test_rrf_fusion();
+    test_weighted_fusions();
     test_sparse_bm25();
     test_gpu_sparse_bm25();
     test_hybrid_search();

@@ -149,6 +149,36 @@ def test_rrf_matches_oracle(gv):
             assert np.all(ids[q, r:] == gv.NO_ID) and np.all(np.isneginf(sc[q, r:]))
 
 
+def test_weighted_fusions_match_oracle(gv):
+    """linear_fusion and normalized_fusion (src/hybrid.rs:491-616) on the GPU: documents and score BITS equal the
+    oracle's, incl. duplicates inside the dense list (insert overwrites), lists cut short by NO_ID, exact score
+    ties (first appearance), constant lists (normalize -> 1.0), an empty text list."""
+    rng = np.random.default_rng(21)
+    nq, nd, ns, nt = 9, 40, 30, 12
+    d = rng.integers(0, 60, size=(nq, nd)).astype(np.uint64)          # duplicates on purpose
+    s = np.stack([rng.choice(60, size=ns, replace=False) for _ in range(nq)]).astype(np.uint64)
+    t = np.stack([rng.choice(60, size=nt, replace=False) for _ in range(nq)]).astype(np.uint64)
+    dsc = (rng.integers(-16, 17, size=(nq, nd)) / 8).astype(np.float32)  # coarse grid: plenty of exact ties
+    ssc = (rng.integers(0, 40, size=(nq, ns)) / 4).astype(np.float32)
+    tsc = (rng.integers(0, 6, size=(nq, nt))).astype(np.float32)
+    dsc[3] = 0.25                                                       # a constant list
+    d[1, 25:] = gv.NO_ID; s[2, 7:] = gv.NO_ID; t[4, :] = gv.NO_ID       # lists that end early / an empty list
+    trim = lambda a, sc: (a[a != gv.NO_ID][:np.argmax(a == gv.NO_ID) if (a == gv.NO_ID).any() else a.size],
+                          sc[:np.argmax(a == gv.NO_ID) if (a == gv.NO_ID).any() else a.size])
+    for normalize in (False, True):
+        for limit in (15, nd + ns + nt):
+            ids, sc = gv.weighted_fusion_batch(d, dsc, s, ssc, t, tsc, (0.7, 0.2, 0.1), normalize, limit)
+            for q in range(nq):
+                (a, asc), (b, bsc), (c, csc) = trim(d[q], dsc[q]), trim(s[q], ssc[q]), trim(t[q], tsc[q])
+                oi, os_ = oracle.weighted_fusion(a, asc, b, bsc, c, csc, (0.7, 0.2, 0.1), normalize)
+                r = min(limit, len(oi))
+                assert np.array_equal(ids[q, :r], oi[:r]), (normalize, limit, q)
+                assert np.array_equal(_bits(sc[q, :r]), _bits(os_[:r])), (normalize, limit, q)
+                assert np.all(ids[q, r:] == gv.NO_ID) and np.all(np.isneginf(sc[q, r:]))
+    ids, sc = gv.weighted_fusion_batch([[1, 2]], [[0.9, 0.5]], [[2, 3]], [[4.0, 1.0]], None, None, (0.7, 0.2, 0.1), False)
+    assert ids[0].tolist()[:3] == [2, 1, 3]
+
+
 def test_hybrid_search_matches_oracle_composition(gv):
     """HybridSearchEngine::search (src/hybrid.rs:286-356) on the GPU == oracle dense list + oracle BM25
     list + oracle RRF, for two-stage and exact dense lists."""

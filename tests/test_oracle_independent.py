@@ -179,3 +179,61 @@ def test_bm25_and_rrf_match_independent_restatement():
         ids, sc = oracle.rrf_fusion(d, s, t, 60.0)
         assert [int(i) for i in ids] == [i for i, _ in want]
         assert np.array_equal(_bits(sc), _bits([x for _, x in want]))
+
+
+def py_normalize(scores):                       # src/hybrid.rs:589-616
+    if not scores:
+        return []
+    mx, mn = F(-np.inf), F(np.inf)
+    for s in scores:
+        mx = s if s > mx else mx                 # f32::max / f32::min
+        mn = s if s < mn else mn
+    rng_ = F(mx - mn)
+    return [F(F(s - mn) / rng_) if rng_ > 0 else F(1.0) for s in scores]
+
+
+def py_weighted(dense, sparse, text, weights, normalize):    # src/hybrid.rs:491-587; lists of (doc, score)
+    lists = []
+    for lst in (dense, sparse, text):
+        sc = [F(s) for _, s in lst]
+        if normalize:
+            sc = py_normalize(sc)
+        lists.append([(d, s) for (d, _), s in zip(lst, sc)])
+    score, first = {}, []
+    for d, s in lists[0]:
+        if d not in score:
+            first.append(d)
+        score[d] = F(s * F(weights[0]))          # insert: overwrites
+    for li in (1, 2):
+        for d, s in lists[li]:
+            w = F(s * F(weights[li]))
+            if d in score:
+                score[d] = F(score[d] + w)
+            else:
+                score[d] = w
+                first.append(d)
+    order = sorted(range(len(first)), key=lambda i: -score[first[i]])    # stable: ties by first appearance
+    return [(first[i], score[first[i]]) for i in order]
+
+
+def test_weighted_fusions_match_independent_restatement_and_known_values():
+    # known answers: dense [(1, .9), (2, .5)], sparse [(2, 4.0), (3, 1.0)], weights .7 / .2 / .1
+    ids, sc = oracle.weighted_fusion([1, 2], [0.9, 0.5], [2, 3], [4.0, 1.0], [], [], (0.7, 0.2, 0.1), False)
+    want = {1: F(F(0.9) * F(0.7)), 2: F(F(F(0.5) * F(0.7)) + F(F(4.0) * F(0.2))), 3: F(F(1.0) * F(0.2))}
+    assert [int(i) for i in ids] == [2, 1, 3]
+    assert np.array_equal(_bits(sc), _bits([want[2], want[1], want[3]]))
+    # normalized: every list mapped to [0, 1] first — dense (1.0, 0.0), sparse (1.0, 0.0); a one-entry list becomes 1.0
+    ids, sc = oracle.weighted_fusion([1, 2], [0.9, 0.5], [2, 3], [4.0, 1.0], [7], [123.0], (0.7, 0.2, 0.1), True)
+    assert [int(i) for i in ids] == [1, 2, 7, 3]
+    assert np.array_equal(_bits(sc), _bits([F(0.7), F(F(0.0) + F(0.2)), F(0.1), F(0.0)]))
+    rng = np.random.default_rng(13)
+    for trial in range(8):
+        mk = lambda n: list(zip(rng.choice(30, size=n, replace=trial % 2 == 1).tolist(),
+                                (rng.integers(-8, 9, size=n) / 4).astype(np.float32).tolist()))
+        d, s, t = mk(12), mk(10), mk(int(rng.integers(0, 8)))
+        for normalize in (False, True):
+            want = py_weighted(d, s, t, (0.7, 0.2, 0.1), normalize)
+            ids, sc = oracle.weighted_fusion([x for x, _ in d], [y for _, y in d], [x for x, _ in s], [y for _, y in s],
+                                             [x for x, _ in t], [y for _, y in t], (0.7, 0.2, 0.1), normalize)
+            assert [int(i) for i in ids] == [i for i, _ in want]
+            assert np.array_equal(_bits(sc), _bits([x for _, x in want]))
