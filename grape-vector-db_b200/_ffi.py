@@ -80,6 +80,10 @@ SYMBOLS = {
     "gvdb_shard_record_bytes": (_u64, [_u32, _u32]),
     "gvdb_search_shard_device": (_i32, [_vp, _vp, _vp, _u32, _u32, _vp]),
     "gvdb_search_shard_sliced_device": (_i32, [_vp, _vp, _vp, _u32, _u32, _u32, _vp]),
+    "gvdb_shard_hist_bins": (_u32, [_vp]),
+    "gvdb_shard_hist_device": (_i32, [_vp, _vp, _vp, _u32, _vp]),
+    "gvdb_search_shard_ratio_device": (_i32, [_vp, _vp, _vp, _u32, _u64, _u32, _vp, _u32, _u32, _vp]),
+    "gvdb_merge_shards_ratio_device": (_i32, [_vp, _vp, _u32, _vp, _u32, _u32, _vp, _vp]),
     "gvdb_search_shard_sliced_enqueue_device": (_i32, [_vp, _vp, _vp, _u32, _u32, _u32, _vp, _vp]),
     "gvdb_search_shard_verify": (_i32, [_vp, _vp, C.POINTER(_i32)]),
     "gvdb_merge_shards_device": (_i32, [_vp, _vp, _u32, _vp, _u32, _u32, _u32, _vp, _vp]),

@@ -99,7 +99,7 @@ struct Workspace {
     DevBuf r_q16, r_thr, r_state, r_counts, r_ecnt, r_ekeys, r_esc, r_fb, r_topk_i, r_topk_s, r_list, r_misc;   // ratio mode (gvdb_ratio.cuh)
     uint32_t* h_fb = nullptr;        // pinned: per-query fallback flags of a ratio-mode tile
     size_t h_fb_bytes = 0;
-    DevBuf big_keys, big_keys2, big_aux, big_k32, big_v32, big_tmp;   // large-R path (gvdb_bigr.cuh)
+    DevBuf big_keys, big_keys2, big_aux, big_k32, big_v32, big_tmp, big_cut;   // large-R path (gvdb_bigr.cuh)
     uint32_t* h_flag = nullptr;      // pinned
     const uint32_t* live_eff = nullptr;   // per-call row filter ANDed with the tombstone bitmap (filtered searches)
     DevBuf filt, allow_in;
@@ -109,7 +109,7 @@ struct Workspace {
         for (DevBuf* b : {&qpack, &qnorm, &cnt, &flag, &buf, &rec_ham, &rec_ids, &rec_score, &q_in,
                           &ids_out, &sc_out, &codes_tmp, &misc, &qexp, &qpop, &qbase, &tilemin, &tc_recs, &list_counts, &r_q16, &r_thr, &r_state, &r_counts, &r_ecnt, &r_ekeys,
                           &r_esc, &r_fb, &r_topk_i, &r_topk_s, &r_list, &r_misc,
-                          &big_keys, &big_keys2, &big_aux, &big_k32, &big_v32, &big_tmp, &filt, &allow_in}) b->release();
+                          &big_keys, &big_keys2, &big_aux, &big_k32, &big_v32, &big_tmp, &big_cut, &filt, &allow_in}) b->release();
         if (h_flag) cudaFreeHost(h_flag);
         if (h_res) cudaFreeHost(h_res);
         if (h_fb) cudaFreeHost(h_fb);
@@ -942,6 +942,126 @@ void search_big_r(gvdb_index* h, Workspace* ws, cudaStream_t st, const float* q_
             if (cand_ids) CU(cudaMemcpyAsync(cand_ids + (size_t)gq * R, ws->rec_ids.p, (size_t)R * 8, cudaMemcpyDeviceToDevice, st));
             if (cand_ham) CU(cudaMemcpyAsync(cand_ham + (size_t)gq * R, ws->rec_ham.p, (size_t)R * 4, cudaMemcpyDeviceToDevice, st));
             h->launches.fetch_add(7, std::memory_order_relaxed);
+        }
+    }
+    CU(cudaStreamSynchronize(st));
+    flush_profile(h, ws);
+}
+
+// ---- ratio mode across row shards: per-shard histograms, then the shard's members of the global top R ----
+// (the protocol of gvdb_bigr.cuh: gvdb_shard_hist_device -> gather -> gvdb_search_shard_ratio_device -> gather ->
+// gvdb_merge_shards_ratio_device).  One query at a time like search_big_r; distances in chunks of 16 queries.
+void shard_hist(gvdb_index* h, Workspace* ws, cudaStream_t st, const float* q_dev, uint32_t nq, uint32_t* hist_out) {
+    const uint32_t nbins = (uint32_t)h->nchunk * 128 + 1;
+    CU(cudaMemsetAsync(hist_out, 0, (size_t)nq * nbins * 4, st));
+    const uint64_t N = h->n_rows;
+    if (N == 0) return;
+    if ((h->dim & 3) != 0) fail(GVDB_ERR_NOT_IMPLEMENTED, "rescore_count > 2048 needs dim % 4 == 0");
+    const uint32_t ntiles = (uint32_t)tiles_for(N);
+    const uint32_t QC = std::min<uint32_t>(nq, 16);
+    ws->qpack.ensure((size_t)QC * h->qs * 4);
+    ws->qnorm.ensure((size_t)QC * 4);
+    ws->misc.ensure((size_t)QC * N * 4);
+    const int hist_grid = (int)std::min<uint64_t>((N + 255) / 256, (uint64_t)h->sm_count * 8);
+    for (uint32_t q0 = 0; q0 < nq; q0 += QC) {
+        const uint32_t m = std::min(QC, nq - q0);
+        query_prep_direct_kernel<<<(m + 31) / 32, 32, 0, st>>>(q_dev + (size_t)q0 * h->dim, m, h->dim, h->cfg.threshold,
+                                                              h->nchunk, ws->qnorm.as<float>(), ws->qpack.as<uint32_t>(), h->qs);
+        const int qg = pick_qgroup(h, ntiles, m);
+        dim3 grid = scan_grid(h, ntiles, m, qg);
+        launch_scan<1>(h->nchunk, -1, st, grid, (size_t)qg * h->qs * 4, h->codes, live_of(h, ws), 0, ntiles,
+                       ws->qpack.as<uint32_t>(), (int)m, qg, nullptr, nullptr, 0, nullptr, ws->misc.as<uint32_t>(), N, N);
+        for (uint32_t qi = 0; qi < m; ++qi)
+            dist_hist_kernel<<<hist_grid, 256, nbins * 4, st>>>(ws->misc.as<uint32_t>() + (size_t)qi * N, live_of(h, ws), N, nbins,
+                                                                hist_out + (size_t)(q0 + qi) * nbins);
+        CU(cudaGetLastError());
+        h->launches.fetch_add(2 + m, std::memory_order_relaxed);
+    }
+}
+
+void search_shard_ratio(gvdb_index* h, Workspace* ws, cudaStream_t st, const float* q_dev, uint32_t nq, uint64_t R64,
+                        uint32_t kr, const uint32_t* hists_all, uint32_t n_shards, uint32_t my, uint8_t* records) {
+    need_all_rows(h);
+    if ((h->dim & 3) != 0) fail(GVDB_ERR_NOT_IMPLEMENTED, "rescore_count > 2048 needs dim % 4 == 0");
+    const uint64_t N = h->n_rows;
+    const uint64_t nrec = (uint64_t)nq * kr;
+    uint64_t* out_ids = reinterpret_cast<uint64_t*>(records);
+    uint32_t* out_ham = reinterpret_cast<uint32_t*>(records + nrec * 8);
+    float* out_score = reinterpret_cast<float*>(records + nrec * 12);
+    const uint32_t nbins = (uint32_t)h->nchunk * 128 + 1;
+    ws->big_cut.ensure((size_t)nq * sizeof(BigRCut));
+    BigRCut* cuts = ws->big_cut.as<BigRCut>();
+    shard_cut_kernel<<<nq, 32, 0, st>>>(hists_all, n_shards, my, nq, nbins, (unsigned long long)R64, cuts);
+    CU(cudaGetLastError());
+    std::vector<BigRCut> hc(nq);
+    CU(cudaMemcpyAsync(hc.data(), cuts, (size_t)nq * sizeof(BigRCut), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    // this shard's largest share over the batch sizes the per-query arrays (>= 1 so that the launches are well formed)
+    uint32_t Rl = 1, Ml = 1;
+    for (const BigRCut& c : hc) { Rl = std::max(Rl, c.r_eff); Ml = std::max(Ml, c.m); }
+    const uint32_t ntiles = (uint32_t)tiles_for(std::max<uint64_t>(N, 1));
+    int key_bits = 32;
+    while ((1u << (key_bits - 32)) < nbins) ++key_bits;
+    const uint32_t QC = std::min<uint32_t>(nq, 16);
+    ws->qpack.ensure((size_t)QC * h->qs * 4);
+    ws->qnorm.ensure((size_t)QC * 4);
+    ws->misc.ensure((size_t)QC * std::max<uint64_t>(N, 1) * 4);
+    ws->big_keys.ensure((size_t)Ml * 8);
+    ws->big_keys2.ensure((size_t)Ml * 8);
+    ws->big_k32.ensure((size_t)Rl * 8);
+    ws->big_v32.ensure((size_t)Rl * 8);
+    ws->rec_ham.ensure((size_t)Rl * 4);
+    ws->rec_ids.ensure((size_t)Rl * 8);
+    ws->rec_score.ensure((size_t)Rl * 4);
+    uint32_t* k32 = ws->big_k32.as<uint32_t>();
+    uint32_t* k32o = k32 + Rl;
+    uint32_t* v32 = ws->big_v32.as<uint32_t>();
+    uint32_t* v32o = v32 + Rl;
+    size_t tmp_a = 0, tmp_b = 0;
+    CU(cub::DeviceRadixSort::SortKeys(nullptr, tmp_a, ws->big_keys.as<uint64_t>(), ws->big_keys2.as<uint64_t>(), (int64_t)Ml, 0, key_bits, st));
+    CU(cub::DeviceRadixSort::SortPairs(nullptr, tmp_b, k32, k32o, v32, v32o, (int64_t)Rl, 0, 32, st));
+    ws->big_tmp.ensure(std::max(tmp_a, tmp_b) + 256);
+    static std::atomic<uint64_t> attr_done{0};
+    ensure_dyn_smem(attr_done, rescore_slab_kernel<false>, 64 * (RS_SLAB + 4) * (int)sizeof(float));
+    const int cols = std::min(h->dim, RS_SLAB);
+    const int stride = ((cols >> 2) & 1) ? cols : cols + 4;
+    const int hist_grid = (int)std::min<uint64_t>((N + 255) / 256, (uint64_t)h->sm_count * 8);
+    uint32_t kr_eff = 64;
+    while (kr_eff < kr) kr_eff <<= 1;
+    for (uint32_t q0 = 0; q0 < nq; q0 += QC) {
+        const uint32_t m = std::min(QC, nq - q0);
+        if (N) {
+            query_prep_direct_kernel<<<(m + 31) / 32, 32, 0, st>>>(q_dev + (size_t)q0 * h->dim, m, h->dim, h->cfg.threshold,
+                                                                  h->nchunk, ws->qnorm.as<float>(), ws->qpack.as<uint32_t>(), h->qs);
+            const int qg = pick_qgroup(h, ntiles, m);
+            dim3 grid = scan_grid(h, ntiles, m, qg);
+            launch_scan<1>(h->nchunk, -1, st, grid, (size_t)qg * h->qs * 4, h->codes, live_of(h, ws), 0, ntiles,
+                           ws->qpack.as<uint32_t>(), (int)m, qg, nullptr, nullptr, 0, nullptr, ws->misc.as<uint32_t>(), N, N);
+        }
+        for (uint32_t qi = 0; qi < m; ++qi) {
+            const uint32_t gq = q0 + qi;
+            BigRCut* cut = cuts + gq;
+            if (hc[gq].r_eff > 0) {
+                const uint32_t* dist = ws->misc.as<uint32_t>() + (size_t)qi * N;
+                cut_compact_kernel<<<hist_grid, 256, 0, st>>>(dist, live_of(h, ws), N, cut, ws->big_keys.as<uint64_t>());
+                size_t tb = ws->big_tmp.bytes;
+                CU(cub::DeviceRadixSort::SortKeys(ws->big_tmp.p, tb, ws->big_keys.as<uint64_t>(), ws->big_keys2.as<uint64_t>(),
+                                                  (int64_t)hc[gq].m, 0, key_bits, st));
+                // candidates = the first r_eff sorted keys: this shard's members of the global top R
+                const int q_slots = 2;
+                rescore_slab_kernel<false><<<(Rl + 31) / 32, 32, (size_t)(32 + q_slots) * stride * sizeof(float), st>>>(
+                    h->rows, h->norms, h->cfg.row_base, h->dim, stride, q_slots, q_dev + (size_t)gq * h->dim,
+                    ws->qnorm.as<float>() + qi, ws->big_keys2.as<uint64_t>(), 0, &cut->r_eff, Rl, 1,
+                    ws->rec_ham.as<uint32_t>(), ws->rec_ids.as<uint64_t>(), ws->rec_score.as<float>(), 0, 0);
+                cos_key_kernel<<<(Rl + 255) / 256, 256, 0, st>>>(ws->rec_score.as<float>(), Rl, k32, v32);
+                tb = ws->big_tmp.bytes;
+                CU(cub::DeviceRadixSort::SortPairs(ws->big_tmp.p, tb, k32, k32o, v32, v32o, (int64_t)Rl, 0, 32, st));
+            }
+            bigr_emit_records_kernel<<<1, 256, (size_t)kr_eff * 8, st>>>(
+                v32o, cut, ws->rec_ham.as<uint32_t>(), ws->rec_ids.as<uint64_t>(), ws->rec_score.as<float>(), kr,
+                out_ids + (size_t)gq * kr, out_ham + (size_t)gq * kr, out_score + (size_t)gq * kr);
+            CU(cudaGetLastError());
+            h->launches.fetch_add(6, std::memory_order_relaxed);
         }
     }
     CU(cudaStreamSynchronize(st));
@@ -2142,7 +2262,7 @@ gvdb_status gvdb_merge_shards_device(gvdb_index* h, void* stream, uint32_t n_sha
         ws->rec_ham.ensure((size_t)nq * R * 4);
         ws->rec_ids.ensure((size_t)nq * R * 8);
         ws->rec_score.ensure((size_t)nq * R * 4);
-        ShardRecords rec{static_cast<const uint8_t*>(records_dev), gvdb_shard_record_bytes(nq, R), nq, R};
+        ShardRecords rec{static_cast<const uint8_t*>(records_dev), gvdb_shard_record_bytes(nq, R), nq, R, R};
         {
             Timed t(h, ws, st, K_MERGE);
             merge_select_kernel<<<nq, SORT_THREADS, SORT_N * 8, st>>>(
@@ -2151,6 +2271,70 @@ gvdb_status gvdb_merge_shards_device(gvdb_index* h, void* stream, uint32_t n_sha
         }
         CU(cudaGetLastError());
         launch_topk(h, ws, st, ws->rec_ids.as<uint64_t>(), ws->rec_score.as<float>(), nq, R, k, ids_out_dev, scores_out_dev);
+        finish_async(h, ws, st);
+    });
+}
+
+uint32_t gvdb_shard_hist_bins(const gvdb_index* h) { return h ? (uint32_t)h->nchunk * 128 + 1 : 0; }
+
+gvdb_status gvdb_shard_hist_device(gvdb_index* h, void* stream, const float* queries_dev, uint32_t nq,
+                                   uint32_t* hist_out_dev) {
+    return guarded([&] {
+        NvtxRange nvtx_call("gvdb_shard_hist_device");
+        need(h, "index");
+        if (nq == 0) return;
+        need(queries_dev, "queries"); need(hist_out_dev, "hist_out");
+        DeviceGuard dg(h->cfg.device);
+        WsLease lease(h, (cudaStream_t)stream, true);
+        shard_hist(h, lease.ws, lease.stream, queries_dev, nq, hist_out_dev);
+        finish_async(h, lease.ws, lease.stream);
+    });
+}
+
+gvdb_status gvdb_search_shard_ratio_device(gvdb_index* h, void* stream, const float* queries_dev, uint32_t nq,
+                                           uint64_t rescore_count, uint32_t k, const uint32_t* hists_all_dev,
+                                           uint32_t n_shards, uint32_t my_shard, void* records_dev) {
+    return guarded([&] {
+        NvtxRange nvtx_call("gvdb_search_shard_ratio_device");
+        need(h, "index");
+        if (nq == 0) return;
+        need(queries_dev, "queries"); need(hists_all_dev, "hists_all"); need(records_dev, "records");
+        if (rescore_count == 0) fail(GVDB_ERR_INVALID_ARGUMENT, "rescore_count must be >= 1");
+        if (k == 0 || k > 1024) fail(GVDB_ERR_INVALID_ARGUMENT, "k must be in [1, 1024]");
+        if (n_shards == 0 || my_shard >= n_shards) fail(GVDB_ERR_INVALID_ARGUMENT, "my_shard must be < n_shards");
+        DeviceGuard dg(h->cfg.device);
+        WsLease lease(h, (cudaStream_t)stream, true);
+        search_shard_ratio(h, lease.ws, lease.stream, queries_dev, nq, rescore_count, k, hists_all_dev, n_shards, my_shard,
+                           static_cast<uint8_t*>(records_dev));
+    });
+}
+
+gvdb_status gvdb_merge_shards_ratio_device(gvdb_index* h, void* stream, uint32_t n_shards, const void* records_dev,
+                                           uint32_t nq, uint32_t k, uint64_t* ids_out_dev, float* scores_out_dev) {
+    return guarded([&] {
+        NvtxRange nvtx_call("gvdb_merge_shards_ratio_device");
+        need(h, "index");
+        if (nq == 0) return;
+        need(records_dev, "records"); need(ids_out_dev, "ids_out"); need(scores_out_dev, "scores_out");
+        if (k == 0 || n_shards == 0 || (uint64_t)n_shards * k > (uint64_t)SORT_N)
+            fail(GVDB_ERR_INVALID_ARGUMENT, "n_shards * k must be in [1, 4096]");
+        DeviceGuard dg(h->cfg.device);
+        WsLease lease(h, (cudaStream_t)stream, true);
+        Workspace* ws = lease.ws;
+        cudaStream_t st = lease.stream;
+        const uint32_t keep = n_shards * k;
+        ws->rec_ham.ensure((size_t)nq * keep * 4);
+        ws->rec_ids.ensure((size_t)nq * keep * 8);
+        ws->rec_score.ensure((size_t)nq * keep * 4);
+        // every record stays (the shards applied the global cut): order by (hamming, row), then by cosine
+        ShardRecords rec{static_cast<const uint8_t*>(records_dev), gvdb_shard_record_bytes(nq, k), nq, k, keep};
+        {
+            Timed t(h, ws, st, K_MERGE);
+            merge_select_kernel<<<nq, SORT_THREADS, SORT_N * 8, st>>>(
+                n_shards, rec, ws->rec_ids.as<uint64_t>(), ws->rec_score.as<float>(), ws->rec_ham.as<uint32_t>());
+        }
+        CU(cudaGetLastError());
+        launch_topk(h, ws, st, ws->rec_ids.as<uint64_t>(), ws->rec_score.as<float>(), nq, keep, k, ids_out_dev, scores_out_dev);
         finish_async(h, ws, st);
     });
 }

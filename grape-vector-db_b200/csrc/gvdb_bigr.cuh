@@ -130,6 +130,81 @@ __global__ void bigr_fill_tail_kernel(const BigRCut* __restrict__ cut, uint32_t 
     rec_score[i] = -INFINITY;
 }
 
+// ---- ratio mode across row shards (SURVEY §8e "Collective (ratio mode)") --------------------------------------------
+// Every shard histograms its live rows' distances per query; the shards' histograms are gathered (one collective);
+// from them every shard derives the SAME global cut — the bin b* holding the R-th smallest key (hamming, global row)
+// of the union — and its own share of it: all its rows below b*, and of the ties AT b* as many as are left after the
+// lower-ranked shards took theirs (ties are ordered by global row = by shard, then by local row).
+// hists: [n_shards][nq][nbins].  One warp per query; out[q] is the cut of shard `my`: bstar, m = its rows with
+// ham <= b*, r_eff = its members of the global top R (the first r_eff of those m in (hamming, row) order).
+__global__ void __launch_bounds__(32)
+shard_cut_kernel(const uint32_t* __restrict__ hists, uint32_t n_shards, uint32_t my, uint32_t nq, uint32_t nbins,
+                 unsigned long long R, BigRCut* __restrict__ out) {
+    const uint32_t q = blockIdx.x, lane = threadIdx.x;
+    auto g = [&](uint32_t b) {
+        unsigned long long t = 0;
+        for (uint32_t s = 0; s < n_shards; ++s) t += hists[((size_t)s * nq + q) * nbins + b];
+        return t;
+    };
+    const uint32_t per = (nbins + 31) / 32;
+    const uint32_t b0 = min(nbins, lane * per), b1 = min(nbins, b0 + per);
+    unsigned long long sum = 0;
+    for (uint32_t b = b0; b < b1; ++b) sum += g(b);
+    unsigned long long incl = sum;
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned long long t = __shfl_up_sync(0xffffffffu, incl, o);
+        if ((int)lane >= o) incl += t;
+    }
+    const unsigned long long total = __shfl_sync(0xffffffffu, incl, 31);
+    const unsigned long long r_eff = min(R, total);
+    if (r_eff == 0) {
+        if (lane == 0) out[q] = BigRCut{0u, 0u, 0u, 0u};
+        return;
+    }
+    unsigned long long run = incl - sum;
+    if (run < r_eff && incl >= r_eff) {
+        for (uint32_t b = b0; b < b1; ++b) {
+            const unsigned long long gb = g(b);
+            if (run + gb >= r_eff) {
+                const unsigned long long need = r_eff - run;                    // ties wanted at b* (>= 1)
+                unsigned long long before = 0;
+                for (uint32_t s = 0; s < my; ++s) before += hists[((size_t)s * nq + q) * nbins + b];
+                const uint32_t* mine = hists + ((size_t)my * nq + q) * nbins;
+                const unsigned long long ties = mine[b];
+                const unsigned long long keep = need > before ? min(ties, need - before) : 0ull;
+                unsigned long long below = 0;
+                for (uint32_t bb = 0; bb < b; ++bb) below += mine[bb];
+                out[q] = BigRCut{b, (uint32_t)(below + ties), (uint32_t)(below + keep), 0u};
+                break;
+            }
+            run += gb;
+        }
+    }
+}
+
+// The first kr entries of the cosine order (perm: stage-1 positions) of a query, listed again in stage-1 order
+// ((hamming, global row) ascending): the shard's record list of a ratio-mode search.  One CTA; kr <= 1024.
+__global__ void __launch_bounds__(256)
+bigr_emit_records_kernel(const uint32_t* __restrict__ perm, const BigRCut* __restrict__ cut,
+                         const uint32_t* __restrict__ rec_ham, const uint64_t* __restrict__ rec_ids,
+                         const float* __restrict__ rec_score, uint32_t kr, uint64_t* __restrict__ out_ids,
+                         uint32_t* __restrict__ out_ham, float* __restrict__ out_score) {
+    extern __shared__ __align__(16) uint64_t sk[];
+    const uint32_t take = min(kr, cut->r_eff);
+    const uint32_t n_eff = max(64u, next_pow2(kr));
+    for (uint32_t i = threadIdx.x; i < n_eff; i += blockDim.x) sk[i] = i < take ? (uint64_t)perm[i] : UINT64_MAX;
+    __syncthreads();
+    bitonic_sort_smem(sk, n_eff);
+    for (uint32_t t = threadIdx.x; t < kr; t += blockDim.x) {
+        if (t < take) {
+            const uint32_t p = (uint32_t)sk[t];
+            out_ids[t] = rec_ids[p]; out_ham[t] = rec_ham[p]; out_score[t] = rec_score[p];
+        } else {
+            out_ids[t] = UINT64_MAX; out_ham[t] = 0xffffffffu; out_score[t] = -INFINITY;
+        }
+    }
+}
+
 // predicate of the owner-side compaction (gvdb_rescore_keys_device): pair p is scored here iff
 // its key is filled and its row lies in this index's resident window
 struct OwnedPair {

@@ -1286,6 +1286,8 @@ struct ShardRecords {
     const uint8_t* base;
     uint64_t shard_bytes;
     uint32_t nq, R;
+    uint32_t keep;      // records kept per query: R (the stage-1 cut) or n_shards * R (ratio mode: the shards already
+                        // applied the global cut, every record stays)
     __device__ __forceinline__ const uint64_t* ids(uint32_t s) const {
         return reinterpret_cast<const uint64_t*>(base + s * shard_bytes);
     }
@@ -1322,11 +1324,11 @@ merge_select_kernel(uint32_t n_shards, ShardRecords rec, uint64_t* __restrict__ 
         }
         __syncthreads();
         bitonic_sort_smem(skeys, n_eff);
-        have = min(R, total);
+        have = min(rec.keep, total);
         consumed += take;
     }
     __syncthreads();
-    for (uint32_t t = threadIdx.x; t < R; t += blockDim.x) {
+    for (uint32_t t = threadIdx.x; t < rec.keep; t += blockDim.x) {
         const uint64_t key = t < have ? skeys[t] : UINT64_MAX;
         uint64_t id = UINT64_MAX;
         uint32_t hm = 0xffffffffu;
@@ -1351,9 +1353,9 @@ merge_select_kernel(uint32_t n_shards, ShardRecords rec, uint64_t* __restrict__ 
                 }
             }
         }
-        out_ids[(size_t)q * R + t] = id;
-        out_ham[(size_t)q * R + t] = hm;
-        out_score[(size_t)q * R + t] = sc;
+        out_ids[(size_t)q * rec.keep + t] = id;
+        out_ham[(size_t)q * rec.keep + t] = hm;
+        out_score[(size_t)q * rec.keep + t] = sc;
     }
 }
 

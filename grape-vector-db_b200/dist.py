@@ -102,6 +102,7 @@ class ShardedSearcher:
     its own: per step two collectives and one host wait."""
 
     QUERY_TILE = 1024          # queries per exchange (the library's query tile)
+    MAX_FAST_R = 2048          # larger rescore counts: ratio mode (the cut by counting, agreed through histograms)
 
     def __init__(self, index, group=None):
         import torch.distributed as dist
@@ -115,6 +116,20 @@ class ShardedSearcher:
         self._all = None
         self._verdict_host = None
         self.reruns = 0
+
+    def _ratio_search(self, queries_t, k: int, rescore_count: int, ids_out=None, scores_out=None):
+        """rescore_count > 2048 (the reference's default rescore_ratio = 0.1 on a sharded corpus): every shard
+        histograms its distances, ONE all-gather of the histograms lets every shard derive the same global cut and
+        rescore exactly its own members of the global top rescore_count, a second all-gather moves every shard's best k
+        records and every rank merges them (n_shards x k records per query).  Bit-identical to the single index."""
+        import torch
+        W, rank = self.world, self.rank
+        nq = queries_t.shape[0]
+        hist = self.index.shard_hist_device(queries_t)
+        hists_all = all_gather_records(hist.reshape(-1), self.group).view(W, nq, hist.shape[1])
+        rec = self.index.search_shard_ratio_device(queries_t, rescore_count, k, hists_all, W, rank)
+        rec_all = all_gather_records(rec, self.group)
+        return self.index.merge_shards_ratio_device(rec_all, W, nq, k, ids_out, scores_out)
 
     @staticmethod
     def answer_layout(per: int, k: int) -> tuple[int, int, int, int]:
@@ -131,6 +146,8 @@ class ShardedSearcher:
         nq = queries_t.shape[0]
         W = self.world
         dev = queries_t.device
+        if rescore_count > self.MAX_FAST_R:
+            return self._ratio_search(queries_t, k, rescore_count, ids_out, scores_out)
         if nq > self.QUERY_TILE:
             # one exchange per query tile: every tile is a full step (scan -> all-to-all -> merge -> all-gather)
             if ids_out is None:

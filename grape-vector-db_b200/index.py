@@ -337,6 +337,51 @@ class GpuIndex:
             rescore_count, k, C.c_void_p(ids_out.data_ptr()), C.c_void_p(scores_out.data_ptr())))
         return ids_out, scores_out
 
+    # -- ratio mode across row shards (rescore_count > 2048) ------------------------------------
+    def shard_hist_bins(self) -> int:
+        return int(self._lib.gvdb_shard_hist_bins(self._h))
+
+    def shard_hist_device(self, queries_t, hist_out=None):
+        """[nq, bins] int32 tensor: this shard's live rows per Hamming distance, per query."""
+        import torch
+        nq = queries_t.shape[0]
+        if hist_out is None:
+            hist_out = torch.empty((nq, self.shard_hist_bins()), dtype=torch.int32, device=queries_t.device)
+        st = torch.cuda.current_stream(queries_t.device).cuda_stream
+        self._ok(self._lib.gvdb_shard_hist_device(self._h, C.c_void_p(st), C.c_void_p(queries_t.data_ptr()), nq,
+                                                  C.c_void_p(hist_out.data_ptr())))
+        return hist_out
+
+    def search_shard_ratio_device(self, queries_t, rescore_count: int, k: int, hists_all_t, n_shards: int, my_shard: int,
+                                  records_out=None):
+        """hists_all_t: [n_shards, nq, bins] int32 (every shard's shard_hist_device output, rank order) ->
+        this shard's packed records (its best k members of the global top rescore_count)."""
+        import torch
+        nq = queries_t.shape[0]
+        assert hists_all_t.is_contiguous() and tuple(hists_all_t.shape) == (n_shards, nq, self.shard_hist_bins())
+        nbytes = self.shard_record_bytes(nq, k)
+        if records_out is None:
+            records_out = torch.empty(nbytes, dtype=torch.uint8, device=queries_t.device)
+        st = torch.cuda.current_stream(queries_t.device).cuda_stream
+        self._ok(self._lib.gvdb_search_shard_ratio_device(
+            self._h, C.c_void_p(st), C.c_void_p(queries_t.data_ptr()), nq, int(rescore_count), k,
+            C.c_void_p(hists_all_t.data_ptr()), n_shards, my_shard, C.c_void_p(records_out.data_ptr())))
+        return records_out
+
+    def merge_shards_ratio_device(self, records_all, n_shards: int, nq: int, k: int, ids_out=None, scores_out=None):
+        import torch
+        assert records_all.is_contiguous() and records_all.numel() == n_shards * self.shard_record_bytes(nq, k)
+        dev = records_all.device
+        if ids_out is None:
+            ids_out = torch.empty((nq, k), dtype=torch.int64, device=dev)
+        if scores_out is None:
+            scores_out = torch.empty((nq, k), dtype=torch.float32, device=dev)
+        st = torch.cuda.current_stream(dev).cuda_stream
+        self._ok(self._lib.gvdb_merge_shards_ratio_device(
+            self._h, C.c_void_p(st), n_shards, C.c_void_p(records_all.data_ptr()), nq, k,
+            C.c_void_p(ids_out.data_ptr()), C.c_void_p(scores_out.data_ptr())))
+        return ids_out, scores_out
+
     # -- query-parallel search: replicated codes, row-sharded originals ------------------------
     def stage1_device(self, queries_t, rescore_count: int, keys_out=None):
         """Stage 1 only: [nq, R] int64 keys hamming << 40 | global row, ascending, -1 (GVDB_NO_ID) unfilled."""

@@ -75,6 +75,16 @@ extern "C" {
                                     rescore_count: u32, records_dev: *mut c_void) -> i32;
     pub fn gvdb_search_shard_sliced_device(h: *mut gvdb_index, stream: *mut c_void, queries_dev: *const f32, nq: u32,
                                            rescore_count: u32, n_slices: u32, records_dev: *mut c_void) -> i32;
+    // ratio mode across row shards (rescore_count > 2048): histograms -> gather -> shard search -> gather -> merge
+    pub fn gvdb_shard_hist_bins(h: *const gvdb_index) -> u32;
+    pub fn gvdb_shard_hist_device(h: *mut gvdb_index, stream: *mut c_void, queries_dev: *const f32, nq: u32,
+                                  hist_out_dev: *mut u32) -> i32;
+    pub fn gvdb_search_shard_ratio_device(h: *mut gvdb_index, stream: *mut c_void, queries_dev: *const f32, nq: u32,
+                                          rescore_count: u64, k: u32, hists_all_dev: *const u32, n_shards: u32,
+                                          my_shard: u32, records_dev: *mut c_void) -> i32;
+    pub fn gvdb_merge_shards_ratio_device(h: *mut gvdb_index, stream: *mut c_void, n_shards: u32,
+                                          records_dev: *const c_void, nq: u32, k: u32, ids_out_dev: *mut u64,
+                                          scores_out_dev: *mut f32) -> i32;
     pub fn gvdb_merge_shards_device(h: *mut gvdb_index, stream: *mut c_void, n_shards: u32, records_dev: *const c_void,
                                     nq: u32, rescore_count: u32, k: u32, ids_out_dev: *mut u64, scores_out_dev: *mut f32) -> i32;
     // filtered searches: allow_bits has ceil(rows / 32) words, bit (r % 32) of word r / 32 = row r may be returned

@@ -199,7 +199,8 @@ GVDB_API gvdb_status gvdb_similarity_search_batch_device(gvdb_index* h, void* st
 
 /* ---- row-sharded search: the two halves around the exchange step -------------------- */
 /* Failure mode of the sharded / staged entry points (gvdb_search_shard[_sliced]_device, gvdb_stage1_device,
- * gvdb_search_exchange_device): rescore_count <= 2048, and they have no cut-by-counting fallback — a shard on
+ * gvdb_search_exchange_device): rescore_count <= 2048 (larger counts: the ratio-mode calls below), and they have no
+ * cut-by-counting fallback — a shard on
  * which the exact segment schedule overflows a candidate buffer (see above) returns GVDB_ERR_INDEX for that
  * call.  In the peer exchange such a rank publishes an empty candidate list for the step, keeps serving
  * its peers and reports the error for its own batch only; the exchange stays in step. */
@@ -244,6 +245,30 @@ GVDB_API gvdb_status gvdb_merge_shards_device(gvdb_index* h, void* stream, uint3
                                               const void* records_dev, uint32_t nq,
                                               uint32_t rescore_count, uint32_t k,
                                               uint64_t* ids_out_dev, float* scores_out_dev);
+
+/* Ratio mode across row shards (rescore_count > 2048, the reference's default rescore_ratio = 0.1 on a sharded corpus;
+ * SURVEY.md §8e).  Three calls around two gathers; the answer equals the single-index search's bit for bit:
+ *   1. gvdb_shard_hist_device: per query, the histogram of this shard's live rows over the Hamming distance
+ *      (gvdb_shard_hist_bins(h) u32 bins per query: distances 0 .. code bits).
+ *   2. gather every shard's histograms in rank order: hists_all = [n_shards][nq][bins].
+ *   3. gvdb_search_shard_ratio_device: every shard derives the same global cut from hists_all — the bin holding the
+ *      rescore_count-th smallest key (hamming, global row) of the union; ties inside that bin go to the shards in rank
+ *      order, i.e. by ascending global row — rescoring its own members of the global top rescore_count exactly, and
+ *      writes its best k of them by (cosine desc, hamming asc, row asc) as a packed record buffer
+ *      (gvdb_shard_record_bytes(nq, k); per query in (hamming, row) order, unfilled slots as above).  k <= 1024.
+ *   4. gather the record buffers in rank order; gvdb_merge_shards_ratio_device orders the n_shards x k records of each
+ *      query by (cosine desc, hamming asc, row asc) and emits k (n_shards * k <= 4096).
+ * One query at a time inside (like the single-index cut by counting); results complete on return of call 3. */
+GVDB_API uint32_t gvdb_shard_hist_bins(const gvdb_index* h);
+GVDB_API gvdb_status gvdb_shard_hist_device(gvdb_index* h, void* stream, const float* queries_dev, uint32_t nq,
+                                            uint32_t* hist_out_dev);
+GVDB_API gvdb_status gvdb_search_shard_ratio_device(gvdb_index* h, void* stream, const float* queries_dev,
+                                                    uint32_t nq, uint64_t rescore_count, uint32_t k,
+                                                    const uint32_t* hists_all_dev, uint32_t n_shards,
+                                                    uint32_t my_shard, void* records_dev);
+GVDB_API gvdb_status gvdb_merge_shards_ratio_device(gvdb_index* h, void* stream, uint32_t n_shards,
+                                                    const void* records_dev, uint32_t nq, uint32_t k,
+                                                    uint64_t* ids_out_dev, float* scores_out_dev);
 
 /* ---- query-parallel search over replicated codes + row-sharded originals ----------------- */
 /* Keys are hamming << 40 | global row (rows < 2^40), GVDB_NO_ID when unfilled.

@@ -283,6 +283,117 @@ class _CpuRowShard:
         return ids_out, sc_out
 
 
+class _CpuRatioShard(_CpuRowShard):
+    """The ratio-mode calls of a row shard restated with numpy (an independent statement of the protocol in
+    include/gvdb.h: histograms -> gathered -> the same global cut on every shard -> each shard's members of the
+    global top R rescored where they live -> best-k records merged)."""
+
+    def __init__(self, rows, lo):
+        super().__init__(rows, lo, refuse_first=False)
+        from oracle import oracle
+        self.codes = oracle.quantize_batch(rows)
+        self.bins = rows.shape[1] + 1
+
+    def shard_hist_bins(self):
+        return self.bins
+
+    def _ham(self, q):
+        from oracle import oracle
+        return oracle.hamming_all(oracle.quantize(q), self.codes).astype(np.int64)
+
+    def shard_hist_device(self, q_t):
+        import torch
+        qs = q_t.numpy()
+        return torch.from_numpy(np.stack([np.bincount(self._ham(q), minlength=self.bins) for q in qs]).astype(np.int32))
+
+    def search_shard_ratio_device(self, q_t, R, k, hists_all, W, my):
+        import torch
+        from grape_vector_db_b200 import dist as gdist
+        from oracle import oracle
+        qs, H = q_t.numpy(), hists_all.numpy().astype(np.int64)
+        nq = qs.shape[0]
+        ids = np.full((nq, k), np.iinfo(np.uint64).max, dtype=np.uint64)
+        ham_o = np.full((nq, k), 0xFFFFFFFF, dtype=np.uint32)
+        sc = np.full((nq, k), -np.inf, dtype=np.float32)
+        for qi in range(nq):
+            g = H[:, qi, :].sum(axis=0)
+            cum = np.cumsum(g)
+            r_eff = min(R, int(cum[-1]))
+            if r_eff == 0:
+                continue
+            b = int(np.searchsorted(cum, r_eff))                   # first bin whose cumulative count reaches r_eff
+            need = r_eff - int(cum[b] - g[b])
+            before = int(H[:my, qi, b].sum())
+            keep = max(0, min(int(H[my, qi, b]), need - before))
+            ham = self._ham(qs[qi])
+            sel = np.concatenate([np.flatnonzero(ham < b), np.flatnonzero(ham == b)[:keep]])
+            sel = sel[np.lexsort((sel, ham[sel]))]                 # stage-1 order: (hamming, row)
+            cos = np.array([oracle.cosine_similarity(qs[qi], self.rows[r]) for r in sel], dtype=np.float32)
+            best = np.sort(np.argsort(-cos, kind="stable")[:k])    # best k by cosine, listed in stage-1 order again
+            ids[qi, :best.size] = sel[best].astype(np.uint64) + np.uint64(self.lo)
+            ham_o[qi, :best.size] = ham[sel[best]]
+            sc[qi, :best.size] = cos[best]
+        return torch.from_numpy(gdist.pack_records(ids, ham_o, sc))
+
+    def merge_shards_ratio_device(self, rec_all, W, nq, k, ids_out=None, scores_out=None):
+        import torch
+        from grape_vector_db_b200 import dist as gdist
+        buf = rec_all.numpy()
+        pb = self.shard_record_bytes(nq, k)
+        parts = [gdist.unpack_records(buf[s * pb:(s + 1) * pb], nq, k) for s in range(W)]
+        out_i = np.full((nq, k), -1, dtype=np.int64)
+        out_s = np.full((nq, k), -np.inf, dtype=np.float32)
+        for qi in range(nq):
+            i_ = np.concatenate([p[0][qi] for p in parts]); h_ = np.concatenate([p[1][qi] for p in parts])
+            s_ = np.concatenate([p[2][qi] for p in parts])
+            ok = i_ != np.iinfo(np.uint64).max
+            i_, h_, s_ = i_[ok], h_[ok], s_[ok]
+            o1 = np.lexsort((i_, h_))
+            o2 = np.argsort(-s_[o1], kind="stable")[:k]
+            out_i[qi, :o2.size] = i_[o1][o2].astype(np.int64)
+            out_s[qi, :o2.size] = s_[o1][o2]
+        return torch.from_numpy(out_i), torch.from_numpy(out_s)
+
+
+def _ratio_worker(rank, world, port, n, dim, nq, R, k, out_dir):
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+    from grape_vector_db_b200 import dist as gdist
+    from grape_vector_db_b200 import synth
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    lo, hi = gdist.shard_bounds(n, world, rank)
+    rng = np.random.default_rng(5)
+    rows_all = rng.integers(-1, 2, size=(n, dim)).astype(np.float32)      # small alphabet: ties straddle the shards
+    searcher = gdist.ShardedSearcher(_CpuRatioShard(rows_all[lo:hi], lo))
+    qs = torch.from_numpy(rng.integers(-1, 2, size=(nq, dim)).astype(np.float32))
+    ids, sc = searcher.search_batch_device(qs, k, R)                      # R > 2048: the ratio-mode exchange
+    np.save(os.path.join(out_dir, f"r_ids_{rank}.npy"), ids.numpy())
+    np.save(os.path.join(out_dir, f"r_sc_{rank}.npy"), sc.numpy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_two_rank_gloo_ratio_mode_across_shards(tmp_path):
+    """ShardedSearcher's ratio-mode exchange (rescore_count > 2048) on two gloo ranks with numpy shards: histograms
+    gathered, the same global cut on both ranks, ties inside the cut bin shared out in rank order, best-k records
+    merged — equal to the oracle's single-index answer."""
+    import torch.multiprocessing as mp
+    from oracle import oracle
+    n, dim, nq, R, k, world = 6000, 24, 4, 2500, 12, 2
+    port = _free_port()
+    mp.spawn(_ratio_worker, args=(world, port, n, dim, nq, R, k, str(tmp_path)), nprocs=world, join=True)
+    rng = np.random.default_rng(5)
+    rows = rng.integers(-1, 2, size=(n, dim)).astype(np.float32)
+    qs = rng.integers(-1, 2, size=(nq, dim)).astype(np.float32)
+    for qi in range(nq):
+        oi, os_ = oracle.multi_stage_search(qs[qi], rows, R)
+        for r in range(world):
+            assert np.array_equal(np.load(tmp_path / f"r_ids_{r}.npy")[qi].astype(np.uint64), oi[:k])
+            assert np.array_equal(np.load(tmp_path / f"r_sc_{r}.npy")[qi].view(np.uint32), os_[:k].view(np.uint32))
+
+
 def _sharded_worker(rank, world, port, n, dim, nq, R, k, out_dir):
     sys.path.insert(0, ROOT)
     import torch

@@ -382,6 +382,61 @@ def test_tensor_core_search_path(gv, monkeypatch):
     assert np.array_equal(a[0], b[0]) and np.array_equal(_bits(a[1]), _bits(b[1]))
 
 
+@pytest.mark.parametrize("n_shards", [2, 3])
+def test_ratio_mode_across_row_shards_equals_single_index(gv, n_shards):
+    """rescore_count > 2048 on a row-sharded corpus (VERDICT r1 missing #2): per-shard histograms, the
+    global cut derived from the gathered histograms on every shard, each shard's members of the global top R rescored
+    where they live, best-k records merged.  Ids and score bits equal the single index's and the oracle's: low-rank
+    data, a 3-letter alphabet whose tie groups straddle the shards, tombstones, R above the live row count."""
+    import torch
+    from grape_vector_db_b200 import synth
+    from grape_vector_db_b200 import dist as gdist
+    dev = torch.device("cuda:0")
+
+    def run(rows, qs, R, k, dead=()):
+        n, dim = rows.shape
+        shards = []
+        for s_ in range(n_shards):
+            lo, hi = gdist.shard_bounds(n, n_shards, s_)
+            idx = gv.GpuIndex(dim, row_base=lo)
+            if hi > lo:
+                idx.add(rows[lo:hi])
+            for d in dead:
+                if lo <= d < hi:
+                    idx.remove(d - lo)
+            shards.append(idx)
+        q_t = torch.from_numpy(qs).to(dev)
+        nq = qs.shape[0]
+        hists = torch.stack([sh.shard_hist_device(q_t) for sh in shards]).contiguous()
+        recs = torch.cat([sh.search_shard_ratio_device(q_t, R, k, hists, n_shards, s_) for s_, sh in enumerate(shards)])
+        ids, sc = shards[0].merge_shards_ratio_device(recs, n_shards, nq, k)
+        torch.cuda.synchronize()
+        ids, sc = ids.cpu().numpy().astype(np.uint64), sc.cpu().numpy()
+        for sh in shards:
+            sh.close()
+        live = np.ones(n, dtype=bool)
+        live[list(dead)] = False
+        kept = np.flatnonzero(live)
+        for qi in range(nq):
+            oi, os_ = oracle.multi_stage_search(qs[qi], rows[live], R)
+            r = min(k, len(oi))
+            assert np.array_equal(ids[qi, :r], kept[oi[:r].astype(np.int64)].astype(np.uint64)), (qi, R, k)
+            assert np.array_equal(_bits(sc[qi, :r]), _bits(os_[:r])), (qi, R, k)
+            assert np.all(ids[qi, r:] == gv.NO_ID) and np.all(np.isneginf(sc[qi, r:]))
+
+    rows = synth.lowrank_rows(0, 30_000, 128)
+    qs = synth.lowrank_queries(0, 5, 128)
+    run(rows, qs, 3000, 10)
+    run(rows, qs[:2], 3000, 300, dead=tuple(range(1, 30_000, 7)))
+    rng = np.random.default_rng(11)
+    rows2 = rng.integers(-1, 2, size=(20_000, 24)).astype(np.float32)       # 24-bit codes: huge tie groups
+    qs2 = rng.integers(-1, 2, size=(4, 24)).astype(np.float32)
+    run(rows2, qs2, 2500, 50)
+    run(rows2, qs2[:2], 7001, 17, dead=(0, 1, 2, 9_999, 19_999))
+    rows3 = synth.iid_rows(0, 2500, 64)
+    run(rows3, synth.iid_queries(0, 3, 64), 5000, 100)                      # R above the live row count
+
+
 def test_save_load_round_trip(gv, tmp_path):
     """gvdb_save / gvdb_load: the file holds the reference-layout code bytes,
     norms, tombstones and rows; a loaded shard answers bit-identically without re-quantising."""
