@@ -513,7 +513,11 @@ void launch_tc_scan(gvdb_index* h, Workspace* ws, cudaStream_t st, uint32_t tile
     CU(cudaGetLastError());
     if (MODE == 0) {
         Timed t(h, ws, st, K_SCATTER);
-        launch_pdl(tc_scatter_kernel, dim3(TC_SCATTER_X, nlists), dim3(256), 0, st,
+        // CTAs per list: enough threads for the survivors a list is expected to hold (a second CTA on a list of
+        // ~170 records only adds a wave of blocks that find nothing to do)
+        const uint64_t per_list = ((uint64_t)nq * std::max<uint32_t>(expect_per_query, 1) + nlists - 1) / nlists;
+        const unsigned sx = (unsigned)std::min<uint64_t>(8, std::max<uint64_t>(1, (per_list + 255) / 256));
+        launch_pdl(tc_scatter_kernel, dim3(sx, nlists), dim3(256), 0, st,
                    recs, rec_cap, lc, h->codes, h->nchunk, ws->qpack.as<uint32_t>(), h->qs, cnt, buf, cap, overflow);
         CU(cudaGetLastError());
     }

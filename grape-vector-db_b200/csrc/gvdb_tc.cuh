@@ -942,9 +942,19 @@ tc_scatter_kernel(const uint2* __restrict__ recs, uint32_t rec_cap, const uint32
         const uint4* rc = codes + ((size_t)(row >> 5) * nchunk) * 32 + (row & 31);
         const uint4* qc = reinterpret_cast<const uint4*>(qpack + (size_t)q * qs);
         uint32_t d = 0;
-        for (int c = 0; c < nchunk; ++c) {
-            const uint4 a = rc[c * 32], b = qc[c];
-            d += __popc(a.x ^ b.x) + __popc(a.y ^ b.y) + __popc(a.z ^ b.z) + __popc(a.w ^ b.w);
+        // six chunk pairs in flight (a loop over the runtime chunk count issued one L2 round trip after the other:
+        // 88 % of this kernel's samples waited on them)
+        for (int c0 = 0; c0 < nchunk; c0 += 6) {
+            uint4 a[6], b[6];
+#pragma unroll
+            for (int u = 0; u < 6; ++u) {
+                const bool in = c0 + u < nchunk;
+                a[u] = in ? __ldg(rc + (c0 + u) * 32) : make_uint4(0, 0, 0, 0);
+                b[u] = in ? __ldg(qc + c0 + u) : make_uint4(0, 0, 0, 0);
+            }
+#pragma unroll
+            for (int u = 0; u < 6; ++u)
+                d += __popc(a[u].x ^ b[u].x) + __popc(a[u].y ^ b[u].y) + __popc(a[u].z ^ b[u].z) + __popc(a[u].w ^ b[u].w);
         }
         const uint32_t pos = atomicAdd(&cnt[(size_t)q * CNT_STRIDE], 1u);
         if (pos < cap) buf[(size_t)q * cap + pos] = ((uint64_t)d << 32) | row;
