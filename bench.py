@@ -719,7 +719,25 @@ def run_ours(args, rank, world, local_rank):
     if world == 1:
         # recall@10 against the exact f32 flat search (GPU, bit-exact FaissVectorIndex semantics)
         nr = min(args.recall_queries, B)
-        fid, _ = index.flat_search_batch_device(q_dev[last_batch][:nr].contiguous(), k)
+        q_flat = q_dev[last_batch][:nr].contiguous()
+        fid, _ = index.flat_search_batch_device(q_flat, k)
+        if nr > 0:
+            # the exact flat search itself (FaissVectorIndex::search, src/index.rs:620-640), timed: f32 multiply and add
+            # kept separate (no FMA: bit-exact folds), so its bound is the FP32 issue rate, 2 instructions per element
+            torch.cuda.synchronize()
+            f0_, f1_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            f0_.record()
+            for _ in range(3):
+                index.flat_search_batch_device(q_flat, k)
+            f1_.record(); torch.cuda.synchronize()
+            fms = f0_.elapsed_time(f1_) / 3
+            sm_count = torch.cuda.get_device_properties(dev).multi_processor_count
+            peak_ops = sm_count * 128 * (clk.get("sm_mhz") or 1965.0) * 1e6
+            ops = 2.0 * n * nr * dim
+            extra["flat_exact"] = {"queries": nr, "ms_per_batch": fms, "qps": nr / (fms * 1e-3),
+                                   "f32_ops_per_s": ops / (fms * 1e-3), "fp32_issue_peak_ops_per_s": peak_ops,
+                                   "frac_of_fp32_issue_peak": ops / (fms * 1e-3) / peak_ops,
+                                   "note": "rows x queries x dim x (FMUL + FADD), no FMA; peak = SMs x 128 lanes x SM clock"}
         fid = fid.cpu().numpy().astype(np.uint64)
         extra["recall_at_10"] = float(np.mean([len(set(last_ids[i]) & set(fid[i])) / k for i in range(nr)]))
         extra["recall_queries"] = nr

@@ -140,6 +140,7 @@ struct Exchange {
     DevBuf my_keys, err, done;             // done: one block counter per signal kind (128 bytes apart)
     uint32_t* h_err = nullptr;             // pinned copy of err, refreshed at the end of every step
     bool broken = false;                   // a step failed on the host after its epoch began: peers are out of step
+    bool dma_queries = true;               // GVDB_XCHG_DMA=0: queries pushed by a kernel instead of the copy engines
     std::mutex mu;                         // steps of one rank are issued one at a time
     ~Exchange() {                          // the device of the owning index is current (gvdb_destroy / create)
         for (void* p : opened) cudaIpcCloseMemHandle(p);
@@ -2569,6 +2570,7 @@ gvdb_status gvdb_exchange_create(gvdb_index* h, uint32_t world, uint32_t rank, u
         x->flags_off = 2 * x->set_bytes;
         x->mailbox_bytes = x->flags_off + (size_t)XCHG_KINDS * world * XCHG_FLAG_STRIDE * 4;
         if (const char* e = getenv("GVDB_XCHG_TIMEOUT_MS")) x->limit_ns = (uint64_t)std::max(1, atoi(e)) * 1000000ull;
+        if (const char* e = getenv("GVDB_XCHG_DMA")) x->dma_queries = e[0] == '1';
         // plain cudaMalloc (not a pool allocation): the block is exported with cudaIpcGetMemHandle
         CU(cudaMalloc((void**)&x->mailbox, x->mailbox_bytes));
         CU(cudaMemset(x->mailbox, 0, x->mailbox_bytes));
@@ -2696,7 +2698,18 @@ gvdb_status gvdb_search_exchange_device(gvdb_index* h, void* stream, const float
         // my queries to every owner, on the side stream, under stage 1
         CU(cudaEventRecord(x->fork, st));
         CU(cudaStreamWaitEvent(x->side, x->fork, 0));
-        xchg_push(h, ws, x->side, x, set_off + x->q_off + x->rank * q_bytes, queries_dev, 0, q_bytes, XCHG_Q);
+        if (x->dma_queries) {
+            // the queries (the big message: nq x dim x 4 bytes to every peer) go by the copy engines, so that the push
+            // takes no SM from query prep and the sample pass running beside it; the flag follows in stream order
+            Timed t(h, ws, x->side, K_XCHG);
+            for (uint32_t w = 0; w < x->world; ++w)
+                CU(cudaMemcpyAsync(x->peers[w] + set_off + x->q_off + x->rank * q_bytes, queries_dev, q_bytes,
+                                   cudaMemcpyDeviceToDevice, x->side));
+            xchg_signal_kernel<<<1, 32, 0, x->side>>>(x->peers_dev, x->flags_off, XCHG_Q, x->world, x->rank, x->epoch);
+            CU(cudaGetLastError());
+        } else {
+            xchg_push(h, ws, x->side, x, set_off + x->q_off + x->rank * q_bytes, queries_dev, 0, q_bytes, XCHG_Q);
+        }
         CU(cudaEventRecord(x->join, x->side));
         // stage 1 on my batch
         uint64_t* my_keys = x->my_keys.as<uint64_t>();
