@@ -99,7 +99,7 @@ class ShardedSearcher:
     final order) and ONE all-gather makes the top-k lists complete on every rank.  The gathered
     message carries, behind each rank's k-lists, the verdict of that rank's single scan pass, so
     the ranks agree on a (rare) repeat of the step without a collective or a host round trip of
-    its own: per step two collectives and one host wait."""
+    its own: per query tile two collectives, and ONE host wait per batch however many tiles it has."""
 
     QUERY_TILE = 1024          # queries per exchange (the library's query tile)
     MAX_FAST_R = 2048          # larger rescore counts: ratio mode (the cut by counting, agreed through histograms)
@@ -111,9 +111,7 @@ class ShardedSearcher:
         self.distributed = dist.is_available() and dist.is_initialized()
         self.world = dist.get_world_size(group) if self.distributed else 1
         self.rank = dist.get_rank(group) if self.distributed else 0
-        self._send = None
-        self._mine = None
-        self._all = None
+        self._tiles = []
         self._verdict_host = None
         self.reruns = 0
 
@@ -138,8 +136,26 @@ class ShardedSearcher:
         lk = per * k
         return 0, lk * 8, lk * 12, (lk * 12 + 8 + 15) // 16 * 16
 
+    class _TileBufs:
+        """Exchange buffers of one query tile (kept across calls: the collectives write into them)."""
+
+        def __init__(self, torch, dev, W, nbytes, stride):
+            self.send = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            self.mine = torch.zeros(stride, dtype=torch.uint8, device=dev)
+            self.all = torch.empty(W * stride, dtype=torch.uint8, device=dev)
+
+    def _bufs(self, torch, dev, n_tiles, nbytes, stride):
+        sets = self.__dict__.setdefault("_bufsets", {})
+        lst = sets.setdefault((str(dev), nbytes, stride), [])
+        while len(lst) < n_tiles:
+            lst.append(self._TileBufs(torch, dev, self.world, nbytes, stride))
+        return lst[:n_tiles]
+
     def search_batch_device(self, queries_t, k: int, rescore_count: int, ids_out=None,
                             scores_out=None):
+        """Tiles of QUERY_TILE queries; EVERY tile's step (scan -> all-to-all -> merge -> all-gather) is enqueued
+        before the host waits once for the whole batch and reads every rank's verdict for every tile; a tile whose
+        pass some rank refused (rare) is repeated synchronously on every rank."""
         import torch
         if self.world == 1:
             return self.index.search_batch_device(queries_t, k, rescore_count, ids_out, scores_out)
@@ -148,65 +164,79 @@ class ShardedSearcher:
         dev = queries_t.device
         if rescore_count > self.MAX_FAST_R:
             return self._ratio_search(queries_t, k, rescore_count, ids_out, scores_out)
-        if nq > self.QUERY_TILE:
-            # one exchange per query tile: every tile is a full step (scan -> all-to-all -> merge -> all-gather)
-            if ids_out is None:
-                ids_out = torch.empty((nq, k), dtype=torch.int64, device=dev)
-                scores_out = torch.empty((nq, k), dtype=torch.float32, device=dev)
-            for q0 in range(0, nq, self.QUERY_TILE):
-                q1 = min(nq, q0 + self.QUERY_TILE)
-                self.search_batch_device(queries_t[q0:q1], k, rescore_count, ids_out[q0:q1], scores_out[q0:q1])
-            return ids_out, scores_out
-        pad = (-nq) % W
-        if pad:   # equal slices: repeat the last query, drop its answers below
-            queries_t = torch.cat([queries_t, queries_t[-1:].expand(pad, -1)]).contiguous()
-        nqp = nq + pad
-        per = nqp // W
-        lk = per * k
-        o_ids, o_sc, o_vd, stride = self.answer_layout(per, k)
-        nbytes = W * self.index.shard_record_bytes(per, rescore_count)
-        if self._send is None or self._send.numel() != nbytes or self._send.device != dev:
-            self._send = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-        if self._mine is None or self._mine.numel() != stride or self._mine.device != dev:
-            self._mine = torch.zeros(stride, dtype=torch.uint8, device=dev)
-            self._all = torch.empty(W * stride, dtype=torch.uint8, device=dev)
-            self._verdict_host = torch.zeros((W, 8), dtype=torch.uint8)
-            if dev.type == "cuda":
-                self._verdict_host = self._verdict_host.pin_memory()
-        mine, allb = self._mine, self._all
-        my_ids = mine[o_ids:o_ids + lk * 8].view(torch.int64).view(per, k)
-        my_sc = mine[o_sc:o_sc + lk * 4].view(torch.float32).view(per, k)
-        my_vd = mine[o_vd:o_vd + 8]
-        # the whole step is enqueued before the host waits: scan -> all-to-all -> merge -> all-gather -> verdicts
-        # to pinned memory, then ONE synchronisation (the step is repeated synchronously if any rank's pass was refused)
-        enq = self.index.search_shard_sliced_enqueue_device(queries_t, rescore_count, W, self._send, my_vd)
-        for attempt in range(2):
-            if not enq or attempt == 1:
-                my_vd.zero_()
-                self.index.search_shard_sliced_device(queries_t, rescore_count, W, records_out=self._send)
-            recv = all_to_all_records(self._send, self.group)
-            self.index.merge_shards_device(recv, W, per, rescore_count, k, my_ids, my_sc)
-            gathered = all_gather_records(mine, self.group, out=allb).view(W, stride)
-            if not enq or attempt == 1:
-                break
-            self._verdict_host.copy_(gathered[:, o_vd:o_vd + 8], non_blocking=True)
-            if dev.type == "cuda":
-                torch.cuda.current_stream(dev).synchronize()
-            self.index.search_shard_verify(dev)            # the stream is idle: clears the index's pending state
-            if not bool(self._verdict_host.any()):
-                break
-            self.reruns += 1
         if ids_out is None:
             ids_out = torch.empty((nq, k), dtype=torch.int64, device=dev)
             scores_out = torch.empty((nq, k), dtype=torch.float32, device=dev)
-        all_ids = gathered[:, o_ids:o_ids + lk * 8].view(torch.int64)      # [W, per*k] (strided rows)
-        all_sc = gathered[:, o_sc:o_sc + lk * 4].view(torch.float32)
-        if pad == 0:
-            ids_out.view(W, lk).copy_(all_ids)
-            scores_out.view(W, lk).copy_(all_sc)
-        else:
-            ids_out.copy_(all_ids.reshape(nqp, k)[:nq])
-            scores_out.copy_(all_sc.reshape(nqp, k)[:nq])
+        T = self.QUERY_TILE
+        # equal slices inside every tile: the last tile is padded with copies of the last query (answers dropped)
+        tiles = []
+        for q0 in range(0, nq, T):
+            q1 = min(nq, q0 + T)
+            qt = queries_t[q0:q1]
+            pad = (-(q1 - q0)) % W
+            if pad:
+                qt = torch.cat([qt, qt[-1:].expand(pad, -1)]).contiguous()
+            tiles.append((q0, q1, qt))
+        # every tile has exchange buffers of its own (kept across calls), grouped by tile size
+        groups = {}
+        for t_i, (q0, q1, qt) in enumerate(tiles):
+            groups.setdefault(qt.shape[0], []).append(t_i)
+        plan = [None] * len(tiles)
+        for nqp, members in groups.items():
+            per = nqp // W
+            layout = self.answer_layout(per, k)
+            nbytes = W * self.index.shard_record_bytes(per, rescore_count)
+            bufs = self._bufs(torch, dev, len(members), nbytes, layout[3])
+            for b_, t_i in zip(bufs, members):
+                plan[t_i] = (per, layout, b_)
+        if self._verdict_host is None or self._verdict_host.shape[0] < len(tiles) or self._verdict_host.shape[1] != W:
+            self._verdict_host = torch.zeros((max(len(tiles), 16), W, 8), dtype=torch.uint8)
+            if dev.type == "cuda":
+                self._verdict_host = self._verdict_host.pin_memory()
+
+        def exchange(t_i, synchronous):
+            q0, q1, qt = tiles[t_i]
+            per, (o_ids, o_sc, o_vd, stride), b_ = plan[t_i]
+            lk = per * k
+            my_ids = b_.mine[o_ids:o_ids + lk * 8].view(torch.int64).view(per, k)
+            my_sc = b_.mine[o_sc:o_sc + lk * 4].view(torch.float32).view(per, k)
+            my_vd = b_.mine[o_vd:o_vd + 8]
+            enq = False
+            if not synchronous:
+                enq = self.index.search_shard_sliced_enqueue_device(qt, rescore_count, W, b_.send, my_vd)
+            if not enq:
+                my_vd.zero_()
+                self.index.search_shard_sliced_device(qt, rescore_count, W, records_out=b_.send)
+            recv = all_to_all_records(b_.send, self.group)
+            self.index.merge_shards_device(recv, W, per, rescore_count, k, my_ids, my_sc)
+            gathered = all_gather_records(b_.mine, self.group, out=b_.all).view(W, stride)
+            if enq:
+                self._verdict_host[t_i].copy_(gathered[:, o_vd:o_vd + 8], non_blocking=True)
+            return enq, gathered
+
+        def deliver(t_i, gathered):
+            q0, q1, qt = tiles[t_i]
+            per, (o_ids, o_sc, o_vd, stride), b_ = plan[t_i]
+            lk, n_t = per * k, q1 - q0
+            all_ids = gathered[:, o_ids:o_ids + lk * 8].view(torch.int64)      # [W, per*k] (strided rows)
+            all_sc = gathered[:, o_sc:o_sc + lk * 4].view(torch.float32)
+            if qt.shape[0] == n_t:
+                ids_out[q0:q1].view(W, lk).copy_(all_ids)
+                scores_out[q0:q1].view(W, lk).copy_(all_sc)
+            else:
+                ids_out[q0:q1].copy_(all_ids.reshape(qt.shape[0], k)[:n_t])
+                scores_out[q0:q1].copy_(all_sc.reshape(qt.shape[0], k)[:n_t])
+
+        state = [exchange(t_i, False) for t_i in range(len(tiles))]
+        if any(enq for enq, _ in state):
+            if dev.type == "cuda":
+                torch.cuda.current_stream(dev).synchronize()
+            self.index.search_shard_verify(dev)                    # the stream is idle: clears the index's pending state
+        for t_i, (enq, gathered) in enumerate(state):
+            if enq and bool(self._verdict_host[t_i].any()):
+                self.reruns += 1
+                _, gathered = exchange(t_i, True)
+            deliver(t_i, gathered)
         return ids_out, scores_out
 
 

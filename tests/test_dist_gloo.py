@@ -252,7 +252,7 @@ class _CpuRowShard:
 
     def search_shard_sliced_enqueue_device(self, q_t, R, W, send, verdict_out=None):
         self.enqueued += 1
-        if self.refuse and self.enqueued == 1:
+        if self.refuse and self.enqueued == 1:          # (a worker may re-arm this with enqueued = -1: the second enqueue)
             send.fill_(0x5A)
             verdict_out[4] = 1
         else:
@@ -409,6 +409,12 @@ def _sharded_worker(rank, world, port, n, dim, nq, R, k, out_dir):
     assert searcher.reruns == 1 and shard.synchronous == 1, (searcher.reruns, shard.synchronous)
     ids2, sc2 = searcher.search_batch_device(qs[:nq - 1], k, R)   # nq not a multiple of the world size; no rerun
     assert searcher.reruns == 1 and shard.synchronous == 1
+    # several tiles per batch (all enqueued before the one host wait), ragged tile sizes, a refusal in the middle
+    searcher.QUERY_TILE = 3
+    shard.refuse, shard.enqueued = (rank == 0), -1            # rank 0 refuses its SECOND enqueue of this batch (tile 1)
+    ids3, sc3 = searcher.search_batch_device(qs, k, R)
+    assert searcher.reruns == 2 and shard.synchronous == 2, (searcher.reruns, shard.synchronous)
+    assert torch.equal(ids3, ids1) and torch.equal(sc3.view(torch.int32), sc1.view(torch.int32))
     np.save(os.path.join(out_dir, f"a_ids_{rank}.npy"), ids1.numpy())
     np.save(os.path.join(out_dir, f"a_sc_{rank}.npy"), sc1.numpy())
     np.save(os.path.join(out_dir, f"b_ids_{rank}.npy"), ids2.numpy())
