@@ -2861,7 +2861,6 @@ namespace {
 // (asynchronous; the caller synchronises).  Holds s->mu.
 void bm25_core(gvdb_sparse* s, cudaStream_t st, uint32_t nq, const uint64_t* q_off, const uint32_t* q_terms,
                const float* q_tfs, uint32_t limit, uint64_t* doc_out_dev, float* score_out_dev) {
-    if (limit > (uint32_t)SORT_N) fail(GVDB_ERR_NOT_IMPLEMENTED, "BM25 limit > 4096 is not implemented");
     // the scratch buffers are shared by every call on this handle: a call on another stream waits for the last one
     if (s->used) CU(cudaStreamWaitEvent(st, s->idle, 0));
     struct Done { gvdb_sparse* s; cudaStream_t st; ~Done() { cudaEventRecord(s->idle, st); s->used = true; } } done{s, st};
@@ -2920,7 +2919,15 @@ void bm25_core(gvdb_sparse* s, cudaStream_t st, uint32_t nq, const uint64_t* q_o
     }
     const uint64_t stride = (s->n_docs + 3) / 4 * 4;               // accumulators per query: uint4-readable, padding stays "absent"
     const uint32_t QC = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(std::min<uint64_t>(nq, 64), (512ull << 20) / (stride * 4)));
-    const uint32_t key_cap = SORT_N;
+    // keys inside the cut: exactly min(limit, touched) per query; up to SORT_N they are ordered by a block bitonic sort,
+    // above that by a device radix sort, one query at a time
+    const uint32_t key_cap = std::max<uint32_t>(SORT_N, limit);
+    const bool big_limit = limit > (uint32_t)SORT_N;
+    size_t sort_tmp = 0;
+    if (big_limit) {
+        CU(cub::DeviceRadixSort::SortKeys(nullptr, sort_tmp, (const uint64_t*)nullptr, (uint64_t*)nullptr, (int64_t)key_cap, 0, 64, st));
+        s->seg_keys.ensure((size_t)key_cap * 8 + sort_tmp + 256);      // sorted keys of one query + the sort's scratch
+    }
     s->acc.ensure((size_t)QC * stride * 4);
     s->hist.ensure((size_t)QC * BM25_LEVEL_BINS * 4);
     s->cut.ensure((size_t)QC * sizeof(Bm25Cut));
@@ -2931,6 +2938,7 @@ void bm25_core(gvdb_sparse* s, cudaStream_t st, uint32_t nq, const uint64_t* q_o
         const uint32_t m = std::min(QC, nq - q0);
         CU(cudaMemsetAsync(s->acc.p, 0xFF, (size_t)m * stride * 4, st));
         CU(cudaMemsetAsync(s->cut.p, 0, (size_t)m * sizeof(Bm25Cut), st));
+        if (big_limit) CU(cudaMemsetAsync(s->keys.p, 0xFF, (size_t)m * key_cap * 8, st));
         for (uint32_t rank = 0; rank < max_terms; ++rank)
             bm25_accumulate_kernel<<<dim3(gx, m), 256, 0, st>>>(
                 s->post_off.as<uint64_t>(), s->post_doc.as<uint32_t>(), s->post_w.as<float>(),
@@ -2952,9 +2960,22 @@ void bm25_core(gvdb_sparse* s, cudaStream_t st, uint32_t nq, const uint64_t* q_o
                                              s->tie_counts.as<uint32_t>(), gx);
         bm25_compact_kernel<<<dim3(gx, m), 256, 0, st>>>(s->acc.as<uint32_t>(), stride, s->cut.as<Bm25Cut>(),
                                                         s->keys.as<uint64_t>(), key_cap);
-        bm25_topk_kernel<<<m, SORT_THREADS, SORT_N * 8, st>>>(s->keys.as<uint64_t>(), key_cap, s->cut.as<Bm25Cut>(),
-                                                             s->acc.as<uint32_t>(), stride, limit,
-                                                             doc_out_dev + (size_t)q0 * limit, score_out_dev + (size_t)q0 * limit);
+        if (!big_limit) {
+            bm25_topk_kernel<<<m, SORT_THREADS, SORT_N * 8, st>>>(s->keys.as<uint64_t>(), key_cap, s->cut.as<Bm25Cut>(),
+                                                                 s->acc.as<uint32_t>(), stride, limit,
+                                                                 doc_out_dev + (size_t)q0 * limit, score_out_dev + (size_t)q0 * limit);
+        } else {
+            // unwritten key slots must sort last: the compaction wrote min(limit, touched) keys, the rest is set here
+            uint64_t* sorted = s->seg_keys.as<uint64_t>();
+            void* tmp = s->seg_keys.as<uint8_t>() + (size_t)key_cap * 8;
+            for (uint32_t qi = 0; qi < m; ++qi) {
+                size_t tb = sort_tmp;
+                CU(cub::DeviceRadixSort::SortKeys(tmp, tb, s->keys.as<uint64_t>() + (size_t)qi * key_cap, sorted, (int64_t)key_cap, 0, 64, st));
+                bm25_emit_sorted_kernel<<<(limit + 255) / 256, 256, 0, st>>>(
+                    sorted, s->cut.as<Bm25Cut>() + qi, s->acc.as<uint32_t>() + (size_t)qi * stride, limit,
+                    doc_out_dev + (size_t)(q0 + qi) * limit, score_out_dev + (size_t)(q0 + qi) * limit);
+            }
+        }
         CU(cudaGetLastError());
     }
     s->launches += (uint64_t)((nq + QC - 1) / QC) * (max_terms + 10);

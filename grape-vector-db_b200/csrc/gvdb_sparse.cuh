@@ -787,6 +787,24 @@ bm25_merge_kernel(const uint64_t* __restrict__ seg_keys, uint32_t n_seg, uint32_
     }
 }
 
+// limits above the block bitonic capacity: the query's keys were sorted by a device radix sort; emit (doc, score)
+__global__ void __launch_bounds__(256)
+bm25_emit_sorted_kernel(const uint64_t* __restrict__ sorted_keys, const Bm25Cut* __restrict__ cut,
+                        const uint32_t* __restrict__ acc, uint32_t limit, uint64_t* __restrict__ doc_out,
+                        float* __restrict__ score_out) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= limit) return;
+    const uint32_t m = min(cut->present, limit);
+    if (t < m) {
+        const uint32_t doc = (uint32_t)sorted_keys[t];
+        doc_out[t] = doc;
+        score_out[t] = __uint_as_float(acc[doc]);
+    } else {
+        doc_out[t] = UINT64_MAX;
+        score_out[t] = -INFINITY;
+    }
+}
+
 __global__ void fill_f32_kernel(float* __restrict__ p, size_t n, float v) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) p[i] = v;

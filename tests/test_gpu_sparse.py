@@ -59,7 +59,7 @@ def test_bm25_massive_ties_and_small_limits(gv):
     post_doc = np.arange(n, dtype=np.uint32)
     post_tf = np.full(n, 0.25, dtype=np.float32)
     doc_len = np.ones(n, dtype=np.float32)
-    for limit in (1, 7, 4096):
+    for limit in (1, 7, 4096, 6000):          # 6000: above the block sort's capacity (device radix sort per query)
         _check(gv, post_off, post_doc, post_tf, doc_len, [([0], [1.0]), ([0, 0], [0.5, 0.25])], limit)
 
 
@@ -93,6 +93,7 @@ def test_bm25_both_paths_and_their_limits(gv, monkeypatch):
     _check(gv, *post, queries[:7], 1000)          # blocked, LP = 1024
     _check(gv, *post, queries, 50)                # a 70-term query sends the batch down the dense path
     _check(gv, *post, queries[:7], 1500)          # limit > 1024: dense
+    _check(gv, *post, queries[:3], 5000)          # limit > 4096: dense, ordered by a device radix sort
     _check(gv, *post, queries[:1], 200)           # one query: many segments of one block each
     monkeypatch.setenv("GVDB_BM25_DENSE", "1")
     _check(gv, *post, queries[:7], 200)           # the dense path on what the blocked path normally answers
