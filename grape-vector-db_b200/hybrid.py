@@ -72,11 +72,18 @@ def weighted_fusion_batch(dense, dense_scores, sparse, sparse_scores, text=None,
 
 
 class HybridSearcher:
-    """dense GpuIndex + GpuSparseIndex + RRF, all on one GPU."""
+    """dense GpuIndex + GpuSparseIndex + fusion, all on one GPU.
+    fusion: "rrf" (FusionStrategy::RRF { k }, the default), "linear" or "normalized" (FusionStrategy::Linear /
+    Normalized with `weights` = (dense, sparse, text), src/hybrid.rs:370-394): the weighted strategies fuse the
+    scores the two searches return (the dense list's second field as the index returns it — cosine for the
+    two-stage search, 1 - cosine for the exact flat search — and the BM25 scores)."""
 
-    def __init__(self, dense_index, sparse_index, rrf_k: float = 60.0, oversample: int = 4, exact_dense: bool = False):
+    def __init__(self, dense_index, sparse_index, rrf_k: float = 60.0, oversample: int = 4, exact_dense: bool = False,
+                 fusion: str = "rrf", weights=(0.7, 0.2, 0.1)):
+        assert fusion in ("rrf", "linear", "normalized")
         self.dense, self.sparse = dense_index, sparse_index
         self.k, self.oversample, self.exact_dense = rrf_k, oversample, exact_dense
+        self.fusion, self.weights = fusion, tuple(float(w) for w in weights)
         self._lib = _ffi.lib()
 
     def search_batch_device(self, dense_queries_t, sparse_queries, limit: int):
@@ -86,17 +93,25 @@ class HybridSearcher:
         dev = torch.device("cuda", self.dense.device)
         want = 2 * limit
         nq = dense_queries_t.shape[0] if dense_queries_t is not None else len(sparse_queries)
-        d_ids = s_ids = None
+        d_ids = s_ids = d_sc = s_sc = None
         if dense_queries_t is not None:
             if self.exact_dense:
-                d_ids, _ = self.dense.flat_search_batch_device(dense_queries_t, want)
+                d_ids, d_sc = self.dense.flat_search_batch_device(dense_queries_t, want)
             else:
-                d_ids, _ = self.dense.search_batch_device(dense_queries_t, want, want * self.oversample)
+                d_ids, d_sc = self.dense.search_batch_device(dense_queries_t, want, want * self.oversample)
         if sparse_queries is not None:
-            s_ids, _ = self.sparse.search_bm25_batch_device(sparse_queries, want)
+            s_ids, s_sc = self.sparse.search_bm25_batch_device(sparse_queries, want)
         ids = torch.empty((nq, limit), dtype=torch.int64, device=dev)
         sc = torch.empty((nq, limit), dtype=torch.float32, device=dev)
         st = torch.cuda.current_stream(dev).cuda_stream
+        p = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
+        if self.fusion != "rrf":
+            raise_for_status(self._lib.gvdb_weighted_fusion_batch_device(
+                self.dense.device, C.c_void_p(st), p(d_ids), p(d_sc), want if d_ids is not None else 0,
+                p(s_ids), p(s_sc), want if s_ids is not None else 0, None, None, 0, nq,
+                self.weights[0], self.weights[1], self.weights[2], 1 if self.fusion == "normalized" else 0, limit,
+                C.c_void_p(ids.data_ptr()), C.c_void_p(sc.data_ptr())), self._lib)
+            return ids, sc
         raise_for_status(self._lib.gvdb_rrf_fusion_batch_device(
             self.dense.device, C.c_void_p(st),
             C.c_void_p(d_ids.data_ptr()) if d_ids is not None else None, want if d_ids is not None else 0,

@@ -205,6 +205,16 @@ def test_hybrid_search_matches_oracle_composition(gv):
                 oi, os_ = oracle.rrf_fusion(od[q], ob, [], 60.0)
                 assert np.array_equal(ids[q], oi[:limit]), (exact, q)
                 assert np.array_equal(_bits(sc[q]), _bits(os_[:limit]))
+        # the weighted strategies fuse the scores the two searches return
+        od, osc = oracle.multi_stage_search_batch(qs, rows, want * 4, want, nthreads=8)
+        for fusion in ("linear", "normalized"):
+            hy = gv.HybridSearcher(dense, sparse, oversample=4, fusion=fusion, weights=(0.6, 0.3, 0.1))
+            ids, sc = hy.search_batch(qs, sq, limit)
+            for q in range(nq):
+                ob, obs = oracle.bm25_search(sq[q][0], sq[q][1], *post, want)
+                oi, os_ = oracle.weighted_fusion(od[q], osc[q], ob, obs, [], [], (0.6, 0.3, 0.1), fusion == "normalized")
+                assert np.array_equal(ids[q], oi[:limit]), (fusion, q)
+                assert np.array_equal(_bits(sc[q]), _bits(os_[:limit])), (fusion, q)
         # sparse-only and dense-only requests (the Option fields of HybridSearchRequest)
         hy = gv.HybridSearcher(dense, sparse)
         ids, _ = hy.search_batch(None, sq[:8], limit)
