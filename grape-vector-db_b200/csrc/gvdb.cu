@@ -712,9 +712,11 @@ void search_core(gvdb_index* h, Workspace* ws, cudaStream_t st, const float* que
                               (uint32_t)std::min<uint64_t>(cap, (uint64_t)sp.m * ((ntiles + 3) / 4) / sp.n_sgroups + 1));
             {
                 Timed t(h, ws, st, K_SELECT);
-                launch_pdl(select_hist_kernel, dim3(nqt), dim3(SELH_THREADS), selh_smem, st,
+                const uint32_t tie_cap = 1024;                     // a few hundred survivors per query: small CTAs, one wave
+                launch_pdl(select_hist_kernel, dim3(nqt), dim3(SELH_THREADS),
+                           (size_t)r_pow2 * 8 + (size_t)tie_cap * 8 + (size_t)nbins * 4, st,
                            ws->buf.as<uint64_t>(), cap, ws->cnt.as<uint32_t>(), R, r_pow2, nbins,
-                           ws->qpack.as<uint32_t>(), h->qs, h->nchunk * 4, 0u, 2, ws->flag.as<uint32_t>());
+                           ws->qpack.as<uint32_t>(), h->qs, h->nchunk * 4, 0u, 2, ws->flag.as<uint32_t>(), tie_cap);
             }
             CU(cudaGetLastError());
         } else {
@@ -756,7 +758,7 @@ void search_core(gvdb_index* h, Workspace* ws, cudaStream_t st, const float* que
                     Timed t(h, ws, st, K_SELECT);
                     select_hist_kernel<<<nqt, SELH_THREADS, selh_smem, st>>>(
                         ws->buf.as<uint64_t>(), cap, ws->cnt.as<uint32_t>(), R, r_pow2, nbins,
-                        ws->qpack.as<uint32_t>(), h->qs, h->nchunk * 4, 0u, 0, ws->flag.as<uint32_t>());
+                        ws->qpack.as<uint32_t>(), h->qs, h->nchunk * 4, 0u, 0, ws->flag.as<uint32_t>(), (uint32_t)SORT_N);
                 }
                 CU(cudaGetLastError());
                 lo = hi;

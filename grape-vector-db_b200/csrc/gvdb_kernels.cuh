@@ -466,12 +466,15 @@ __device__ __forceinline__ void select_set_tau(const uint64_t* sel, uint32_t hav
 __global__ void __launch_bounds__(SELH_THREADS)
 select_hist_kernel(uint64_t* __restrict__ buf, uint32_t cap, uint32_t* __restrict__ cnt, uint32_t R,
                    uint32_t r_pow2, uint32_t nbins, uint32_t* __restrict__ qpack, int qs, int tau_word,
-                   uint32_t opt_m, int verify, uint32_t* __restrict__ flags) {
+                   uint32_t opt_m, int verify, uint32_t* __restrict__ flags, uint32_t tie_cap) {
+    // tie_cap (a power of two in [256, SORT_N]): keys of the threshold bin that are ordered in shared memory; a larger
+    // tie set goes through the radix select.  The single-pass search expects a few hundred keys per query and asks for
+    // 1024: the CTA then needs 12 KB instead of 36 KB and all 1024 queries of a tile are resident at once.
     pdl_launch_dependents();
     pdl_wait();
     extern __shared__ __align__(16) uint64_t sel[];
     uint64_t* tie = sel + r_pow2;
-    uint32_t* hist = reinterpret_cast<uint32_t*>(tie + SORT_N);
+    uint32_t* hist = reinterpret_cast<uint32_t*>(tie + tie_cap);
     __shared__ uint32_t s_bstar, s_below, s_nsel, s_ntie, s_prefix, s_need;
     const uint32_t q = blockIdx.x;
     uint64_t* mine = buf + (size_t)q * cap;
@@ -517,7 +520,7 @@ select_hist_kernel(uint64_t* __restrict__ buf, uint32_t cap, uint32_t* __restric
     __syncthreads();
     const uint32_t bstar = s_bstar, below = s_below, need = s_need;
     const uint32_t ntie_all = hist[bstar];
-    const bool small_ties = ntie_all <= (uint32_t)SORT_N;
+    const bool small_ties = ntie_all <= tie_cap;
     for (uint32_t i = tid; i < n; i += SELH_THREADS) {
         const uint64_t key = mine[i];
         const uint32_t h = min((uint32_t)(key >> 32), nbins - 1);

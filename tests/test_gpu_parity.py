@@ -105,6 +105,17 @@ def test_iid_dataset_and_ties(gv):
     _check_two_stage(gv, rows, qs, 300, 17)
 
 
+def test_single_pass_with_heavy_ties(gv):
+    """>= 64 queries (the tensor-core single pass) on corpora whose Hamming distances tie by the hundred and by the
+    thousand: the cut's tie set is ordered in shared memory up to its capacity (1024 keys in the single pass) and
+    by the radix select above it; overflowing candidate buffers fall back to the exact schedules."""
+    rng = np.random.default_rng(17)
+    for n, dim, R in ((6000, 64, 64), (20_000, 24, 100), (30_000, 128, 40)):
+        rows = rng.integers(-1, 2, size=(n, dim)).astype(np.float32)
+        qs = rng.integers(-1, 2, size=(72, dim)).astype(np.float32)
+        _check_two_stage(gv, rows, qs, R, 10)
+
+
 def test_ratio_mode_large_rescore_count(gv):
     """The reference's default rescore_ratio = 0.1 on corpora where R > 2048 (quantization.rs:178-179):
     the cut-by-counting path.  Stage-1 list, ids and scores bit-exact; k = R (the reference returns
