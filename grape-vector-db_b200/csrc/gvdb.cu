@@ -627,10 +627,9 @@ struct FusedTopk {
 };
 bool rescore_topk_fits(const gvdb_index* h, uint32_t R);
 size_t rescore_topk_smem(int dim, uint32_t R) {
-    const uint32_t nwarps = (R + 31) / 32;
     uint32_t n_eff = 64;
     while (n_eff < R) n_eff <<= 1;
-    return ((size_t)dim + (size_t)nwarps * 2 * 32 * RT_STRIDE) * sizeof(float) + (size_t)n_eff * 8;
+    return ((size_t)dim + (size_t)R * 2 * RT_STRIDE) * sizeof(float) + (size_t)n_eff * 8;   // two slabs of R staged rows
 }
 
 bool rescore_topk_fits(const gvdb_index* h, uint32_t R) {

@@ -858,11 +858,13 @@ rescore_topk_kernel(const float* __restrict__ rows, const float* __restrict__ no
     pdl_wait();
     extern __shared__ __align__(16) float rt_smem[];         // query row | per warp: 2 slabs of 32 x RT_STRIDE | sort keys
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int nwarps = blockDim.x >> 5;
     const uint32_t q = blockIdx.x;
     float* s_q = rt_smem;
+    // every warp stages two slabs of ITS rows: 32, except the last warp of the CTA, which holds R - 32 (nwarps - 1)
+    // (R = 40: 8 rows — the CTA then needs 25 KB instead of 38 KB and all 1024 queries of a tile are resident at once)
+    const int rw = min(32, (int)R - warp * 32);
     float* s_rows = rt_smem + dim + (size_t)warp * 2 * 32 * RT_STRIDE;
-    uint64_t* skeys = reinterpret_cast<uint64_t*>(rt_smem + dim + (size_t)nwarps * 2 * 32 * RT_STRIDE);
+    uint64_t* skeys = reinterpret_cast<uint64_t*>(rt_smem + dim + (size_t)R * 2 * RT_STRIDE);
     __shared__ __align__(8) uint64_t s_bar[1 + 2 * (RT_MAX_R / 32)];
     const uint32_t bar_q = smem_u32(&s_bar[0]);
     const uint32_t bar0 = smem_u32(&s_bar[1 + 2 * warp]);
@@ -893,7 +895,7 @@ rescore_topk_kernel(const float* __restrict__ rows, const float* __restrict__ no
         const uint32_t bar = bar0 + 8u * (sl & 1);
         if (lane == 0) mbar_expect_tx(bar, n_valid * bytes);
         __syncwarp();
-        if (valid) tma_bulk_g2s(smem_u32(s_rows + ((size_t)(sl & 1) * 32 + lane) * RT_STRIDE), src + c0, bytes, bar);
+        if (valid) tma_bulk_g2s(smem_u32(s_rows + ((size_t)(sl & 1) * rw + lane) * RT_STRIDE), src + c0, bytes, bar);
     };
     float dot = 0.0f;
     if (n_valid) {
@@ -909,7 +911,7 @@ rescore_topk_kernel(const float* __restrict__ rows, const float* __restrict__ no
             while (!mbar_try_wait(bar0 + 8u * (sl & 1), (uint32_t)(sl >> 1) & 1u)) {}
             if (valid) {
                 const int nv = min(RT_SLAB, dim - sl * RT_SLAB) >> 2;
-                const float4* mine = reinterpret_cast<const float4*>(s_rows + ((size_t)(sl & 1) * 32 + lane) * RT_STRIDE);
+                const float4* mine = reinterpret_cast<const float4*>(s_rows + ((size_t)(sl & 1) * rw + lane) * RT_STRIDE);
                 const float4* myq = reinterpret_cast<const float4*>(s_q + sl * RT_SLAB);
 #pragma unroll 8
                 for (int v = 0; v < nv; ++v) {
