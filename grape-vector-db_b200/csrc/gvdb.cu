@@ -711,7 +711,9 @@ void search_core(gvdb_index* h, Workspace* ws, cudaStream_t st, const float* que
                               (uint32_t)std::min<uint64_t>(cap, (uint64_t)sp.m * ((ntiles + 3) / 4) / sp.n_sgroups + 1));
             {
                 Timed t(h, ws, st, K_SELECT);
-                const uint32_t tie_cap = 1024;                     // a few hundred survivors per query: small CTAs, one wave
+                // the tie area follows the survivors expected per query (a few hundred at R = 40: small CTAs, one wave)
+                uint32_t tie_cap = 1024;
+                while (tie_cap < (uint32_t)SORT_N && tie_cap < (uint64_t)sp.m * ((ntiles + 3) / 4) / sp.n_sgroups + 1) tie_cap <<= 1;
                 launch_pdl(select_hist_kernel, dim3(nqt), dim3(SELH_THREADS),
                            (size_t)r_pow2 * 8 + (size_t)tie_cap * 8 + (size_t)nbins * 4, st,
                            ws->buf.as<uint64_t>(), cap, ws->cnt.as<uint32_t>(), R, r_pow2, nbins,
