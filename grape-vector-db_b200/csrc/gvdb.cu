@@ -1663,10 +1663,38 @@ struct FileHeader {
     uint32_t version, dim;
     float threshold, rescore_ratio;
     uint64_t rows, live_rows, row_base;
-    uint32_t code_bytes, pad0;
-    uint8_t pad[8];
+    uint32_t code_bytes, flags;      // flags bit 0: `checksum` covers the four sections
+    uint64_t checksum;
 };
 static_assert(sizeof(FileHeader) == 64, "header is 64 bytes");
+constexpr uint32_t FILE_FLAG_CHECKSUM = 1u;
+
+// FNV-1a over the little-endian u64 words of the four sections' bytes (codes, norms, live, rows, in file order,
+// WITHOUT their zero padding, taken as one byte stream; the last partial word zero-extended), then over the
+// stream's length in bytes.  Documented in include/gvdb.h so that any reader of the file can check it.
+struct SectionHash {
+    uint64_t h = 0xcbf29ce484222325ull, total = 0;
+    uint8_t carry[8];
+    size_t nc = 0;
+    static constexpr uint64_t P = 0x100000001b3ull;
+    void update(const void* data, size_t n) {
+        const uint8_t* p = static_cast<const uint8_t*>(data);
+        total += n;
+        if (nc) {
+            while (n && nc < 8) { carry[nc++] = *p++; --n; }
+            if (nc < 8) return;
+            uint64_t w; memcpy(&w, carry, 8);
+            h = (h ^ w) * P; nc = 0;
+        }
+        for (; n >= 8; n -= 8, p += 8) { uint64_t w; memcpy(&w, p, 8); h = (h ^ w) * P; }
+        while (n) { carry[nc++] = *p++; --n; }
+    }
+    uint64_t digest() const {
+        uint64_t r = h;
+        if (nc) { uint64_t w = 0; memcpy(&w, carry, nc); r = (r ^ w) * P; }
+        return (r ^ total) * P;
+    }
+};
 uint64_t pad64(uint64_t n) { return (n + 63) / 64 * 64; }
 
 struct File {
@@ -1676,20 +1704,24 @@ struct File {
 };
 
 // device <-> file through a pinned staging buffer
-void dev_to_file(FILE* f, const void* dev, uint64_t bytes, uint64_t padded, void* stage, size_t stage_bytes) {
+void dev_to_file(FILE* f, const void* dev, uint64_t bytes, uint64_t padded, void* stage, size_t stage_bytes,
+                 SectionHash& hash) {
     for (uint64_t off = 0; off < bytes; off += stage_bytes) {
         const size_t m = (size_t)std::min<uint64_t>(stage_bytes, bytes - off);
         CU(cudaMemcpy(stage, static_cast<const uint8_t*>(dev) + off, m, cudaMemcpyDeviceToHost));
+        hash.update(stage, m);
         if (fwrite(stage, 1, m, f) != m) fail(GVDB_ERR_INDEX, "gvdb_save: short write");
     }
     static const uint8_t zeros[64] = {0};
     if (padded > bytes && fwrite(zeros, 1, (size_t)(padded - bytes), f) != padded - bytes)
         fail(GVDB_ERR_INDEX, "gvdb_save: short write");
 }
-void file_to_dev(FILE* f, void* dev, uint64_t bytes, uint64_t padded, void* stage, size_t stage_bytes) {
+void file_to_dev(FILE* f, void* dev, uint64_t bytes, uint64_t padded, void* stage, size_t stage_bytes,
+                 SectionHash& hash) {
     for (uint64_t off = 0; off < bytes; off += stage_bytes) {
         const size_t m = (size_t)std::min<uint64_t>(stage_bytes, bytes - off);
         if (fread(stage, 1, m, f) != m) fail(GVDB_ERR_INDEX, "gvdb_load: truncated file");
+        hash.update(stage, m);
         CU(cudaMemcpy(static_cast<uint8_t*>(dev) + off, stage, m, cudaMemcpyHostToDevice));
     }
     if (padded > bytes && fseek(f, (long)(padded - bytes), SEEK_CUR) != 0) fail(GVDB_ERR_INDEX, "gvdb_load: truncated file");
@@ -1714,7 +1746,9 @@ gvdb_status gvdb_save(gvdb_index* h, const char* path) {
         hd.threshold = h->cfg.threshold; hd.rescore_ratio = h->cfg.rescore_ratio;
         hd.rows = h->n_rows; hd.live_rows = h->n_live; hd.row_base = h->cfg.row_base;
         hd.code_bytes = (uint32_t)h->nbytes;
+        hd.flags = FILE_FLAG_CHECKSUM;          // the checksum itself is written once the sections are out
         if (fwrite(&hd, sizeof(hd), 1, file.f) != 1) fail(GVDB_ERR_INDEX, "gvdb_save: short write");
+        SectionHash hash;
         const size_t stage_bytes = 32u << 20;
         void* stage = nullptr;
         CU(cudaMallocHost(&stage, stage_bytes));
@@ -1728,7 +1762,7 @@ gvdb_status gvdb_save(gvdb_index* h, const char* path) {
                 const uint64_t m = std::min(chunk, N - i0);
                 unblock_codes_kernel<<<(unsigned)((m + 255) / 256), 256>>>(h->codes, h->nchunk, i0, m, h->nbytes, tmp.as<uint8_t>());
                 CU(cudaGetLastError());
-                dev_to_file(file.f, tmp.p, m * h->nbytes, m * h->nbytes, stage, stage_bytes);
+                dev_to_file(file.f, tmp.p, m * h->nbytes, m * h->nbytes, stage, stage_bytes, hash);
                 written += m * h->nbytes;
             }
             tmp.release();
@@ -1736,9 +1770,12 @@ gvdb_status gvdb_save(gvdb_index* h, const char* path) {
             const uint64_t padn = pad64(written) - written;
             if (padn && fwrite(zeros, 1, (size_t)padn, file.f) != padn) fail(GVDB_ERR_INDEX, "gvdb_save: short write");
         }
-        dev_to_file(file.f, h->norms, N * 4, pad64(N * 4), stage, stage_bytes);
-        dev_to_file(file.f, h->live, tiles_for(N) * 4, pad64(tiles_for(N) * 4), stage, stage_bytes);
-        dev_to_file(file.f, h->rows, N * (uint64_t)h->dim * 4, N * (uint64_t)h->dim * 4, stage, stage_bytes);
+        dev_to_file(file.f, h->norms, N * 4, pad64(N * 4), stage, stage_bytes, hash);
+        dev_to_file(file.f, h->live, tiles_for(N) * 4, pad64(tiles_for(N) * 4), stage, stage_bytes, hash);
+        dev_to_file(file.f, h->rows, N * (uint64_t)h->dim * 4, N * (uint64_t)h->dim * 4, stage, stage_bytes, hash);
+        hd.checksum = hash.digest();
+        if (fseek(file.f, 0, SEEK_SET) != 0 || fwrite(&hd, sizeof(hd), 1, file.f) != 1)
+            fail(GVDB_ERR_INDEX, "gvdb_save: cannot write the checksum");
         if (fflush(file.f) != 0 || fsync(fileno(file.f)) != 0) fail(GVDB_ERR_INDEX, "gvdb_save: flush failed");
         fclose(file.f); file.f = nullptr;
         if (::rename(tmp_path.c_str(), path) != 0) fail(GVDB_ERR_INDEX, std::string("gvdb_save: cannot rename onto ") + path);
@@ -1769,13 +1806,14 @@ gvdb_status gvdb_load(const char* path, int32_t device, gvdb_index** out) {
         void* stage = nullptr;
         CU(cudaMallocHost(&stage, stage_bytes));
         struct Free { void* p; ~Free() { cudaFreeHost(p); } } guard{stage};
+        SectionHash hash;
         if (N) {
             const uint64_t chunk = stage_bytes / (uint64_t)h->nbytes;
             DevBuf tmp; tmp.ensure(std::min(chunk, N) * h->nbytes);
             uint64_t readn = 0;
             for (uint64_t i0 = 0; i0 < N; i0 += chunk) {
                 const uint64_t m = std::min(chunk, N - i0);
-                file_to_dev(file.f, tmp.p, m * h->nbytes, m * h->nbytes, stage, stage_bytes);
+                file_to_dev(file.f, tmp.p, m * h->nbytes, m * h->nbytes, stage, stage_bytes, hash);
                 block_codes_kernel<<<(unsigned)((m + 255) / 256), 256>>>(tmp.as<uint8_t>(), h->nchunk, i0, m, h->nbytes, h->codes);
                 CU(cudaGetLastError());
                 CU(cudaDeviceSynchronize());
@@ -1784,10 +1822,13 @@ gvdb_status gvdb_load(const char* path, int32_t device, gvdb_index** out) {
             tmp.release();
             if (pad64(readn) > readn && fseek(file.f, (long)(pad64(readn) - readn), SEEK_CUR) != 0)
                 fail(GVDB_ERR_INDEX, "gvdb_load: truncated file");
-            file_to_dev(file.f, h->norms, N * 4, pad64(N * 4), stage, stage_bytes);
-            file_to_dev(file.f, h->live, tiles_for(N) * 4, pad64(tiles_for(N) * 4), stage, stage_bytes);
-            file_to_dev(file.f, h->rows, N * (uint64_t)h->dim * 4, N * (uint64_t)h->dim * 4, stage, stage_bytes);
+            file_to_dev(file.f, h->norms, N * 4, pad64(N * 4), stage, stage_bytes, hash);
+            file_to_dev(file.f, h->live, tiles_for(N) * 4, pad64(tiles_for(N) * 4), stage, stage_bytes, hash);
+            file_to_dev(file.f, h->rows, N * (uint64_t)h->dim * 4, N * (uint64_t)h->dim * 4, stage, stage_bytes, hash);
         }
+        // files written before the checksum existed carry flags = 0 and are taken as they are
+        if ((hd.flags & FILE_FLAG_CHECKSUM) && hash.digest() != hd.checksum)
+            fail(GVDB_ERR_INDEX, "gvdb_load: checksum mismatch (the file is corrupt or was cut short)");
         h->n_rows = N;
         // the bitmap is the truth: bits past the last row are cleared and the live count is taken from it
         uint64_t live_rows = 0;

@@ -141,7 +141,7 @@ bm25_hist_kernel(const uint32_t* __restrict__ acc, uint64_t acc_stride, uint32_t
             for (int e = 0; e < 4; ++e) {
                 bool ok = w[e] != BM25_ABSENT;
                 const uint32_t img = bm25_desc_image(w[e]);
-                if (LEVEL == 0) present += ok;
+                if constexpr (LEVEL == 0) present += ok;
                 else ok = ok && (img >> (shift + bits)) == prefix;
                 const uint32_t bin = ok ? (img >> shift) & ((1u << bits) - 1u) : 0xFFFFFFFFu;
                 if (__any_sync(0xffffffffu, ok)) {

@@ -114,12 +114,19 @@ GVDB_API gvdb_status gvdb_get_stats(const gvdb_index* h, gvdb_stats* out);
 /* ---- persistence ------------------------------------------------ */
 /* One flat little-endian file per shard, readable with mmap:
  *   [  0, 64)  header: "GVDBIDX1", u32 version = 1, u32 dim, f32 threshold, f32 rescore_ratio,
- *              u64 rows, u64 live rows, u64 row_base, u32 code bytes per row = ceil(dim/8), zero pad
+ *              u64 rows, u64 live rows, u64 row_base, u32 code bytes per row = ceil(dim/8),
+ *              u32 flags (bit 0: the checksum is present), u64 checksum
  *   codes      rows x ceil(dim/8) bytes, BinaryVector::to_bytes() layout (src/quantization.rs:54-56),
  *              padded to a multiple of 64 bytes
  *   norms      rows x f32 (sequential-fold L2 norms), padded to 64
  *   live       ceil(rows/32) x u32 bitmap (bit r of word t = row 32t + r; 0 = tombstone), padded to 64
  *   rows       rows x dim f32, row-major
+ * checksum = 64-bit FNV-1a taken over 8-byte little-endian WORDS instead of bytes: h = 0xcbf29ce484222325;
+ * for every u64 word w of the four sections' bytes (file order, without their padding, as one byte
+ * stream, the last partial word zero-extended) h = (h ^ w) * 0x100000001b3; finally h = (h ^ stream
+ * length in bytes) * 0x100000001b3.  gvdb_load refuses a file whose checksum does not match; a file
+ * with flags = 0 (written before the checksum existed) is loaded unchecked.  gvdb_save writes to
+ * `path`.tmp, fsyncs and renames, so a crash mid-save leaves the previous file intact.
  * The reference reserves a `quantized` sled tree but never writes it and re-inserts vectors one
  * at a time on restart (src/advanced_storage.rs:52-62,105-112; src/query.rs:282-409); loading
  * this file restores the shard without re-quantising. */

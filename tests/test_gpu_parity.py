@@ -494,7 +494,32 @@ def test_save_load_round_trip(gv, tmp_path):
         gv.GpuIndex.load(str(tmp_path / "bad_rows.gvdb"))
     pad64 = lambda x: (x + 63) // 64 * 64
     live_off = 64 + pad64(n * nb) + pad64(n * 4)
+    # the header's checksum (flags @52 bit 0, u64 @56) is the word-wise FNV-1a include/gvdb.h documents, restated here
+    nt = (n + 31) // 32
+    rows_off = live_off + pad64(nt * 4)
+    stream = np.concatenate([raw[64:64 + n * nb], raw[64 + pad64(n * nb):64 + pad64(n * nb) + n * 4],
+                             raw[live_off:live_off + nt * 4], raw[rows_off:rows_off + n * dim * 4]])
+    assert rows_off + n * dim * 4 == raw.size
+    words = np.frombuffer(stream.tobytes() + b"\0" * (-stream.size % 8), dtype="<u8").tolist()
+    hsh, P, M = 0xcbf29ce484222325, 0x100000001b3, (1 << 64) - 1
+    for w in words:
+        hsh = ((hsh ^ w) * P) & M
+    hsh = ((hsh ^ stream.size) * P) & M
+    assert int(np.frombuffer(raw[52:56].tobytes(), dtype="<u4")[0]) & 1
+    assert int(np.frombuffer(raw[56:64].tobytes(), dtype="<u8")[0]) == hsh
+    # one flipped bit anywhere in the sections is refused (a checksum in the header) ...
+    for name, off in (("codes", 64 + 1234), ("norms", 64 + pad64(n * nb) + 40), ("rows", rows_off + 100_001)):
+        bad = raw.copy(); bad[off] ^= 0x10
+        bad.tofile(tmp_path / f"flip_{name}.gvdb")
+        with pytest.raises(gv.VectorDbError, match="checksum"):
+            gv.GpuIndex.load(str(tmp_path / f"flip_{name}.gvdb"))
+    # ... as is a file cut short
+    raw[:raw.size - 4096].tofile(tmp_path / "short.gvdb")
+    with pytest.raises(gv.VectorDbError):
+        gv.GpuIndex.load(str(tmp_path / "short.gvdb"))
+    # a file from a writer without the checksum (flags = 0) is loaded unchecked, its stray bitmap bits cleared
     stray = raw.copy(); stray[live_off + (n // 32) * 4 + 3] |= 0x80          # bit 31 of the last word: row 9023 does not exist
+    stray[52:64] = 0
     stray.tofile(tmp_path / "stray.gvdb")
     with gv.GpuIndex.load(str(tmp_path / "stray.gvdb")) as idx3:
         assert len(idx3) == n - 4
