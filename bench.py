@@ -410,6 +410,12 @@ def run_north_star(args, rank, world, dev, gv, gdist, synth, torch, dist, barrie
         "e2e": {"value": B * K / e2e_s, "unit": UNIT, "h2d_bytes_per_step": B * dim * 4, "d2h_bytes_per_step": B * k * 12,
                 "how": "rank 0: pinned H2D of the batch (double-buffered on a copy stream: the next batch travels while this one is searched), NCCL broadcast, search, D2H of the k-lists every step"},
         "stage_ms_per_step_rank0": {x: prof[x] / K for x in stage_keys},
+        # rank 0's tensor-core scan launches of the profiled steps: algorithmic MACs (rows x queries x code bits) over
+        # their summed CUDA-event time; the caller sets `frac` against the FP4 MMA rate measured in this run
+        "tc_scan_rank0": ({"bound": "tensor", "achieved": 2.0 * prof["tc_macs"] / (prof["tc_ms"] * 1e-3) / 1e12,
+                           "unit": "TFLOP/s", "launches_per_step": prof["tc_launches"] / K,
+                           "ms_per_step": prof["tc_ms"] / K}
+                          if prof.get("tc_ms", 0) > 0 and prof.get("tc_macs", 0) > 0 else None),
         "optimistic_reruns": int(prof["optimistic_reruns"]) + int(getattr(searcher, "reruns", 0)),
         "build_s": build_s, "parity": parity,
         "l2": "256 MB L2 flush between timed steps",
@@ -861,6 +867,11 @@ def run_ours(args, rank, world, local_rank):
                                          n=args.ns4_rows_per_gpu * world, dim=args.dim, B=args.ns4_batch, scaling="weak",
                                          oversamples=(4, 8, 16), max_steps=5)
     if rank == 0:
+        for ns in (north_star, north_star4):      # the large launches of the north-star configs against the same FP4 peak
+            tc = ns.get("tc_scan_rank0") if ns else None
+            if tc and roofline.get("unit") == "TFLOP/s" and roofline.get("peak"):
+                tc["peak"] = roofline["peak"]
+                tc["frac"] = tc["achieved"] / roofline["peak"]
         if north_star is not None:
             extra["north_star_c2"] = north_star
         if north_star4 is not None:
