@@ -445,14 +445,17 @@ TcSplit tc_split(const gvdb_index* h, uint32_t ngroups, uint32_t nq_pad, bool sa
     if (h->tc_qb_force) qb_min = qb_max = std::min<uint32_t>(qb_max, h->tc_qb_force);   // GVDB_TC_QB (tuning)
     TcSplit best{1, 1, 1, 1};
     double best_cost = 1e300;
-    // makespan model: waves x (row groups per item) x (blocks per item + the per-group A expansion share)
+    // makespan model: waves x (row groups per item) x (blocks per item + the per-group A expansion share).
+    // The share (0.45 of a block's MMAs) is fitted to configs[1] on a B200 (tools/knob_sweep.sh, 1M x 768 x 1024
+    // queries): items of 4 / 3 / 2 query blocks take 0.258 / 0.296 / 0.277 ms — with the earlier 0.1 the model
+    // preferred 2 blocks x 37 row slices over 4 x 74 by 0.3 % where 4 x 74 is 7 % faster.
     for (uint32_t qb = qb_min; qb <= qb_max; ++qb) {
         const uint32_t qsl = (nqb + qb - 1) / qb;
         const uint32_t rmax = std::max<uint32_t>(1, std::min<uint32_t>(ngroups, std::max<uint32_t>(1, 8 * sms / qsl)));
         for (uint32_t r = 1; r <= rmax; ++r) {
             const uint64_t items = (uint64_t)qsl * r;
             const uint64_t waves = (items + sms - 1) / sms;
-            const double cost = (double)waves * (std::ceil((double)ngroups / r) * (qb + 0.1) + 6.0 * qb);
+            const double cost = (double)waves * (std::ceil((double)ngroups / r) * (qb + 0.45) + 6.0 * qb);
             if (cost < best_cost - 1e-9) {
                 best_cost = cost;
                 best = TcSplit{qsl, r, (uint32_t)std::min<uint64_t>(items, sms), qb};
