@@ -347,8 +347,14 @@ mod quantizer_shim {
                 let st = unsafe { gvdb_quantize(ix.h, flat.as_ptr(), vectors.len() as u64, codes.as_mut_ptr()) };
                 if st != 0 { Err(err(st, dim, dim)) } else { Ok(()) }
             })?;
-            // BinaryVector::from_bytes(bytes, dimension)  (:59-62)
-            Ok(codes.chunks(nb).map(|c| BinaryVector::from_bytes(c.to_vec(), dim)).collect())
+            // BinaryVector::from_bytes(bytes, dimension)  (:59-62) makes a BitVec of 8 * bytes bits, while the
+            // reference's quantize pushes exactly `dimension` bits (:97-101) and its own test asserts
+            // `data.len() == 5` for a 5-d vector (:369): the pad bits (zero) are cut off again
+            Ok(codes.chunks(nb).map(|c| {
+                let mut v = BinaryVector::from_bytes(c.to_vec(), dim);
+                v.data.truncate(dim);
+                v
+            }).collect())
         }
 
         /// :130-141 — popcount(a XOR b) over the code bytes as f32; InvalidVectorDimension if the dimensions differ
