@@ -1,0 +1,100 @@
+"""Property tests (hypothesis) of the C++ oracle against the independent Python restatement in
+tests/test_oracle_independent.py and against numpy, over inputs a seeded generator does not reach:
+arbitrary f32 bit patterns (NaN, +-inf, +-0, subnormals) for the quantizer, arbitrary thresholds,
+dimensions that are not multiples of 8, heavy ties.  CPU only; the oracle is the checker here."""
+import numpy as np
+from hypothesis import given, settings, strategies as st
+from hypothesis.extra import numpy as hnp
+
+from oracle import oracle
+from test_oracle_independent import F, _bits, py_cosine, py_flat, py_hamming, py_quantize, py_two_stage
+
+# the same examples on every run (the driver's CPU pass must not depend on a random seed), no example database on disk
+settings.register_profile("gvdb", derandomize=True, deadline=None, database=None)
+settings.load_profile("gvdb")
+
+ANY_F32 = st.floats(width=32, allow_nan=True, allow_infinity=True)
+FINITE = st.floats(min_value=-1e6, max_value=1e6, width=32, allow_nan=False)     # sums of 64 squares stay finite in f32
+
+
+@settings(max_examples=150, deadline=None)
+@given(x=st.lists(ANY_F32, min_size=1, max_size=70), thr=st.floats(width=32, allow_nan=False, allow_infinity=False))
+def test_quantize_any_bit_pattern(x, thr):
+    """bit = value > threshold, strictly (src/quantization.rs:99): NaN, the threshold itself and -0.0 at
+    threshold 0 give 0; Msb0 bytes; pad bits zero — also against numpy.packbits."""
+    xs = np.asarray(x, dtype=np.float32)
+    code = oracle.quantize(xs, thr)
+    assert bytes(code) == py_quantize(xs, F(thr))
+    with np.errstate(invalid="ignore"):
+        assert np.array_equal(code, np.packbits(xs > F(thr), bitorder="big"))
+
+
+@settings(max_examples=100, deadline=None)
+@given(data=st.data(), nbytes=st.integers(1, 40))
+def test_hamming_is_the_number_of_differing_bits(data, nbytes):
+    a = np.frombuffer(data.draw(st.binary(min_size=nbytes, max_size=nbytes)), dtype=np.uint8)
+    b = np.frombuffer(data.draw(st.binary(min_size=nbytes, max_size=nbytes)), dtype=np.uint8)
+    d = oracle.hamming(a, b)
+    assert d == py_hamming(bytes(a), bytes(b)) == int(np.unpackbits(a ^ b).sum())
+    assert oracle.hamming(b, a) == d and oracle.hamming(a, a) == 0
+    dim = nbytes * 8
+    assert _bits(oracle.similarity(a, b, dim)) == _bits(F(F(1.0) - F(F(d) / F(dim))))       # :145-147
+
+
+@settings(max_examples=150, deadline=None)
+@given(data=st.data(), dim=st.integers(1, 64))
+def test_cosine_is_three_sequential_f32_folds(data, dim):
+    q = np.asarray(data.draw(st.lists(FINITE, min_size=dim, max_size=dim)), dtype=np.float32)
+    c = np.asarray(data.draw(st.lists(FINITE, min_size=dim, max_size=dim)), dtype=np.float32)
+    with np.errstate(all="ignore"):
+        want = py_cosine(q, c)
+    assert _bits(oracle.cosine_similarity(q, c)) == _bits(want)
+    # the flat index's distance: 1 - cos, +inf when a norm is zero (src/index.rs:686-700)
+    with np.errstate(all="ignore"):
+        flat = py_flat(q, c[None, :], np.ones(1, dtype=bool), 1)[0][1]
+    assert _bits(oracle.cosine_distance(q, c)) == _bits(flat)
+
+
+@settings(max_examples=200, deadline=None)
+@given(n=st.integers(0, 1 << 40), ratio=st.floats(min_value=-1.0, max_value=3.0, width=32, allow_nan=False))
+def test_rescore_count_is_the_f32_product_truncated(n, ratio):
+    """(candidates.len() as f32 * rescore_ratio) as usize, then .min(len) — src/quantization.rs:178-179;
+    Rust's float -> usize cast saturates (negative -> 0)."""
+    p = F(F(n) * F(ratio))
+    want = min(int(p) if p > 0 else 0, n)
+    assert oracle.rescore_count(n, float(F(ratio))) == want
+
+
+@settings(max_examples=40, deadline=None)
+@given(data=st.data(), n=st.integers(1, 40), dim=st.integers(1, 20),
+       ratio=st.sampled_from([0.0, 0.1, 0.34, 0.5, 1.0, 1.5]),
+       thr=st.sampled_from([0.0, -0.0, 0.5, -1.0]))
+def test_two_stage_on_tie_heavy_rows(data, n, dim, ratio, thr):
+    """Values from a three-letter alphabet: many equal Hamming distances and equal cosines — both stable sorts
+    (src/quantization.rs:175,190) decide the order."""
+    vals = st.sampled_from([-1.0, 0.0, 2.0])
+    rows = np.asarray(data.draw(hnp.arrays(np.float32, (n, dim), elements=vals)))
+    q = np.asarray(data.draw(hnp.arrays(np.float32, (dim,), elements=vals)))
+    with np.errstate(all="ignore"):
+        want = py_two_stage(q, rows, ratio, thr)
+    r = len(want)
+    assert r == oracle.rescore_count(n, ratio)
+    if r == 0:
+        return
+    ids, sc = oracle.multi_stage_search(q, rows, r, thr)
+    assert [int(i) for i in ids] == [i for i, _ in want]
+    assert np.array_equal(_bits(sc), _bits([s for _, s in want]))
+
+
+@settings(max_examples=40, deadline=None)
+@given(data=st.data(), n=st.integers(1, 30), dim=st.integers(1, 12), k=st.integers(1, 35))
+def test_flat_search_with_tombstones_and_zero_rows(data, n, dim, k):
+    vals = st.sampled_from([-2.0, 0.0, 0.0, 1.0, 3.0])
+    rows = np.asarray(data.draw(hnp.arrays(np.float32, (n, dim), elements=vals)))
+    q = np.asarray(data.draw(hnp.arrays(np.float32, (dim,), elements=vals)))
+    live = np.asarray(data.draw(hnp.arrays(np.bool_, (n,))))
+    with np.errstate(all="ignore"):
+        want = py_flat(q, rows, live, k)
+    ids, d = oracle.flat_search(q, rows, k, live=live)
+    assert [int(i) for i in ids] == [i for i, _ in want]          # min(k, live rows) answers, (distance, row) ascending
+    assert np.array_equal(_bits(d), _bits([x for _, x in want]))
