@@ -98,3 +98,99 @@ def test_flat_search_with_tombstones_and_zero_rows(data, n, dim, k):
     ids, d = oracle.flat_search(q, rows, k, live=live)
     assert [int(i) for i in ids] == [i for i, _ in want]          # min(k, live rows) answers, (distance, row) ascending
     assert np.array_equal(_bits(d), _bits([x for _, x in want]))
+
+
+# ---- the hybrid side: RRF, weighted fusions, BM25, and the cross-shard merge ----------------------------------------
+from test_oracle_independent import py_bm25, py_rrf, py_weighted      # noqa: E402
+
+DOC_LIST = st.lists(st.integers(0, 25), max_size=14)        # duplicates allowed: an id may sit twice in one list
+
+
+@settings(max_examples=120, deadline=None)
+@given(dense=DOC_LIST, sparse=DOC_LIST, text=DOC_LIST, k=st.sampled_from([60.0, 1.0, 0.0, 1000.0]))
+def test_rrf_any_lists(dense, sparse, text, k):
+    """src/hybrid.rs:422-488: the dense list INSERTS (a repeated id keeps its last rank), the other lists add;
+    ties in first-appearance order (the oracle's statement of the reference's unspecified HashMap order)."""
+    want = py_rrf(dense, sparse, text, k)
+    ids, sc = oracle.rrf_fusion(dense, sparse, text, k)
+    assert [int(i) for i in ids] == [i for i, _ in want]
+    assert np.array_equal(_bits(sc), _bits([x for _, x in want]))
+
+
+SCORED = st.lists(st.tuples(st.integers(0, 25), st.sampled_from([-2.0, -0.25, 0.0, 0.5, 0.5, 1.0, 3.75])), max_size=12)
+
+
+@settings(max_examples=120, deadline=None)
+@given(dense=SCORED, sparse=SCORED, text=SCORED, normalize=st.booleans(),
+       weights=st.sampled_from([(0.7, 0.2, 0.1), (1.0, 0.0, 0.0), (0.5, 0.5, 0.0), (0.2, 0.3, 0.5)]))
+def test_weighted_fusion_any_lists(dense, sparse, text, normalize, weights):
+    """linear_fusion / normalized_fusion (src/hybrid.rs:491-616): constant lists normalise to 1.0, empty lists vanish."""
+    with np.errstate(all="ignore"):
+        want = py_weighted(dense, sparse, text, weights, normalize)
+    ids, sc = oracle.weighted_fusion([d for d, _ in dense], [s for _, s in dense], [d for d, _ in sparse],
+                                     [s for _, s in sparse], [d for d, _ in text], [s for _, s in text], weights, normalize)
+    assert [int(i) for i in ids] == [i for i, _ in want]
+    assert np.array_equal(_bits(sc), _bits([x for _, x in want]))
+
+
+@settings(max_examples=60, deadline=None)
+@given(data=st.data(), n_docs=st.integers(1, 30), vocab=st.integers(1, 8), limit=st.integers(1, 40))
+def test_bm25_any_small_index(data, n_docs, vocab, limit):
+    """src/sparse.rs:153-222 incl. negative idf (df > N/2), terms outside the vocabulary, repeated query terms and the
+    average length taken per POSTING (:96-104)."""
+    eighths = st.integers(1, 8).map(lambda v: v / 8)
+    doc_len = np.asarray(data.draw(st.lists(eighths, min_size=n_docs, max_size=n_docs)), dtype=np.float32)
+    postings, post_off, post_doc, post_tf = {}, [0], [], []
+    for t in range(vocab):
+        docs = sorted(data.draw(st.sets(st.integers(0, n_docs - 1), max_size=n_docs)))
+        tfs = data.draw(st.lists(eighths, min_size=len(docs), max_size=len(docs)))
+        postings[t] = list(zip(docs, tfs))
+        post_doc += docs
+        post_tf += tfs
+        post_off.append(len(post_doc))
+    if not post_doc:
+        return
+    total = F(0)
+    for t in range(vocab):
+        for doc, _ in postings[t]:
+            total = F(total + doc_len[doc])
+    avg = F(total / F(n_docs))
+    assert _bits([avg])[0] == _bits([oracle.bm25_avg_len(post_off, post_doc, doc_len)])[0]
+    qt = data.draw(st.lists(st.integers(0, vocab + 1), min_size=1, max_size=5))
+    qv = np.asarray(data.draw(st.lists(st.integers(1, 4).map(lambda v: v / 4), min_size=len(qt), max_size=len(qt))),
+                    dtype=np.float32)
+    with np.errstate(all="ignore"):
+        want = py_bm25(qt, qv, postings, doc_len, n_docs, avg, limit)
+    docs, sc = oracle.bm25_search(qt, qv, post_off, post_doc, post_tf, doc_len, limit)
+    assert [int(d) for d in docs] == [d for d, _ in want]
+    assert np.array_equal(_bits(sc), _bits([s for _, s in want]))
+
+
+@settings(max_examples=40, deadline=None)
+@given(data=st.data(), n=st.integers(2, 48), dim=st.integers(1, 16), shards=st.integers(1, 5),
+       R=st.integers(1, 12), k=st.integers(1, 12))
+def test_shard_merge_equals_the_single_index(data, n, dim, shards, R, k):
+    """per-shard top R by (hamming, row) + cosine, merged by the global stage-1 cut and the final order
+    (cos desc, ham asc, row asc), equals multi_stage_search over the whole corpus — for any contiguous split."""
+    vals = st.sampled_from([-1.0, 0.0, 2.0, 2.0])
+    rows = np.asarray(data.draw(hnp.arrays(np.float32, (n, dim), elements=vals)))
+    q = np.asarray(data.draw(hnp.arrays(np.float32, (dim,), elements=vals)))
+    R = min(R, n)
+    ids, sc = oracle.multi_stage_search(q, rows, R)
+    want_ids, want_sc = np.asarray(ids)[:k], np.asarray(sc)[:k]
+    qc = oracle.quantize(q)
+    per = (n + shards - 1) // shards
+    ham, idx, score = [], [], []
+    for s_ in range(shards):
+        lo, hi = min(n, s_ * per), min(n, (s_ + 1) * per)
+        if lo == hi:
+            continue
+        li, ls = oracle.multi_stage_search(q, rows[lo:hi], min(R, hi - lo))
+        for i, c in zip(np.asarray(li), np.asarray(ls)):
+            g = lo + int(i)
+            ham.append(oracle.hamming(qc, oracle.quantize(rows[g])))
+            idx.append(g)
+            score.append(c)
+    mi, ms = oracle.shard_merge(ham, idx, score, R, k)
+    assert [int(i) for i in mi] == [int(i) for i in want_ids]
+    assert np.array_equal(_bits(ms), _bits(want_sc))
