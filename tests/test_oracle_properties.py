@@ -2,12 +2,17 @@
 tests/test_oracle_independent.py and against numpy, over inputs a seeded generator does not reach:
 arbitrary f32 bit patterns (NaN, +-inf, +-0, subnormals) for the quantizer, arbitrary thresholds,
 dimensions that are not multiples of 8, heavy ties.  CPU only; the oracle is the checker here."""
+import os
+import sys
+
 import numpy as np
 from hypothesis import given, settings, strategies as st
 from hypothesis.extra import numpy as hnp
 
-from oracle import oracle
-from test_oracle_independent import F, _bits, py_cosine, py_flat, py_hamming, py_quantize, py_two_stage
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))       # the sibling module, whatever the import mode
+
+from oracle import oracle                                            # noqa: E402
+from test_oracle_independent import F, _bits, py_cosine, py_flat, py_hamming, py_quantize, py_two_stage   # noqa: E402
 
 # the same examples on every run (the driver's CPU pass must not depend on a random seed), no example database on disk
 settings.register_profile("gvdb", derandomize=True, deadline=None, database=None)
