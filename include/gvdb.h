@@ -232,7 +232,10 @@ GVDB_API gvdb_status gvdb_search_shard_sliced_device(gvdb_index* h, void* stream
  * single pass is enqueued on `stream` and the call returns, so the exchange and the merge can be queued behind it
  * without the GPU idling on the host.  gvdb_search_shard_verify, called once the step's other work is enqueued,
  * waits for the stream; *rerun_out = 1 means the device refused the pass's thresholds (rare) and the step must be
- * repeated with gvdb_search_shard_sliced_device.  One enqueue in flight per index.
+ * repeated with gvdb_search_shard_sliced_device.  gvdb_search_shard_verify reads ONE pinned pair of words per index:
+ * a caller that goes through it keeps one enqueue in flight per index.  Several enqueues on the same stream may be
+ * in flight when each gets its own verdict_out_dev and the caller reads those itself (the multi-tile batches of
+ * grape-vector-db_b200/dist.py: every query tile's step is enqueued before one host wait).
  * verdict_out_dev (optional, DEVICE, 2 x u32): the same verdict written on the stream (any word nonzero = repeat),
  * so that the ranks of a sharded deployment can pass their verdicts round with the answers (one collective, one
  * host wait per step) instead of agreeing through the host. */
