@@ -37,3 +37,16 @@ def test_reference_arm_other_ranks_exit_quietly():
     env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
     assert _run("--gpus", "2", "--rows", "20000", "--batch", "64", "--cpu-sample", "16", "--steps", "1", "--warmup", "0",
                 env=env) == []
+
+
+def test_own_arm_fails_loudly_without_a_gpu():
+    """No CPU fallback: without a CUDA device our arm must stop with an error and print no result line."""
+    import pytest
+    torch = pytest.importorskip("torch")
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--rows", "2000", "--batch", "64", "--steps", "1",
+                          "--warmup", "0", "--north-star", "0", "--stream-rows", "0"],
+                         capture_output=True, text=True, timeout=300, cwd=ROOT)
+    assert out.returncode != 0
+    assert not [l for l in out.stdout.splitlines() if l.startswith("{")]
